@@ -1,0 +1,942 @@
+// badba.cu -- C ABI (include/badba.h) and host orchestration of libbadba_b200.
+//
+// Host-side structure mirrors the reference's DirectBA (direct_ba.{h,cc}, direct_ba_alternating.cc) but the
+// schedule is B200-first: per outer BA iteration the device runs
+//     1 launch   activation + normals      (reference: 1 + K_active + 1 + K + 1 launches)
+//     1 launch   position + descriptors    (reference: 1 + K + 1 launches)
+//     <=30 x 2   pose accumulate + solve for ALL keyframes at once (reference: K x n_GN x {2 clears, kernel,
+//                2 D2H copies, stream sync}, kernel_opt_pose.cc:67-96)
+// and the host synchronises ONCE per outer iteration to read back the poses.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/badba.h"
+#include "host_math.hpp"
+#include "kernels.cuh"
+
+namespace {
+
+using bba::KfDevice;
+using bba::Pose;
+
+struct Frustum {   // libvis/src/libvis/camera_frustum.h:43-250
+  float p[8][3];
+  float bmin[3], bmax[3];
+  float axes[6][3];
+  float plane_n[6][3];
+  float plane_d[6];
+};
+
+inline void Sub(const float a[3], const float b[3], float o[3]) { o[0] = a[0] - b[0]; o[1] = a[1] - b[1]; o[2] = a[2] - b[2]; }
+inline void CrossP(const float a[3], const float b[3], float o[3]) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+inline float DotP(const float a[3], const float b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+void MakeFrustum(Frustum* f, const float K[4], int width, int height, float min_depth, float max_depth, const Pose& global_T_cam) {
+  float M[12];
+  bba::ToMatrix3x4(global_T_cam, M);
+  for (int i = 0; i < 3; ++i) {
+    f->bmin[i] = std::numeric_limits<float>::infinity();
+    f->bmax[i] = -std::numeric_limits<float>::infinity();
+  }
+  // corner order of camera_frustum.h:155-177: top-left, top-right, bottom-left, bottom-right; min then max depth
+  const float cx[4] = {0.f, static_cast<float>(width), 0.f, static_cast<float>(width)};
+  const float cy[4] = {0.f, 0.f, static_cast<float>(height), static_cast<float>(height)};
+  for (int c = 0; c < 4; ++c) {
+    const float dx = (cx[c] - K[2]) / K[0], dy = (cy[c] - K[3]) / K[1];   // UnprojectFromPixelCornerConv
+    for (int d = 0; d < 2; ++d) {
+      const float depth = d ? max_depth : min_depth;
+      const float v[3] = {depth * dx, depth * dy, depth};
+      float* o = f->p[2 * c + d];
+      for (int r = 0; r < 3; ++r) {
+        o[r] = M[r * 4] * v[0] + M[r * 4 + 1] * v[1] + M[r * 4 + 2] * v[2] + M[r * 4 + 3];
+        f->bmin[r] = std::fmin(f->bmin[r], o[r]);
+        f->bmax[r] = std::fmax(f->bmax[r], o[r]);
+      }
+    }
+  }
+  // camera_frustum.h:180-218
+  Sub(f->p[7], f->p[6], f->axes[0]);
+  Sub(f->p[3], f->p[2], f->axes[1]);
+  Sub(f->p[5], f->p[4], f->axes[2]);
+  Sub(f->p[1], f->p[0], f->axes[3]);
+  Sub(f->p[2], f->p[6], f->axes[4]);
+  Sub(f->p[0], f->p[2], f->axes[5]);
+  float fwd[3];
+  CrossP(f->axes[5], f->axes[4], fwd);
+  for (int i = 0; i < 3; ++i) {
+    f->plane_n[0][i] = fwd[i];
+    f->plane_n[1][i] = -fwd[i];
+  }
+  f->plane_d[0] = -DotP(fwd, f->p[1]);
+  f->plane_d[1] = DotP(fwd, f->p[0]);
+  CrossP(f->axes[0], f->axes[4], f->plane_n[2]); f->plane_d[2] = -DotP(f->plane_n[2], f->p[6]);
+  CrossP(f->axes[1], f->axes[5], f->plane_n[3]); f->plane_d[3] = -DotP(f->plane_n[3], f->p[2]);
+  CrossP(f->axes[4], f->axes[2], f->plane_n[4]); f->plane_d[4] = -DotP(f->plane_n[4], f->p[4]);
+  CrossP(f->axes[5], f->axes[0], f->plane_n[5]); f->plane_d[5] = -DotP(f->plane_n[5], f->p[6]);
+}
+
+bool AllOutside(const Frustum& planes_of, const Frustum& points_of) {
+  for (int pl = 0; pl < 6; ++pl) {
+    int v = 0;
+    for (; v < 8; ++v)
+      if (DotP(planes_of.plane_n[pl], points_of.p[v]) + planes_of.plane_d[pl] < 0) break;
+    if (v == 8) return true;
+  }
+  return false;
+}
+
+bool FrustaIntersect(const Frustum& a, const Frustum& b) {   // camera_frustum.h:73-143
+  for (int i = 0; i < 3; ++i)
+    if (std::fmax(a.bmin[i], b.bmin[i]) > std::fmin(a.bmax[i], b.bmax[i])) return false;
+  if (AllOutside(a, b) || AllOutside(b, a)) return false;
+  // Separating-axis part.  The reference crosses two edge directions of the SAME frustum (camera_frustum.h:122
+  // uses axes_[this_edge] and axes_[other_edge], both members of `this`); kept as is for parity.
+  for (int e1 = 0; e1 < 6; ++e1)
+    for (int e2 = 0; e2 < 6; ++e2) {
+      float dir[3];
+      CrossP(a.axes[e1], a.axes[e2], dir);
+      if (DotP(dir, dir) < 1e-5f) continue;
+      float amin = INFINITY, amax = -INFINITY, bmin = INFINITY, bmax = -INFINITY;
+      for (int p = 0; p < 8; ++p) {
+        const float va = DotP(dir, a.p[p]), vb = DotP(dir, b.p[p]);
+        amin = std::fmin(amin, va); amax = std::fmax(amax, va);
+        bmin = std::fmin(bmin, vb); bmax = std::fmax(bmax, vb);
+      }
+      if (amax <= bmin || amin >= bmax) return false;
+    }
+  return true;
+}
+
+struct Keyframe {
+  const uint16_t* depth = nullptr;
+  const uint16_t* normals = nullptr;
+  const uint16_t* radius = nullptr;
+  size_t depth_pitch = 0, normals_pitch = 0, radius_pitch = 0;
+  uint8_t* luma = nullptr;   // library-owned u8 plane (the .w channel of the caller's uchar4 colour buffer)
+  size_t luma_pitch = 0;
+  cudaTextureObject_t tex = 0;
+  void* owned[3] = {nullptr, nullptr, nullptr};   // depth / normals / radius copies made by bba_add_keyframe_host
+  Pose pose;                 // global_T_frame
+  int activation = BBA_KF_ACTIVE;
+  float min_depth = 0.f, max_depth = 0.f;
+  Frustum frustum;
+  std::vector<int> covis;
+};
+
+}  // namespace
+
+struct bba_context {
+  bba_config cfg;
+  float depth_K[4], color_K[4];
+  float depth_a = 0.f;
+  int cf_w = 0, cf_h = 0;
+  int sm_count = 148;
+  std::string error;
+
+  float* surfels = nullptr;
+  size_t surfel_pitch_bytes = 0;
+  uint32_t surfels_size = 0;
+  uint8_t* active = nullptr;
+  float* owned_surfels = nullptr;
+  size_t owned_surfel_pitch = 0;
+  uint8_t* owned_active = nullptr;
+
+  float* d_cfactor = nullptr;
+  std::vector<Keyframe> keyframes;
+
+  // device state sized for cfg.max_keyframes
+  KfDevice* d_kfs = nullptr;
+  float* d_pose_est = nullptr;
+  double* d_acc = nullptr;
+  unsigned long long* d_stage_counts = nullptr;
+  int* d_work[2] = {nullptr, nullptr};
+  int* d_count = nullptr;   // 2 ints
+  int* d_iterations = nullptr;
+  int* d_converged = nullptr;
+  double* d_first_stats = nullptr;
+  int* d_geo_list = nullptr;
+
+  // pinned staging
+  KfDevice* h_kfs = nullptr;
+  float* h_pose_est = nullptr;
+  int* h_work = nullptr;    // max_kf + 2
+  int* h_geo_list = nullptr;
+  int* h_iterations = nullptr;
+  int* h_converged = nullptr;
+  double* h_first_stats = nullptr;
+  double* h_acc = nullptr;        // one record (32) + 2 stage counts, for bba_accumulate_pose_coeffs
+  cudaEvent_t staging_event = nullptr;
+  bool staging_pending = false;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+
+  bba_allgather_fn allgather = nullptr;
+  void* allgather_user = nullptr;
+
+  uint64_t launches = 0;
+  int ba_iteration_count = 0;
+};
+
+namespace {
+
+bba_status Fail(bba_handle h, bba_status s, const std::string& msg) {
+  if (h) h->error = msg;
+  return s;
+}
+
+#define BBA_CUDA(h, expr)                                                                                  \
+  do {                                                                                                      \
+    cudaError_t e__ = (expr);                                                                               \
+    if (e__ != cudaSuccess)                                                                                 \
+      return Fail(h, BBA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));                    \
+  } while (0)
+
+Pose PoseFromArray(const float p[7]) {
+  Pose r;
+  r.q[0] = p[0]; r.q[1] = p[1]; r.q[2] = p[2]; r.q[3] = p[3];
+  r.t[0] = p[4]; r.t[1] = p[5]; r.t[2] = p[6];
+  return r;
+}
+void PoseToArray(const Pose& r, float p[7]) {
+  p[0] = r.q[0]; p[1] = r.q[1]; p[2] = r.q[2]; p[3] = r.q[3];
+  p[4] = r.t[0]; p[5] = r.t[1]; p[6] = r.t[2];
+}
+
+bba::CameraParams MakeCamera(bba_handle h) {
+  bba::CameraParams c;
+  c.w = h->cfg.depth_width; c.h = h->cfg.depth_height; c.cw = h->cfg.color_width; c.ch = h->cfg.color_height;
+  // surfel_projection.h:42-67
+  c.fx = h->depth_K[0]; c.fy = h->depth_K[1]; c.cx = h->depth_K[2]; c.cy = h->depth_K[3];
+  c.fx_inv = 1.0f / c.fx;
+  c.fy_inv = 1.0f / c.fy;
+  c.cx_inv = -(c.cx - 0.5f) * c.fx_inv;
+  c.cy_inv = -(c.cy - 0.5f) * c.fy_inv;
+  c.cfx = h->color_K[0]; c.cfy = h->color_K[1]; c.ccx = h->color_K[2]; c.ccy = h->color_K[3];
+  // surfel_projection.h:105-124
+  c.d2c_fx = c.cfx / c.fx;
+  c.d2c_cx = -1 * c.cfx * c.cx / c.fx + c.ccx;
+  c.d2c_fy = c.cfy / c.fy;
+  c.d2c_cy = -1 * c.cfy * c.cy / c.fy + c.ccy;
+  c.a = h->depth_a;
+  c.raw_to_float = h->cfg.raw_to_float_depth;
+  c.baseline_fx = h->cfg.baseline_fx;
+  c.cell = h->cfg.sparse_surfel_cell_size;
+  c.cf_w = h->cf_w;
+  c.cfactor = h->d_cfactor;
+  c.use_depth = h->cfg.use_depth_residuals;
+  c.use_desc = h->cfg.use_descriptor_residuals;
+  return c;
+}
+
+bba_status WaitStaging(bba_handle h) {
+  if (h->staging_pending) {
+    BBA_CUDA(h, cudaEventSynchronize(h->staging_event));
+    h->staging_pending = false;
+  }
+  return BBA_OK;
+}
+bba_status MarkStaging(bba_handle h, cudaStream_t s) {
+  BBA_CUDA(h, cudaEventRecord(h->staging_event, s));
+  h->staging_pending = true;
+  return BBA_OK;
+}
+
+void FillKfDevice(const Keyframe& kf, const Pose& global_T_frame, KfDevice* d) {
+  bba::ToMatrix3x4(bba::Inverse(global_T_frame), d->T);
+  d->depth = kf.depth;
+  d->normals = kf.normals;
+  d->tex = kf.tex;
+  d->depth_pitch = static_cast<uint32_t>(kf.depth_pitch);
+  d->normals_pitch = static_cast<uint32_t>(kf.normals_pitch);
+  d->activation = kf.activation;
+  d->pad = 0;
+}
+
+// Uploads every keyframe's parameters (pose, pointers, activation).  K x 96 bytes.
+bba_status UploadKeyframes(bba_handle h, cudaStream_t s) {
+  const int K = static_cast<int>(h->keyframes.size());
+  if (K == 0) return BBA_OK;
+  if (bba_status st = WaitStaging(h)) return st;
+  for (int k = 0; k < K; ++k) FillKfDevice(h->keyframes[k], h->keyframes[k].pose, h->h_kfs + k);
+  BBA_CUDA(h, cudaMemcpyAsync(h->d_kfs, h->h_kfs, sizeof(KfDevice) * K, cudaMemcpyHostToDevice, s));
+  return MarkStaging(h, s);
+}
+
+bba_status CheckSurfels(bba_handle h) {
+  if (!h->surfels || !h->active) return Fail(h, BBA_ERR_STATE, "surfel buffer / active flags not set");
+  return BBA_OK;
+}
+
+// Runs the Gauss-Newton loop of EstimateFramePose for the keyframes in `ids`, all at once, starting from
+// `init` poses.  On return (stream synchronised) h_pose_est / h_iterations / h_converged / h_first_stats hold the results.
+bba_status RunPoseStep(bba_handle h, const std::vector<int>& ids, const std::vector<Pose>& init, int max_iterations, cudaStream_t s) {
+  const int K = static_cast<int>(h->keyframes.size());
+  const int n = static_cast<int>(ids.size());
+  if (n == 0) return BBA_OK;
+  if (bba_status st = WaitStaging(h)) return st;
+  for (int k = 0; k < K; ++k) {
+    FillKfDevice(h->keyframes[k], h->keyframes[k].pose, h->h_kfs + k);
+    PoseToArray(h->keyframes[k].pose, h->h_pose_est + 7 * k);
+  }
+  for (int i = 0; i < n; ++i) {
+    FillKfDevice(h->keyframes[ids[i]], init[i], h->h_kfs + ids[i]);
+    PoseToArray(init[i], h->h_pose_est + 7 * ids[i]);
+    h->h_work[i] = ids[i];
+  }
+  h->h_work[h->cfg.max_keyframes] = n;
+  h->h_work[h->cfg.max_keyframes + 1] = 0;
+  BBA_CUDA(h, cudaMemcpyAsync(h->d_kfs, h->h_kfs, sizeof(KfDevice) * K, cudaMemcpyHostToDevice, s));
+  BBA_CUDA(h, cudaMemcpyAsync(h->d_pose_est, h->h_pose_est, sizeof(float) * 7 * K, cudaMemcpyHostToDevice, s));
+  BBA_CUDA(h, cudaMemcpyAsync(h->d_work[0], h->h_work, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+  BBA_CUDA(h, cudaMemcpyAsync(h->d_count, h->h_work + h->cfg.max_keyframes, sizeof(int) * 2, cudaMemcpyHostToDevice, s));
+  BBA_CUDA(h, cudaMemsetAsync(h->d_acc, 0, sizeof(double) * bba::kPoseAccSize * K, s));
+  BBA_CUDA(h, cudaMemsetAsync(h->d_stage_counts, 0, sizeof(unsigned long long) * 2 * K, s));
+  BBA_CUDA(h, cudaMemsetAsync(h->d_iterations, 0, sizeof(int) * K, s));
+  BBA_CUDA(h, cudaMemsetAsync(h->d_converged, 0, sizeof(int) * K, s));
+  if (bba_status st = MarkStaging(h, s)) return st;
+
+  bba::PoseAccumulateArgs acc;
+  acc.cam = MakeCamera(h);
+  acc.surfels = h->surfels;
+  acc.pitch = static_cast<uint32_t>(h->surfel_pitch_bytes / sizeof(float));
+  acc.n = h->surfels_size;
+  acc.kfs = h->d_kfs;
+  acc.acc = h->d_acc;
+  acc.stage_counts = h->d_stage_counts;
+  bba::PoseSolveArgs sol;
+  sol.kfs = h->d_kfs;
+  sol.pose_est = h->d_pose_est;
+  sol.acc = h->d_acc;
+  sol.stage_counts = h->d_stage_counts;
+  sol.iterations = h->d_iterations;
+  sol.converged = h->d_converged;
+  sol.first_stats = h->d_first_stats;
+  sol.max_iterations = max_iterations;
+  for (int it = 0; it < max_iterations; ++it) {
+    const int cur = it & 1;
+    acc.work_list = h->d_work[cur];
+    acc.work_count = h->d_count + cur;
+    if (h->surfels_size > 0) {
+      bba::LaunchPoseAccumulate(acc, h->sm_count, s);
+      ++h->launches;
+    }
+    sol.work_in = h->d_work[cur];
+    sol.count_in = h->d_count + cur;
+    sol.work_out = h->d_work[cur ^ 1];
+    sol.count_out = h->d_count + (cur ^ 1);
+    sol.iteration = it;
+    bba::LaunchPoseSolve(sol, s);
+    ++h->launches;
+  }
+  BBA_CUDA(h, cudaGetLastError());
+  BBA_CUDA(h, cudaMemcpyAsync(h->h_pose_est, h->d_pose_est, sizeof(float) * 7 * K, cudaMemcpyDeviceToHost, s));
+  BBA_CUDA(h, cudaMemcpyAsync(h->h_iterations, h->d_iterations, sizeof(int) * K, cudaMemcpyDeviceToHost, s));
+  BBA_CUDA(h, cudaMemcpyAsync(h->h_converged, h->d_converged, sizeof(int) * K, cudaMemcpyDeviceToHost, s));
+  BBA_CUDA(h, cudaMemcpyAsync(h->h_first_stats, h->d_first_stats, sizeof(double) * 8 * K, cudaMemcpyDeviceToHost, s));
+  BBA_CUDA(h, cudaStreamSynchronize(s));
+  h->staging_pending = false;
+  return BBA_OK;
+}
+
+// direct_ba.cc:549-564
+void DetermineCovisibleActiveKeyframes(bba_handle h) {
+  for (Keyframe& kf : h->keyframes) {
+    if (kf.activation != BBA_KF_ACTIVE) continue;
+    for (int o : kf.covis) {
+      Keyframe& other = h->keyframes[o];
+      if (other.activation == BBA_KF_INACTIVE) other.activation = BBA_KF_COVISIBLE_ACTIVE;
+    }
+  }
+}
+
+bba_status BuildGeometryArgs(bba_handle h, bba::GeometryArgs* g, cudaStream_t s) {
+  const int K = static_cast<int>(h->keyframes.size());
+  int cnt = 0;
+  for (int k = 0; k < K; ++k)
+    if (h->keyframes[k].activation != BBA_KF_INACTIVE) h->h_geo_list[cnt++] = k;
+  if (cnt) BBA_CUDA(h, cudaMemcpyAsync(h->d_geo_list, h->h_geo_list, sizeof(int) * cnt, cudaMemcpyHostToDevice, s));
+  g->cam = MakeCamera(h);
+  g->surfels = h->surfels;
+  g->pitch = static_cast<uint32_t>(h->surfel_pitch_bytes / sizeof(float));
+  g->n = h->surfels_size;
+  g->begin = 0;
+  g->end = h->surfels_size;
+  g->active = h->active;
+  g->kfs = h->d_kfs;
+  g->kf_list = h->d_geo_list;
+  g->kf_count = cnt;
+  return BBA_OK;
+}
+
+bba_status AddKeyframeCommon(bba_handle h, Keyframe&& kf, const uint8_t* device_rgba, size_t color_pitch, const float pose[7],
+                             float min_depth, float max_depth, cudaStream_t s, int* out_id) {
+  if (static_cast<int>(h->keyframes.size()) >= h->cfg.max_keyframes) return Fail(h, BBA_ERR_STATE, "max_keyframes exceeded");
+  const int cw = h->cfg.color_width, ch = h->cfg.color_height;
+  BBA_CUDA(h, cudaMallocPitch(reinterpret_cast<void**>(&kf.luma), &kf.luma_pitch, cw, ch));
+  bba::LaunchExtractLuma(device_rgba, color_pitch, kf.luma, kf.luma_pitch, cw, ch, s);
+  ++h->launches;
+  BBA_CUDA(h, cudaGetLastError());
+  // Texture with the reference's sampling state (keyframe.cc:67-73) over the single luma channel.
+  cudaResourceDesc res;
+  std::memset(&res, 0, sizeof(res));
+  res.resType = cudaResourceTypePitch2D;
+  res.res.pitch2D.devPtr = kf.luma;
+  res.res.pitch2D.desc = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
+  res.res.pitch2D.width = cw;
+  res.res.pitch2D.height = ch;
+  res.res.pitch2D.pitchInBytes = kf.luma_pitch;
+  cudaTextureDesc tex;
+  std::memset(&tex, 0, sizeof(tex));
+  tex.addressMode[0] = cudaAddressModeClamp;
+  tex.addressMode[1] = cudaAddressModeClamp;
+  tex.filterMode = cudaFilterModeLinear;
+  tex.readMode = cudaReadModeNormalizedFloat;
+  tex.normalizedCoords = 0;
+  BBA_CUDA(h, cudaCreateTextureObject(&kf.tex, &res, &tex, nullptr));
+  kf.pose = PoseFromArray(pose);
+  kf.activation = BBA_KF_ACTIVE;   // keyframe.cc:75
+  kf.min_depth = min_depth;
+  kf.max_depth = max_depth;
+  MakeFrustum(&kf.frustum, h->depth_K, h->cfg.depth_width, h->cfg.depth_height, min_depth, max_depth, kf.pose);
+  const int id = static_cast<int>(h->keyframes.size());
+  // DetermineNewKeyframeCoVisibility, direct_ba.cc:231-249
+  for (int k = 0; k < id; ++k) {
+    Keyframe& other = h->keyframes[k];
+    Frustum other_frustum;
+    MakeFrustum(&other_frustum, h->depth_K, h->cfg.depth_width, h->cfg.depth_height, other.min_depth, other.max_depth, other.pose);
+    if (FrustaIntersect(kf.frustum, other_frustum)) {
+      kf.covis.push_back(k);
+      other.covis.push_back(id);
+      if (other.activation == BBA_KF_INACTIVE) other.activation = BBA_KF_COVISIBLE_ACTIVE;
+    }
+  }
+  h->keyframes.push_back(std::move(kf));
+  if (out_id) *out_id = id;
+  return BBA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bba_abi_version(void) { return BBA_ABI_VERSION; }
+
+const char* bba_last_error(bba_handle h) { return h ? h->error.c_str() : "null handle"; }
+
+bba_status bba_create(const bba_config* cfg, bba_handle* out) {
+  if (!cfg || !out) return BBA_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  if (cfg->depth_width <= 0 || cfg->depth_height <= 0 || cfg->color_width <= 0 || cfg->color_height <= 0 ||
+      cfg->sparse_surfel_cell_size <= 0 || cfg->max_keyframes <= 0 || cfg->world_size <= 0 || cfg->rank < 0 ||
+      cfg->rank >= cfg->world_size || (!cfg->use_depth_residuals && !cfg->use_descriptor_residuals))
+    return BBA_ERR_INVALID_ARGUMENT;
+  int device_count = 0;
+  if (cudaGetDeviceCount(&device_count) != cudaSuccess || device_count == 0) {
+    cudaGetLastError();
+    return BBA_ERR_NO_DEVICE;   // no CPU fallback exists, by design
+  }
+  bba_handle h = new bba_context();
+  h->cfg = *cfg;
+  std::memcpy(h->depth_K, cfg->depth_intrinsics, sizeof(h->depth_K));
+  std::memcpy(h->color_K, cfg->color_intrinsics, sizeof(h->color_K));
+  h->cf_w = (cfg->depth_width - 1) / cfg->sparse_surfel_cell_size + 1;    // direct_ba.cc:110-113
+  h->cf_h = (cfg->depth_height - 1) / cfg->sparse_surfel_cell_size + 1;
+  auto fail = [&](const char* what, cudaError_t e) {
+    std::fprintf(stderr, "bba_create: %s: %s\n", what, cudaGetErrorString(e));
+    bba_destroy(h);
+    return BBA_ERR_CUDA;
+  };
+#define CREATE_TRY(expr)                           \
+  do {                                             \
+    cudaError_t e__ = (expr);                      \
+    if (e__ != cudaSuccess) return fail(#expr, e__); \
+  } while (0)
+  CREATE_TRY(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CREATE_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+  h->sm_count = prop.multiProcessorCount;
+  const size_t K = static_cast<size_t>(cfg->max_keyframes);
+  CREATE_TRY(cudaMalloc(&h->d_cfactor, sizeof(float) * h->cf_w * h->cf_h));
+  CREATE_TRY(cudaMemset(h->d_cfactor, 0, sizeof(float) * h->cf_w * h->cf_h));
+  CREATE_TRY(cudaMalloc(&h->d_kfs, sizeof(KfDevice) * K));
+  CREATE_TRY(cudaMalloc(&h->d_pose_est, sizeof(float) * 7 * K));
+  CREATE_TRY(cudaMalloc(&h->d_acc, sizeof(double) * bba::kPoseAccSize * K));
+  CREATE_TRY(cudaMemset(h->d_acc, 0, sizeof(double) * bba::kPoseAccSize * K));
+  CREATE_TRY(cudaMalloc(&h->d_stage_counts, sizeof(unsigned long long) * 2 * K));
+  CREATE_TRY(cudaMemset(h->d_stage_counts, 0, sizeof(unsigned long long) * 2 * K));
+  CREATE_TRY(cudaMalloc(&h->d_work[0], sizeof(int) * K));
+  CREATE_TRY(cudaMalloc(&h->d_work[1], sizeof(int) * K));
+  CREATE_TRY(cudaMalloc(&h->d_count, sizeof(int) * 2));
+  CREATE_TRY(cudaMalloc(&h->d_iterations, sizeof(int) * K));
+  CREATE_TRY(cudaMalloc(&h->d_converged, sizeof(int) * K));
+  CREATE_TRY(cudaMalloc(&h->d_first_stats, sizeof(double) * 8 * K));
+  CREATE_TRY(cudaMemset(h->d_first_stats, 0, sizeof(double) * 8 * K));
+  CREATE_TRY(cudaMalloc(&h->d_geo_list, sizeof(int) * K));
+  CREATE_TRY(cudaMallocHost(&h->h_kfs, sizeof(KfDevice) * K));
+  CREATE_TRY(cudaMallocHost(&h->h_pose_est, sizeof(float) * 7 * K));
+  CREATE_TRY(cudaMallocHost(&h->h_work, sizeof(int) * (K + 2)));
+  CREATE_TRY(cudaMallocHost(&h->h_geo_list, sizeof(int) * K));
+  CREATE_TRY(cudaMallocHost(&h->h_iterations, sizeof(int) * K));
+  CREATE_TRY(cudaMallocHost(&h->h_converged, sizeof(int) * K));
+  CREATE_TRY(cudaMallocHost(&h->h_first_stats, sizeof(double) * 8 * K));
+  CREATE_TRY(cudaMallocHost(&h->h_acc, sizeof(double) * (bba::kPoseAccSize + 2)));
+  CREATE_TRY(cudaEventCreateWithFlags(&h->staging_event, cudaEventDisableTiming));
+  for (auto& e : h->ev) CREATE_TRY(cudaEventCreate(&e));
+#undef CREATE_TRY
+  h->keyframes.reserve(K);
+  *out = h;
+  return BBA_OK;
+}
+
+void bba_destroy(bba_handle h) {
+  if (!h) return;
+  cudaDeviceSynchronize();
+  for (Keyframe& kf : h->keyframes) {
+    if (kf.tex) cudaDestroyTextureObject(kf.tex);
+    cudaFree(kf.luma);
+    for (void* p : kf.owned) cudaFree(p);
+  }
+  cudaFree(h->owned_surfels);
+  cudaFree(h->owned_active);
+  cudaFree(h->d_cfactor);
+  cudaFree(h->d_kfs);
+  cudaFree(h->d_pose_est);
+  cudaFree(h->d_acc);
+  cudaFree(h->d_stage_counts);
+  cudaFree(h->d_work[0]);
+  cudaFree(h->d_work[1]);
+  cudaFree(h->d_count);
+  cudaFree(h->d_iterations);
+  cudaFree(h->d_converged);
+  cudaFree(h->d_first_stats);
+  cudaFree(h->d_geo_list);
+  cudaFreeHost(h->h_kfs);
+  cudaFreeHost(h->h_pose_est);
+  cudaFreeHost(h->h_work);
+  cudaFreeHost(h->h_geo_list);
+  cudaFreeHost(h->h_iterations);
+  cudaFreeHost(h->h_converged);
+  cudaFreeHost(h->h_first_stats);
+  cudaFreeHost(h->h_acc);
+  if (h->staging_event) cudaEventDestroy(h->staging_event);
+  for (auto& e : h->ev)
+    if (e) cudaEventDestroy(e);
+  delete h;
+}
+
+bba_status bba_set_surfels(bba_handle h, float* device_surfels, size_t pitch_bytes, uint32_t surfels_size) {
+  if (!h) return BBA_ERR_INVALID_ARGUMENT;
+  if (!device_surfels || pitch_bytes % 16 != 0 || (reinterpret_cast<uintptr_t>(device_surfels) & 15) != 0 ||
+      pitch_bytes < static_cast<size_t>((surfels_size + 3) / 4) * 16 || surfels_size > h->cfg.max_surfel_count)
+    return Fail(h, BBA_ERR_INVALID_ARGUMENT,
+                "surfel buffer must be 16-byte aligned with a row pitch that is a multiple of 16 bytes and holds surfels_size floats");
+  h->surfels = device_surfels;
+  h->surfel_pitch_bytes = pitch_bytes;
+  h->surfels_size = surfels_size;
+  return BBA_OK;
+}
+
+bba_status bba_set_active_flags(bba_handle h, uint8_t* device_flags) {
+  if (!h || !device_flags) return BBA_ERR_INVALID_ARGUMENT;
+  h->active = device_flags;
+  return BBA_OK;
+}
+
+bba_status bba_set_surfels_host(bba_handle h, const float* host_surfels, size_t pitch_bytes, uint32_t surfels_size, void* stream) {
+  if (!h || !host_surfels) return BBA_ERR_INVALID_ARGUMENT;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!h->owned_surfels) {
+    const size_t pitch = (static_cast<size_t>(h->cfg.max_surfel_count) * 4 + 511) / 512 * 512;
+    BBA_CUDA(h, cudaMalloc(&h->owned_surfels, pitch * bba::kSurfelRowCount));
+    BBA_CUDA(h, cudaMalloc(&h->owned_active, h->cfg.max_surfel_count));
+    BBA_CUDA(h, cudaMemsetAsync(h->owned_active, 0, h->cfg.max_surfel_count, s));
+    h->owned_surfel_pitch = pitch;
+  }
+  if (surfels_size > h->cfg.max_surfel_count || pitch_bytes < static_cast<size_t>(surfels_size) * 4)
+    return Fail(h, BBA_ERR_INVALID_ARGUMENT, "surfels_size exceeds max_surfel_count or the host pitch");
+  // only the 8 data rows are inputs (kSurfelDataAttributeCount, kernels.cuh:89); rows 8-16 are scratch
+  BBA_CUDA(h, cudaMemcpy2DAsync(h->owned_surfels, h->owned_surfel_pitch, host_surfels, pitch_bytes,
+                                static_cast<size_t>(surfels_size) * 4, 8, cudaMemcpyHostToDevice, s));
+  if (bba_status st = bba_set_surfels(h, h->owned_surfels, h->owned_surfel_pitch, surfels_size)) return st;
+  return bba_set_active_flags(h, h->owned_active);
+}
+
+bba_status bba_get_surfels_host(bba_handle h, float* host_surfels, size_t pitch_bytes, int rows, void* stream) {
+  if (!h || !host_surfels || rows < 1 || rows > bba::kSurfelRowCount) return BBA_ERR_INVALID_ARGUMENT;
+  if (bba_status st = CheckSurfels(h)) return st;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  BBA_CUDA(h, cudaMemcpy2DAsync(host_surfels, pitch_bytes, h->surfels, h->surfel_pitch_bytes,
+                                static_cast<size_t>(h->surfels_size) * 4, rows, cudaMemcpyDeviceToHost, s));
+  BBA_CUDA(h, cudaStreamSynchronize(s));
+  return BBA_OK;
+}
+
+bba_status bba_get_active_flags_host(bba_handle h, uint8_t* host_flags, void* stream) {
+  if (!h || !host_flags) return BBA_ERR_INVALID_ARGUMENT;
+  if (bba_status st = CheckSurfels(h)) return st;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  BBA_CUDA(h, cudaMemcpyAsync(host_flags, h->active, h->surfels_size, cudaMemcpyDeviceToHost, s));
+  BBA_CUDA(h, cudaStreamSynchronize(s));
+  return BBA_OK;
+}
+
+bba_status bba_get_surfels_device(bba_handle h, float** device_surfels, size_t* pitch_bytes, uint32_t* surfels_size) {
+  if (!h) return BBA_ERR_INVALID_ARGUMENT;
+  if (device_surfels) *device_surfels = h->surfels;
+  if (pitch_bytes) *pitch_bytes = h->surfel_pitch_bytes;
+  if (surfels_size) *surfels_size = h->surfels_size;
+  return BBA_OK;
+}
+
+bba_status bba_add_keyframe(bba_handle h, const uint16_t* device_depth, size_t depth_pitch, const uint16_t* device_normals,
+                            size_t normals_pitch, const uint16_t* device_radius, size_t radius_pitch,
+                            const uint8_t* device_color_rgba, size_t color_pitch, const float global_T_frame[7], float min_depth,
+                            float max_depth, void* stream, int* out_keyframe_id) {
+  if (!h || !device_depth || !device_normals || !device_color_rgba || !global_T_frame) return BBA_ERR_INVALID_ARGUMENT;
+  if (depth_pitch < static_cast<size_t>(h->cfg.depth_width) * 2 || normals_pitch < static_cast<size_t>(h->cfg.depth_width) * 2 ||
+      color_pitch < static_cast<size_t>(h->cfg.color_width) * 4 || depth_pitch > 0xffffffffull || normals_pitch > 0xffffffffull)
+    return Fail(h, BBA_ERR_INVALID_ARGUMENT, "keyframe buffer pitch too small");
+  Keyframe kf;
+  kf.depth = device_depth; kf.depth_pitch = depth_pitch;
+  kf.normals = device_normals; kf.normals_pitch = normals_pitch;
+  kf.radius = device_radius; kf.radius_pitch = radius_pitch;
+  return AddKeyframeCommon(h, std::move(kf), device_color_rgba, color_pitch, global_T_frame, min_depth, max_depth,
+                           static_cast<cudaStream_t>(stream), out_keyframe_id);
+}
+
+bba_status bba_add_keyframe_host(bba_handle h, const uint16_t* host_depth, const uint16_t* host_normals, const uint16_t* host_radius,
+                                 const uint8_t* host_color_rgba, const float global_T_frame[7], float min_depth, float max_depth,
+                                 void* stream, int* out_keyframe_id) {
+  if (!h || !host_depth || !host_normals || !host_color_rgba || !global_T_frame) return BBA_ERR_INVALID_ARGUMENT;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int w = h->cfg.depth_width, hh = h->cfg.depth_height, cw = h->cfg.color_width, ch = h->cfg.color_height;
+  Keyframe kf;
+  size_t pitch = 0;
+  const uint16_t* srcs[3] = {host_depth, host_normals, host_radius};
+  for (int i = 0; i < 3; ++i) {
+    if (!srcs[i]) continue;
+    BBA_CUDA(h, cudaMallocPitch(&kf.owned[i], &pitch, static_cast<size_t>(w) * 2, hh));
+    BBA_CUDA(h, cudaMemcpy2DAsync(kf.owned[i], pitch, srcs[i], static_cast<size_t>(w) * 2, static_cast<size_t>(w) * 2, hh,
+                                  cudaMemcpyHostToDevice, s));
+  }
+  kf.depth = static_cast<const uint16_t*>(kf.owned[0]); kf.depth_pitch = pitch;
+  kf.normals = static_cast<const uint16_t*>(kf.owned[1]); kf.normals_pitch = pitch;
+  kf.radius = static_cast<const uint16_t*>(kf.owned[2]); kf.radius_pitch = pitch;
+  // the colour image is only needed to derive the luma plane: stage it in a temporary
+  uint8_t* tmp = nullptr;
+  size_t tmp_pitch = 0;
+  BBA_CUDA(h, cudaMallocPitch(reinterpret_cast<void**>(&tmp), &tmp_pitch, static_cast<size_t>(cw) * 4, ch));
+  BBA_CUDA(h, cudaMemcpy2DAsync(tmp, tmp_pitch, host_color_rgba, static_cast<size_t>(cw) * 4, static_cast<size_t>(cw) * 4, ch,
+                                cudaMemcpyHostToDevice, s));
+  bba_status st = AddKeyframeCommon(h, std::move(kf), tmp, tmp_pitch, global_T_frame, min_depth, max_depth, s, out_keyframe_id);
+  cudaStreamSynchronize(s);
+  cudaFree(tmp);
+  return st;
+}
+
+int bba_keyframe_count(bba_handle h) { return h ? static_cast<int>(h->keyframes.size()) : 0; }
+
+#define CHECK_KF(h, id)                                                                   \
+  if (!(h)) return BBA_ERR_INVALID_ARGUMENT;                                              \
+  if ((id) < 0 || (id) >= static_cast<int>((h)->keyframes.size())) return Fail(h, BBA_ERR_INVALID_ARGUMENT, "bad keyframe id")
+
+bba_status bba_set_keyframe_pose(bba_handle h, int id, const float p[7]) {
+  CHECK_KF(h, id);
+  h->keyframes[id].pose = PoseFromArray(p);
+  return BBA_OK;
+}
+bba_status bba_get_keyframe_pose(bba_handle h, int id, float p[7]) {
+  CHECK_KF(h, id);
+  PoseToArray(h->keyframes[id].pose, p);
+  return BBA_OK;
+}
+bba_status bba_set_keyframe_activation(bba_handle h, int id, int activation) {
+  CHECK_KF(h, id);
+  if (activation < 0 || activation > 2) return Fail(h, BBA_ERR_INVALID_ARGUMENT, "bad activation");
+  h->keyframes[id].activation = activation;
+  return BBA_OK;
+}
+bba_status bba_get_keyframe_activation(bba_handle h, int id, int* activation) {
+  CHECK_KF(h, id);
+  *activation = h->keyframes[id].activation;
+  return BBA_OK;
+}
+bba_status bba_get_covisibility(bba_handle h, int id, uint8_t* out_row) {
+  CHECK_KF(h, id);
+  std::memset(out_row, 0, h->keyframes.size());
+  for (int o : h->keyframes[id].covis) out_row[o] = 1;
+  return BBA_OK;
+}
+
+bba_status bba_set_intrinsics(bba_handle h, const float d[4], const float c[4], float a) {
+  if (!h) return BBA_ERR_INVALID_ARGUMENT;
+  if (d) std::memcpy(h->depth_K, d, sizeof(h->depth_K));
+  if (c) std::memcpy(h->color_K, c, sizeof(h->color_K));
+  h->depth_a = a;
+  return BBA_OK;
+}
+bba_status bba_get_intrinsics(bba_handle h, float d[4], float c[4], float* a) {
+  if (!h) return BBA_ERR_INVALID_ARGUMENT;
+  if (d) std::memcpy(d, h->depth_K, sizeof(h->depth_K));
+  if (c) std::memcpy(c, h->color_K, sizeof(h->color_K));
+  if (a) *a = h->depth_a;
+  return BBA_OK;
+}
+bba_status bba_cfactor_size(bba_handle h, int* w, int* hh) {
+  if (!h) return BBA_ERR_INVALID_ARGUMENT;
+  if (w) *w = h->cf_w;
+  if (hh) *hh = h->cf_h;
+  return BBA_OK;
+}
+bba_status bba_set_cfactor_host(bba_handle h, const float* host, void* stream) {
+  if (!h || !host) return BBA_ERR_INVALID_ARGUMENT;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  BBA_CUDA(h, cudaMemcpyAsync(h->d_cfactor, host, sizeof(float) * h->cf_w * h->cf_h, cudaMemcpyHostToDevice, s));
+  BBA_CUDA(h, cudaStreamSynchronize(s));
+  return BBA_OK;
+}
+bba_status bba_get_cfactor_host(bba_handle h, float* host, void* stream) {
+  if (!h || !host) return BBA_ERR_INVALID_ARGUMENT;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  BBA_CUDA(h, cudaMemcpyAsync(host, h->d_cfactor, sizeof(float) * h->cf_w * h->cf_h, cudaMemcpyDeviceToHost, s));
+  BBA_CUDA(h, cudaStreamSynchronize(s));
+  return BBA_OK;
+}
+
+bba_status bba_accumulate_pose_coeffs(bba_handle h, int id, const float pose[7], bba_pose_coeffs* out, void* stream) {
+  CHECK_KF(h, id);
+  if (!pose || !out) return BBA_ERR_INVALID_ARGUMENT;
+  if (bba_status st = CheckSurfels(h)) return st;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int K = static_cast<int>(h->keyframes.size());
+  if (bba_status st = WaitStaging(h)) return st;
+  for (int k = 0; k < K; ++k) FillKfDevice(h->keyframes[k], h->keyframes[k].pose, h->h_kfs + k);
+  FillKfDevice(h->keyframes[id], PoseFromArray(pose), h->h_kfs + id);
+  h->h_work[0] = id;
+  h->h_work[h->cfg.max_keyframes] = 1;
+  BBA_CUDA(h, cudaMemcpyAsync(h->d_kfs, h->h_kfs, sizeof(KfDevice) * K, cudaMemcpyHostToDevice, s));
+  BBA_CUDA(h, cudaMemcpyAsync(h->d_work[0], h->h_work, sizeof(int), cudaMemcpyHostToDevice, s));
+  BBA_CUDA(h, cudaMemcpyAsync(h->d_count, h->h_work + h->cfg.max_keyframes, sizeof(int), cudaMemcpyHostToDevice, s));
+  BBA_CUDA(h, cudaMemsetAsync(h->d_acc + static_cast<size_t>(id) * bba::kPoseAccSize, 0, sizeof(double) * bba::kPoseAccSize, s));
+  BBA_CUDA(h, cudaMemsetAsync(h->d_stage_counts + 2 * id, 0, sizeof(unsigned long long) * 2, s));
+  bba::PoseAccumulateArgs acc;
+  acc.cam = MakeCamera(h);
+  acc.surfels = h->surfels;
+  acc.pitch = static_cast<uint32_t>(h->surfel_pitch_bytes / sizeof(float));
+  acc.n = h->surfels_size;
+  acc.kfs = h->d_kfs;
+  acc.acc = h->d_acc;
+  acc.stage_counts = h->d_stage_counts;
+  acc.work_list = h->d_work[0];
+  acc.work_count = h->d_count;
+  if (h->surfels_size > 0) {
+    bba::LaunchPoseAccumulate(acc, h->sm_count, s);
+    ++h->launches;
+  }
+  BBA_CUDA(h, cudaGetLastError());
+  BBA_CUDA(h, cudaMemcpyAsync(h->h_acc, h->d_acc + static_cast<size_t>(id) * bba::kPoseAccSize, sizeof(double) * bba::kPoseAccSize,
+                              cudaMemcpyDeviceToHost, s));
+  BBA_CUDA(h, cudaMemcpyAsync(h->h_acc + bba::kPoseAccSize, h->d_stage_counts + 2 * id, sizeof(unsigned long long) * 2,
+                              cudaMemcpyDeviceToHost, s));
+  BBA_CUDA(h, cudaMemsetAsync(h->d_acc + static_cast<size_t>(id) * bba::kPoseAccSize, 0, sizeof(double) * bba::kPoseAccSize, s));
+  BBA_CUDA(h, cudaMemsetAsync(h->d_stage_counts + 2 * id, 0, sizeof(unsigned long long) * 2, s));
+  BBA_CUDA(h, cudaStreamSynchronize(s));
+  h->staging_pending = false;
+  for (int i = 0; i < 21; ++i) out->H[i] = static_cast<float>(h->h_acc[i]);
+  for (int i = 0; i < 6; ++i) out->b[i] = static_cast<float>(h->h_acc[21 + i]);
+  unsigned long long sc[2];
+  std::memcpy(sc, h->h_acc + bba::kPoseAccSize, sizeof(sc));
+  out->n_pair = h->surfels_size;
+  out->n_inimg = sc[0];
+  out->n_depthok = sc[1];
+  out->n_assoc = static_cast<uint64_t>(h->h_acc[27] + 0.5);
+  out->n_photo = static_cast<uint64_t>(h->h_acc[28] + 0.5);
+  out->cost_depth = h->h_acc[29];
+  out->cost_desc1 = h->h_acc[30];
+  out->cost_desc2 = h->h_acc[31];
+  return BBA_OK;
+}
+
+bba_status bba_estimate_frame_pose(bba_handle h, int id, const float init[7], float out[7], int* iterations, int* converged,
+                                   void* stream) {
+  CHECK_KF(h, id);
+  if (!init || !out) return BBA_ERR_INVALID_ARGUMENT;
+  if (bba_status st = CheckSurfels(h)) return st;
+  std::vector<int> ids(1, id);
+  std::vector<Pose> poses(1, PoseFromArray(init));
+  if (bba_status st = RunPoseStep(h, ids, poses, 30, static_cast<cudaStream_t>(stream))) return st;
+  std::memcpy(out, h->h_pose_est + 7 * id, sizeof(float) * 7);
+  if (iterations) *iterations = h->h_iterations[id];
+  if (converged) *converged = h->h_converged[id];
+  return BBA_OK;
+}
+
+bba_status bba_update_surfel_activation(bba_handle h, void* stream) {
+  if (!h) return BBA_ERR_INVALID_ARGUMENT;
+  if (bba_status st = CheckSurfels(h)) return st;
+  if (h->surfels_size == 0) return BBA_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (bba_status st = UploadKeyframes(h, s)) return st;
+  bba::GeometryArgs g;
+  if (bba_status st = BuildGeometryArgs(h, &g, s)) return st;
+  bba::LaunchActivationAndNormals(g, true, false, s);
+  ++h->launches;
+  BBA_CUDA(h, cudaGetLastError());
+  return MarkStaging(h, s);
+}
+
+bba_status bba_optimize_geometry_iteration(bba_handle h, void* stream) {
+  if (!h) return BBA_ERR_INVALID_ARGUMENT;
+  if (bba_status st = CheckSurfels(h)) return st;
+  if (h->surfels_size == 0) return BBA_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (bba_status st = UploadKeyframes(h, s)) return st;
+  bba::GeometryArgs g;
+  if (bba_status st = BuildGeometryArgs(h, &g, s)) return st;
+  bba::LaunchActivationAndNormals(g, false, true, s);
+  bba::LaunchPositionAndDescriptor(g, s);
+  h->launches += 2;
+  BBA_CUDA(h, cudaGetLastError());
+  return MarkStaging(h, s);
+}
+
+bba_status bba_optimize_intrinsics(bba_handle h, int optimize_depth, int optimize_color, void* stream) {
+  (void)optimize_depth; (void)optimize_color; (void)stream;
+  return Fail(h, BBA_ERR_UNSUPPORTED, "intrinsics optimisation is not implemented yet");
+}
+
+bba_status bba_bundle_adjust(bba_handle h, const bba_ba_options* o, bba_ba_result* res, void* stream) {
+  if (!h || !o || !res) return BBA_ERR_INVALID_ARGUMENT;
+  std::memset(res, 0, sizeof(*res));
+  if (bba_status st = CheckSurfels(h)) return st;
+  if (o->use_pcg) return Fail(h, BBA_ERR_UNSUPPORTED, "use_pcg: the PCG solver (direct_ba_pcg.cc) is not implemented");
+  if (o->do_surfel_updates) return Fail(h, BBA_ERR_UNSUPPORTED, "do_surfel_updates: surfel creation/merge/deletion is not implemented");
+  // direct_ba.cc:427-434
+  const bool opt_depth_intr = o->optimize_depth_intrinsics && h->cfg.use_depth_residuals;
+  const bool opt_color_intr = o->optimize_color_intrinsics && h->cfg.use_descriptor_residuals;
+  if (opt_depth_intr || opt_color_intr) return Fail(h, BBA_ERR_UNSUPPORTED, "intrinsics optimisation is not implemented yet");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int K = static_cast<int>(h->keyframes.size());
+  const uint64_t launches_before = h->launches;
+  const auto t_start = std::chrono::steady_clock::now();
+
+  const bool fixed_window = o->active_keyframe_window_start > 0 || o->active_keyframe_window_end > 0;   // :330-331
+  const bool whole_window = !(o->active_keyframe_window_start != 0 || o->active_keyframe_window_end != K - 1);
+
+  BBA_CUDA(h, cudaMemsetAsync(h->active, 0, h->surfels_size, s));   // :338
+
+  for (int iteration = 0; iteration < o->max_iterations; ++iteration) {
+    ++res->iterations_done;
+    if (fixed_window) {   // :354-372
+      for (int k = 0; k < K; ++k)
+        h->keyframes[k].activation =
+            (k >= o->active_keyframe_window_start && k <= o->active_keyframe_window_end) ? BBA_KF_ACTIVE : BBA_KF_INACTIVE;
+      DetermineCovisibleActiveKeyframes(h);
+    }
+
+    if (bba_status st = UploadKeyframes(h, s)) return st;
+    bba::GeometryArgs g;
+    if (bba_status st = BuildGeometryArgs(h, &g, s)) return st;
+
+    // --- surfel activation (:444-456) fused with the normal update of the geometry step (:466-485)
+    BBA_CUDA(h, cudaEventRecord(h->ev[0], s));
+    if (!whole_window) BBA_CUDA(h, cudaMemsetAsync(h->active, bba::kSurfelActiveFlag, h->surfels_size, s));
+    if (h->surfels_size > 0) {
+      if (whole_window) {
+        bba::LaunchActivationAndNormals(g, true, o->optimize_geometry != 0, s);
+        ++h->launches;
+      } else if (o->optimize_geometry) {
+        bba::LaunchActivationAndNormals(g, false, true, s);
+        ++h->launches;
+      }
+    }
+    BBA_CUDA(h, cudaEventRecord(h->ev[1], s));
+    if (o->optimize_geometry && h->surfels_size > 0) {
+      bba::LaunchPositionAndDescriptor(g, s);
+      ++h->launches;
+    }
+    BBA_CUDA(h, cudaEventRecord(h->ev[2], s));
+    BBA_CUDA(h, cudaGetLastError());
+    if (bba_status st = MarkStaging(h, s)) return st;
+
+    // --- pose optimisation (:543-577): all non-inactive keyframes at once
+    int num_converged = 0;
+    if (o->optimize_poses) {
+      std::vector<int> ids;
+      std::vector<Pose> init;
+      for (int k = 0; k < K; ++k) {
+        if (h->keyframes[k].activation == BBA_KF_INACTIVE) {
+          ++num_converged;
+          continue;
+        }
+        ids.push_back(k);
+        init.push_back(h->keyframes[k].pose);
+      }
+      if (bba_status st = RunPoseStep(h, ids, init, 30, s)) return st;
+      res->depth_residual_count = 0;
+      res->descriptor_residual_count = 0;
+      res->cost = 0;
+      for (int k : ids) {
+        Keyframe& kf = h->keyframes[k];
+        const Pose est = PoseFromArray(h->h_pose_est + 7 * k);
+        float lg[6];
+        bba::Log(bba::Compose(bba::Inverse(kf.pose), est), lg);   // :562-563
+        const bool moved = !bba::IsScale1PoseEstimationConverged(lg);
+        kf.pose = est;
+        if (moved) {
+          kf.activation = BBA_KF_ACTIVE;
+        } else {
+          kf.activation = BBA_KF_INACTIVE;
+          ++num_converged;
+        }
+        res->pose_iterations_total += h->h_iterations[k];
+        const double* fs = h->h_first_stats + 8 * k;
+        res->depth_residual_count += static_cast<uint64_t>(fs[0] + 0.5);
+        res->descriptor_residual_count += 2 * static_cast<uint64_t>(fs[1] + 0.5);
+        res->cost += fs[2] + fs[3];
+      }
+    } else {
+      BBA_CUDA(h, cudaStreamSynchronize(s));
+    }
+    BBA_CUDA(h, cudaEventRecord(h->ev[3], s));
+    BBA_CUDA(h, cudaEventSynchronize(h->ev[3]));
+    cudaEventElapsedTime(&res->ms_surfel_activation, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&res->ms_geometry_optimization, h->ev[1], h->ev[2]);
+    cudaEventElapsedTime(&res->ms_pose_optimization, h->ev[2], h->ev[3]);
+
+    // --- convergence (:693-701)
+    if (iteration >= o->min_iterations - 1 && (num_converged == K || !o->optimize_poses)) {
+      res->converged = 1;
+      break;
+    }
+    if (o->time_limit_seconds > 0) {   // :704-709
+      const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+      if (el > o->time_limit_seconds) break;
+    }
+    DetermineCovisibleActiveKeyframes(h);   // :711-717
+  }
+  if (o->increase_ba_iteration_count) ++h->ba_iteration_count;
+  res->kernel_launches = h->launches - launches_before;
+  return BBA_OK;
+}
+
+bba_status bba_set_allgather(bba_handle h, bba_allgather_fn fn, void* user) {
+  if (!h) return BBA_ERR_INVALID_ARGUMENT;
+  h->allgather = fn;
+  h->allgather_user = user;
+  return BBA_OK;
+}
+
+uint64_t bba_kernel_launch_count(bba_handle h) { return h ? h->launches : 0; }
+
+}  // extern "C"

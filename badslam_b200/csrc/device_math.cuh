@@ -1,0 +1,255 @@
+// device_math.cuh -- device-side surfel/keyframe maths of libbadba_b200 (sm_100a).
+//
+// What is computed follows the reference's device headers (cited per function, paths relative to
+// /root/reference/applications/badslam/src/badslam/); how it is computed is our own: keyframe
+// parameters live in one 96-byte record, images are addressed through raw pitched pointers with
+// read-only (ld.global.nc) gathers, the luma plane is a single-channel u8 texture, and all
+// association stages are expressed as early-outs that report which stage was reached (for the
+// algorithmic-bytes counters of SURVEY.md 8d).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bba {
+
+// cost_function.cuh:44-52,105-109,126 ; kernels.cuh:38-58
+constexpr float kDepthTukey = 10.f;
+constexpr float kDepthUncertaintyFactor = 0.1f;
+constexpr float kDescWeight = 1e-2f;
+constexpr float kDescHuber = 10.f;
+constexpr float kTangentScaling = 2.0f;
+constexpr uint16_t kInvalidDepthBit = 0x8000u;
+constexpr float kCosNormalCompat = 0.76604f;
+constexpr uint8_t kSurfelActiveFlag = 1u;
+
+// kernels.cuh:69-93
+enum SurfelRow { kRowX = 0, kRowY, kRowZ, kRowNormal, kRowRadiusSq, kRowColor, kRowD1, kRowD2, kRowAccum0 };
+constexpr int kSurfelRowCount = 17;
+
+// Camera / depth model shared by all keyframes (surfel_projection.h:42-124 builders, DepthParameters
+// surfel_projection.cuh:134-156).  Passed to kernels by value.
+struct CameraParams {
+  int w, h, cw, ch;
+  float fx, fy, cx, cy;                  // depth PixelCornerProjector
+  float fx_inv, fy_inv, cx_inv, cy_inv;  // depth PixelCenterUnprojector
+  float d2c_fx, d2c_fy, d2c_cx, d2c_cy;  // DepthToColorPixelCorner
+  float cfx, cfy, ccx, ccy;              // colour PixelCornerProjector (PixelCenterProjector shares fx, fy)
+  float a, raw_to_float, baseline_fx;
+  int cell, cf_w;
+  const float* __restrict__ cfactor;     // dense [cf_h][cf_w]
+  int use_depth, use_desc;
+};
+
+// One keyframe as the kernels see it (Keyframe members keyframe.h:160-237).
+struct __align__(16) KfDevice {
+  float T[12];                       // frame_T_global, row-major 3x4
+  const uint16_t* depth;             // pitched u16
+  const uint16_t* normals;           // pitched u16
+  cudaTextureObject_t tex;           // u8 luma, linear filter, normalized float, clamp, unnormalized coords
+  uint32_t depth_pitch, normals_pitch;   // bytes
+  int activation;
+  int pad;
+};
+static_assert(sizeof(KfDevice) == 96, "KfDevice layout");
+
+struct Vec3 {
+  float x, y, z;
+};
+__device__ __forceinline__ Vec3 V3(float x, float y, float z) { return Vec3{x, y, z}; }
+__device__ __forceinline__ float Dot(const Vec3& a, const Vec3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ Vec3 operator-(const Vec3& a, const Vec3& b) { return V3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ Vec3 operator+(const Vec3& a, const Vec3& b) { return V3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ Vec3 operator*(float s, const Vec3& a) { return V3(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ Vec3 Cross(const Vec3& a, const Vec3& b) {   // cuda_util.cuh:76-80
+  return V3(a.y * b.z - b.y * a.z, b.x * a.z - a.x * b.z, a.x * b.y - b.x * a.y);
+}
+__device__ __forceinline__ Vec3 Rotate(const float* __restrict__ T, const Vec3& p) {   // cuda_matrix.cuh:126-135
+  return V3(T[0] * p.x + T[1] * p.y + T[2] * p.z, T[4] * p.x + T[5] * p.y + T[6] * p.z,
+            T[8] * p.x + T[9] * p.y + T[10] * p.z);
+}
+__device__ __forceinline__ Vec3 Transform(const float* __restrict__ T, const Vec3& p) {   // cuda_matrix.cuh:104-112
+  return V3(T[0] * p.x + T[1] * p.y + T[2] * p.z + T[3], T[4] * p.x + T[5] * p.y + T[6] * p.z + T[7],
+            T[8] * p.x + T[9] * p.y + T[10] * p.z + T[11]);
+}
+
+// robust_weighting.cuh:39-86
+__device__ __forceinline__ float TukeyResidual(float r, float p) {
+  if (fabsf(r) < p) {
+    const float q = r / p, t = 1.f - q * q;
+    return (1 / 6.f) * p * p * (1 - t * t * t);
+  }
+  return (1 / 6.f) * p * p;
+}
+__device__ __forceinline__ float TukeyWeight(float r, float p) {
+  if (fabsf(r) < p) {
+    const float q = r / p, t = 1.f - q * q;
+    return t * t;
+  }
+  return 0.f;
+}
+__device__ __forceinline__ float HuberResidual(float r, float p) {
+  const float a = fabsf(r);
+  return (a < p) ? 0.5f * r * r : p * (a - 0.5f * p);
+}
+__device__ __forceinline__ float HuberWeight(float r, float p) {
+  const float a = fabsf(r);
+  return (a < p) ? 1.f : (p / a);
+}
+// cost_function.cuh:91-98,177-185 (kDepthResidualWeight = 1)
+__device__ __forceinline__ float DepthWeight(float r) { return TukeyWeight(r, kDepthTukey); }
+__device__ __forceinline__ float DepthCost(float r) { return TukeyResidual(r, kDepthTukey); }
+__device__ __forceinline__ float DescWeight(float r) { return kDescWeight * HuberWeight(r, kDescHuber); }
+__device__ __forceinline__ float DescCost(float r) { return kDescWeight * HuberResidual(r, kDescHuber); }
+
+// util_nvcc_only.cuh:67-95 (10-bit signed pack / unpack, normal re-normalised after unpack)
+__device__ __forceinline__ float S10ToFloat(uint32_t v) {
+  // sign-extend the low 10 bits
+  const int s = (static_cast<int>(v << 22)) >> 22;
+  return s * (1.0f / 511);
+}
+__device__ __forceinline__ Vec3 UnpackNormal(uint32_t v) {
+  Vec3 n = V3(S10ToFloat(v), S10ToFloat(v >> 10), S10ToFloat(v >> 20));
+  const float f = 1.0f / sqrtf(Dot(n, n));
+  return f * n;
+}
+__device__ __forceinline__ uint32_t FloatToS10(float v) {
+  return 0x03ffu & static_cast<uint16_t>(static_cast<int16_t>(v * 511 + ((v > 0) ? 0.5f : -0.5f)));
+}
+__device__ __forceinline__ uint32_t PackNormal(const Vec3& n) {
+  return FloatToS10(n.x) | (FloatToS10(n.y) << 10) | (FloatToS10(n.z) << 20);
+}
+// util.cuh:126-146
+__device__ __forceinline__ Vec3 U16ToImageSpaceNormal(uint16_t v) {
+  Vec3 r;
+  r.x = static_cast<int8_t>(v & 0x00ff) * (1.0f / 127);
+  r.y = static_cast<int8_t>(v >> 8) * (1.0f / 127);
+  const float z = 1 - r.x * r.x - r.y * r.y;
+  r.z = -sqrtf((z > 0.f) ? z : 0.f);
+  return r;
+}
+// util.cuh:62-69
+__device__ __forceinline__ float RawToCalibratedDepth(float a, float cfactor, float raw_to_float, uint16_t measured) {
+  const float inv_depth = 1.0f / (raw_to_float * measured);
+  return 1.f / (inv_depth + cfactor * expf(-a * inv_depth));
+}
+
+__device__ __forceinline__ uint16_t LoadPixelU16(const uint16_t* base, uint32_t pitch, int px, int py) {
+  return __ldg(reinterpret_cast<const uint16_t*>(reinterpret_cast<const char*>(base) + static_cast<size_t>(py) * pitch) + px);
+}
+
+// Result of projecting one surfel into one keyframe.
+struct Assoc {
+  Vec3 lp;      // surfel position in the keyframe frame
+  Vec3 ln;      // surfel normal rotated into the keyframe frame
+  float d;      // calibrated depth of the pixel
+  float nx, ny; // unprojector ray of the pixel
+  int px, py;
+  float pxf, pyf;
+  uint16_t kf_normal;
+};
+
+// Projection + association.  Returns the stage reached: 0 culled / outside, 1 in image,
+// 2 passed valid-depth + depth-threshold + facing tests (keyframe normal read), 3 associated.
+// surfel_projection_nvcc_only.cuh:48-127,332-359 ; util.cuh:83-118 ; cuda_matrix.cuh:115-124 ; cost_function.cuh:81-83
+__device__ __forceinline__ int ProjectAssociate(const CameraParams& cam, const float* __restrict__ T,
+                                                const uint16_t* __restrict__ depth, uint32_t depth_pitch,
+                                                const uint16_t* __restrict__ normals, uint32_t normals_pitch,
+                                                const Vec3& gp, const Vec3& n, Assoc* r) {
+  r->lp.z = T[8] * gp.x + T[9] * gp.y + T[10] * gp.z + T[11];
+  if (r->lp.z <= 0.f) return 0;
+  r->lp.x = T[0] * gp.x + T[1] * gp.y + T[2] * gp.z + T[3];
+  r->lp.y = T[4] * gp.x + T[5] * gp.y + T[6] * gp.z + T[7];
+  const float inv_z = 1.0f / r->lp.z;
+  r->pxf = cam.fx * (r->lp.x * inv_z) + cam.cx;
+  r->pyf = cam.fy * (r->lp.y * inv_z) + cam.cy;
+  // float -> int conversion saturates on the device, so the reference's bounds test is safe as is
+  r->px = static_cast<int>(r->pxf);
+  r->py = static_cast<int>(r->pyf);
+  if (!(r->pxf >= 0.f) || !(r->pyf >= 0.f) || r->px >= cam.w || r->py >= cam.h) return 0;
+
+  const uint16_t measured = LoadPixelU16(depth, depth_pitch, r->px, r->py);
+  if (measured & kInvalidDepthBit) return 1;
+  const float cf = __ldg(cam.cfactor + (r->py / cam.cell) * cam.cf_w + (r->px / cam.cell));
+  r->d = RawToCalibratedDepth(cam.a, cf, cam.raw_to_float, measured);
+  r->ln = Rotate(T, n);
+  r->nx = cam.fx_inv * r->px + cam.cx_inv;
+  r->ny = cam.fy_inv * r->py + cam.cy_inv;
+  const float stddev =
+      (kDepthUncertaintyFactor * fabsf(r->ln.x * r->nx + r->ln.y * r->ny + r->ln.z) * (r->d * r->d)) / cam.baseline_fx;
+  if (fabsf(r->lp.z - r->d) > kDepthTukey * stddev) return 1;
+  const float dist = sqrtf(Dot(r->lp, r->lp));
+  if ((1.0f / dist) * Dot(r->lp, r->ln) > 0) return 1;
+  r->kf_normal = LoadPixelU16(normals, normals_pitch, r->px, r->py);
+  if (Dot(r->ln, U16ToImageSpaceNormal(r->kf_normal)) < kCosNormalCompat) return 2;
+  return 3;
+}
+
+// surfel_projection.cuh:196-207
+__device__ __forceinline__ bool DepthToColor(const CameraParams& cam, float pxf, float pyf, float* cx, float* cy) {
+  *cx = cam.d2c_fx * pxf + cam.d2c_cx;
+  *cy = cam.d2c_fy * pyf + cam.d2c_cy;
+  return *cx >= 0 && *cy >= 0 && static_cast<int>(*cx) < cam.cw && static_cast<int>(*cy) < cam.ch;
+}
+
+// cost_function.cuh:56-88 + kernel_opt_pose.cu:45-94 (inv_stddev, unprojected pixel point, raw residual)
+__device__ __forceinline__ float DepthResidual(const CameraParams& cam, const Assoc& r, float* inv_stddev, Vec3* unproj) {
+  *inv_stddev = cam.baseline_fx / (kDepthUncertaintyFactor * fabsf(r.ln.x * r.nx + r.ln.y * r.ny + r.ln.z) * (r.d * r.d));
+  *unproj = V3(r.d * r.nx, r.d * r.ny, r.d);
+  return *inv_stddev * Dot(r.ln, *unproj - r.lp);
+}
+
+// cost_function.cuh:115-136
+__device__ __forceinline__ void TangentProjections(const CameraParams& cam, const float* __restrict__ T, const Vec3& gp,
+                                                   const Vec3& n, float radius_sq, float* t1x, float* t1y, float* t2x,
+                                                   float* t2y) {
+  Vec3 t1 = Cross(n, (fabsf(n.x) > 0.9f) ? V3(0, 1, 0) : V3(1, 0, 0));
+  t1 = (kTangentScaling * sqrtf(radius_sq / fmaxf(1e-12f, Dot(t1, t1)))) * t1;
+  const Vec3 p1 = Transform(T, gp + t1);
+  *t1x = cam.cfx * (p1.x / p1.z) + cam.ccx;
+  *t1y = cam.cfy * (p1.y / p1.z) + cam.ccy;
+  Vec3 t2 = Cross(n, t1);
+  t2 = (kTangentScaling * sqrtf(radius_sq / fmaxf(1e-12f, Dot(t2, t2)))) * t2;
+  const Vec3 p2 = Transform(T, gp + t2);
+  *t2x = cam.cfx * (p2.x / p2.z) + cam.ccx;
+  *t2y = cam.cfy * (p2.y / p2.z) + cam.ccy;
+}
+
+// One sample point of DescriptorJacobianWrtProjectedPosition (cost_function.cuh:191-254): the four texels around
+// (x, y) read at their centres (no filtering) and combined into a finite-difference gradient.
+__device__ __forceinline__ void PointGradient(cudaTextureObject_t tex, float x, float y, float* dx, float* dy) {
+  const int ix = static_cast<int>(fmaxf(0.f, x - 0.5f));
+  const int iy = static_cast<int>(fmaxf(0.f, y - 0.5f));
+  const float tx = fmaxf(0.f, fminf(1.f, x - 0.5f - ix));
+  const float ty = fmaxf(0.f, fminf(1.f, y - 0.5f - iy));
+  const float tl = tex2D<float>(tex, ix + 0.5f, iy + 0.5f);
+  const float tr = tex2D<float>(tex, ix + 1.5f, iy + 0.5f);
+  const float bl = tex2D<float>(tex, ix + 0.5f, iy + 1.5f);
+  const float br = tex2D<float>(tex, ix + 1.5f, iy + 1.5f);
+  *dx = (br - bl) * ty + (tr - tl) * (1 - ty);
+  *dy = (br - tr) * tx + (bl - tl) * (1 - tx);
+}
+
+struct DescEval {
+  float r1, r2;              // raw residuals (cost_function.cuh:140-156)
+  float gx1, gy1, gx2, gy2;  // gradients wrt the projected position (cost_function.cuh:250-253)
+};
+
+__device__ __forceinline__ void EvalDescriptor(cudaTextureObject_t tex, float cx, float cy, float t1x, float t1y, float t2x,
+                                               float t2y, float d1, float d2, DescEval* e) {
+  const float intensity = tex2D<float>(tex, cx, cy);
+  const float t1i = tex2D<float>(tex, t1x, t1y);
+  const float t2i = tex2D<float>(tex, t2x, t2y);
+  e->r1 = (180.f * (t1i - intensity)) - d1;
+  e->r2 = (180.f * (t2i - intensity)) - d2;
+  float cdx, cdy, t1dx, t1dy, t2dx, t2dy;
+  PointGradient(tex, cx, cy, &cdx, &cdy);
+  PointGradient(tex, t1x, t1y, &t1dx, &t1dy);
+  PointGradient(tex, t2x, t2y, &t2dx, &t2dy);
+  e->gx1 = 180.f * (t1dx - cdx);
+  e->gy1 = 180.f * (t1dy - cdy);
+  e->gx2 = 180.f * (t2dx - cdx);
+  e->gy2 = 180.f * (t2dy - cdy);
+}
+
+}  // namespace bba

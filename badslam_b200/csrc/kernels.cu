@@ -1,0 +1,492 @@
+// kernels.cu -- hand-written sm_100a kernels of the direct-BA hot path.
+//
+//  * PoseAccumulateKernel: ONE persistent launch evaluates the pose normal equations of a whole LIST of
+//    keyframes (the reference launches AccumulatePoseEstimationCoeffsCUDAKernel once per keyframe and
+//    Gauss-Newton iteration, kernel_opt_pose.cc:74-88).  Surfel tiles are staged into shared memory by the
+//    TMA engine (cp.async.bulk + mbarrier, double-buffered); each warp owns (tile, keyframe) work items,
+//    keeps the 21 H + 6 b + 5 bookkeeping sums in registers across the whole tile, and reduces them with a
+//    31-shuffle transposed butterfly followed by one fp64 RED per lane (the reference does 27 block-wide CUB
+//    reductions + atomics per residual type per 256 surfels, gauss_newton.cuh:59-92).
+//  * ActivationNormalsKernel / PositionDescriptorKernel: surfel-major geometry step.  One thread owns one
+//    surfel, loops over all non-inactive keyframes with the accumulators in registers and applies the update
+//    in the same kernel -- the reference's reset / K x accumulate / update launch chain with 16-72 bytes of
+//    read-modify-write per associated pair (kernel_opt_geometry.cc:114-199) becomes one pass with none.
+//
+// Built with -use_fast_math like the reference (applications/badslam/CMakeLists.txt:74-75).
+#include "kernels.cuh"
+
+#include <cuda.h>
+
+namespace bba {
+
+// ------------------------------------------------------------------------------------------------
+// mbarrier / bulk-copy (TMA) primitives, raw PTX.
+
+__device__ __forceinline__ uint32_t SmemAddr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void MbarInit(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(SmemAddr(bar)), "r"(count));
+}
+__device__ __forceinline__ void FenceBarrierInit() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void MbarArriveExpectTx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(SmemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void MbarWait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(SmemAddr(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk copy global -> shared, completion signalled on an mbarrier (TMA engine; SASS UBLKCP).
+__device__ __forceinline__ void BulkCopyG2S(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(SmemAddr(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(SmemAddr(bar))
+               : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+
+struct KfRegs {
+  float T[12];
+  const uint16_t* depth;
+  const uint16_t* normals;
+  cudaTextureObject_t tex;
+  uint32_t depth_pitch, normals_pitch;
+  int activation;
+};
+
+__device__ __forceinline__ void LoadKf(const KfDevice* __restrict__ kfs, int kf, KfRegs* r) {
+  const float4* p = reinterpret_cast<const float4*>(kfs + kf);
+  const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+  r->T[0] = a.x; r->T[1] = a.y; r->T[2] = a.z; r->T[3] = a.w;
+  r->T[4] = b.x; r->T[5] = b.y; r->T[6] = b.z; r->T[7] = b.w;
+  r->T[8] = c.x; r->T[9] = c.y; r->T[10] = c.z; r->T[11] = c.w;
+  const ulonglong2 q = __ldg(reinterpret_cast<const ulonglong2*>(p + 3));
+  r->depth = reinterpret_cast<const uint16_t*>(q.x);
+  r->normals = reinterpret_cast<const uint16_t*>(q.y);
+  const ulonglong2 q2 = __ldg(reinterpret_cast<const ulonglong2*>(p + 4));
+  r->tex = static_cast<cudaTextureObject_t>(q2.x);
+  r->depth_pitch = static_cast<uint32_t>(q2.y & 0xffffffffu);
+  r->normals_pitch = static_cast<uint32_t>(q2.y >> 32);
+  r->activation = __ldg(reinterpret_cast<const int*>(p + 5));
+}
+
+// kernel_opt_pose.cu:96-142: Jacobian of a descriptor residual wrt the pose (global_T_frame * exp(hat(delta))).
+__device__ __forceinline__ void DescPoseJacobian(const CameraParams& cam, const Vec3& ls, float gx, float gy, float (&J)[6]) {
+  gx *= cam.cfx;
+  gy *= cam.cfy;
+  const float inv_z = 1.f / ls.z, z_sq = ls.z * ls.z, inv_z_sq = inv_z * inv_z, xy = ls.x * ls.y;
+  J[0] = -gx * inv_z;
+  J[1] = -gy * inv_z;
+  J[2] = (ls.x * gx + ls.y * gy) * inv_z_sq;
+  J[3] = ((ls.y * ls.y + z_sq) * gy + xy * gx) * inv_z_sq;
+  J[4] = -((ls.x * ls.x + z_sq) * gx + xy * gy) * inv_z_sq;
+  J[5] = -(ls.x * gy - ls.y * gx) * inv_z;
+}
+
+// H += w J^T J (upper triangle, row-major), b += w r J   (gauss_newton.cuh:59-92, per thread)
+__device__ __forceinline__ void AccumulateHb(float (&acc)[kPoseAccSize], const float (&J)[6], float raw, float w) {
+  int idx = 0;
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    const float wj = w * J[r];
+#pragma unroll
+    for (int c = r; c < 6; ++c) acc[idx++] += wj * J[c];
+  }
+  const float wr = w * raw;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) acc[21 + i] += wr * J[i];
+}
+
+// Sums acc[i] over the 32 lanes of the warp for all 32 i at once: after the call lane L holds the total of
+// acc[L].  16+8+4+2+1 = 31 shuffles instead of 32 x 5.
+__device__ __forceinline__ float WarpTransposeReduce(float (&v)[32], int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float lo = v[i], hi = v[i + half];
+      const float send = upper ? lo : hi;
+      const float keep = upper ? hi : lo;
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return v[0];
+}
+
+constexpr int kPoseThreads = 256;
+constexpr int kPoseWarps = kPoseThreads / 32;
+constexpr int kPoseStagedRows = 7;   // x y z normal radius^2 d1 d2
+
+template <int TILE>
+__global__ void __launch_bounds__(kPoseThreads, 2) PoseAccumulateKernel(const __grid_constant__ PoseAccumulateArgs args) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* stage_base = reinterpret_cast<float*>(smem_raw);   // [2][7][TILE]
+  __shared__ __align__(8) uint64_t full_bar[2];
+
+  const int n_work = __ldg(args.work_count);
+  if (n_work <= 0) return;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const uint32_t n_tiles = (args.n + TILE - 1) / TILE;
+  if (blockIdx.x >= n_tiles) return;
+
+  if (tid == 0) {
+    MbarInit(&full_bar[0], 1);
+    MbarInit(&full_bar[1], 1);
+    FenceBarrierInit();
+  }
+  __syncthreads();
+
+  // With fewer keyframes than warps (e.g. EstimateFramePose of a single frame) every tile is split into
+  // 2, 4 or 8 parts so that all warps of the CTA have work.
+  int split_shift = 0;
+  if (n_work < kPoseWarps) split_shift = 31 - __clz(kPoseWarps / n_work);
+  const int n_split = 1 << split_shift;
+  const int n_items = n_work << split_shift;
+  const uint32_t part_len = TILE >> split_shift;
+
+  const CameraParams& cam = args.cam;
+  constexpr int kRowIds[kPoseStagedRows] = {kRowX, kRowY, kRowZ, kRowNormal, kRowRadiusSq, kRowD1, kRowD2};
+
+  auto issue_tile = [&](uint32_t tile, int s) {
+    const uint32_t base = tile * TILE;
+    const uint32_t cnt = min(static_cast<uint32_t>(TILE), args.n - base);
+    const uint32_t bytes = ((cnt * 4u + 15u) / 16u) * 16u;
+    MbarArriveExpectTx(&full_bar[s], bytes * kPoseStagedRows);
+#pragma unroll
+    for (int r = 0; r < kPoseStagedRows; ++r) {
+      BulkCopyG2S(stage_base + (s * kPoseStagedRows + r) * TILE,
+                  args.surfels + static_cast<size_t>(kRowIds[r]) * args.pitch + base, bytes, &full_bar[s]);
+    }
+  };
+
+  if (tid == 0) issue_tile(blockIdx.x, 0);
+
+  uint32_t it = 0;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int s = it & 1;
+    if (tid == 0) {
+      const uint32_t next = tile + gridDim.x;
+      if (next < n_tiles) issue_tile(next, s ^ 1);   // stage s^1 was released by the __syncthreads below
+    }
+    MbarWait(&full_bar[s], (it >> 1) & 1);
+
+    const float* sx = stage_base + (s * kPoseStagedRows + 0) * TILE;
+    const float* sy = sx + TILE;
+    const float* sz = sy + TILE;
+    const float* sn = sz + TILE;
+    const float* sr = sn + TILE;
+    const float* sd1 = sr + TILE;
+    const float* sd2 = sd1 + TILE;
+    const uint32_t base = tile * TILE;
+    const uint32_t cnt = min(static_cast<uint32_t>(TILE), args.n - base);
+
+    for (int wi = warp; wi < n_items; wi += kPoseWarps) {
+      const int kf = __ldg(args.work_list + (wi >> split_shift));
+      const uint32_t j0 = static_cast<uint32_t>(wi & (n_split - 1)) * part_len;
+      if (j0 >= cnt) continue;
+      const uint32_t j1 = min(cnt, j0 + part_len);
+      KfRegs K;
+      LoadKf(args.kfs, kf, &K);
+
+      float acc[kPoseAccSize];
+#pragma unroll
+      for (int i = 0; i < kPoseAccSize; ++i) acc[i] = 0.f;
+      unsigned touched = 0;
+      unsigned n_inimg = 0, n_depthok = 0;
+
+#pragma unroll 1
+      for (uint32_t j = j0 + lane; j < j0 + (j1 - j0 + 31u) / 32u * 32u; j += 32) {
+        int st = 0;
+        Assoc r;
+        Vec3 gp, nrm;
+        if (j < j1) {
+          gp = V3(sx[j], sy[j], sz[j]);
+          // cheap frustum part first; unpack the normal only if the surfel lands in the image
+          const float z = K.T[8] * gp.x + K.T[9] * gp.y + K.T[10] * gp.z + K.T[11];
+          if (z > 0.f) {
+            nrm = UnpackNormal(__float_as_uint(sn[j]));
+            st = ProjectAssociate(cam, K.T, K.depth, K.depth_pitch, K.normals, K.normals_pitch, gp, nrm, &r);
+          }
+        }
+        n_inimg += __popc(__ballot_sync(0xffffffffu, st >= 1));
+        n_depthok += __popc(__ballot_sync(0xffffffffu, st >= 2));
+        const unsigned assoc_mask = __ballot_sync(0xffffffffu, st == 3);
+        if (assoc_mask == 0) continue;
+        touched |= assoc_mask;
+        if (st == 3) {
+          acc[27] += 1.f;
+          float J[6];
+          if (cam.use_depth) {
+            float inv_stddev;
+            Vec3 up;
+            const float raw = DepthResidual(cam, r, &inv_stddev, &up);
+            // kernel_opt_pose.cu:88-93
+            J[0] = inv_stddev * r.ln.x;
+            J[1] = inv_stddev * r.ln.y;
+            J[2] = inv_stddev * r.ln.z;
+            J[3] = inv_stddev * (-r.ln.y * up.z + r.ln.z * up.y);
+            J[4] = inv_stddev * (r.ln.x * up.z - r.ln.z * up.x);
+            J[5] = inv_stddev * (-r.ln.x * up.y + r.ln.y * up.x);
+            AccumulateHb(acc, J, raw, DepthWeight(raw));
+            acc[29] += DepthCost(raw);
+          }
+          if (cam.use_desc) {
+            float ccx, ccy;
+            if (DepthToColor(cam, r.pxf, r.pyf, &ccx, &ccy)) {
+              acc[28] += 1.f;
+              float t1x, t1y, t2x, t2y;
+              TangentProjections(cam, K.T, gp, nrm, sr[j], &t1x, &t1y, &t2x, &t2y);
+              DescEval e;
+              EvalDescriptor(K.tex, ccx, ccy, t1x, t1y, t2x, t2y, sd1[j], sd2[j], &e);
+              DescPoseJacobian(cam, r.lp, e.gx1, e.gy1, J);
+              AccumulateHb(acc, J, e.r1, DescWeight(e.r1));
+              DescPoseJacobian(cam, r.lp, e.gx2, e.gy2, J);
+              AccumulateHb(acc, J, e.r2, DescWeight(e.r2));
+              acc[30] += DescCost(e.r1);
+              acc[31] += DescCost(e.r2);
+            }
+          }
+        }
+      }
+
+      if (touched) {
+        const float total = WarpTransposeReduce(acc, lane);
+        atomicAdd(args.acc + static_cast<size_t>(kf) * kPoseAccSize + lane, static_cast<double>(total));
+      }
+      if (lane == 0 && n_inimg) {
+        atomicAdd(args.stage_counts + 2 * kf, static_cast<unsigned long long>(n_inimg));
+        if (n_depthok) atomicAdd(args.stage_counts + 2 * kf + 1, static_cast<unsigned long long>(n_depthok));
+      }
+    }
+    __syncthreads();   // every warp is done with stage s before it is refilled
+  }
+}
+
+template <int TILE>
+static void LaunchPoseAccumulateT(const PoseAccumulateArgs& args, int sm_count, cudaStream_t stream) {
+  const size_t smem = static_cast<size_t>(2) * kPoseStagedRows * TILE * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(PoseAccumulateKernel<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    configured = true;
+  }
+  const uint32_t n_tiles = (args.n + TILE - 1) / TILE;
+  const uint32_t grid = min(n_tiles, static_cast<uint32_t>(2 * sm_count));   // persistent: 2 CTAs per SM
+  PoseAccumulateKernel<TILE><<<grid, kPoseThreads, smem, stream>>>(args);
+}
+
+void LaunchPoseAccumulate(const PoseAccumulateArgs& args, int sm_count, cudaStream_t stream) {
+  if (args.n == 0) return;
+  // Pick the tile so that there are at least ~4 tiles per resident CTA (tail balance), but as large as possible
+  // (the warp-level reduction is paid once per (tile, keyframe)).
+  const uint64_t slots = static_cast<uint64_t>(2 * sm_count) * 4;
+  if (args.n >= slots * 1024) LaunchPoseAccumulateT<1024>(args, sm_count, stream);
+  else if (args.n >= slots * 512) LaunchPoseAccumulateT<512>(args, sm_count, stream);
+  else LaunchPoseAccumulateT<256>(args, sm_count, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Geometry step, surfel-major.
+
+constexpr int kGeoThreads = 256;
+
+template <bool DETERMINE, bool NORMALS>
+__global__ void __launch_bounds__(kGeoThreads) ActivationNormalsKernel(const __grid_constant__ GeometryArgs a) {
+  const uint32_t i = a.begin + blockIdx.x * kGeoThreads + threadIdx.x;
+  if (i >= a.end) return;
+  const uint8_t flags = a.active[i];
+  if (!DETERMINE && !(flags & kSurfelActiveFlag)) return;
+
+  const Vec3 gp = V3(a.surfels[static_cast<size_t>(kRowX) * a.pitch + i], a.surfels[static_cast<size_t>(kRowY) * a.pitch + i],
+                     a.surfels[static_cast<size_t>(kRowZ) * a.pitch + i]);
+  const Vec3 nrm = UnpackNormal(__float_as_uint(a.surfels[static_cast<size_t>(kRowNormal) * a.pitch + i]));
+
+  bool act = !DETERMINE;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  for (int j = 0; j < a.kf_count; ++j) {
+    const int kf = __ldg(a.kf_list + j);
+    KfRegs K;
+    LoadKf(a.kfs, kf, &K);
+    if (!NORMALS && K.activation != 0) continue;   // activation only looks at kActive keyframes
+    Assoc r;
+    const int st = ProjectAssociate(a.cam, K.T, K.depth, K.depth_pitch, K.normals, K.normals_pitch, gp, nrm, &r);
+    if (st == 3) {
+      if (K.activation == 0) act = true;
+      if (NORMALS) {
+        // kernel_opt_geometry.cu:545-553: global_R_frame * local normal, global_R_frame = R(frame_T_global)^T
+        const Vec3 ln = U16ToImageSpaceNormal(r.kf_normal);
+        s0 += K.T[0] * ln.x + K.T[4] * ln.y + K.T[8] * ln.z;
+        s1 += K.T[1] * ln.x + K.T[5] * ln.y + K.T[9] * ln.z;
+        s2 += K.T[2] * ln.x + K.T[6] * ln.y + K.T[10] * ln.z;
+        s3 += 1.f;
+      } else if (act) {
+        break;
+      }
+    }
+  }
+  if (DETERMINE) a.active[i] = act ? kSurfelActiveFlag : static_cast<uint8_t>(flags & ~kSurfelActiveFlag);
+  if (NORMALS && act && s3 >= 1.f) {
+    // kernel_opt_geometry.cu:577-597: the mean is packed without re-normalisation
+    const float inv = 1.f / s3;
+    a.surfels[static_cast<size_t>(kRowNormal) * a.pitch + i] = __uint_as_float(PackNormal(V3(inv * s0, inv * s1, inv * s2)));
+  }
+}
+
+void LaunchActivationAndNormals(const GeometryArgs& a, bool determine_activation, bool update_normals, cudaStream_t stream) {
+  if (a.end <= a.begin) return;
+  const uint32_t grid = (a.end - a.begin + kGeoThreads - 1) / kGeoThreads;
+  if (determine_activation && update_normals) ActivationNormalsKernel<true, true><<<grid, kGeoThreads, 0, stream>>>(a);
+  else if (determine_activation) ActivationNormalsKernel<true, false><<<grid, kGeoThreads, 0, stream>>>(a);
+  else if (update_normals) ActivationNormalsKernel<false, true><<<grid, kGeoThreads, 0, stream>>>(a);
+}
+
+template <bool USE_DEPTH, bool USE_DESC>
+__global__ void __launch_bounds__(kGeoThreads) PositionDescriptorKernel(const __grid_constant__ GeometryArgs a) {
+  const uint32_t i = a.begin + blockIdx.x * kGeoThreads + threadIdx.x;
+  if (i >= a.end) return;
+  if (!(a.active[i] & kSurfelActiveFlag)) return;
+  const size_t P = a.pitch;
+  const Vec3 gp = V3(a.surfels[kRowX * P + i], a.surfels[kRowY * P + i], a.surfels[kRowZ * P + i]);
+  const Vec3 nrm = UnpackNormal(__float_as_uint(a.surfels[kRowNormal * P + i]));
+  float radius_sq = 0.f, d1 = 0.f, d2 = 0.f;
+  if (USE_DESC) {
+    radius_sq = a.surfels[kRowRadiusSq * P + i];
+    d1 = a.surfels[kRowD1 * P + i];
+    d2 = a.surfels[kRowD2 * P + i];
+  }
+  // 3x3 normal equations over (t along normal, d1, d2): H00 H01 H02 H11 H12 H22 | b0 b1 b2
+  float H00 = 0.f, H01 = 0.f, H02 = 0.f, H11 = 0.f, H22 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+  const float H12 = 0.f;   // never accumulated by the reference either (kernel_opt_geometry.cu:216-227)
+
+  for (int j = 0; j < a.kf_count; ++j) {
+    const int kf = __ldg(a.kf_list + j);
+    KfRegs K;
+    LoadKf(a.kfs, kf, &K);
+    Assoc r;
+    if (ProjectAssociate(a.cam, K.T, K.depth, K.depth_pitch, K.normals, K.normals_pitch, gp, nrm, &r) != 3) continue;
+    if (USE_DEPTH) {
+      float inv_stddev;
+      Vec3 up;
+      const float raw = DepthResidual(a.cam, r, &inv_stddev, &up);
+      const float jac = -inv_stddev;   // kernel_opt_geometry.cu:138
+      const float w = DepthWeight(raw);
+      if (USE_DESC) {
+        H00 += w * jac * jac;
+        b0 += w * raw * jac;
+      } else {
+        // kernel_opt_geometry.cu:452-456
+        const float wj = w * jac;
+        H00 += wj * jac;
+        b0 += wj * raw;
+      }
+    }
+    if (USE_DESC) {
+      float ccx, ccy;
+      if (DepthToColor(a.cam, r.pxf, r.pyf, &ccx, &ccy)) {
+        float t1x, t1y, t2x, t2y;
+        TangentProjections(a.cam, K.T, gp, nrm, radius_sq, &t1x, &t1y, &t2x, &t2y);
+        DescEval e;
+        EvalDescriptor(K.tex, ccx, ccy, t1x, t1y, t2x, t2y, d1, d2, &e);
+        // kernel_opt_geometry.cu:176-181
+        const float term1 = -a.cam.cfx * (r.ln.x * r.lp.z - r.ln.z * r.lp.x);
+        const float term2 = -a.cam.cfy * (r.ln.y * r.lp.z - r.ln.z * r.lp.y);
+        const float term3 = 1.f / (r.lp.z * r.lp.z);
+        const float j1 = -(e.gx1 * term1 + e.gy1 * term2) * term3;
+        const float j2 = -(e.gx2 * term1 + e.gy2 * term2) * term3;
+        constexpr float jd = -1.f;
+        const float w1 = DescWeight(e.r1), wr1 = w1 * e.r1;
+        const float w2 = DescWeight(e.r2), wr2 = w2 * e.r2;
+        H00 += w1 * j1 * j1 + w2 * j2 * j2;
+        H01 += w1 * j1 * jd;
+        H11 += w1 * jd * jd;
+        b0 += wr1 * j1 + wr2 * j2;
+        b1 += wr1 * jd;
+        H02 += w2 * j2 * jd;
+        H22 += w2 * jd * jd;
+        b2 += wr2 * jd;
+      }
+    }
+  }
+
+  if (!USE_DESC) {
+    // UpdateSurfelPositionCUDAKernel, kernel_opt_geometry.cu:487-507
+    if (H00 > 1e-6f) {
+      const float t = -1.f * b0 / H00;
+      a.surfels[kRowX * P + i] = gp.x + t * nrm.x;
+      a.surfels[kRowY * P + i] = gp.y + t * nrm.y;
+      a.surfels[kRowZ * P + i] = gp.z + t * nrm.z;
+    }
+    return;
+  }
+  // UpdateSurfelPositionAndDescriptorCUDAKernel, kernel_opt_geometry.cu:273-361 (in-place Cholesky)
+  constexpr float kEpsilon = 1e-6f;
+  float L00 = sqrtf(H00 + kEpsilon);
+  float L01 = H01 / L00;
+  float L11 = sqrtf((H11 + kEpsilon) - L01 * L01);
+  float L02 = H02 / L00;
+  float L12 = (H12 - L02 * L01) / L11;
+  float L22 = sqrtf((H22 + kEpsilon) - L02 * L02 - L12 * L12);
+  const float y0 = b0 / L00;
+  const float y1 = (b1 - L01 * y0) / L11;
+  const float y2 = (b2 - L02 * y0 - L12 * y1) / L22;
+  const float x2 = y2 / L22;
+  const float x1 = (y1 - L12 * x2) / L11;
+  const float x0 = (y0 - L02 * x2 - L01 * x1) / L00;
+  if (x0 != 0) {
+    a.surfels[kRowX * P + i] = gp.x - x0 * nrm.x;
+    a.surfels[kRowY * P + i] = gp.y - x0 * nrm.y;
+    a.surfels[kRowZ * P + i] = gp.z - x0 * nrm.z;
+  }
+  if (x1 != 0) a.surfels[kRowD1 * P + i] = fmaxf(-180.f, fminf(180.f, d1 - x1));
+  if (x2 != 0) a.surfels[kRowD2 * P + i] = fmaxf(-180.f, fminf(180.f, d2 - x2));
+}
+
+void LaunchPositionAndDescriptor(const GeometryArgs& a, cudaStream_t stream) {
+  if (a.end <= a.begin) return;
+  const uint32_t grid = (a.end - a.begin + kGeoThreads - 1) / kGeoThreads;
+  if (a.cam.use_desc) {
+    if (a.cam.use_depth) PositionDescriptorKernel<true, true><<<grid, kGeoThreads, 0, stream>>>(a);
+    else PositionDescriptorKernel<false, true><<<grid, kGeoThreads, 0, stream>>>(a);
+  } else {
+    PositionDescriptorKernel<true, false><<<grid, kGeoThreads, 0, stream>>>(a);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// uchar4 (.w = luma, cuda_image_processing.cu:165-176) -> dense u8 luma plane.  128-bit loads: 4 pixels per thread.
+
+__global__ void __launch_bounds__(256) ExtractLumaKernel(const uint8_t* __restrict__ rgba, size_t rgba_pitch,
+                                                         uint8_t* __restrict__ luma, size_t luma_pitch, int w, int h) {
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y = blockIdx.y;
+  if (x4 >= w || y >= h) return;
+  const uint8_t* src = rgba + static_cast<size_t>(y) * rgba_pitch + static_cast<size_t>(x4) * 4;
+  uint8_t* dst = luma + static_cast<size_t>(y) * luma_pitch + x4;
+  if (x4 + 3 < w && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
+    const uint32_t packed = (v.x >> 24) | ((v.y >> 24) << 8) | ((v.z >> 24) << 16) | ((v.w >> 24) << 24);
+    *reinterpret_cast<uint32_t*>(dst) = packed;
+  } else {
+    for (int k = 0; k < 4 && x4 + k < w; ++k) dst[k] = src[4 * k + 3];
+  }
+}
+
+void LaunchExtractLuma(const uint8_t* rgba, size_t rgba_pitch, uint8_t* luma, size_t luma_pitch, int w, int h, cudaStream_t stream) {
+  dim3 block(256);
+  dim3 grid((w / 4 + 255) / 256 + 1, h);
+  ExtractLumaKernel<<<grid, block, 0, stream>>>(rgba, rgba_pitch, luma, luma_pitch, w, h);
+}
+
+}  // namespace bba

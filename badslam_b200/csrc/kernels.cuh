@@ -1,0 +1,71 @@
+// kernels.cuh -- launch interface between the host orchestration (badba.cu) and the sm_100a kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_math.cuh"
+
+namespace bba {
+
+// Accumulator record per keyframe written by the pose kernel: 32 fp64 sums
+//   [0..20] H upper triangle row-major, [21..26] b, [27] n_assoc, [28] n_photo,
+//   [29] cost_depth, [30] cost_desc1, [31] cost_desc2
+// followed (separately) by 2 u64 stage counters {n_inimg, n_depthok} for the byte model.
+constexpr int kPoseAccSize = 32;
+
+struct PoseAccumulateArgs {
+  CameraParams cam;
+  const float* surfels;      // 17-row SoA
+  uint32_t pitch;            // floats per row
+  uint32_t n;                // surfels_size
+  const KfDevice* kfs;
+  const int* work_list;      // keyframe ids to evaluate
+  const int* work_count;     // device scalar
+  double* acc;               // [max_kf][32]
+  unsigned long long* stage_counts;  // [max_kf][2]
+};
+
+// Persistent, TMA-staged pose residual/Jacobian/Hessian kernel (AccumulatePoseEstimationCoeffsCUDAKernel,
+// kernel_opt_pose.cu:251-383, for a whole list of keyframes in one launch).
+void LaunchPoseAccumulate(const PoseAccumulateArgs& args, int sm_count, cudaStream_t stream);
+
+struct PoseSolveArgs {
+  KfDevice* kfs;
+  float* pose_est;             // [max_kf][7] global_T_frame estimates, updated in place
+  double* acc;                 // consumed and re-zeroed
+  unsigned long long* stage_counts;
+  const int* work_in;          // list consumed by this iteration
+  const int* count_in;
+  int* work_out;               // list of keyframes that need another iteration
+  int* count_out;
+  int* iterations;             // [max_kf]
+  int* converged;              // [max_kf]
+  double* first_stats;         // [max_kf][8]: n_assoc n_photo cost_depth cost_desc1 cost_desc2 n_inimg n_depthok (iteration 0)
+  int iteration;
+  int max_iterations;
+};
+// Device-side Gauss-Newton step for every keyframe in the list (direct_ba_alternating.cc:173-233).
+void LaunchPoseSolve(const PoseSolveArgs& args, cudaStream_t stream);
+
+struct GeometryArgs {
+  CameraParams cam;
+  float* surfels;
+  uint32_t pitch;
+  uint32_t n;
+  uint32_t begin, end;         // surfel range processed by this rank
+  uint8_t* active;
+  const KfDevice* kfs;
+  const int* kf_list;          // non-inactive keyframes (ascending ids)
+  int kf_count;
+};
+// SetSurfelInactive + DetermineActiveSurfels (kernel_surfel_activation.cu:38-79) fused with the normal
+// accumulation + update (kernel_opt_geometry.cu:527-597).
+void LaunchActivationAndNormals(const GeometryArgs& args, bool determine_activation, bool update_normals, cudaStream_t stream);
+// Position (+ descriptor) accumulation and per-surfel solve (kernel_opt_geometry.cu:118-231,273-361 or :417-507).
+void LaunchPositionAndDescriptor(const GeometryArgs& args, cudaStream_t stream);
+
+// uchar4 (.w = luma) -> u8 plane.
+void LaunchExtractLuma(const uint8_t* rgba, size_t rgba_pitch, uint8_t* luma, size_t luma_pitch, int w, int h, cudaStream_t stream);
+
+}  // namespace bba

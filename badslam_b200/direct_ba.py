@@ -1,0 +1,369 @@
+"""Host-side mirror of the reference's `DirectBA` / `Keyframe` interface on top of the C ABI.
+
+Same names, argument meaning and error behaviour as
+applications/badslam/src/badslam/direct_ba.h:65-550 and keyframe.h:50-237, so the parity tests
+read like the reference's own tests (test/test_*_optimization_*.cc).  PyTorch is used only for
+device memory and streams; every computation happens inside libbadba_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import BadBAError
+
+
+@dataclass
+class PinholeCamera4f:
+    """libvis PinholeCamera4f (libvis/src/libvis/camera.h:1005-1056): fx, fy, cx, cy in pixel-corner convention."""
+    width: int
+    height: int
+    parameters: np.ndarray
+
+    def __post_init__(self):
+        self.parameters = np.asarray(self.parameters, dtype=np.float32).copy()
+
+
+def _as_u16(t: torch.Tensor) -> torch.Tensor:
+    assert t.dtype in (torch.uint16, torch.int16), t.dtype
+    return t
+
+
+class Keyframe:
+    """Mirror of vis::Keyframe's buffer-taking constructor (keyframe.cc:41-79): owns the device buffers."""
+
+    def __init__(self, frame_index: int, min_depth: float, max_depth: float,
+                 depth_buffer: torch.Tensor, normals_buffer: torch.Tensor, radius_buffer: torch.Tensor,
+                 color_buffer: torch.Tensor, global_T_frame):
+        self.frame_index = frame_index
+        self.min_depth = float(min_depth)
+        self.max_depth = float(max_depth)
+        self.depth_buffer = _as_u16(depth_buffer)          # [h, w] u16
+        self.normals_buffer = _as_u16(normals_buffer)      # [h, w] u16
+        self.radius_buffer = _as_u16(radius_buffer)        # [h, w] u16
+        self.color_buffer = color_buffer                   # [h, w, 4] u8
+        self._global_T_frame = np.asarray(global_T_frame, dtype=np.float32).copy()
+        self.id = -1
+        self._ba: Optional["DirectBA"] = None
+
+    @classmethod
+    def from_host(cls, frame_index, depth, normals, radius, color, global_T_frame, min_depth, max_depth, device):
+        def up(a, dt):
+            return torch.from_numpy(np.ascontiguousarray(a).view(dt)).to(device)
+        return cls(frame_index, min_depth, max_depth, up(depth, np.int16).view(torch.uint16),
+                   up(normals, np.int16).view(torch.uint16), up(radius, np.int16).view(torch.uint16),
+                   torch.from_numpy(np.ascontiguousarray(color)).to(device), global_T_frame)
+
+    def global_T_frame(self) -> np.ndarray:
+        if self._ba is not None:
+            return self._ba._get_pose(self.id)
+        return self._global_T_frame.copy()
+
+    def set_global_T_frame(self, pose):
+        self._global_T_frame = np.asarray(pose, dtype=np.float32).copy()
+        if self._ba is not None:
+            self._ba._set_pose(self.id, self._global_T_frame)
+
+    def activation(self) -> int:
+        return self._ba._get_activation(self.id) if self._ba is not None else 0
+
+    def SetActivation(self, activation: int):
+        self._ba._set_activation(self.id, activation)
+
+
+@dataclass
+class BAResult:
+    iterations_done: int
+    converged: bool
+    depth_residual_count: int
+    descriptor_residual_count: int
+    cost: float
+    pose_iterations_total: int
+    ms_surfel_activation: float
+    ms_geometry_optimization: float
+    ms_pose_optimization: float
+    ms_intrinsics_optimization: float
+    kernel_launches: int
+
+    @property
+    def residual_count(self):
+        return self.depth_residual_count + self.descriptor_residual_count
+
+
+class DirectBA:
+    """Drop-in for vis::DirectBA (direct_ba.h:65-550) backed by the sm_100a library."""
+
+    def __init__(self, max_surfel_count: int, raw_to_float_depth: float, baseline_fx: float,
+                 sparse_surfel_cell_size: int, surfel_merge_dist_factor: float = 0.8,
+                 min_observation_count_while_bootstrapping_1: int = 1,
+                 min_observation_count_while_bootstrapping_2: int = 2, min_observation_count: int = 3,
+                 color_camera_initial_estimate: PinholeCamera4f = None,
+                 depth_camera_initial_estimate: PinholeCamera4f = None, pyramid_level_for_color: int = 0,
+                 use_depth_residuals: bool = True, use_descriptor_residuals: bool = True,
+                 render_window=None, global_T_anchor_frame=None, *, device=None, max_keyframes: int = 1024,
+                 rank: int = 0, world_size: int = 1):
+        if not torch.cuda.is_available():
+            raise BadBAError(_lib.ERR_NO_DEVICE, "no CUDA device: libbadba_b200 has no CPU fallback")
+        self._lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.surfel_merge_dist_factor = surfel_merge_dist_factor
+        self.min_observation_counts = (min_observation_count_while_bootstrapping_1,
+                                       min_observation_count_while_bootstrapping_2, min_observation_count)
+        cc, dc = color_camera_initial_estimate, depth_camera_initial_estimate
+        cfg = _lib.Config()
+        cfg.depth_width, cfg.depth_height = dc.width, dc.height
+        cfg.color_width, cfg.color_height = cc.width, cc.height
+        cfg.depth_intrinsics[:] = [float(v) for v in dc.parameters]
+        cfg.color_intrinsics[:] = [float(v) for v in cc.parameters]
+        cfg.raw_to_float_depth = raw_to_float_depth
+        cfg.baseline_fx = baseline_fx
+        cfg.sparse_surfel_cell_size = int(sparse_surfel_cell_size)
+        cfg.max_surfel_count = int(max_surfel_count)
+        cfg.max_keyframes = int(max_keyframes)
+        cfg.use_depth_residuals = int(use_depth_residuals)
+        cfg.use_descriptor_residuals = int(use_descriptor_residuals)
+        cfg.device = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        cfg.rank, cfg.world_size = rank, world_size
+        self._cfg = cfg
+        self._h = C.c_void_p()
+        st = self._lib.bba_create(C.byref(cfg), C.byref(self._h))
+        if st != _lib.OK:
+            raise BadBAError(st, "bba_create failed")
+        self._keyframes: List[Keyframe] = []
+        self._surfels: Optional[torch.Tensor] = None
+        self._active: Optional[torch.Tensor] = None
+        self._allgather_cb = None
+        self.depth_width, self.depth_height = dc.width, dc.height
+        self.color_width, self.color_height = cc.width, cc.height
+
+    # -- plumbing -------------------------------------------------------------------------------
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._h.value:
+                self._lib.bba_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def close(self):
+        self.__del__()
+
+    def _check(self, st):
+        if st != _lib.OK:
+            raise BadBAError(st, self._lib.bba_last_error(self._h).decode())
+
+    @staticmethod
+    def _stream_ptr(stream):
+        if stream is None:
+            stream = torch.cuda.current_stream()
+        if isinstance(stream, torch.cuda.Stream):
+            return C.c_void_p(stream.cuda_stream)
+        return C.c_void_p(int(stream))
+
+    def _get_pose(self, kf_id):
+        p = np.zeros(7, np.float32)
+        self._check(self._lib.bba_get_keyframe_pose(self._h, kf_id, p.ctypes.data_as(C.POINTER(C.c_float))))
+        return p
+
+    def _set_pose(self, kf_id, pose):
+        p = np.ascontiguousarray(pose, np.float32)
+        self._check(self._lib.bba_set_keyframe_pose(self._h, kf_id, p.ctypes.data_as(C.POINTER(C.c_float))))
+
+    def _get_activation(self, kf_id):
+        a = C.c_int()
+        self._check(self._lib.bba_get_keyframe_activation(self._h, kf_id, C.byref(a)))
+        return a.value
+
+    def _set_activation(self, kf_id, a):
+        self._check(self._lib.bba_set_keyframe_activation(self._h, kf_id, int(a)))
+
+    # -- scene model (direct_ba.h:95-121, 243-377) ------------------------------------------------
+    def AddKeyframe(self, keyframe: Keyframe, stream=None) -> int:
+        kf = keyframe
+        out = C.c_int(-1)
+        pose = np.ascontiguousarray(kf._global_T_frame, np.float32)
+        self._check(self._lib.bba_add_keyframe(
+            self._h,
+            kf.depth_buffer.data_ptr(), kf.depth_buffer.stride(0) * 2,
+            kf.normals_buffer.data_ptr(), kf.normals_buffer.stride(0) * 2,
+            kf.radius_buffer.data_ptr(), kf.radius_buffer.stride(0) * 2,
+            kf.color_buffer.data_ptr(), kf.color_buffer.stride(0),
+            pose.ctypes.data_as(C.POINTER(C.c_float)), kf.min_depth, kf.max_depth,
+            self._stream_ptr(stream), C.byref(out)))
+        kf.id = out.value
+        kf._ba = self
+        self._keyframes.append(kf)
+        return kf.id
+
+    def keyframes(self) -> List[Keyframe]:
+        return self._keyframes
+
+    def SetSurfels(self, surfels: torch.Tensor, surfels_size: int, active: Optional[torch.Tensor] = None):
+        """surfels_: [17, pitch] float32 CUDA tensor (kernels.cuh:69-93), used in place."""
+        assert surfels.is_cuda and surfels.dtype == torch.float32 and surfels.shape[0] == 17
+        if active is None:
+            active = torch.zeros(max(int(surfels.shape[1]), 1), dtype=torch.uint8, device=surfels.device)
+        self._surfels, self._active = surfels, active
+        self._check(self._lib.bba_set_surfels(self._h, surfels.data_ptr(), surfels.stride(0) * 4, int(surfels_size)))
+        self._check(self._lib.bba_set_active_flags(self._h, active.data_ptr()))
+
+    def SetSurfelsHost(self, surfels: np.ndarray, surfels_size: int, stream=None):
+        s = np.ascontiguousarray(surfels, np.float32)
+        self._check(self._lib.bba_set_surfels_host(self._h, s.ctypes.data, s.strides[0], int(surfels_size),
+                                                   self._stream_ptr(stream)))
+
+    def surfels(self) -> torch.Tensor:
+        return self._surfels
+
+    def active_surfels(self) -> torch.Tensor:
+        return self._active
+
+    def surfels_size(self) -> int:
+        n = C.c_uint32()
+        self._check(self._lib.bba_get_surfels_device(self._h, None, None, C.byref(n)))
+        return n.value
+
+    def GetSurfelsHost(self, rows: int = 8, stream=None) -> np.ndarray:
+        n = self.surfels_size()
+        out = np.zeros((rows, max(n, 1)), np.float32)
+        self._check(self._lib.bba_get_surfels_host(self._h, out.ctypes.data, out.strides[0], rows, self._stream_ptr(stream)))
+        return out[:, :n]
+
+    def GetActiveHost(self, stream=None) -> np.ndarray:
+        n = self.surfels_size()
+        out = np.zeros(max(n, 1), np.uint8)
+        self._check(self._lib.bba_get_active_flags_host(self._h, out.ctypes.data, self._stream_ptr(stream)))
+        return out[:n]
+
+    def _intrinsics(self):
+        d = (C.c_float * 4)()
+        c = (C.c_float * 4)()
+        a = C.c_float()
+        self._check(self._lib.bba_get_intrinsics(self._h, d, c, C.byref(a)))
+        return np.array(d[:], np.float32), np.array(c[:], np.float32), a.value
+
+    def depth_camera(self) -> PinholeCamera4f:
+        return PinholeCamera4f(self.depth_width, self.depth_height, self._intrinsics()[0])
+
+    def color_camera(self) -> PinholeCamera4f:
+        return PinholeCamera4f(self.color_width, self.color_height, self._intrinsics()[1])
+
+    def a(self) -> float:
+        return self._intrinsics()[2]
+
+    def SetColorCamera(self, camera: PinholeCamera4f):
+        d, _, a = self._intrinsics()
+        self._set_intrinsics(d, camera.parameters, a)
+
+    def SetDepthCamera(self, camera: PinholeCamera4f):
+        _, c, a = self._intrinsics()
+        self._set_intrinsics(camera.parameters, c, a)
+
+    def SetA(self, a: float):
+        d, c, _ = self._intrinsics()
+        self._set_intrinsics(d, c, a)
+
+    def _set_intrinsics(self, d, c, a):
+        d = np.ascontiguousarray(d, np.float32)
+        c = np.ascontiguousarray(c, np.float32)
+        self._check(self._lib.bba_set_intrinsics(self._h, d.ctypes.data_as(C.POINTER(C.c_float)),
+                                                 c.ctypes.data_as(C.POINTER(C.c_float)), float(a)))
+
+    def cfactor_buffer(self, stream=None) -> np.ndarray:
+        w, h = C.c_int(), C.c_int()
+        self._check(self._lib.bba_cfactor_size(self._h, C.byref(w), C.byref(h)))
+        out = np.zeros((h.value, w.value), np.float32)
+        self._check(self._lib.bba_get_cfactor_host(self._h, out.ctypes.data, self._stream_ptr(stream)))
+        return out
+
+    def SetCFactorBuffer(self, cfactor: np.ndarray, stream=None):
+        c = np.ascontiguousarray(cfactor, np.float32)
+        self._check(self._lib.bba_set_cfactor_host(self._h, c.ctypes.data, self._stream_ptr(stream)))
+
+    def covisibility(self) -> np.ndarray:
+        K = len(self._keyframes)
+        out = np.zeros((K, K), np.uint8)
+        for k in range(K):
+            self._check(self._lib.bba_get_covisibility(self._h, k, out[k].ctypes.data))
+        return out
+
+    # -- hot path ---------------------------------------------------------------------------------
+    def AccumulatePoseEstimationCoeffs(self, keyframe_id: int, global_T_frame_estimate, stream=None):
+        """kernels.h:156-174 AccumulatePoseEstimationCoeffsCUDA (debug = true)."""
+        p = np.ascontiguousarray(global_T_frame_estimate, np.float32)
+        out = _lib.PoseCoeffs()
+        self._check(self._lib.bba_accumulate_pose_coeffs(self._h, keyframe_id, p.ctypes.data_as(C.POINTER(C.c_float)),
+                                                         C.byref(out), self._stream_ptr(stream)))
+        return out
+
+    def EstimateFramePose(self, stream, global_T_frame_initial_estimate, keyframe_id: int):
+        """direct_ba.h:122-129; returns (global_T_frame_estimate, iterations, converged)."""
+        p = np.ascontiguousarray(global_T_frame_initial_estimate, np.float32)
+        out = np.zeros(7, np.float32)
+        it, conv = C.c_int(), C.c_int()
+        self._check(self._lib.bba_estimate_frame_pose(self._h, keyframe_id, p.ctypes.data_as(C.POINTER(C.c_float)),
+                                                      out.ctypes.data_as(C.POINTER(C.c_float)), C.byref(it), C.byref(conv),
+                                                      self._stream_ptr(stream)))
+        return out, it.value, bool(conv.value)
+
+    def UpdateSurfelActivation(self, stream=None):
+        self._check(self._lib.bba_update_surfel_activation(self._h, self._stream_ptr(stream)))
+
+    def OptimizeGeometryIteration(self, stream=None):
+        self._check(self._lib.bba_optimize_geometry_iteration(self._h, self._stream_ptr(stream)))
+
+    def OptimizeIntrinsics(self, optimize_depth_intrinsics: bool, optimize_color_intrinsics: bool, stream=None):
+        self._check(self._lib.bba_optimize_intrinsics(self._h, int(optimize_depth_intrinsics),
+                                                      int(optimize_color_intrinsics), self._stream_ptr(stream)))
+
+    def BundleAdjustment(self, stream, optimize_depth_intrinsics: bool, optimize_color_intrinsics: bool,
+                         do_surfel_updates: bool, optimize_poses: bool, optimize_geometry: bool,
+                         min_iterations: int, max_iterations: int, use_pcg: bool = False,
+                         active_keyframe_window_start: int = 0, active_keyframe_window_end: int = -1,
+                         increase_ba_iteration_count: bool = True, time_limit: float = 0.0) -> BAResult:
+        """direct_ba.h:143-162."""
+        if active_keyframe_window_end < 0:
+            active_keyframe_window_end = len(self._keyframes) - 1
+        o = _lib.BAOptions(int(optimize_depth_intrinsics), int(optimize_color_intrinsics), int(do_surfel_updates),
+                           int(optimize_poses), int(optimize_geometry), int(min_iterations), int(max_iterations),
+                           int(use_pcg), int(active_keyframe_window_start), int(active_keyframe_window_end),
+                           int(increase_ba_iteration_count), float(time_limit))
+        r = _lib.BAResult()
+        self._check(self._lib.bba_bundle_adjust(self._h, C.byref(o), C.byref(r), self._stream_ptr(stream)))
+        return BAResult(r.iterations_done, bool(r.converged), r.depth_residual_count, r.descriptor_residual_count,
+                        r.cost, r.pose_iterations_total, r.ms_surfel_activation, r.ms_geometry_optimization,
+                        r.ms_pose_optimization, r.ms_intrinsics_optimization, r.kernel_launches)
+
+    def kernel_launch_count(self) -> int:
+        return int(self._lib.bba_kernel_launch_count(self._h))
+
+    # -- convenience: build from a synthetic scene ---------------------------------------------------
+    @classmethod
+    def from_scene(cls, scene, poses=None, use_depth_residuals=True, use_descriptor_residuals=True,
+                   device=None, max_keyframes=None, **kw):
+        cfg = scene.cfg
+        cam_d = PinholeCamera4f(cfg.width, cfg.height, scene.depth_K)
+        cam_c = PinholeCamera4f(cfg.width, cfg.height, scene.color_K)
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        ba = cls(max_surfel_count=scene.pitch, raw_to_float_depth=cfg.raw_to_float_depth, baseline_fx=cfg.baseline_fx,
+                 sparse_surfel_cell_size=cfg.cell, color_camera_initial_estimate=cam_c,
+                 depth_camera_initial_estimate=cam_d, use_depth_residuals=use_depth_residuals,
+                 use_descriptor_residuals=use_descriptor_residuals, device=device,
+                 max_keyframes=max_keyframes or max(cfg.num_keyframes, 1), **kw)
+        poses = scene.poses_init if poses is None else poses
+        for k in range(cfg.num_keyframes):
+            kf = Keyframe.from_host(k, scene.depth[k], scene.normals[k], scene.radius[k], scene.color[k], poses[k],
+                                    scene.min_depth[k], scene.max_depth[k], device)
+            ba.AddKeyframe(kf)
+        surf = torch.from_numpy(scene.surfels).to(device)
+        ba.SetSurfels(surf, scene.num_surfels)
+        if scene.depth_a != 0.0:
+            ba.SetA(scene.depth_a)
+        if np.any(scene.cfactor != 0):
+            ba.SetCFactorBuffer(scene.cfactor)
+        return ba

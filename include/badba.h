@@ -1,0 +1,186 @@
+/* include/badba.h -- C ABI of libbadba_b200.so, the Blackwell (sm_100a) direct
+ * bundle-adjustment backend that drops in behind ETH3D/badslam's DirectBA.
+ *
+ * The reference has no FFI layer: its seam is the C++ class `DirectBA`
+ * (applications/badslam/src/badslam/direct_ba.h:65-550) on top of the free functions of
+ * applications/badslam/src/badslam/kernels.h:94-495.  Every entry point below names the
+ * reference interface it replaces.  The header-only C++ adaptor include/badba_direct_ba.hpp
+ * keeps the reference's own signatures on top of this ABI.
+ *
+ * Conventions (mirroring SURVEY.md 8b):
+ *  - plain pointers and sizes only; no C++/torch types cross the boundary;
+ *  - device pointers are CALLER-OWNED and are NOT copied unless the function name ends in
+ *    `_host` (those copy from host memory into library-owned device memory);
+ *  - a pitched 2-D device buffer is (pointer, pitch in BYTES), i.e. the fields of the
+ *    reference's CUDABuffer_<T> (libvis/src/libvis/cuda/cuda_buffer.cuh:112-118);
+ *  - poses are float[7] = {qx,qy,qz,qw,tx,ty,tz} = Sophus::SE3f::data() of global_T_frame;
+ *  - every call is stream-ordered on the cudaStream_t passed as `void* stream` (0 = default
+ *    stream); calls that return host scalars synchronise that stream before returning, like
+ *    the reference (kernel_opt_pose.cc:96, kernel_opt_intrinsics.cc:136,263);
+ *  - one in-flight call per handle (DirectBA::Mutex(), direct_ba.h:196-208);
+ *  - errors are status codes + bba_last_error(); nothing aborts (the reference LOG(FATAL)s,
+ *    libvis/src/libvis/cuda/cuda_util.h:35-49) and nothing falls back to a CPU path.
+ */
+#ifndef BADBA_H
+#define BADBA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BBA_ABI_VERSION 1
+
+typedef struct bba_context* bba_handle;
+
+typedef enum {
+  BBA_OK = 0,
+  BBA_ERR_INVALID_ARGUMENT = 1,
+  BBA_ERR_CUDA = 2,
+  BBA_ERR_STATE = 3,
+  BBA_ERR_UNSUPPORTED = 4,
+  BBA_ERR_NO_DEVICE = 5
+} bba_status;
+
+/* Keyframe::Activation (keyframe.h:54-67) */
+typedef enum { BBA_KF_ACTIVE = 0, BBA_KF_COVISIBLE_ACTIVE = 1, BBA_KF_INACTIVE = 2 } bba_kf_activation;
+
+/* DirectBA constructor arguments (direct_ba.h:73-88, direct_ba.cc:74-163). */
+typedef struct {
+  int depth_width, depth_height;
+  int color_width, color_height;
+  float depth_intrinsics[4];   /* fx, fy, cx, cy: PinholeCamera4f::parameters(), pixel-corner convention */
+  float color_intrinsics[4];
+  float raw_to_float_depth;
+  float baseline_fx;
+  int sparse_surfel_cell_size;
+  uint32_t max_surfel_count;
+  int max_keyframes;
+  int use_depth_residuals;
+  int use_descriptor_residuals;
+  int device;                  /* CUDA device ordinal this handle lives on */
+  int rank, world_size;        /* position in a one-process-per-GPU job (world_size 1 = single GPU) */
+} bba_config;
+
+/* Arguments of DirectBA::BundleAdjustment (direct_ba.h:143-162). */
+typedef struct {
+  int optimize_depth_intrinsics;
+  int optimize_color_intrinsics;
+  int do_surfel_updates;
+  int optimize_poses;
+  int optimize_geometry;
+  int min_iterations;
+  int max_iterations;
+  int use_pcg;
+  int active_keyframe_window_start;
+  int active_keyframe_window_end;
+  int increase_ba_iteration_count;
+  double time_limit_seconds;   /* 0 = none (direct_ba_alternating.cc:704-709) */
+} bba_ba_options;
+
+typedef struct {
+  int iterations_done;
+  int converged;
+  /* residual bookkeeping of the LAST executed iteration's pose step, taken at its starting state
+   * (what the reference's debug counters report, kernel_opt_pose.cu:224-248) */
+  uint64_t depth_residual_count;       /* associated (surfel, keyframe) pairs */
+  uint64_t descriptor_residual_count;  /* 2 x pairs whose colour pixel is in bounds */
+  double cost;                         /* sum Tukey(depth) + sum Huber(descriptor 1), reference convention */
+  int pose_iterations_total;           /* Gauss-Newton iterations summed over keyframes and outer iterations */
+  /* per-stage device time of the last iteration, reference stage names
+   * (direct_ba_alternating.cc:629-689) */
+  float ms_surfel_activation;
+  float ms_geometry_optimization;
+  float ms_pose_optimization;
+  float ms_intrinsics_optimization;
+  uint64_t kernel_launches;            /* kernels this call launched */
+} bba_ba_result;
+
+/* Counters of one pose pass (superset of kernel_opt_pose.cu's debug outputs; the n_* feed the
+ * algorithmic-bytes model of SURVEY.md 8d). */
+typedef struct {
+  float H[21];
+  float b[6];
+  uint64_t n_pair, n_inimg, n_depthok, n_assoc, n_photo;
+  double cost_depth, cost_desc1, cost_desc2;
+} bba_pose_coeffs;
+
+typedef void (*bba_allgather_fn)(void* user, void* device_buffer, size_t bytes_per_rank, void* stream);
+
+/* ---- lifetime ---- */
+int         bba_abi_version(void);
+bba_status  bba_create(const bba_config* config, bba_handle* out);           /* DirectBA::DirectBA  direct_ba.cc:74 */
+void        bba_destroy(bba_handle h);                                        /* DirectBA::~DirectBA direct_ba.cc:165 */
+const char* bba_last_error(bba_handle h);                                     /* replaces LOG(FATAL) */
+
+/* ---- scene model ---- */
+/* surfels_ / surfels_size_ (direct_ba.cc:122, accessors direct_ba.h:300-340): 17-row pitched SoA. */
+bba_status bba_set_surfels(bba_handle h, float* device_surfels, size_t pitch_bytes, uint32_t surfels_size);
+/* active_surfels_ (direct_ba.cc:123) */
+bba_status bba_set_active_flags(bba_handle h, uint8_t* device_flags);
+/* Same two, from host memory into library-owned device buffers (e2e / harness path). */
+bba_status bba_set_surfels_host(bba_handle h, const float* host_surfels, size_t pitch_bytes, uint32_t surfels_size, void* stream);
+bba_status bba_get_surfels_host(bba_handle h, float* host_surfels, size_t pitch_bytes, int rows, void* stream);
+bba_status bba_get_active_flags_host(bba_handle h, uint8_t* host_flags, void* stream);
+bba_status bba_get_surfels_device(bba_handle h, float** device_surfels, size_t* pitch_bytes, uint32_t* surfels_size);
+
+/* DirectBA::AddKeyframe (direct_ba.cc:197-205) with the Keyframe buffers of keyframe.h:160-200.
+ * Computes frustum co-visibility against all earlier keyframes (direct_ba.cc:231-249). */
+bba_status bba_add_keyframe(bba_handle h,
+                            const uint16_t* device_depth, size_t depth_pitch,
+                            const uint16_t* device_normals, size_t normals_pitch,
+                            const uint16_t* device_radius, size_t radius_pitch,
+                            const uint8_t* device_color_rgba, size_t color_pitch,
+                            const float global_T_frame[7], float min_depth, float max_depth,
+                            void* stream, int* out_keyframe_id);
+bba_status bba_add_keyframe_host(bba_handle h,
+                                 const uint16_t* host_depth, const uint16_t* host_normals,
+                                 const uint16_t* host_radius, const uint8_t* host_color_rgba,
+                                 const float global_T_frame[7], float min_depth, float max_depth,
+                                 void* stream, int* out_keyframe_id);
+int        bba_keyframe_count(bba_handle h);
+bba_status bba_set_keyframe_pose(bba_handle h, int keyframe_id, const float global_T_frame[7]);   /* Keyframe::set_global_T_frame */
+bba_status bba_get_keyframe_pose(bba_handle h, int keyframe_id, float global_T_frame[7]);         /* Keyframe::global_T_frame */
+bba_status bba_set_keyframe_activation(bba_handle h, int keyframe_id, int activation);            /* Keyframe::SetActivation */
+bba_status bba_get_keyframe_activation(bba_handle h, int keyframe_id, int* activation);
+bba_status bba_get_covisibility(bba_handle h, int keyframe_id, uint8_t* out_row /* [keyframe_count] */);
+
+/* depth_params_ / cameras (direct_ba.h:243-297; SetColorCamera etc.) */
+bba_status bba_set_intrinsics(bba_handle h, const float depth_intrinsics[4], const float color_intrinsics[4], float depth_a);
+bba_status bba_get_intrinsics(bba_handle h, float depth_intrinsics[4], float color_intrinsics[4], float* depth_a);
+bba_status bba_set_cfactor_host(bba_handle h, const float* host_cfactor /* dense [cf_h][cf_w] */, void* stream);
+bba_status bba_get_cfactor_host(bba_handle h, float* host_cfactor, void* stream);
+bba_status bba_cfactor_size(bba_handle h, int* cf_width, int* cf_height);
+
+/* ---- the hot path (kernels.h) ---- */
+/* AccumulatePoseEstimationCoeffsCUDA (kernels.h:156-174, kernel_opt_pose.cc:39-97) for keyframe
+ * `keyframe_id` evaluated at global_T_frame_estimate.  Synchronises the stream. */
+bba_status bba_accumulate_pose_coeffs(bba_handle h, int keyframe_id, const float global_T_frame_estimate[7],
+                                      bba_pose_coeffs* out, void* stream);
+/* DirectBA::EstimateFramePose (direct_ba.h:122-129, direct_ba_alternating.cc:42-283) against a stored keyframe's
+ * images.  iterations/converged may be NULL. */
+bba_status bba_estimate_frame_pose(bba_handle h, int keyframe_id, const float global_T_frame_initial[7],
+                                   float global_T_frame_out[7], int* iterations, int* converged, void* stream);
+/* UpdateSurfelActivationCUDA (kernels.h:262-269, kernel_surfel_activation.cc:39-67) */
+bba_status bba_update_surfel_activation(bba_handle h, void* stream);
+/* OptimizeGeometryIterationCUDA (kernels.h:234-244, kernel_opt_geometry.cc:80-201) */
+bba_status bba_optimize_geometry_iteration(bba_handle h, void* stream);
+/* OptimizeIntrinsicsCUDA (kernels.h:246-260, kernel_opt_intrinsics.cc:39-281) */
+bba_status bba_optimize_intrinsics(bba_handle h, int optimize_depth_intrinsics, int optimize_color_intrinsics, void* stream);
+/* DirectBA::BundleAdjustment (direct_ba.h:143-162, direct_ba.cc:407-453 -> direct_ba_alternating.cc:285-738) */
+bba_status bba_bundle_adjust(bba_handle h, const bba_ba_options* options, bba_ba_result* result, void* stream);
+
+/* ---- multi-GPU (one process per GPU; not present in the reference) ---- */
+/* Registers the exchange step: an in-place all-gather over equal per-rank slices of a device buffer,
+ * enqueued on `stream` (the harness implements it with torch.distributed / NCCL). */
+bba_status bba_set_allgather(bba_handle h, bba_allgather_fn fn, void* user);
+
+/* ---- instrumentation ---- */
+uint64_t   bba_kernel_launch_count(bba_handle h);   /* kernels launched through this handle so far */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

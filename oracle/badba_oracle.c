@@ -1,0 +1,905 @@
+/* oracle/badba_oracle.c -- TEST INFRASTRUCTURE ONLY (see badba_oracle.h).
+ *
+ * CPU restatement of the reference's direct-BA hot path.  Every function cites
+ * the reference file:line it follows (paths relative to
+ * /root/reference/applications/badslam/src/badslam/).  Arithmetic is fp32 like the
+ * device code, sums are accumulated in fp64 (the reference sums in fp32 with a
+ * non-deterministic atomic order, gauss_newton.cuh:63-91, so fp64 sums are the
+ * value both GPU implementations scatter around).  -use_fast_math approximations
+ * of the reference build are NOT mimicked.
+ */
+#include "badba_oracle.h"
+#include "host_math.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ---- constants: cost_function.cuh:44-52,105-109,126 ; kernels.cuh:38-58 ---- */
+#define K_DEPTH_RESIDUAL_WEIGHT 1.f
+#define K_DEPTH_TUKEY 10.f
+#define K_DEPTH_UNCERTAINTY_FACTOR 0.1f
+#define K_DESC_RESIDUAL_WEIGHT 1e-2f
+#define K_DESC_HUBER 10.f
+#define K_TANGENT_SCALING 2.0f
+#define K_INVALID_DEPTH_BIT 0x8000u
+#define K_COS_NORMAL_COMPAT 0.76604f
+#define K_SURFEL_ACTIVE_FLAG 1u
+
+enum { ROW_X = 0, ROW_Y, ROW_Z, ROW_NORMAL, ROW_R2, ROW_COLOR, ROW_D1, ROW_D2, ROW_ACC0 };
+
+static int g_tex_mode = 1;
+void orc_set_tex_mode(int mode) { g_tex_mode = mode; }
+int orc_get_tex_mode(void) { return g_tex_mode; }
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+int orc_get_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+typedef struct { float x, y, z; } f3;
+static inline f3 mk3(float x, float y, float z) { f3 r = {x, y, z}; return r; }
+static inline f3 sub3(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline f3 add3(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline f3 scale3(f3 a, float s) { return mk3(s * a.x, s * a.y, s * a.z); }
+static inline float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static inline f3 cross3(f3 a, f3 b) {  /* cuda_util.cuh:76-80 */
+  return mk3(a.y * b.z - b.y * a.z, b.x * a.z - a.x * b.z, a.x * b.y - b.x * a.y);
+}
+/* cuda_matrix.cuh:104-135 */
+static inline f3 T_mul(const float T[12], f3 p) {
+  return mk3(T[0] * p.x + T[1] * p.y + T[2] * p.z + T[3],
+             T[4] * p.x + T[5] * p.y + T[6] * p.z + T[7],
+             T[8] * p.x + T[9] * p.y + T[10] * p.z + T[11]);
+}
+static inline f3 T_rot(const float T[12], f3 p) {
+  return mk3(T[0] * p.x + T[1] * p.y + T[2] * p.z,
+             T[4] * p.x + T[5] * p.y + T[6] * p.z,
+             T[8] * p.x + T[9] * p.y + T[10] * p.z);
+}
+
+/* robust_weighting.cuh:39-86 */
+static inline float tukey_residual(float r, float p) {
+  if (fabsf(r) < p) {
+    float q = r / p, t = 1.f - q * q;
+    return (1 / 6.f) * p * p * (1 - t * t * t);
+  }
+  return (1 / 6.f) * p * p;
+}
+static inline float tukey_weight(float r, float p) {
+  if (fabsf(r) < p) {
+    float q = r / p, t = 1.f - q * q;
+    return t * t;
+  }
+  return 0.f;
+}
+static inline float huber_residual(float r, float p) {
+  float a = fabsf(r);
+  return (a < p) ? 0.5f * r * r : p * (a - 0.5f * p);
+}
+static inline float huber_weight(float r, float p) {
+  float a = fabsf(r);
+  return (a < p) ? 1.f : (p / a);
+}
+/* cost_function.cuh:91-98,177-185 */
+static inline float depth_weight(float r) { return K_DEPTH_RESIDUAL_WEIGHT * tukey_weight(r, K_DEPTH_TUKEY); }
+static inline float depth_cost(float r) { return K_DEPTH_RESIDUAL_WEIGHT * tukey_residual(r, K_DEPTH_TUKEY); }
+static inline float desc_weight(float r) { return K_DESC_RESIDUAL_WEIGHT * huber_weight(r, K_DESC_HUBER); }
+static inline float desc_cost(float r) { return K_DESC_RESIDUAL_WEIGHT * huber_residual(r, K_DESC_HUBER); }
+
+/* util.cuh:62-69 */
+static inline float raw_to_calibrated_depth(float a, float cfactor, float raw_to_float, uint16_t measured) {
+  const float inv_depth = 1.0f / (raw_to_float * measured);
+  return 1.f / (inv_depth + cfactor * expf(-a * inv_depth));
+}
+/* util.cuh:126-146 */
+static inline f3 u16_to_image_space_normal(uint16_t v) {
+  f3 r;
+  r.x = (int8_t)(v & 0x00ff) * (1.0f / 127);
+  r.y = (int8_t)((v & 0xff00) >> 8) * (1.0f / 127);
+  r.z = 1 - r.x * r.x - r.y * r.y;
+  r.z = -sqrtf((r.z > 0.f) ? r.z : 0.f);
+  return r;
+}
+/* util_nvcc_only.cuh:67-95 */
+static inline uint32_t small_float_to_ten_bit_signed(float value) {
+  return 0x03ffu & (uint16_t)((int16_t)(value * 511 + ((value > 0) ? 0.5f : -0.5f)));
+}
+static inline float ten_bit_signed_to_small_float(uint32_t value) {
+  uint16_t temp = (uint16_t)(((0x0200 & value) ? 0xfc00 : 0) | (0x03ff & value));
+  return (int16_t)temp * (1.0f / 511);
+}
+static inline uint32_t pack_normal(f3 n) {
+  return (small_float_to_ten_bit_signed(n.x) << 0) | (small_float_to_ten_bit_signed(n.y) << 10) |
+         (small_float_to_ten_bit_signed(n.z) << 20);
+}
+static inline f3 unpack_normal(uint32_t v) {
+  f3 n = mk3(ten_bit_signed_to_small_float(v >> 0), ten_bit_signed_to_small_float(v >> 10),
+             ten_bit_signed_to_small_float(v >> 20));
+  float factor = 1.0f / sqrtf(n.x * n.x + n.y * n.y + n.z * n.z);
+  return scale3(n, factor);
+}
+static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+/* ---- per-keyframe view ---- */
+typedef struct {
+  const uint16_t* depth;
+  const uint16_t* normals;
+  const uint8_t* color;
+  int w, h, cw, ch;
+  /* surfel_projection.h:42-124 builders */
+  float fx, fy, cx, cy;                 /* PixelCornerProjector (depth) */
+  float fx_inv, fy_inv, cx_inv, cy_inv; /* PixelCenterUnprojector (depth) */
+  float d2c_fx, d2c_fy, d2c_cx, d2c_cy; /* DepthToColorPixelCorner */
+  float cfx, cfy, ccx, ccy;             /* colour PixelCornerProjector; PixelCenterProjector has cx-0.5 */
+  float a, raw_to_float, baseline_fx;
+  int cell, cf_w;
+  const float* cfactor;
+} kfview;
+
+static void make_view(const orc_model* m, const orc_keyframes* kfs, int k, kfview* v) {
+  size_t npx = (size_t)m->depth_w * m->depth_h;
+  size_t ncpx = (size_t)m->color_w * m->color_h;
+  v->depth = kfs->depth + npx * k;
+  v->normals = kfs->normals + npx * k;
+  v->color = kfs->color + ncpx * 4 * k;
+  v->w = m->depth_w; v->h = m->depth_h; v->cw = m->color_w; v->ch = m->color_h;
+  v->fx = m->depth_K[0]; v->fy = m->depth_K[1]; v->cx = m->depth_K[2]; v->cy = m->depth_K[3];
+  v->fx_inv = 1.0f / v->fx;
+  v->fy_inv = 1.0f / v->fy;
+  v->cx_inv = -(v->cx - 0.5f) * v->fx_inv;
+  v->cy_inv = -(v->cy - 0.5f) * v->fy_inv;
+  v->cfx = m->color_K[0]; v->cfy = m->color_K[1]; v->ccx = m->color_K[2]; v->ccy = m->color_K[3];
+  v->d2c_fx = v->cfx / v->fx;
+  v->d2c_cx = -1 * v->cfx * v->cx / v->fx + v->ccx;
+  v->d2c_fy = v->cfy / v->fy;
+  v->d2c_cy = -1 * v->cfy * v->cy / v->fy + v->ccy;
+  v->a = m->a; v->raw_to_float = m->raw_to_float_depth; v->baseline_fx = m->baseline_fx;
+  v->cell = m->cell; v->cf_w = m->cf_w; v->cfactor = m->cfactor;
+}
+
+/* Emulates tex2D<float4>(color_texture, x, y).w for the texture of keyframe.cc:67-73
+ * (clamp addressing, linear filter, normalized-float read, unnormalized coords). */
+static inline float texel(const kfview* v, int i, int j) {
+  if (i < 0) i = 0;
+  if (j < 0) j = 0;
+  if (i > v->cw - 1) i = v->cw - 1;
+  if (j > v->ch - 1) j = v->ch - 1;
+  return v->color[((size_t)j * v->cw + i) * 4 + 3] * (1.0f / 255.0f);
+}
+static inline float tex_w(const kfview* v, float x, float y) {
+  float xb = x - 0.5f, yb = y - 0.5f;
+  float fi = floorf(xb), fj = floorf(yb);
+  float al = xb - fi, be = yb - fj;
+  if (g_tex_mode == 1) {
+    al = floorf(al * 256.f + 0.5f) * (1.f / 256.f);
+    be = floorf(be * 256.f + 0.5f) * (1.f / 256.f);
+  } else if (g_tex_mode == 2) {
+    al = floorf(al * 256.f) * (1.f / 256.f);
+    be = floorf(be * 256.f) * (1.f / 256.f);
+  }
+  int i = (int)fi, j = (int)fj;
+  float t00 = texel(v, i, j), t10 = texel(v, i + 1, j), t01 = texel(v, i, j + 1), t11 = texel(v, i + 1, j + 1);
+  return (1.f - al) * (1.f - be) * t00 + al * (1.f - be) * t10 + (1.f - al) * be * t01 + al * be * t11;
+}
+
+float orc_tex_luma(const orc_model* m, const orc_keyframes* kfs, int k, float x, float y) {
+  kfview v;
+  make_view(m, kfs, k, &v);
+  return tex_w(&v, x, y);
+}
+
+/* ---- projection + association ---- */
+typedef struct {
+  f3 gp;        /* surfel global position */
+  f3 lp;        /* local position */
+  f3 n;         /* global normal (unpacked, normalised) */
+  float d;      /* calibrated depth of the pixel */
+  int px, py;
+  float pxf, pyf;
+} assoc;
+
+/* Stage reached (for the SURVEY 8d byte model): 0 culled, 1 in image, 2 depth ok (KF normal read), 3 associated.
+ * surfel_projection_nvcc_only.cuh:48-127 (IsAssociatedWithPixel), :302-359 (SurfelProjectsToAssociatedPixel),
+ * util.cuh:83-118 (ProjectSurfelToImage), cuda_matrix.cuh:115-124. */
+static inline int project_associate(const kfview* v, const float T[12], f3 gp, uint32_t packed_normal, assoc* r) {
+  r->gp = gp;
+  r->lp.z = T[8] * gp.x + T[9] * gp.y + T[10] * gp.z + T[11];
+  if (r->lp.z <= 0.f) return 0;
+  r->lp.x = T[0] * gp.x + T[1] * gp.y + T[2] * gp.z + T[3];
+  r->lp.y = T[4] * gp.x + T[5] * gp.y + T[6] * gp.z + T[7];
+  r->pxf = v->fx * (r->lp.x / r->lp.z) + v->cx;
+  r->pyf = v->fy * (r->lp.y / r->lp.z) + v->cy;
+  /* static_cast<int> of a float out of int range is UB on the host; the device saturates.
+   * Reject non-finite / huge values first (they fail the bounds test on the device as well). */
+  if (!(r->pxf >= 0.f) || !(r->pyf >= 0.f) || !(r->pxf < 1e9f) || !(r->pyf < 1e9f)) return 0;
+  r->px = (int)r->pxf;
+  r->py = (int)r->pyf;
+  if (r->px >= v->w || r->py >= v->h) return 0;
+
+  uint16_t measured = v->depth[(size_t)r->py * v->w + r->px];
+  if (measured & K_INVALID_DEPTH_BIT) return 1;
+  r->d = raw_to_calibrated_depth(v->a, v->cfactor[(size_t)(r->py / v->cell) * v->cf_w + (r->px / v->cell)],
+                                 v->raw_to_float, measured);
+  r->n = unpack_normal(packed_normal);
+  f3 ln = T_rot(T, r->n);
+  /* cost_function.cuh:81-83 */
+  float nx = v->fx_inv * r->px + v->cx_inv, ny = v->fy_inv * r->py + v->cy_inv;
+  float stddev = (K_DEPTH_UNCERTAINTY_FACTOR * fabsf(ln.x * nx + ln.y * ny + ln.z) * (r->d * r->d)) / v->baseline_fx;
+  float thr = K_DEPTH_TUKEY * stddev;
+  if (fabsf(r->lp.z - r->d) > thr) return 1;
+  float dist = sqrtf(dot3(r->lp, r->lp));
+  float facing = (1.0f / dist) * dot3(r->lp, ln);
+  if (facing > 0) return 1;
+  f3 pn = u16_to_image_space_normal(v->normals[(size_t)r->py * v->w + r->px]);
+  if (dot3(ln, pn) < K_COS_NORMAL_COMPAT) return 2;
+  return 3;
+}
+
+/* surfel_projection.cuh:196-207 */
+static inline int depth_to_color(const kfview* v, float pxf, float pyf, float* cx, float* cy) {
+  *cx = v->d2c_fx * pxf + v->d2c_cx;
+  *cy = v->d2c_fy * pyf + v->d2c_cy;
+  return *cx >= 0 && *cy >= 0 && (int)*cx < v->cw && (int)*cy < v->ch;
+}
+
+/* cost_function.cuh:115-136 */
+static inline void tangent_projections(const kfview* v, const float T[12], f3 gp, f3 n, float r2,
+                                       float* t1x, float* t1y, float* t2x, float* t2y) {
+  f3 t1 = cross3(n, (fabsf(n.x) > 0.9f) ? mk3(0, 1, 0) : mk3(1, 0, 0));
+  t1 = scale3(t1, K_TANGENT_SCALING * sqrtf(r2 / fmaxf(1e-12f, dot3(t1, t1))));
+  f3 p1 = T_mul(T, add3(gp, t1));
+  *t1x = v->cfx * (p1.x / p1.z) + v->ccx;
+  *t1y = v->cfy * (p1.y / p1.z) + v->ccy;
+  f3 t2 = cross3(n, t1);
+  t2 = scale3(t2, K_TANGENT_SCALING * sqrtf(r2 / fmaxf(1e-12f, dot3(t2, t2))));
+  f3 p2 = T_mul(T, add3(gp, t2));
+  *t2x = v->cfx * (p2.x / p2.z) + v->ccx;
+  *t2y = v->cfy * (p2.y / p2.z) + v->ccy;
+}
+
+/* cost_function.cuh:191-254: finite-difference gradient at one sample point. */
+static inline void point_gradient(const kfview* v, float x, float y, float* dx, float* dy) {
+  float ax = fmaxf(0.f, x - 0.5f), ay = fmaxf(0.f, y - 0.5f);
+  int ix = (ax < 2e9f) ? (int)ax : 2000000000;
+  int iy = (ay < 2e9f) ? (int)ay : 2000000000;
+  float tx = fmaxf(0.f, fminf(1.f, x - 0.5f - ix));
+  float ty = fmaxf(0.f, fminf(1.f, y - 0.5f - iy));
+  float tl = texel(v, ix, iy), tr = texel(v, ix + 1, iy), bl = texel(v, ix, iy + 1), br = texel(v, ix + 1, iy + 1);
+  *dx = (br - bl) * ty + (tr - tl) * (1 - ty);
+  *dy = (br - tr) * tx + (bl - tl) * (1 - tx);
+}
+
+typedef struct {
+  float r1, r2;                  /* raw descriptor residuals */
+  float gx1, gy1, gx2, gy2;      /* DescriptorJacobianWrtProjectedPosition outputs */
+} desc_eval;
+
+static inline void descriptor_eval(const kfview* v, float cx, float cy, float t1x, float t1y, float t2x, float t2y,
+                                   float d1, float d2, desc_eval* e) {
+  /* cost_function.cuh:140-156 */
+  float intensity = tex_w(v, cx, cy);
+  float t1i = tex_w(v, t1x, t1y), t2i = tex_w(v, t2x, t2y);
+  e->r1 = (180.f * (t1i - intensity)) - d1;
+  e->r2 = (180.f * (t2i - intensity)) - d2;
+  float cdx, cdy, t1dx, t1dy, t2dx, t2dy;
+  point_gradient(v, cx, cy, &cdx, &cdy);
+  point_gradient(v, t1x, t1y, &t1dx, &t1dy);
+  point_gradient(v, t2x, t2y, &t2dx, &t2dy);
+  e->gx1 = 180.f * (t1dx - cdx);
+  e->gy1 = 180.f * (t1dy - cdy);
+  e->gx2 = 180.f * (t2dx - cdx);
+  e->gy2 = 180.f * (t2dy - cdy);
+}
+
+/* kernel_opt_pose.cu:96-142 */
+static inline void desc_pose_jacobian(const kfview* v, f3 ls, float gx, float gy, float J[6]) {
+  gx *= v->cfx;
+  gy *= v->cfy;
+  float inv_z = 1.f / ls.z, z_sq = ls.z * ls.z, inv_z_sq = inv_z * inv_z, xy = ls.x * ls.y;
+  J[0] = -gx * inv_z;
+  J[1] = -gy * inv_z;
+  J[2] = (ls.x * gx + ls.y * gy) * inv_z_sq;
+  J[3] = ((ls.y * ls.y + z_sq) * gy + xy * gx) * inv_z_sq;
+  J[4] = -((ls.x * ls.x + z_sq) * gx + xy * gy) * inv_z_sq;
+  J[5] = -(ls.x * gy - ls.y * gx) * inv_z;
+}
+
+/* kernel_opt_pose.cu:45-94 ; returns raw residual */
+static inline float depth_pose_residual_jacobian(const kfview* v, const assoc* r, f3 ln, float J[6], float* inv_stddev_out,
+                                                 f3* unproj_out) {
+  float nx = v->fx_inv * r->px + v->cx_inv, ny = v->fy_inv * r->py + v->cy_inv;
+  /* cost_function.cuh:86-88 */
+  float inv_stddev = v->baseline_fx / (K_DEPTH_UNCERTAINTY_FACTOR * fabsf(ln.x * nx + ln.y * ny + ln.z) * (r->d * r->d));
+  f3 up = mk3(r->d * nx, r->d * ny, r->d);
+  float raw = inv_stddev * dot3(ln, sub3(up, r->lp));
+  if (J) {
+    J[0] = inv_stddev * ln.x;
+    J[1] = inv_stddev * ln.y;
+    J[2] = inv_stddev * ln.z;
+    J[3] = inv_stddev * (-ln.y * up.z + ln.z * up.y);
+    J[4] = inv_stddev * (ln.x * up.z - ln.z * up.x);
+    J[5] = inv_stddev * (-ln.x * up.y + ln.y * up.x);
+  }
+  if (inv_stddev_out) *inv_stddev_out = inv_stddev;
+  if (unproj_out) *unproj_out = up;
+  return raw;
+}
+
+static inline void accum_hb(double H[21], double b[6], const float J[6], float raw, float w) {
+  int idx = 0;
+  for (int r = 0; r < 6; ++r)
+    for (int c = r; c < 6; ++c) H[idx++] += (double)(w * J[r] * J[c]);
+  float wr = w * raw;
+  for (int i = 0; i < 6; ++i) b[i] += (double)(wr * J[i]);
+}
+
+void orc_frame_T_global(const float global_T_frame[7], float out12[12]) {
+  float inv[7];
+  hm_se3_inverse(global_T_frame, inv);
+  hm_se3_matrix3x4(inv, out12);
+}
+
+/* kernel_opt_pose.cu:251-383 */
+void orc_pose_coeffs(const orc_model* m, const orc_keyframes* kfs, int k, const float T[12],
+                     const float* surfels, int pitch, uint32_t n, orc_pose_stats* out) {
+  kfview v;
+  make_view(m, kfs, k, &v);
+  memset(out, 0, sizeof(*out));
+  out->n_pair = n;
+  const int use_depth = m->use_depth_residuals, use_desc = m->use_descriptor_residuals;
+#pragma omp parallel
+  {
+    orc_pose_stats loc;
+    memset(&loc, 0, sizeof(loc));
+#pragma omp for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; ++i) {
+      assoc r;
+      f3 gp = mk3(surfels[ROW_X * (size_t)pitch + i], surfels[ROW_Y * (size_t)pitch + i], surfels[ROW_Z * (size_t)pitch + i]);
+      int st = project_associate(&v, T, gp, f2u(surfels[ROW_NORMAL * (size_t)pitch + i]), &r);
+      if (st >= 1) loc.n_inimg++;
+      if (st >= 2) loc.n_depthok++;
+      if (st < 3) continue;
+      loc.n_assoc++;
+      float J[6];
+      if (use_depth) {
+        f3 ln = T_rot(T, r.n);
+        float raw = depth_pose_residual_jacobian(&v, &r, ln, J, NULL, NULL);
+        accum_hb(loc.H, loc.b, J, raw, depth_weight(raw));
+        loc.cost_depth += depth_cost(raw);
+      }
+      if (use_desc) {
+        float ccx, ccy;
+        if (depth_to_color(&v, r.pxf, r.pyf, &ccx, &ccy)) {
+          loc.n_photo++;
+          float t1x, t1y, t2x, t2y;
+          tangent_projections(&v, T, r.gp, r.n, surfels[ROW_R2 * (size_t)pitch + i], &t1x, &t1y, &t2x, &t2y);
+          desc_eval e;
+          descriptor_eval(&v, ccx, ccy, t1x, t1y, t2x, t2y, surfels[ROW_D1 * (size_t)pitch + i],
+                          surfels[ROW_D2 * (size_t)pitch + i], &e);
+          desc_pose_jacobian(&v, r.lp, e.gx1, e.gy1, J);
+          accum_hb(loc.H, loc.b, J, e.r1, desc_weight(e.r1));
+          desc_pose_jacobian(&v, r.lp, e.gx2, e.gy2, J);
+          accum_hb(loc.H, loc.b, J, e.r2, desc_weight(e.r2));
+          loc.cost_desc1 += desc_cost(e.r1);
+          loc.cost_desc2 += desc_cost(e.r2);
+        }
+      }
+    }
+#pragma omp critical
+    {
+      for (int j = 0; j < 21; ++j) out->H[j] += loc.H[j];
+      for (int j = 0; j < 6; ++j) out->b[j] += loc.b[j];
+      out->n_inimg += loc.n_inimg; out->n_depthok += loc.n_depthok;
+      out->n_assoc += loc.n_assoc; out->n_photo += loc.n_photo;
+      out->cost_depth += loc.cost_depth; out->cost_desc1 += loc.cost_desc1; out->cost_desc2 += loc.cost_desc2;
+    }
+  }
+  if (!use_depth) out->cost_depth = 0;
+}
+
+int orc_pair_residuals(const orc_model* m, const orc_keyframes* kfs, int k, const float T[12],
+                       const float surfel[8], float r_out[3], float J_pose[18], float J_geom[9]) {
+  kfview v;
+  make_view(m, kfs, k, &v);
+  assoc r;
+  int st = project_associate(&v, T, mk3(surfel[0], surfel[1], surfel[2]), f2u(surfel[3]), &r);
+  memset(r_out, 0, 3 * sizeof(float));
+  memset(J_pose, 0, 18 * sizeof(float));
+  memset(J_geom, 0, 9 * sizeof(float));
+  if (st < 3) return 0;
+  int flags = 1;
+  f3 ln = T_rot(T, r.n);
+  float inv_stddev;
+  r_out[0] = depth_pose_residual_jacobian(&v, &r, ln, J_pose, &inv_stddev, NULL);
+  J_geom[0] = -inv_stddev;  /* kernel_opt_geometry.cu:138 */
+  float ccx, ccy;
+  if (depth_to_color(&v, r.pxf, r.pyf, &ccx, &ccy)) {
+    flags |= 2;
+    float t1x, t1y, t2x, t2y;
+    tangent_projections(&v, T, r.gp, r.n, surfel[4], &t1x, &t1y, &t2x, &t2y);
+    desc_eval e;
+    descriptor_eval(&v, ccx, ccy, t1x, t1y, t2x, t2y, surfel[6], surfel[7], &e);
+    r_out[1] = e.r1;
+    r_out[2] = e.r2;
+    desc_pose_jacobian(&v, r.lp, e.gx1, e.gy1, J_pose + 6);
+    desc_pose_jacobian(&v, r.lp, e.gx2, e.gy2, J_pose + 12);
+    /* kernel_opt_geometry.cu:176-181 */
+    float term1 = -v.cfx * (ln.x * r.lp.z - ln.z * r.lp.x);
+    float term2 = -v.cfy * (ln.y * r.lp.z - ln.z * r.lp.y);
+    float term3 = 1.f / (r.lp.z * r.lp.z);
+    J_geom[3] = -(e.gx1 * term1 + e.gy1 * term2) * term3;
+    J_geom[6] = -(e.gx2 * term1 + e.gy2 * term2) * term3;
+    J_geom[4] = -1.f;
+    J_geom[8] = -1.f;
+  }
+  return flags;
+}
+
+/* direct_ba_alternating.cc:42-283 */
+int orc_estimate_frame_pose(const orc_model* m, const orc_keyframes* kfs, int k, const float init[7],
+                            const float* surfels, int pitch, uint32_t n, float out[7], int* converged_out,
+                            int max_iterations) {
+  float est[7];
+  memcpy(est, init, sizeof(est));
+  int converged = 0, iteration;
+  for (iteration = 0; iteration < max_iterations; ++iteration) {
+    float T[12];
+    orc_frame_T_global(est, T);
+    double Hd[36], bd[6], xd[6];
+    memset(Hd, 0, sizeof(Hd));
+    if (n == 0) {
+      memset(bd, 0, sizeof(bd));
+    } else {
+      orc_pose_stats st;
+      orc_pose_coeffs(m, kfs, k, T, surfels, pitch, n, &st);
+      int idx = 0;
+      /* the reference downloads fp32 H/b and casts to double (:173-179,206) */
+      for (int r = 0; r < 6; ++r)
+        for (int c = r; c < 6; ++c) Hd[r * 6 + c] = (double)(float)st.H[idx++];
+      for (int i = 0; i < 6; ++i) bd[i] = (double)(float)st.b[i];
+    }
+    hm_ldlt_solve(6, Hd, bd, xd);
+    float x[6], nx[6], e[7], next[7];
+    for (int i = 0; i < 6; ++i) { x[i] = (float)xd[i]; nx[i] = -x[i]; }
+    hm_se3_exp(nx, e);
+    hm_se3_mul(est, e, next);
+    memcpy(est, next, sizeof(est));
+    converged = hm_is_scale1_pose_converged(x);
+    if (converged) { ++iteration; break; }
+  }
+  memcpy(out, est, sizeof(est));
+  if (converged_out) *converged_out = converged;
+  return iteration;
+}
+
+/* kernel_surfel_activation.cu:38-79 + kernel_surfel_activation.cc:39-67 */
+void orc_update_activation(const orc_model* m, const orc_keyframes* kfs, const float* surfels, int pitch,
+                           uint32_t n, uint8_t* active) {
+  if (n == 0) return;
+  int K = kfs->K;
+  float* Ts = (float*)malloc(sizeof(float) * 12 * (size_t)K);
+  kfview* vs = (kfview*)malloc(sizeof(kfview) * (size_t)K);
+  for (int k = 0; k < K; ++k) { orc_frame_T_global(kfs->global_T_frame + 7 * k, Ts + 12 * k); make_view(m, kfs, k, vs + k); }
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < (int64_t)n; ++i) {
+    uint8_t flag = active[i] & (uint8_t)~K_SURFEL_ACTIVE_FLAG;
+    f3 gp = mk3(surfels[ROW_X * (size_t)pitch + i], surfels[ROW_Y * (size_t)pitch + i], surfels[ROW_Z * (size_t)pitch + i]);
+    uint32_t pn = f2u(surfels[ROW_NORMAL * (size_t)pitch + i]);
+    for (int k = 0; k < K; ++k) {
+      if (kfs->activation[k] != ORC_KF_ACTIVE) continue;
+      assoc r;
+      if (project_associate(vs + k, Ts + 12 * k, gp, pn, &r) == 3) { flag = K_SURFEL_ACTIVE_FLAG; break; }
+    }
+    active[i] = flag;
+  }
+  free(Ts);
+  free(vs);
+}
+
+/* kernel_opt_geometry.cc:80-201 with kernels kernel_opt_geometry.cu (cited inline).
+ * Surfel-major evaluation is exact: one thread owns one surfel in every reference kernel and
+ * keyframes are visited in index order, so the fp32 accumulation order is identical. */
+void orc_optimize_geometry_iteration(const orc_model* m, const orc_keyframes* kfs, float* surfels, int pitch,
+                                     uint32_t n, const uint8_t* active) {
+  if (n == 0) return;
+  int K = kfs->K;
+  float* Ts = (float*)malloc(sizeof(float) * 12 * (size_t)K);
+  kfview* vs = (kfview*)malloc(sizeof(kfview) * (size_t)K);
+  for (int k = 0; k < K; ++k) { orc_frame_T_global(kfs->global_T_frame + 7 * k, Ts + 12 * k); make_view(m, kfs, k, vs + k); }
+  const int use_depth = m->use_depth_residuals, use_desc = m->use_descriptor_residuals;
+  const size_t P = (size_t)pitch;
+
+  /* --- normals: :527-557 accumulate, :577-597 update --- */
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < (int64_t)n; ++i) {
+    if (!(active[i] & K_SURFEL_ACTIVE_FLAG)) continue;
+    f3 gp = mk3(surfels[ROW_X * P + i], surfels[ROW_Y * P + i], surfels[ROW_Z * P + i]);
+    uint32_t pn = f2u(surfels[ROW_NORMAL * P + i]);
+    float a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int k = 0; k < K; ++k) {
+      if (kfs->activation[k] == ORC_KF_INACTIVE) continue;
+      assoc r;
+      const float* T = Ts + 12 * k;
+      if (project_associate(vs + k, T, gp, pn, &r) != 3) continue;
+      f3 ln = u16_to_image_space_normal(vs[k].normals[(size_t)r.py * vs[k].w + r.px]);
+      /* global_R_frame = (frame_T_global rotation)^T (keyframe.h: global_T_frame.rotationMatrix()) */
+      a0 += T[0] * ln.x + T[4] * ln.y + T[8] * ln.z;
+      a1 += T[1] * ln.x + T[5] * ln.y + T[9] * ln.z;
+      a2 += T[2] * ln.x + T[6] * ln.y + T[10] * ln.z;
+      a3 += 1.f;
+    }
+    surfels[(ROW_ACC0 + 0) * P + i] = a0; surfels[(ROW_ACC0 + 1) * P + i] = a1;
+    surfels[(ROW_ACC0 + 2) * P + i] = a2; surfels[(ROW_ACC0 + 3) * P + i] = a3;
+    if (a3 >= 1) {
+      float inv = 1.f / a3;
+      surfels[ROW_NORMAL * P + i] = u2f(pack_normal(mk3(inv * a0, inv * a1, inv * a2)));
+    }
+  }
+
+  if (!use_desc) {
+    /* --- position from depth residual only: :417-459 accumulate, :487-507 update --- */
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; ++i) {
+      if (!(active[i] & K_SURFEL_ACTIVE_FLAG)) continue;
+      f3 gp = mk3(surfels[ROW_X * P + i], surfels[ROW_Y * P + i], surfels[ROW_Z * P + i]);
+      uint32_t pn = f2u(surfels[ROW_NORMAL * P + i]);
+      float H = 0, b = 0;
+      for (int k = 0; k < K; ++k) {
+        if (kfs->activation[k] == ORC_KF_INACTIVE) continue;
+        assoc r;
+        const float* T = Ts + 12 * k;
+        if (project_associate(vs + k, T, gp, pn, &r) != 3) continue;
+        f3 rn = T_rot(T, r.n);
+        float inv_stddev;
+        float raw = depth_pose_residual_jacobian(vs + k, &r, rn, NULL, &inv_stddev, NULL);
+        float jac = -inv_stddev;
+        float wj = depth_weight(raw) * jac;
+        H += wj * jac;
+        b += wj * raw;
+      }
+      surfels[(ROW_ACC0 + 0) * P + i] = H;
+      surfels[(ROW_ACC0 + 1) * P + i] = b;
+      if (H > 1e-6f) {
+        float t = -1.f * b / H;
+        f3 nrm = unpack_normal(pn);
+        surfels[ROW_X * P + i] = gp.x + t * nrm.x;
+        surfels[ROW_Y * P + i] = gp.y + t * nrm.y;
+        surfels[ROW_Z * P + i] = gp.z + t * nrm.z;
+      }
+    }
+  } else {
+    /* --- position + descriptors jointly: :118-231 accumulate, :273-361 update --- */
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; ++i) {
+      if (!(active[i] & K_SURFEL_ACTIVE_FLAG)) continue;
+      f3 gp = mk3(surfels[ROW_X * P + i], surfels[ROW_Y * P + i], surfels[ROW_Z * P + i]);
+      uint32_t pn = f2u(surfels[ROW_NORMAL * P + i]);
+      const float r2 = surfels[ROW_R2 * P + i];
+      const float d1 = surfels[ROW_D1 * P + i], d2 = surfels[ROW_D2 * P + i];
+      float A[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (int k = 0; k < K; ++k) {
+        if (kfs->activation[k] == ORC_KF_INACTIVE) continue;
+        assoc r;
+        const float* T = Ts + 12 * k;
+        const kfview* v = vs + k;
+        if (project_associate(v, T, gp, pn, &r) != 3) continue;
+        f3 rn = T_rot(T, r.n);
+        if (use_depth) {
+          float inv_stddev;
+          float raw = depth_pose_residual_jacobian(v, &r, rn, NULL, &inv_stddev, NULL);
+          float jac = -inv_stddev;
+          float w = depth_weight(raw);
+          A[0] += w * jac * jac;
+          A[6] += w * raw * jac;
+        }
+        float ccx, ccy;
+        if (depth_to_color(v, r.pxf, r.pyf, &ccx, &ccy)) {
+          float t1x, t1y, t2x, t2y;
+          tangent_projections(v, T, r.gp, r.n, r2, &t1x, &t1y, &t2x, &t2y);
+          desc_eval e;
+          descriptor_eval(v, ccx, ccy, t1x, t1y, t2x, t2y, d1, d2, &e);
+          float term1 = -v->cfx * (rn.x * r.lp.z - rn.z * r.lp.x);
+          float term2 = -v->cfy * (rn.y * r.lp.z - rn.z * r.lp.y);
+          float term3 = 1.f / (r.lp.z * r.lp.z);
+          float j1 = -(e.gx1 * term1 + e.gy1 * term2) * term3;
+          float j2 = -(e.gx2 * term1 + e.gy2 * term2) * term3;
+          const float jd = -1.f;
+          float w1 = desc_weight(e.r1), wr1 = w1 * e.r1;
+          float w2 = desc_weight(e.r2), wr2 = w2 * e.r2;
+          A[0] += w1 * j1 * j1 + w2 * j2 * j2;
+          A[1] += w1 * j1 * jd;
+          A[3] += w1 * jd * jd;
+          A[6] += wr1 * j1 + wr2 * j2;
+          A[7] += wr1 * jd;
+          A[2] += w2 * j2 * jd;
+          A[5] += w2 * jd * jd;
+          A[8] += wr2 * jd;
+        }
+      }
+      for (int j = 0; j < 9; ++j) surfels[(ROW_ACC0 + j) * P + i] = A[j];
+      /* :273-361 */
+      float H00 = A[0], H01 = A[1], H02 = A[2], H11 = A[3], H12 = A[4], H22 = A[5];
+      const float kEps = 1e-6f;
+      H00 += kEps; H11 += kEps; H22 += kEps;
+      H00 = sqrtf(H00);
+      H01 = H01 / H00;
+      H11 = sqrtf(H11 - H01 * H01);
+      H02 = H02 / H00;
+      H12 = (H12 - H02 * H01) / H11;
+      H22 = sqrtf(H22 - H02 * H02 - H12 * H12);
+      float y0 = A[6] / H00;
+      float y1 = (A[7] - H01 * y0) / H11;
+      float y2 = (A[8] - H02 * y0 - H12 * y1) / H22;
+      float x2 = y2 / H22;
+      float x1 = (y1 - H12 * x2) / H11;
+      float x0 = (y0 - H02 * x2 - H01 * x1) / H00;
+      if (x0 != 0) {
+        f3 nrm = unpack_normal(pn);
+        surfels[ROW_X * P + i] = gp.x - x0 * nrm.x;
+        surfels[ROW_Y * P + i] = gp.y - x0 * nrm.y;
+        surfels[ROW_Z * P + i] = gp.z - x0 * nrm.z;
+      }
+      if (x1 != 0) surfels[ROW_D1 * P + i] = fmaxf(-180.f, fminf(180.f, d1 - x1));
+      if (x2 != 0) surfels[ROW_D2 * P + i] = fmaxf(-180.f, fminf(180.f, d2 - x2));
+    }
+  }
+  free(Ts);
+  free(vs);
+}
+
+/* kernel_opt_intrinsics.cu:46-217 (accumulate), :265-347 (Schur intermediates), :374-424 (cfactor update)
+ * and kernel_opt_intrinsics.cc:39-281 (host: prior on a, fp64 LDLT, parameter update). */
+void orc_optimize_intrinsics(orc_model* m, const orc_keyframes* kfs, const float* surfels, int pitch, uint32_t n,
+                             int opt_depth, int opt_color) {
+  if (n == 0 || (!opt_depth && !opt_color)) return;
+  const int K = kfs->K;
+  const int Pn = m->cf_w * m->cf_h;
+  const size_t P = (size_t)pitch;
+  double A[15], b1[5], cH[10], cb[4];
+  memset(A, 0, sizeof(A)); memset(b1, 0, sizeof(b1)); memset(cH, 0, sizeof(cH)); memset(cb, 0, sizeof(cb));
+  double* B = (double*)calloc((size_t)5 * Pn, sizeof(double));
+  double* D = (double*)calloc((size_t)Pn, sizeof(double));
+  double* b2 = (double*)calloc((size_t)Pn, sizeof(double));
+  uint32_t* obs = (uint32_t*)calloc((size_t)Pn, sizeof(uint32_t));
+
+  for (int k = 0; k < K; ++k) {   /* ALL keyframes, also inactive ones (kernel_opt_intrinsics.cc:84-88) */
+    kfview v;
+    make_view(m, kfs, k, &v);
+    float T[12];
+    orc_frame_T_global(kfs->global_T_frame + 7 * k, T);
+    /* serial over surfels: per-cell accumulators; fine for an oracle */
+    for (uint32_t i = 0; i < n; ++i) {
+      assoc r;
+      f3 gp = mk3(surfels[ROW_X * P + i], surfels[ROW_Y * P + i], surfels[ROW_Z * P + i]);
+      if (project_associate(&v, T, gp, f2u(surfels[ROW_NORMAL * P + i]), &r) != 3) continue;
+      float nx = v.fx_inv * r.px + v.cx_inv, ny = v.fy_inv * r.py + v.cy_inv;
+      if (opt_depth) {
+        int spx = r.px / v.cell, spy = r.py / v.cell;
+        float cfactor = v.cfactor[(size_t)spy * v.cf_w + spx];
+        float raw_inv_depth = 1.0f / (v.raw_to_float * v.depth[(size_t)r.py * v.w + r.px]);
+        float exp_inv_depth = expf(-v.a * raw_inv_depth);
+        float corrected_inv_depth = cfactor * exp_inv_depth + raw_inv_depth;
+        if (fabsf(corrected_inv_depth) > 1e-4f) {
+          f3 ln = T_rot(T, r.n);
+          float dot = nx * ln.x + ny * ln.y + ln.z;
+          float inv_stddev = v.baseline_fx / (K_DEPTH_UNCERTAINTY_FACTOR * fabsf(ln.x * nx + ln.y * ny + ln.z) * (r.d * r.d));
+          float jac_base = inv_stddev * dot * exp_inv_depth / (corrected_inv_depth * corrected_inv_depth);
+          float J[6];
+          J[2] = inv_stddev * r.d * (r.n.x * T[0] + r.n.y * T[1] + r.n.z * T[2]);
+          J[3] = inv_stddev * r.d * (r.n.x * T[4] + r.n.y * T[5] + r.n.z * T[6]);
+          J[0] = r.px * J[2];
+          J[1] = r.py * J[3];
+          J[4] = cfactor * raw_inv_depth * jac_base;
+          J[5] = -jac_base;
+          f3 up = mk3(r.d * nx, r.d * ny, r.d);
+          float raw = inv_stddev * dot3(ln, sub3(up, r.lp));
+          int sp = spx + spy * v.cf_w;
+          float w = depth_weight(raw);
+          int idx = 0;
+          for (int rr = 0; rr < 5; ++rr)
+            for (int c = rr; c < 5; ++c) A[idx++] += (double)(w * J[rr] * J[c]);
+          float wr = w * raw;
+          for (int rr = 0; rr < 5; ++rr) b1[rr] += (double)(wr * J[rr]);
+          for (int rr = 0; rr < 5; ++rr) B[(size_t)rr * Pn + sp] += (double)(w * J[rr] * J[5]);
+          D[sp] += (double)(w * J[5] * J[5]);
+          b2[sp] += (double)(w * raw * J[5]);
+          obs[sp] += 1;
+        }
+      }
+      if (opt_color) {
+        float ccx, ccy;
+        if (depth_to_color(&v, r.pxf, r.pyf, &ccx, &ccy)) {
+          float t1x, t1y, t2x, t2y;
+          tangent_projections(&v, T, r.gp, r.n, surfels[ROW_R2 * P + i], &t1x, &t1y, &t2x, &t2y);
+          desc_eval e;
+          descriptor_eval(&v, ccx, ccy, t1x, t1y, t2x, t2y, surfels[ROW_D1 * P + i], surfels[ROW_D2 * P + i], &e);
+          float J1[4] = {e.gx1 * nx, e.gy1 * ny, e.gx1, e.gy1};
+          float J2[4] = {e.gx2 * nx, e.gy2 * ny, e.gx2, e.gy2};
+          const float* Js[2] = {J1, J2};
+          float rs[2] = {e.r1, e.r2};
+          for (int q = 0; q < 2; ++q) {
+            if (rs[q] == 0) continue;   /* valid == (raw != 0), kernel_opt_intrinsics.cu:199,207 */
+            float w = desc_weight(rs[q]);
+            int idx = 0;
+            for (int rr = 0; rr < 4; ++rr)
+              for (int c = rr; c < 4; ++c) cH[idx++] += (double)(w * Js[q][rr] * Js[q][c]);
+            float wr = w * rs[q];
+            for (int rr = 0; rr < 4; ++rr) cb[rr] += (double)(wr * Js[q][rr]);
+          }
+        }
+      }
+    }
+  }
+
+  if (opt_depth) {
+    /* buffers are fp32 on the device: round the accumulated values to float first */
+    float* Bf = (float*)malloc(sizeof(float) * 5 * (size_t)Pn);
+    float* Df = (float*)malloc(sizeof(float) * (size_t)Pn);
+    for (int p = 0; p < Pn; ++p) { Df[p] = (float)D[p]; for (int r = 0; r < 5; ++r) Bf[(size_t)r * Pn + p] = (float)B[(size_t)r * Pn + p]; }
+    double Ad[15], b1d[5];
+    for (int i = 0; i < 15; ++i) Ad[i] = (double)(float)A[i];
+    for (int i = 0; i < 5; ++i) b1d[i] = (double)(float)b1[i];
+    for (int p = 0; p < Pn; ++p) {
+      const float D_inverse = 1.0f / Df[p];
+      if (!(D_inverse < 1e12f)) { Df[p] = NAN; continue; }
+      float D_inv_b2 = D_inverse * (float)b2[p];
+      Df[p] = D_inv_b2;
+      int idx = 0;
+      for (int r = 0; r < 5; ++r)
+        for (int c = r; c < 5; ++c) Ad[idx++] -= (double)(Bf[(size_t)r * Pn + p] * D_inverse * Bf[(size_t)c * Pn + p]);
+      for (int r = 0; r < 5; ++r) b1d[r] -= (double)(Bf[(size_t)r * Pn + p] * D_inv_b2);
+      for (int r = 0; r < 5; ++r) Bf[(size_t)r * Pn + p] = D_inverse * Bf[(size_t)r * Pn + p];
+    }
+    double M[25], rhs[5], x1d[5];
+    memset(M, 0, sizeof(M));
+    int idx = 0;
+    for (int r = 0; r < 5; ++r)
+      for (int c = r; c < 5; ++c) M[r * 5 + c] = (double)(float)Ad[idx++];
+    for (int r = 0; r < 5; ++r) rhs[r] = (double)(float)b1d[r];
+    const float kAPriorWeight = 10;
+    M[4 * 5 + 4] = (double)((float)M[4 * 5 + 4] + kAPriorWeight * kAPriorWeight);
+    rhs[4] = (double)((float)rhs[4] + kAPriorWeight * kAPriorWeight * m->a);
+    hm_ldlt_solve(5, M, rhs, x1d);
+    float x1[5];
+    for (int r = 0; r < 5; ++r) x1[r] = (float)x1d[r];
+    float fx_inv = 1.0f / m->depth_K[0], fy_inv = 1.0f / m->depth_K[1];
+    float cx_inv = -(m->depth_K[2] - 0.5f) * fx_inv, cy_inv = -(m->depth_K[3] - 0.5f) * fy_inv;
+    float new_fx = 1.0f / (fx_inv - x1[0]);
+    float new_fy = 1.0f / (fy_inv - x1[1]);
+    float new_cx = -(new_fx * (cx_inv - x1[2])) + 0.5f;
+    float new_cy = -(new_fy * (cy_inv - x1[3])) + 0.5f;
+    m->depth_K[0] = new_fx; m->depth_K[1] = new_fy; m->depth_K[2] = new_cx; m->depth_K[3] = new_cy;
+    m->a -= x1[4];
+    for (int p = 0; p < Pn; ++p) {
+      float offset = Df[p];
+      if (isnan(offset)) offset = 0;
+      else for (int r = 0; r < 5; ++r) offset -= Bf[(size_t)r * Pn + p] * x1[r];
+      float cf = m->cfactor[p] - offset;
+      if (obs[p] == 0) cf = 0;
+      m->cfactor[p] = cf;
+    }
+    free(Bf); free(Df);
+  }
+  if (opt_color) {
+    double M[16], rhs[4], x[4];
+    memset(M, 0, sizeof(M));
+    int idx = 0;
+    for (int r = 0; r < 4; ++r)
+      for (int c = r; c < 4; ++c) M[r * 4 + c] = (double)(float)cH[idx++];
+    for (int r = 0; r < 4; ++r) rhs[r] = (double)(float)cb[r];
+    hm_ldlt_solve(4, M, rhs, x);
+    for (int r = 0; r < 4; ++r) m->color_K[r] = m->color_K[r] - (float)x[r];
+  }
+  free(B); free(D); free(b2); free(obs);
+}
+
+/* direct_ba.cc:231-249 applied for keyframes added in index order (AddKeyframe :197-205). */
+void orc_compute_covisibility(const orc_model* m, orc_keyframes* kfs) {
+  int K = kfs->K;
+  hm_frustum* fr = (hm_frustum*)malloc(sizeof(hm_frustum) * (size_t)K);
+  for (int k = 0; k < K; ++k)
+    hm_frustum_create(fr + k, m->depth_K, m->depth_w, m->depth_h, kfs->min_depth[k], kfs->max_depth[k],
+                      kfs->global_T_frame + 7 * k);
+  memset(kfs->covis, 0, (size_t)K * K);
+  for (int nk = 0; nk < K; ++nk)
+    for (int k = 0; k < nk; ++k)
+      if (hm_frustum_intersects(fr + nk, fr + k)) {
+        kfs->covis[(size_t)nk * K + k] = 1;
+        kfs->covis[(size_t)k * K + nk] = 1;
+      }
+  free(fr);
+}
+
+/* direct_ba.cc:549-564 */
+static void determine_covisible_active(orc_keyframes* kfs) {
+  int K = kfs->K;
+  for (int k = 0; k < K; ++k) {
+    if (kfs->activation[k] != ORC_KF_ACTIVE) continue;
+    for (int o = 0; o < K; ++o)
+      if (kfs->covis[(size_t)k * K + o] && kfs->activation[o] == ORC_KF_INACTIVE) kfs->activation[o] = ORC_KF_COVIS_ACTIVE;
+  }
+}
+
+/* direct_ba_alternating.cc:285-738 (lifecycle branches omitted: do_surfel_updates must be 0). */
+void orc_bundle_adjust(orc_model* m, orc_keyframes* kfs, float* surfels, int pitch, uint32_t n, uint8_t* active,
+                       const orc_ba_options* opt, orc_ba_result* res) {
+  memset(res, 0, sizeof(*res));
+  const int K = kfs->K;
+  const int fixed_window = opt->active_keyframe_window_start > 0 || opt->active_keyframe_window_end > 0;
+  const int whole_window = !(opt->active_keyframe_window_start != 0 || opt->active_keyframe_window_end != K - 1);
+  memset(active, 0, n);   /* :338 */
+  for (int iteration = 0; iteration < opt->max_iterations; ++iteration) {
+    res->iterations_done++;
+    if (fixed_window) {   /* :354-372 */
+      for (int k = 0; k < K; ++k)
+        kfs->activation[k] = (k >= opt->active_keyframe_window_start && k <= opt->active_keyframe_window_end)
+                                 ? ORC_KF_ACTIVE : ORC_KF_INACTIVE;
+      determine_covisible_active(kfs);
+    }
+    /* :444-456 */
+    if (!whole_window) memset(active, K_SURFEL_ACTIVE_FLAG, n);
+    else orc_update_activation(m, kfs, surfels, pitch, n, active);
+    /* :466-485 */
+    if (opt->optimize_geometry) orc_optimize_geometry_iteration(m, kfs, surfels, pitch, n, active);
+    /* :543-577 */
+    int num_converged = 0;
+    if (opt->optimize_poses) {
+      res->n_assoc = res->n_photo = 0;
+      res->cost = 0;
+      for (int k = 0; k < K; ++k) {
+        if (kfs->activation[k] == ORC_KF_INACTIVE) { ++num_converged; continue; }
+        float* pose = kfs->global_T_frame + 7 * k;
+        {  /* bookkeeping for the metric: counts at the pose step's starting state */
+          float T[12];
+          orc_pose_stats st;
+          orc_frame_T_global(pose, T);
+          orc_pose_coeffs(m, kfs, k, T, surfels, pitch, n, &st);
+          res->n_assoc += st.n_assoc;
+          res->n_photo += st.n_photo;
+          res->cost += st.cost_depth + st.cost_desc1;
+        }
+        float est[7], ftg[7], diff[7], lg[6];
+        int conv;
+        res->pose_iterations_total += orc_estimate_frame_pose(m, kfs, k, pose, surfels, pitch, n, est, &conv,
+                                                              opt->max_pose_iterations > 0 ? opt->max_pose_iterations : 30);
+        hm_se3_inverse(pose, ftg);
+        hm_se3_mul(ftg, est, diff);
+        hm_se3_log(diff, lg);
+        int moved = !hm_is_scale1_pose_converged(lg);
+        memcpy(pose, est, sizeof(est));
+        if (moved) kfs->activation[k] = ORC_KF_ACTIVE;
+        else { kfs->activation[k] = ORC_KF_INACTIVE; ++num_converged; }
+      }
+    }
+    /* :580-626 */
+    if (opt->optimize_depth_intrinsics || opt->optimize_color_intrinsics)
+      orc_optimize_intrinsics(m, kfs, surfels, pitch, n,
+                              opt->optimize_depth_intrinsics && m->use_depth_residuals,
+                              opt->optimize_color_intrinsics && m->use_descriptor_residuals);
+    /* :693-701 */
+    if (iteration >= opt->min_iterations - 1 && (num_converged == K || !opt->optimize_poses)) {
+      res->converged = 1;
+      break;
+    }
+    determine_covisible_active(kfs);   /* :711-717 */
+  }
+}
+
+void orc_se3_exp(const float a[6], float out[7]) { hm_se3_exp(a, out); }
+void orc_se3_log(const float T[7], float out[6]) { hm_se3_log(T, out); }
+void orc_se3_mul(const float A[7], const float B[7], float out[7]) { hm_se3_mul(A, B, out); }
+void orc_se3_inverse(const float A[7], float out[7]) { hm_se3_inverse(A, out); }

@@ -1,0 +1,187 @@
+"""ctypes binding of oracle/_ref/libbadslam_ref.so: the reference's OWN CUDA kernels (unmodified,
+compiled by oracle/build_ref.sh) behind oracle/ref_driver.cu.
+
+TEST / BASELINE INFRASTRUCTURE ONLY.  Needs a GPU; `available()` tells whether it can be used.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libbadslam_ref.so")
+
+
+class Config(C.Structure):
+    _fields_ = [("depth_w", C.c_int), ("depth_h", C.c_int), ("color_w", C.c_int), ("color_h", C.c_int),
+                ("depth_K", C.c_float * 4), ("color_K", C.c_float * 4),
+                ("raw_to_float_depth", C.c_float), ("baseline_fx", C.c_float), ("cell", C.c_int),
+                ("use_depth_residuals", C.c_int), ("use_descriptor_residuals", C.c_int)]
+
+
+class BAOptions(C.Structure):
+    _fields_ = [("optimize_poses", C.c_int), ("optimize_geometry", C.c_int),
+                ("min_iterations", C.c_int), ("max_iterations", C.c_int),
+                ("active_keyframe_window_start", C.c_int), ("active_keyframe_window_end", C.c_int)]
+
+
+class BAResult(C.Structure):
+    _fields_ = [("iterations_done", C.c_int), ("converged", C.c_int), ("n_count", C.c_ulonglong), ("cost", C.c_double),
+                ("pose_iterations_total", C.c_int), ("ms_surfel_activation", C.c_float),
+                ("ms_geometry_optimization", C.c_float), ("ms_pose_optimization", C.c_float),
+                ("kernel_launches", C.c_ulonglong)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        l = C.CDLL(LIB_PATH)
+        l.ref_create.restype = C.c_void_p
+        l.ref_create.argtypes = [C.POINTER(Config), C.c_uint]
+        l.ref_destroy.argtypes = [C.c_void_p]
+        l.ref_set_surfels.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint]
+        l.ref_get_surfels.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        l.ref_get_active.argtypes = [C.c_void_p, C.c_void_p]
+        l.ref_set_active.argtypes = [C.c_void_p, C.c_void_p]
+        l.ref_set_depth_params.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
+        l.ref_set_intrinsics.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        l.ref_add_keyframe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_float, C.c_float]
+        l.ref_get_pose.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        l.ref_set_pose.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        l.ref_get_activation.argtypes = [C.c_void_p, C.c_int]
+        l.ref_set_activation.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        l.ref_launch_count.restype = C.c_ulonglong
+        l.ref_launch_count.argtypes = [C.c_void_p]
+        l.ref_pose_coeffs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.ref_estimate_frame_pose.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.ref_update_activation.argtypes = [C.c_void_p]
+        l.ref_optimize_geometry_iteration.argtypes = [C.c_void_p]
+        l.ref_bundle_adjust.argtypes = [C.c_void_p, C.POINTER(BAOptions), C.POINTER(BAResult), C.c_int]
+        l.ref_last_cuda_error.restype = C.c_char_p
+        _lib = l
+    return _lib
+
+
+def available() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return False
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+class RefDirectBA:
+    """The reference's CUDA DirectBA hot path on a synthetic scene."""
+
+    def __init__(self, scene, use_depth=True, use_descriptor=True, poses=None):
+        self.l = lib()
+        cfg = scene.cfg
+        c = Config()
+        c.depth_w, c.depth_h, c.color_w, c.color_h = cfg.width, cfg.height, cfg.width, cfg.height
+        c.depth_K[:] = [float(v) for v in scene.depth_K]
+        c.color_K[:] = [float(v) for v in scene.color_K]
+        c.raw_to_float_depth, c.baseline_fx, c.cell = cfg.raw_to_float_depth, cfg.baseline_fx, cfg.cell
+        c.use_depth_residuals, c.use_descriptor_residuals = int(use_depth), int(use_descriptor)
+        self.h = self.l.ref_create(C.byref(c), max(scene.pitch, 1))
+        if not self.h:
+            raise RuntimeError("ref_create failed (no GPU?)")
+        self.K = cfg.num_keyframes
+        self.n = scene.num_surfels
+        poses = scene.poses_init if poses is None else poses
+        for k in range(self.K):
+            p = np.ascontiguousarray(poses[k], np.float32)
+            rid = self.l.ref_add_keyframe(self.h, np.ascontiguousarray(scene.depth[k]).ctypes.data,
+                                          np.ascontiguousarray(scene.normals[k]).ctypes.data,
+                                          np.ascontiguousarray(scene.radius[k]).ctypes.data,
+                                          np.ascontiguousarray(scene.color[k]).ctypes.data, p.ctypes.data,
+                                          float(scene.min_depth[k]), float(scene.max_depth[k]))
+            assert rid == k, rid
+        s = np.ascontiguousarray(scene.surfels, np.float32)
+        assert self.l.ref_set_surfels(self.h, s.ctypes.data, s.strides[0], self.n) == 0
+        if scene.depth_a != 0.0 or np.any(scene.cfactor != 0):
+            cf = np.ascontiguousarray(scene.cfactor, np.float32)
+            self.l.ref_set_depth_params(self.h, float(scene.depth_a), cf.ctypes.data)
+
+    def close(self):
+        if self.h:
+            self.l.ref_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def pose(self, k):
+        p = np.zeros(7, np.float32)
+        self.l.ref_get_pose(self.h, k, p.ctypes.data)
+        return p
+
+    def poses(self):
+        return np.stack([self.pose(k) for k in range(self.K)])
+
+    def set_pose(self, k, pose):
+        p = np.ascontiguousarray(pose, np.float32)
+        self.l.ref_set_pose(self.h, k, p.ctypes.data)
+
+    def activation(self):
+        return np.array([self.l.ref_get_activation(self.h, k) for k in range(self.K)], np.int32)
+
+    def set_activation(self, k, a):
+        self.l.ref_set_activation(self.h, k, int(a))
+
+    def surfels(self, rows=8):
+        out = np.zeros((rows, max(self.n, 1)), np.float32)
+        assert self.l.ref_get_surfels(self.h, out.ctypes.data, out.strides[0], rows) == 0
+        return out[:, :self.n]
+
+    def active(self):
+        out = np.zeros(max(self.n, 1), np.uint8)
+        assert self.l.ref_get_active(self.h, out.ctypes.data) == 0
+        return out[:self.n]
+
+    def set_active(self, flags):
+        f = np.ascontiguousarray(flags, np.uint8)
+        assert self.l.ref_set_active(self.h, f.ctypes.data) == 0
+
+    def pose_coeffs(self, k, pose):
+        p = np.ascontiguousarray(pose, np.float32)
+        H = np.zeros(21, np.float32)
+        b = np.zeros(6, np.float32)
+        cnt = C.c_uint()
+        cost = C.c_float()
+        self.l.ref_pose_coeffs(self.h, k, p.ctypes.data, H.ctypes.data, b.ctypes.data, C.byref(cnt), C.byref(cost))
+        return H, b, cnt.value, cost.value
+
+    def estimate_frame_pose(self, k, init):
+        p = np.ascontiguousarray(init, np.float32)
+        out = np.zeros(7, np.float32)
+        conv = C.c_int()
+        its = self.l.ref_estimate_frame_pose(self.h, k, p.ctypes.data, out.ctypes.data, C.byref(conv))
+        return out, its, bool(conv.value)
+
+    def update_activation(self):
+        self.l.ref_update_activation(self.h)
+
+    def optimize_geometry_iteration(self):
+        self.l.ref_optimize_geometry_iteration(self.h)
+
+    def bundle_adjust(self, optimize_poses=True, optimize_geometry=True, min_iterations=1, max_iterations=10,
+                      window_start=0, window_end=None, count_residuals=True):
+        o = BAOptions(int(optimize_poses), int(optimize_geometry), min_iterations, max_iterations, window_start,
+                      self.K - 1 if window_end is None else window_end)
+        r = BAResult()
+        self.l.ref_bundle_adjust(self.h, C.byref(o), C.byref(r), int(count_residuals))
+        return r
+
+    def launch_count(self):
+        return int(self.l.ref_launch_count(self.h))

@@ -1,0 +1,477 @@
+// oracle/ref_driver.cu -- TEST / BASELINE INFRASTRUCTURE ONLY (never loaded by the product path).
+//
+// Drives the reference's OWN, UNMODIFIED CUDA kernels (compiled by build_ref.sh from the sources where they
+// lie under /root/reference) through their Call...Kernel launchers.  The reference's thin host wrappers
+// (kernel_opt_pose.cc, kernel_opt_geometry.cc, kernel_surfel_activation.cc) and its BA loop
+// (direct_ba_alternating.cc) need Eigen/Sophus, which this image does not have, so their control flow is
+// restated here on top of oracle/host_math.h -- same launches, same order, same host<->device traffic
+// (2 Clear launches + kernel + 2 D2H copies + stream sync per Gauss-Newton iteration and keyframe).
+//
+// This is (a) the authoritative parity oracle on the GPU box ("the reference's own CUDA DirectBA on identical
+// synthetic RGB-D input", BASELINE.json north_star) and (b) the reference arm of bench.py.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "badslam/kernel_opt_geometry.h"
+#include "badslam/kernel_opt_pose.h"
+#include "badslam/kernel_surfel_activation.h"
+#include "badslam/kernels.cuh"
+#include "badslam/surfel_projection.cuh"
+#include "host_math.h"
+
+using namespace vis;
+
+namespace {
+
+struct RefKeyframe {
+  u16* depth = nullptr; size_t depth_pitch = 0;
+  u16* normals = nullptr; size_t normals_pitch = 0;
+  u16* radius = nullptr; size_t radius_pitch = 0;
+  uchar4* color = nullptr; size_t color_pitch = 0;
+  cudaTextureObject_t tex = 0;
+  float pose[7];        // global_T_frame
+  int activation = 0;   // 0 active, 1 covis-active, 2 inactive
+  float min_depth = 0, max_depth = 0;
+  std::vector<int> covis;
+};
+
+}  // namespace
+
+struct ref_config {
+  int depth_w, depth_h, color_w, color_h;
+  float depth_K[4], color_K[4];
+  float raw_to_float_depth, baseline_fx;
+  int cell;
+  int use_depth_residuals, use_descriptor_residuals;
+};
+
+struct ref_ba_options {
+  int optimize_poses, optimize_geometry;
+  int min_iterations, max_iterations;
+  int active_keyframe_window_start, active_keyframe_window_end;
+};
+
+struct ref_ba_result {
+  int iterations_done, converged;
+  unsigned long long n_count;   // debug residual_count summed over keyframes at the LAST iteration's pose step start
+  double cost;                  // debug residual sum, same convention
+  int pose_iterations_total;
+  float ms_surfel_activation, ms_geometry_optimization, ms_pose_optimization;
+  unsigned long long kernel_launches;
+};
+
+struct ref_context {
+  ref_config cfg;
+  float a = 0.f;
+  float* cfactor = nullptr; size_t cfactor_pitch = 0; int cf_w = 0, cf_h = 0;
+  float* surfels = nullptr; size_t surfel_pitch = 0; u32 surfels_size = 0; u32 max_surfels = 0;
+  u8* active = nullptr;
+  // PoseEstimationHelperBuffers (kernels.h:47-58)
+  u32* residual_count = nullptr; float* residual_sum = nullptr; float* H = nullptr; float* b = nullptr;
+  std::vector<RefKeyframe> kfs;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4];
+  unsigned long long launches = 0;
+};
+
+namespace {
+
+CUDAMatrix3x4 MakeFrameTGlobal(const float global_T_frame[7]) {
+  float inv[7], M[12];
+  hm_se3_inverse(global_T_frame, inv);
+  hm_se3_matrix3x4(inv, M);
+  CUDAMatrix3x4 r;
+  r.row0 = make_float4(M[0], M[1], M[2], M[3]);
+  r.row1 = make_float4(M[4], M[5], M[6], M[7]);
+  r.row2 = make_float4(M[8], M[9], M[10], M[11]);
+  return r;
+}
+
+CUDAMatrix3x3 MakeGlobalRFrame(const float global_T_frame[7]) {   // Keyframe::global_R_frame_cuda
+  float R[9];
+  hm_quat_to_R(global_T_frame, R);
+  CUDAMatrix3x3 r;
+  r.row0 = make_float3(R[0], R[1], R[2]);
+  r.row1 = make_float3(R[3], R[4], R[5]);
+  r.row2 = make_float3(R[6], R[7], R[8]);
+  return r;
+}
+
+DepthParameters MakeDepthParams(ref_context* c) {   // direct_ba.cc:108-120
+  DepthParameters d;
+  d.cfactor_buffer = CUDABuffer_<float>(c->cfactor, c->cf_h, c->cf_w, c->cfactor_pitch);
+  d.a = c->a;
+  d.raw_to_float_depth = c->cfg.raw_to_float_depth;
+  d.baseline_fx = c->cfg.baseline_fx;
+  d.sparse_surfel_cell_size = c->cfg.cell;
+  return d;
+}
+
+// surfel_projection.h:42-124
+PixelCornerProjector CornerProjector(const float K[4]) { return PixelCornerProjector(K[0], K[1], K[2], K[3]); }
+PixelCenterProjector CenterProjector(const float K[4]) { return PixelCenterProjector(K[0], K[1], K[2] - 0.5f, K[3] - 0.5f); }
+PixelCenterUnprojector CenterUnprojector(const float K[4]) {
+  const float fx_inv = 1.0f / K[0], fy_inv = 1.0f / K[1];
+  return PixelCenterUnprojector(fx_inv, fy_inv, -(K[2] - 0.5f) * fx_inv, -(K[3] - 0.5f) * fy_inv);
+}
+DepthToColorPixelCorner DepthToColor(const ref_config& cfg) {
+  DepthToColorPixelCorner r;
+  r.width = cfg.color_w;
+  r.height = cfg.color_h;
+  r.fx = cfg.color_K[0] / cfg.depth_K[0];
+  r.cx = -1 * cfg.color_K[0] * cfg.depth_K[2] / cfg.depth_K[0] + cfg.color_K[2];
+  r.fy = cfg.color_K[1] / cfg.depth_K[1];
+  r.cy = -1 * cfg.color_K[1] * cfg.depth_K[3] / cfg.depth_K[1] + cfg.color_K[3];
+  return r;
+}
+
+SurfelProjectionParameters MakeProjection(ref_context* c, const RefKeyframe& kf, const CUDAMatrix3x4& frame_T_global,
+                                          u32 surfels_size) {
+  return SurfelProjectionParameters(
+      CUDABuffer_<float>(c->surfels, kSurfelAttributeCount, c->max_surfels, c->surfel_pitch),
+      CUDABuffer_<u16>(kf.depth, c->cfg.depth_h, c->cfg.depth_w, kf.depth_pitch),
+      CUDABuffer_<u16>(kf.normals, c->cfg.depth_h, c->cfg.depth_w, kf.normals_pitch), MakeDepthParams(c),
+      CornerProjector(c->cfg.depth_K), CenterUnprojector(c->cfg.depth_K), frame_T_global, surfels_size);
+}
+
+CUDABuffer_<float> SurfelBuf(ref_context* c) { return CUDABuffer_<float>(c->surfels, kSurfelAttributeCount, c->max_surfels, c->surfel_pitch); }
+CUDABuffer_<u8> ActiveBuf(ref_context* c) { return CUDABuffer_<u8>(c->active, 1, c->max_surfels, c->max_surfels); }
+
+// kernel_opt_pose.cc:39-97 (debug = true)
+void AccumulatePoseEstimationCoeffs(ref_context* c, int k, const float global_T_frame[7], bool debug, u32* residual_count,
+                                    float* residual_sum, float* H, float* b) {
+  cudaStream_t s = c->stream;
+  CUDABuffer_<u32> count_buf(c->residual_count, 1, 1, sizeof(u32));
+  CUDABuffer_<float> sum_buf(c->residual_sum, 1, 1, sizeof(float));
+  CUDABuffer_<float> H_buf(c->H, 1, 21, 21 * sizeof(float));
+  CUDABuffer_<float> b_buf(c->b, 1, 6, 6 * sizeof(float));
+  if (debug) {
+    count_buf.Clear(0, s);
+    sum_buf.Clear(0, s);
+    c->launches += 2;
+  }
+  H_buf.Clear(0, s);
+  b_buf.Clear(0, s);
+  const RefKeyframe& kf = c->kfs[k];
+  CallAccumulatePoseEstimationCoeffsCUDAKernel(
+      s, debug, c->cfg.use_depth_residuals != 0, c->cfg.use_descriptor_residuals != 0,
+      MakeProjection(c, kf, MakeFrameTGlobal(global_T_frame), c->surfels_size), DepthToColor(c->cfg),
+      CenterProjector(c->cfg.color_K), CornerProjector(c->cfg.color_K), CenterUnprojector(c->cfg.depth_K), kf.tex, count_buf,
+      sum_buf, H_buf, b_buf);
+  c->launches += 3;
+  if (debug) {
+    cudaMemcpyAsync(residual_count, c->residual_count, sizeof(u32), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(residual_sum, c->residual_sum, sizeof(float), cudaMemcpyDeviceToHost, s);
+  }
+  cudaMemcpyAsync(H, c->H, 21 * sizeof(float), cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(b, c->b, 6 * sizeof(float), cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+}
+
+// direct_ba_alternating.cc:42-283
+int EstimateFramePose(ref_context* c, int k, const float init[7], float out[7], int* converged_out, bool debug_first,
+                      u32* first_count, float* first_sum) {
+  float est[7];
+  std::memcpy(est, init, sizeof(est));
+  int converged = 0, iteration;
+  for (iteration = 0; iteration < 30; ++iteration) {
+    float H[21], b[6];
+    u32 cnt = 0;
+    float sum = 0;
+    double Hd[36], bd[6], xd[6];
+    std::memset(Hd, 0, sizeof(Hd));
+    if (c->surfels_size == 0) {
+      std::memset(bd, 0, sizeof(bd));
+    } else {
+      const bool dbg = debug_first && iteration == 0;
+      AccumulatePoseEstimationCoeffs(c, k, est, dbg, &cnt, &sum, H, b);
+      if (dbg) { *first_count = cnt; *first_sum = sum; }
+      int idx = 0;
+      for (int r = 0; r < 6; ++r)
+        for (int cc = r; cc < 6; ++cc) Hd[r * 6 + cc] = H[idx++];
+      for (int i = 0; i < 6; ++i) bd[i] = b[i];
+    }
+    hm_ldlt_solve(6, Hd, bd, xd);
+    float x[6], nx[6], e[7], next[7];
+    for (int i = 0; i < 6; ++i) { x[i] = static_cast<float>(xd[i]); nx[i] = -x[i]; }
+    hm_se3_exp(nx, e);
+    hm_se3_mul(est, e, next);
+    std::memcpy(est, next, sizeof(est));
+    converged = hm_is_scale1_pose_converged(x);
+    if (converged) { ++iteration; break; }
+  }
+  std::memcpy(out, est, sizeof(est));
+  if (converged_out) *converged_out = converged;
+  return iteration;
+}
+
+// kernel_surfel_activation.cc:39-67
+void UpdateSurfelActivation(ref_context* c) {
+  if (c->surfels_size == 0) return;
+  CallSetSurfelInactiveKernel(c->stream, c->surfels_size, ActiveBuf(c));
+  ++c->launches;
+  for (const RefKeyframe& kf : c->kfs) {
+    if (kf.activation != 0) continue;
+    CallDetermineActiveSurfelsKernel(c->stream, MakeProjection(c, kf, MakeFrameTGlobal(kf.pose), c->surfels_size), ActiveBuf(c));
+    ++c->launches;
+  }
+}
+
+// kernel_opt_geometry.cc:80-201
+void OptimizeGeometryIteration(ref_context* c) {
+  if (c->surfels_size == 0) return;
+  cudaStream_t s = c->stream;
+  CallResetSurfelAccum0to3CUDAKernel(s, c->surfels_size, SurfelBuf(c), ActiveBuf(c));
+  ++c->launches;
+  for (const RefKeyframe& kf : c->kfs) {
+    if (kf.activation == 2) continue;
+    CallAccumulateSurfelNormalOptimizationCoeffsCUDAKernel(s, MakeProjection(c, kf, MakeFrameTGlobal(kf.pose), c->surfels_size),
+                                                           MakeGlobalRFrame(kf.pose), ActiveBuf(c));
+    ++c->launches;
+  }
+  CallUpdateSurfelNormalCUDAKernel(s, c->surfels_size, SurfelBuf(c), ActiveBuf(c));
+  ++c->launches;
+  if (!c->cfg.use_descriptor_residuals) {
+    CallResetSurfelAccum0to1CUDAKernel(s, c->surfels_size, SurfelBuf(c), ActiveBuf(c));
+    ++c->launches;
+    for (const RefKeyframe& kf : c->kfs) {
+      if (kf.activation == 2) continue;
+      CallAccumulateSurfelPositionOptimizationCoeffsFromDepthResidualCUDAKernel(
+          s, MakeProjection(c, kf, MakeFrameTGlobal(kf.pose), c->surfels_size), CenterUnprojector(c->cfg.depth_K),
+          DepthToColor(c->cfg), c->cfg.color_K[0], c->cfg.color_K[1], kf.tex, ActiveBuf(c));
+      ++c->launches;
+    }
+    CallUpdateSurfelPositionCUDAKernel(s, c->surfels_size, SurfelBuf(c), ActiveBuf(c));
+    ++c->launches;
+  } else {
+    CallResetSurfelAccumCUDAKernel(s, c->surfels_size, SurfelBuf(c), ActiveBuf(c));
+    ++c->launches;
+    for (const RefKeyframe& kf : c->kfs) {
+      if (kf.activation == 2) continue;
+      AccumulateSurfelPositionAndDescriptorOptimizationCoeffsCUDAKernel(
+          s, MakeProjection(c, kf, MakeFrameTGlobal(kf.pose), c->surfels_size), CenterUnprojector(c->cfg.depth_K),
+          DepthToColor(c->cfg), CornerProjector(c->cfg.color_K), kf.tex, ActiveBuf(c), c->cfg.use_depth_residuals != 0);
+      ++c->launches;
+    }
+    CallUpdateSurfelPositionAndDescriptorCUDAKernel(s, c->surfels_size, SurfelBuf(c), ActiveBuf(c));
+    ++c->launches;
+  }
+}
+
+void DetermineCovisibleActive(ref_context* c) {   // direct_ba.cc:549-564
+  for (RefKeyframe& kf : c->kfs) {
+    if (kf.activation != 0) continue;
+    for (int o : kf.covis)
+      if (c->kfs[o].activation == 2) c->kfs[o].activation = 1;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+ref_context* ref_create(const ref_config* cfg, unsigned int max_surfels) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return nullptr;
+  ref_context* c = new ref_context();
+  c->cfg = *cfg;
+  c->cf_w = (cfg->depth_w - 1) / cfg->cell + 1;
+  c->cf_h = (cfg->depth_h - 1) / cfg->cell + 1;
+  // libvis CUDABuffer = cudaMallocPitch (cuda_buffer_inl.h:36-41)
+  cudaMallocPitch(reinterpret_cast<void**>(&c->cfactor), &c->cfactor_pitch, c->cf_w * sizeof(float), c->cf_h);
+  cudaMemset2D(c->cfactor, c->cfactor_pitch, 0, c->cf_w * sizeof(float), c->cf_h);
+  c->max_surfels = max_surfels;
+  cudaMallocPitch(reinterpret_cast<void**>(&c->surfels), &c->surfel_pitch, static_cast<size_t>(max_surfels) * sizeof(float),
+                  kSurfelAttributeCount);
+  cudaMemset2D(c->surfels, c->surfel_pitch, 0, static_cast<size_t>(max_surfels) * sizeof(float), kSurfelAttributeCount);
+  cudaMalloc(&c->active, max_surfels);
+  cudaMemset(c->active, 0, max_surfels);
+  cudaMalloc(&c->residual_count, sizeof(u32));
+  cudaMalloc(&c->residual_sum, sizeof(float));
+  cudaMalloc(&c->H, 21 * sizeof(float));
+  cudaMalloc(&c->b, 6 * sizeof(float));
+  cudaStreamCreate(&c->stream);
+  for (auto& e : c->ev) cudaEventCreate(&e);
+  if (cudaDeviceSynchronize() != cudaSuccess) { delete c; return nullptr; }
+  return c;
+}
+
+void ref_destroy(ref_context* c) {
+  if (!c) return;
+  cudaDeviceSynchronize();
+  for (RefKeyframe& kf : c->kfs) {
+    if (kf.tex) cudaDestroyTextureObject(kf.tex);
+    cudaFree(kf.depth); cudaFree(kf.normals); cudaFree(kf.radius); cudaFree(kf.color);
+  }
+  cudaFree(c->cfactor); cudaFree(c->surfels); cudaFree(c->active);
+  cudaFree(c->residual_count); cudaFree(c->residual_sum); cudaFree(c->H); cudaFree(c->b);
+  for (auto& e : c->ev) cudaEventDestroy(e);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int ref_set_surfels(ref_context* c, const float* host, size_t host_pitch_bytes, unsigned int n) {
+  if (n > c->max_surfels) return 1;
+  c->surfels_size = n;
+  cudaMemcpy2D(c->surfels, c->surfel_pitch, host, host_pitch_bytes, static_cast<size_t>(n) * 4, 8, cudaMemcpyHostToDevice);
+  return cudaGetLastError() != cudaSuccess;
+}
+int ref_get_surfels(ref_context* c, float* host, size_t host_pitch_bytes, int rows) {
+  cudaMemcpy2D(host, host_pitch_bytes, c->surfels, c->surfel_pitch, static_cast<size_t>(c->surfels_size) * 4, rows,
+               cudaMemcpyDeviceToHost);
+  return cudaGetLastError() != cudaSuccess;
+}
+int ref_get_active(ref_context* c, unsigned char* host) {
+  cudaMemcpy(host, c->active, c->surfels_size, cudaMemcpyDeviceToHost);
+  return cudaGetLastError() != cudaSuccess;
+}
+int ref_set_active(ref_context* c, const unsigned char* host) {
+  cudaMemcpy(c->active, host, c->surfels_size, cudaMemcpyHostToDevice);
+  return cudaGetLastError() != cudaSuccess;
+}
+void ref_set_depth_params(ref_context* c, float a, const float* cfactor_dense) {
+  c->a = a;
+  if (cfactor_dense)
+    cudaMemcpy2D(c->cfactor, c->cfactor_pitch, cfactor_dense, c->cf_w * sizeof(float), c->cf_w * sizeof(float), c->cf_h,
+                 cudaMemcpyHostToDevice);
+}
+void ref_set_intrinsics(ref_context* c, const float* depth_K, const float* color_K) {
+  if (depth_K) std::memcpy(c->cfg.depth_K, depth_K, sizeof(float) * 4);
+  if (color_K) std::memcpy(c->cfg.color_K, color_K, sizeof(float) * 4);
+}
+
+int ref_add_keyframe(ref_context* c, const unsigned short* depth, const unsigned short* normals, const unsigned short* radius,
+                     const unsigned char* color_rgba, const float pose[7], float min_depth, float max_depth) {
+  RefKeyframe kf;
+  const int w = c->cfg.depth_w, h = c->cfg.depth_h, cw = c->cfg.color_w, ch = c->cfg.color_h;
+  cudaMallocPitch(reinterpret_cast<void**>(&kf.depth), &kf.depth_pitch, w * 2, h);
+  cudaMallocPitch(reinterpret_cast<void**>(&kf.normals), &kf.normals_pitch, w * 2, h);
+  cudaMallocPitch(reinterpret_cast<void**>(&kf.radius), &kf.radius_pitch, w * 2, h);
+  cudaMallocPitch(reinterpret_cast<void**>(&kf.color), &kf.color_pitch, cw * 4, ch);
+  cudaMemcpy2D(kf.depth, kf.depth_pitch, depth, w * 2, w * 2, h, cudaMemcpyHostToDevice);
+  cudaMemcpy2D(kf.normals, kf.normals_pitch, normals, w * 2, w * 2, h, cudaMemcpyHostToDevice);
+  if (radius) cudaMemcpy2D(kf.radius, kf.radius_pitch, radius, w * 2, w * 2, h, cudaMemcpyHostToDevice);
+  cudaMemcpy2D(kf.color, kf.color_pitch, color_rgba, cw * 4, cw * 4, ch, cudaMemcpyHostToDevice);
+  // CUDABuffer<uchar4>::CreateTextureObject as called in keyframe.cc:67-73 (cuda_buffer_inl.h:188-214)
+  cudaResourceDesc res;
+  std::memset(&res, 0, sizeof(res));
+  res.resType = cudaResourceTypePitch2D;
+  res.res.pitch2D.devPtr = kf.color;
+  res.res.pitch2D.desc = cudaCreateChannelDesc<uchar4>();
+  res.res.pitch2D.width = cw;
+  res.res.pitch2D.height = ch;
+  res.res.pitch2D.pitchInBytes = kf.color_pitch;
+  cudaTextureDesc tex;
+  std::memset(&tex, 0, sizeof(tex));
+  tex.addressMode[0] = cudaAddressModeClamp;
+  tex.addressMode[1] = cudaAddressModeClamp;
+  tex.filterMode = cudaFilterModeLinear;
+  tex.readMode = cudaReadModeNormalizedFloat;
+  tex.normalizedCoords = 0;
+  if (cudaCreateTextureObject(&kf.tex, &res, &tex, nullptr) != cudaSuccess) return -1;
+  std::memcpy(kf.pose, pose, sizeof(kf.pose));
+  kf.activation = 0;
+  kf.min_depth = min_depth;
+  kf.max_depth = max_depth;
+  const int id = static_cast<int>(c->kfs.size());
+  hm_frustum fn;
+  hm_frustum_create(&fn, c->cfg.depth_K, w, h, min_depth, max_depth, pose);
+  for (int k = 0; k < id; ++k) {   // direct_ba.cc:231-249
+    hm_frustum fo;
+    hm_frustum_create(&fo, c->cfg.depth_K, w, h, c->kfs[k].min_depth, c->kfs[k].max_depth, c->kfs[k].pose);
+    if (hm_frustum_intersects(&fn, &fo)) {
+      kf.covis.push_back(k);
+      c->kfs[k].covis.push_back(id);
+      if (c->kfs[k].activation == 2) c->kfs[k].activation = 1;
+    }
+  }
+  c->kfs.push_back(kf);
+  return id;
+}
+
+void ref_get_pose(ref_context* c, int k, float pose[7]) { std::memcpy(pose, c->kfs[k].pose, sizeof(float) * 7); }
+void ref_set_pose(ref_context* c, int k, const float pose[7]) { std::memcpy(c->kfs[k].pose, pose, sizeof(float) * 7); }
+int ref_get_activation(ref_context* c, int k) { return c->kfs[k].activation; }
+void ref_set_activation(ref_context* c, int k, int a) { c->kfs[k].activation = a; }
+unsigned long long ref_launch_count(ref_context* c) { return c->launches; }
+
+void ref_pose_coeffs(ref_context* c, int k, const float pose[7], float H[21], float b[6], unsigned int* count, float* cost) {
+  AccumulatePoseEstimationCoeffs(c, k, pose, true, count, cost, H, b);
+}
+
+int ref_estimate_frame_pose(ref_context* c, int k, const float init[7], float out[7], int* converged) {
+  return EstimateFramePose(c, k, init, out, converged, false, nullptr, nullptr);
+}
+
+void ref_update_activation(ref_context* c) { UpdateSurfelActivation(c); cudaStreamSynchronize(c->stream); }
+void ref_optimize_geometry_iteration(ref_context* c) { OptimizeGeometryIteration(c); cudaStreamSynchronize(c->stream); }
+
+// direct_ba_alternating.cc:285-738 without the surfel lifecycle / intrinsics branches.
+// `count_residuals`: run the first Gauss-Newton iteration of every keyframe with debug = true to obtain the
+// reference's own residual count / cost (kernel_opt_pose.cu:224-248).
+void ref_bundle_adjust(ref_context* c, const ref_ba_options* o, ref_ba_result* res, int count_residuals) {
+  std::memset(res, 0, sizeof(*res));
+  const int K = static_cast<int>(c->kfs.size());
+  cudaStream_t s = c->stream;
+  const unsigned long long launches_before = c->launches;
+  const bool fixed_window = o->active_keyframe_window_start > 0 || o->active_keyframe_window_end > 0;
+  const bool whole_window = !(o->active_keyframe_window_start != 0 || o->active_keyframe_window_end != K - 1);
+  cudaMemsetAsync(c->active, 0, c->surfels_size, s);
+  for (int iteration = 0; iteration < o->max_iterations; ++iteration) {
+    ++res->iterations_done;
+    if (fixed_window) {
+      for (int k = 0; k < K; ++k)
+        c->kfs[k].activation = (k >= o->active_keyframe_window_start && k <= o->active_keyframe_window_end) ? 0 : 2;
+      DetermineCovisibleActive(c);
+    }
+    cudaEventRecord(c->ev[0], s);
+    if (!whole_window) cudaMemsetAsync(c->active, kSurfelActiveFlag, c->surfels_size, s);
+    else UpdateSurfelActivation(c);
+    cudaEventRecord(c->ev[1], s);
+    if (o->optimize_geometry) OptimizeGeometryIteration(c);
+    cudaEventRecord(c->ev[2], s);
+    int num_converged = 0;
+    if (o->optimize_poses) {
+      res->n_count = 0;
+      res->cost = 0;
+      for (int k = 0; k < K; ++k) {
+        RefKeyframe& kf = c->kfs[k];
+        if (kf.activation == 2) { ++num_converged; continue; }
+        float est[7], ftg[7], diff[7], lg[6];
+        int conv;
+        u32 cnt = 0;
+        float sum = 0;
+        res->pose_iterations_total += EstimateFramePose(c, k, kf.pose, est, &conv, count_residuals != 0, &cnt, &sum);
+        res->n_count += cnt;
+        res->cost += sum;
+        hm_se3_inverse(kf.pose, ftg);
+        hm_se3_mul(ftg, est, diff);
+        hm_se3_log(diff, lg);
+        const int moved = !hm_is_scale1_pose_converged(lg);
+        std::memcpy(kf.pose, est, sizeof(est));
+        if (moved) kf.activation = 0;
+        else { kf.activation = 2; ++num_converged; }
+      }
+    }
+    cudaEventRecord(c->ev[3], s);
+    cudaEventSynchronize(c->ev[3]);
+    cudaEventElapsedTime(&res->ms_surfel_activation, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&res->ms_geometry_optimization, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&res->ms_pose_optimization, c->ev[2], c->ev[3]);
+    if (iteration >= o->min_iterations - 1 && (num_converged == K || !o->optimize_poses)) {
+      res->converged = 1;
+      break;
+    }
+    DetermineCovisibleActive(c);
+  }
+  res->kernel_launches = c->launches - launches_before;
+}
+
+const char* ref_last_cuda_error(void) { return cudaGetErrorString(cudaGetLastError()); }
+
+}  // extern "C"
