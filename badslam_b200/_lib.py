@@ -49,6 +49,14 @@ class PoseCoeffs(C.Structure):
                 ("cost_depth", C.c_double), ("cost_desc1", C.c_double), ("cost_desc2", C.c_double)]
 
 
+class Profile(C.Structure):
+    _fields_ = [("pose_launches", C.c_uint64), ("pose_ms", C.c_double), ("kf_evals", C.c_uint64),
+                ("n_pair", C.c_uint64), ("n_inimg", C.c_uint64), ("n_depthok", C.c_uint64),
+                ("n_assoc", C.c_uint64), ("n_photo", C.c_uint64),
+                ("geometry_launches", C.c_uint64), ("activation_normals_ms", C.c_double),
+                ("position_descriptor_ms", C.c_double)]
+
+
 ALLGATHER_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
 
 # every symbol include/badba.h declares: (name, restype, argtypes)
@@ -73,6 +81,8 @@ SYMBOLS = {
     "bba_get_keyframe_pose": (C.c_int, [_P, C.c_int, _F7]),
     "bba_set_keyframe_activation": (C.c_int, [_P, C.c_int, C.c_int]),
     "bba_get_keyframe_activation": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int)]),
+    "bba_set_keyframe_states": (C.c_int, [_P, C.c_int, _P, _P]),
+    "bba_get_keyframe_states": (C.c_int, [_P, C.c_int, _P, _P]),
     "bba_get_covisibility": (C.c_int, [_P, C.c_int, _P]),
     "bba_set_intrinsics": (C.c_int, [_P, _F7, _F7, C.c_float]),
     "bba_get_intrinsics": (C.c_int, [_P, _F7, _F7, C.POINTER(C.c_float)]),
@@ -87,6 +97,9 @@ SYMBOLS = {
     "bba_bundle_adjust": (C.c_int, [_P, C.POINTER(BAOptions), C.POINTER(BAResult), _P]),
     "bba_set_allgather": (C.c_int, [_P, ALLGATHER_FN, _P]),
     "bba_kernel_launch_count": (C.c_uint64, [_P]),
+    "bba_update_keyframe_host": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
+    "bba_set_profiling": (C.c_int, [_P, C.c_int]),
+    "bba_get_profile": (C.c_int, [_P, C.POINTER(Profile), C.c_int]),
 }
 
 _lib = None

@@ -9,6 +9,7 @@
 // and the host synchronises ONCE per outer iteration to read back the poses.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -123,8 +124,7 @@ struct Keyframe {
   const uint16_t* normals = nullptr;
   const uint16_t* radius = nullptr;
   size_t depth_pitch = 0, normals_pitch = 0, radius_pitch = 0;
-  uint8_t* luma = nullptr;   // library-owned u8 plane (the .w channel of the caller's uchar4 colour buffer)
-  size_t luma_pitch = 0;
+  cudaArray_t luma = nullptr;   // library-owned u8 CUDA array (the .w channel of the caller's uchar4 colour buffer)
   cudaTextureObject_t tex = 0;
   void* owned[3] = {nullptr, nullptr, nullptr};   // depth / normals / radius copies made by bba_add_keyframe_host
   Pose pose;                 // global_T_frame
@@ -153,6 +153,10 @@ struct bba_context {
   uint8_t* owned_active = nullptr;
 
   float* d_cfactor = nullptr;
+  uint8_t* luma_staging = nullptr;    // u8 plane staging for the luma arrays
+  size_t luma_staging_pitch = 0;
+  uint8_t* color_staging = nullptr;   // uchar4 staging image for bba_update_keyframe_host
+  size_t color_staging_pitch = 0;
   std::vector<Keyframe> keyframes;
 
   // device state sized for cfg.max_keyframes
@@ -166,6 +170,10 @@ struct bba_context {
   int* d_converged = nullptr;
   double* d_first_stats = nullptr;
   int* d_geo_list = nullptr;
+  unsigned long long* d_totals = nullptr;   // [8]
+  unsigned int* d_queue = nullptr;          // work-item counter of the pose kernel
+  volatile int* h_flag = nullptr;           // mapped pinned: {iterations completed, work items left}
+  int* d_flag = nullptr;                    // device alias of h_flag
 
   // pinned staging
   KfDevice* h_kfs = nullptr;
@@ -185,6 +193,12 @@ struct bba_context {
 
   uint64_t launches = 0;
   int ba_iteration_count = 0;
+
+  // profiling (bba_set_profiling)
+  bool profiling = false;
+  bba_profile profile;
+  cudaEvent_t prof_ev[64];
+  unsigned long long* h_totals = nullptr;
 };
 
 namespace {
@@ -303,6 +317,7 @@ bba_status RunPoseStep(bba_handle h, const std::vector<int>& ids, const std::vec
   BBA_CUDA(h, cudaMemsetAsync(h->d_stage_counts, 0, sizeof(unsigned long long) * 2 * K, s));
   BBA_CUDA(h, cudaMemsetAsync(h->d_iterations, 0, sizeof(int) * K, s));
   BBA_CUDA(h, cudaMemsetAsync(h->d_converged, 0, sizeof(int) * K, s));
+  BBA_CUDA(h, cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned int), s));
   if (bba_status st = MarkStaging(h, s)) return st;
 
   bba::PoseAccumulateArgs acc;
@@ -313,6 +328,7 @@ bba_status RunPoseStep(bba_handle h, const std::vector<int>& ids, const std::vec
   acc.kfs = h->d_kfs;
   acc.acc = h->d_acc;
   acc.stage_counts = h->d_stage_counts;
+  acc.queue = h->d_queue;
   bba::PoseSolveArgs sol;
   sol.kfs = h->d_kfs;
   sol.pose_est = h->d_pose_est;
@@ -322,12 +338,21 @@ bba_status RunPoseStep(bba_handle h, const std::vector<int>& ids, const std::vec
   sol.converged = h->d_converged;
   sol.first_stats = h->d_first_stats;
   sol.max_iterations = max_iterations;
+  sol.totals = h->d_totals;
+  sol.host_flag = h->d_flag;
+  sol.queue = h->d_queue;
+  h->h_flag[0] = 0;
+  h->h_flag[1] = n;
+  if (h->profiling) BBA_CUDA(h, cudaMemsetAsync(h->d_totals, 0, sizeof(unsigned long long) * 8, s));
+  int enqueued = 0;
   for (int it = 0; it < max_iterations; ++it) {
     const int cur = it & 1;
     acc.work_list = h->d_work[cur];
     acc.work_count = h->d_count + cur;
     if (h->surfels_size > 0) {
+      if (h->profiling && it < 32) BBA_CUDA(h, cudaEventRecord(h->prof_ev[2 * it], s));
       bba::LaunchPoseAccumulate(acc, h->sm_count, s);
+      if (h->profiling && it < 32) BBA_CUDA(h, cudaEventRecord(h->prof_ev[2 * it + 1], s));
       ++h->launches;
     }
     sol.work_in = h->d_work[cur];
@@ -337,14 +362,40 @@ bba_status RunPoseStep(bba_handle h, const std::vector<int>& ids, const std::vec
     sol.iteration = it;
     bba::LaunchPoseSolve(sol, s);
     ++h->launches;
+    ++enqueued;
+    // Keep exactly one iteration queued ahead of the one executing: wait (host spin on zero-copy memory, the stream is
+    // never blocked) until iteration it-1 has finished, and stop as soon as it left no unconverged keyframe.
+    if (it >= 1) {
+      while (h->h_flag[0] < it) {
+        if (cudaStreamQuery(s) == cudaSuccess) break;   // everything drained (or an error surfaced below)
+      }
+      if (h->h_flag[0] >= it && h->h_flag[1] == 0) break;
+    }
   }
   BBA_CUDA(h, cudaGetLastError());
   BBA_CUDA(h, cudaMemcpyAsync(h->h_pose_est, h->d_pose_est, sizeof(float) * 7 * K, cudaMemcpyDeviceToHost, s));
   BBA_CUDA(h, cudaMemcpyAsync(h->h_iterations, h->d_iterations, sizeof(int) * K, cudaMemcpyDeviceToHost, s));
   BBA_CUDA(h, cudaMemcpyAsync(h->h_converged, h->d_converged, sizeof(int) * K, cudaMemcpyDeviceToHost, s));
   BBA_CUDA(h, cudaMemcpyAsync(h->h_first_stats, h->d_first_stats, sizeof(double) * 8 * K, cudaMemcpyDeviceToHost, s));
+  if (h->profiling) BBA_CUDA(h, cudaMemcpyAsync(h->h_totals, h->d_totals, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, s));
   BBA_CUDA(h, cudaStreamSynchronize(s));
   h->staging_pending = false;
+  if (h->profiling && h->surfels_size > 0) {
+    int real_iterations = 0;   // iterations that had a non-empty work list
+    for (int i = 0; i < n; ++i) real_iterations = std::max(real_iterations, h->h_iterations[ids[i]]);
+    for (int it = 0; it < std::min(real_iterations, std::min(enqueued, 32)); ++it) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, h->prof_ev[2 * it], h->prof_ev[2 * it + 1]);
+      h->profile.pose_ms += ms;
+      ++h->profile.pose_launches;
+    }
+    h->profile.kf_evals += h->h_totals[0];
+    h->profile.n_pair += h->h_totals[0] * static_cast<uint64_t>(h->surfels_size);
+    h->profile.n_inimg += h->h_totals[1];
+    h->profile.n_depthok += h->h_totals[2];
+    h->profile.n_assoc += h->h_totals[3];
+    h->profile.n_photo += h->h_totals[4];
+  }
   return BBA_OK;
 }
 
@@ -382,19 +433,20 @@ bba_status AddKeyframeCommon(bba_handle h, Keyframe&& kf, const uint8_t* device_
                              float min_depth, float max_depth, cudaStream_t s, int* out_id) {
   if (static_cast<int>(h->keyframes.size()) >= h->cfg.max_keyframes) return Fail(h, BBA_ERR_STATE, "max_keyframes exceeded");
   const int cw = h->cfg.color_width, ch = h->cfg.color_height;
-  BBA_CUDA(h, cudaMallocPitch(reinterpret_cast<void**>(&kf.luma), &kf.luma_pitch, cw, ch));
-  bba::LaunchExtractLuma(device_rgba, color_pitch, kf.luma, kf.luma_pitch, cw, ch, s);
+  if (!h->luma_staging)
+    BBA_CUDA(h, cudaMallocPitch(reinterpret_cast<void**>(&h->luma_staging), &h->luma_staging_pitch, cw, ch));
+  // luma plane (the .w channel) -> gather-enabled CUDA array (block-linear: 2-D locality for the sample footprints)
+  const cudaChannelFormatDesc desc = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
+  BBA_CUDA(h, cudaMallocArray(&kf.luma, &desc, cw, ch, cudaArrayTextureGather));
+  bba::LaunchExtractLuma(device_rgba, color_pitch, h->luma_staging, h->luma_staging_pitch, cw, ch, s);
   ++h->launches;
   BBA_CUDA(h, cudaGetLastError());
+  BBA_CUDA(h, cudaMemcpy2DToArrayAsync(kf.luma, 0, 0, h->luma_staging, h->luma_staging_pitch, cw, ch, cudaMemcpyDeviceToDevice, s));
   // Texture with the reference's sampling state (keyframe.cc:67-73) over the single luma channel.
   cudaResourceDesc res;
   std::memset(&res, 0, sizeof(res));
-  res.resType = cudaResourceTypePitch2D;
-  res.res.pitch2D.devPtr = kf.luma;
-  res.res.pitch2D.desc = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
-  res.res.pitch2D.width = cw;
-  res.res.pitch2D.height = ch;
-  res.res.pitch2D.pitchInBytes = kf.luma_pitch;
+  res.resType = cudaResourceTypeArray;
+  res.res.array.array = kf.luma;
   cudaTextureDesc tex;
   std::memset(&tex, 0, sizeof(tex));
   tex.addressMode[0] = cudaAddressModeClamp;
@@ -482,6 +534,21 @@ bba_status bba_create(const bba_config* cfg, bba_handle* out) {
   CREATE_TRY(cudaMalloc(&h->d_first_stats, sizeof(double) * 8 * K));
   CREATE_TRY(cudaMemset(h->d_first_stats, 0, sizeof(double) * 8 * K));
   CREATE_TRY(cudaMalloc(&h->d_geo_list, sizeof(int) * K));
+  CREATE_TRY(cudaMalloc(&h->d_queue, sizeof(unsigned int)));
+  CREATE_TRY(cudaMemset(h->d_queue, 0, sizeof(unsigned int)));
+  CREATE_TRY(cudaMalloc(&h->d_totals, sizeof(unsigned long long) * 8));
+  CREATE_TRY(cudaMemset(h->d_totals, 0, sizeof(unsigned long long) * 8));
+  {
+    int* flag = nullptr;
+    CREATE_TRY(cudaHostAlloc(&flag, sizeof(int) * 4, cudaHostAllocMapped));
+    flag[0] = flag[1] = flag[2] = flag[3] = 0;
+    h->h_flag = flag;
+    CREATE_TRY(cudaHostGetDevicePointer(&h->d_flag, flag, 0));
+  }
+  CREATE_TRY(cudaMallocHost(&h->h_totals, sizeof(unsigned long long) * 8));
+  std::memset(&h->profile, 0, sizeof(h->profile));
+  for (auto& e : h->prof_ev) e = nullptr;
+  for (auto& e : h->prof_ev) CREATE_TRY(cudaEventCreate(&e));
   CREATE_TRY(cudaMallocHost(&h->h_kfs, sizeof(KfDevice) * K));
   CREATE_TRY(cudaMallocHost(&h->h_pose_est, sizeof(float) * 7 * K));
   CREATE_TRY(cudaMallocHost(&h->h_work, sizeof(int) * (K + 2)));
@@ -503,12 +570,14 @@ void bba_destroy(bba_handle h) {
   cudaDeviceSynchronize();
   for (Keyframe& kf : h->keyframes) {
     if (kf.tex) cudaDestroyTextureObject(kf.tex);
-    cudaFree(kf.luma);
+    if (kf.luma) cudaFreeArray(kf.luma);
     for (void* p : kf.owned) cudaFree(p);
   }
   cudaFree(h->owned_surfels);
   cudaFree(h->owned_active);
   cudaFree(h->d_cfactor);
+  cudaFree(h->color_staging);
+  cudaFree(h->luma_staging);
   cudaFree(h->d_kfs);
   cudaFree(h->d_pose_est);
   cudaFree(h->d_acc);
@@ -520,6 +589,12 @@ void bba_destroy(bba_handle h) {
   cudaFree(h->d_converged);
   cudaFree(h->d_first_stats);
   cudaFree(h->d_geo_list);
+  cudaFree(h->d_totals);
+  cudaFree(h->d_queue);
+  if (h->h_flag) cudaFreeHost(const_cast<int*>(h->h_flag));
+  cudaFreeHost(h->h_totals);
+  for (auto& e : h->prof_ev)
+    if (e) cudaEventDestroy(e);
   cudaFreeHost(h->h_kfs);
   cudaFreeHost(h->h_pose_est);
   cudaFreeHost(h->h_work);
@@ -671,6 +746,25 @@ bba_status bba_get_keyframe_activation(bba_handle h, int id, int* activation) {
   *activation = h->keyframes[id].activation;
   return BBA_OK;
 }
+bba_status bba_set_keyframe_states(bba_handle h, int count, const float* poses, const int* activation) {
+  if (!h || count < 0 || count > static_cast<int>(h->keyframes.size())) return BBA_ERR_INVALID_ARGUMENT;
+  for (int k = 0; k < count; ++k) {
+    if (poses) h->keyframes[k].pose = PoseFromArray(poses + 7 * k);
+    if (activation) {
+      if (activation[k] < 0 || activation[k] > 2) return Fail(h, BBA_ERR_INVALID_ARGUMENT, "bad activation");
+      h->keyframes[k].activation = activation[k];
+    }
+  }
+  return BBA_OK;
+}
+bba_status bba_get_keyframe_states(bba_handle h, int count, float* poses, int* activation) {
+  if (!h || count < 0 || count > static_cast<int>(h->keyframes.size())) return BBA_ERR_INVALID_ARGUMENT;
+  for (int k = 0; k < count; ++k) {
+    if (poses) PoseToArray(h->keyframes[k].pose, poses + 7 * k);
+    if (activation) activation[k] = h->keyframes[k].activation;
+  }
+  return BBA_OK;
+}
 bba_status bba_get_covisibility(bba_handle h, int id, uint8_t* out_row) {
   CHECK_KF(h, id);
   std::memset(out_row, 0, h->keyframes.size());
@@ -737,6 +831,8 @@ bba_status bba_accumulate_pose_coeffs(bba_handle h, int id, const float pose[7],
   acc.kfs = h->d_kfs;
   acc.acc = h->d_acc;
   acc.stage_counts = h->d_stage_counts;
+  acc.queue = h->d_queue;
+  BBA_CUDA(h, cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned int), s));
   acc.work_list = h->d_work[0];
   acc.work_count = h->d_count;
   if (h->surfels_size > 0) {
@@ -913,6 +1009,11 @@ bba_status bba_bundle_adjust(bba_handle h, const bba_ba_options* o, bba_ba_resul
     cudaEventElapsedTime(&res->ms_surfel_activation, h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&res->ms_geometry_optimization, h->ev[1], h->ev[2]);
     cudaEventElapsedTime(&res->ms_pose_optimization, h->ev[2], h->ev[3]);
+    if (h->profiling) {
+      h->profile.activation_normals_ms += res->ms_surfel_activation;
+      h->profile.position_descriptor_ms += res->ms_geometry_optimization;
+      h->profile.geometry_launches += (o->optimize_geometry ? 2 : 1);
+    }
 
     // --- convergence (:693-701)
     if (iteration >= o->min_iterations - 1 && (num_converged == K || !o->optimize_poses)) {
@@ -938,5 +1039,48 @@ bba_status bba_set_allgather(bba_handle h, bba_allgather_fn fn, void* user) {
 }
 
 uint64_t bba_kernel_launch_count(bba_handle h) { return h ? h->launches : 0; }
+
+bba_status bba_set_profiling(bba_handle h, int enable) {
+  if (!h) return BBA_ERR_INVALID_ARGUMENT;
+  h->profiling = enable != 0;
+  return BBA_OK;
+}
+
+bba_status bba_get_profile(bba_handle h, bba_profile* out, int reset) {
+  if (!h || !out) return BBA_ERR_INVALID_ARGUMENT;
+  *out = h->profile;
+  if (reset) std::memset(&h->profile, 0, sizeof(h->profile));
+  return BBA_OK;
+}
+
+bba_status bba_update_keyframe_host(bba_handle h, int id, const uint16_t* host_depth, const uint16_t* host_normals,
+                                    const uint16_t* host_radius, const uint8_t* host_color_rgba, void* stream) {
+  CHECK_KF(h, id);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Keyframe& kf = h->keyframes[id];
+  const int w = h->cfg.depth_width, hh = h->cfg.depth_height, cw = h->cfg.color_width, ch = h->cfg.color_height;
+  // The library can only write into buffers it owns (keyframes added with bba_add_keyframe_host); caller-owned
+  // device buffers are updated by the caller.
+  const uint16_t* srcs[3] = {host_depth, host_normals, host_radius};
+  const size_t pitches[3] = {kf.depth_pitch, kf.normals_pitch, kf.radius_pitch};
+  for (int i = 0; i < 3; ++i) {
+    if (!srcs[i]) continue;
+    if (!kf.owned[i]) return Fail(h, BBA_ERR_STATE, "keyframe buffers are caller-owned; update them directly");
+    BBA_CUDA(h, cudaMemcpy2DAsync(kf.owned[i], pitches[i], srcs[i], static_cast<size_t>(w) * 2, static_cast<size_t>(w) * 2, hh,
+                                  cudaMemcpyHostToDevice, s));
+  }
+  if (host_color_rgba) {
+    if (!h->color_staging) {
+      BBA_CUDA(h, cudaMallocPitch(reinterpret_cast<void**>(&h->color_staging), &h->color_staging_pitch, static_cast<size_t>(cw) * 4, ch));
+    }
+    BBA_CUDA(h, cudaMemcpy2DAsync(h->color_staging, h->color_staging_pitch, host_color_rgba, static_cast<size_t>(cw) * 4,
+                                  static_cast<size_t>(cw) * 4, ch, cudaMemcpyHostToDevice, s));
+    bba::LaunchExtractLuma(h->color_staging, h->color_staging_pitch, h->luma_staging, h->luma_staging_pitch, cw, ch, s);
+    ++h->launches;
+    BBA_CUDA(h, cudaGetLastError());
+    BBA_CUDA(h, cudaMemcpy2DToArrayAsync(kf.luma, 0, 0, h->luma_staging, h->luma_staging_pitch, cw, ch, cudaMemcpyDeviceToDevice, s));
+  }
+  return BBA_OK;
+}
 
 }  // extern "C"

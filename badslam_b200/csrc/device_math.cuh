@@ -46,7 +46,7 @@ struct __align__(16) KfDevice {
   float T[12];                       // frame_T_global, row-major 3x4
   const uint16_t* depth;             // pitched u16
   const uint16_t* normals;           // pitched u16
-  cudaTextureObject_t tex;           // u8 luma, linear filter, normalized float, clamp, unnormalized coords
+  cudaTextureObject_t tex;           // u8 luma CUDA array (gather-enabled): linear filter, normalized float, clamp
   uint32_t depth_pitch, normals_pitch;   // bytes
   int activation;
   int pad;
@@ -215,19 +215,21 @@ __device__ __forceinline__ void TangentProjections(const CameraParams& cam, cons
   *t2y = cam.cfy * (p2.y / p2.z) + cam.ccy;
 }
 
-// One sample point of DescriptorJacobianWrtProjectedPosition (cost_function.cuh:191-254): the four texels around
-// (x, y) read at their centres (no filtering) and combined into a finite-difference gradient.
-__device__ __forceinline__ void PointGradient(cudaTextureObject_t tex, float x, float y, float* dx, float* dy) {
+// One sample point of the descriptor residual: the bilinearly filtered intensity at (x, y)
+// (ComputeRawDescriptorResidual, cost_function.cuh:140-156) and the finite-difference gradient built from the
+// four texels around it (DescriptorJacobianWrtProjectedPosition, cost_function.cuh:191-254).
+// The reference reads those four texels with four point fetches at (ix+0.5|1.5, iy+0.5|1.5); here ONE
+// tex2Dgather centred on the 2x2 footprint returns exactly the same four (clamped) texels:
+// .w = (ix, iy) top-left, .z = (ix+1, iy) top-right, .x = (ix, iy+1) bottom-left, .y = (ix+1, iy+1) bottom-right.
+__device__ __forceinline__ void SamplePoint(cudaTextureObject_t tex, float x, float y, float* intensity, float* dx, float* dy) {
   const int ix = static_cast<int>(fmaxf(0.f, x - 0.5f));
   const int iy = static_cast<int>(fmaxf(0.f, y - 0.5f));
   const float tx = fmaxf(0.f, fminf(1.f, x - 0.5f - ix));
   const float ty = fmaxf(0.f, fminf(1.f, y - 0.5f - iy));
-  const float tl = tex2D<float>(tex, ix + 0.5f, iy + 0.5f);
-  const float tr = tex2D<float>(tex, ix + 1.5f, iy + 0.5f);
-  const float bl = tex2D<float>(tex, ix + 0.5f, iy + 1.5f);
-  const float br = tex2D<float>(tex, ix + 1.5f, iy + 1.5f);
-  *dx = (br - bl) * ty + (tr - tl) * (1 - ty);
-  *dy = (br - tr) * tx + (bl - tl) * (1 - tx);
+  const float4 g = tex2Dgather<float4>(tex, ix + 1.0f, iy + 1.0f, 0);
+  *intensity = tex2D<float>(tex, x, y);
+  *dx = (g.y - g.x) * ty + (g.z - g.w) * (1 - ty);
+  *dy = (g.y - g.z) * tx + (g.x - g.w) * (1 - tx);
 }
 
 struct DescEval {
@@ -237,15 +239,12 @@ struct DescEval {
 
 __device__ __forceinline__ void EvalDescriptor(cudaTextureObject_t tex, float cx, float cy, float t1x, float t1y, float t2x,
                                                float t2y, float d1, float d2, DescEval* e) {
-  const float intensity = tex2D<float>(tex, cx, cy);
-  const float t1i = tex2D<float>(tex, t1x, t1y);
-  const float t2i = tex2D<float>(tex, t2x, t2y);
+  float intensity, t1i, t2i, cdx, cdy, t1dx, t1dy, t2dx, t2dy;
+  SamplePoint(tex, cx, cy, &intensity, &cdx, &cdy);
+  SamplePoint(tex, t1x, t1y, &t1i, &t1dx, &t1dy);
+  SamplePoint(tex, t2x, t2y, &t2i, &t2dx, &t2dy);
   e->r1 = (180.f * (t1i - intensity)) - d1;
   e->r2 = (180.f * (t2i - intensity)) - d2;
-  float cdx, cdy, t1dx, t1dy, t2dx, t2dy;
-  PointGradient(tex, cx, cy, &cdx, &cdy);
-  PointGradient(tex, t1x, t1y, &t1dx, &t1dy);
-  PointGradient(tex, t2x, t2y, &t2dx, &t2dy);
   e->gx1 = 180.f * (t1dx - cdx);
   e->gy1 = 180.f * (t1dy - cdy);
   e->gx2 = 180.f * (t2dx - cdx);

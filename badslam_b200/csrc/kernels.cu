@@ -125,36 +125,31 @@ __device__ __forceinline__ float WarpTransposeReduce(float (&v)[32], int lane) {
 constexpr int kPoseThreads = 256;
 constexpr int kPoseWarps = kPoseThreads / 32;
 constexpr int kPoseStagedRows = 7;   // x y z normal radius^2 d1 d2
+constexpr int kPoseGroup = 8;        // keyframes per work item
+constexpr int kPoseChunk = 128;      // surfels per stolen sub-item
 
+// Work decomposition.  A work ITEM is (group of <= 8 keyframes from the work list) x (tile of TILE surfels); items are
+// handed out through a global counter in GROUP-MAJOR order, so at any moment all resident CTAs read the images of the
+// same 8-16 keyframes (~12-24 MB: stays in the 126 MB L2) while surfel tiles stream through shared memory via TMA.
+// Inside an item the 8 warps steal SUB-ITEMS (keyframe, 128-surfel chunk) from a shared-memory counter, which evens out
+// the very different cost of culled vs. associated chunks.
 template <int TILE>
 __global__ void __launch_bounds__(kPoseThreads, 2) PoseAccumulateKernel(const __grid_constant__ PoseAccumulateArgs args) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stage_base = reinterpret_cast<float*>(smem_raw);   // [2][7][TILE]
   __shared__ __align__(8) uint64_t full_bar[2];
+  __shared__ unsigned int s_item[2];
+  __shared__ int s_sub[2];
 
   const int n_work = __ldg(args.work_count);
   if (n_work <= 0) return;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
-  const int warp = tid >> 5;
   const uint32_t n_tiles = (args.n + TILE - 1) / TILE;
-  if (blockIdx.x >= n_tiles) return;
-
-  if (tid == 0) {
-    MbarInit(&full_bar[0], 1);
-    MbarInit(&full_bar[1], 1);
-    FenceBarrierInit();
-  }
-  __syncthreads();
-
-  // With fewer keyframes than warps (e.g. EstimateFramePose of a single frame) every tile is split into
-  // 2, 4 or 8 parts so that all warps of the CTA have work.
-  int split_shift = 0;
-  if (n_work < kPoseWarps) split_shift = 31 - __clz(kPoseWarps / n_work);
-  const int n_split = 1 << split_shift;
-  const int n_items = n_work << split_shift;
-  const uint32_t part_len = TILE >> split_shift;
+  const uint32_t n_groups = (n_work + kPoseGroup - 1) / kPoseGroup;
+  const uint32_t n_items = n_groups * n_tiles;
+  constexpr int kChunksPerTile = TILE / kPoseChunk;
 
   const CameraParams& cam = args.cam;
   constexpr int kRowIds[kPoseStagedRows] = {kRowX, kRowY, kRowZ, kRowNormal, kRowRadiusSq, kRowD1, kRowD2};
@@ -171,14 +166,27 @@ __global__ void __launch_bounds__(kPoseThreads, 2) PoseAccumulateKernel(const __
     }
   };
 
-  if (tid == 0) issue_tile(blockIdx.x, 0);
+  if (tid == 0) {
+    MbarInit(&full_bar[0], 1);
+    MbarInit(&full_bar[1], 1);
+    FenceBarrierInit();
+    s_sub[0] = 0;
+    s_sub[1] = 0;
+    const unsigned int first = atomicAdd(args.queue, 1u);
+    s_item[0] = first;
+    if (first < n_items) issue_tile(first % n_tiles, 0);
+  }
+  __syncthreads();
 
-  uint32_t it = 0;
-  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+  for (uint32_t it = 0;; ++it) {
     const int s = it & 1;
+    const unsigned int item = s_item[s];
+    if (item >= n_items) break;
     if (tid == 0) {
-      const uint32_t next = tile + gridDim.x;
-      if (next < n_tiles) issue_tile(next, s ^ 1);   // stage s^1 was released by the __syncthreads below
+      // stage s^1 was released by the __syncthreads that ended the previous iteration
+      const unsigned int next = atomicAdd(args.queue, 1u);
+      s_item[s ^ 1] = next;
+      if (next < n_items) issue_tile(next % n_tiles, s ^ 1);
     }
     MbarWait(&full_bar[s], (it >> 1) & 1);
 
@@ -189,14 +197,23 @@ __global__ void __launch_bounds__(kPoseThreads, 2) PoseAccumulateKernel(const __
     const float* sr = sn + TILE;
     const float* sd1 = sr + TILE;
     const float* sd2 = sd1 + TILE;
+    const uint32_t group = item / n_tiles;
+    const uint32_t tile = item - group * n_tiles;
     const uint32_t base = tile * TILE;
     const uint32_t cnt = min(static_cast<uint32_t>(TILE), args.n - base);
+    const int kfs_in_group = min(kPoseGroup, n_work - static_cast<int>(group) * kPoseGroup);
+    const int n_sub = kfs_in_group * kChunksPerTile;
 
-    for (int wi = warp; wi < n_items; wi += kPoseWarps) {
-      const int kf = __ldg(args.work_list + (wi >> split_shift));
-      const uint32_t j0 = static_cast<uint32_t>(wi & (n_split - 1)) * part_len;
+    for (;;) {
+      int sub = 0;
+      if (lane == 0) sub = atomicAdd(&s_sub[s], 1);
+      sub = __shfl_sync(0xffffffffu, sub, 0);
+      if (sub >= n_sub) break;
+      const int kf_local = sub / kChunksPerTile;
+      const uint32_t j0 = static_cast<uint32_t>(sub - kf_local * kChunksPerTile) * kPoseChunk;
       if (j0 >= cnt) continue;
-      const uint32_t j1 = min(cnt, j0 + part_len);
+      const uint32_t j1 = min(cnt, j0 + kPoseChunk);
+      const int kf = __ldg(args.work_list + group * kPoseGroup + kf_local);
       KfRegs K;
       LoadKf(args.kfs, kf, &K);
 
@@ -213,7 +230,7 @@ __global__ void __launch_bounds__(kPoseThreads, 2) PoseAccumulateKernel(const __
         Vec3 gp, nrm;
         if (j < j1) {
           gp = V3(sx[j], sy[j], sz[j]);
-          // cheap frustum part first; unpack the normal only if the surfel lands in the image
+          // cheap frustum part first; unpack the normal only if the surfel is in front of the camera
           const float z = K.T[8] * gp.x + K.T[9] * gp.y + K.T[10] * gp.z + K.T[11];
           if (z > 0.f) {
             nrm = UnpackNormal(__float_as_uint(sn[j]));
@@ -270,7 +287,8 @@ __global__ void __launch_bounds__(kPoseThreads, 2) PoseAccumulateKernel(const __
         if (n_depthok) atomicAdd(args.stage_counts + 2 * kf + 1, static_cast<unsigned long long>(n_depthok));
       }
     }
-    __syncthreads();   // every warp is done with stage s before it is refilled
+    __syncthreads();   // every warp is done with stage s (and with s_item[s]) before either is refilled
+    if (tid == 0) s_sub[s] = 0;
   }
 }
 
@@ -282,15 +300,13 @@ static void LaunchPoseAccumulateT(const PoseAccumulateArgs& args, int sm_count, 
     cudaFuncSetAttribute(PoseAccumulateKernel<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     configured = true;
   }
-  const uint32_t n_tiles = (args.n + TILE - 1) / TILE;
-  const uint32_t grid = min(n_tiles, static_cast<uint32_t>(2 * sm_count));   // persistent: 2 CTAs per SM
-  PoseAccumulateKernel<TILE><<<grid, kPoseThreads, smem, stream>>>(args);
+  PoseAccumulateKernel<TILE><<<2 * sm_count, kPoseThreads, smem, stream>>>(args);   // persistent: 2 CTAs per SM
 }
 
 void LaunchPoseAccumulate(const PoseAccumulateArgs& args, int sm_count, cudaStream_t stream) {
   if (args.n == 0) return;
-  // Pick the tile so that there are at least ~4 tiles per resident CTA (tail balance), but as large as possible
-  // (the warp-level reduction is paid once per (tile, keyframe)).
+  // Tile size: as large as possible (one TMA transaction + one CTA barrier per item), but small enough that a
+  // keyframe group still yields several items per resident CTA.
   const uint64_t slots = static_cast<uint64_t>(2 * sm_count) * 4;
   if (args.n >= slots * 1024) LaunchPoseAccumulateT<1024>(args, sm_count, stream);
   else if (args.n >= slots * 512) LaunchPoseAccumulateT<512>(args, sm_count, stream);

@@ -24,6 +24,7 @@ struct PoseAccumulateArgs {
   const int* work_count;     // device scalar
   double* acc;               // [max_kf][32]
   unsigned long long* stage_counts;  // [max_kf][2]
+  unsigned int* queue;       // global work-item counter, must be 0 at launch
 };
 
 // Persistent, TMA-staged pose residual/Jacobian/Hessian kernel (AccumulatePoseEstimationCoeffsCUDAKernel,
@@ -42,6 +43,9 @@ struct PoseSolveArgs {
   int* iterations;             // [max_kf]
   int* converged;              // [max_kf]
   double* first_stats;         // [max_kf][8]: n_assoc n_photo cost_depth cost_desc1 cost_desc2 n_inimg n_depthok (iteration 0)
+  unsigned long long* totals;  // [8] cumulative: kf_evals, n_inimg, n_depthok, n_assoc, n_photo (over all iterations)
+  volatile int* host_flag;     // mapped pinned memory: {iterations completed, work items left}
+  unsigned int* queue;         // PoseAccumulateKernel's work-item counter, re-armed here
   int iteration;
   int max_iterations;
 };

@@ -14,8 +14,10 @@ namespace bba {
 
 __global__ void __launch_bounds__(256) PoseSolveKernel(const PoseSolveArgs a) {
   __shared__ int next_count;
+  __shared__ unsigned long long tot[5];
   const int count = *a.count_in;
   if (threadIdx.x == 0) next_count = 0;
+  if (threadIdx.x < 5) tot[threadIdx.x] = 0ull;
   __syncthreads();
   for (int i = threadIdx.x; i < count; i += blockDim.x) {
     const int kf = a.work_in[i];
@@ -32,6 +34,11 @@ __global__ void __launch_bounds__(256) PoseSolveKernel(const PoseSolveArgs a) {
       fs[6] = static_cast<double>(a.stage_counts[2 * kf + 1]);
       fs[7] = 0.0;
     }
+    atomicAdd(&tot[0], 1ull);
+    atomicAdd(&tot[1], a.stage_counts[2 * kf]);
+    atomicAdd(&tot[2], a.stage_counts[2 * kf + 1]);
+    atomicAdd(&tot[3], static_cast<unsigned long long>(acc[27] + 0.5));
+    atomicAdd(&tot[4], static_cast<unsigned long long>(acc[28] + 0.5));
     for (int j = 0; j < kPoseAccSize; ++j) acc[j] = 0.0;
     a.stage_counts[2 * kf] = 0ull;
     a.stage_counts[2 * kf + 1] = 0ull;
@@ -62,7 +69,16 @@ __global__ void __launch_bounds__(256) PoseSolveKernel(const PoseSolveArgs a) {
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) *a.count_out = next_count;
+  if (threadIdx.x < 5 && tot[threadIdx.x]) atomicAdd(a.totals + threadIdx.x, tot[threadIdx.x]);
+  if (threadIdx.x == 0) {
+    *a.queue = 0u;
+    *a.count_out = next_count;
+    // Publish progress to the host (zero-copy) so that it can stop enqueueing iterations once every keyframe
+    // has converged, without ever blocking the stream.
+    a.host_flag[1] = next_count;
+    __threadfence_system();
+    a.host_flag[0] = a.iteration + 1;
+  }
 }
 
 void LaunchPoseSolve(const PoseSolveArgs& args, cudaStream_t stream) { PoseSolveKernel<<<1, 256, 0, stream>>>(args); }

@@ -285,6 +285,35 @@ class DirectBA:
         c = np.ascontiguousarray(cfactor, np.float32)
         self._check(self._lib.bba_set_cfactor_host(self._h, c.ctypes.data, self._stream_ptr(stream)))
 
+    def SetKeyframeStates(self, poses=None, activations=None):
+        K = len(self._keyframes)
+        p = None if poses is None else np.ascontiguousarray(poses, np.float32)
+        a = None if activations is None else np.ascontiguousarray(activations, np.int32)
+        self._check(self._lib.bba_set_keyframe_states(self._h, K, None if p is None else p.ctypes.data,
+                                                      None if a is None else a.ctypes.data))
+
+    def GetKeyframeStates(self):
+        K = len(self._keyframes)
+        p = np.zeros((K, 7), np.float32)
+        a = np.zeros(K, np.int32)
+        self._check(self._lib.bba_get_keyframe_states(self._h, K, p.ctypes.data, a.ctypes.data))
+        return p, a
+
+    def SurfelsDeviceView(self) -> torch.Tensor:
+        """The 17-row surfel buffer as a torch tensor, whoever owns it (zero-copy)."""
+        if self._surfels is not None:
+            return self._surfels
+        ptr, pitch, n = C.c_void_p(), C.c_size_t(), C.c_uint32()
+        self._check(self._lib.bba_get_surfels_device(self._h, C.byref(ptr), C.byref(pitch), C.byref(n)))
+
+        class _Raw:
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {"shape": (17, pitch.value // 4), "typestr": "<f4", "data": (ptr.value, False),
+                                        "version": 2, "strides": None}
+        self._raw_keepalive = raw
+        return torch.as_tensor(raw, device=self.device)
+
     def covisibility(self) -> np.ndarray:
         K = len(self._keyframes)
         out = np.zeros((K, K), np.uint8)
@@ -342,10 +371,48 @@ class DirectBA:
     def kernel_launch_count(self) -> int:
         return int(self._lib.bba_kernel_launch_count(self._h))
 
+    def SetProfiling(self, enable: bool):
+        self._check(self._lib.bba_set_profiling(self._h, int(enable)))
+
+    def GetProfile(self, reset: bool = False) -> dict:
+        p = _lib.Profile()
+        self._check(self._lib.bba_get_profile(self._h, C.byref(p), int(reset)))
+        return {name: getattr(p, name) for name, _ in p._fields_}
+
+    def AddKeyframeHost(self, depth, normals, radius, color, global_T_frame, min_depth, max_depth, stream=None) -> int:
+        """Keyframe whose device buffers are owned by the library (uploaded from host arrays)."""
+        out = C.c_int(-1)
+        pose = np.ascontiguousarray(global_T_frame, np.float32)
+        arrs = [np.ascontiguousarray(a) for a in (depth, normals, radius, color)]
+        self._check(self._lib.bba_add_keyframe_host(self._h, arrs[0].ctypes.data, arrs[1].ctypes.data, arrs[2].ctypes.data,
+                                                    arrs[3].ctypes.data, pose.ctypes.data_as(C.POINTER(C.c_float)),
+                                                    float(min_depth), float(max_depth), self._stream_ptr(stream), C.byref(out)))
+        kf = Keyframe.__new__(Keyframe)
+        kf.frame_index, kf.min_depth, kf.max_depth = out.value, float(min_depth), float(max_depth)
+        kf.depth_buffer = kf.normals_buffer = kf.radius_buffer = kf.color_buffer = None
+        kf._global_T_frame = pose.copy()
+        kf.id, kf._ba = out.value, self
+        self._keyframes.append(kf)
+        return out.value
+
+    def UpdateKeyframeHost(self, keyframe_id: int, depth=None, normals=None, radius=None, color=None, stream=None):
+        """bba_update_keyframe_host: re-uploads keyframe images from (pinned) host memory."""
+        def ptr(a):
+            if a is None:
+                return None
+            if isinstance(a, torch.Tensor):
+                return a.data_ptr()
+            return a.ctypes.data
+        self._check(self._lib.bba_update_keyframe_host(self._h, keyframe_id, ptr(depth), ptr(normals), ptr(radius), ptr(color),
+                                                       self._stream_ptr(stream)))
+
     # -- convenience: build from a synthetic scene ---------------------------------------------------
     @classmethod
     def from_scene(cls, scene, poses=None, use_depth_residuals=True, use_descriptor_residuals=True,
-                   device=None, max_keyframes=None, **kw):
+                   device=None, max_keyframes=None, host_owned=False, **kw):
+        """Builds a DirectBA from a synthetic scene.  host_owned=True uploads everything through the `_host`
+        entry points (library-owned device memory) -- the e2e path of bench.py."""
+        kw_host_owned = host_owned
         cfg = scene.cfg
         cam_d = PinholeCamera4f(cfg.width, cfg.height, scene.depth_K)
         cam_c = PinholeCamera4f(cfg.width, cfg.height, scene.color_K)
@@ -356,6 +423,16 @@ class DirectBA:
                  use_descriptor_residuals=use_descriptor_residuals, device=device,
                  max_keyframes=max_keyframes or max(cfg.num_keyframes, 1), **kw)
         poses = scene.poses_init if poses is None else poses
+        if kw_host_owned:
+            for k in range(cfg.num_keyframes):
+                ba.AddKeyframeHost(scene.depth[k], scene.normals[k], scene.radius[k], scene.color[k], poses[k],
+                                   scene.min_depth[k], scene.max_depth[k])
+            ba.SetSurfelsHost(scene.surfels, scene.num_surfels)
+            if scene.depth_a != 0.0:
+                ba.SetA(scene.depth_a)
+            if np.any(scene.cfactor != 0):
+                ba.SetCFactorBuffer(scene.cfactor)
+            return ba
         for k in range(cfg.num_keyframes):
             kf = Keyframe.from_host(k, scene.depth[k], scene.normals[k], scene.radius[k], scene.color[k], poses[k],
                                     scene.min_depth[k], scene.max_depth[k], device)

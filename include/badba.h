@@ -145,6 +145,9 @@ bba_status bba_set_keyframe_pose(bba_handle h, int keyframe_id, const float glob
 bba_status bba_get_keyframe_pose(bba_handle h, int keyframe_id, float global_T_frame[7]);         /* Keyframe::global_T_frame */
 bba_status bba_set_keyframe_activation(bba_handle h, int keyframe_id, int activation);            /* Keyframe::SetActivation */
 bba_status bba_get_keyframe_activation(bba_handle h, int keyframe_id, int* activation);
+/* Bulk variants over keyframes [0, count): poses [count][7], activations [count] (either may be NULL). */
+bba_status bba_set_keyframe_states(bba_handle h, int count, const float* global_T_frame, const int* activation);
+bba_status bba_get_keyframe_states(bba_handle h, int count, float* global_T_frame, int* activation);
 bba_status bba_get_covisibility(bba_handle h, int keyframe_id, uint8_t* out_row /* [keyframe_count] */);
 
 /* depth_params_ / cameras (direct_ba.h:243-297; SetColorCamera etc.) */
@@ -177,8 +180,29 @@ bba_status bba_bundle_adjust(bba_handle h, const bba_ba_options* options, bba_ba
  * enqueued on `stream` (the harness implements it with torch.distributed / NCCL). */
 bba_status bba_set_allgather(bba_handle h, bba_allgather_fn fn, void* user);
 
+/* Re-uploads the images of an existing keyframe from host memory (same sizes as at creation) -- the per-step
+ * host->device input path of a live system, where a keyframe's RGB-D data arrives from the sensor thread
+ * (BadSlam::CreateKeyframe, bad_slam.cc).  NULL pointers leave the corresponding buffer untouched. */
+bba_status bba_update_keyframe_host(bba_handle h, int keyframe_id,
+                                    const uint16_t* host_depth, const uint16_t* host_normals,
+                                    const uint16_t* host_radius, const uint8_t* host_color_rgba, void* stream);
+
 /* ---- instrumentation ---- */
 uint64_t   bba_kernel_launch_count(bba_handle h);   /* kernels launched through this handle so far */
+
+/* Per-kernel device timing (cudaEvents on the launching stream) and the counters of the algorithmic-bytes
+ * model of SURVEY.md 8d, accumulated over every pose / geometry launch while profiling is enabled. */
+typedef struct {
+  uint64_t pose_launches;        /* PoseAccumulateKernel launches (non-empty work list) */
+  double   pose_ms;              /* their summed device time */
+  uint64_t kf_evals;             /* sum over launches of keyframes in the work list */
+  uint64_t n_pair, n_inimg, n_depthok, n_assoc, n_photo;   /* summed over those launches */
+  uint64_t geometry_launches;
+  double   activation_normals_ms;
+  double   position_descriptor_ms;
+} bba_profile;
+bba_status bba_set_profiling(bba_handle h, int enable);
+bba_status bba_get_profile(bba_handle h, bba_profile* out, int reset);
 
 #ifdef __cplusplus
 }

@@ -411,8 +411,8 @@ void orc_pose_coeffs(const orc_model* m, const orc_keyframes* kfs, int k, const 
   if (!use_depth) out->cost_depth = 0;
 }
 
-int orc_pair_residuals(const orc_model* m, const orc_keyframes* kfs, int k, const float T[12],
-                       const float surfel[8], float r_out[3], float J_pose[18], float J_geom[9]) {
+int orc_pair_residuals_debug(const orc_model* m, const orc_keyframes* kfs, int k, const float T[12],
+                             const float surfel[8], float r_out[3], float J_pose[18], float J_geom[9], float dbg[16]) {
   kfview v;
   make_view(m, kfs, k, &v);
   assoc r;
@@ -420,12 +420,14 @@ int orc_pair_residuals(const orc_model* m, const orc_keyframes* kfs, int k, cons
   memset(r_out, 0, 3 * sizeof(float));
   memset(J_pose, 0, 18 * sizeof(float));
   memset(J_geom, 0, 9 * sizeof(float));
+  if (dbg) memset(dbg, 0, 16 * sizeof(float));
   if (st < 3) return 0;
   int flags = 1;
   f3 ln = T_rot(T, r.n);
   float inv_stddev;
   r_out[0] = depth_pose_residual_jacobian(&v, &r, ln, J_pose, &inv_stddev, NULL);
   J_geom[0] = -inv_stddev;  /* kernel_opt_geometry.cu:138 */
+  if (dbg) { dbg[0] = (float)r.px; dbg[1] = (float)r.py; dbg[2] = r.d; dbg[3] = inv_stddev; }
   float ccx, ccy;
   if (depth_to_color(&v, r.pxf, r.pyf, &ccx, &ccy)) {
     flags |= 2;
@@ -445,8 +447,17 @@ int orc_pair_residuals(const orc_model* m, const orc_keyframes* kfs, int k, cons
     J_geom[6] = -(e.gx2 * term1 + e.gy2 * term2) * term3;
     J_geom[4] = -1.f;
     J_geom[8] = -1.f;
+    if (dbg) {
+      dbg[4] = ccx; dbg[5] = ccy; dbg[6] = t1x; dbg[7] = t1y; dbg[8] = t2x; dbg[9] = t2y;
+      dbg[10] = e.gx1; dbg[11] = e.gy1; dbg[12] = e.gx2; dbg[13] = e.gy2;
+    }
   }
   return flags;
+}
+
+int orc_pair_residuals(const orc_model* m, const orc_keyframes* kfs, int k, const float T[12],
+                       const float surfel[8], float r_out[3], float J_pose[18], float J_geom[9]) {
+  return orc_pair_residuals_debug(m, kfs, k, T, surfel, r_out, J_pose, J_geom, NULL);
 }
 
 /* direct_ba_alternating.cc:42-283 */

@@ -140,6 +140,11 @@ void orc_bundle_adjust(orc_model* m, orc_keyframes* kfs,
 int orc_pair_residuals(const orc_model* m, const orc_keyframes* kfs, int k,
                        const float frame_T_global[12],
                        const float surfel[8], float r[3], float J_pose[18], float J_geom[9]);
+/* Same, plus the intermediate quantities (for the known-answer tests):
+ * dbg[16] = px, py, calibrated depth, inv_stddev, colour x, colour y, t1x, t1y, t2x, t2y, gx1, gy1, gx2, gy2, 0, 0 */
+int orc_pair_residuals_debug(const orc_model* m, const orc_keyframes* kfs, int k,
+                             const float frame_T_global[12],
+                             const float surfel[8], float r[3], float J_pose[18], float J_geom[9], float dbg[16]);
 
 /* Sampling helper exposed for the generator / hardware validation. */
 float orc_tex_luma(const orc_model* m, const orc_keyframes* kfs, int k, float x, float y);

@@ -73,6 +73,7 @@ def lib():
         _lib.orc_tex_luma.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float]
         _lib.orc_estimate_frame_pose.restype = C.c_int
         _lib.orc_pair_residuals.restype = C.c_int
+        _lib.orc_pair_residuals_debug.restype = C.c_int
         _lib.orc_get_max_threads.restype = C.c_int
     return _lib
 
@@ -182,8 +183,11 @@ class Oracle:
         r = np.zeros(3, np.float32)
         Jp = np.zeros(18, np.float32)
         Jg = np.zeros(9, np.float32)
-        flags = self.lib.orc_pair_residuals(C.byref(self.model), C.byref(self.kfs), C.c_int(k), _p(T, C.c_float),
-                                            _p(s, C.c_float), _p(r, C.c_float), _p(Jp, C.c_float), _p(Jg, C.c_float))
+        dbg = np.zeros(16, np.float32)
+        flags = self.lib.orc_pair_residuals_debug(C.byref(self.model), C.byref(self.kfs), C.c_int(k), _p(T, C.c_float),
+                                                  _p(s, C.c_float), _p(r, C.c_float), _p(Jp, C.c_float), _p(Jg, C.c_float),
+                                                  _p(dbg, C.c_float))
+        self.last_debug = dbg
         return flags, r, Jp.reshape(3, 6), Jg.reshape(3, 3)
 
     def tex_luma(self, k, x, y):

@@ -63,6 +63,9 @@ def lib():
         l.ref_update_activation.argtypes = [C.c_void_p]
         l.ref_optimize_geometry_iteration.argtypes = [C.c_void_p]
         l.ref_bundle_adjust.argtypes = [C.c_void_p, C.POINTER(BAOptions), C.POINTER(BAResult), C.c_int]
+        l.ref_snapshot.argtypes = [C.c_void_p]
+        l.ref_restore.argtypes = [C.c_void_p]
+        l.ref_sync.argtypes = [C.c_void_p]
         l.ref_last_cuda_error.restype = C.c_char_p
         _lib = l
     return _lib
@@ -182,6 +185,15 @@ class RefDirectBA:
         r = BAResult()
         self.l.ref_bundle_adjust(self.h, C.byref(o), C.byref(r), int(count_residuals))
         return r
+
+    def snapshot(self):
+        self.l.ref_snapshot(self.h)
+
+    def restore(self):
+        self.l.ref_restore(self.h)
+
+    def sync(self):
+        self.l.ref_sync(self.h)
 
     def launch_count(self):
         return int(self.l.ref_launch_count(self.h))

@@ -472,6 +472,26 @@ void ref_bundle_adjust(ref_context* c, const ref_ba_options* o, ref_ba_result* r
   res->kernel_launches = c->launches - launches_before;
 }
 
+// Device-side snapshot / restore of the mutable state (surfel data rows, poses, activations) for benchmarking
+// repeated steps from the same starting point without host traffic.
+static float* g_snapshot = nullptr;
+static size_t g_snapshot_pitch = 0;
+static std::vector<RefKeyframe> g_snapshot_kfs;
+void ref_snapshot(ref_context* c) {
+  if (!g_snapshot) cudaMallocPitch(reinterpret_cast<void**>(&g_snapshot), &g_snapshot_pitch, static_cast<size_t>(c->max_surfels) * 4, 8);
+  cudaMemcpy2D(g_snapshot, g_snapshot_pitch, c->surfels, c->surfel_pitch, static_cast<size_t>(c->surfels_size) * 4, 8, cudaMemcpyDeviceToDevice);
+  g_snapshot_kfs = c->kfs;
+}
+void ref_restore(ref_context* c) {
+  cudaMemcpy2DAsync(c->surfels, c->surfel_pitch, g_snapshot, g_snapshot_pitch, static_cast<size_t>(c->surfels_size) * 4, 8,
+                    cudaMemcpyDeviceToDevice, c->stream);
+  for (size_t k = 0; k < c->kfs.size(); ++k) {
+    std::memcpy(c->kfs[k].pose, g_snapshot_kfs[k].pose, sizeof(float) * 7);
+    c->kfs[k].activation = g_snapshot_kfs[k].activation;
+  }
+}
+void ref_sync(ref_context* c) { cudaStreamSynchronize(c->stream); }
+
 const char* ref_last_cuda_error(void) { return cudaGetErrorString(cudaGetLastError()); }
 
 }  // extern "C"

@@ -1,0 +1,70 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/badba.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "badba.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = set(re.findall(r"\b(bba_[a-z_0-9]+)\s*\(", src))
+    names -= {"bba_allgather_fn"}
+    return sorted(names)
+
+
+def test_header_declares_the_hot_path():
+    names = declared_symbols()
+    for required in ("bba_create", "bba_destroy", "bba_add_keyframe", "bba_set_surfels", "bba_accumulate_pose_coeffs",
+                     "bba_estimate_frame_pose", "bba_update_surfel_activation", "bba_optimize_geometry_iteration",
+                     "bba_optimize_intrinsics", "bba_bundle_adjust"):
+        assert required in names
+
+
+def test_library_exports_every_declared_symbol():
+    from badslam_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "build libbadba_b200.so first (python -m badslam_b200.build)"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(lib, name), f"{name} declared in include/badba.h but not exported"
+    # and the python binding types every one of them
+    assert set(declared_symbols()) == set(_lib.SYMBOLS.keys())
+    assert _lib.load().bba_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_a_device():
+    """Without a GPU the product path must fail loudly, not fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from badslam_b200 import _lib
+    lib = _lib.load()
+    cfg = _lib.Config()
+    cfg.depth_width = cfg.color_width = 64
+    cfg.depth_height = cfg.color_height = 48
+    cfg.depth_intrinsics[:] = [30, 30, 32, 24]
+    cfg.color_intrinsics[:] = [30, 30, 32, 24]
+    cfg.raw_to_float_depth, cfg.baseline_fx, cfg.sparse_surfel_cell_size = 1e-3, 40, 4
+    cfg.max_surfel_count, cfg.max_keyframes = 1024, 4
+    cfg.use_depth_residuals = cfg.use_descriptor_residuals = 1
+    cfg.world_size = 1
+    h = ctypes.c_void_p()
+    assert lib.bba_create(ctypes.byref(cfg), ctypes.byref(h)) == _lib.ERR_NO_DEVICE
+    from badslam_b200.direct_ba import DirectBA, PinholeCamera4f
+    cam = PinholeCamera4f(64, 48, [30, 30, 32, 24])
+    with pytest.raises(_lib.BadBAError):
+        DirectBA(1024, 1e-3, 40, 4, color_camera_initial_estimate=cam, depth_camera_initial_estimate=cam)
+
+
+def test_product_does_not_import_the_oracle():
+    """Nothing under badslam_b200/ may reference oracle/ (the oracle is test infrastructure)."""
+    pkg = os.path.join(ROOT, "badslam_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f
+                assert '#include "../../oracle' not in txt and "oracle/host_math" not in txt, f

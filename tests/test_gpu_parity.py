@@ -1,0 +1,260 @@
+"""GPU parity tests (run with `-m gpu` on the B200 box): the sm_100a path, called through the C ABI, against
+(a) the reference's own CUDA kernels (oracle/_ref), (b) the CPU oracle and (c) the committed golden fixtures.
+
+Tolerances (BASELINE.json north_star): 1e-4 relative on residual sums / normal-equation coefficients,
+1e-5 m / 1e-5 rad on poses; counts are integers and must match exactly unless noted.
+"""
+import copy
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-4
+POSE_T, POSE_R = 1e-5, 1e-5
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-30))
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import torch
+    assert torch.cuda.is_available()
+    from badslam_b200 import scene as S
+    from badslam_b200.direct_ba import DirectBA
+    from oracle import cpu_oracle, ref_cuda
+    assert ref_cuda.available(), "oracle/_ref/libbadslam_ref.so missing (oracle/build_ref.sh)"
+    return S, DirectBA, cpu_oracle, ref_cuda
+
+
+def test_pose_coefficients_three_way(mods, small_scene):
+    S, DirectBA, O, R = mods
+    sc = small_scene
+    ba, ref, orc = DirectBA.from_scene(sc), R.RefDirectBA(sc), O.Oracle(sc)
+    for k in range(sc.cfg.num_keyframes):
+        pc = ba.AccumulatePoseEstimationCoeffs(k, sc.poses_init[k])
+        H, b, cnt, cost = ref.pose_coeffs(k, sc.poses_init[k])
+        st = orc.pose_coeffs(k)
+        # counters: exact against the reference's debug counter and the oracle's stage counters
+        assert pc.n_assoc + pc.n_photo == cnt
+        assert (pc.n_pair, pc.n_inimg, pc.n_depthok, pc.n_assoc, pc.n_photo) == (st.n_pair, st.n_inimg, st.n_depthok, st.n_assoc, st.n_photo)
+        assert pc.n_pair >= pc.n_inimg >= pc.n_depthok >= pc.n_assoc >= pc.n_photo
+        # normal equations and residual sums: 1e-4 relative to the reference
+        assert rel(pc.H[:], H) < REL and rel(pc.b[:], b) < REL
+        assert abs(pc.cost_depth + pc.cost_desc1 - cost) < REL * cost
+        # and the CPU oracle agrees with both (its texture filter is an emulation: slightly looser on b)
+        assert rel(pc.H[:], st.H[:]) < REL and rel(pc.b[:], st.b[:]) < 3 * REL
+        assert abs(pc.cost_depth - st.cost_depth) < REL * max(st.cost_depth, 1.0)
+        assert abs(pc.cost_desc1 - st.cost_desc1) < 2 * REL * st.cost_desc1
+        assert abs(pc.cost_desc2 - st.cost_desc2) < 2 * REL * st.cost_desc2
+
+
+@pytest.mark.parametrize("use_depth,use_desc", [(True, False), (False, True)])
+def test_single_residual_type(mods, tiny_scene, use_depth, use_desc):
+    S, DirectBA, O, R = mods
+    sc = tiny_scene
+    ba = DirectBA.from_scene(sc, use_depth_residuals=use_depth, use_descriptor_residuals=use_desc)
+    ref = R.RefDirectBA(sc, use_depth, use_desc)
+    for k in range(sc.cfg.num_keyframes):
+        pc = ba.AccumulatePoseEstimationCoeffs(k, sc.poses_init[k])
+        H, b, cnt, cost = ref.pose_coeffs(k, sc.poses_init[k])
+        assert rel(pc.H[:], H) < REL and rel(pc.b[:], b) < REL
+        expect = (pc.n_assoc if use_depth else 0) + (pc.n_photo if use_desc else 0)
+        assert expect == cnt
+    ba.UpdateSurfelActivation(); ref.update_activation()
+    ba.OptimizeGeometryIteration(); ref.optimize_geometry_iteration()
+    a, b_ = ba.GetSurfelsHost(), ref.surfels()
+    assert np.max(np.abs(a[:3] - b_[:3])) < 2e-6
+    assert np.array_equal(a[3].view(np.uint32), b_[3].view(np.uint32))
+    assert np.max(np.abs(a[6:8] - b_[6:8])) < 2e-3
+
+
+def test_estimate_frame_pose(mods, small_scene):
+    S, DirectBA, O, R = mods
+    sc = small_scene
+    ba, ref, orc = DirectBA.from_scene(sc), R.RefDirectBA(sc), O.Oracle(sc)
+    for k in range(sc.cfg.num_keyframes):
+        pp, ip, cp = ba.EstimateFramePose(None, sc.poses_init[k], k)
+        pr, ir, cr = ref.estimate_frame_pose(k, sc.poses_init[k])
+        po, io, co = orc.estimate_frame_pose(k)
+        dt, dr = S.pose_error(pp, pr)
+        assert dt < POSE_T and dr < POSE_R, (k, dt, dr)
+        assert ip == ir and cp == cr
+        dt, dr = S.pose_error(po, pr)      # the oracle is pinned by the reference as well
+        assert dt < POSE_T and dr < POSE_R, (k, dt, dr)
+    # EstimateFramePose does not change the stored keyframe pose (direct_ba.h:122-129 returns the estimate)
+    assert np.allclose(ba.keyframes()[0].global_T_frame(), sc.poses_init[0])
+
+
+def test_activation_and_geometry(mods, small_scene):
+    S, DirectBA, O, R = mods
+    sc = small_scene
+    ba, ref, orc = DirectBA.from_scene(sc), R.RefDirectBA(sc), O.Oracle(sc)
+    # make keyframe 1 inactive and 2 covisible-active to exercise the activation rules
+    for obj_set in (lambda k, a: ba.keyframes()[k].SetActivation(a), ref.set_activation):
+        obj_set(1, 2)
+        obj_set(2, 1)
+    orc.activation[1], orc.activation[2] = 2, 1
+    ba.UpdateSurfelActivation(); ref.update_activation(); orc.update_activation()
+    fa, fr, fo = ba.GetActiveHost(), ref.active(), orc.active[:sc.num_surfels]
+    assert np.array_equal(fa, fr) and np.array_equal(fo, fr)
+    assert 0 < fr.sum() <= sc.num_surfels
+    ba.OptimizeGeometryIteration(); ref.optimize_geometry_iteration(); orc.optimize_geometry_iteration()
+    a, b_, c = ba.GetSurfelsHost(), ref.surfels(), orc.surfels[:8, :sc.num_surfels]
+    assert np.max(np.abs(a[:3] - b_[:3])) < 2e-6                      # positions (m)
+    assert (a[3].view(np.uint32) != b_[3].view(np.uint32)).sum() == 0  # packed normals
+    assert np.max(np.abs(a[6:8] - b_[6:8])) < 2e-3                    # descriptors (range +-180)
+    assert np.array_equal(a[4:6].view(np.uint32), sc.surfels[4:6, :sc.num_surfels].view(np.uint32))   # radius / colour untouched
+    assert np.max(np.abs(c[:3] - b_[:3])) < 5e-4 and (c[3].view(np.uint32) != b_[3].view(np.uint32)).mean() < 1e-3
+    moved = np.abs(b_[:3] - sc.surfels[:3, :sc.num_surfels]).max()
+    assert moved > 1e-4      # the step did something
+
+
+def test_bundle_adjustment_against_reference(mods, small_scene):
+    S, DirectBA, O, R = mods
+    sc = small_scene
+    K = sc.cfg.num_keyframes
+    ba, ref, ref2 = DirectBA.from_scene(sc), R.RefDirectBA(sc), R.RefDirectBA(sc)
+    ro = ba.BundleAdjustment(None, False, False, False, True, True, 3, 3)
+    rr = ref.bundle_adjust(True, True, 3, 3)
+    ref2.bundle_adjust(True, True, 3, 3)
+    assert ro.iterations_done == rr.iterations_done == 3
+    assert ro.pose_iterations_total == rr.pose_iterations_total
+    ours_pairs = ro.depth_residual_count + ro.descriptor_residual_count // 2
+    assert abs(ours_pairs - rr.n_count) <= max(2, 1e-5 * rr.n_count)      # association flips near thresholds
+    assert abs(ro.cost - rr.cost) < REL * rr.cost
+    self_noise = max(max(S.pose_error(ref.pose(k), ref2.pose(k))) for k in range(K))
+    for k in range(K):
+        dt, dr = S.pose_error(ba.keyframes()[k].global_T_frame(), ref.pose(k))
+        assert dt < POSE_T + 2 * self_noise and dr < POSE_R + 2 * self_noise, (k, dt, dr, self_noise)
+    assert np.array_equal(ba.GetKeyframeStates()[1], ref.activation())
+    a, b_ = ba.GetSurfelsHost(), ref.surfels()
+    assert np.mean(np.abs(a[:3] - b_[:3])) < 1e-6
+
+
+def test_windowed_bundle_adjustment(mods, small_scene):
+    """active_keyframe_window != all keyframes: fixed activation + all surfels active (direct_ba_alternating.cc:354-372,444-446)."""
+    S, DirectBA, O, R = mods
+    sc = small_scene
+    ba, ref = DirectBA.from_scene(sc), R.RefDirectBA(sc)
+    ro = ba.BundleAdjustment(None, False, False, False, True, True, 2, 2, active_keyframe_window_start=1, active_keyframe_window_end=3)
+    rr = ref.bundle_adjust(True, True, 2, 2, window_start=1, window_end=3)
+    assert ro.pose_iterations_total == rr.pose_iterations_total
+    assert ba.GetActiveHost().all() and ref.active().all()
+    for k in range(sc.cfg.num_keyframes):
+        dt, dr = S.pose_error(ba.keyframes()[k].global_T_frame(), ref.pose(k))
+        assert dt < POSE_T and dr < POSE_R
+
+
+def test_edge_cases(mods, tiny_scene):
+    S, DirectBA, O, R = mods
+    # ragged sizes: 1 surfel, tile-size +- 1, exactly one tile
+    for n in (1, 255, 256, 257, 1023, 1025):
+        sc = copy.copy(tiny_scene)
+        sc.num_surfels = n
+        ba, orc = DirectBA.from_scene(sc), O.Oracle(sc)
+        pc, st = ba.AccumulatePoseEstimationCoeffs(0, sc.poses_init[0]), orc.pose_coeffs(0)
+        assert (pc.n_inimg, pc.n_assoc, pc.n_photo) == (st.n_inimg, st.n_assoc, st.n_photo), n
+        if st.n_assoc:
+            assert rel(pc.H[:], st.H[:]) < 2 * REL
+        r = ba.BundleAdjustment(None, False, False, False, True, True, 1, 2)
+        assert r.iterations_done >= 1
+    # empty surfel set: H = 0 -> x = 0 -> converged immediately (direct_ba_alternating.cc:147-150)
+    sc = copy.copy(tiny_scene)
+    sc.num_surfels = 0
+    ba = DirectBA.from_scene(sc)
+    p, it, conv = ba.EstimateFramePose(None, sc.poses_init[0], 0)
+    assert np.allclose(p, sc.poses_init[0]) and it == 1 and conv
+    assert ba.BundleAdjustment(None, False, False, False, True, True, 1, 3).converged
+    # surfels behind the cameras: nothing associates, nothing is activated, geometry is a no-op
+    sc = copy.copy(tiny_scene)
+    sc.surfels = tiny_scene.surfels.copy()
+    sc.surfels[2] = -5.0
+    ba = DirectBA.from_scene(sc)
+    pc = ba.AccumulatePoseEstimationCoeffs(0, sc.poses_init[0])
+    assert pc.n_inimg == 0 and not any(pc.H[:])
+    ba.UpdateSurfelActivation()
+    assert not ba.GetActiveHost().any()
+    before = ba.GetSurfelsHost()
+    ba.OptimizeGeometryIteration()
+    assert np.array_equal(before.view(np.uint32), ba.GetSurfelsHost().view(np.uint32))
+    # unsupported options fail loudly instead of silently doing something else
+    from badslam_b200._lib import BadBAError
+    with pytest.raises(BadBAError):
+        ba.BundleAdjustment(None, False, False, True, True, True, 1, 1)      # do_surfel_updates
+    with pytest.raises(BadBAError):
+        ba.BundleAdjustment(None, False, False, False, True, True, 1, 1, use_pcg=True)
+
+
+def test_host_buffer_entry_points(mods, tiny_scene):
+    """The *_host path (library-owned device memory) gives the same results as caller-owned device buffers."""
+    S, DirectBA, O, R = mods
+    sc = tiny_scene
+    a, b_ = DirectBA.from_scene(sc), DirectBA.from_scene(sc, host_owned=True)
+    ra = a.BundleAdjustment(None, False, False, False, True, True, 2, 2)
+    b_.UpdateKeyframeHost(1, sc.depth[1], sc.normals[1], sc.radius[1], sc.color[1])
+    rb = b_.BundleAdjustment(None, False, False, False, True, True, 2, 2)
+    assert ra.depth_residual_count == rb.depth_residual_count and ra.pose_iterations_total == rb.pose_iterations_total
+    pa, pb = a.GetKeyframeStates()[0], b_.GetKeyframeStates()[0]
+    assert max(max(S.pose_error(pa[k], pb[k])) for k in range(sc.cfg.num_keyframes)) < 2e-6
+    assert np.max(np.abs(a.GetSurfelsHost()[:3] - b_.GetSurfelsHost()[:3])) < 2e-6
+
+
+@pytest.mark.parametrize("name,tag,use_depth,use_desc", [("cfg1", "", True, True), ("tiny", "", True, True),
+                                                          ("tiny", "_depth_only", True, False), ("tiny", "_desc_only", False, True)])
+def test_against_golden_fixtures(mods, name, tag, use_depth, use_desc):
+    S, DirectBA, O, R = mods
+    path = os.path.join(GOLDEN, f"{name}{tag}.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden fixture not generated yet (tools/make_golden.py)")
+    g = np.load(path)
+    sc = S.make_scene(S.config_by_name(name))
+    assert abs(float(np.sum(sc.surfels[:3, :sc.num_surfels].astype(np.float64))) - float(g["surfel_checksum"])) < 1e-6
+    ba = DirectBA.from_scene(sc, use_depth_residuals=use_depth, use_descriptor_residuals=use_desc)
+    for k in range(sc.cfg.num_keyframes):
+        pc = ba.AccumulatePoseEstimationCoeffs(k, sc.poses_init[k])
+        assert rel(pc.H[:], g["pose_H"][k]) < REL and rel(pc.b[:], g["pose_b"][k]) < REL
+        assert (pc.n_assoc if use_depth else 0) + (pc.n_photo if use_desc else 0) == g["pose_count"][k]
+        p, it, conv = ba.EstimateFramePose(None, sc.poses_init[k], k)
+        dt, dr = S.pose_error(p, g["efp_pose"][k])
+        assert dt < POSE_T and dr < POSE_R and it == g["efp_iterations"][k]
+    ba.UpdateSurfelActivation()
+    assert np.array_equal(np.packbits(ba.GetActiveHost()), g["activation_flags"])
+    ba.OptimizeGeometryIteration()
+    rows = ba.GetSurfelsHost()[[0, 1, 2, 3, 6, 7]]
+    assert np.max(np.abs(rows[:3] - g["geometry_rows"][:3])) < 2e-6
+    assert (rows[3].view(np.uint32) != g["geometry_rows"][3].view(np.uint32)).sum() == 0
+
+
+def test_full_size_properties(mods):
+    """cfg2 (20 keyframes x 200k surfels, 640x480): size-independent properties + oracle spot checks."""
+    S, DirectBA, O, R = mods
+    sc = S.make_scene(S.config_by_name("cfg2"))
+    ba, orc = DirectBA.from_scene(sc), O.Oracle(sc)
+    for k in (0, 7, 19):
+        pc, st = ba.AccumulatePoseEstimationCoeffs(k, sc.poses_init[k]), orc.pose_coeffs(k)
+        assert (pc.n_inimg, pc.n_depthok, pc.n_assoc, pc.n_photo) == (st.n_inimg, st.n_depthok, st.n_assoc, st.n_photo)
+        assert rel(pc.H[:], st.H[:]) < REL
+        # idempotence: the accumulators are consumed and re-armed by every call
+        pc2 = ba.AccumulatePoseEstimationCoeffs(k, sc.poses_init[k])
+        assert rel(pc2.H[:], pc.H[:]) < 1e-6 and pc2.n_assoc == pc.n_assoc
+        # H is symmetric positive semi-definite
+        H = np.zeros((6, 6))
+        H[np.triu_indices(6)] = pc.H[:]
+        H = H + H.T - np.diag(H.diagonal())
+        assert np.linalg.eigvalsh(H).min() > -1e-3 * np.abs(H).max()
+    r1 = ba.BundleAdjustment(None, False, False, False, True, True, 1, 1)
+    r5 = ba.BundleAdjustment(None, False, False, False, True, True, 4, 4)
+    assert r5.cost < r1.cost                      # BA lowers the robust cost
+    assert r5.depth_residual_count > 0.3 * 20 * sc.num_surfels
+    poses, act = ba.GetKeyframeStates()
+    assert np.allclose(np.linalg.norm(poses[:, :4], axis=1), 1.0, atol=1e-5)     # unit quaternions
+    errs = [S.pose_error(poses[k], sc.poses_true[k])[0] for k in range(20)]
+    errs0 = [S.pose_error(sc.poses_init[k], sc.poses_true[k])[0] for k in range(20)]
+    assert np.mean(errs) < np.mean(errs0)

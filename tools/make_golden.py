@@ -1,0 +1,61 @@
+"""Generates tests/golden/*.npz from the REFERENCE's own CUDA kernels (oracle/_ref) on the GPU box.
+
+    gpurun -- python tools/make_golden.py        # writes gpurun_out/golden/<scene>.npz
+    cp gpurun_out/golden/*.npz tests/golden/      # commit
+
+The reference holds no golden vectors for this path; these fixtures are outputs of the reference
+implementation itself on the seeded synthetic scenes of badslam_b200/scene.py, so that the CPU-only test suite can
+pin the oracle (and the GPU suite the CUDA path) against the reference without /root/reference being present.
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from badslam_b200.scene import config_by_name, make_scene  # noqa: E402
+from oracle import ref_cuda  # noqa: E402
+
+
+def golden_for(name, use_depth=True, use_desc=True, tag=""):
+    sc = make_scene(config_by_name(name))
+    K = sc.cfg.num_keyframes
+    out = {"scene": name, "use_depth": use_depth, "use_desc": use_desc, "num_surfels": sc.num_surfels,
+           "surfel_checksum": float(np.sum(sc.surfels[:3, :sc.num_surfels].astype(np.float64))),
+           "depth_checksum": int(sc.depth.astype(np.uint64).sum())}
+    ref = ref_cuda.RefDirectBA(sc, use_depth, use_desc)
+    H, b, cnt, cost = [], [], [], []
+    for k in range(K):
+        h_, b_, c_, s_ = ref.pose_coeffs(k, sc.poses_init[k])
+        H.append(h_); b.append(b_); cnt.append(c_); cost.append(s_)
+    out.update(pose_H=np.array(H), pose_b=np.array(b), pose_count=np.array(cnt), pose_cost=np.array(cost))
+    est, its, conv = [], [], []
+    for k in range(K):
+        p, i, c = ref.estimate_frame_pose(k, sc.poses_init[k])
+        est.append(p); its.append(i); conv.append(c)
+    out.update(efp_pose=np.array(est), efp_iterations=np.array(its), efp_converged=np.array(conv))
+    ref.update_activation()
+    out["activation_flags"] = np.packbits(ref.active())
+    ref.optimize_geometry_iteration()
+    out["geometry_rows"] = ref.surfels()[[0, 1, 2, 3, 6, 7]].copy()
+    ref.close()
+    ref = ref_cuda.RefDirectBA(sc, use_depth, use_desc)
+    r = ref.bundle_adjust(True, True, 3, 3, count_residuals=True)
+    out.update(ba_poses=ref.poses(), ba_activation=ref.activation(), ba_count=int(r.n_count), ba_cost=float(r.cost),
+               ba_pose_iterations=int(r.pose_iterations_total), ba_surfels=ref.surfels()[[0, 1, 2, 6, 7]].copy())
+    # run-to-run noise of the reference itself (float atomics): a second identical run
+    ref2 = ref_cuda.RefDirectBA(sc, use_depth, use_desc)
+    ref2.bundle_adjust(True, True, 3, 3, count_residuals=True)
+    out["ba_poses_rerun"] = ref2.poses()
+    ref.close(); ref2.close()
+    os.makedirs("gpurun_out/golden", exist_ok=True)
+    np.savez_compressed(f"gpurun_out/golden/{name}{tag}.npz", **out)
+    print("wrote", name, tag, "counts", out["pose_count"][:4], "ba_count", out["ba_count"])
+
+
+if __name__ == "__main__":
+    golden_for("cfg1")
+    golden_for("tiny")
+    golden_for("tiny", True, False, "_depth_only")
+    golden_for("tiny", False, True, "_desc_only")
