@@ -195,7 +195,7 @@ struct bba_context {
   int ba_iteration_count = 0;
 
   // profiling (bba_set_profiling)
-  bool profiling = false;
+  int profiling = 0;   // 0 off, 1 event timing, 2 event timing + byte-model counters in every iteration
   bba_profile profile;
   cudaEvent_t prof_ev[64];
   unsigned long long* h_totals = nullptr;
@@ -246,6 +246,7 @@ bba::CameraParams MakeCamera(bba_handle h) {
   c.baseline_fx = h->cfg.baseline_fx;
   c.cell = h->cfg.sparse_surfel_cell_size;
   c.cf_w = h->cf_w;
+  c.cell_magic = c.cell > 1 ? static_cast<unsigned int>((0x100000000ull + c.cell - 1) / c.cell) : 0u;
   c.cfactor = h->d_cfactor;
   c.use_depth = h->cfg.use_depth_residuals;
   c.use_desc = h->cfg.use_descriptor_residuals;
@@ -351,7 +352,7 @@ bba_status RunPoseStep(bba_handle h, const std::vector<int>& ids, const std::vec
     acc.work_count = h->d_count + cur;
     if (h->surfels_size > 0) {
       if (h->profiling && it < 32) BBA_CUDA(h, cudaEventRecord(h->prof_ev[2 * it], s));
-      bba::LaunchPoseAccumulate(acc, h->sm_count, s);
+      bba::LaunchPoseAccumulate(acc, h->sm_count, /*with_stats=*/it == 0 || h->profiling >= 2, s);
       if (h->profiling && it < 32) BBA_CUDA(h, cudaEventRecord(h->prof_ev[2 * it + 1], s));
       ++h->launches;
     }
@@ -836,7 +837,7 @@ bba_status bba_accumulate_pose_coeffs(bba_handle h, int id, const float pose[7],
   acc.work_list = h->d_work[0];
   acc.work_count = h->d_count;
   if (h->surfels_size > 0) {
-    bba::LaunchPoseAccumulate(acc, h->sm_count, s);
+    bba::LaunchPoseAccumulate(acc, h->sm_count, /*with_stats=*/true, s);
     ++h->launches;
   }
   BBA_CUDA(h, cudaGetLastError());
@@ -1042,7 +1043,7 @@ uint64_t bba_kernel_launch_count(bba_handle h) { return h ? h->launches : 0; }
 
 bba_status bba_set_profiling(bba_handle h, int enable) {
   if (!h) return BBA_ERR_INVALID_ARGUMENT;
-  h->profiling = enable != 0;
+  h->profiling = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
   return BBA_OK;
 }
 

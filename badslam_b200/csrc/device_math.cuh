@@ -37,6 +37,7 @@ struct CameraParams {
   float cfx, cfy, ccx, ccy;              // colour PixelCornerProjector (PixelCenterProjector shares fx, fy)
   float a, raw_to_float, baseline_fx;
   int cell, cf_w;
+  unsigned int cell_magic;               // ceil(2^32 / cell): n / cell == __umulhi(n, cell_magic) for n, cell < 2^16 (cell > 1)
   const float* __restrict__ cfactor;     // dense [cf_h][cf_w]
   int use_depth, use_desc;
 };
@@ -170,7 +171,10 @@ __device__ __forceinline__ int ProjectAssociate(const CameraParams& cam, const f
 
   const uint16_t measured = LoadPixelU16(depth, depth_pitch, r->px, r->py);
   if (measured & kInvalidDepthBit) return 1;
-  const float cf = __ldg(cam.cfactor + (r->py / cam.cell) * cam.cf_w + (r->px / cam.cell));
+  // sparse cell of the pixel: exact integer division by multiplication with a precomputed reciprocal
+  const unsigned int cell_x = (cam.cell == 1) ? static_cast<unsigned int>(r->px) : __umulhi(static_cast<unsigned int>(r->px), cam.cell_magic);
+  const unsigned int cell_y = (cam.cell == 1) ? static_cast<unsigned int>(r->py) : __umulhi(static_cast<unsigned int>(r->py), cam.cell_magic);
+  const float cf = __ldg(cam.cfactor + cell_y * cam.cf_w + cell_x);
   r->d = RawToCalibratedDepth(cam.a, cf, cam.raw_to_float, measured);
   r->ln = Rotate(T, n);
   r->nx = cam.fx_inv * r->px + cam.cx_inv;
@@ -178,8 +182,9 @@ __device__ __forceinline__ int ProjectAssociate(const CameraParams& cam, const f
   const float stddev =
       (kDepthUncertaintyFactor * fabsf(r->ln.x * r->nx + r->ln.y * r->ny + r->ln.z) * (r->d * r->d)) / cam.baseline_fx;
   if (fabsf(r->lp.z - r->d) > kDepthTukey * stddev) return 1;
-  const float dist = sqrtf(Dot(r->lp, r->lp));
-  if ((1.0f / dist) * Dot(r->lp, r->ln) > 0) return 1;
+  // The reference tests (1 / |lp|) * dot(lp, ln) > 0 (surfel_projection_nvcc_only.cuh:104-108); for the finite,
+  // positive |lp| of a point in front of the camera that is the sign of the dot product alone.
+  if (Dot(r->lp, r->ln) > 0) return 1;
   r->kf_normal = LoadPixelU16(normals, normals_pitch, r->px, r->py);
   if (Dot(r->ln, U16ToImageSpaceNormal(r->kf_normal)) < kCosNormalCompat) return 2;
   return 3;
@@ -222,11 +227,12 @@ __device__ __forceinline__ void TangentProjections(const CameraParams& cam, cons
 // tex2Dgather centred on the 2x2 footprint returns exactly the same four (clamped) texels:
 // .w = (ix, iy) top-left, .z = (ix+1, iy) top-right, .x = (ix, iy+1) bottom-left, .y = (ix+1, iy+1) bottom-right.
 __device__ __forceinline__ void SamplePoint(cudaTextureObject_t tex, float x, float y, float* intensity, float* dx, float* dy) {
-  const int ix = static_cast<int>(fmaxf(0.f, x - 0.5f));
-  const int iy = static_cast<int>(fmaxf(0.f, y - 0.5f));
-  const float tx = fmaxf(0.f, fminf(1.f, x - 0.5f - ix));
-  const float ty = fmaxf(0.f, fminf(1.f, y - 0.5f - iy));
-  const float4 g = tex2Dgather<float4>(tex, ix + 1.0f, iy + 1.0f, 0);
+  // ix = int(max(0, x - 0.5)), tx = clamp(x - 0.5 - ix, 0, 1) of the reference, without leaving the float domain:
+  // xm >= 0, fx = floor(xm) = float(ix), tx = xm - fx in [0, 1) (and 0 where the reference's clamp bites, x < 0.5).
+  const float xm = fmaxf(0.f, x - 0.5f), ym = fmaxf(0.f, y - 0.5f);
+  const float fx = floorf(xm), fy = floorf(ym);
+  const float tx = xm - fx, ty = ym - fy;
+  const float4 g = tex2Dgather<float4>(tex, fx + 1.0f, fy + 1.0f, 0);
   *intensity = tex2D<float>(tex, x, y);
   *dx = (g.y - g.x) * ty + (g.z - g.w) * (1 - ty);
   *dy = (g.y - g.z) * tx + (g.x - g.w) * (1 - tx);

@@ -126,14 +126,15 @@ constexpr int kPoseThreads = 256;
 constexpr int kPoseWarps = kPoseThreads / 32;
 constexpr int kPoseStagedRows = 7;   // x y z normal radius^2 d1 d2
 constexpr int kPoseGroup = 8;        // keyframes per work item
-constexpr int kPoseChunk = 128;      // surfels per stolen sub-item
 
 // Work decomposition.  A work ITEM is (group of <= 8 keyframes from the work list) x (tile of TILE surfels); items are
 // handed out through a global counter in GROUP-MAJOR order, so at any moment all resident CTAs read the images of the
 // same 8-16 keyframes (~12-24 MB: stays in the 126 MB L2) while surfel tiles stream through shared memory via TMA.
-// Inside an item the 8 warps steal SUB-ITEMS (keyframe, 128-surfel chunk) from a shared-memory counter, which evens out
-// the very different cost of culled vs. associated chunks.
-template <int TILE>
+// Inside an item the 8 warps steal SUB-ITEMS (keyframe, 256- or 128-surfel chunk) from a shared-memory counter, which
+// evens out the very different cost of culled vs. associated chunks.
+// STATS: also produce the residual costs and the stage counters of the byte model (the reference computes its
+// residual count / cost only in debug mode, kernel_opt_pose.cu:312-320,373-381).
+template <int TILE, bool STATS>
 __global__ void __launch_bounds__(kPoseThreads, 2) PoseAccumulateKernel(const __grid_constant__ PoseAccumulateArgs args) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stage_base = reinterpret_cast<float*>(smem_raw);   // [2][7][TILE]
@@ -149,7 +150,10 @@ __global__ void __launch_bounds__(kPoseThreads, 2) PoseAccumulateKernel(const __
   const uint32_t n_tiles = (args.n + TILE - 1) / TILE;
   const uint32_t n_groups = (n_work + kPoseGroup - 1) / kPoseGroup;
   const uint32_t n_items = n_groups * n_tiles;
-  constexpr int kChunksPerTile = TILE / kPoseChunk;
+  // 256-surfel chunks (one warp-level reduction per 8 steps); 128 when there are few keyframes so that all warps get work
+  const int chunk_shift = (n_work >= 4) ? 8 : 7;
+  const uint32_t chunk_len = 1u << chunk_shift;
+  const int chunks_per_tile = TILE >> chunk_shift;
 
   const CameraParams& cam = args.cam;
   constexpr int kRowIds[kPoseStagedRows] = {kRowX, kRowY, kRowZ, kRowNormal, kRowRadiusSq, kRowD1, kRowD2};
@@ -202,17 +206,17 @@ __global__ void __launch_bounds__(kPoseThreads, 2) PoseAccumulateKernel(const __
     const uint32_t base = tile * TILE;
     const uint32_t cnt = min(static_cast<uint32_t>(TILE), args.n - base);
     const int kfs_in_group = min(kPoseGroup, n_work - static_cast<int>(group) * kPoseGroup);
-    const int n_sub = kfs_in_group * kChunksPerTile;
+    const int n_sub = kfs_in_group * chunks_per_tile;
 
     for (;;) {
       int sub = 0;
       if (lane == 0) sub = atomicAdd(&s_sub[s], 1);
       sub = __shfl_sync(0xffffffffu, sub, 0);
       if (sub >= n_sub) break;
-      const int kf_local = sub / kChunksPerTile;
-      const uint32_t j0 = static_cast<uint32_t>(sub - kf_local * kChunksPerTile) * kPoseChunk;
+      const int kf_local = sub / chunks_per_tile;
+      const uint32_t j0 = static_cast<uint32_t>(sub - kf_local * chunks_per_tile) << chunk_shift;
       if (j0 >= cnt) continue;
-      const uint32_t j1 = min(cnt, j0 + kPoseChunk);
+      const uint32_t j1 = min(cnt, j0 + chunk_len);
       const int kf = __ldg(args.work_list + group * kPoseGroup + kf_local);
       KfRegs K;
       LoadKf(args.kfs, kf, &K);
@@ -237,8 +241,10 @@ __global__ void __launch_bounds__(kPoseThreads, 2) PoseAccumulateKernel(const __
             st = ProjectAssociate(cam, K.T, K.depth, K.depth_pitch, K.normals, K.normals_pitch, gp, nrm, &r);
           }
         }
-        n_inimg += __popc(__ballot_sync(0xffffffffu, st >= 1));
-        n_depthok += __popc(__ballot_sync(0xffffffffu, st >= 2));
+        if (STATS) {
+          n_inimg += __popc(__ballot_sync(0xffffffffu, st >= 1));
+          n_depthok += __popc(__ballot_sync(0xffffffffu, st >= 2));
+        }
         const unsigned assoc_mask = __ballot_sync(0xffffffffu, st == 3);
         if (assoc_mask == 0) continue;
         touched |= assoc_mask;
@@ -257,7 +263,7 @@ __global__ void __launch_bounds__(kPoseThreads, 2) PoseAccumulateKernel(const __
             J[4] = inv_stddev * (r.ln.x * up.z - r.ln.z * up.x);
             J[5] = inv_stddev * (-r.ln.x * up.y + r.ln.y * up.x);
             AccumulateHb(acc, J, raw, DepthWeight(raw));
-            acc[29] += DepthCost(raw);
+            if (STATS) acc[29] += DepthCost(raw);
           }
           if (cam.use_desc) {
             float ccx, ccy;
@@ -271,8 +277,10 @@ __global__ void __launch_bounds__(kPoseThreads, 2) PoseAccumulateKernel(const __
               AccumulateHb(acc, J, e.r1, DescWeight(e.r1));
               DescPoseJacobian(cam, r.lp, e.gx2, e.gy2, J);
               AccumulateHb(acc, J, e.r2, DescWeight(e.r2));
-              acc[30] += DescCost(e.r1);
-              acc[31] += DescCost(e.r2);
+              if (STATS) {
+                acc[30] += DescCost(e.r1);
+                acc[31] += DescCost(e.r2);
+              }
             }
           }
         }
@@ -282,7 +290,7 @@ __global__ void __launch_bounds__(kPoseThreads, 2) PoseAccumulateKernel(const __
         const float total = WarpTransposeReduce(acc, lane);
         atomicAdd(args.acc + static_cast<size_t>(kf) * kPoseAccSize + lane, static_cast<double>(total));
       }
-      if (lane == 0 && n_inimg) {
+      if (STATS && lane == 0 && n_inimg) {
         atomicAdd(args.stage_counts + 2 * kf, static_cast<unsigned long long>(n_inimg));
         if (n_depthok) atomicAdd(args.stage_counts + 2 * kf + 1, static_cast<unsigned long long>(n_depthok));
       }
@@ -292,25 +300,31 @@ __global__ void __launch_bounds__(kPoseThreads, 2) PoseAccumulateKernel(const __
   }
 }
 
-template <int TILE>
+template <int TILE, bool STATS>
 static void LaunchPoseAccumulateT(const PoseAccumulateArgs& args, int sm_count, cudaStream_t stream) {
   const size_t smem = static_cast<size_t>(2) * kPoseStagedRows * TILE * sizeof(float);
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(PoseAccumulateKernel<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaFuncSetAttribute(PoseAccumulateKernel<TILE, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     configured = true;
   }
-  PoseAccumulateKernel<TILE><<<2 * sm_count, kPoseThreads, smem, stream>>>(args);   // persistent: 2 CTAs per SM
+  PoseAccumulateKernel<TILE, STATS><<<2 * sm_count, kPoseThreads, smem, stream>>>(args);   // persistent: 2 CTAs per SM
 }
 
-void LaunchPoseAccumulate(const PoseAccumulateArgs& args, int sm_count, cudaStream_t stream) {
-  if (args.n == 0) return;
+template <bool STATS>
+static void LaunchPoseAccumulateS(const PoseAccumulateArgs& args, int sm_count, cudaStream_t stream) {
   // Tile size: as large as possible (one TMA transaction + one CTA barrier per item), but small enough that a
   // keyframe group still yields several items per resident CTA.
   const uint64_t slots = static_cast<uint64_t>(2 * sm_count) * 4;
-  if (args.n >= slots * 1024) LaunchPoseAccumulateT<1024>(args, sm_count, stream);
-  else if (args.n >= slots * 512) LaunchPoseAccumulateT<512>(args, sm_count, stream);
-  else LaunchPoseAccumulateT<256>(args, sm_count, stream);
+  if (args.n >= slots * 1024) LaunchPoseAccumulateT<1024, STATS>(args, sm_count, stream);
+  else if (args.n >= slots * 512) LaunchPoseAccumulateT<512, STATS>(args, sm_count, stream);
+  else LaunchPoseAccumulateT<256, STATS>(args, sm_count, stream);
+}
+
+void LaunchPoseAccumulate(const PoseAccumulateArgs& args, int sm_count, bool with_stats, cudaStream_t stream) {
+  if (args.n == 0) return;
+  if (with_stats) LaunchPoseAccumulateS<true>(args, sm_count, stream);
+  else LaunchPoseAccumulateS<false>(args, sm_count, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -29,7 +29,8 @@ struct PoseAccumulateArgs {
 
 // Persistent, TMA-staged pose residual/Jacobian/Hessian kernel (AccumulatePoseEstimationCoeffsCUDAKernel,
 // kernel_opt_pose.cu:251-383, for a whole list of keyframes in one launch).
-void LaunchPoseAccumulate(const PoseAccumulateArgs& args, int sm_count, cudaStream_t stream);
+// with_stats: also accumulate residual costs + the stage counters (iteration 0 of a pose step, profiling, debug API).
+void LaunchPoseAccumulate(const PoseAccumulateArgs& args, int sm_count, bool with_stats, cudaStream_t stream);
 
 struct PoseSolveArgs {
   KfDevice* kfs;

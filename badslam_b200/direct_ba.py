@@ -371,8 +371,9 @@ class DirectBA:
     def kernel_launch_count(self) -> int:
         return int(self._lib.bba_kernel_launch_count(self._h))
 
-    def SetProfiling(self, enable: bool):
-        self._check(self._lib.bba_set_profiling(self._h, int(enable)))
+    def SetProfiling(self, level: int):
+        """0 off, 1 per-launch event timing, 2 timing + byte-model counters in every Gauss-Newton iteration."""
+        self._check(self._lib.bba_set_profiling(self._h, int(level)))
 
     def GetProfile(self, reset: bool = False) -> dict:
         p = _lib.Profile()

@@ -201,7 +201,8 @@ typedef struct {
   double   activation_normals_ms;
   double   position_descriptor_ms;
 } bba_profile;
-bba_status bba_set_profiling(bba_handle h, int enable);
+/* level 0 = off, 1 = per-launch cudaEvent timing, 2 = timing + byte-model counters (n_inimg, n_depthok) in every iteration */
+bba_status bba_set_profiling(bba_handle h, int level);
 bba_status bba_get_profile(bba_handle h, bba_profile* out, int reset);
 
 #ifdef __cplusplus

@@ -63,8 +63,22 @@ int main() {
                          "integer numerator * (1/(65536*255)) float",
                          "coords to fixed point first: rint(x*256), integer",
                          "integer [trunc weights]",
-                         "lerp form, rounded weights"};
-  const int NC = 8;
+                         "lerp form, rounded weights",
+                         "unorm16 one-shot round, /65535.f",
+                         "unorm16 two-stage x then y (round each), /65535.f",
+                         "unorm16 two-stage y then x (round each), /65535.f",
+                         "unorm16 one-shot trunc, /65535.f",
+                         "unorm16 one-shot round, *(1/65535.f)",
+                         "unorm16 two-stage x then y, *(1/65535.f)",
+                         "8-bit product weights, sum rounded once",
+                         "8-bit product weights, w11 = 256 - rest",
+                         "8-bit product weights, per-texel rounding",
+                         "8-bit product weights, sum truncated",
+                         "hierarchical: rows then columns",
+                         "hierarchical: columns then rows",
+                         "hierarchical: from w11",
+                         "8-bit product weights, ties to even"};
+  const int NC = 22;
   long mism[NC] = {0};
   double maxd[NC] = {0};
   for (int k = 0; k < N; ++k) {
@@ -97,6 +111,45 @@ int main() {
     {
       float top = t00 + ar * (t10 - t00), bot = t01 + ar * (t11 - t01);
       c[7] = top + br * (bot - top);
+    }
+    {
+      long T00 = T(i, j) * 257, T10 = T(i + 1, j) * 257, T01 = T(i, j + 1) * 257, T11 = T(i + 1, j + 1) * 257;
+      long a8 = ai, b8 = bi;
+      long sum = (256 - a8) * (256 - b8) * T00 + a8 * (256 - b8) * T10 + (256 - a8) * b8 * T01 + a8 * b8 * T11;
+      long one = (sum + 32768) >> 16;
+      c[8] = (float)one / 65535.f;
+      long top = ((256 - a8) * T00 + a8 * T10 + 128) >> 8, bot = ((256 - a8) * T01 + a8 * T11 + 128) >> 8;
+      long two = ((256 - b8) * top + b8 * bot + 128) >> 8;
+      c[9] = (float)two / 65535.f;
+      long lef = ((256 - b8) * T00 + b8 * T01 + 128) >> 8, rig = ((256 - b8) * T10 + b8 * T11 + 128) >> 8;
+      long two2 = ((256 - a8) * lef + a8 * rig + 128) >> 8;
+      c[10] = (float)two2 / 65535.f;
+      c[11] = (float)(sum >> 16) / 65535.f;
+      c[12] = (float)one * (1.0f / 65535.f);
+      c[13] = (float)two * (1.0f / 65535.f);
+      // per-texel weights = 8-bit rounded products of the 1.8 fixed-point fractions (tex_probe3: exact for one texel)
+      long w00 = ((256 - a8) * (256 - b8) + 128) >> 8, w10 = (a8 * (256 - b8) + 128) >> 8;
+      long w01 = ((256 - a8) * b8 + 128) >> 8, w11 = (a8 * b8 + 128) >> 8;
+      c[14] = (float)((w00 * T00 + w10 * T10 + w01 * T01 + w11 * T11 + 128) >> 8) / 65535.f;
+      long w11b = 256 - w00 - w10 - w01;
+      c[15] = (float)((w00 * T00 + w10 * T10 + w01 * T01 + w11b * T11 + 128) >> 8) / 65535.f;
+      c[16] = (float)(((w00 * T00 + 128) >> 8) + ((w10 * T10 + 128) >> 8) + ((w01 * T01 + 128) >> 8) + ((w11 * T11 + 128) >> 8)) / 65535.f;
+      c[17] = (float)((w00 * T00 + w10 * T10 + w01 * T01 + w11 * T11) >> 8) / 65535.f;
+      {  // hierarchical splits that keep the weight sum at exactly 256
+        long r0 = 256 - b8, r1 = b8;   // row weights, split between columns
+        long h00 = (r0 * (256 - a8) + 128) >> 8, h10 = r0 - h00, h01 = (r1 * (256 - a8) + 128) >> 8, h11 = r1 - h01;
+        c[18] = (float)((h00 * T00 + h10 * T10 + h01 * T01 + h11 * T11 + 128) >> 8) / 65535.f;
+        long c0 = 256 - a8, c1 = a8;   // column weights, split between rows
+        long g00 = (c0 * (256 - b8) + 128) >> 8, g01 = c0 - g00, g10 = (c1 * (256 - b8) + 128) >> 8, g11 = c1 - g10;
+        c[19] = (float)((g00 * T00 + g10 * T10 + g01 * T01 + g11 * T11 + 128) >> 8) / 65535.f;
+        // round the "far" weights instead
+        long k11 = (a8 * b8 + 128) >> 8, k10 = c1 - k11, k01 = r1 - k11, k00 = 256 - k11 - k10 - k01;
+        c[20] = (float)((k00 * T00 + k10 * T10 + k01 * T01 + k11 * T11 + 128) >> 8) / 65535.f;
+        // ties to even on each product
+        auto rne = [](long v) { long q = v >> 8, r = v & 255; return (r > 128 || (r == 128 && (q & 1))) ? q + 1 : q; };
+        long e00 = rne((256 - a8) * (256 - b8)), e10 = rne(a8 * (256 - b8)), e01 = rne((256 - a8) * b8), e11 = rne(a8 * b8);
+        c[21] = (float)((e00 * T00 + e10 * T10 + e01 * T01 + e11 * T11 + 128) >> 8) / 65535.f;
+      }
     }
     for (int q = 0; q < NC; ++q) {
       if (c[q] != hw[k]) mism[q]++;
