@@ -172,6 +172,9 @@ struct bba_context {
   int* d_geo_list = nullptr;
   unsigned long long* d_totals = nullptr;   // [8]
   unsigned int* d_queue = nullptr;          // work-item counter of the pose kernel
+  unsigned int* d_geo_queue = nullptr;      // work-item counter of the geometry kernels
+  unsigned int* d_tile_epoch = nullptr;     // per-tile group epochs of the geometry kernels
+  uint32_t tile_epoch_capacity = 0;
   volatile int* h_flag = nullptr;           // mapped pinned: {iterations completed, work items left}
   int* d_flag = nullptr;                    // device alias of h_flag
 
@@ -427,6 +430,13 @@ bba_status BuildGeometryArgs(bba_handle h, bba::GeometryArgs* g, cudaStream_t s)
   g->kfs = h->d_kfs;
   g->kf_list = h->d_geo_list;
   g->kf_count = cnt;
+  g->queue = h->d_geo_queue;
+  if (!h->d_tile_epoch || h->tile_epoch_capacity < (h->surfels_size + 255u) / 256u) {
+    cudaFree(h->d_tile_epoch);
+    h->tile_epoch_capacity = std::max<uint32_t>((h->cfg.max_surfel_count + 255u) / 256u, (h->surfels_size + 255u) / 256u) + 1;
+    BBA_CUDA(h, cudaMalloc(&h->d_tile_epoch, sizeof(unsigned int) * h->tile_epoch_capacity));
+  }
+  g->tile_epoch = h->d_tile_epoch;
   return BBA_OK;
 }
 
@@ -535,6 +545,7 @@ bba_status bba_create(const bba_config* cfg, bba_handle* out) {
   CREATE_TRY(cudaMalloc(&h->d_first_stats, sizeof(double) * 8 * K));
   CREATE_TRY(cudaMemset(h->d_first_stats, 0, sizeof(double) * 8 * K));
   CREATE_TRY(cudaMalloc(&h->d_geo_list, sizeof(int) * K));
+  CREATE_TRY(cudaMalloc(&h->d_geo_queue, sizeof(unsigned int)));
   CREATE_TRY(cudaMalloc(&h->d_queue, sizeof(unsigned int)));
   CREATE_TRY(cudaMemset(h->d_queue, 0, sizeof(unsigned int)));
   CREATE_TRY(cudaMalloc(&h->d_totals, sizeof(unsigned long long) * 8));
@@ -592,6 +603,8 @@ void bba_destroy(bba_handle h) {
   cudaFree(h->d_geo_list);
   cudaFree(h->d_totals);
   cudaFree(h->d_queue);
+  cudaFree(h->d_geo_queue);
+  cudaFree(h->d_tile_epoch);
   if (h->h_flag) cudaFreeHost(const_cast<int*>(h->h_flag));
   cudaFreeHost(h->h_totals);
   for (auto& e : h->prof_ev)
@@ -886,7 +899,7 @@ bba_status bba_update_surfel_activation(bba_handle h, void* stream) {
   if (bba_status st = UploadKeyframes(h, s)) return st;
   bba::GeometryArgs g;
   if (bba_status st = BuildGeometryArgs(h, &g, s)) return st;
-  bba::LaunchActivationAndNormals(g, true, false, s);
+  bba::LaunchActivationAndNormals(g, h->sm_count, true, false, s);
   ++h->launches;
   BBA_CUDA(h, cudaGetLastError());
   return MarkStaging(h, s);
@@ -900,8 +913,8 @@ bba_status bba_optimize_geometry_iteration(bba_handle h, void* stream) {
   if (bba_status st = UploadKeyframes(h, s)) return st;
   bba::GeometryArgs g;
   if (bba_status st = BuildGeometryArgs(h, &g, s)) return st;
-  bba::LaunchActivationAndNormals(g, false, true, s);
-  bba::LaunchPositionAndDescriptor(g, s);
+  bba::LaunchActivationAndNormals(g, h->sm_count, false, true, s);
+  bba::LaunchPositionAndDescriptor(g, h->sm_count, s);
   h->launches += 2;
   BBA_CUDA(h, cudaGetLastError());
   return MarkStaging(h, s);
@@ -950,16 +963,16 @@ bba_status bba_bundle_adjust(bba_handle h, const bba_ba_options* o, bba_ba_resul
     if (!whole_window) BBA_CUDA(h, cudaMemsetAsync(h->active, bba::kSurfelActiveFlag, h->surfels_size, s));
     if (h->surfels_size > 0) {
       if (whole_window) {
-        bba::LaunchActivationAndNormals(g, true, o->optimize_geometry != 0, s);
+        bba::LaunchActivationAndNormals(g, h->sm_count, true, o->optimize_geometry != 0, s);
         ++h->launches;
       } else if (o->optimize_geometry) {
-        bba::LaunchActivationAndNormals(g, false, true, s);
+        bba::LaunchActivationAndNormals(g, h->sm_count, false, true, s);
         ++h->launches;
       }
     }
     BBA_CUDA(h, cudaEventRecord(h->ev[1], s));
     if (o->optimize_geometry && h->surfels_size > 0) {
-      bba::LaunchPositionAndDescriptor(g, s);
+      bba::LaunchPositionAndDescriptor(g, h->sm_count, s);
       ++h->launches;
     }
     BBA_CUDA(h, cudaEventRecord(h->ev[2], s));

@@ -150,15 +150,15 @@ struct Assoc {
   uint16_t kf_normal;
 };
 
-// Projection + association.  Returns the stage reached: 0 culled / outside, 1 in image,
-// 2 passed valid-depth + depth-threshold + facing tests (keyframe normal read), 3 associated.
+// Projection + association, split into three steps so that callers can put ALL gathers of a (surfel, keyframe) pair in
+// flight before the first dependent use (the association tests are cheap; the latency of the depth -> normal -> texture
+// chain is what the reference's early-outs serialise).
 // surfel_projection_nvcc_only.cuh:48-127,332-359 ; util.cuh:83-118 ; cuda_matrix.cuh:115-124 ; cost_function.cuh:81-83
-__device__ __forceinline__ int ProjectAssociate(const CameraParams& cam, const float* __restrict__ T,
-                                                const uint16_t* __restrict__ depth, uint32_t depth_pitch,
-                                                const uint16_t* __restrict__ normals, uint32_t normals_pitch,
-                                                const Vec3& gp, const Vec3& n, Assoc* r) {
+
+// Step A: project into the depth image.  No memory access.  Returns false if behind the camera or outside the image.
+__device__ __forceinline__ bool ProjectIntoImage(const CameraParams& cam, const float* __restrict__ T, const Vec3& gp, Assoc* r) {
   r->lp.z = T[8] * gp.x + T[9] * gp.y + T[10] * gp.z + T[11];
-  if (r->lp.z <= 0.f) return 0;
+  if (r->lp.z <= 0.f) return false;
   r->lp.x = T[0] * gp.x + T[1] * gp.y + T[2] * gp.z + T[3];
   r->lp.y = T[4] * gp.x + T[5] * gp.y + T[6] * gp.z + T[7];
   const float inv_z = 1.0f / r->lp.z;
@@ -167,15 +167,34 @@ __device__ __forceinline__ int ProjectAssociate(const CameraParams& cam, const f
   // float -> int conversion saturates on the device, so the reference's bounds test is safe as is
   r->px = static_cast<int>(r->pxf);
   r->py = static_cast<int>(r->pyf);
-  if (!(r->pxf >= 0.f) || !(r->pyf >= 0.f) || r->px >= cam.w || r->py >= cam.h) return 0;
+  return (r->pxf >= 0.f) && (r->pyf >= 0.f) && r->px < cam.w && r->py < cam.h;
+}
 
-  const uint16_t measured = LoadPixelU16(depth, depth_pitch, r->px, r->py);
-  if (measured & kInvalidDepthBit) return 1;
+// Step B: the three independent gathers of the pixel the surfel projects to.  The keyframe normal is fetched together
+// with the depth (the reference reads it only after the depth and facing tests passed; ~99 % of in-image pairs do).
+struct PixelLoads {
+  uint16_t measured;
+  uint16_t kf_normal;
+  float cf;
+};
+__device__ __forceinline__ PixelLoads LoadPixel(const CameraParams& cam, const uint16_t* __restrict__ depth, uint32_t depth_pitch,
+                                                const uint16_t* __restrict__ normals, uint32_t normals_pitch, const Assoc& r) {
+  PixelLoads l;
+  l.measured = LoadPixelU16(depth, depth_pitch, r.px, r.py);
+  l.kf_normal = LoadPixelU16(normals, normals_pitch, r.px, r.py);
   // sparse cell of the pixel: exact integer division by multiplication with a precomputed reciprocal
-  const unsigned int cell_x = (cam.cell == 1) ? static_cast<unsigned int>(r->px) : __umulhi(static_cast<unsigned int>(r->px), cam.cell_magic);
-  const unsigned int cell_y = (cam.cell == 1) ? static_cast<unsigned int>(r->py) : __umulhi(static_cast<unsigned int>(r->py), cam.cell_magic);
-  const float cf = __ldg(cam.cfactor + cell_y * cam.cf_w + cell_x);
-  r->d = RawToCalibratedDepth(cam.a, cf, cam.raw_to_float, measured);
+  const unsigned int cell_x = (cam.cell == 1) ? static_cast<unsigned int>(r.px) : __umulhi(static_cast<unsigned int>(r.px), cam.cell_magic);
+  const unsigned int cell_y = (cam.cell == 1) ? static_cast<unsigned int>(r.py) : __umulhi(static_cast<unsigned int>(r.py), cam.cell_magic);
+  l.cf = __ldg(cam.cfactor + cell_y * cam.cf_w + cell_x);
+  return l;
+}
+
+// Step C: the association tests.  Returns the stage reached: 1 in image only, 2 passed valid-depth + depth-threshold +
+// facing tests, 3 associated.
+__device__ __forceinline__ int Associate(const CameraParams& cam, const float* __restrict__ T, const Vec3& n, const PixelLoads& l,
+                                         Assoc* r) {
+  if (l.measured & kInvalidDepthBit) return 1;
+  r->d = RawToCalibratedDepth(cam.a, l.cf, cam.raw_to_float, l.measured);
   r->ln = Rotate(T, n);
   r->nx = cam.fx_inv * r->px + cam.cx_inv;
   r->ny = cam.fy_inv * r->py + cam.cy_inv;
@@ -185,9 +204,19 @@ __device__ __forceinline__ int ProjectAssociate(const CameraParams& cam, const f
   // The reference tests (1 / |lp|) * dot(lp, ln) > 0 (surfel_projection_nvcc_only.cuh:104-108); for the finite,
   // positive |lp| of a point in front of the camera that is the sign of the dot product alone.
   if (Dot(r->lp, r->ln) > 0) return 1;
-  r->kf_normal = LoadPixelU16(normals, normals_pitch, r->px, r->py);
-  if (Dot(r->ln, U16ToImageSpaceNormal(r->kf_normal)) < kCosNormalCompat) return 2;
+  r->kf_normal = l.kf_normal;
+  if (Dot(r->ln, U16ToImageSpaceNormal(l.kf_normal)) < kCosNormalCompat) return 2;
   return 3;
+}
+
+// All three steps.  Returns 0 culled / outside, else the stage of Associate().
+__device__ __forceinline__ int ProjectAssociate(const CameraParams& cam, const float* __restrict__ T,
+                                                const uint16_t* __restrict__ depth, uint32_t depth_pitch,
+                                                const uint16_t* __restrict__ normals, uint32_t normals_pitch,
+                                                const Vec3& gp, const Vec3& n, Assoc* r) {
+  if (!ProjectIntoImage(cam, T, gp, r)) return 0;
+  const PixelLoads l = LoadPixel(cam, depth, depth_pitch, normals, normals_pitch, *r);
+  return Associate(cam, T, n, l, r);
 }
 
 // surfel_projection.cuh:196-207

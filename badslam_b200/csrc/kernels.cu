@@ -17,6 +17,8 @@
 
 #include <cuda.h>
 
+#include <algorithm>
+
 namespace bba {
 
 // ------------------------------------------------------------------------------------------------
@@ -232,13 +234,24 @@ __global__ void __launch_bounds__(kPoseThreads, 2) PoseAccumulateKernel(const __
         int st = 0;
         Assoc r;
         Vec3 gp, nrm;
+        DescEval e;
+        bool photo = false;
         if (j < j1) {
           gp = V3(sx[j], sy[j], sz[j]);
-          // cheap frustum part first; unpack the normal only if the surfel is in front of the camera
-          const float z = K.T[8] * gp.x + K.T[9] * gp.y + K.T[10] * gp.z + K.T[11];
-          if (z > 0.f) {
+          if (ProjectIntoImage(cam, K.T, gp, &r)) {
+            // Put every gather of the pair in flight before the first dependent use: the pixel's depth / normal /
+            // cfactor, and -- speculatively, ~99 % of in-image pairs end up associated -- the six texture fetches of
+            // the descriptor residual.  The association tests below then wait for the slowest load once.
+            const PixelLoads l = LoadPixel(cam, K.depth, K.depth_pitch, K.normals, K.normals_pitch, r);
             nrm = UnpackNormal(__float_as_uint(sn[j]));
-            st = ProjectAssociate(cam, K.T, K.depth, K.depth_pitch, K.normals, K.normals_pitch, gp, nrm, &r);
+            if (cam.use_desc) {
+              float ccx, ccy;
+              photo = DepthToColor(cam, r.pxf, r.pyf, &ccx, &ccy);
+              float t1x, t1y, t2x, t2y;
+              TangentProjections(cam, K.T, gp, nrm, sr[j], &t1x, &t1y, &t2x, &t2y);
+              EvalDescriptor(K.tex, ccx, ccy, t1x, t1y, t2x, t2y, sd1[j], sd2[j], &e);
+            }
+            st = Associate(cam, K.T, nrm, l, &r);
           }
         }
         if (STATS) {
@@ -265,22 +278,15 @@ __global__ void __launch_bounds__(kPoseThreads, 2) PoseAccumulateKernel(const __
             AccumulateHb(acc, J, raw, DepthWeight(raw));
             if (STATS) acc[29] += DepthCost(raw);
           }
-          if (cam.use_desc) {
-            float ccx, ccy;
-            if (DepthToColor(cam, r.pxf, r.pyf, &ccx, &ccy)) {
-              acc[28] += 1.f;
-              float t1x, t1y, t2x, t2y;
-              TangentProjections(cam, K.T, gp, nrm, sr[j], &t1x, &t1y, &t2x, &t2y);
-              DescEval e;
-              EvalDescriptor(K.tex, ccx, ccy, t1x, t1y, t2x, t2y, sd1[j], sd2[j], &e);
-              DescPoseJacobian(cam, r.lp, e.gx1, e.gy1, J);
-              AccumulateHb(acc, J, e.r1, DescWeight(e.r1));
-              DescPoseJacobian(cam, r.lp, e.gx2, e.gy2, J);
-              AccumulateHb(acc, J, e.r2, DescWeight(e.r2));
-              if (STATS) {
-                acc[30] += DescCost(e.r1);
-                acc[31] += DescCost(e.r2);
-              }
+          if (cam.use_desc && photo) {
+            acc[28] += 1.f;
+            DescPoseJacobian(cam, r.lp, e.gx1, e.gy1, J);
+            AccumulateHb(acc, J, e.r1, DescWeight(e.r1));
+            DescPoseJacobian(cam, r.lp, e.gx2, e.gy2, J);
+            AccumulateHb(acc, J, e.r2, DescWeight(e.r2));
+            if (STATS) {
+              acc[30] += DescCost(e.r1);
+              acc[31] += DescCost(e.r2);
             }
           }
         }
@@ -328,169 +334,311 @@ void LaunchPoseAccumulate(const PoseAccumulateArgs& args, int sm_count, bool wit
 }
 
 // ------------------------------------------------------------------------------------------------
-// Geometry step, surfel-major.
+// Geometry step.  One thread owns one surfel and keeps its accumulators in registers while it walks over a GROUP of
+// keyframes; work items (keyframe group, 256-surfel tile) are handed out group-major through a global counter so that
+// all resident CTAs gather from the same <= 16 keyframes' images at a time (L2-resident) -- the surfel-major variant
+// that looped over all K keyframes per thread re-read the images from HBM ~40 times (profiles/r1_notes.md).
+// Between groups the partial sums of a surfel are parked in the scratch rows 8..16 of the surfel buffer (the rows the
+// reference uses for exactly this purpose, kernels.cuh:78-86); a per-tile epoch word orders (group g, tile t) after
+// (group g-1, tile t).  With K <= 16 there is a single group and no scratch traffic at all.
 
 constexpr int kGeoThreads = 256;
+constexpr int kGeoGroup = 16;   // keyframes per work item
 
-template <bool DETERMINE, bool NORMALS>
-__global__ void __launch_bounds__(kGeoThreads) ActivationNormalsKernel(const __grid_constant__ GeometryArgs a) {
-  const uint32_t i = a.begin + blockIdx.x * kGeoThreads + threadIdx.x;
-  if (i >= a.end) return;
-  const uint8_t flags = a.active[i];
-  if (!DETERMINE && !(flags & kSurfelActiveFlag)) return;
+__device__ __forceinline__ unsigned int LoadAcquire(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void StoreRelease(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
-  const Vec3 gp = V3(a.surfels[static_cast<size_t>(kRowX) * a.pitch + i], a.surfels[static_cast<size_t>(kRowY) * a.pitch + i],
-                     a.surfels[static_cast<size_t>(kRowZ) * a.pitch + i]);
-  const Vec3 nrm = UnpackNormal(__float_as_uint(a.surfels[static_cast<size_t>(kRowNormal) * a.pitch + i]));
-
-  bool act = !DETERMINE;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  for (int j = 0; j < a.kf_count; ++j) {
-    const int kf = __ldg(a.kf_list + j);
-    KfRegs K;
-    LoadKf(a.kfs, kf, &K);
-    if (!NORMALS && K.activation != 0) continue;   // activation only looks at kActive keyframes
-    Assoc r;
-    const int st = ProjectAssociate(a.cam, K.T, K.depth, K.depth_pitch, K.normals, K.normals_pitch, gp, nrm, &r);
-    if (st == 3) {
-      if (K.activation == 0) act = true;
-      if (NORMALS) {
-        // kernel_opt_geometry.cu:545-553: global_R_frame * local normal, global_R_frame = R(frame_T_global)^T
-        const Vec3 ln = U16ToImageSpaceNormal(r.kf_normal);
-        s0 += K.T[0] * ln.x + K.T[4] * ln.y + K.T[8] * ln.z;
-        s1 += K.T[1] * ln.x + K.T[5] * ln.y + K.T[9] * ln.z;
-        s2 += K.T[2] * ln.x + K.T[6] * ln.y + K.T[10] * ln.z;
-        s3 += 1.f;
-      } else if (act) {
-        break;
-      }
+// Work items are owned by WARPS (no CTA-wide barrier anywhere in these kernels): a warp takes (group, 256-surfel tile),
+// waits until the previous group of that tile has been retired, and walks the tile in 8 sub-steps of 32 surfels.
+__device__ __forceinline__ bool NextGeoItem(const GeometryArgs& a, uint32_t n_tiles, uint32_t n_items, uint32_t* group, uint32_t* tile) {
+  unsigned int item = 0;
+  if ((threadIdx.x & 31) == 0) {
+    item = atomicAdd(a.queue, 1u);
+    if (item < n_items) {
+      const uint32_t g = item / n_tiles, t = item - g * n_tiles;
+      while (LoadAcquire(a.tile_epoch + t) < g) __nanosleep(64);
     }
   }
-  if (DETERMINE) a.active[i] = act ? kSurfelActiveFlag : static_cast<uint8_t>(flags & ~kSurfelActiveFlag);
-  if (NORMALS && act && s3 >= 1.f) {
-    // kernel_opt_geometry.cu:577-597: the mean is packed without re-normalisation
-    const float inv = 1.f / s3;
-    a.surfels[static_cast<size_t>(kRowNormal) * a.pitch + i] = __uint_as_float(PackNormal(V3(inv * s0, inv * s1, inv * s2)));
+  item = __shfl_sync(0xffffffffu, item, 0);
+  if (item >= n_items) return false;
+  *group = item / n_tiles;
+  *tile = item - *group * n_tiles;
+  return true;
+}
+
+__device__ __forceinline__ void RetireGeoItem(const GeometryArgs& a, uint32_t group, uint32_t tile) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    __threadfence();
+    StoreRelease(a.tile_epoch + tile, group + 1);
   }
 }
 
-void LaunchActivationAndNormals(const GeometryArgs& a, bool determine_activation, bool update_normals, cudaStream_t stream) {
-  if (a.end <= a.begin) return;
-  const uint32_t grid = (a.end - a.begin + kGeoThreads - 1) / kGeoThreads;
-  if (determine_activation && update_normals) ActivationNormalsKernel<true, true><<<grid, kGeoThreads, 0, stream>>>(a);
-  else if (determine_activation) ActivationNormalsKernel<true, false><<<grid, kGeoThreads, 0, stream>>>(a);
-  else if (update_normals) ActivationNormalsKernel<false, true><<<grid, kGeoThreads, 0, stream>>>(a);
+template <bool DETERMINE, bool NORMALS>
+__global__ void __launch_bounds__(kGeoThreads) ActivationNormalsKernel(const __grid_constant__ GeometryArgs a) {
+  const uint32_t n_tiles = (a.end - a.begin + kGeoThreads - 1) / kGeoThreads;
+  const uint32_t n_groups = (a.kf_count + kGeoGroup - 1) / kGeoGroup;
+  const uint32_t n_items = n_groups * n_tiles;
+  const size_t P = a.pitch;
+  const int lane = threadIdx.x & 31;
+  uint32_t group, tile;
+  while (NextGeoItem(a, n_tiles, n_items, &group, &tile)) {
+    const bool first = group == 0, last = group + 1 == n_groups;
+    const int j_begin = group * kGeoGroup, j_end = min(a.kf_count, static_cast<int>(group + 1) * kGeoGroup);
+    for (uint32_t sub = 0; sub < kGeoThreads / 32; ++sub) {
+      const uint32_t i = a.begin + tile * kGeoThreads + sub * 32 + lane;
+      if (i >= a.end) continue;
+      const uint8_t flags = a.active[i];
+      if (!DETERMINE && !(flags & kSurfelActiveFlag)) continue;   // normals are updated for active surfels only
+      bool act = !DETERMINE;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      if (!first) {
+        if (NORMALS) {
+          s0 = __ldcg(a.surfels + (kRowAccum0 + 0) * P + i);
+          s1 = __ldcg(a.surfels + (kRowAccum0 + 1) * P + i);
+          s2 = __ldcg(a.surfels + (kRowAccum0 + 2) * P + i);
+          s3 = __ldcg(a.surfels + (kRowAccum0 + 3) * P + i);
+        }
+        if (DETERMINE) act = __ldcg(a.surfels + (kRowAccum0 + 4) * P + i) != 0.f;
+      }
+      if (NORMALS || !act) {   // activation alone stops at the first association with an active keyframe
+        const Vec3 gp = V3(a.surfels[kRowX * P + i], a.surfels[kRowY * P + i], a.surfels[kRowZ * P + i]);
+        const Vec3 nrm = UnpackNormal(__float_as_uint(a.surfels[kRowNormal * P + i]));
+        for (int j = j_begin; j < j_end; ++j) {
+          const int kf = __ldg(a.kf_list + j);
+          KfRegs K;
+          LoadKf(a.kfs, kf, &K);
+          if (!NORMALS && K.activation != 0) continue;   // activation only looks at kActive keyframes
+          Assoc r;
+          const int st = ProjectAssociate(a.cam, K.T, K.depth, K.depth_pitch, K.normals, K.normals_pitch, gp, nrm, &r);
+          if (st == 3) {
+            if (K.activation == 0) act = true;
+            if (NORMALS) {
+              // kernel_opt_geometry.cu:545-553: global_R_frame * local normal, global_R_frame = R(frame_T_global)^T
+              const Vec3 ln = U16ToImageSpaceNormal(r.kf_normal);
+              s0 += K.T[0] * ln.x + K.T[4] * ln.y + K.T[8] * ln.z;
+              s1 += K.T[1] * ln.x + K.T[5] * ln.y + K.T[9] * ln.z;
+              s2 += K.T[2] * ln.x + K.T[6] * ln.y + K.T[10] * ln.z;
+              s3 += 1.f;
+            } else if (act) {
+              break;
+            }
+          }
+        }
+      }
+      if (!last) {
+        if (NORMALS) {
+          __stcg(a.surfels + (kRowAccum0 + 0) * P + i, s0);
+          __stcg(a.surfels + (kRowAccum0 + 1) * P + i, s1);
+          __stcg(a.surfels + (kRowAccum0 + 2) * P + i, s2);
+          __stcg(a.surfels + (kRowAccum0 + 3) * P + i, s3);
+        }
+        if (DETERMINE) __stcg(a.surfels + (kRowAccum0 + 4) * P + i, act ? 1.f : 0.f);
+      } else {
+        // SetSurfelInactive + DetermineActiveSurfels (kernel_surfel_activation.cu:38-79)
+        if (DETERMINE) a.active[i] = act ? kSurfelActiveFlag : static_cast<uint8_t>(flags & ~kSurfelActiveFlag);
+        if (NORMALS && act && s3 >= 1.f) {
+          // kernel_opt_geometry.cu:577-597: the mean is packed without re-normalisation
+          const float inv = 1.f / s3;
+          a.surfels[kRowNormal * P + i] = __uint_as_float(PackNormal(V3(inv * s0, inv * s1, inv * s2)));
+        }
+      }
+    }
+    RetireGeoItem(a, group, tile);
+  }
 }
 
 template <bool USE_DEPTH, bool USE_DESC>
 __global__ void __launch_bounds__(kGeoThreads) PositionDescriptorKernel(const __grid_constant__ GeometryArgs a) {
-  const uint32_t i = a.begin + blockIdx.x * kGeoThreads + threadIdx.x;
-  if (i >= a.end) return;
-  if (!(a.active[i] & kSurfelActiveFlag)) return;
+  const uint32_t n_tiles = (a.end - a.begin + kGeoThreads - 1) / kGeoThreads;
+  const uint32_t n_groups = (a.kf_count + kGeoGroup - 1) / kGeoGroup;
+  const uint32_t n_items = n_groups * n_tiles;
   const size_t P = a.pitch;
-  const Vec3 gp = V3(a.surfels[kRowX * P + i], a.surfels[kRowY * P + i], a.surfels[kRowZ * P + i]);
-  const Vec3 nrm = UnpackNormal(__float_as_uint(a.surfels[kRowNormal * P + i]));
-  float radius_sq = 0.f, d1 = 0.f, d2 = 0.f;
-  if (USE_DESC) {
-    radius_sq = a.surfels[kRowRadiusSq * P + i];
-    d1 = a.surfels[kRowD1 * P + i];
-    d2 = a.surfels[kRowD2 * P + i];
-  }
-  // 3x3 normal equations over (t along normal, d1, d2): H00 H01 H02 H11 H12 H22 | b0 b1 b2
-  float H00 = 0.f, H01 = 0.f, H02 = 0.f, H11 = 0.f, H22 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
-  const float H12 = 0.f;   // never accumulated by the reference either (kernel_opt_geometry.cu:216-227)
-
-  for (int j = 0; j < a.kf_count; ++j) {
-    const int kf = __ldg(a.kf_list + j);
-    KfRegs K;
-    LoadKf(a.kfs, kf, &K);
-    Assoc r;
-    if (ProjectAssociate(a.cam, K.T, K.depth, K.depth_pitch, K.normals, K.normals_pitch, gp, nrm, &r) != 3) continue;
-    if (USE_DEPTH) {
-      float inv_stddev;
-      Vec3 up;
-      const float raw = DepthResidual(a.cam, r, &inv_stddev, &up);
-      const float jac = -inv_stddev;   // kernel_opt_geometry.cu:138
-      const float w = DepthWeight(raw);
+  const int lane = threadIdx.x & 31;
+  uint32_t group, tile;
+  while (NextGeoItem(a, n_tiles, n_items, &group, &tile)) {
+    const bool first = group == 0, last = group + 1 == n_groups;
+    const int j_begin = group * kGeoGroup, j_end = min(a.kf_count, static_cast<int>(group + 1) * kGeoGroup);
+    for (uint32_t sub = 0; sub < kGeoThreads / 32; ++sub) {
+      const uint32_t i = a.begin + tile * kGeoThreads + sub * 32 + lane;
+      if (i >= a.end || !(a.active[i] & kSurfelActiveFlag)) continue;
+      const Vec3 gp = V3(a.surfels[kRowX * P + i], a.surfels[kRowY * P + i], a.surfels[kRowZ * P + i]);
+      const Vec3 nrm = UnpackNormal(__float_as_uint(a.surfels[kRowNormal * P + i]));
+      float radius_sq = 0.f, d1 = 0.f, d2 = 0.f;
       if (USE_DESC) {
-        H00 += w * jac * jac;
-        b0 += w * raw * jac;
-      } else {
-        // kernel_opt_geometry.cu:452-456
-        const float wj = w * jac;
-        H00 += wj * jac;
-        b0 += wj * raw;
+        radius_sq = a.surfels[kRowRadiusSq * P + i];
+        d1 = a.surfels[kRowD1 * P + i];
+        d2 = a.surfels[kRowD2 * P + i];
       }
-    }
-    if (USE_DESC) {
-      float ccx, ccy;
-      if (DepthToColor(a.cam, r.pxf, r.pyf, &ccx, &ccy)) {
-        float t1x, t1y, t2x, t2y;
-        TangentProjections(a.cam, K.T, gp, nrm, radius_sq, &t1x, &t1y, &t2x, &t2y);
+      // 3x3 normal equations over (t along normal, d1, d2): H00 H01 H02 H11 H12 H22 | b0 b1 b2
+      float H00 = 0.f, H01 = 0.f, H02 = 0.f, H11 = 0.f, H22 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+      const float H12 = 0.f;   // never accumulated by the reference either (kernel_opt_geometry.cu:216-227)
+      if (!first) {
+        // same row assignment as the reference's accumulators (kernel_opt_geometry.cu:216-227)
+        H00 = __ldcg(a.surfels + (kRowAccum0 + 0) * P + i);
+        b0 = __ldcg(a.surfels + (kRowAccum0 + 6) * P + i);
+        if (USE_DESC) {
+          H01 = __ldcg(a.surfels + (kRowAccum0 + 1) * P + i);
+          H02 = __ldcg(a.surfels + (kRowAccum0 + 2) * P + i);
+          H11 = __ldcg(a.surfels + (kRowAccum0 + 3) * P + i);
+          H22 = __ldcg(a.surfels + (kRowAccum0 + 5) * P + i);
+          b1 = __ldcg(a.surfels + (kRowAccum0 + 7) * P + i);
+          b2 = __ldcg(a.surfels + (kRowAccum0 + 8) * P + i);
+        }
+      }
+      for (int j = j_begin; j < j_end; ++j) {
+        const int kf = __ldg(a.kf_list + j);
+        KfRegs K;
+        LoadKf(a.kfs, kf, &K);
+        Assoc r;
+        if (!ProjectIntoImage(a.cam, K.T, gp, &r)) continue;
+        // all gathers of the pair in flight before the first dependent use (see PoseAccumulateKernel)
+        const PixelLoads l = LoadPixel(a.cam, K.depth, K.depth_pitch, K.normals, K.normals_pitch, r);
         DescEval e;
-        EvalDescriptor(K.tex, ccx, ccy, t1x, t1y, t2x, t2y, d1, d2, &e);
-        // kernel_opt_geometry.cu:176-181
-        const float term1 = -a.cam.cfx * (r.ln.x * r.lp.z - r.ln.z * r.lp.x);
-        const float term2 = -a.cam.cfy * (r.ln.y * r.lp.z - r.ln.z * r.lp.y);
-        const float term3 = 1.f / (r.lp.z * r.lp.z);
-        const float j1 = -(e.gx1 * term1 + e.gy1 * term2) * term3;
-        const float j2 = -(e.gx2 * term1 + e.gy2 * term2) * term3;
-        constexpr float jd = -1.f;
-        const float w1 = DescWeight(e.r1), wr1 = w1 * e.r1;
-        const float w2 = DescWeight(e.r2), wr2 = w2 * e.r2;
-        H00 += w1 * j1 * j1 + w2 * j2 * j2;
-        H01 += w1 * j1 * jd;
-        H11 += w1 * jd * jd;
-        b0 += wr1 * j1 + wr2 * j2;
-        b1 += wr1 * jd;
-        H02 += w2 * j2 * jd;
-        H22 += w2 * jd * jd;
-        b2 += wr2 * jd;
+        bool photo = false;
+        if (USE_DESC) {
+          float ccx, ccy;
+          photo = DepthToColor(a.cam, r.pxf, r.pyf, &ccx, &ccy);
+          float t1x, t1y, t2x, t2y;
+          TangentProjections(a.cam, K.T, gp, nrm, radius_sq, &t1x, &t1y, &t2x, &t2y);
+          EvalDescriptor(K.tex, ccx, ccy, t1x, t1y, t2x, t2y, d1, d2, &e);
+        }
+        if (Associate(a.cam, K.T, nrm, l, &r) != 3) continue;
+        if (USE_DEPTH) {
+          float inv_stddev;
+          Vec3 up;
+          const float raw = DepthResidual(a.cam, r, &inv_stddev, &up);
+          const float jac = -inv_stddev;   // kernel_opt_geometry.cu:138
+          const float w = DepthWeight(raw);
+          if (USE_DESC) {
+            H00 += w * jac * jac;
+            b0 += w * raw * jac;
+          } else {
+            // kernel_opt_geometry.cu:452-456
+            const float wj = w * jac;
+            H00 += wj * jac;
+            b0 += wj * raw;
+          }
+        }
+        if (USE_DESC && photo) {
+          // kernel_opt_geometry.cu:176-181
+          const float term1 = -a.cam.cfx * (r.ln.x * r.lp.z - r.ln.z * r.lp.x);
+          const float term2 = -a.cam.cfy * (r.ln.y * r.lp.z - r.ln.z * r.lp.y);
+          const float term3 = 1.f / (r.lp.z * r.lp.z);
+          const float j1 = -(e.gx1 * term1 + e.gy1 * term2) * term3;
+          const float j2 = -(e.gx2 * term1 + e.gy2 * term2) * term3;
+          constexpr float jd = -1.f;
+          const float w1 = DescWeight(e.r1), wr1 = w1 * e.r1;
+          const float w2 = DescWeight(e.r2), wr2 = w2 * e.r2;
+          H00 += w1 * j1 * j1 + w2 * j2 * j2;
+          H01 += w1 * j1 * jd;
+          H11 += w1 * jd * jd;
+          b0 += wr1 * j1 + wr2 * j2;
+          b1 += wr1 * jd;
+          H02 += w2 * j2 * jd;
+          H22 += w2 * jd * jd;
+          b2 += wr2 * jd;
+        }
+      }
+
+      if (!last) {
+        __stcg(a.surfels + (kRowAccum0 + 0) * P + i, H00);
+        __stcg(a.surfels + (kRowAccum0 + 6) * P + i, b0);
+        if (USE_DESC) {
+          __stcg(a.surfels + (kRowAccum0 + 1) * P + i, H01);
+          __stcg(a.surfels + (kRowAccum0 + 2) * P + i, H02);
+          __stcg(a.surfels + (kRowAccum0 + 3) * P + i, H11);
+          __stcg(a.surfels + (kRowAccum0 + 5) * P + i, H22);
+          __stcg(a.surfels + (kRowAccum0 + 7) * P + i, b1);
+          __stcg(a.surfels + (kRowAccum0 + 8) * P + i, b2);
+        }
+      } else if (!USE_DESC) {
+        // UpdateSurfelPositionCUDAKernel, kernel_opt_geometry.cu:487-507
+        if (H00 > 1e-6f) {
+          const float t = -1.f * b0 / H00;
+          a.surfels[kRowX * P + i] = gp.x + t * nrm.x;
+          a.surfels[kRowY * P + i] = gp.y + t * nrm.y;
+          a.surfels[kRowZ * P + i] = gp.z + t * nrm.z;
+        }
+      } else {
+        // UpdateSurfelPositionAndDescriptorCUDAKernel, kernel_opt_geometry.cu:273-361 (in-place Cholesky)
+        constexpr float kEpsilon = 1e-6f;
+        const float L00 = sqrtf(H00 + kEpsilon);
+        const float L01 = H01 / L00;
+        const float L11 = sqrtf((H11 + kEpsilon) - L01 * L01);
+        const float L02 = H02 / L00;
+        const float L12 = (H12 - L02 * L01) / L11;
+        const float L22 = sqrtf((H22 + kEpsilon) - L02 * L02 - L12 * L12);
+        const float y0 = b0 / L00;
+        const float y1 = (b1 - L01 * y0) / L11;
+        const float y2 = (b2 - L02 * y0 - L12 * y1) / L22;
+        const float x2 = y2 / L22;
+        const float x1 = (y1 - L12 * x2) / L11;
+        const float x0 = (y0 - L02 * x2 - L01 * x1) / L00;
+        if (x0 != 0) {
+          a.surfels[kRowX * P + i] = gp.x - x0 * nrm.x;
+          a.surfels[kRowY * P + i] = gp.y - x0 * nrm.y;
+          a.surfels[kRowZ * P + i] = gp.z - x0 * nrm.z;
+        }
+        if (x1 != 0) a.surfels[kRowD1 * P + i] = fmaxf(-180.f, fminf(180.f, d1 - x1));
+        if (x2 != 0) a.surfels[kRowD2 * P + i] = fmaxf(-180.f, fminf(180.f, d2 - x2));
       }
     }
+    RetireGeoItem(a, group, tile);
   }
-
-  if (!USE_DESC) {
-    // UpdateSurfelPositionCUDAKernel, kernel_opt_geometry.cu:487-507
-    if (H00 > 1e-6f) {
-      const float t = -1.f * b0 / H00;
-      a.surfels[kRowX * P + i] = gp.x + t * nrm.x;
-      a.surfels[kRowY * P + i] = gp.y + t * nrm.y;
-      a.surfels[kRowZ * P + i] = gp.z + t * nrm.z;
-    }
-    return;
-  }
-  // UpdateSurfelPositionAndDescriptorCUDAKernel, kernel_opt_geometry.cu:273-361 (in-place Cholesky)
-  constexpr float kEpsilon = 1e-6f;
-  float L00 = sqrtf(H00 + kEpsilon);
-  float L01 = H01 / L00;
-  float L11 = sqrtf((H11 + kEpsilon) - L01 * L01);
-  float L02 = H02 / L00;
-  float L12 = (H12 - L02 * L01) / L11;
-  float L22 = sqrtf((H22 + kEpsilon) - L02 * L02 - L12 * L12);
-  const float y0 = b0 / L00;
-  const float y1 = (b1 - L01 * y0) / L11;
-  const float y2 = (b2 - L02 * y0 - L12 * y1) / L22;
-  const float x2 = y2 / L22;
-  const float x1 = (y1 - L12 * x2) / L11;
-  const float x0 = (y0 - L02 * x2 - L01 * x1) / L00;
-  if (x0 != 0) {
-    a.surfels[kRowX * P + i] = gp.x - x0 * nrm.x;
-    a.surfels[kRowY * P + i] = gp.y - x0 * nrm.y;
-    a.surfels[kRowZ * P + i] = gp.z - x0 * nrm.z;
-  }
-  if (x1 != 0) a.surfels[kRowD1 * P + i] = fmaxf(-180.f, fminf(180.f, d1 - x1));
-  if (x2 != 0) a.surfels[kRowD2 * P + i] = fmaxf(-180.f, fminf(180.f, d2 - x2));
 }
 
-void LaunchPositionAndDescriptor(const GeometryArgs& a, cudaStream_t stream) {
-  if (a.end <= a.begin) return;
-  const uint32_t grid = (a.end - a.begin + kGeoThreads - 1) / kGeoThreads;
+// Persistent grid: as many CTAs as can be co-resident (the epoch wait relies on every launched CTA being scheduled).
+template <typename Kernel>
+static uint32_t GeoGrid(Kernel kernel, const GeometryArgs& a, int sm_count) {
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kGeoThreads, 0);
+  if (per_sm < 1) per_sm = 1;
+  const uint32_t n_tiles = (a.end - a.begin + kGeoThreads - 1) / kGeoThreads;
+  const uint32_t n_groups = (a.kf_count + kGeoGroup - 1) / kGeoGroup;
+  const uint64_t n_items = static_cast<uint64_t>(n_tiles) * (n_groups ? n_groups : 1);
+  const uint64_t ctas_needed = (n_items + kGeoThreads / 32 - 1) / (kGeoThreads / 32);   // one item per warp
+  return static_cast<uint32_t>(std::min<uint64_t>(ctas_needed, static_cast<uint64_t>(per_sm) * sm_count));
+}
+
+static void PrepareGeo(const GeometryArgs& a, cudaStream_t stream) {
+  const uint32_t n_tiles = (a.end - a.begin + kGeoThreads - 1) / kGeoThreads;
+  cudaMemsetAsync(a.queue, 0, sizeof(unsigned int), stream);
+  cudaMemsetAsync(a.tile_epoch, 0, sizeof(unsigned int) * n_tiles, stream);
+}
+
+void LaunchActivationAndNormals(const GeometryArgs& a, int sm_count, bool determine_activation, bool update_normals, cudaStream_t stream) {
+  if (a.end <= a.begin || (!determine_activation && !update_normals)) return;
+  if (a.kf_count <= 0) {
+    // no keyframe to look at: activation clears every flag, normals keep their value
+    if (determine_activation) cudaMemsetAsync(a.active + a.begin, 0, a.end - a.begin, stream);
+    return;
+  }
+  PrepareGeo(a, stream);
+  if (determine_activation && update_normals)
+    ActivationNormalsKernel<true, true><<<GeoGrid(ActivationNormalsKernel<true, true>, a, sm_count), kGeoThreads, 0, stream>>>(a);
+  else if (determine_activation)
+    ActivationNormalsKernel<true, false><<<GeoGrid(ActivationNormalsKernel<true, false>, a, sm_count), kGeoThreads, 0, stream>>>(a);
+  else
+    ActivationNormalsKernel<false, true><<<GeoGrid(ActivationNormalsKernel<false, true>, a, sm_count), kGeoThreads, 0, stream>>>(a);
+}
+
+void LaunchPositionAndDescriptor(const GeometryArgs& a, int sm_count, cudaStream_t stream) {
+  if (a.end <= a.begin || a.kf_count <= 0) return;
+  PrepareGeo(a, stream);
   if (a.cam.use_desc) {
-    if (a.cam.use_depth) PositionDescriptorKernel<true, true><<<grid, kGeoThreads, 0, stream>>>(a);
-    else PositionDescriptorKernel<false, true><<<grid, kGeoThreads, 0, stream>>>(a);
+    if (a.cam.use_depth)
+      PositionDescriptorKernel<true, true><<<GeoGrid(PositionDescriptorKernel<true, true>, a, sm_count), kGeoThreads, 0, stream>>>(a);
+    else
+      PositionDescriptorKernel<false, true><<<GeoGrid(PositionDescriptorKernel<false, true>, a, sm_count), kGeoThreads, 0, stream>>>(a);
   } else {
-    PositionDescriptorKernel<true, false><<<grid, kGeoThreads, 0, stream>>>(a);
+    PositionDescriptorKernel<true, false><<<GeoGrid(PositionDescriptorKernel<true, false>, a, sm_count), kGeoThreads, 0, stream>>>(a);
   }
 }
 

@@ -63,12 +63,14 @@ struct GeometryArgs {
   const KfDevice* kfs;
   const int* kf_list;          // non-inactive keyframes (ascending ids)
   int kf_count;
+  unsigned int* queue;         // work-item counter (reset by the launcher)
+  unsigned int* tile_epoch;    // [ceil(n / 256)] keyframe groups retired per tile (reset by the launcher)
 };
 // SetSurfelInactive + DetermineActiveSurfels (kernel_surfel_activation.cu:38-79) fused with the normal
 // accumulation + update (kernel_opt_geometry.cu:527-597).
-void LaunchActivationAndNormals(const GeometryArgs& args, bool determine_activation, bool update_normals, cudaStream_t stream);
+void LaunchActivationAndNormals(const GeometryArgs& args, int sm_count, bool determine_activation, bool update_normals, cudaStream_t stream);
 // Position (+ descriptor) accumulation and per-surfel solve (kernel_opt_geometry.cu:118-231,273-361 or :417-507).
-void LaunchPositionAndDescriptor(const GeometryArgs& args, cudaStream_t stream);
+void LaunchPositionAndDescriptor(const GeometryArgs& args, int sm_count, cudaStream_t stream);
 
 // uchar4 (.w = luma) -> u8 plane.
 void LaunchExtractLuma(const uint8_t* rgba, size_t rgba_pitch, uint8_t* luma, size_t luma_pitch, int w, int h, cudaStream_t stream);

@@ -222,14 +222,31 @@ def raw_to_calibrated_depth(a, cfactor, raw_to_float, raw):
     return np.float32(1.0) / (inv + np.float32(cfactor) * np.exp(-np.float32(a) * inv, dtype=np.float32))
 
 
-def tex_luma(luma_u8, x, y, weight_mode=1):
-    """tex2D(..).w of a clamp / linear-filter / normalized-float u8 texture (keyframe.cc:67-73);
-    weights in 1.8 fixed point (CUDA programming guide, texture fetching)."""
+def tex_luma(luma_u8, x, y, weight_mode=3):
+    """tex2D(..).w of a clamp / linear-filter / normalized-float u8 texture (keyframe.cc:67-73).
+    weight_mode 3 (default) reproduces the B200 texture unit bit-exactly, 1 rounds the two fractions to 1/256 and
+    interpolates in float, 0 uses exact float weights."""
     h, w = luma_u8.shape
     xb = np.asarray(x, dtype=np.float32) - np.float32(0.5)
     yb = np.asarray(y, dtype=np.float32) - np.float32(0.5)
     fi, fj = np.floor(xb), np.floor(yb)
     al, be = xb - fi, yb - fj
+    if weight_mode == 3:
+        # The filter of the B200 texture unit as measured (tools/tex_probe*.cu, bit-exact): 1.8 fixed-point fractions,
+        # w11 = round(a*b/256), w10 = a - w11, w01 = b - w11, w00 = 256 - rest, unorm16 texels, one final rounding.
+        a = np.floor(al * 256 + np.float32(0.5)).astype(np.int64)
+        b = np.floor(be * 256 + np.float32(0.5)).astype(np.int64)
+        i, j = fi.astype(np.int64), fj.astype(np.int64)
+        T16 = luma_u8.astype(np.int64) * 257
+
+        def t16(ii, jj):
+            return T16[np.clip(jj, 0, h - 1), np.clip(ii, 0, w - 1)]
+
+        w11 = (a * b + 128) >> 8
+        w10, w01 = a - w11, b - w11
+        w00 = 256 - w11 - w10 - w01
+        s = w00 * t16(i, j) + w10 * t16(i + 1, j) + w01 * t16(i, j + 1) + w11 * t16(i + 1, j + 1)
+        return (((s + 128) >> 8).astype(np.float32) / np.float32(65535.0)).astype(np.float32)
     if weight_mode == 1:
         al = np.floor(al * 256 + np.float32(0.5)) / np.float32(256)
         be = np.floor(be * 256 + np.float32(0.5)) / np.float32(256)

