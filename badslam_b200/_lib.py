@@ -57,7 +57,8 @@ class Profile(C.Structure):
                 ("position_descriptor_ms", C.c_double)]
 
 
-ALLGATHER_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+COLLECTIVE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p)
+COLLECTIVE_ALLGATHER, COLLECTIVE_ALLREDUCE_SUM = 0, 1
 
 # every symbol include/badba.h declares: (name, restype, argtypes)
 _P = C.c_void_p
@@ -95,7 +96,9 @@ SYMBOLS = {
     "bba_optimize_geometry_iteration": (C.c_int, [_P, _P]),
     "bba_optimize_intrinsics": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "bba_bundle_adjust": (C.c_int, [_P, C.POINTER(BAOptions), C.POINTER(BAResult), _P]),
-    "bba_set_allgather": (C.c_int, [_P, ALLGATHER_FN, _P]),
+    "bba_set_collective": (C.c_int, [_P, COLLECTIVE_FN, _P]),
+    "bba_shard_surfel_range": (None, [C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "bba_shard_keyframe_owner": (C.c_int, [C.c_int, C.c_int]),
     "bba_kernel_launch_count": (C.c_uint64, [_P]),
     "bba_update_keyframe_host": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
     "bba_set_profiling": (C.c_int, [_P, C.c_int]),

@@ -191,8 +191,13 @@ struct bba_context {
   bool staging_pending = false;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
-  bba_allgather_fn allgather = nullptr;
-  void* allgather_user = nullptr;
+  bba_collective_fn collective = nullptr;
+  void* collective_user = nullptr;
+  float* d_exchange = nullptr;        // [world][kShardRows][shard_len] floats
+  size_t exchange_floats = 0;
+  float* d_pose_pack = nullptr;       // [max_kf][kPoseSlot] floats
+  float* h_pose_pack = nullptr;       // pinned copy
+  int* d_local_ids = nullptr;         // [max_kf]
 
   uint64_t launches = 0;
   int ba_iteration_count = 0;
@@ -297,6 +302,8 @@ bba_status CheckSurfels(bba_handle h) {
 
 // Runs the Gauss-Newton loop of EstimateFramePose for the keyframes in `ids`, all at once, starting from
 // `init` poses.  On return (stream synchronised) h_pose_est / h_iterations / h_converged / h_first_stats hold the results.
+bba_status CheckCollective(bba_handle h);
+
 bba_status RunPoseStep(bba_handle h, const std::vector<int>& ids, const std::vector<Pose>& init, int max_iterations, cudaStream_t s) {
   const int K = static_cast<int>(h->keyframes.size());
   const int n = static_cast<int>(ids.size());
@@ -306,16 +313,27 @@ bba_status RunPoseStep(bba_handle h, const std::vector<int>& ids, const std::vec
     FillKfDevice(h->keyframes[k], h->keyframes[k].pose, h->h_kfs + k);
     PoseToArray(h->keyframes[k].pose, h->h_pose_est + 7 * k);
   }
+  // Multi-GPU: the work list is dealt round-robin to the ranks; every rank runs the Gauss-Newton loops of its own
+  // keyframes and the results are published with one sum all-reduce over disjoint slots (below).
+  const int world = h->cfg.world_size, rank = h->cfg.rank;
+  if (bba_status st = CheckCollective(h)) return st;
+  std::vector<int> local;
+  local.reserve(n);
   for (int i = 0; i < n; ++i) {
     FillKfDevice(h->keyframes[ids[i]], init[i], h->h_kfs + ids[i]);
     PoseToArray(init[i], h->h_pose_est + 7 * ids[i]);
-    h->h_work[i] = ids[i];
+    if (world == 1 || i % world == rank) {
+      h->h_work[local.size()] = ids[i];
+      local.push_back(ids[i]);
+    }
   }
-  h->h_work[h->cfg.max_keyframes] = n;
+  const int n_local = static_cast<int>(local.size());
+  h->h_work[h->cfg.max_keyframes] = n_local;
   h->h_work[h->cfg.max_keyframes + 1] = 0;
   BBA_CUDA(h, cudaMemcpyAsync(h->d_kfs, h->h_kfs, sizeof(KfDevice) * K, cudaMemcpyHostToDevice, s));
   BBA_CUDA(h, cudaMemcpyAsync(h->d_pose_est, h->h_pose_est, sizeof(float) * 7 * K, cudaMemcpyHostToDevice, s));
-  BBA_CUDA(h, cudaMemcpyAsync(h->d_work[0], h->h_work, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+  if (n_local) BBA_CUDA(h, cudaMemcpyAsync(h->d_work[0], h->h_work, sizeof(int) * n_local, cudaMemcpyHostToDevice, s));
+  if (world > 1 && n_local) BBA_CUDA(h, cudaMemcpyAsync(h->d_local_ids, h->h_work, sizeof(int) * n_local, cudaMemcpyHostToDevice, s));
   BBA_CUDA(h, cudaMemcpyAsync(h->d_count, h->h_work + h->cfg.max_keyframes, sizeof(int) * 2, cudaMemcpyHostToDevice, s));
   BBA_CUDA(h, cudaMemsetAsync(h->d_acc, 0, sizeof(double) * bba::kPoseAccSize * K, s));
   BBA_CUDA(h, cudaMemsetAsync(h->d_stage_counts, 0, sizeof(unsigned long long) * 2 * K, s));
@@ -346,7 +364,7 @@ bba_status RunPoseStep(bba_handle h, const std::vector<int>& ids, const std::vec
   sol.host_flag = h->d_flag;
   sol.queue = h->d_queue;
   h->h_flag[0] = 0;
-  h->h_flag[1] = n;
+  h->h_flag[1] = n_local;
   if (h->profiling) BBA_CUDA(h, cudaMemsetAsync(h->d_totals, 0, sizeof(unsigned long long) * 8, s));
   int enqueued = 0;
   for (int it = 0; it < max_iterations; ++it) {
@@ -377,16 +395,36 @@ bba_status RunPoseStep(bba_handle h, const std::vector<int>& ids, const std::vec
     }
   }
   BBA_CUDA(h, cudaGetLastError());
-  BBA_CUDA(h, cudaMemcpyAsync(h->h_pose_est, h->d_pose_est, sizeof(float) * 7 * K, cudaMemcpyDeviceToHost, s));
-  BBA_CUDA(h, cudaMemcpyAsync(h->h_iterations, h->d_iterations, sizeof(int) * K, cudaMemcpyDeviceToHost, s));
-  BBA_CUDA(h, cudaMemcpyAsync(h->h_converged, h->d_converged, sizeof(int) * K, cudaMemcpyDeviceToHost, s));
-  BBA_CUDA(h, cudaMemcpyAsync(h->h_first_stats, h->d_first_stats, sizeof(double) * 8 * K, cudaMemcpyDeviceToHost, s));
+  if (world > 1) {
+    // ONE all-reduce per pose step: every rank contributes the slots of its keyframes, all others are zero.
+    BBA_CUDA(h, cudaMemsetAsync(h->d_pose_pack, 0, sizeof(float) * bba::kPoseSlot * K, s));
+    bba::LaunchPackPoseResults(h->d_local_ids, n_local, h->d_pose_est, h->d_iterations, h->d_converged, h->d_first_stats,
+                               h->d_pose_pack, s);
+    ++h->launches;
+    h->collective(h->collective_user, BBA_COLLECTIVE_ALLREDUCE_SUM, h->d_pose_pack, static_cast<size_t>(bba::kPoseSlot) * K, s);
+    BBA_CUDA(h, cudaMemcpyAsync(h->h_pose_pack, h->d_pose_pack, sizeof(float) * bba::kPoseSlot * K, cudaMemcpyDeviceToHost, s));
+  } else {
+    BBA_CUDA(h, cudaMemcpyAsync(h->h_pose_est, h->d_pose_est, sizeof(float) * 7 * K, cudaMemcpyDeviceToHost, s));
+    BBA_CUDA(h, cudaMemcpyAsync(h->h_iterations, h->d_iterations, sizeof(int) * K, cudaMemcpyDeviceToHost, s));
+    BBA_CUDA(h, cudaMemcpyAsync(h->h_converged, h->d_converged, sizeof(int) * K, cudaMemcpyDeviceToHost, s));
+    BBA_CUDA(h, cudaMemcpyAsync(h->h_first_stats, h->d_first_stats, sizeof(double) * 8 * K, cudaMemcpyDeviceToHost, s));
+  }
   if (h->profiling) BBA_CUDA(h, cudaMemcpyAsync(h->h_totals, h->d_totals, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, s));
   BBA_CUDA(h, cudaStreamSynchronize(s));
   h->staging_pending = false;
+  if (world > 1) {
+    for (int i = 0; i < n; ++i) {
+      const int kf = ids[i];
+      const float* slot = h->h_pose_pack + static_cast<size_t>(kf) * bba::kPoseSlot;
+      std::memcpy(h->h_pose_est + 7 * kf, slot, sizeof(float) * 7);
+      h->h_iterations[kf] = static_cast<int>(slot[7] + 0.5f);
+      h->h_converged[kf] = static_cast<int>(slot[8] + 0.5f);
+      for (int j = 0; j < 8; ++j) h->h_first_stats[8 * kf + j] = slot[9 + j];
+    }
+  }
   if (h->profiling && h->surfels_size > 0) {
     int real_iterations = 0;   // iterations that had a non-empty work list
-    for (int i = 0; i < n; ++i) real_iterations = std::max(real_iterations, h->h_iterations[ids[i]]);
+    for (int kf : local) real_iterations = std::max(real_iterations, h->h_iterations[kf]);
     for (int it = 0; it < std::min(real_iterations, std::min(enqueued, 32)); ++it) {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, h->prof_ev[2 * it], h->prof_ev[2 * it + 1]);
@@ -400,6 +438,48 @@ bba_status RunPoseStep(bba_handle h, const std::vector<int>& ids, const std::vec
     h->profile.n_assoc += h->h_totals[3];
     h->profile.n_photo += h->h_totals[4];
   }
+  return BBA_OK;
+}
+
+// ---- multi-GPU sharding (one process per GPU) --------------------------------------------------------------------
+void ShardSurfelRange(uint32_t n, int rank, int world, uint32_t* begin, uint32_t* end, uint32_t* shard_len) {
+  const uint32_t tiles = (n + 255u) / 256u;
+  const uint32_t tiles_per_rank = (tiles + world - 1) / world;
+  const uint32_t len = tiles_per_rank * 256u;
+  const uint64_t b = static_cast<uint64_t>(len) * rank, e = b + len;
+  *begin = static_cast<uint32_t>(std::min<uint64_t>(b, n));
+  *end = static_cast<uint32_t>(std::min<uint64_t>(e, n));
+  if (shard_len) *shard_len = len;
+}
+
+bba_status CheckCollective(bba_handle h) {
+  if (h->cfg.world_size > 1 && !h->collective)
+    return Fail(h, BBA_ERR_STATE, "world_size > 1 but no collective registered (bba_set_collective)");
+  return BBA_OK;
+}
+
+// After the geometry step every rank has updated only its own surfel shard: one all-gather makes the replicas equal.
+bba_status ExchangeGeometry(bba_handle h, cudaStream_t s) {
+  if (h->cfg.world_size <= 1 || h->surfels_size == 0) return BBA_OK;
+  const int world = h->cfg.world_size, rank = h->cfg.rank;
+  uint32_t begin, end, shard_len;
+  ShardSurfelRange(h->surfels_size, rank, world, &begin, &end, &shard_len);
+  const size_t need = static_cast<size_t>(world) * bba::kShardRows * shard_len;
+  if (need > h->exchange_floats) {
+    cudaFree(h->d_exchange);
+    h->d_exchange = nullptr;
+    uint32_t b2, e2, max_len;
+    ShardSurfelRange(std::max(h->cfg.max_surfel_count, h->surfels_size), 0, world, &b2, &e2, &max_len);
+    h->exchange_floats = static_cast<size_t>(world) * bba::kShardRows * max_len;
+    BBA_CUDA(h, cudaMalloc(&h->d_exchange, sizeof(float) * h->exchange_floats));
+  }
+  const uint32_t pitch = static_cast<uint32_t>(h->surfel_pitch_bytes / sizeof(float));
+  const size_t slice_floats = static_cast<size_t>(bba::kShardRows) * shard_len;
+  bba::LaunchPackShard(h->surfels, pitch, h->active, begin, end, shard_len, h->d_exchange + slice_floats * rank, s);
+  h->collective(h->collective_user, BBA_COLLECTIVE_ALLGATHER, h->d_exchange, slice_floats * sizeof(float), s);
+  bba::LaunchUnpackShards(h->surfels, pitch, h->active, h->surfels_size, shard_len, world, rank, h->d_exchange, s);
+  h->launches += 2;
+  BBA_CUDA(h, cudaGetLastError());
   return BBA_OK;
 }
 
@@ -426,6 +506,7 @@ bba_status BuildGeometryArgs(bba_handle h, bba::GeometryArgs* g, cudaStream_t s)
   g->n = h->surfels_size;
   g->begin = 0;
   g->end = h->surfels_size;
+  if (h->cfg.world_size > 1) ShardSurfelRange(h->surfels_size, h->cfg.rank, h->cfg.world_size, &g->begin, &g->end, nullptr);
   g->active = h->active;
   g->kfs = h->d_kfs;
   g->kf_list = h->d_geo_list;
@@ -546,6 +627,9 @@ bba_status bba_create(const bba_config* cfg, bba_handle* out) {
   CREATE_TRY(cudaMemset(h->d_first_stats, 0, sizeof(double) * 8 * K));
   CREATE_TRY(cudaMalloc(&h->d_geo_list, sizeof(int) * K));
   CREATE_TRY(cudaMalloc(&h->d_geo_queue, sizeof(unsigned int)));
+  CREATE_TRY(cudaMalloc(&h->d_pose_pack, sizeof(float) * bba::kPoseSlot * K));
+  CREATE_TRY(cudaMallocHost(&h->h_pose_pack, sizeof(float) * bba::kPoseSlot * K));
+  CREATE_TRY(cudaMalloc(&h->d_local_ids, sizeof(int) * K));
   CREATE_TRY(cudaMalloc(&h->d_queue, sizeof(unsigned int)));
   CREATE_TRY(cudaMemset(h->d_queue, 0, sizeof(unsigned int)));
   CREATE_TRY(cudaMalloc(&h->d_totals, sizeof(unsigned long long) * 8));
@@ -604,6 +688,10 @@ void bba_destroy(bba_handle h) {
   cudaFree(h->d_totals);
   cudaFree(h->d_queue);
   cudaFree(h->d_geo_queue);
+  cudaFree(h->d_exchange);
+  cudaFree(h->d_pose_pack);
+  cudaFreeHost(h->h_pose_pack);
+  cudaFree(h->d_local_ids);
   cudaFree(h->d_tile_epoch);
   if (h->h_flag) cudaFreeHost(const_cast<int*>(h->h_flag));
   cudaFreeHost(h->h_totals);
@@ -899,9 +987,11 @@ bba_status bba_update_surfel_activation(bba_handle h, void* stream) {
   if (bba_status st = UploadKeyframes(h, s)) return st;
   bba::GeometryArgs g;
   if (bba_status st = BuildGeometryArgs(h, &g, s)) return st;
+  if (bba_status st = CheckCollective(h)) return st;
   bba::LaunchActivationAndNormals(g, h->sm_count, true, false, s);
   ++h->launches;
   BBA_CUDA(h, cudaGetLastError());
+  if (bba_status st = ExchangeGeometry(h, s)) return st;
   return MarkStaging(h, s);
 }
 
@@ -913,10 +1003,12 @@ bba_status bba_optimize_geometry_iteration(bba_handle h, void* stream) {
   if (bba_status st = UploadKeyframes(h, s)) return st;
   bba::GeometryArgs g;
   if (bba_status st = BuildGeometryArgs(h, &g, s)) return st;
+  if (bba_status st = CheckCollective(h)) return st;
   bba::LaunchActivationAndNormals(g, h->sm_count, false, true, s);
   bba::LaunchPositionAndDescriptor(g, h->sm_count, s);
   h->launches += 2;
   BBA_CUDA(h, cudaGetLastError());
+  if (bba_status st = ExchangeGeometry(h, s)) return st;
   return MarkStaging(h, s);
 }
 
@@ -935,6 +1027,7 @@ bba_status bba_bundle_adjust(bba_handle h, const bba_ba_options* o, bba_ba_resul
   const bool opt_depth_intr = o->optimize_depth_intrinsics && h->cfg.use_depth_residuals;
   const bool opt_color_intr = o->optimize_color_intrinsics && h->cfg.use_descriptor_residuals;
   if (opt_depth_intr || opt_color_intr) return Fail(h, BBA_ERR_UNSUPPORTED, "intrinsics optimisation is not implemented yet");
+  if (bba_status st = CheckCollective(h)) return st;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int K = static_cast<int>(h->keyframes.size());
   const uint64_t launches_before = h->launches;
@@ -975,8 +1068,9 @@ bba_status bba_bundle_adjust(bba_handle h, const bba_ba_options* o, bba_ba_resul
       bba::LaunchPositionAndDescriptor(g, h->sm_count, s);
       ++h->launches;
     }
-    BBA_CUDA(h, cudaEventRecord(h->ev[2], s));
     BBA_CUDA(h, cudaGetLastError());
+    if (bba_status st = ExchangeGeometry(h, s)) return st;   // multi-GPU: all-gather of the updated surfel shards
+    BBA_CUDA(h, cudaEventRecord(h->ev[2], s));
     if (bba_status st = MarkStaging(h, s)) return st;
 
     // --- pose optimisation (:543-577): all non-inactive keyframes at once
@@ -1045,12 +1139,21 @@ bba_status bba_bundle_adjust(bba_handle h, const bba_ba_options* o, bba_ba_resul
   return BBA_OK;
 }
 
-bba_status bba_set_allgather(bba_handle h, bba_allgather_fn fn, void* user) {
+bba_status bba_set_collective(bba_handle h, bba_collective_fn fn, void* user) {
   if (!h) return BBA_ERR_INVALID_ARGUMENT;
-  h->allgather = fn;
-  h->allgather_user = user;
+  h->collective = fn;
+  h->collective_user = user;
   return BBA_OK;
 }
+
+void bba_shard_surfel_range(uint32_t surfels_size, int rank, int world_size, uint32_t* begin, uint32_t* end) {
+  uint32_t b = 0, e = surfels_size;
+  if (world_size > 1 && rank >= 0 && rank < world_size) ShardSurfelRange(surfels_size, rank, world_size, &b, &e, nullptr);
+  if (begin) *begin = b;
+  if (end) *end = e;
+}
+
+int bba_shard_keyframe_owner(int list_index, int world_size) { return world_size > 1 ? list_index % world_size : 0; }
 
 uint64_t bba_kernel_launch_count(bba_handle h) { return h ? h->launches : 0; }
 

@@ -643,6 +643,70 @@ void LaunchPositionAndDescriptor(const GeometryArgs& a, int sm_count, cudaStream
 }
 
 // ------------------------------------------------------------------------------------------------
+// Multi-GPU exchange helpers (the collectives themselves run in the host's NCCL communicator).
+
+__constant__ int kShardRowIds[kShardRows - 1] = {kRowX, kRowY, kRowZ, kRowNormal, kRowD1, kRowD2};
+
+__global__ void __launch_bounds__(256) PackShardKernel(const float* __restrict__ surfels, uint32_t pitch,
+                                                       const uint8_t* __restrict__ active, uint32_t begin, uint32_t end,
+                                                       uint32_t shard_len, float* __restrict__ slice) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= shard_len) return;
+  const uint32_t i = begin + c;
+  const bool in = i < end;
+#pragma unroll
+  for (int r = 0; r < kShardRows - 1; ++r)
+    slice[static_cast<size_t>(r) * shard_len + c] = in ? surfels[static_cast<size_t>(kShardRowIds[r]) * pitch + i] : 0.f;
+  slice[static_cast<size_t>(kShardRows - 1) * shard_len + c] = in ? static_cast<float>(active[i]) : 0.f;
+}
+
+__global__ void __launch_bounds__(256) UnpackShardsKernel(float* __restrict__ surfels, uint32_t pitch, uint8_t* __restrict__ active,
+                                                          uint32_t n, uint32_t shard_len, int skip_rank,
+                                                          const float* __restrict__ buffer) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t rank = i / shard_len, c = i - rank * shard_len;
+  if (static_cast<int>(rank) == skip_rank) return;
+  const float* slice = buffer + static_cast<size_t>(rank) * kShardRows * shard_len;
+#pragma unroll
+  for (int r = 0; r < kShardRows - 1; ++r)
+    surfels[static_cast<size_t>(kShardRowIds[r]) * pitch + i] = slice[static_cast<size_t>(r) * shard_len + c];
+  active[i] = static_cast<uint8_t>(slice[static_cast<size_t>(kShardRows - 1) * shard_len + c]);
+}
+
+void LaunchPackShard(const float* surfels, uint32_t pitch, const uint8_t* active, uint32_t begin, uint32_t end, uint32_t shard_len,
+                     float* slice, cudaStream_t stream) {
+  if (shard_len == 0) return;
+  PackShardKernel<<<(shard_len + 255) / 256, 256, 0, stream>>>(surfels, pitch, active, begin, end, shard_len, slice);
+}
+
+void LaunchUnpackShards(float* surfels, uint32_t pitch, uint8_t* active, uint32_t n, uint32_t shard_len, int world, int skip_rank,
+                        const float* buffer, cudaStream_t stream) {
+  (void)world;
+  if (n == 0) return;
+  UnpackShardsKernel<<<(n + 255) / 256, 256, 0, stream>>>(surfels, pitch, active, n, shard_len, skip_rank, buffer);
+}
+
+__global__ void PackPoseResultsKernel(const int* __restrict__ ids, int n, const float* __restrict__ pose_est,
+                                      const int* __restrict__ iterations, const int* __restrict__ converged,
+                                      const double* __restrict__ first_stats, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int kf = ids[i];
+  float* o = out + static_cast<size_t>(kf) * kPoseSlot;
+  for (int j = 0; j < 7; ++j) o[j] = pose_est[kf * 7 + j];
+  o[7] = static_cast<float>(iterations[kf]);
+  o[8] = static_cast<float>(converged[kf]);
+  for (int j = 0; j < 8; ++j) o[9 + j] = static_cast<float>(first_stats[kf * 8 + j]);
+}
+
+void LaunchPackPoseResults(const int* ids, int n, const float* pose_est, const int* iterations, const int* converged,
+                           const double* first_stats, float* out, cudaStream_t stream) {
+  if (n <= 0) return;
+  PackPoseResultsKernel<<<(n + 127) / 128, 128, 0, stream>>>(ids, n, pose_est, iterations, converged, first_stats, out);
+}
+
+// ------------------------------------------------------------------------------------------------
 // uchar4 (.w = luma, cuda_image_processing.cu:165-176) -> dense u8 luma plane.  128-bit loads: 4 pixels per thread.
 
 __global__ void __launch_bounds__(256) ExtractLumaKernel(const uint8_t* __restrict__ rgba, size_t rgba_pitch,

@@ -72,6 +72,17 @@ void LaunchActivationAndNormals(const GeometryArgs& args, int sm_count, bool det
 // Position (+ descriptor) accumulation and per-surfel solve (kernel_opt_geometry.cu:118-231,273-361 or :417-507).
 void LaunchPositionAndDescriptor(const GeometryArgs& args, int sm_count, cudaStream_t stream);
 
+// Multi-GPU exchange of a surfel shard: 7 rows (x y z normal d1 d2 active-as-float) x shard_len floats per rank.
+constexpr int kShardRows = 7;
+void LaunchPackShard(const float* surfels, uint32_t pitch, const uint8_t* active, uint32_t begin, uint32_t end, uint32_t shard_len,
+                     float* slice, cudaStream_t stream);
+void LaunchUnpackShards(float* surfels, uint32_t pitch, uint8_t* active, uint32_t n, uint32_t shard_len, int world, int skip_rank,
+                        const float* buffer, cudaStream_t stream);
+// Pose results of the locally owned keyframes -> [K][17] floats (zeros elsewhere) for the sum all-reduce.
+constexpr int kPoseSlot = 17;   // 7 pose, iterations, converged, 8 first-iteration statistics
+void LaunchPackPoseResults(const int* ids, int n, const float* pose_est, const int* iterations, const int* converged,
+                           const double* first_stats, float* out, cudaStream_t stream);
+
 // uchar4 (.w = luma) -> u8 plane.
 void LaunchExtractLuma(const uint8_t* rgba, size_t rgba_pitch, uint8_t* luma, size_t luma_pitch, int w, int h, cudaStream_t stream);
 

@@ -368,6 +368,42 @@ class DirectBA:
                         r.cost, r.pose_iterations_total, r.ms_surfel_activation, r.ms_geometry_optimization,
                         r.ms_pose_optimization, r.ms_intrinsics_optimization, r.kernel_launches)
 
+    # -- multi-GPU (one process per GPU) ---------------------------------------------------------------
+    def SetCollective(self, group=None):
+        """Registers the exchange step (bba_set_collective) on top of torch.distributed (NCCL over NVLink): in-place
+        all-gather of the updated surfel shards, sum all-reduce of the pose slots."""
+        import torch.distributed as dist
+        lib_defs = _lib
+        rank, world = self._cfg.rank, self._cfg.world_size
+        views = {}
+
+        def view(ptr, nbytes, dtype):
+            key = (ptr, nbytes, dtype)
+            t = views.get(key)
+            if t is None:
+                class _Raw:
+                    pass
+                raw = _Raw()
+                n = nbytes // (4 if dtype == torch.float32 else 1)
+                raw.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4" if dtype == torch.float32 else "|u1",
+                                                "data": (ptr, False), "version": 2, "strides": None}
+                t = torch.as_tensor(raw, device=self.device)
+                views[key] = (t, raw)
+                return t
+            return t[0]
+
+        def cb(user, op, ptr, count, stream):
+            st = torch.cuda.ExternalStream(stream or 0, device=self.device) if stream else torch.cuda.default_stream(self.device)
+            with torch.cuda.stream(st):
+                if op == lib_defs.COLLECTIVE_ALLGATHER:
+                    out = view(ptr, count * world, torch.uint8)
+                    dist.all_gather_into_tensor(out, out[rank * count:(rank + 1) * count], group=group)
+                else:
+                    dist.all_reduce(view(ptr, count * 4, torch.float32), group=group)
+
+        self._collective_cb = lib_defs.COLLECTIVE_FN(cb)   # keep alive
+        self._check(self._lib.bba_set_collective(self._h, self._collective_cb, None))
+
     def kernel_launch_count(self) -> int:
         return int(self._lib.bba_kernel_launch_count(self._h))
 

@@ -122,10 +122,19 @@ def run_ours(args, scene, rank, world):
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
     torch.cuda.set_device(dev)
     K = scene.cfg.num_keyframes
+    import torch.distributed as dist
     if world > 1:
-        raise NotImplementedError("multi-GPU bench path is added with the sharded BA (see DESIGN.md)")
+        # one process per GPU (torchrun); keyframe images + surfels replicated, surfel shards / keyframe work list split
+        if not dist.is_initialized():
+            dist.init_process_group(backend="nccl", device_id=dev)
 
-    ba = DirectBA.from_scene(scene, device=dev)
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[dev.index])
+
+    ba = DirectBA.from_scene(scene, device=dev, rank=rank, world_size=world)
+    if world > 1:
+        ba.SetCollective()
     surf = ba.surfels()
     backup = surf[:8].clone()
     poses0 = scene.poses_init.copy()
@@ -149,6 +158,7 @@ def run_ours(args, scene, rank, world):
     sampler = ClockSampler(dev.index or 0)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
     torch.cuda.synchronize()
     ev0.record()
     stage = np.zeros(3)
@@ -157,8 +167,14 @@ def run_ours(args, scene, rank, world):
         stage += [res.ms_surfel_activation, res.ms_geometry_optimization, res.ms_pose_optimization]
     ev1.record()
     torch.cuda.synchronize()
+    barrier()
+    torch.cuda.synchronize()
     clocks = sampler.stop()
     ms_total = ev0.elapsed_time(ev1)
+    if world > 1:   # device time, max over ranks
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
     ms_step = ms_total / args.steps
     launches = ba.kernel_launch_count() - launches0
     prof = ba.GetProfile(reset=True)
@@ -198,7 +214,10 @@ def run_ours(args, scene, rank, world):
 
     # e2e: same step through the public API with HOST buffers: one keyframe's RGB-D images (pinned) + all poses go
     # host->device, poses/statistics come back, every step.
-    e2e = run_e2e(args, scene, dev, residuals)
+    if world == 1:
+        e2e = run_e2e(args, scene, dev, residuals)
+    else:
+        e2e = run_e2e_multi(args, scene, dev, residuals, rank, world)
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -216,6 +235,10 @@ def run_ours(args, scene, rank, world):
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_port_baseline(scene)
+    if world > 1:
+        out["config"]["parallelism"] = (f"gpus={world}: keyframe images + surfels replicated; geometry step sharded by surfel range "
+                                        "(1 all-gather), pose step sharded by keyframe (1 all-reduce); NCCL over NVLink")
+        dist.barrier(device_ids=[dev.index])
     return out
 
 
@@ -257,6 +280,50 @@ def run_e2e(args, scene, dev, residuals):
             "d2h_bytes_per_step": int(d2h),
             "path": "badslam_b200.DirectBA (C ABI *_host entry points): keyframe RGB-D images from pinned host memory + poses H2D, "
                     "BundleAdjustment(1 iteration), poses/activations/statistics D2H"}
+
+
+def run_e2e_multi(args, scene, dev, residuals, rank, world):
+    """e2e at N > 1: every rank drives its replica through the host-buffer entry points; time = max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from badslam_b200.direct_ba import DirectBA
+    K = scene.cfg.num_keyframes
+    ba = DirectBA.from_scene(scene, device=dev, host_owned=True, rank=rank, world_size=world)
+    ba.SetCollective()
+    surf = ba.SurfelsDeviceView()
+    backup = surf[:8].clone()
+    poses0 = scene.poses_init.copy()
+    act0 = np.zeros(K, np.int32)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int16 if a.dtype == np.uint16 else a.dtype)).pin_memory()
+    slots = min(K, 4)
+    pinned = [(pin(scene.depth[k]), pin(scene.normals[k]), pin(scene.radius[k]), pin(scene.color[k])) for k in range(slots)]
+    h2d = sum(t.numel() * t.element_size() for t in pinned[0]) + K * (96 + 28 + 4)
+    d2h = K * 17 * 4
+
+    def step(i):
+        d, n, r, c = pinned[i % slots]
+        ba.UpdateKeyframeHost(i % slots, d, n, r, c)
+        surf[:8].copy_(backup, non_blocking=True)
+        ba.SetKeyframeStates(poses0, act0)
+        ba.BundleAdjustment(None, False, False, False, True, True, 1, 1, increase_ba_iteration_count=False)
+        ba.GetKeyframeStates()
+
+    for i in range(3):
+        step(i)
+    dist.barrier(device_ids=[dev.index])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i)
+    torch.cuda.synchronize()
+    dist.barrier(device_ids=[dev.index])
+    dt = torch.tensor([(time.perf_counter() - t0) / args.steps], device=dev, dtype=torch.float64)
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    dt = float(dt.item())
+    del ba
+    return {"value": residuals / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "h2d_bytes_per_step": int(h2d * world),
+            "d2h_bytes_per_step": int(d2h * world),
+            "path": "badslam_b200.DirectBA per rank (C ABI *_host entry points) + torch.distributed NCCL exchange"}
 
 
 def run_reference(args, scene):

@@ -107,7 +107,13 @@ typedef struct {
   double cost_depth, cost_desc1, cost_desc2;
 } bba_pose_coeffs;
 
-typedef void (*bba_allgather_fn)(void* user, void* device_buffer, size_t bytes_per_rank, void* stream);
+/* Exchange step of a one-process-per-GPU job, implemented by the host (torch.distributed / NCCL in the harness, raw
+ * ncclAllGather / ncclAllReduce in a C++ integration).  Both operate IN PLACE on a library-owned device buffer and are
+ * enqueued on `stream`:
+ *   BBA_COLLECTIVE_ALLGATHER      buffer = world_size slices of `count` BYTES; this rank's slice is slice[rank]
+ *   BBA_COLLECTIVE_ALLREDUCE_SUM  buffer = `count` fp32 values, summed over ranks */
+typedef enum { BBA_COLLECTIVE_ALLGATHER = 0, BBA_COLLECTIVE_ALLREDUCE_SUM = 1 } bba_collective_op;
+typedef void (*bba_collective_fn)(void* user, int op, void* device_buffer, size_t count, void* stream);
 
 /* ---- lifetime ---- */
 int         bba_abi_version(void);
@@ -176,9 +182,17 @@ bba_status bba_optimize_intrinsics(bba_handle h, int optimize_depth_intrinsics, 
 bba_status bba_bundle_adjust(bba_handle h, const bba_ba_options* options, bba_ba_result* result, void* stream);
 
 /* ---- multi-GPU (one process per GPU; not present in the reference) ---- */
-/* Registers the exchange step: an in-place all-gather over equal per-rank slices of a device buffer,
- * enqueued on `stream` (the harness implements it with torch.distributed / NCCL). */
-bba_status bba_set_allgather(bba_handle h, bba_allgather_fn fn, void* user);
+/* Sharding (DESIGN.md "Multi-GPU"): keyframe images and the surfel buffer are replicated on every rank.
+ *  - geometry step: rank r updates the surfels of its contiguous shard; ONE all-gather of the updated rows
+ *    (x, y, z, normal, descriptor 1/2, active flag) per outer iteration makes every replica identical again;
+ *  - pose step: the non-inactive keyframes are dealt round-robin to the ranks, each rank runs the Gauss-Newton
+ *    loops of its keyframes locally, and ONE all-reduce (sum of disjoint slots, K x 17 floats) publishes the poses.
+ * Registers the exchange callback; required before any hot-path call when world_size > 1. */
+bba_status bba_set_collective(bba_handle h, bba_collective_fn fn, void* user);
+/* The partition itself, exposed so that hosts and tests can reason about it: surfel shard [begin, end) of `rank`
+ * (256-aligned), and the owner rank of the i-th entry of a keyframe work list. */
+void bba_shard_surfel_range(uint32_t surfels_size, int rank, int world_size, uint32_t* begin, uint32_t* end);
+int  bba_shard_keyframe_owner(int list_index, int world_size);
 
 /* Re-uploads the images of an existing keyframe from host memory (same sizes as at creation) -- the per-step
  * host->device input path of a live system, where a keyframe's RGB-D data arrives from the sensor thread

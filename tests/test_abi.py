@@ -12,7 +12,7 @@ def declared_symbols():
     src = open(os.path.join(ROOT, "include", "badba.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     names = set(re.findall(r"\b(bba_[a-z_0-9]+)\s*\(", src))
-    names -= {"bba_allgather_fn"}
+    names -= {"bba_collective_fn", "bba_collective_op"}
     return sorted(names)
 
 
