@@ -512,9 +512,10 @@ bba_status BuildGeometryArgs(bba_handle h, bba::GeometryArgs* g, cudaStream_t s)
   g->kf_list = h->d_geo_list;
   g->kf_count = cnt;
   g->queue = h->d_geo_queue;
-  if (!h->d_tile_epoch || h->tile_epoch_capacity < (h->surfels_size + 255u) / 256u) {
+  g->tile_shift = 8;
+  if (!h->d_tile_epoch || h->tile_epoch_capacity < (h->surfels_size + 31u) / 32u) {
     cudaFree(h->d_tile_epoch);
-    h->tile_epoch_capacity = std::max<uint32_t>((h->cfg.max_surfel_count + 255u) / 256u, (h->surfels_size + 255u) / 256u) + 1;
+    h->tile_epoch_capacity = std::max<uint32_t>((h->cfg.max_surfel_count + 31u) / 32u, (h->surfels_size + 31u) / 32u) + 1;
     BBA_CUDA(h, cudaMalloc(&h->d_tile_epoch, sizeof(unsigned int) * h->tile_epoch_capacity));
   }
   g->tile_epoch = h->d_tile_epoch;

@@ -382,7 +382,8 @@ __device__ __forceinline__ void RetireGeoItem(const GeometryArgs& a, uint32_t gr
 
 template <bool DETERMINE, bool NORMALS>
 __global__ void __launch_bounds__(kGeoThreads) ActivationNormalsKernel(const __grid_constant__ GeometryArgs a) {
-  const uint32_t n_tiles = (a.end - a.begin + kGeoThreads - 1) / kGeoThreads;
+  const uint32_t tile_len = 1u << a.tile_shift;
+  const uint32_t n_tiles = (a.end - a.begin + tile_len - 1) >> a.tile_shift;
   const uint32_t n_groups = (a.kf_count + kGeoGroup - 1) / kGeoGroup;
   const uint32_t n_items = n_groups * n_tiles;
   const size_t P = a.pitch;
@@ -391,8 +392,8 @@ __global__ void __launch_bounds__(kGeoThreads) ActivationNormalsKernel(const __g
   while (NextGeoItem(a, n_tiles, n_items, &group, &tile)) {
     const bool first = group == 0, last = group + 1 == n_groups;
     const int j_begin = group * kGeoGroup, j_end = min(a.kf_count, static_cast<int>(group + 1) * kGeoGroup);
-    for (uint32_t sub = 0; sub < kGeoThreads / 32; ++sub) {
-      const uint32_t i = a.begin + tile * kGeoThreads + sub * 32 + lane;
+    for (uint32_t sub = 0; sub < tile_len / 32; ++sub) {
+      const uint32_t i = a.begin + (tile << a.tile_shift) + sub * 32 + lane;
       if (i >= a.end) continue;
       const uint8_t flags = a.active[i];
       if (!DETERMINE && !(flags & kSurfelActiveFlag)) continue;   // normals are updated for active surfels only
@@ -456,7 +457,8 @@ __global__ void __launch_bounds__(kGeoThreads) ActivationNormalsKernel(const __g
 
 template <bool USE_DEPTH, bool USE_DESC>
 __global__ void __launch_bounds__(kGeoThreads) PositionDescriptorKernel(const __grid_constant__ GeometryArgs a) {
-  const uint32_t n_tiles = (a.end - a.begin + kGeoThreads - 1) / kGeoThreads;
+  const uint32_t tile_len = 1u << a.tile_shift;
+  const uint32_t n_tiles = (a.end - a.begin + tile_len - 1) >> a.tile_shift;
   const uint32_t n_groups = (a.kf_count + kGeoGroup - 1) / kGeoGroup;
   const uint32_t n_items = n_groups * n_tiles;
   const size_t P = a.pitch;
@@ -465,8 +467,8 @@ __global__ void __launch_bounds__(kGeoThreads) PositionDescriptorKernel(const __
   while (NextGeoItem(a, n_tiles, n_items, &group, &tile)) {
     const bool first = group == 0, last = group + 1 == n_groups;
     const int j_begin = group * kGeoGroup, j_end = min(a.kf_count, static_cast<int>(group + 1) * kGeoGroup);
-    for (uint32_t sub = 0; sub < kGeoThreads / 32; ++sub) {
-      const uint32_t i = a.begin + tile * kGeoThreads + sub * 32 + lane;
+    for (uint32_t sub = 0; sub < tile_len / 32; ++sub) {
+      const uint32_t i = a.begin + (tile << a.tile_shift) + sub * 32 + lane;
       if (i >= a.end || !(a.active[i] & kSurfelActiveFlag)) continue;
       const Vec3 gp = V3(a.surfels[kRowX * P + i], a.surfels[kRowY * P + i], a.surfels[kRowZ * P + i]);
       const Vec3 nrm = UnpackNormal(__float_as_uint(a.surfels[kRowNormal * P + i]));
@@ -595,22 +597,36 @@ __global__ void __launch_bounds__(kGeoThreads) PositionDescriptorKernel(const __
 }
 
 // Persistent grid: as many CTAs as can be co-resident (the epoch wait relies on every launched CTA being scheduled).
+// The tile (the unit one warp walks through, 32..256 surfels) is chosen so that every keyframe group offers several
+// items per resident warp: with too few tiles the per-tile epoch chain serialises the groups (seen at 2+ ranks).
 template <typename Kernel>
-static uint32_t GeoGrid(Kernel kernel, const GeometryArgs& a, int sm_count) {
+static uint32_t GeoGrid(Kernel kernel, GeometryArgs* a, int sm_count) {
   int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kGeoThreads, 0);
   if (per_sm < 1) per_sm = 1;
-  const uint32_t n_tiles = (a.end - a.begin + kGeoThreads - 1) / kGeoThreads;
-  const uint32_t n_groups = (a.kf_count + kGeoGroup - 1) / kGeoGroup;
+  const uint64_t resident_warps = static_cast<uint64_t>(per_sm) * sm_count * (kGeoThreads / 32);
+  const uint32_t n = a->end - a->begin;
+  int shift = 8;
+  while (shift > 5 && 2 * static_cast<uint64_t>((n + (1u << shift) - 1) >> shift) < 3 * resident_warps) --shift;
+  a->tile_shift = shift;
+  const uint32_t n_tiles = (n + (1u << shift) - 1) >> shift;
+  const uint32_t n_groups = (a->kf_count + kGeoGroup - 1) / kGeoGroup;
   const uint64_t n_items = static_cast<uint64_t>(n_tiles) * (n_groups ? n_groups : 1);
   const uint64_t ctas_needed = (n_items + kGeoThreads / 32 - 1) / (kGeoThreads / 32);   // one item per warp
   return static_cast<uint32_t>(std::min<uint64_t>(ctas_needed, static_cast<uint64_t>(per_sm) * sm_count));
 }
 
 static void PrepareGeo(const GeometryArgs& a, cudaStream_t stream) {
-  const uint32_t n_tiles = (a.end - a.begin + kGeoThreads - 1) / kGeoThreads;
+  const uint32_t n_tiles = (a.end - a.begin + (1u << a.tile_shift) - 1) >> a.tile_shift;
   cudaMemsetAsync(a.queue, 0, sizeof(unsigned int), stream);
   cudaMemsetAsync(a.tile_epoch, 0, sizeof(unsigned int) * n_tiles, stream);
+}
+
+template <typename Kernel>
+static void LaunchGeo(Kernel kernel, GeometryArgs a, int sm_count, cudaStream_t stream) {
+  const uint32_t grid = GeoGrid(kernel, &a, sm_count);
+  PrepareGeo(a, stream);
+  kernel<<<grid, kGeoThreads, 0, stream>>>(a);
 }
 
 void LaunchActivationAndNormals(const GeometryArgs& a, int sm_count, bool determine_activation, bool update_normals, cudaStream_t stream) {
@@ -620,25 +636,18 @@ void LaunchActivationAndNormals(const GeometryArgs& a, int sm_count, bool determ
     if (determine_activation) cudaMemsetAsync(a.active + a.begin, 0, a.end - a.begin, stream);
     return;
   }
-  PrepareGeo(a, stream);
-  if (determine_activation && update_normals)
-    ActivationNormalsKernel<true, true><<<GeoGrid(ActivationNormalsKernel<true, true>, a, sm_count), kGeoThreads, 0, stream>>>(a);
-  else if (determine_activation)
-    ActivationNormalsKernel<true, false><<<GeoGrid(ActivationNormalsKernel<true, false>, a, sm_count), kGeoThreads, 0, stream>>>(a);
-  else
-    ActivationNormalsKernel<false, true><<<GeoGrid(ActivationNormalsKernel<false, true>, a, sm_count), kGeoThreads, 0, stream>>>(a);
+  if (determine_activation && update_normals) LaunchGeo(ActivationNormalsKernel<true, true>, a, sm_count, stream);
+  else if (determine_activation) LaunchGeo(ActivationNormalsKernel<true, false>, a, sm_count, stream);
+  else LaunchGeo(ActivationNormalsKernel<false, true>, a, sm_count, stream);
 }
 
 void LaunchPositionAndDescriptor(const GeometryArgs& a, int sm_count, cudaStream_t stream) {
   if (a.end <= a.begin || a.kf_count <= 0) return;
-  PrepareGeo(a, stream);
   if (a.cam.use_desc) {
-    if (a.cam.use_depth)
-      PositionDescriptorKernel<true, true><<<GeoGrid(PositionDescriptorKernel<true, true>, a, sm_count), kGeoThreads, 0, stream>>>(a);
-    else
-      PositionDescriptorKernel<false, true><<<GeoGrid(PositionDescriptorKernel<false, true>, a, sm_count), kGeoThreads, 0, stream>>>(a);
+    if (a.cam.use_depth) LaunchGeo(PositionDescriptorKernel<true, true>, a, sm_count, stream);
+    else LaunchGeo(PositionDescriptorKernel<false, true>, a, sm_count, stream);
   } else {
-    PositionDescriptorKernel<true, false><<<GeoGrid(PositionDescriptorKernel<true, false>, a, sm_count), kGeoThreads, 0, stream>>>(a);
+    LaunchGeo(PositionDescriptorKernel<true, false>, a, sm_count, stream);
   }
 }
 

@@ -64,7 +64,8 @@ struct GeometryArgs {
   const int* kf_list;          // non-inactive keyframes (ascending ids)
   int kf_count;
   unsigned int* queue;         // work-item counter (reset by the launcher)
-  unsigned int* tile_epoch;    // [ceil(n / 256)] keyframe groups retired per tile (reset by the launcher)
+  unsigned int* tile_epoch;    // [ceil(n / 32)] keyframe groups retired per tile (reset by the launcher)
+  int tile_shift;              // log2(surfels per tile), 5..8; chosen by the launcher
 };
 // SetSurfelInactive + DetermineActiveSurfels (kernel_surfel_activation.cu:38-79) fused with the normal
 // accumulation + update (kernel_opt_geometry.cu:527-597).

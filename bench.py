@@ -393,6 +393,22 @@ def run_reference(args, scene):
 
 
 def main():
+    # Exactly one JSON line may reach stdout: route everything libraries print there (e.g. NCCL's version banner)
+    # to stderr while the benchmark runs.
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        return _main(saved_stdout)
+    finally:
+        try:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
+        except Exception:
+            pass
+
+
+def _main(saved_stdout):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -415,7 +431,8 @@ def main():
     else:
         out = run_ours(args, scene, rank, world)
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        sys.stdout.flush()
+        os.write(saved_stdout, (json.dumps(out) + "\n").encode())
     return 0
 
 

@@ -1,0 +1,147 @@
+// include/badba_direct_ba.hpp -- header-only C++ adaptor that keeps the reference's own signatures on top of the
+// C ABI of include/badba.h, so that BadSlam::RunBundleAdjustment (applications/badslam/src/badslam/bad_slam.cc:485-540)
+// and the BA thread (bad_slam.cc:1196-1317) can call the sm_100a backend without source changes beyond the include.
+//
+// It mirrors  class vis::DirectBA  (applications/badslam/src/badslam/direct_ba.h:65-550):
+//   ctor                      direct_ba.h:73-88
+//   AddKeyframe               direct_ba.h:95      (takes the keyframe's device buffers, keyframe.h:160-200)
+//   EstimateFramePose         direct_ba.h:122-129
+//   BundleAdjustment          direct_ba.h:143-162
+//   accessors                 direct_ba.h:243-377
+// The reference passes Eigen / Sophus / libvis types; this adaptor is templated on them so that it compiles both
+// inside the reference tree (SE3f = Sophus::SE3f, PinholeCamera4f = vis::PinholeCamera4f, CUDABuffer<T>) and in a
+// tree without Eigen (any type with .data() returning {qx,qy,qz,qw,tx,ty,tz} and .parameters()).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <functional>
+#include <stdexcept>
+#include <string>
+
+#include "badba.h"
+
+namespace badba {
+
+class Error : public std::runtime_error {
+ public:
+  Error(bba_status s, const std::string& what) : std::runtime_error(what), status(s) {}
+  bba_status status;
+};
+
+// A pitched device image as the reference's CUDABuffer_<T> exposes it (cuda_buffer.cuh:112-118).
+template <typename T>
+struct DeviceImage {
+  const T* address;
+  size_t pitch_bytes;
+};
+
+template <typename SE3f, typename PinholeCamera4f>
+class DirectBA {
+ public:
+  DirectBA(int max_surfel_count, float raw_to_float_depth, float baseline_fx, int sparse_surfel_cell_size,
+           float /*surfel_merge_dist_factor*/, int /*min_observation_count_while_bootstrapping_1*/,
+           int /*min_observation_count_while_bootstrapping_2*/, int /*min_observation_count*/,
+           const PinholeCamera4f& color_camera_initial_estimate, const PinholeCamera4f& depth_camera_initial_estimate,
+           int /*pyramid_level_for_color*/, bool use_depth_residuals, bool use_descriptor_residuals, int max_keyframes = 2500,
+           int device = 0, int rank = 0, int world_size = 1) {
+    bba_config c{};
+    c.depth_width = depth_camera_initial_estimate.width();
+    c.depth_height = depth_camera_initial_estimate.height();
+    c.color_width = color_camera_initial_estimate.width();
+    c.color_height = color_camera_initial_estimate.height();
+    for (int i = 0; i < 4; ++i) {
+      c.depth_intrinsics[i] = depth_camera_initial_estimate.parameters()[i];
+      c.color_intrinsics[i] = color_camera_initial_estimate.parameters()[i];
+    }
+    c.raw_to_float_depth = raw_to_float_depth;
+    c.baseline_fx = baseline_fx;
+    c.sparse_surfel_cell_size = sparse_surfel_cell_size;
+    c.max_surfel_count = static_cast<uint32_t>(max_surfel_count);
+    c.max_keyframes = max_keyframes;
+    c.use_depth_residuals = use_depth_residuals;
+    c.use_descriptor_residuals = use_descriptor_residuals;
+    c.device = device;
+    c.rank = rank;
+    c.world_size = world_size;
+    Check(bba_create(&c, &h_), "bba_create");
+  }
+  ~DirectBA() { bba_destroy(h_); }
+  DirectBA(const DirectBA&) = delete;
+  DirectBA& operator=(const DirectBA&) = delete;
+
+  // surfels_ / active_surfels_ are owned by the caller exactly as in the reference (direct_ba.cc:122-123).
+  void SetSurfelBuffers(float* surfels, size_t pitch_bytes, uint32_t surfels_size, uint8_t* active_surfels) {
+    Check(bba_set_surfels(h_, surfels, pitch_bytes, surfels_size), "bba_set_surfels");
+    Check(bba_set_active_flags(h_, active_surfels), "bba_set_active_flags");
+  }
+
+  // DirectBA::AddKeyframe(const shared_ptr<Keyframe>&): pass keyframe->depth_buffer().ToCUDA() etc.
+  int AddKeyframe(cudaStream_t stream, DeviceImage<uint16_t> depth, DeviceImage<uint16_t> normals, DeviceImage<uint16_t> radius,
+                  DeviceImage<uint8_t> color_rgba, const SE3f& global_T_frame, float min_depth, float max_depth) {
+    int id = -1;
+    Check(bba_add_keyframe(h_, depth.address, depth.pitch_bytes, normals.address, normals.pitch_bytes, radius.address,
+                           radius.pitch_bytes, color_rgba.address, color_rgba.pitch_bytes, global_T_frame.data(), min_depth,
+                           max_depth, stream, &id),
+          "bba_add_keyframe");
+    return id;
+  }
+
+  // direct_ba.h:122-129 (frame = an already added keyframe)
+  void EstimateFramePose(cudaStream_t stream, const SE3f& global_T_frame_initial_estimate, int keyframe_id,
+                         SE3f* out_global_T_frame_estimate, bool /*called_within_ba*/ = false) {
+    float out[7];
+    Check(bba_estimate_frame_pose(h_, keyframe_id, global_T_frame_initial_estimate.data(), out, nullptr, nullptr, stream),
+          "bba_estimate_frame_pose");
+    for (int i = 0; i < 7; ++i) out_global_T_frame_estimate->data()[i] = out[i];
+  }
+
+  // direct_ba.h:143-162, same argument order and defaults.
+  void BundleAdjustment(cudaStream_t stream, bool optimize_depth_intrinsics, bool optimize_color_intrinsics, bool do_surfel_updates,
+                        bool optimize_poses, bool optimize_geometry, int min_iterations, int max_iterations, bool use_pcg,
+                        int active_keyframe_window_start, int active_keyframe_window_end, bool increase_ba_iteration_count,
+                        int* iterations_done = nullptr, bool* converged = nullptr, double time_limit = 0, void* /*timer*/ = nullptr,
+                        int /*pcg_max_inner_iterations*/ = 30, int /*pcg_max_keyframes*/ = 2500,
+                        std::function<bool(int)> /*progress_function*/ = nullptr) {
+    bba_ba_options o{};
+    o.optimize_depth_intrinsics = optimize_depth_intrinsics;
+    o.optimize_color_intrinsics = optimize_color_intrinsics;
+    o.do_surfel_updates = do_surfel_updates;
+    o.optimize_poses = optimize_poses;
+    o.optimize_geometry = optimize_geometry;
+    o.min_iterations = min_iterations;
+    o.max_iterations = max_iterations;
+    o.use_pcg = use_pcg;
+    o.active_keyframe_window_start = active_keyframe_window_start;
+    o.active_keyframe_window_end = active_keyframe_window_end;
+    o.increase_ba_iteration_count = increase_ba_iteration_count;
+    o.time_limit_seconds = time_limit;
+    bba_ba_result r{};
+    Check(bba_bundle_adjust(h_, &o, &r, stream), "bba_bundle_adjust");
+    if (iterations_done) *iterations_done = r.iterations_done;
+    if (converged) *converged = r.converged != 0;
+    last_result_ = r;
+  }
+
+  void GetKeyframePose(int keyframe_id, SE3f* global_T_frame) const {
+    float p[7];
+    Check(bba_get_keyframe_pose(h_, keyframe_id, p), "bba_get_keyframe_pose");
+    for (int i = 0; i < 7; ++i) global_T_frame->data()[i] = p[i];
+  }
+  void SetKeyframePose(int keyframe_id, const SE3f& global_T_frame) {
+    Check(bba_set_keyframe_pose(h_, keyframe_id, global_T_frame.data()), "bba_set_keyframe_pose");
+  }
+  void GetIntrinsics(float depth[4], float color[4], float* a) const { Check(bba_get_intrinsics(h_, depth, color, a), "bba_get_intrinsics"); }
+  const bba_ba_result& last_result() const { return last_result_; }
+  bba_handle handle() const { return h_; }
+
+ private:
+  void Check(bba_status s, const char* where) const {
+    if (s != BBA_OK) throw Error(s, std::string(where) + ": " + (h_ ? bba_last_error(h_) : "no handle"));
+  }
+  bba_handle h_ = nullptr;
+  bba_ba_result last_result_{};
+};
+
+}  // namespace badba

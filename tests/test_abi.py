@@ -68,3 +68,30 @@ def test_product_does_not_import_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f
                 assert '#include "../../oracle' not in txt and "oracle/host_math" not in txt, f
+
+
+def test_cpp_adaptor_header_compiles_and_fails_loudly_without_device(tmp_path):
+    """include/badba_direct_ba.hpp (the reference-signature adaptor of INTEGRATION.md) compiles against the library."""
+    import shutil
+    import subprocess
+    import torch
+    gxx = shutil.which("g++")
+    if gxx is None or not os.path.isdir("/usr/local/cuda/include"):
+        pytest.skip("no host compiler / CUDA headers")
+    src = tmp_path / "adaptor.cpp"
+    src.write_text(r'''
+#include "badba_direct_ba.hpp"
+struct SE3 { float d[7]; float* data() { return d; } const float* data() const { return d; } };
+struct Cam { int w, h; float p[4]; int width() const { return w; } int height() const { return h; } const float* parameters() const { return p; } };
+int main() {
+  Cam c{64, 48, {30, 30, 32, 24}};
+  try { badba::DirectBA<SE3, Cam> ba(1000, 1e-3f, 40.f, 4, 0.8f, 1, 2, 3, c, c, 0, true, true); }
+  catch (const badba::Error& e) { return e.status == BBA_ERR_NO_DEVICE ? 42 : 1; }
+  return 0;
+}''')
+    exe = tmp_path / "adaptor"
+    libdir = os.path.join(ROOT, "badslam_b200")
+    subprocess.check_call([gxx, "-std=c++17", "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include", str(src), "-o", str(exe),
+                           "-L", libdir, "-lbadba_b200", f"-Wl,-rpath,{libdir}"])
+    rc = subprocess.call([str(exe)])
+    assert rc == (0 if torch.cuda.is_available() else 42)
