@@ -199,6 +199,13 @@ struct bba_context {
   float* h_pose_pack = nullptr;       // pinned copy
   int* d_local_ids = nullptr;         // [max_kf]
 
+  // intrinsics step (lazily allocated): [head 64 | B 5P | D P | b2 P | obs P | x1 8] floats + 34 fp64 sums
+  float* d_intr = nullptr;
+  double* d_intr_sums = nullptr;
+  int* d_all_list = nullptr;          // 0 .. max_kf-1
+  double* h_intr_sums = nullptr;      // pinned
+  float* h_intr_x1 = nullptr;         // pinned, 8 floats
+
   uint64_t launches = 0;
   int ba_iteration_count = 0;
 
@@ -522,6 +529,101 @@ bba_status BuildGeometryArgs(bba_handle h, bba::GeometryArgs* g, cudaStream_t s)
   return BBA_OK;
 }
 
+// OptimizeIntrinsicsCUDA (kernel_opt_intrinsics.cc:39-281): accumulate over EVERY keyframe, Schur-complement the
+// per-cell cfactors away, solve the 5x5 / 4x4 systems in fp64 on the host, update intrinsics, a and the cfactors.
+bba_status OptimizeIntrinsics(bba_handle h, bool opt_depth, bool opt_color, cudaStream_t s) {
+  const int K = static_cast<int>(h->keyframes.size());
+  if (h->surfels_size == 0 || K == 0) return BBA_OK;   // :56-58
+  const uint32_t P = static_cast<uint32_t>(h->cf_w) * h->cf_h;
+  const size_t intr_floats = 64 + static_cast<size_t>(8) * P + 8;
+  if (!h->d_intr) {
+    BBA_CUDA(h, cudaMalloc(&h->d_intr, sizeof(float) * intr_floats));
+    BBA_CUDA(h, cudaMalloc(&h->d_intr_sums, sizeof(double) * bba::kIntrinsicsSums));
+    BBA_CUDA(h, cudaMalloc(&h->d_all_list, sizeof(int) * h->cfg.max_keyframes));
+    BBA_CUDA(h, cudaMallocHost(&h->h_intr_sums, sizeof(double) * bba::kIntrinsicsSums));
+    BBA_CUDA(h, cudaMallocHost(&h->h_intr_x1, sizeof(float) * 8));
+    std::vector<int> iota(h->cfg.max_keyframes);
+    for (int i = 0; i < h->cfg.max_keyframes; ++i) iota[i] = i;
+    BBA_CUDA(h, cudaMemcpy(h->d_all_list, iota.data(), sizeof(int) * iota.size(), cudaMemcpyHostToDevice));
+  }
+  if (bba_status st = UploadKeyframes(h, s)) return st;
+  BBA_CUDA(h, cudaMemsetAsync(h->d_intr, 0, sizeof(float) * intr_floats, s));                      // :69-80
+  BBA_CUDA(h, cudaMemsetAsync(h->d_intr_sums, 0, sizeof(double) * bba::kIntrinsicsSums, s));
+  float* cell_B = h->d_intr + 64;
+  float* cell_D = cell_B + static_cast<size_t>(5) * P;
+  float* cell_b2 = cell_D + P;
+  float* cell_obs = cell_b2 + P;
+  float* d_x1 = cell_obs + P;
+
+  bba::IntrinsicsArgs a;
+  a.cam = MakeCamera(h);
+  a.surfels = h->surfels;
+  a.pitch = static_cast<uint32_t>(h->surfel_pitch_bytes / sizeof(float));
+  a.begin = 0;
+  a.end = h->surfels_size;
+  if (h->cfg.world_size > 1) ShardSurfelRange(h->surfels_size, h->cfg.rank, h->cfg.world_size, &a.begin, &a.end, nullptr);
+  a.kfs = h->d_kfs;
+  a.kf_list = h->d_all_list;
+  a.kf_count = K;
+  a.queue = h->d_geo_queue;
+  a.sums = h->d_intr_sums;
+  a.cell_B = cell_B;
+  a.cell_D = cell_D;
+  a.cell_b2 = cell_b2;
+  a.cell_obs = cell_obs;
+  a.cell_count = P;
+  bba::LaunchIntrinsicsAccumulate(a, h->sm_count, opt_color, opt_depth, s);   // :84-108, one launch for all keyframes
+  ++h->launches;
+  if (h->cfg.world_size > 1) {
+    // every rank accumulated its surfel shard: one sum all-reduce over [34 global sums | B | D | b2 | obs]
+    bba::LaunchIntrinsicsConvertSums(h->d_intr_sums, h->d_intr, true, s);
+    h->collective(h->collective_user, BBA_COLLECTIVE_ALLREDUCE_SUM, h->d_intr, 64 + static_cast<size_t>(8) * P, s);
+    bba::LaunchIntrinsicsConvertSums(h->d_intr_sums, h->d_intr, false, s);
+    h->launches += 2;
+  }
+  if (opt_depth) {
+    bba::LaunchIntrinsicsSchur(P, cell_B, cell_D, cell_b2, h->d_intr_sums, s);   // :120-127
+    ++h->launches;
+  }
+  BBA_CUDA(h, cudaGetLastError());
+  BBA_CUDA(h, cudaMemcpyAsync(h->h_intr_sums, h->d_intr_sums, sizeof(double) * bba::kIntrinsicsSums, cudaMemcpyDeviceToHost, s));
+  BBA_CUDA(h, cudaStreamSynchronize(s));   // :136
+
+  if (opt_depth) {
+    // the reference keeps A and b1 in fp32 buffers and solves in fp64 (:130-171)
+    double A[15], b1[5], x1[5];
+    for (int i = 0; i < 15; ++i) A[i] = static_cast<double>(static_cast<float>(h->h_intr_sums[i]));
+    for (int i = 0; i < 5; ++i) b1[i] = static_cast<double>(static_cast<float>(h->h_intr_sums[15 + i]));
+    constexpr float kAPriorWeight = 10;   // :153-155
+    A[14] = static_cast<double>(static_cast<float>(A[14]) + kAPriorWeight * kAPriorWeight);
+    b1[4] = static_cast<double>(static_cast<float>(b1[4]) + kAPriorWeight * kAPriorWeight * h->depth_a);
+    bba::SolveLDLT<5>(A, b1, x1);
+    float x1f[5];
+    for (int i = 0; i < 5; ++i) x1f[i] = static_cast<float>(x1[i]);
+    const bba::CameraParams& c = a.cam;   // :183-194
+    const float new_fx = 1.0f / (c.fx_inv - x1f[0]);
+    const float new_fy = 1.0f / (c.fy_inv - x1f[1]);
+    const float new_cx = -(new_fx * (c.cx_inv - x1f[2])) + 0.5f;
+    const float new_cy = -(new_fy * (c.cy_inv - x1f[3])) + 0.5f;
+    for (int i = 0; i < 5; ++i) h->h_intr_x1[i] = x1f[i];
+    BBA_CUDA(h, cudaMemcpyAsync(d_x1, h->h_intr_x1, sizeof(float) * 5, cudaMemcpyHostToDevice, s));   // :196
+    bba::LaunchIntrinsicsCellUpdate(P, cell_obs, cell_B, cell_D, d_x1, h->d_cfactor, s);             // :205-212
+    ++h->launches;
+    BBA_CUDA(h, cudaGetLastError());
+    BBA_CUDA(h, cudaStreamSynchronize(s));   // h_intr_x1 is reused by the next call
+    h->depth_K[0] = new_fx; h->depth_K[1] = new_fy; h->depth_K[2] = new_cx; h->depth_K[3] = new_cy;
+    h->depth_a -= x1f[4];
+  }
+  if (opt_color) {   // :256-280
+    double H[10], b[4], x[4];
+    for (int i = 0; i < 10; ++i) H[i] = static_cast<double>(static_cast<float>(h->h_intr_sums[20 + i]));
+    for (int i = 0; i < 4; ++i) b[i] = static_cast<double>(static_cast<float>(h->h_intr_sums[30 + i]));
+    bba::SolveLDLT<4>(H, b, x);
+    for (int i = 0; i < 4; ++i) h->color_K[i] -= static_cast<float>(x[i]);
+  }
+  return BBA_OK;
+}
+
 bba_status AddKeyframeCommon(bba_handle h, Keyframe&& kf, const uint8_t* device_rgba, size_t color_pitch, const float pose[7],
                              float min_depth, float max_depth, cudaStream_t s, int* out_id) {
   if (static_cast<int>(h->keyframes.size()) >= h->cfg.max_keyframes) return Fail(h, BBA_ERR_STATE, "max_keyframes exceeded");
@@ -694,6 +796,11 @@ void bba_destroy(bba_handle h) {
   cudaFreeHost(h->h_pose_pack);
   cudaFree(h->d_local_ids);
   cudaFree(h->d_tile_epoch);
+  cudaFree(h->d_intr);
+  cudaFree(h->d_intr_sums);
+  cudaFree(h->d_all_list);
+  cudaFreeHost(h->h_intr_sums);
+  cudaFreeHost(h->h_intr_x1);
   if (h->h_flag) cudaFreeHost(const_cast<int*>(h->h_flag));
   cudaFreeHost(h->h_totals);
   for (auto& e : h->prof_ev)
@@ -1014,8 +1121,11 @@ bba_status bba_optimize_geometry_iteration(bba_handle h, void* stream) {
 }
 
 bba_status bba_optimize_intrinsics(bba_handle h, int optimize_depth, int optimize_color, void* stream) {
-  (void)optimize_depth; (void)optimize_color; (void)stream;
-  return Fail(h, BBA_ERR_UNSUPPORTED, "intrinsics optimisation is not implemented yet");
+  if (!h) return BBA_ERR_INVALID_ARGUMENT;
+  if (!optimize_depth && !optimize_color) return Fail(h, BBA_ERR_INVALID_ARGUMENT, "nothing to optimise");   // kernel_opt_intrinsics.cc:54
+  if (bba_status st = CheckSurfels(h)) return st;
+  if (bba_status st = CheckCollective(h)) return st;
+  return OptimizeIntrinsics(h, optimize_depth != 0, optimize_color != 0, static_cast<cudaStream_t>(stream));
 }
 
 bba_status bba_bundle_adjust(bba_handle h, const bba_ba_options* o, bba_ba_result* res, void* stream) {
@@ -1027,7 +1137,6 @@ bba_status bba_bundle_adjust(bba_handle h, const bba_ba_options* o, bba_ba_resul
   // direct_ba.cc:427-434
   const bool opt_depth_intr = o->optimize_depth_intrinsics && h->cfg.use_depth_residuals;
   const bool opt_color_intr = o->optimize_color_intrinsics && h->cfg.use_descriptor_residuals;
-  if (opt_depth_intr || opt_color_intr) return Fail(h, BBA_ERR_UNSUPPORTED, "intrinsics optimisation is not implemented yet");
   if (bba_status st = CheckCollective(h)) return st;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int K = static_cast<int>(h->keyframes.size());
@@ -1114,6 +1223,13 @@ bba_status bba_bundle_adjust(bba_handle h, const bba_ba_options* o, bba_ba_resul
       BBA_CUDA(h, cudaStreamSynchronize(s));
     }
     BBA_CUDA(h, cudaEventRecord(h->ev[3], s));
+    // --- intrinsics optimisation (:584-624)
+    if (opt_depth_intr || opt_color_intr) {
+      if (bba_status st = OptimizeIntrinsics(h, opt_depth_intr, opt_color_intr, s)) return st;
+      BBA_CUDA(h, cudaEventRecord(h->ev[4], s));
+      BBA_CUDA(h, cudaEventSynchronize(h->ev[4]));
+      cudaEventElapsedTime(&res->ms_intrinsics_optimization, h->ev[3], h->ev[4]);
+    }
     BBA_CUDA(h, cudaEventSynchronize(h->ev[3]));
     cudaEventElapsedTime(&res->ms_surfel_activation, h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&res->ms_geometry_optimization, h->ev[1], h->ev[2]);

@@ -84,6 +84,30 @@ constexpr int kPoseSlot = 17;   // 7 pose, iterations, converged, 8 first-iterat
 void LaunchPackPoseResults(const int* ids, int n, const float* pose_est, const int* iterations, const int* converged,
                            const double* first_stats, float* out, cudaStream_t stream);
 
+// Intrinsics + depth-deformation step (intrinsics.cu; OptimizeIntrinsicsCUDA, kernel_opt_intrinsics.cc:39-281).
+constexpr int kIntrinsicsSums = 34;   // A (15) b1 (5) colour H (10) colour b (4), fp64
+struct IntrinsicsArgs {
+  CameraParams cam;
+  const float* surfels;
+  uint32_t pitch;
+  uint32_t begin, end;         // surfel range processed by this rank
+  const KfDevice* kfs;
+  const int* kf_list;          // every keyframe (ascending ids)
+  int kf_count;
+  unsigned int* queue;         // work-item counter (reset by the launcher)
+  double* sums;                // [kIntrinsicsSums]
+  float* cell_B;               // [5][cell_count]
+  float* cell_D;               // [cell_count]
+  float* cell_b2;              // [cell_count]
+  float* cell_obs;             // [cell_count] observation count (fp32 so that one sum all-reduce covers everything)
+  uint32_t cell_count;
+};
+void LaunchIntrinsicsAccumulate(const IntrinsicsArgs& a, int sm_count, bool optimize_color, bool optimize_depth, cudaStream_t stream);
+void LaunchIntrinsicsSchur(uint32_t cell_count, float* B, float* D, const float* b2, double* sums, cudaStream_t stream);
+void LaunchIntrinsicsConvertSums(double* sums, float* head, bool to_float, cudaStream_t stream);
+void LaunchIntrinsicsCellUpdate(uint32_t cell_count, const float* obs, const float* B, const float* D, const float* x1,
+                                float* cfactor, cudaStream_t stream);
+
 // uchar4 (.w = luma) -> u8 plane.
 void LaunchExtractLuma(const uint8_t* rgba, size_t rgba_pitch, uint8_t* luma, size_t luma_pitch, int w, int h, cudaStream_t stream);
 

@@ -24,7 +24,8 @@ class Config(C.Structure):
 class BAOptions(C.Structure):
     _fields_ = [("optimize_poses", C.c_int), ("optimize_geometry", C.c_int),
                 ("min_iterations", C.c_int), ("max_iterations", C.c_int),
-                ("active_keyframe_window_start", C.c_int), ("active_keyframe_window_end", C.c_int)]
+                ("active_keyframe_window_start", C.c_int), ("active_keyframe_window_end", C.c_int),
+                ("optimize_depth_intrinsics", C.c_int), ("optimize_color_intrinsics", C.c_int)]
 
 
 class BAResult(C.Structure):
@@ -61,6 +62,9 @@ def lib():
         l.ref_pose_coeffs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         l.ref_estimate_frame_pose.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         l.ref_update_activation.argtypes = [C.c_void_p]
+        l.ref_optimize_intrinsics.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        l.ref_get_intrinsics.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.ref_get_cfactor.argtypes = [C.c_void_p, C.c_void_p]
         l.ref_optimize_geometry_iteration.argtypes = [C.c_void_p]
         l.ref_bundle_adjust.argtypes = [C.c_void_p, C.POINTER(BAOptions), C.POINTER(BAResult), C.c_int]
         l.ref_snapshot.argtypes = [C.c_void_p]
@@ -98,6 +102,7 @@ class RefDirectBA:
             raise RuntimeError("ref_create failed (no GPU?)")
         self.K = cfg.num_keyframes
         self.n = scene.num_surfels
+        self.cf_shape = tuple(scene.cfactor.shape)
         poses = scene.poses_init if poses is None else poses
         for k in range(self.K):
             p = np.ascontiguousarray(poses[k], np.float32)
@@ -178,10 +183,31 @@ class RefDirectBA:
     def optimize_geometry_iteration(self):
         self.l.ref_optimize_geometry_iteration(self.h)
 
+    def optimize_intrinsics(self, depth=True, color=True):
+        self.l.ref_optimize_intrinsics(self.h, int(depth), int(color))
+
+    def intrinsics(self):
+        d = np.zeros(4, np.float32)
+        c = np.zeros(4, np.float32)
+        a = C.c_float()
+        self.l.ref_get_intrinsics(self.h, d.ctypes.data, c.ctypes.data, C.byref(a))
+        return d, c, a.value
+
+    def cfactor(self):
+        out = np.zeros(self.cf_shape, np.float32)
+        self.l.ref_get_cfactor(self.h, out.ctypes.data)
+        return out
+
+    def set_depth_params(self, a, cfactor):
+        cf = np.ascontiguousarray(cfactor, np.float32)
+        self.l.ref_set_depth_params(self.h, float(a), cf.ctypes.data)
+
     def bundle_adjust(self, optimize_poses=True, optimize_geometry=True, min_iterations=1, max_iterations=10,
-                      window_start=0, window_end=None, count_residuals=True):
+                      window_start=0, window_end=None, count_residuals=True, optimize_depth_intrinsics=False,
+                      optimize_color_intrinsics=False):
         o = BAOptions(int(optimize_poses), int(optimize_geometry), min_iterations, max_iterations, window_start,
-                      self.K - 1 if window_end is None else window_end)
+                      self.K - 1 if window_end is None else window_end, int(optimize_depth_intrinsics),
+                      int(optimize_color_intrinsics))
         r = BAResult()
         self.l.ref_bundle_adjust(self.h, C.byref(o), C.byref(r), int(count_residuals))
         return r

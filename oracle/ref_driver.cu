@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "badslam/kernel_opt_geometry.h"
+#include "badslam/kernel_opt_intrinsics.h"
 #include "badslam/kernel_opt_pose.h"
 #include "badslam/kernel_surfel_activation.h"
 #include "badslam/kernels.cuh"
@@ -54,6 +55,7 @@ struct ref_ba_options {
   int optimize_poses, optimize_geometry;
   int min_iterations, max_iterations;
   int active_keyframe_window_start, active_keyframe_window_end;
+  int optimize_depth_intrinsics, optimize_color_intrinsics;
 };
 
 struct ref_ba_result {
@@ -77,6 +79,9 @@ struct ref_context {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4];
   unsigned long long launches = 0;
+  // IntrinsicsOptimizationHelperBuffers (kernels.h:60-93), lazily allocated
+  u32* intr_obs = nullptr; float* intr_A = nullptr; float* intr_B = nullptr; float* intr_D = nullptr;
+  float* intr_b1 = nullptr; float* intr_b2 = nullptr; float* intr_H = nullptr; float* intr_b = nullptr;
 };
 
 namespace {
@@ -263,6 +268,89 @@ void OptimizeGeometryIteration(ref_context* c) {
   }
 }
 
+// kernel_opt_intrinsics.cc:39-281 (thin host wrapper around the reference's three kernels; Eigen's fp64 LDLT -> hm_ldlt_solve)
+void OptimizeIntrinsics(ref_context* c, bool opt_depth, bool opt_color) {
+  if (c->surfels_size == 0) return;
+  constexpr int kARows = 5;
+  cudaStream_t s = c->stream;
+  const int P = c->cf_w * c->cf_h;
+  if (!c->intr_obs) {
+    cudaMalloc(&c->intr_obs, sizeof(u32) * P);
+    cudaMalloc(&c->intr_A, sizeof(float) * 15);
+    cudaMalloc(&c->intr_B, sizeof(float) * kARows * P);
+    cudaMalloc(&c->intr_D, sizeof(float) * P);
+    cudaMalloc(&c->intr_b1, sizeof(float) * kARows);
+    cudaMalloc(&c->intr_b2, sizeof(float) * P);
+    cudaMalloc(&c->intr_H, sizeof(float) * 10);
+    cudaMalloc(&c->intr_b, sizeof(float) * 4);
+  }
+  CUDABuffer_<u32> obs(c->intr_obs, 1, P, sizeof(u32) * P);
+  CUDABuffer_<float> A(c->intr_A, 1, 15, sizeof(float) * 15), B(c->intr_B, kARows, P, sizeof(float) * P),
+      D(c->intr_D, 1, P, sizeof(float) * P), b1(c->intr_b1, 1, kARows, sizeof(float) * kARows),
+      b2(c->intr_b2, 1, P, sizeof(float) * P), H(c->intr_H, 1, 10, sizeof(float) * 10), b(c->intr_b, 1, 4, sizeof(float) * 4);
+  if (opt_depth) {
+    cudaMemsetAsync(c->intr_obs, 0, sizeof(u32) * P, s);
+    cudaMemsetAsync(c->intr_A, 0, sizeof(float) * 15, s);
+    cudaMemsetAsync(c->intr_B, 0, sizeof(float) * kARows * P, s);
+    cudaMemsetAsync(c->intr_D, 0, sizeof(float) * P, s);
+    cudaMemsetAsync(c->intr_b1, 0, sizeof(float) * kARows, s);
+    cudaMemsetAsync(c->intr_b2, 0, sizeof(float) * P, s);
+  }
+  if (opt_color) {
+    cudaMemsetAsync(c->intr_H, 0, sizeof(float) * 10, s);
+    cudaMemsetAsync(c->intr_b, 0, sizeof(float) * 4, s);
+  }
+  const PixelCenterUnprojector unproj = CenterUnprojector(c->cfg.depth_K);
+  for (const RefKeyframe& kf : c->kfs) {
+    CallAccumulateIntrinsicsCoefficientsCUDAKernel(s, opt_color, opt_depth,
+                                                   MakeProjection(c, kf, MakeFrameTGlobal(kf.pose), c->surfels_size),
+                                                   DepthToColor(c->cfg), CornerProjector(c->cfg.color_K), unproj,
+                                                   c->cfg.color_K[0], c->cfg.color_K[1], kf.tex, obs, A, B, D, b1, b2, H, b);
+    ++c->launches;
+  }
+  if (opt_depth) {
+    CallComputeIntrinsicsIntermediateMatricesCUDAKernel(s, P, A, B, D, b1, b2);
+    ++c->launches;
+    float A_cpu[15], rhs[kARows];
+    cudaMemcpyAsync(A_cpu, c->intr_A, sizeof(A_cpu), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(rhs, c->intr_b1, sizeof(rhs), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    constexpr float kAPriorWeight = 10;
+    A_cpu[14] += kAPriorWeight * kAPriorWeight;
+    rhs[4] += kAPriorWeight * kAPriorWeight * c->a;
+    double Ad[kARows * kARows] = {0}, bd[kARows], xd[kARows];   // hm_ldlt_solve reads the upper triangle of a full matrix
+    for (int r = 0, i = 0; r < kARows; ++r)
+      for (int col = r; col < kARows; ++col) Ad[r * kARows + col] = A_cpu[i++];
+    for (int i = 0; i < kARows; ++i) bd[i] = rhs[i];
+    hm_ldlt_solve(kARows, Ad, bd, xd);
+    float x1[kARows];
+    for (int i = 0; i < kARows; ++i) x1[i] = static_cast<float>(xd[i]);
+    const float new_fx = 1.0f / (unproj.fx_inv - x1[0]);
+    const float new_fy = 1.0f / (unproj.fy_inv - x1[1]);
+    const float new_cx = -(new_fx * (unproj.cx_inv - x1[2])) + 0.5f;
+    const float new_cy = -(new_fy * (unproj.cy_inv - x1[3])) + 0.5f;
+    cudaMemcpyAsync(c->intr_b1, x1, sizeof(x1), cudaMemcpyHostToDevice, s);
+    CallSolveForPixelIntrinsicsUpdateCUDAKernel(s, P, obs, B, D, b1,
+                                                CUDABuffer_<float>(c->cfactor, c->cf_h, c->cf_w, c->cfactor_pitch));
+    ++c->launches;
+    cudaStreamSynchronize(s);
+    c->cfg.depth_K[0] = new_fx; c->cfg.depth_K[1] = new_fy; c->cfg.depth_K[2] = new_cx; c->cfg.depth_K[3] = new_cy;
+    c->a -= x1[4];
+  }
+  if (opt_color) {   // kernel_opt_intrinsics.cc:256-280 (system accumulated above, before any update)
+    float H_cpu[10], rhs4[4];
+    cudaMemcpyAsync(H_cpu, c->intr_H, sizeof(H_cpu), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(rhs4, c->intr_b, sizeof(rhs4), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    double Hd[16] = {0}, b4[4], x4[4];
+    for (int r = 0, i = 0; r < 4; ++r)
+      for (int col = r; col < 4; ++col) Hd[r * 4 + col] = H_cpu[i++];
+    for (int i = 0; i < 4; ++i) b4[i] = rhs4[i];
+    hm_ldlt_solve(4, Hd, b4, x4);
+    for (int i = 0; i < 4; ++i) c->cfg.color_K[i] -= static_cast<float>(x4[i]);
+  }
+}
+
 void DetermineCovisibleActive(ref_context* c) {   // direct_ba.cc:549-564
   for (RefKeyframe& kf : c->kfs) {
     if (kf.activation != 0) continue;
@@ -408,6 +496,16 @@ int ref_estimate_frame_pose(ref_context* c, int k, const float init[7], float ou
   return EstimateFramePose(c, k, init, out, converged, false, nullptr, nullptr);
 }
 
+void ref_optimize_intrinsics(ref_context* c, int opt_depth, int opt_color) { OptimizeIntrinsics(c, opt_depth != 0, opt_color != 0); }
+void ref_get_intrinsics(ref_context* c, float depth_K[4], float color_K[4], float* a) {
+  std::memcpy(depth_K, c->cfg.depth_K, sizeof(float) * 4);
+  std::memcpy(color_K, c->cfg.color_K, sizeof(float) * 4);
+  *a = c->a;
+}
+void ref_get_cfactor(ref_context* c, float* cfactor_dense) {
+  cudaMemcpy2D(cfactor_dense, c->cf_w * sizeof(float), c->cfactor, c->cfactor_pitch, c->cf_w * sizeof(float), c->cf_h,
+               cudaMemcpyDeviceToHost);
+}
 void ref_update_activation(ref_context* c) { UpdateSurfelActivation(c); cudaStreamSynchronize(c->stream); }
 void ref_optimize_geometry_iteration(ref_context* c) { OptimizeGeometryIteration(c); cudaStreamSynchronize(c->stream); }
 
@@ -459,6 +557,11 @@ void ref_bundle_adjust(ref_context* c, const ref_ba_options* o, ref_ba_result* r
       }
     }
     cudaEventRecord(c->ev[3], s);
+    {   // direct_ba_alternating.cc:584-624 (flags gated like direct_ba.cc:427-434)
+      const bool od = o->optimize_depth_intrinsics && c->cfg.use_depth_residuals;
+      const bool oc = o->optimize_color_intrinsics && c->cfg.use_descriptor_residuals;
+      if (od || oc) OptimizeIntrinsics(c, od, oc);
+    }
     cudaEventSynchronize(c->ev[3]);
     cudaEventElapsedTime(&res->ms_surfel_activation, c->ev[0], c->ev[1]);
     cudaEventElapsedTime(&res->ms_geometry_optimization, c->ev[1], c->ev[2]);

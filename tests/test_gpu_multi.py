@@ -62,3 +62,53 @@ def test_two_rank_bundle_adjustment_matches_single_gpu(tmp_path):
         dt, dr = pose_error(r0["poses"][k], poses[k])
         assert dt < 1e-5 and dr < 1e-5
     assert np.mean(np.abs(r0["surfels"][:3] - surf[:3])) < 1e-6
+
+
+def _distorted_small():
+    import dataclasses
+    from badslam_b200.scene import config_by_name, make_scene
+    sc = make_scene(dataclasses.replace(config_by_name("small"), depth_a=0.03, cfactor=0.005))
+    sc.depth_K = (np.asarray(sc.depth_K, np.float32) * np.float32([1.003, 0.998, 1.002, 0.997])).astype(np.float32)
+    sc.color_K = (np.asarray(sc.color_K, np.float32) * np.float32([0.998, 1.002, 1.001, 0.999])).astype(np.float32)
+    return sc
+
+
+def _intrinsics_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from badslam_b200.direct_ba import DirectBA
+    ba = DirectBA.from_scene(_distorted_small(), device=f"cuda:{rank}", rank=rank, world_size=world)
+    ba.SetCollective()
+    ba.OptimizeIntrinsics(True, True)
+    d, c, a = ba._intrinsics()
+    step = dict(d=d, c=c, a=np.float32(a), cf=ba.cfactor_buffer())
+    ba.BundleAdjustment(None, True, True, False, True, True, 2, 2)
+    d2, c2, a2 = ba._intrinsics()
+    np.savez(os.path.join(out_dir, f"intr{rank}.npz"), d2=d2, c2=c2, a2=np.float32(a2), cf2=ba.cfactor_buffer(),
+             poses=ba.GetKeyframeStates()[0], **step)
+    dist.barrier(device_ids=[rank])
+    dist.destroy_process_group()
+
+
+def test_two_rank_intrinsics_step_matches_single_gpu(tmp_path):
+    """Surfel-sharded intrinsics accumulation + one sum all-reduce: replicas bit-identical, equal to one GPU up to fp32 sums."""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from badslam_b200.direct_ba import DirectBA
+    mp.spawn(_intrinsics_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    ba = DirectBA.from_scene(_distorted_small(), device="cuda:0")
+    ba.OptimizeIntrinsics(True, True)
+    d, c, a = ba._intrinsics()
+    cf = ba.cfactor_buffer()
+    r0, r1 = np.load(tmp_path / "intr0.npz"), np.load(tmp_path / "intr1.npz")
+    for key in ("d", "c", "a", "cf", "d2", "c2", "a2", "cf2", "poses"):
+        assert np.array_equal(r0[key].view(np.uint32), r1[key].view(np.uint32)), key
+    # the all-reduce sums fp32 partials: agreement with the single-GPU fp64 accumulation at the fp32 level
+    assert np.abs(r0["d"] - d).max() < 2e-3 and np.abs(r0["c"] - c).max() < 2e-3 and abs(float(r0["a"]) - a) < 1e-5
+    assert np.abs(r0["cf"] - cf).max() < 1e-4
