@@ -30,7 +30,8 @@ class BAOptions(C.Structure):
                 ("do_surfel_updates", C.c_int), ("optimize_poses", C.c_int), ("optimize_geometry", C.c_int),
                 ("min_iterations", C.c_int), ("max_iterations", C.c_int), ("use_pcg", C.c_int),
                 ("active_keyframe_window_start", C.c_int), ("active_keyframe_window_end", C.c_int),
-                ("increase_ba_iteration_count", C.c_int), ("time_limit_seconds", C.c_double)]
+                ("increase_ba_iteration_count", C.c_int), ("time_limit_seconds", C.c_double),
+                ("pcg_max_inner_iterations", C.c_int), ("pcg_max_keyframes", C.c_int), ("pcg_gauge_keyframe", C.c_int)]
 
 
 class BAResult(C.Structure):
@@ -39,7 +40,8 @@ class BAResult(C.Structure):
                 ("pose_iterations_total", C.c_int),
                 ("ms_surfel_activation", C.c_float), ("ms_geometry_optimization", C.c_float),
                 ("ms_pose_optimization", C.c_float), ("ms_intrinsics_optimization", C.c_float),
-                ("kernel_launches", C.c_uint64)]
+                ("kernel_launches", C.c_uint64),
+                ("pcg_inner_iterations_total", C.c_int), ("pcg_last_r_norm", C.c_float), ("ms_pcg", C.c_float)]
 
 
 class PoseCoeffs(C.Structure):
@@ -95,6 +97,7 @@ SYMBOLS = {
     "bba_update_surfel_activation": (C.c_int, [_P, _P]),
     "bba_optimize_geometry_iteration": (C.c_int, [_P, _P]),
     "bba_optimize_intrinsics": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "bba_pcg_debug": (C.c_int, [_P, C.POINTER(BAOptions), C.POINTER(C.c_uint32), _P, _P, _P, _P, _P, _P]),
     "bba_bundle_adjust": (C.c_int, [_P, C.POINTER(BAOptions), C.POINTER(BAResult), _P]),
     "bba_set_collective": (C.c_int, [_P, COLLECTIVE_FN, _P]),
     "bba_shard_surfel_range": (None, [C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
@@ -121,7 +124,7 @@ def load():
         fn = getattr(lib, name)   # AttributeError if the symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.bba_abi_version() != 1:
+    if lib.bba_abi_version() != 2:
         raise ImportError("libbadba_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -21,6 +21,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 UNITS = [
     ("kernels.cu", ["-use_fast_math", "-Xptxas", "-v"]),
     ("intrinsics.cu", ["-use_fast_math", "-Xptxas", "-v"]),
+    ("pcg.cu", ["-use_fast_math", "-Xptxas", "-v"]),
     ("pose_solve.cu", []),
     ("badba.cu", []),
 ]

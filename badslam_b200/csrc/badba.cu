@@ -206,6 +206,13 @@ struct bba_context {
   double* h_intr_sums = nullptr;      // pinned
   float* h_intr_x1 = nullptr;         // pinned, 8 floats
 
+  // PCG solver (lazily allocated): r, M, delta, g, p with pcg_capacity floats each
+  float* d_pcg[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t pcg_capacity = 0;
+  double* d_pcg_scalars = nullptr;    // [0] / [2] alpha_n, beta_n (roles swap), [1] alpha_d
+  double* h_pcg_scalars = nullptr;    // pinned copy
+  float* h_pcg_delta = nullptr;       // pinned: pose part (6 * max_keyframes) + 16
+
   uint64_t launches = 0;
   int ba_iteration_count = 0;
 
@@ -624,6 +631,223 @@ bba_status OptimizeIntrinsics(bba_handle h, bool opt_depth, bool opt_color, cuda
   return BBA_OK;
 }
 
+// Unknown layout of the PCG solver (direct_ba_pcg.cc:273-309) + the vectors sized for it.
+struct PcgLayout {
+  bool opt_poses, opt_geometry, opt_depth_intr, opt_color_intr, use_desc;
+  uint32_t surfel_start, stride, depth_start, a_index, color_start, unknown_count;
+};
+
+bba_status MakePcgLayout(bba_handle h, const bba_ba_options* o, PcgLayout* L) {
+  constexpr uint32_t kInvalid = 0xffffffffu;
+  const int K = static_cast<int>(h->keyframes.size());
+  const uint32_t N = h->surfels_size, P = static_cast<uint32_t>(h->cf_w) * h->cf_h;
+  L->opt_depth_intr = o->optimize_depth_intrinsics && h->cfg.use_depth_residuals;   // direct_ba.cc:427-434
+  L->opt_color_intr = o->optimize_color_intrinsics && h->cfg.use_descriptor_residuals;
+  L->opt_poses = o->optimize_poses != 0;
+  L->opt_geometry = o->optimize_geometry != 0;
+  L->use_desc = h->cfg.use_descriptor_residuals != 0;
+  L->stride = L->use_desc ? 3u : 1u;
+  uint32_t cur = 0;
+  if (L->opt_poses) cur += 6u * static_cast<uint32_t>(K - 1);
+  L->surfel_start = L->depth_start = L->a_index = L->color_start = kInvalid;
+  if (L->opt_geometry) { L->surfel_start = cur; cur += L->stride * N; }
+  if (L->opt_depth_intr) { L->depth_start = cur; cur += 5u + P; L->a_index = L->depth_start + 4u; }
+  if (L->opt_color_intr) { L->color_start = cur; cur += 4u; }
+  L->unknown_count = cur;
+  if (!h->d_pcg_scalars) {
+    BBA_CUDA(h, cudaMalloc(&h->d_pcg_scalars, sizeof(double) * 4));
+    BBA_CUDA(h, cudaMallocHost(&h->h_pcg_scalars, sizeof(double) * 4));
+    BBA_CUDA(h, cudaMallocHost(&h->h_pcg_delta, sizeof(float) * (6 * static_cast<size_t>(h->cfg.max_keyframes) + 16)));
+  }
+  if (L->unknown_count > h->pcg_capacity) {
+    const size_t cap = std::max<size_t>(L->unknown_count, 6 * static_cast<size_t>(h->cfg.max_keyframes) +
+                                                              3 * static_cast<size_t>(std::max(h->cfg.max_surfel_count, N)) + 9 + P);
+    for (float*& v : h->d_pcg) {
+      cudaFree(v);
+      v = nullptr;
+      BBA_CUDA(h, cudaMalloc(&v, sizeof(float) * cap));
+    }
+    h->pcg_capacity = cap;
+  }
+  return BBA_OK;
+}
+
+bba::PcgArgs MakePcgArgs(bba_handle h, const PcgLayout& L, int gauge) {
+  bba::PcgArgs a;
+  a.cam = MakeCamera(h);
+  a.surfels = h->surfels;
+  a.pitch = static_cast<uint32_t>(h->surfel_pitch_bytes / sizeof(float));
+  a.begin = 0;
+  a.end = h->surfels_size;
+  a.kfs = h->d_kfs;
+  a.kf_count = static_cast<int>(h->keyframes.size());
+  a.gauge_kf = gauge;
+  a.opt_poses = L.opt_poses;
+  a.opt_geometry = L.opt_geometry;
+  a.opt_depth_intr = L.opt_depth_intr;
+  a.opt_color_intr = L.opt_color_intr;
+  a.surfel_start = L.surfel_start;
+  a.surfel_stride = L.stride;
+  a.depth_intr_start = L.depth_start;
+  a.color_intr_start = L.color_start;
+  a.r = h->d_pcg[0];
+  a.M = h->d_pcg[1];
+  a.p = h->d_pcg[4];
+  a.g = h->d_pcg[3];
+  a.scalars = h->d_pcg_scalars;
+  a.queue = h->d_geo_queue;
+  return a;
+}
+
+// DirectBA::BundleAdjustmentPCG (direct_ba_pcg.cc:43-819) without the surfel lifecycle branches.
+bba_status BundleAdjustPCG(bba_handle h, const bba_ba_options* o, bba_ba_result* res, cudaStream_t s) {
+  const int K = static_cast<int>(h->keyframes.size());
+  if (h->cfg.world_size > 1) return Fail(h, BBA_ERR_UNSUPPORTED, "use_pcg is single-GPU only");
+  if (K == 0) return Fail(h, BBA_ERR_STATE, "use_pcg: no keyframes");
+  const int max_inner = o->pcg_max_inner_iterations > 0 ? o->pcg_max_inner_iterations : 30;
+  const int max_keyframes = o->pcg_max_keyframes > 0 ? o->pcg_max_keyframes : 2500;
+  if (K > max_keyframes) return Fail(h, BBA_ERR_INVALID_ARGUMENT, "use_pcg: more keyframes than pcg_max_keyframes");   // :232
+  if (o->pcg_gauge_keyframe >= K) return Fail(h, BBA_ERR_INVALID_ARGUMENT, "pcg_gauge_keyframe out of range");
+  PcgLayout L;
+  if (bba_status st = MakePcgLayout(h, o, &L)) return st;
+  const bool opt_depth_intr = L.opt_depth_intr, opt_color_intr = L.opt_color_intr, opt_poses = L.opt_poses, opt_geometry = L.opt_geometry;
+  const bool use_desc = L.use_desc;
+  const uint32_t N = h->surfels_size;
+  const uint32_t P = static_cast<uint32_t>(h->cf_w) * h->cf_h;
+  const uint64_t launches_before = h->launches;
+  const auto t_start = std::chrono::steady_clock::now();
+
+  for (int iteration = 0; iteration < o->max_iterations; ++iteration) {
+    ++res->iterations_done;
+    if (N > 0) BBA_CUDA(h, cudaMemsetAsync(h->active, bba::kSurfelActiveFlag, N, s));   // :209-212
+    if (bba_status st = UploadKeyframes(h, s)) return st;
+    BBA_CUDA(h, cudaEventRecord(h->ev[0], s));
+    if (opt_geometry && N > 0) {   // UpdateSurfelNormalsCUDA, :215-227
+      bba::GeometryArgs g;
+      if (bba_status st = BuildGeometryArgs(h, &g, s)) return st;
+      bba::LaunchActivationAndNormals(g, h->sm_count, false, true, s);
+      ++h->launches;
+    }
+    BBA_CUDA(h, cudaEventRecord(h->ev[1], s));
+
+    if (bba_status st = MakePcgLayout(h, o, &L)) return st;   // unknown layout (:273-309)
+    const uint32_t surfel_start = L.surfel_start, depth_start = L.depth_start, a_index = L.a_index, color_start = L.color_start;
+    const uint32_t unknown_count = L.unknown_count;
+    float *pcg_r = h->d_pcg[0], *pcg_M = h->d_pcg[1], *pcg_delta = h->d_pcg[2], *pcg_g = h->d_pcg[3], *pcg_p = h->d_pcg[4];
+    const int gauge = o->pcg_gauge_keyframe >= 0 ? o->pcg_gauge_keyframe : (rand() % K);   // :324
+
+    int num_converged = 0;
+    if (unknown_count > 0) {
+      BBA_CUDA(h, cudaMemsetAsync(pcg_r, 0, sizeof(float) * unknown_count, s));   // :312-313
+      BBA_CUDA(h, cudaMemsetAsync(pcg_M, 0, sizeof(float) * unknown_count, s));
+      BBA_CUDA(h, cudaMemsetAsync(h->d_pcg_scalars, 0, sizeof(double) * 4, s));
+      const bba::PcgArgs a = MakePcgArgs(h, L, gauge);
+      bba::LaunchPcgAccumulate(a, h->sm_count, true, s);   // PCGInitCUDA for every keyframe, :336-361
+      int an = 0, bn = 2;
+      bba::LaunchPcgInit2(unknown_count, a_index, h->depth_a, K, pcg_r, pcg_M, pcg_delta, pcg_g, pcg_p, h->d_pcg_scalars, an,
+                          h->sm_count, s);   // :363-373
+      h->launches += 2;
+      float prev_r_norm = std::numeric_limits<float>::infinity();
+      int without_improvement = 0;
+      for (int step = 0; step < max_inner; ++step) {
+        if (step > 0) std::swap(an, bn);   // alpha_n <- beta_n (:386); g was cleared and alpha_d re-armed by PcgStep3Kernel
+        bba::LaunchPcgAccumulate(a, h->sm_count, false, s);   // PCGStep1CUDA for every keyframe, :392-419
+        BBA_CUDA(h, cudaMemsetAsync(h->d_pcg_scalars + bn, 0, sizeof(double), s));
+        bba::LaunchPcgStep2(unknown_count, a_index, pcg_r, pcg_M, pcg_delta, pcg_g, pcg_p, h->d_pcg_scalars, an, bn, h->sm_count, s);
+        h->launches += 2;
+        BBA_CUDA(h, cudaGetLastError());
+        BBA_CUDA(h, cudaMemcpyAsync(h->h_pcg_scalars, h->d_pcg_scalars, sizeof(double) * 4, cudaMemcpyDeviceToHost, s));
+        BBA_CUDA(h, cudaStreamSynchronize(s));   // :436-437
+        ++res->pcg_inner_iterations_total;
+        const float r_norm = std::sqrt(static_cast<float>(h->h_pcg_scalars[bn]));
+        res->pcg_last_r_norm = r_norm;
+        if (static_cast<double>(r_norm) < static_cast<double>(prev_r_norm) - 1e-3) {   // :442-449
+          without_improvement = 0;
+        } else if (++without_improvement >= 3) {
+          break;
+        }
+        prev_r_norm = r_norm;
+        if (step < max_inner - 1) {   // :456-464
+          BBA_CUDA(h, cudaMemsetAsync(h->d_pcg_scalars + 1, 0, sizeof(double), s));
+          bba::LaunchPcgStep3(unknown_count, a_index, K, pcg_g, pcg_p, h->d_pcg_scalars, an, bn, h->sm_count, s);
+          ++h->launches;
+        }
+      }
+      BBA_CUDA(h, cudaEventRecord(h->ev[2], s));
+
+      // --- apply pcg_delta (:552-638)
+      size_t n_host = 0;
+      const size_t pose_floats = opt_poses ? 6 * static_cast<size_t>(K - 1) : 0;
+      if (pose_floats) BBA_CUDA(h, cudaMemcpyAsync(h->h_pcg_delta, pcg_delta, sizeof(float) * pose_floats, cudaMemcpyDeviceToHost, s));
+      n_host = pose_floats;
+      float* h_di = h->h_pcg_delta + n_host;
+      if (opt_depth_intr) {
+        BBA_CUDA(h, cudaMemcpyAsync(h_di, pcg_delta + depth_start, sizeof(float) * 5, cudaMemcpyDeviceToHost, s));
+        n_host += 5;
+      }
+      float* h_ci = h->h_pcg_delta + n_host;
+      if (opt_color_intr) BBA_CUDA(h, cudaMemcpyAsync(h_ci, pcg_delta + color_start, sizeof(float) * 4, cudaMemcpyDeviceToHost, s));
+      if (opt_geometry && N > 0) {
+        bba::LaunchPcgUpdateSurfels(h->surfels, a.pitch, N, use_desc, surfel_start, pcg_delta, s);
+        ++h->launches;
+      }
+      if (opt_depth_intr) {
+        bba::LaunchPcgUpdateCfactor(h->d_cfactor, P, pcg_delta + depth_start + 5, s);
+        ++h->launches;
+      }
+      BBA_CUDA(h, cudaGetLastError());
+      BBA_CUDA(h, cudaStreamSynchronize(s));
+      if (opt_poses) {
+        for (int k = 0; k < K; ++k) {
+          if (k == gauge) {
+            ++num_converged;
+            continue;
+          }
+          const float* d6 = h->h_pcg_delta + 6 * static_cast<size_t>(k < gauge ? k : k - 1);
+          const Pose delta = bba::Exp(d6);
+          h->keyframes[k].pose = bba::Compose(h->keyframes[k].pose, delta);   // :569-570
+          float lg[6];
+          bba::Log(delta, lg);
+          if (bba::IsScale1PoseEstimationConverged(lg)) ++num_converged;
+        }
+      }
+      if (opt_depth_intr) {   // :590-612
+        const double old_fx_inv = 1. / h->depth_K[0], old_fy_inv = 1. / h->depth_K[1];
+        const double old_cx_inv = -(h->depth_K[2] - 0.5) * old_fx_inv, old_cy_inv = -(h->depth_K[3] - 0.5) * old_fy_inv;
+        const double new_fx = 1. / (old_fx_inv + h_di[0]);
+        const double new_fy = 1. / (old_fy_inv + h_di[1]);
+        const double new_cx = -(new_fx * (old_cx_inv + h_di[2])) + 0.5;
+        const double new_cy = -(new_fy * (old_cy_inv + h_di[3])) + 0.5;
+        h->depth_K[0] = static_cast<float>(new_fx);
+        h->depth_K[1] = static_cast<float>(new_fy);
+        h->depth_K[2] = static_cast<float>(new_cx);
+        h->depth_K[3] = static_cast<float>(new_cy);
+        h->depth_a += h_di[4];
+      }
+      if (opt_color_intr)   // :623-638
+        for (int c = 0; c < 4; ++c) h->color_K[c] = static_cast<float>(h->color_K[c] + h_ci[c]);
+    } else {
+      BBA_CUDA(h, cudaEventRecord(h->ev[2], s));
+      BBA_CUDA(h, cudaStreamSynchronize(s));
+      num_converged = opt_poses ? 1 : 0;
+    }
+    cudaEventElapsedTime(&res->ms_geometry_optimization, h->ev[0], h->ev[1]);   // "BA normals update", :722-727
+    cudaEventElapsedTime(&res->ms_pcg, h->ev[1], h->ev[2]);
+
+    if (iteration >= o->min_iterations - 1 && (num_converged == K || !opt_poses)) {   // :757-766
+      res->converged = 1;
+      break;
+    }
+    if (o->time_limit_seconds > 0) {
+      const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+      if (el > o->time_limit_seconds) break;
+    }
+  }
+  if (o->increase_ba_iteration_count) ++h->ba_iteration_count;
+  res->kernel_launches = h->launches - launches_before;
+  return BBA_OK;
+}
+
 bba_status AddKeyframeCommon(bba_handle h, Keyframe&& kf, const uint8_t* device_rgba, size_t color_pitch, const float pose[7],
                              float min_depth, float max_depth, cudaStream_t s, int* out_id) {
   if (static_cast<int>(h->keyframes.size()) >= h->cfg.max_keyframes) return Fail(h, BBA_ERR_STATE, "max_keyframes exceeded");
@@ -801,6 +1025,10 @@ void bba_destroy(bba_handle h) {
   cudaFree(h->d_all_list);
   cudaFreeHost(h->h_intr_sums);
   cudaFreeHost(h->h_intr_x1);
+  for (float* v : h->d_pcg) cudaFree(v);
+  cudaFree(h->d_pcg_scalars);
+  cudaFreeHost(h->h_pcg_scalars);
+  cudaFreeHost(h->h_pcg_delta);
   if (h->h_flag) cudaFreeHost(const_cast<int*>(h->h_flag));
   cudaFreeHost(h->h_totals);
   for (auto& e : h->prof_ev)
@@ -1132,8 +1360,8 @@ bba_status bba_bundle_adjust(bba_handle h, const bba_ba_options* o, bba_ba_resul
   if (!h || !o || !res) return BBA_ERR_INVALID_ARGUMENT;
   std::memset(res, 0, sizeof(*res));
   if (bba_status st = CheckSurfels(h)) return st;
-  if (o->use_pcg) return Fail(h, BBA_ERR_UNSUPPORTED, "use_pcg: the PCG solver (direct_ba_pcg.cc) is not implemented");
   if (o->do_surfel_updates) return Fail(h, BBA_ERR_UNSUPPORTED, "do_surfel_updates: surfel creation/merge/deletion is not implemented");
+  if (o->use_pcg) return BundleAdjustPCG(h, o, res, static_cast<cudaStream_t>(stream));   // direct_ba.cc:436-457
   // direct_ba.cc:427-434
   const bool opt_depth_intr = o->optimize_depth_intrinsics && h->cfg.use_depth_residuals;
   const bool opt_color_intr = o->optimize_color_intrinsics && h->cfg.use_descriptor_residuals;
@@ -1254,6 +1482,41 @@ bba_status bba_bundle_adjust(bba_handle h, const bba_ba_options* o, bba_ba_resul
   if (o->increase_ba_iteration_count) ++h->ba_iteration_count;
   res->kernel_launches = h->launches - launches_before;
   return BBA_OK;
+}
+
+bba_status bba_pcg_debug(bba_handle h, const bba_ba_options* o, uint32_t* unknown_count, float* out_r, float* out_M, float* out_p,
+                         float* out_g, double out_scalars[2], void* stream) {
+  if (!h || !o || !unknown_count) return BBA_ERR_INVALID_ARGUMENT;
+  if (bba_status st = CheckSurfels(h)) return st;
+  const int K = static_cast<int>(h->keyframes.size());
+  if (K == 0) return Fail(h, BBA_ERR_STATE, "no keyframes");
+  if (o->pcg_gauge_keyframe < 0 || o->pcg_gauge_keyframe >= K) return Fail(h, BBA_ERR_INVALID_ARGUMENT, "pcg_gauge_keyframe out of range");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PcgLayout L;
+  if (bba_status st = MakePcgLayout(h, o, &L)) return st;
+  *unknown_count = L.unknown_count;
+  if (!out_r || L.unknown_count == 0) return BBA_OK;
+  const uint32_t U = L.unknown_count;
+  if (bba_status st = UploadKeyframes(h, s)) return st;
+  BBA_CUDA(h, cudaMemsetAsync(h->d_pcg[0], 0, sizeof(float) * U, s));
+  BBA_CUDA(h, cudaMemsetAsync(h->d_pcg[1], 0, sizeof(float) * U, s));
+  BBA_CUDA(h, cudaMemsetAsync(h->d_pcg_scalars, 0, sizeof(double) * 4, s));
+  const bba::PcgArgs a = MakePcgArgs(h, L, o->pcg_gauge_keyframe);
+  bba::LaunchPcgAccumulate(a, h->sm_count, true, s);
+  BBA_CUDA(h, cudaMemcpyAsync(out_r, h->d_pcg[0], sizeof(float) * U, cudaMemcpyDeviceToHost, s));
+  BBA_CUDA(h, cudaMemcpyAsync(out_M, h->d_pcg[1], sizeof(float) * U, cudaMemcpyDeviceToHost, s));
+  bba::LaunchPcgInit2(U, L.a_index, h->depth_a, K, h->d_pcg[0], h->d_pcg[1], h->d_pcg[2], h->d_pcg[3], h->d_pcg[4], h->d_pcg_scalars, 0,
+                      h->sm_count, s);
+  BBA_CUDA(h, cudaMemcpyAsync(out_p, h->d_pcg[4], sizeof(float) * U, cudaMemcpyDeviceToHost, s));
+  bba::LaunchPcgAccumulate(a, h->sm_count, false, s);
+  h->launches += 3;
+  BBA_CUDA(h, cudaGetLastError());
+  BBA_CUDA(h, cudaMemcpyAsync(out_g, h->d_pcg[3], sizeof(float) * U, cudaMemcpyDeviceToHost, s));
+  BBA_CUDA(h, cudaMemcpyAsync(h->h_pcg_scalars, h->d_pcg_scalars, sizeof(double) * 4, cudaMemcpyDeviceToHost, s));
+  BBA_CUDA(h, cudaStreamSynchronize(s));
+  out_scalars[0] = h->h_pcg_scalars[0];
+  out_scalars[1] = h->h_pcg_scalars[1];
+  return MarkStaging(h, s);
 }
 
 bba_status bba_set_collective(bba_handle h, bba_collective_fn fn, void* user) {

@@ -286,4 +286,17 @@ __device__ __forceinline__ void EvalDescriptor(cudaTextureObject_t tex, float cx
   e->gy2 = 180.f * (t2dy - cdy);
 }
 
+// kernel_opt_pose.cu:96-142: Jacobian of a descriptor residual wrt the pose (global_T_frame * exp(hat(delta))).
+__device__ __forceinline__ void DescPoseJacobian(const CameraParams& cam, const Vec3& ls, float gx, float gy, float (&J)[6]) {
+  gx *= cam.cfx;
+  gy *= cam.cfy;
+  const float inv_z = 1.f / ls.z, z_sq = ls.z * ls.z, inv_z_sq = inv_z * inv_z, xy = ls.x * ls.y;
+  J[0] = -gx * inv_z;
+  J[1] = -gy * inv_z;
+  J[2] = (ls.x * gx + ls.y * gy) * inv_z_sq;
+  J[3] = ((ls.y * ls.y + z_sq) * gy + xy * gx) * inv_z_sq;
+  J[4] = -((ls.x * ls.x + z_sq) * gx + xy * gy) * inv_z_sq;
+  J[5] = -(ls.x * gy - ls.y * gx) * inv_z;
+}
+
 }  // namespace bba

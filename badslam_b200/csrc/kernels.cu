@@ -80,19 +80,6 @@ __device__ __forceinline__ void LoadKf(const KfDevice* __restrict__ kfs, int kf,
   r->activation = __ldg(reinterpret_cast<const int*>(p + 5));
 }
 
-// kernel_opt_pose.cu:96-142: Jacobian of a descriptor residual wrt the pose (global_T_frame * exp(hat(delta))).
-__device__ __forceinline__ void DescPoseJacobian(const CameraParams& cam, const Vec3& ls, float gx, float gy, float (&J)[6]) {
-  gx *= cam.cfx;
-  gy *= cam.cfy;
-  const float inv_z = 1.f / ls.z, z_sq = ls.z * ls.z, inv_z_sq = inv_z * inv_z, xy = ls.x * ls.y;
-  J[0] = -gx * inv_z;
-  J[1] = -gy * inv_z;
-  J[2] = (ls.x * gx + ls.y * gy) * inv_z_sq;
-  J[3] = ((ls.y * ls.y + z_sq) * gy + xy * gx) * inv_z_sq;
-  J[4] = -((ls.x * ls.x + z_sq) * gx + xy * gy) * inv_z_sq;
-  J[5] = -(ls.x * gy - ls.y * gx) * inv_z;
-}
-
 // H += w J^T J (upper triangle, row-major), b += w r J   (gauss_newton.cuh:59-92, per thread)
 __device__ __forceinline__ void AccumulateHb(float (&acc)[kPoseAccSize], const float (&J)[6], float raw, float w) {
   int idx = 0;

@@ -108,6 +108,36 @@ void LaunchIntrinsicsConvertSums(double* sums, float* head, bool to_float, cudaS
 void LaunchIntrinsicsCellUpdate(uint32_t cell_count, const float* obs, const float* B, const float* D, const float* x1,
                                 float* cfactor, cudaStream_t stream);
 
+// PCG Gauss-Newton step over all unknowns (pcg.cu; BundleAdjustmentPCG, direct_ba_pcg.cc:43-819).
+struct PcgArgs {
+  CameraParams cam;
+  const float* surfels;
+  uint32_t pitch;
+  uint32_t begin, end;         // surfel range processed by this rank
+  const KfDevice* kfs;         // every keyframe, ids 0 .. kf_count-1
+  int kf_count;
+  int gauge_kf;                // keyframe whose pose is fixed (no unknowns), direct_ba_pcg.cc:315-333
+  int opt_poses, opt_geometry, opt_depth_intr, opt_color_intr;
+  uint32_t surfel_start, surfel_stride;   // first surfel unknown, unknowns per surfel (1 or 3)
+  uint32_t depth_intr_start, color_intr_start;
+  float* r;                    // INIT
+  float* M;                    // INIT
+  const float* p;              // STEP1
+  float* g;                    // STEP1
+  double* scalars;             // [0] / [2] alpha_n, beta_n (swapping roles), [1] alpha_d
+  unsigned int* queue;         // work-item counter (reset by the launcher)
+};
+void LaunchPcgAccumulate(const PcgArgs& a, int sm_count, bool init, cudaStream_t stream);
+void LaunchPcgInit2(uint32_t n, uint32_t a_index, float a, int kf_count, const float* r, const float* M, float* delta, float* g, float* p,
+                    double* scalars, int slot_alpha_n, int sm_count, cudaStream_t stream);
+void LaunchPcgStep2(uint32_t n, uint32_t a_index, float* r, const float* M, float* delta, float* g, const float* p, double* scalars,
+                    int slot_alpha_n, int slot_beta_n, int sm_count, cudaStream_t stream);
+void LaunchPcgStep3(uint32_t n, uint32_t a_index, int kf_count, float* g, float* p, double* scalars, int slot_alpha_n, int slot_beta_n,
+                    int sm_count, cudaStream_t stream);
+void LaunchPcgUpdateSurfels(float* surfels, uint32_t pitch, uint32_t n, bool use_desc, uint32_t surfel_start, const float* delta,
+                            cudaStream_t stream);
+void LaunchPcgUpdateCfactor(float* cfactor, uint32_t cells, const float* delta, cudaStream_t stream);
+
 // uchar4 (.w = luma) -> u8 plane.
 void LaunchExtractLuma(const uint8_t* rgba, size_t rgba_pitch, uint8_t* luma, size_t luma_pitch, int w, int h, cudaStream_t stream);
 

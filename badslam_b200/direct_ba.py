@@ -89,6 +89,9 @@ class BAResult:
     ms_pose_optimization: float
     ms_intrinsics_optimization: float
     kernel_launches: int
+    pcg_inner_iterations_total: int = 0
+    pcg_last_r_norm: float = 0.0
+    ms_pcg: float = 0.0
 
     @property
     def residual_count(self):
@@ -354,19 +357,38 @@ class DirectBA:
                          do_surfel_updates: bool, optimize_poses: bool, optimize_geometry: bool,
                          min_iterations: int, max_iterations: int, use_pcg: bool = False,
                          active_keyframe_window_start: int = 0, active_keyframe_window_end: int = -1,
-                         increase_ba_iteration_count: bool = True, time_limit: float = 0.0) -> BAResult:
-        """direct_ba.h:143-162."""
+                         increase_ba_iteration_count: bool = True, time_limit: float = 0.0,
+                         pcg_max_inner_iterations: int = 30, pcg_max_keyframes: int = 2500,
+                         pcg_gauge_keyframe: int = -1) -> BAResult:
+        """direct_ba.h:143-162.  pcg_gauge_keyframe >= 0 pins the keyframe the PCG solver holds fixed (the reference draws
+        rand() % K in every iteration, direct_ba_pcg.cc:324)."""
         if active_keyframe_window_end < 0:
             active_keyframe_window_end = len(self._keyframes) - 1
         o = _lib.BAOptions(int(optimize_depth_intrinsics), int(optimize_color_intrinsics), int(do_surfel_updates),
                            int(optimize_poses), int(optimize_geometry), int(min_iterations), int(max_iterations),
                            int(use_pcg), int(active_keyframe_window_start), int(active_keyframe_window_end),
-                           int(increase_ba_iteration_count), float(time_limit))
+                           int(increase_ba_iteration_count), float(time_limit), int(pcg_max_inner_iterations),
+                           int(pcg_max_keyframes), int(pcg_gauge_keyframe))
         r = _lib.BAResult()
         self._check(self._lib.bba_bundle_adjust(self._h, C.byref(o), C.byref(r), self._stream_ptr(stream)))
         return BAResult(r.iterations_done, bool(r.converged), r.depth_residual_count, r.descriptor_residual_count,
                         r.cost, r.pose_iterations_total, r.ms_surfel_activation, r.ms_geometry_optimization,
-                        r.ms_pose_optimization, r.ms_intrinsics_optimization, r.kernel_launches)
+                        r.ms_pose_optimization, r.ms_intrinsics_optimization, r.kernel_launches,
+                        r.pcg_inner_iterations_total, r.pcg_last_r_norm, r.ms_pcg)
+
+    def PCGDebug(self, optimize_poses=True, optimize_geometry=True, optimize_depth_intrinsics=False,
+                 optimize_color_intrinsics=False, gauge_keyframe=0, stream=None):
+        """Parity hook (bba_pcg_debug): r, M, p0, g = J^T W J p0 and (alpha_n, alpha_d) of the PCG solver's first step."""
+        o = _lib.BAOptions(int(optimize_depth_intrinsics), int(optimize_color_intrinsics), 0, int(optimize_poses),
+                           int(optimize_geometry), 1, 1, 1, 0, len(self._keyframes) - 1, 0, 0.0, 30, 2500, int(gauge_keyframe))
+        n = C.c_uint32()
+        self._check(self._lib.bba_pcg_debug(self._h, C.byref(o), C.byref(n), None, None, None, None, None,
+                                            self._stream_ptr(stream)))
+        r, M, p, g = (np.zeros(n.value, np.float32) for _ in range(4))
+        sc = np.zeros(2, np.float64)
+        self._check(self._lib.bba_pcg_debug(self._h, C.byref(o), C.byref(n), r.ctypes.data, M.ctypes.data, p.ctypes.data,
+                                            g.ctypes.data, sc.ctypes.data, self._stream_ptr(stream)))
+        return r, M, p, g, sc
 
     # -- multi-GPU (one process per GPU) ---------------------------------------------------------------
     def SetCollective(self, group=None):

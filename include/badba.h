@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BBA_ABI_VERSION 1
+#define BBA_ABI_VERSION 2
 
 typedef struct bba_context* bba_handle;
 
@@ -78,6 +78,11 @@ typedef struct {
   int active_keyframe_window_end;
   int increase_ba_iteration_count;
   double time_limit_seconds;   /* 0 = none (direct_ba_alternating.cc:704-709) */
+  /* use_pcg only (direct_ba.h:158-160, direct_ba_pcg.cc:52-53) */
+  int pcg_max_inner_iterations;   /* <= 0: 30 */
+  int pcg_max_keyframes;          /* <= 0: 2500; keyframe_count must not exceed it */
+  int pcg_gauge_keyframe;         /* keyframe whose pose is held fixed in every iteration; < 0: rand() % keyframe_count per
+                                     iteration as the reference does (direct_ba_pcg.cc:324) */
 } bba_ba_options;
 
 typedef struct {
@@ -96,6 +101,11 @@ typedef struct {
   float ms_pose_optimization;
   float ms_intrinsics_optimization;
   uint64_t kernel_launches;            /* kernels this call launched */
+  /* use_pcg: inner PCG steps summed over the outer iterations, last residual norm sqrt(beta_n), device time of the
+   * last iteration's PCG solve ("BA PCG step", direct_ba_pcg.cc:733-737) */
+  int pcg_inner_iterations_total;
+  float pcg_last_r_norm;
+  float ms_pcg;
 } bba_ba_result;
 
 /* Counters of one pose pass (superset of kernel_opt_pose.cu's debug outputs; the n_* feed the
@@ -176,6 +186,12 @@ bba_status bba_estimate_frame_pose(bba_handle h, int keyframe_id, const float gl
 bba_status bba_update_surfel_activation(bba_handle h, void* stream);
 /* OptimizeGeometryIterationCUDA (kernels.h:234-244, kernel_opt_geometry.cc:80-201) */
 bba_status bba_optimize_geometry_iteration(bba_handle h, void* stream);
+/* Parity hook for the PCG solver's building blocks (kernel_pcg.cu:179-1037): runs the init pass (PCGInitCUDA for every
+ * keyframe) -> out_r, out_M; PCGInit2 -> out_p; one PCGStep1 sweep -> out_g, out_scalars = {alpha_n, alpha_d}.
+ * Host output buffers of *unknown_count floats; call with out_r = NULL to query the count.  o->pcg_gauge_keyframe >= 0. */
+bba_status bba_pcg_debug(bba_handle h, const bba_ba_options* o, uint32_t* unknown_count, float* out_r, float* out_M, float* out_p,
+                         float* out_g, double out_scalars[2], void* stream);
+
 /* OptimizeIntrinsicsCUDA (kernels.h:246-260, kernel_opt_intrinsics.cc:39-281) */
 bba_status bba_optimize_intrinsics(bba_handle h, int optimize_depth_intrinsics, int optimize_color_intrinsics, void* stream);
 /* DirectBA::BundleAdjustment (direct_ba.h:143-162, direct_ba.cc:407-453 -> direct_ba_alternating.cc:285-738) */

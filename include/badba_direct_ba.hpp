@@ -102,7 +102,7 @@ class DirectBA {
                         bool optimize_poses, bool optimize_geometry, int min_iterations, int max_iterations, bool use_pcg,
                         int active_keyframe_window_start, int active_keyframe_window_end, bool increase_ba_iteration_count,
                         int* iterations_done = nullptr, bool* converged = nullptr, double time_limit = 0, void* /*timer*/ = nullptr,
-                        int /*pcg_max_inner_iterations*/ = 30, int /*pcg_max_keyframes*/ = 2500,
+                        int pcg_max_inner_iterations = 30, int pcg_max_keyframes = 2500,
                         std::function<bool(int)> /*progress_function*/ = nullptr) {
     bba_ba_options o{};
     o.optimize_depth_intrinsics = optimize_depth_intrinsics;
@@ -117,6 +117,9 @@ class DirectBA {
     o.active_keyframe_window_end = active_keyframe_window_end;
     o.increase_ba_iteration_count = increase_ba_iteration_count;
     o.time_limit_seconds = time_limit;
+    o.pcg_max_inner_iterations = pcg_max_inner_iterations;
+    o.pcg_max_keyframes = pcg_max_keyframes;
+    o.pcg_gauge_keyframe = pcg_gauge_keyframe_;   // -1: rand() % K per iteration like direct_ba_pcg.cc:324
     bba_ba_result r{};
     Check(bba_bundle_adjust(h_, &o, &r, stream), "bba_bundle_adjust");
     if (iterations_done) *iterations_done = r.iterations_done;
@@ -133,6 +136,7 @@ class DirectBA {
     Check(bba_set_keyframe_pose(h_, keyframe_id, global_T_frame.data()), "bba_set_keyframe_pose");
   }
   void GetIntrinsics(float depth[4], float color[4], float* a) const { Check(bba_get_intrinsics(h_, depth, color, a), "bba_get_intrinsics"); }
+  void SetPCGGaugeKeyframe(int keyframe_id) { pcg_gauge_keyframe_ = keyframe_id; }
   const bba_ba_result& last_result() const { return last_result_; }
   bba_handle handle() const { return h_; }
 
@@ -142,6 +146,7 @@ class DirectBA {
   }
   bba_handle h_ = nullptr;
   bba_ba_result last_result_{};
+  int pcg_gauge_keyframe_ = -1;
 };
 
 }  // namespace badba

@@ -556,17 +556,10 @@ void orc_update_activation(const orc_model* m, const orc_keyframes* kfs, const f
 /* kernel_opt_geometry.cc:80-201 with kernels kernel_opt_geometry.cu (cited inline).
  * Surfel-major evaluation is exact: one thread owns one surfel in every reference kernel and
  * keyframes are visited in index order, so the fp32 accumulation order is identical. */
-void orc_optimize_geometry_iteration(const orc_model* m, const orc_keyframes* kfs, float* surfels, int pitch,
-                                     uint32_t n, const uint8_t* active) {
-  if (n == 0) return;
-  int K = kfs->K;
-  float* Ts = (float*)malloc(sizeof(float) * 12 * (size_t)K);
-  kfview* vs = (kfview*)malloc(sizeof(kfview) * (size_t)K);
-  for (int k = 0; k < K; ++k) { orc_frame_T_global(kfs->global_T_frame + 7 * k, Ts + 12 * k); make_view(m, kfs, k, vs + k); }
-  const int use_depth = m->use_depth_residuals, use_desc = m->use_descriptor_residuals;
-  const size_t P = (size_t)pitch;
-
-  /* --- normals: :527-557 accumulate, :577-597 update --- */
+/* UpdateSurfelNormalsCUDA (kernel_opt_geometry.cc:39-77): accumulate :527-557, update :577-597. */
+static void update_normals(const orc_keyframes* kfs, const float* Ts, const kfview* vs, float* surfels, size_t P, uint32_t n,
+                           const uint8_t* active) {
+  const int K = kfs->K;
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < (int64_t)n; ++i) {
     if (!(active[i] & K_SURFEL_ACTIVE_FLAG)) continue;
@@ -592,6 +585,20 @@ void orc_optimize_geometry_iteration(const orc_model* m, const orc_keyframes* kf
       surfels[ROW_NORMAL * P + i] = u2f(pack_normal(mk3(inv * a0, inv * a1, inv * a2)));
     }
   }
+
+}
+
+void orc_optimize_geometry_iteration(const orc_model* m, const orc_keyframes* kfs, float* surfels, int pitch,
+                                     uint32_t n, const uint8_t* active) {
+  if (n == 0) return;
+  int K = kfs->K;
+  float* Ts = (float*)malloc(sizeof(float) * 12 * (size_t)K);
+  kfview* vs = (kfview*)malloc(sizeof(kfview) * (size_t)K);
+  for (int k = 0; k < K; ++k) { orc_frame_T_global(kfs->global_T_frame + 7 * k, Ts + 12 * k); make_view(m, kfs, k, vs + k); }
+  const int use_depth = m->use_depth_residuals, use_desc = m->use_descriptor_residuals;
+  const size_t P = (size_t)pitch;
+
+  update_normals(kfs, Ts, vs, surfels, P, n, active);
 
   if (!use_desc) {
     /* --- position from depth residual only: :417-459 accumulate, :487-507 update --- */
@@ -940,6 +947,372 @@ void orc_bundle_adjust(orc_model* m, orc_keyframes* kfs, float* surfels, int pit
     }
     determine_covisible_active(kfs);   /* :711-717 */
   }
+}
+
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * PCG-based Gauss-Newton (DirectBA::BundleAdjustmentPCG, direct_ba_pcg.cc:43-819; kernels kernel_pcg.cu:179-1372).
+ * Vectors are fp32 (PCGScalar = float, kernels.cuh:62); the sums that the device forms with block reductions + float
+ * atomics (arbitrary order) are accumulated in fp64 here and rounded to fp32 once.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define PCG_DIAG_EPSILON 1e-8f   /* kernel_pcg.cu:44 */
+#define PCG_A_PRIOR 10.f         /* kernel_pcg.cu:48 */
+
+typedef struct {
+  int opt_poses, opt_geometry, opt_di, opt_ci, use_depth, use_desc;
+  int gauge;
+  uint32_t surfel_start, stride, depth_start, color_start;
+} pcg_layout;
+
+/* One (surfel, keyframe) pair: the Jacobian rows of its up to three residuals (kernel_pcg.cu:204-505 / 670-1036). */
+typedef struct {
+  int depth_valid;      /* depth residual present */
+  float raw, w, jg, jp[6];
+  int di_valid; float jd[5], jcf; uint32_t cf_u;
+  int desc_valid;       /* descriptor residuals present */
+  float r1, r2, w1, w2, jg1, jg2, jp1[6], jp2[6], jc1[4], jc2[4];
+} pcg_rows;
+
+static void pcg_eval(const kfview* v, const float T[12], const float* surfels, size_t P, uint32_t i, const pcg_layout* L,
+                     int init, pcg_rows* o) {
+  memset(o, 0, sizeof(*o));
+  assoc r;
+  f3 gp = mk3(surfels[ROW_X * P + i], surfels[ROW_Y * P + i], surfels[ROW_Z * P + i]);
+  if (project_associate(v, T, gp, f2u(surfels[ROW_NORMAL * P + i]), &r) != 3) return;
+  int visible = 1;
+  f3 rn = T_rot(T, r.n);
+  float nx = v->fx_inv * r.px + v->cx_inv, ny = v->fy_inv * r.py + v->cy_inv;
+  if (L->use_depth) {
+    float inv_stddev;
+    f3 up;
+    o->raw = depth_pose_residual_jacobian(v, &r, rn, o->jp, &inv_stddev, &up);
+    o->w = depth_weight(o->raw);
+    o->jg = -inv_stddev;
+    o->depth_valid = 1;
+    if (L->opt_di) {
+      int spx = r.px / v->cell, spy = r.py / v->cell;
+      float cfactor = v->cfactor[(size_t)spy * v->cf_w + spx];
+      float raw_inv_depth = 1.0f / (v->raw_to_float * v->depth[(size_t)r.py * v->w + r.px]);
+      float exp_inv_depth = expf(-v->a * raw_inv_depth);
+      float corrected_inv_depth = cfactor * exp_inv_depth + raw_inv_depth;
+      o->di_valid = !(fabsf(corrected_inv_depth) < 1e-4f);
+      if (init && !o->di_valid) visible = 0;   /* kernel_pcg.cu:266-268 (only the init kernel clears `visible`) */
+      float dot = nx * rn.x + ny * rn.y + rn.z;
+      float jac_base = inv_stddev * dot * exp_inv_depth / (corrected_inv_depth * corrected_inv_depth);
+      o->jd[2] = inv_stddev * r.d * (r.n.x * T[0] + r.n.y * T[1] + r.n.z * T[2]);
+      o->jd[3] = inv_stddev * r.d * (r.n.x * T[4] + r.n.y * T[5] + r.n.z * T[6]);
+      o->jd[0] = r.px * o->jd[2];
+      o->jd[1] = r.py * o->jd[3];
+      o->jd[4] = cfactor * raw_inv_depth * jac_base;
+      o->jcf = -jac_base;
+      o->cf_u = L->depth_start + 5u + (uint32_t)spx + (uint32_t)spy * (uint32_t)v->cf_w;
+    }
+  }
+  if (L->use_desc && visible) {
+    float ccx, ccy;
+    if (!depth_to_color(v, r.pxf, r.pyf, &ccx, &ccy)) return;
+    float t1x, t1y, t2x, t2y;
+    tangent_projections(v, T, r.gp, r.n, surfels[ROW_R2 * P + i], &t1x, &t1y, &t2x, &t2y);
+    desc_eval e;
+    descriptor_eval(v, ccx, ccy, t1x, t1y, t2x, t2y, surfels[ROW_D1 * P + i], surfels[ROW_D2 * P + i], &e);
+    o->desc_valid = 1;
+    o->r1 = e.r1; o->r2 = e.r2;
+    o->w1 = desc_weight(e.r1); o->w2 = desc_weight(e.r2);
+    float gx1 = e.gx1 * v->cfx, gy1 = e.gy1 * v->cfy, gx2 = e.gx2 * v->cfx, gy2 = e.gy2 * v->cfy;
+    float term1 = -(rn.x * r.lp.z - rn.z * r.lp.x);
+    float term2 = -(rn.y * r.lp.z - rn.z * r.lp.y);
+    float term3 = 1.f / (r.lp.z * r.lp.z);
+    o->jg1 = -(gx1 * term1 + gy1 * term2) * term3;
+    o->jg2 = -(gx2 * term1 + gy2 * term2) * term3;
+    desc_pose_jacobian(v, r.lp, e.gx1, e.gy1, o->jp1);
+    desc_pose_jacobian(v, r.lp, e.gx2, e.gy2, o->jp2);
+    float g1x = gx1 / v->cfx, g1y = gy1 / v->cfy, g2x = gx2 / v->cfx, g2y = gy2 / v->cfy;   /* kernel_pcg.cu:454-457 */
+    o->jc1[0] = g1x * nx; o->jc1[1] = g1y * ny; o->jc1[2] = g1x; o->jc1[3] = g1y;
+    o->jc2[0] = g2x * nx; o->jc2[1] = g2y * ny; o->jc2[2] = g2x; o->jc2[3] = g2y;
+  }
+}
+
+static inline uint32_t pcg_pose_index(int k, int gauge) { return (uint32_t)(6 * (k < gauge ? k : k - 1)); }
+
+/* init = 1: out0 = r (-= J^T W F), out1 = M (+= diag J^T W J).  init = 0: out0 = g (+= J^T W J p), returns p^T J^T W J p. */
+static double pcg_pass(const orc_model* m, const orc_keyframes* kfs, const float* surfels, size_t P, uint32_t n,
+                       const pcg_layout* L, int init, const float* p, double* out0, double* out1) {
+  const int K = kfs->K;
+  double alpha_d = 0;
+  for (int k = 0; k < K; ++k) {
+    kfview v;
+    make_view(m, kfs, k, &v);
+    float T[12];
+    orc_frame_T_global(kfs->global_T_frame + 7 * k, T);
+    const int do_pose = L->opt_poses && k != L->gauge;
+    const uint32_t pu = pcg_pose_index(k, L->gauge);
+    double pose0[6] = {0}, pose1[6] = {0}, di0[5] = {0}, di1[5] = {0}, ci0[4] = {0}, ci1[4] = {0};
+    double ad = 0;
+#pragma omp parallel
+    {
+      double t_pose0[6] = {0}, t_pose1[6] = {0}, t_di0[5] = {0}, t_di1[5] = {0}, t_ci0[4] = {0}, t_ci1[4] = {0}, t_ad = 0;
+#pragma omp for schedule(static)
+      for (int64_t ii = 0; ii < (int64_t)n; ++ii) {
+        const uint32_t i = (uint32_t)ii;
+        pcg_rows o;
+        pcg_eval(&v, T, surfels, P, i, L, init, &o);
+        const uint32_t su = L->surfel_start + L->stride * i;
+        if (o.depth_valid) {
+          if (init) {
+            const float wr = o.w * o.raw;
+            if (L->opt_geometry) { out0[su] -= (double)(o.jg * wr); out1[su] += (double)(o.jg * o.w * o.jg); }
+            if (do_pose) for (int c = 0; c < 6; ++c) { t_pose0[c] -= (double)(o.jp[c] * wr); t_pose1[c] += (double)(o.jp[c] * o.w * o.jp[c]); }
+            if (L->opt_di && o.di_valid) {
+              for (int c = 0; c < 5; ++c) { t_di0[c] -= (double)(o.jd[c] * wr); t_di1[c] += (double)(o.jd[c] * o.w * o.jd[c]); }
+#pragma omp atomic
+              out0[o.cf_u] -= (double)(o.jcf * wr);
+#pragma omp atomic
+              out1[o.cf_u] += (double)(o.jcf * o.w * o.jcf);
+            }
+          } else {
+            float sum = 0;
+            if (L->opt_geometry) sum += o.jg * p[su];
+            if (do_pose) for (int c = 0; c < 6; ++c) sum += o.jp[c] * p[pu + c];
+            if (L->opt_di && o.di_valid) {
+              for (int c = 0; c < 5; ++c) sum += o.jd[c] * p[L->depth_start + c];
+              sum += o.jcf * p[o.cf_u];
+            }
+            t_ad += (double)(sum * o.w * sum);
+            sum *= o.w;
+            if (L->opt_geometry) out0[su] += (double)(o.jg * sum);
+            if (do_pose) for (int c = 0; c < 6; ++c) t_pose0[c] += (double)(o.jp[c] * sum);
+            if (L->opt_di && o.di_valid) {
+              for (int c = 0; c < 5; ++c) t_di0[c] += (double)(o.jd[c] * sum);
+#pragma omp atomic
+              out0[o.cf_u] += (double)(o.jcf * sum);
+            }
+          }
+        }
+        if (o.desc_valid) {
+          if (init) {
+            const float wr1 = o.w1 * o.r1, wr2 = o.w2 * o.r2;
+            if (L->opt_geometry) {
+              out0[su] -= (double)(o.jg1 * wr1 + o.jg2 * wr2);
+              out1[su] += (double)(o.jg1 * o.w1 * o.jg1 + o.jg2 * o.w2 * o.jg2);
+              out0[su + 1] += (double)wr1; out1[su + 1] += (double)o.w1;
+              out0[su + 2] += (double)wr2; out1[su + 2] += (double)o.w2;
+            }
+            if (do_pose) for (int c = 0; c < 6; ++c) {
+              t_pose0[c] -= (double)(o.jp1[c] * wr1 + o.jp2[c] * wr2);
+              t_pose1[c] += (double)(o.jp1[c] * o.w1 * o.jp1[c] + o.jp2[c] * o.w2 * o.jp2[c]);
+            }
+            if (L->opt_ci) for (int c = 0; c < 4; ++c) {
+              t_ci0[c] -= (double)(o.jc1[c] * wr1 + o.jc2[c] * wr2);
+              t_ci1[c] += (double)(o.jc1[c] * o.w1 * o.jc1[c] + o.jc2[c] * o.w2 * o.jc2[c]);
+            }
+          } else {
+            float s1 = 0, s2 = 0;
+            if (L->opt_geometry) { s1 += o.jg1 * p[su] - p[su + 1]; s2 += o.jg2 * p[su] - p[su + 2]; }
+            if (do_pose) for (int c = 0; c < 6; ++c) { s1 += o.jp1[c] * p[pu + c]; s2 += o.jp2[c] * p[pu + c]; }
+            if (L->opt_ci) for (int c = 0; c < 4; ++c) { s1 += o.jc1[c] * p[L->color_start + c]; s2 += o.jc2[c] * p[L->color_start + c]; }
+            t_ad += (double)(s1 * o.w1 * s1 + s2 * o.w2 * s2);
+            s1 *= o.w1; s2 *= o.w2;
+            if (L->opt_geometry) {
+              out0[su] += (double)(o.jg1 * s1 + o.jg2 * s2);
+              out0[su + 1] -= (double)s1;
+              out0[su + 2] -= (double)s2;
+            }
+            if (do_pose) for (int c = 0; c < 6; ++c) t_pose0[c] += (double)(o.jp1[c] * s1 + o.jp2[c] * s2);
+            if (L->opt_ci) for (int c = 0; c < 4; ++c) t_ci0[c] += (double)(o.jc1[c] * s1 + o.jc2[c] * s2);
+          }
+        }
+      }
+#pragma omp critical
+      {
+        for (int c = 0; c < 6; ++c) { pose0[c] += t_pose0[c]; pose1[c] += t_pose1[c]; }
+        for (int c = 0; c < 5; ++c) { di0[c] += t_di0[c]; di1[c] += t_di1[c]; }
+        for (int c = 0; c < 4; ++c) { ci0[c] += t_ci0[c]; ci1[c] += t_ci1[c]; }
+        ad += t_ad;
+      }
+    }
+    if (do_pose) for (int c = 0; c < 6; ++c) { out0[pu + c] += pose0[c]; if (init) out1[pu + c] += pose1[c]; }
+    if (L->opt_di) for (int c = 0; c < 5; ++c) { out0[L->depth_start + c] += di0[c]; if (init) out1[L->depth_start + c] += di1[c]; }
+    if (L->opt_ci) for (int c = 0; c < 4; ++c) { out0[L->color_start + c] += ci0[c]; if (init) out1[L->color_start + c] += ci1[c]; }
+    alpha_d += ad;
+  }
+  return alpha_d;
+}
+
+static inline float pcg_diag_extra(uint32_t i, uint32_t a_index) {
+  return PCG_DIAG_EPSILON + ((i == a_index) ? (PCG_A_PRIOR * PCG_A_PRIOR) : 0.f);
+}
+
+void orc_bundle_adjust_pcg(orc_model* m, orc_keyframes* kfs, float* surfels, int pitch, uint32_t n, uint8_t* active,
+                           const orc_pcg_options* opt, orc_pcg_result* res) {
+  memset(res, 0, sizeof(*res));
+  const int K = kfs->K;
+  const size_t P = (size_t)pitch;
+  const uint32_t Pn = (uint32_t)(m->cf_w * m->cf_h);
+  const uint32_t kInvalid = 0xffffffffu;
+  const int max_inner = opt->max_inner_iterations > 0 ? opt->max_inner_iterations : 30;
+  for (int iteration = 0; iteration < opt->max_iterations; ++iteration) {
+    ++res->iterations_done;
+    memset(active, K_SURFEL_ACTIVE_FLAG, n);   /* direct_ba_pcg.cc:209-212 */
+    if (opt->optimize_geometry && n > 0) {     /* :215-227 */
+      float* Ts = (float*)malloc(sizeof(float) * 12 * (size_t)K);
+      kfview* vs = (kfview*)malloc(sizeof(kfview) * (size_t)K);
+      for (int k = 0; k < K; ++k) { orc_frame_T_global(kfs->global_T_frame + 7 * k, Ts + 12 * k); make_view(m, kfs, k, vs + k); }
+      update_normals(kfs, Ts, vs, surfels, P, n, active);
+      free(Ts); free(vs);
+    }
+    pcg_layout L;
+    L.use_depth = m->use_depth_residuals; L.use_desc = m->use_descriptor_residuals;
+    L.opt_poses = opt->optimize_poses; L.opt_geometry = opt->optimize_geometry;
+    L.opt_di = opt->optimize_depth_intrinsics && L.use_depth;      /* direct_ba.cc:427-434 */
+    L.opt_ci = opt->optimize_color_intrinsics && L.use_desc;
+    L.gauge = opt->gauge_keyframe;
+    L.stride = L.use_desc ? 3u : 1u;
+    uint32_t cur = 0, a_index = kInvalid;
+    if (L.opt_poses) cur += 6u * (uint32_t)(K - 1);
+    L.surfel_start = L.depth_start = L.color_start = kInvalid;
+    if (L.opt_geometry) { L.surfel_start = cur; cur += L.stride * n; }
+    if (L.opt_di) { L.depth_start = cur; cur += 5u + Pn; a_index = L.depth_start + 4u; }
+    if (L.opt_ci) { L.color_start = cur; cur += 4u; }
+    const uint32_t U = cur;
+    int num_converged = L.opt_poses ? 1 : 0;
+    if (U > 0) {
+      double* acc0 = (double*)calloc(U, sizeof(double));
+      double* acc1 = (double*)calloc(U, sizeof(double));
+      float* r = (float*)malloc(sizeof(float) * U);
+      float* M = (float*)malloc(sizeof(float) * U);
+      float* delta = (float*)calloc(U, sizeof(float));
+      float* g = (float*)calloc(U, sizeof(float));
+      float* p = (float*)malloc(sizeof(float) * U);
+      pcg_pass(m, kfs, surfels, P, n, &L, 1, NULL, acc0, acc1);
+      double alpha_n = 0, beta_n = 0;
+      for (uint32_t i = 0; i < U; ++i) {   /* PCGInit2CUDAKernel, kernel_pcg.cu:569-605 */
+        r[i] = (float)acc0[i]; M[i] = (float)acc1[i];
+        float r_value = r[i] + ((i == a_index) ? (-PCG_A_PRIOR * PCG_A_PRIOR * m->a) : 0.f);
+        float p_value = r_value / (M[i] + pcg_diag_extra(i, a_index));
+        p[i] = p_value;
+        alpha_n += (double)(r_value * p_value);
+      }
+      float prev_r_norm = INFINITY;
+      int without_improvement = 0;
+      for (int step = 0; step < max_inner; ++step) {
+        if (step > 0) alpha_n = beta_n;   /* :386 */
+        memset(acc0, 0, sizeof(double) * U);
+        double alpha_d = pcg_pass(m, kfs, surfels, P, n, &L, 0, p, acc0, NULL);
+        /* AddAlphaDEpsilonTermsCUDAKernel runs after EVERY per-keyframe PCGStep1 launch (kernel_pcg.cu:1101-1112) */
+        double eps = 0;
+        for (uint32_t i = 0; i < U; ++i) eps += (double)(pcg_diag_extra(i, a_index) * p[i] * p[i]);
+        alpha_d += eps * K;
+        /* PCGStep2CUDAKernel, kernel_pcg.cu:1115-1166 */
+        const float alpha = ((float)alpha_d >= 1e-35f) ? ((float)alpha_n / (float)alpha_d) : 0.f;
+        beta_n = 0;
+        for (uint32_t i = 0; i < U; ++i) {
+          g[i] = (float)acc0[i];
+          delta[i] += alpha * p[i];
+          float r_value = r[i] - alpha * (g[i] + pcg_diag_extra(i, a_index) * p[i]);
+          r[i] = r_value;
+          float z = r_value / (M[i] + pcg_diag_extra(i, a_index));
+          g[i] = z;
+          beta_n += (double)(z * r_value);
+        }
+        ++res->inner_iterations_total;
+        float r_norm = sqrtf((float)beta_n);
+        res->last_r_norm = r_norm;
+        if ((double)r_norm < (double)prev_r_norm - 1e-3) without_improvement = 0;
+        else if (++without_improvement >= 3) break;
+        prev_r_norm = r_norm;
+        if (step < max_inner - 1) {   /* PCGStep3CUDAKernel, kernel_pcg.cu:1206-1224 */
+          const float beta = ((float)alpha_n >= 1e-35f) ? ((float)beta_n / (float)alpha_n) : 0.f;
+          for (uint32_t i = 0; i < U; ++i) p[i] = g[i] + beta * p[i];
+        }
+      }
+      /* apply delta (direct_ba_pcg.cc:552-638) */
+      if (L.opt_poses) {
+        for (int k = 0; k < K; ++k) {
+          if (k == L.gauge) continue;
+          float d7[7], np[7], lg[6];
+          hm_se3_exp(delta + pcg_pose_index(k, L.gauge), d7);
+          hm_se3_mul(kfs->global_T_frame + 7 * k, d7, np);
+          memcpy(kfs->global_T_frame + 7 * k, np, sizeof(np));
+          hm_se3_log(d7, lg);
+          if (hm_is_scale1_pose_converged(lg)) ++num_converged;
+        }
+      }
+      if (L.opt_geometry) {   /* kernel_pcg.cu:1278-1308 */
+        for (uint32_t i = 0; i < n; ++i) {
+          const uint32_t su = L.surfel_start + L.stride * i;
+          float t = delta[su];
+          if (t != 0) {
+            f3 nrm = unpack_normal(f2u(surfels[ROW_NORMAL * P + i]));
+            surfels[ROW_X * P + i] += t * nrm.x;
+            surfels[ROW_Y * P + i] += t * nrm.y;
+            surfels[ROW_Z * P + i] += t * nrm.z;
+          }
+          if (L.use_desc) {
+            surfels[ROW_D1 * P + i] = fmaxf(-180.f, fminf(180.f, surfels[ROW_D1 * P + i] + delta[su + 1]));
+            surfels[ROW_D2 * P + i] = fmaxf(-180.f, fminf(180.f, surfels[ROW_D2 * P + i] + delta[su + 2]));
+          }
+        }
+      }
+      if (L.opt_di) {
+        const float* b = delta + L.depth_start;
+        double old_fx_inv = 1. / m->depth_K[0], old_fy_inv = 1. / m->depth_K[1];
+        double old_cx_inv = -(m->depth_K[2] - 0.5) * old_fx_inv, old_cy_inv = -(m->depth_K[3] - 0.5) * old_fy_inv;
+        double nfx = 1. / (old_fx_inv + b[0]), nfy = 1. / (old_fy_inv + b[1]);
+        double ncx = -(nfx * (old_cx_inv + b[2])) + 0.5, ncy = -(nfy * (old_cy_inv + b[3])) + 0.5;
+        m->depth_K[0] = (float)nfx; m->depth_K[1] = (float)nfy; m->depth_K[2] = (float)ncx; m->depth_K[3] = (float)ncy;
+        m->a += b[4];
+        for (uint32_t c = 0; c < Pn; ++c) m->cfactor[c] += b[5 + c];
+      }
+      if (L.opt_ci) for (int c = 0; c < 4; ++c) m->color_K[c] = (float)(m->color_K[c] + delta[L.color_start + c]);
+      free(acc0); free(acc1); free(r); free(M); free(delta); free(g); free(p);
+    }
+    if (iteration >= opt->min_iterations - 1 && (num_converged == K || !L.opt_poses)) {
+      res->converged = 1;
+      break;
+    }
+  }
+}
+
+/* Parity hook: r, M after the init pass; p = M^-1 r (with the prior on a); g after one J^T W J p sweep;
+ * scalars = {alpha_n, alpha_d}.  Returns the unknown count (call with out_r = NULL to size the buffers). */
+uint32_t orc_pcg_debug(const orc_model* m, const orc_keyframes* kfs, const float* surfels, int pitch, uint32_t n,
+                       const orc_pcg_options* opt, float* out_r, float* out_M, float* out_p, float* out_g, double* out_scalars) {
+  const int K = kfs->K;
+  const size_t P = (size_t)pitch;
+  const uint32_t Pn = (uint32_t)(m->cf_w * m->cf_h), kInvalid = 0xffffffffu;
+  pcg_layout L;
+  L.use_depth = m->use_depth_residuals; L.use_desc = m->use_descriptor_residuals;
+  L.opt_poses = opt->optimize_poses; L.opt_geometry = opt->optimize_geometry;
+  L.opt_di = opt->optimize_depth_intrinsics && L.use_depth;
+  L.opt_ci = opt->optimize_color_intrinsics && L.use_desc;
+  L.gauge = opt->gauge_keyframe;
+  L.stride = L.use_desc ? 3u : 1u;
+  uint32_t cur = 0, a_index = kInvalid;
+  if (L.opt_poses) cur += 6u * (uint32_t)(K - 1);
+  L.surfel_start = L.depth_start = L.color_start = kInvalid;
+  if (L.opt_geometry) { L.surfel_start = cur; cur += L.stride * n; }
+  if (L.opt_di) { L.depth_start = cur; cur += 5u + Pn; a_index = L.depth_start + 4u; }
+  if (L.opt_ci) { L.color_start = cur; cur += 4u; }
+  const uint32_t U = cur;
+  if (!out_r) return U;
+  double* acc0 = (double*)calloc(U, sizeof(double));
+  double* acc1 = (double*)calloc(U, sizeof(double));
+  pcg_pass(m, kfs, surfels, P, n, &L, 1, NULL, acc0, acc1);
+  double alpha_n = 0;
+  for (uint32_t i = 0; i < U; ++i) {
+    out_r[i] = (float)acc0[i]; out_M[i] = (float)acc1[i];
+    float r_value = out_r[i] + ((i == a_index) ? (-PCG_A_PRIOR * PCG_A_PRIOR * m->a) : 0.f);
+    out_p[i] = r_value / (out_M[i] + pcg_diag_extra(i, a_index));
+    alpha_n += (double)(r_value * out_p[i]);
+  }
+  memset(acc0, 0, sizeof(double) * U);
+  double alpha_d = pcg_pass(m, kfs, surfels, P, n, &L, 0, out_p, acc0, NULL);
+  double eps = 0;
+  for (uint32_t i = 0; i < U; ++i) { out_g[i] = (float)acc0[i]; eps += (double)(pcg_diag_extra(i, a_index) * out_p[i] * out_p[i]); }
+  out_scalars[0] = alpha_n;
+  out_scalars[1] = alpha_d + eps * K;
+  free(acc0); free(acc1);
+  return U;
 }
 
 void orc_se3_exp(const float a[6], float out[7]) { hm_se3_exp(a, out); }

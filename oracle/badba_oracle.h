@@ -133,6 +133,23 @@ void orc_bundle_adjust(orc_model* m, orc_keyframes* kfs,
                        float* surfels, int pitch, uint32_t n, uint8_t* active,
                        const orc_ba_options* opt, orc_ba_result* res);
 
+/* DirectBA::BundleAdjustmentPCG (direct_ba_pcg.cc:43-819; kernels kernel_pcg.cu:179-1372) without the surfel lifecycle.
+ * gauge_keyframe: the keyframe held fixed (the reference draws rand() % K per iteration, direct_ba_pcg.cc:324). */
+typedef struct {
+  int optimize_poses, optimize_geometry, optimize_depth_intrinsics, optimize_color_intrinsics;
+  int min_iterations, max_iterations, max_inner_iterations, gauge_keyframe;
+} orc_pcg_options;
+typedef struct {
+  int iterations_done, converged, inner_iterations_total;
+  float last_r_norm;
+} orc_pcg_result;
+void orc_bundle_adjust_pcg(orc_model* m, orc_keyframes* kfs, float* surfels, int pitch, uint32_t n, uint8_t* active,
+                           const orc_pcg_options* opt, orc_pcg_result* res);
+
+/* Parity hook for the PCG building blocks: r, M after the init pass, p0, g after one J^T W J p sweep, {alpha_n, alpha_d}. */
+uint32_t orc_pcg_debug(const orc_model* m, const orc_keyframes* kfs, const float* surfels, int pitch, uint32_t n,
+                       const orc_pcg_options* opt, float* out_r, float* out_M, float* out_p, float* out_g, double* out_scalars);
+
 /* Residual-level access for Jacobian tests: evaluates the raw residuals of one
  * (surfel, keyframe) pair.  Returns bit0 = associated, bit1 = photometric valid.
  * r[0] = depth, r[1], r[2] = descriptor; J_pose (3 x 6) are the reference's

@@ -34,8 +34,9 @@ for s in "${SRCS[@]}"; do
     extra=()
     # AccumulateIntrinsicsCoefficientsCUDAKernel is launched with 1024-thread blocks (CUDA_AUTO_TUNE_1D_TEMPLATED default,
     # kernel_opt_intrinsics.cu:239-242) but compiles to > 64 registers for sm_100: "too many resources requested for
-    # launch".  Cap the registers for that translation unit only (a build flag, the source stays untouched).
-    [[ "$s" == *kernel_opt_intrinsics.cu ]] && extra=(-maxrregcount=64)
+    # launch".  Same for PCGInitCUDAKernel (1024 threads, kernel_pcg.cu:538-541).  Cap the registers for these translation
+    # units only (a build flag, the sources stay untouched).
+    [[ "$s" == *kernel_opt_intrinsics.cu || "$s" == *kernel_pcg.cu ]] && extra=(-maxrregcount=64)
     ( "$NVCC" "${FLAGS[@]}" "${extra[@]}" -c "$s" -o "$o" && echo "built $o" ) &
     pids+=($!)
   fi

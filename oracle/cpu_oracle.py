@@ -62,6 +62,17 @@ class BAResult(C.Structure):
                 ("pose_iterations_total", C.c_int)]
 
 
+class PCGOptions(C.Structure):
+    _fields_ = [("optimize_poses", C.c_int), ("optimize_geometry", C.c_int), ("optimize_depth_intrinsics", C.c_int),
+                ("optimize_color_intrinsics", C.c_int), ("min_iterations", C.c_int), ("max_iterations", C.c_int),
+                ("max_inner_iterations", C.c_int), ("gauge_keyframe", C.c_int)]
+
+
+class PCGResult(C.Structure):
+    _fields_ = [("iterations_done", C.c_int), ("converged", C.c_int), ("inner_iterations_total", C.c_int),
+                ("last_r_norm", C.c_float)]
+
+
 _lib = None
 
 
@@ -176,6 +187,30 @@ class Oracle:
                                    C.c_int(self.pitch), C.c_uint32(self.n), _p(self.active, C.c_uint8),
                                    C.byref(o), C.byref(r))
         return r
+
+    def bundle_adjust_pcg(self, optimize_poses=True, optimize_geometry=True, optimize_depth_intrinsics=False,
+                          optimize_color_intrinsics=False, min_iterations=1, max_iterations=1, max_inner_iterations=30,
+                          gauge_keyframe=0):
+        o = PCGOptions(int(optimize_poses), int(optimize_geometry), int(optimize_depth_intrinsics),
+                       int(optimize_color_intrinsics), min_iterations, max_iterations, max_inner_iterations, gauge_keyframe)
+        r = PCGResult()
+        self.lib.orc_bundle_adjust_pcg(C.byref(self.model), C.byref(self.kfs), _p(self.surfels, C.c_float),
+                                       C.c_int(self.pitch), C.c_uint32(self.n), _p(self.active, C.c_uint8),
+                                       C.byref(o), C.byref(r))
+        return r
+
+    def pcg_debug(self, optimize_poses=True, optimize_geometry=True, optimize_depth_intrinsics=False,
+                  optimize_color_intrinsics=False, gauge_keyframe=0):
+        o = PCGOptions(int(optimize_poses), int(optimize_geometry), int(optimize_depth_intrinsics),
+                       int(optimize_color_intrinsics), 1, 1, 30, gauge_keyframe)
+        self.lib.orc_pcg_debug.restype = C.c_uint32
+        args = (C.byref(self.model), C.byref(self.kfs), _p(self.surfels, C.c_float), C.c_int(self.pitch), C.c_uint32(self.n),
+                C.byref(o))
+        n = self.lib.orc_pcg_debug(*args, None, None, None, None, None)
+        r, M, p, g = (np.zeros(n, np.float32) for _ in range(4))
+        sc = np.zeros(2, np.float64)
+        self.lib.orc_pcg_debug(*args, _p(r, C.c_float), _p(M, C.c_float), _p(p, C.c_float), _p(g, C.c_float), _p(sc, C.c_double))
+        return r, M, p, g, sc
 
     def pair_residuals(self, k, surfel8, pose=None):
         T = self.frame_T_global(self.poses[k] if pose is None else pose)

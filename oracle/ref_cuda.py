@@ -35,6 +35,17 @@ class BAResult(C.Structure):
                 ("kernel_launches", C.c_ulonglong)]
 
 
+class PCGOptions(C.Structure):
+    _fields_ = [("optimize_poses", C.c_int), ("optimize_geometry", C.c_int), ("optimize_depth_intrinsics", C.c_int),
+                ("optimize_color_intrinsics", C.c_int), ("min_iterations", C.c_int), ("max_iterations", C.c_int),
+                ("max_inner_iterations", C.c_int), ("gauge_keyframe", C.c_int)]
+
+
+class PCGResult(C.Structure):
+    _fields_ = [("iterations_done", C.c_int), ("converged", C.c_int), ("inner_iterations_total", C.c_int),
+                ("last_r_norm", C.c_float), ("ms_pcg", C.c_float), ("kernel_launches", C.c_ulonglong)]
+
+
 _lib = None
 
 
@@ -67,6 +78,9 @@ def lib():
         l.ref_get_cfactor.argtypes = [C.c_void_p, C.c_void_p]
         l.ref_optimize_geometry_iteration.argtypes = [C.c_void_p]
         l.ref_bundle_adjust.argtypes = [C.c_void_p, C.POINTER(BAOptions), C.POINTER(BAResult), C.c_int]
+        l.ref_bundle_adjust_pcg.argtypes = [C.c_void_p, C.POINTER(PCGOptions), C.POINTER(PCGResult)]
+        l.ref_pcg_debug.restype = C.c_uint
+        l.ref_pcg_debug.argtypes = [C.c_void_p, C.POINTER(PCGOptions), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         l.ref_snapshot.argtypes = [C.c_void_p]
         l.ref_restore.argtypes = [C.c_void_p]
         l.ref_sync.argtypes = [C.c_void_p]
@@ -211,6 +225,25 @@ class RefDirectBA:
         r = BAResult()
         self.l.ref_bundle_adjust(self.h, C.byref(o), C.byref(r), int(count_residuals))
         return r
+
+    def bundle_adjust_pcg(self, optimize_poses=True, optimize_geometry=True, optimize_depth_intrinsics=False,
+                          optimize_color_intrinsics=False, min_iterations=1, max_iterations=1, max_inner_iterations=30,
+                          gauge_keyframe=0):
+        o = PCGOptions(int(optimize_poses), int(optimize_geometry), int(optimize_depth_intrinsics),
+                       int(optimize_color_intrinsics), min_iterations, max_iterations, max_inner_iterations, gauge_keyframe)
+        r = PCGResult()
+        self.l.ref_bundle_adjust_pcg(self.h, C.byref(o), C.byref(r))
+        return r
+
+    def pcg_debug(self, optimize_poses=True, optimize_geometry=True, optimize_depth_intrinsics=False,
+                  optimize_color_intrinsics=False, gauge_keyframe=0):
+        o = PCGOptions(int(optimize_poses), int(optimize_geometry), int(optimize_depth_intrinsics),
+                       int(optimize_color_intrinsics), 1, 1, 30, gauge_keyframe)
+        n = self.l.ref_pcg_debug(self.h, C.byref(o), None, None, None, None, None)
+        r, M, p, g = (np.zeros(n, np.float32) for _ in range(4))
+        sc = np.zeros(2, np.float32)
+        self.l.ref_pcg_debug(self.h, C.byref(o), r.ctypes.data, M.ctypes.data, p.ctypes.data, g.ctypes.data, sc.ctypes.data)
+        return r, M, p, g, sc.astype(np.float64)
 
     def snapshot(self):
         self.l.ref_snapshot(self.h)

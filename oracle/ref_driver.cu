@@ -27,6 +27,37 @@
 
 using namespace vis;
 
+// Launchers defined in the reference's kernel_pcg.cu.  They are declared in badslam/kernels.h, which cannot be included
+// here (it pulls in Eigen through libvis/camera.h), so the prototypes are repeated (kernels.h:397-495).
+namespace vis {
+void PCGInitCUDA(cudaStream_t stream, const SurfelProjectionParameters& s, const DepthToColorPixelCorner& depth_to_color,
+                 const PixelCenterUnprojector& depth_unprojector, const PixelCornerProjector& color_projector,
+                 cudaTextureObject_t color_texture, u32 kf_pose_unknown_index, u32 surfel_unknown_start_index, bool optimize_poses,
+                 bool optimize_geometry, bool use_depth_residuals, bool use_descriptor_residuals, bool optimize_depth_intrinsics,
+                 bool optimize_color_intrinsics, u32 depth_intrinsics_unknown_start_index, u32 color_intrinsics_unknown_start_index,
+                 CUDABuffer_<PCGScalar>* pcg_r, CUDABuffer_<PCGScalar>* pcg_M, u32 surfels_size);
+void PCGInit2CUDA(cudaStream_t stream, u32 unknown_count, u32 a_unknown_index, float a, const CUDABuffer_<PCGScalar>& pcg_r,
+                  const CUDABuffer_<PCGScalar>& pcg_M, CUDABuffer_<PCGScalar>* pcg_delta, CUDABuffer_<PCGScalar>* pcg_g,
+                  CUDABuffer_<PCGScalar>* pcg_p, CUDABuffer_<PCGScalar>* pcg_alpha_n);
+void PCGStep1CUDA(cudaStream_t stream, u32 unknown_count, const SurfelProjectionParameters& s,
+                  const DepthToColorPixelCorner& depth_to_color, const PixelCenterUnprojector& depth_unprojector,
+                  const PixelCornerProjector& color_projector, cudaTextureObject_t color_texture, u32 kf_pose_unknown_index,
+                  u32 surfel_unknown_start_index, bool optimize_poses, bool optimize_geometry, bool use_depth_residuals,
+                  bool use_descriptor_residuals, bool optimize_depth_intrinsics, bool optimize_color_intrinsics,
+                  u32 depth_intrinsics_unknown_start_index, u32 a_unknown_index, u32 color_intrinsics_unknown_start_index,
+                  CUDABuffer_<PCGScalar>* pcg_p, CUDABuffer_<PCGScalar>* pcg_g, CUDABuffer_<PCGScalar>* pcg_alpha_d, u32 surfels_size);
+void PCGStep2CUDA(cudaStream_t stream, u32 unknown_count, u32 a_unknown_index, const CUDABuffer_<PCGScalar>& pcg_r,
+                  const CUDABuffer_<PCGScalar>& pcg_M, CUDABuffer_<PCGScalar>* pcg_delta, CUDABuffer_<PCGScalar>* pcg_g,
+                  CUDABuffer_<PCGScalar>* pcg_p, CUDABuffer_<PCGScalar>* pcg_alpha_n, CUDABuffer_<PCGScalar>* pcg_alpha_d,
+                  CUDABuffer_<PCGScalar>* pcg_beta_n);
+void PCGStep3CUDA(cudaStream_t stream, u32 unknown_count, CUDABuffer_<PCGScalar>* pcg_g, CUDABuffer_<PCGScalar>* pcg_p,
+                  CUDABuffer_<PCGScalar>* pcg_alpha_n, CUDABuffer_<PCGScalar>* pcg_beta_n);
+void UpdateSurfelsFromPCGDeltaCUDA(cudaStream_t stream, u32 surfels_size, CUDABuffer_<float>* surfels, bool use_descriptor_residuals,
+                                   u32 surfel_unknown_start_index, const CUDABuffer_<PCGScalar>& pcg_delta);
+void UpdateCFactorsFromPCGDeltaCUDA(cudaStream_t stream, CUDABuffer_<float>* cfactor_buffer, u32 cfactor_unknown_start_index,
+                                    const CUDABuffer_<PCGScalar>& pcg_delta);
+}  // namespace vis
+
 namespace {
 
 struct RefKeyframe {
@@ -82,6 +113,8 @@ struct ref_context {
   // IntrinsicsOptimizationHelperBuffers (kernels.h:60-93), lazily allocated
   u32* intr_obs = nullptr; float* intr_A = nullptr; float* intr_B = nullptr; float* intr_D = nullptr;
   float* intr_b1 = nullptr; float* intr_b2 = nullptr; float* intr_H = nullptr; float* intr_b = nullptr;
+  // PCG vectors r, M, delta, g, p (direct_ba_pcg.cc:256-266) + the three scalars
+  float* pcg[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; size_t pcg_capacity = 0; float* pcg_scalars = nullptr;
 };
 
 namespace {
@@ -225,6 +258,22 @@ void UpdateSurfelActivation(ref_context* c) {
     CallDetermineActiveSurfelsKernel(c->stream, MakeProjection(c, kf, MakeFrameTGlobal(kf.pose), c->surfels_size), ActiveBuf(c));
     ++c->launches;
   }
+}
+
+// kernel_opt_geometry.cc:39-77
+void UpdateSurfelNormals(ref_context* c) {
+  if (c->surfels_size == 0) return;
+  cudaStream_t s = c->stream;
+  CallResetSurfelAccum0to3CUDAKernel(s, c->surfels_size, SurfelBuf(c), ActiveBuf(c));
+  ++c->launches;
+  for (const RefKeyframe& kf : c->kfs) {
+    if (kf.activation == 2) continue;
+    CallAccumulateSurfelNormalOptimizationCoeffsCUDAKernel(s, MakeProjection(c, kf, MakeFrameTGlobal(kf.pose), c->surfels_size),
+                                                           MakeGlobalRFrame(kf.pose), ActiveBuf(c));
+    ++c->launches;
+  }
+  CallUpdateSurfelNormalCUDAKernel(s, c->surfels_size, SurfelBuf(c), ActiveBuf(c));
+  ++c->launches;
 }
 
 // kernel_opt_geometry.cc:80-201
@@ -573,6 +622,217 @@ void ref_bundle_adjust(ref_context* c, const ref_ba_options* o, ref_ba_result* r
     DetermineCovisibleActive(c);
   }
   res->kernel_launches = c->launches - launches_before;
+}
+
+struct ref_pcg_options {
+  int optimize_poses, optimize_geometry, optimize_depth_intrinsics, optimize_color_intrinsics;
+  int min_iterations, max_iterations, max_inner_iterations, gauge_keyframe;
+};
+struct ref_pcg_result {
+  int iterations_done, converged, inner_iterations_total;
+  float last_r_norm, ms_pcg;
+  unsigned long long kernel_launches;
+};
+
+// DirectBA::BundleAdjustmentPCG (direct_ba_pcg.cc:43-819) without the surfel lifecycle branches; the gauge keyframe is an
+// argument (the reference draws rand() % K, :324).  Host-side restatement around the reference's own PCG kernels.
+void ref_bundle_adjust_pcg(ref_context* c, const ref_pcg_options* o, ref_pcg_result* res) {
+  std::memset(res, 0, sizeof(*res));
+  cudaStream_t s = c->stream;
+  const int K = static_cast<int>(c->kfs.size());
+  const u32 N = c->surfels_size;
+  const u32 P = static_cast<u32>(c->cf_w) * c->cf_h;
+  const bool use_depth = c->cfg.use_depth_residuals != 0, use_desc = c->cfg.use_descriptor_residuals != 0;
+  const bool od = o->optimize_depth_intrinsics && use_depth, oc = o->optimize_color_intrinsics && use_desc;
+  const bool op = o->optimize_poses != 0, og = o->optimize_geometry != 0;
+  const unsigned long long launches_before = c->launches;
+  constexpr u32 kInvalid = 0xffffffffu;
+  if (!c->pcg_scalars) cudaMalloc(&c->pcg_scalars, sizeof(float) * 4);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  for (int iteration = 0; iteration < o->max_iterations; ++iteration) {
+    ++res->iterations_done;
+    cudaMemsetAsync(c->active, kSurfelActiveFlag, N, s);
+    if (og) UpdateSurfelNormals(c);
+    u32 cur = 0;
+    if (op) cur += 6 * (K - 1);
+    u32 surfel_start = kInvalid, depth_start = kInvalid, a_index = kInvalid, color_start = kInvalid;
+    if (og) { surfel_start = cur; cur += (use_desc ? 3 : 1) * N; }
+    if (od) { depth_start = cur; cur += 5 + P; a_index = depth_start + 4; }
+    if (oc) { color_start = cur; cur += 4; }
+    const u32 unknown_count = cur;
+    if (unknown_count > c->pcg_capacity) {
+      for (float*& v : c->pcg) { cudaFree(v); cudaMalloc(&v, sizeof(float) * unknown_count); }
+      c->pcg_capacity = unknown_count;
+    }
+    auto vec = [&](float* ptr) { return CUDABuffer_<float>(ptr, 1, static_cast<int>(c->pcg_capacity), sizeof(float) * c->pcg_capacity); };
+    CUDABuffer_<float> pcg_r = vec(c->pcg[0]), pcg_M = vec(c->pcg[1]), pcg_delta = vec(c->pcg[2]), pcg_g = vec(c->pcg[3]),
+                       pcg_p = vec(c->pcg[4]);
+    float* sc = c->pcg_scalars;
+    CUDABuffer_<float> alpha_n(sc + 0, 1, 1, sizeof(float)), alpha_d(sc + 1, 1, 1, sizeof(float)), beta_n(sc + 2, 1, 1, sizeof(float));
+    cudaEventRecord(e0, s);
+    cudaMemsetAsync(c->pcg[0], 0, sizeof(float) * unknown_count, s);
+    cudaMemsetAsync(c->pcg[1], 0, sizeof(float) * unknown_count, s);
+    const int gauge = o->gauge_keyframe;
+    auto pose_index = [&](int id) -> u32 {
+      if (id == gauge) return kInvalid;
+      return static_cast<u32>(6 * (id < gauge ? id : id - 1));
+    };
+    const PixelCenterUnprojector unproj = CenterUnprojector(c->cfg.depth_K);
+    for (int k = 0; k < K; ++k) {
+      const RefKeyframe& kf = c->kfs[k];
+      PCGInitCUDA(s, MakeProjection(c, kf, MakeFrameTGlobal(kf.pose), N), DepthToColor(c->cfg), unproj, CornerProjector(c->cfg.color_K),
+                  kf.tex, pose_index(k), surfel_start, (k == gauge) ? false : op, og, use_depth, use_desc, od, oc, depth_start,
+                  color_start, &pcg_r, &pcg_M, N);
+      ++c->launches;
+    }
+    PCGInit2CUDA(s, unknown_count, a_index, c->a, pcg_r, pcg_M, &pcg_delta, &pcg_g, &pcg_p, &alpha_n);
+    ++c->launches;
+    float prev_r_norm = INFINITY;
+    int without_improvement = 0;
+    for (int step = 0; step < o->max_inner_iterations; ++step) {
+      cudaMemsetAsync(alpha_d.address(), 0, sizeof(float), s);
+      if (step > 0) {
+        std::swap(alpha_n, beta_n);
+        cudaMemsetAsync(c->pcg[3], 0, sizeof(float) * unknown_count, s);
+      }
+      for (int k = 0; k < K; ++k) {
+        const RefKeyframe& kf = c->kfs[k];
+        PCGStep1CUDA(s, unknown_count, MakeProjection(c, kf, MakeFrameTGlobal(kf.pose), N), DepthToColor(c->cfg), unproj,
+                     CornerProjector(c->cfg.color_K), kf.tex, pose_index(k), surfel_start, (k == gauge) ? false : op, og, use_depth,
+                     use_desc, od, oc, depth_start, a_index, color_start, &pcg_p, &pcg_g, &alpha_d, N);
+        c->launches += 2;
+      }
+      PCGStep2CUDA(s, unknown_count, a_index, pcg_r, pcg_M, &pcg_delta, &pcg_g, &pcg_p, &alpha_n, &alpha_d, &beta_n);
+      ++c->launches;
+      float r_norm;
+      cudaMemcpyAsync(&r_norm, beta_n.address(), sizeof(float), cudaMemcpyDeviceToHost, s);
+      cudaStreamSynchronize(s);
+      r_norm = std::sqrt(r_norm);
+      ++res->inner_iterations_total;
+      res->last_r_norm = r_norm;
+      if (r_norm < prev_r_norm - 1e-3) {
+        without_improvement = 0;
+      } else {
+        ++without_improvement;
+        if (without_improvement >= 3) break;
+      }
+      prev_r_norm = r_norm;
+      if (step < o->max_inner_iterations - 1) {
+        PCGStep3CUDA(s, unknown_count, &pcg_g, &pcg_p, &alpha_n, &beta_n);
+        ++c->launches;
+      }
+    }
+    cudaEventRecord(e1, s);
+    int num_converged = 0;
+    if (op) {
+      std::vector<float> delta(6 * (K - 1));
+      cudaMemcpyAsync(delta.data(), c->pcg[2], sizeof(float) * delta.size(), cudaMemcpyDeviceToHost, s);
+      cudaStreamSynchronize(s);
+      for (int k = 0; k < K; ++k) {
+        if (k == gauge) { ++num_converged; continue; }
+        float d7[7], np[7], lg[6];
+        hm_se3_exp(delta.data() + pose_index(k), d7);
+        hm_se3_mul(c->kfs[k].pose, d7, np);
+        std::memcpy(c->kfs[k].pose, np, sizeof(np));
+        hm_se3_log(d7, lg);
+        if (hm_is_scale1_pose_converged(lg)) ++num_converged;
+      }
+    }
+    if (og) {
+      CUDABuffer_<float> sb = SurfelBuf(c);
+      UpdateSurfelsFromPCGDeltaCUDA(s, N, &sb, use_desc, surfel_start, pcg_delta);
+      ++c->launches;
+    }
+    if (od) {
+      float b5[5];
+      cudaMemcpyAsync(b5, c->pcg[2] + depth_start, sizeof(b5), cudaMemcpyDeviceToHost, s);
+      cudaStreamSynchronize(s);
+      const double old_fx_inv = 1. / c->cfg.depth_K[0], old_fy_inv = 1. / c->cfg.depth_K[1];
+      const double old_cx_inv = -(c->cfg.depth_K[2] - 0.5) * old_fx_inv, old_cy_inv = -(c->cfg.depth_K[3] - 0.5) * old_fy_inv;
+      const double nfx = 1. / (old_fx_inv + b5[0]), nfy = 1. / (old_fy_inv + b5[1]);
+      const double ncx = -(nfx * (old_cx_inv + b5[2])) + 0.5, ncy = -(nfy * (old_cy_inv + b5[3])) + 0.5;
+      c->cfg.depth_K[0] = static_cast<float>(nfx); c->cfg.depth_K[1] = static_cast<float>(nfy);
+      c->cfg.depth_K[2] = static_cast<float>(ncx); c->cfg.depth_K[3] = static_cast<float>(ncy);
+      c->a += b5[4];
+      CUDABuffer_<float> cf(c->cfactor, c->cf_h, c->cf_w, c->cfactor_pitch);
+      UpdateCFactorsFromPCGDeltaCUDA(s, &cf, depth_start + 5, pcg_delta);
+      ++c->launches;
+    }
+    if (oc) {
+      float b4[4];
+      cudaMemcpyAsync(b4, c->pcg[2] + color_start, sizeof(b4), cudaMemcpyDeviceToHost, s);
+      cudaStreamSynchronize(s);
+      for (int i = 0; i < 4; ++i) c->cfg.color_K[i] = static_cast<float>(c->cfg.color_K[i] + b4[i]);
+    }
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&res->ms_pcg, e0, e1);
+    if (iteration >= o->min_iterations - 1 && (num_converged == K || !op)) {
+      res->converged = 1;
+      break;
+    }
+  }
+  cudaStreamSynchronize(s);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  res->kernel_launches = c->launches - launches_before;
+}
+
+// Parity hook: PCGInit (all keyframes) -> r, M; PCGInit2 -> p, alpha_n; one PCGStep1 sweep -> g, alpha_d.  No state changes.
+unsigned int ref_pcg_debug(ref_context* c, const ref_pcg_options* o, float* out_r, float* out_M, float* out_p, float* out_g,
+                           float* out_scalars) {
+  cudaStream_t s = c->stream;
+  const int K = static_cast<int>(c->kfs.size());
+  const u32 N = c->surfels_size;
+  const u32 P = static_cast<u32>(c->cf_w) * c->cf_h;
+  const bool use_depth = c->cfg.use_depth_residuals != 0, use_desc = c->cfg.use_descriptor_residuals != 0;
+  const bool od = o->optimize_depth_intrinsics && use_depth, oc = o->optimize_color_intrinsics && use_desc;
+  const bool op = o->optimize_poses != 0, og = o->optimize_geometry != 0;
+  constexpr u32 kInvalid = 0xffffffffu;
+  if (!c->pcg_scalars) cudaMalloc(&c->pcg_scalars, sizeof(float) * 4);
+  u32 cur = 0;
+  if (op) cur += 6 * (K - 1);
+  u32 surfel_start = kInvalid, depth_start = kInvalid, a_index = kInvalid, color_start = kInvalid;
+  if (og) { surfel_start = cur; cur += (use_desc ? 3 : 1) * N; }
+  if (od) { depth_start = cur; cur += 5 + P; a_index = depth_start + 4; }
+  if (oc) { color_start = cur; cur += 4; }
+  const u32 U = cur;
+  if (!out_r) return U;
+  if (U > c->pcg_capacity) {
+    for (float*& v : c->pcg) { cudaFree(v); cudaMalloc(&v, sizeof(float) * U); }
+    c->pcg_capacity = U;
+  }
+  auto vec = [&](float* ptr) { return CUDABuffer_<float>(ptr, 1, static_cast<int>(c->pcg_capacity), sizeof(float) * c->pcg_capacity); };
+  CUDABuffer_<float> pcg_r = vec(c->pcg[0]), pcg_M = vec(c->pcg[1]), pcg_delta = vec(c->pcg[2]), pcg_g = vec(c->pcg[3]), pcg_p = vec(c->pcg[4]);
+  float* sc = c->pcg_scalars;
+  CUDABuffer_<float> alpha_n(sc + 0, 1, 1, sizeof(float)), alpha_d(sc + 1, 1, 1, sizeof(float));
+  cudaMemsetAsync(c->pcg[0], 0, sizeof(float) * U, s);
+  cudaMemsetAsync(c->pcg[1], 0, sizeof(float) * U, s);
+  const int gauge = o->gauge_keyframe;
+  auto pose_index = [&](int id) -> u32 { return id == gauge ? kInvalid : static_cast<u32>(6 * (id < gauge ? id : id - 1)); };
+  const PixelCenterUnprojector unproj = CenterUnprojector(c->cfg.depth_K);
+  for (int k = 0; k < K; ++k) {
+    const RefKeyframe& kf = c->kfs[k];
+    PCGInitCUDA(s, MakeProjection(c, kf, MakeFrameTGlobal(kf.pose), N), DepthToColor(c->cfg), unproj, CornerProjector(c->cfg.color_K),
+                kf.tex, pose_index(k), surfel_start, (k == gauge) ? false : op, og, use_depth, use_desc, od, oc, depth_start, color_start,
+                &pcg_r, &pcg_M, N);
+  }
+  cudaMemcpyAsync(out_r, c->pcg[0], sizeof(float) * U, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(out_M, c->pcg[1], sizeof(float) * U, cudaMemcpyDeviceToHost, s);
+  PCGInit2CUDA(s, U, a_index, c->a, pcg_r, pcg_M, &pcg_delta, &pcg_g, &pcg_p, &alpha_n);
+  cudaMemcpyAsync(out_p, c->pcg[4], sizeof(float) * U, cudaMemcpyDeviceToHost, s);
+  cudaMemsetAsync(alpha_d.address(), 0, sizeof(float), s);
+  for (int k = 0; k < K; ++k) {
+    const RefKeyframe& kf = c->kfs[k];
+    PCGStep1CUDA(s, U, MakeProjection(c, kf, MakeFrameTGlobal(kf.pose), N), DepthToColor(c->cfg), unproj, CornerProjector(c->cfg.color_K),
+                 kf.tex, pose_index(k), surfel_start, (k == gauge) ? false : op, og, use_depth, use_desc, od, oc, depth_start, a_index,
+                 color_start, &pcg_p, &pcg_g, &alpha_d, N);
+  }
+  cudaMemcpyAsync(out_g, c->pcg[3], sizeof(float) * U, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(out_scalars, sc, sizeof(float) * 2, cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+  return U;
 }
 
 // Device-side snapshot / restore of the mutable state (surfel data rows, poses, activations) for benchmarking

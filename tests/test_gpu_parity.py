@@ -200,8 +200,10 @@ def test_edge_cases(mods, tiny_scene):
     from badslam_b200._lib import BadBAError
     with pytest.raises(BadBAError):
         ba.BundleAdjustment(None, False, False, True, True, True, 1, 1)      # do_surfel_updates
+    with pytest.raises(BadBAError):   # gauge keyframe out of range / more keyframes than pcg_max_keyframes (direct_ba_pcg.cc:232)
+        ba.BundleAdjustment(None, False, False, False, True, True, 1, 1, use_pcg=True, pcg_gauge_keyframe=sc.cfg.num_keyframes)
     with pytest.raises(BadBAError):
-        ba.BundleAdjustment(None, False, False, False, True, True, 1, 1, use_pcg=True)
+        ba.BundleAdjustment(None, False, False, False, True, True, 1, 1, use_pcg=True, pcg_max_keyframes=1)
 
 
 def test_host_buffer_entry_points(mods, tiny_scene):
@@ -309,7 +311,7 @@ def test_intrinsics_step_three_way(mods, opt_depth, opt_color):
     assert np.all(np.abs(d0 - d1) < tol_d), (d0, d1)
     assert np.all(np.abs(c0 - c1) < REL * np.abs(c1) + 1e-3), (c0, c1)
     assert abs(a0 - a1) < 1e-5
-    assert np.all(np.abs(d0 - d2) < tol_d) and np.all(np.abs(c0 - c2) < REL * np.abs(c2) + 1e-3) and abs(a0 - a2) < 1e-5
+    assert np.all(np.abs(d0 - d2) < tol_d) and np.all(np.abs(c0 - c2) < REL * np.abs(c2) + 1e-3) and abs(a0 - a2) < 1e-4
     cf0, cf1 = ba.cfactor_buffer(), ref.cfactor()
     if opt_depth:
         assert np.any(d0 != np.asarray(sc.depth_K, np.float32)) and np.any(cf0 != cf_init) and abs(a0 - a_init) > 1e-3
@@ -344,3 +346,128 @@ def test_bundle_adjustment_with_intrinsics(mods):
         dt, dr = S.pose_error(ba.keyframes()[k].global_T_frame(), ref.pose(k))
         assert dt < 2e-5 + 3 * self_noise and dr < 2e-5 + 3 * self_noise, (k, dt, dr, self_noise)
     assert np.any(d0 != np.asarray(sc.depth_K, np.float32)) and np.any(c0 != np.asarray(sc.color_K, np.float32))
+
+
+def _segments(K, n, stride, total):
+    segs = {"pose": (0, 6 * (K - 1)), "surfel": (6 * (K - 1), 6 * (K - 1) + stride * n)}
+    if total > segs["surfel"][1]:
+        segs["intr"] = (segs["surfel"][1], total)
+    return segs
+
+
+@pytest.mark.parametrize("name,distort,intr,use_desc,a_init", [("tiny", False, False, True, 0.0), ("tiny", False, False, False, 0.0),
+                                                                ("small", True, True, True, 0.02)])
+def test_pcg_building_blocks_three_way(mods, name, distort, intr, use_desc, a_init):
+    """PCGInit / PCGInit2 / PCGStep1 (kernel_pcg.cu:179-1037): r, M, p0, g = J^T W J p0, alpha_n, alpha_d."""
+    import dataclasses
+    S, DirectBA, O, R = mods
+    cfg = S.config_by_name(name)
+    if distort:
+        cfg = dataclasses.replace(cfg, depth_a=0.03, cfactor=0.005)
+    sc = S.make_scene(cfg)
+    K, n = cfg.num_keyframes, sc.num_surfels
+    ba = DirectBA.from_scene(sc, use_descriptor_residuals=use_desc)
+    ref, orc = R.RefDirectBA(sc, True, use_desc), O.Oracle(sc, True, use_desc)
+    if a_init:
+        cf = (np.random.default_rng(5).standard_normal(sc.cfactor.shape) * 0.003).astype(np.float32)
+        ba.SetA(a_init); ba.SetCFactorBuffer(cf)
+        ref.set_depth_params(a_init, cf)
+        orc.model.a = a_init; orc.cfactor[:] = cf
+    kw = dict(optimize_depth_intrinsics=intr, optimize_color_intrinsics=intr, gauge_keyframe=1)
+    ours, theirs, cpu = ba.PCGDebug(**kw), ref.pcg_debug(**kw), orc.pcg_debug(**kw)
+    assert len(ours[0]) == len(theirs[0]) == len(cpu[0]) == 6 * (K - 1) + (3 if use_desc else 1) * n + ((5 + sc.cfactor.size + 4) if intr else 0)
+    for idx, what in enumerate(("r", "M", "p", "g")):
+        for seg, (lo, hi) in _segments(K, n, 3 if use_desc else 1, len(ours[0])).items():
+            scale = np.abs(theirs[idx][lo:hi]).max()
+            d = np.abs(ours[idx][lo:hi].astype(np.float64) - theirs[idx][lo:hi]).max() / scale
+            assert d < 5e-5, (what, seg, d)      # vs the reference's kernels: fp32 summation order only
+            if seg != "surfel":                  # oracle (software texture filter, threshold flips): aggregated entries only
+                dc = np.abs(cpu[idx][lo:hi].astype(np.float64) - theirs[idx][lo:hi]).max() / scale
+                assert dc < 1e-3, (what, seg, dc)
+    assert np.all(np.abs(ours[4] - theirs[4]) < 1e-5 * np.abs(theirs[4]))
+    assert np.all(np.abs(cpu[4] - theirs[4]) < 1e-4 * np.abs(theirs[4]))
+    assert np.all(ours[1] >= 0) and ours[4][1] > 0   # M = diag(J^T W J) >= 0, p^T A p > 0
+
+
+def test_pcg_bundle_adjustment_against_reference(mods, small_scene):
+    """use_pcg = true (direct_ba_pcg.cc:43-819).  A few inner steps: tight parity.  Full solve: CG in fp32 is not reproducible
+    across summation orders (loss of conjugacy amplifies 1e-7 differences), so the bar is the quality of the solution."""
+    S, DirectBA, O, R = mods
+    sc = small_scene
+    K = sc.cfg.num_keyframes
+    # (1) 4 inner steps per outer iteration
+    ba, ref, ref2 = DirectBA.from_scene(sc), R.RefDirectBA(sc), R.RefDirectBA(sc)
+    ro = ba.BundleAdjustment(None, False, False, False, True, True, 2, 2, use_pcg=True, pcg_max_inner_iterations=4, pcg_gauge_keyframe=2)
+    rr = ref.bundle_adjust_pcg(min_iterations=2, max_iterations=2, max_inner_iterations=4, gauge_keyframe=2)
+    ref2.bundle_adjust_pcg(min_iterations=2, max_iterations=2, max_inner_iterations=4, gauge_keyframe=2)
+    assert ro.iterations_done == rr.iterations_done == 2 and ro.pcg_inner_iterations_total == rr.inner_iterations_total == 8
+    assert abs(ro.pcg_last_r_norm - rr.last_r_norm) < 1e-3 * rr.last_r_norm
+    noise = max(max(S.pose_error(ref.pose(k), ref2.pose(k))) for k in range(K))
+    pa = ba.GetKeyframeStates()[0]
+    assert np.array_equal(pa[2], sc.poses_init[2])     # the gauge keyframe does not move
+    for k in range(K):
+        dt, dr = S.pose_error(pa[k], ref.pose(k))
+        assert dt < 1e-5 + 3 * noise and dr < 1e-5 + 3 * noise, (k, dt, dr, noise)
+    a, b_ = ba.GetSurfelsHost(), ref.surfels()
+    assert np.abs(a[:3] - b_[:3]).max() < 1e-4 and np.abs(a[:3] - b_[:3]).mean() < 1e-6      # 8 fp32 CG steps
+    assert (a[3].view(np.uint32) != b_[3].view(np.uint32)).mean() < 1e-4   # second normals update sees 1e-6-different positions
+    # (2) full solves: same quality as the reference
+    ba, ref = DirectBA.from_scene(sc), R.RefDirectBA(sc)
+    ro = ba.BundleAdjustment(None, False, False, False, True, True, 3, 3, use_pcg=True, pcg_gauge_keyframe=0)
+    rr = ref.bundle_adjust_pcg(min_iterations=3, max_iterations=3, gauge_keyframe=0)
+    def rel_err(poses):
+        e = []
+        for k in range(1, K):
+            x = O.se3_mul(O.se3_inverse(poses[0]), poses[k])
+            y = O.se3_mul(O.se3_inverse(sc.poses_true[0]), sc.poses_true[k])
+            e.append(max(S.pose_error(x, y)))
+        return max(e)
+    e0, eo, er = rel_err(sc.poses_init), rel_err(ba.GetKeyframeStates()[0]), rel_err(ref.poses())
+    assert eo < 0.5 * e0 and eo < 1.5 * er + 1e-4, (e0, eo, er)
+    assert ro.kernel_launches < rr.kernel_launches / 3
+
+
+def test_intrinsics_and_pcg_against_golden_fixture(mods):
+    """The CUDA path against tests/golden/tiny_intrinsics_pcg.npz (outputs of the reference's kernels, tools/make_golden.py)."""
+    from test_oracle_pcg import distorted_scene
+    S, DirectBA, O, R = mods
+    g = np.load(os.path.join(GOLDEN, "tiny_intrinsics_pcg.npz"))
+    sc, a_init, cf_init = distorted_scene("tiny")
+    K, n = sc.cfg.num_keyframes, sc.num_surfels
+
+    def fresh():
+        ba = DirectBA.from_scene(sc)
+        ba.SetA(a_init); ba.SetCFactorBuffer(cf_init)
+        return ba
+
+    ba = fresh()
+    for step in range(2):
+        ba.OptimizeIntrinsics(True, True)
+        d, c, a = ba._intrinsics()
+        assert np.abs(d - g[f"intr{step}_depth_K"]).max() < 1e-3 and np.abs(c - g[f"intr{step}_color_K"]).max() < 1e-3
+        assert abs(a - float(g[f"intr{step}_a"])) < 1e-5 and np.abs(ba.cfactor_buffer() - g[f"intr{step}_cfactor"]).max() < 1e-5
+    for intr in (False, True):
+        tag = "pcgi" if intr else "pcg"
+        ba = fresh()
+        r, M, p, gv, scal = ba.PCGDebug(optimize_depth_intrinsics=intr, optimize_color_intrinsics=intr, gauge_keyframe=1)
+        lo, hi = 6 * (K - 1), 6 * (K - 1) + 3 * n
+        for nm, v in (("r", r), ("M", M), ("p", p), ("g", gv)):
+            ref = g[f"{tag}_{nm}_pose"]
+            assert np.abs(v[:lo] - ref).max() < 5e-5 * np.abs(ref).max(), (tag, nm)
+            assert abs(v[lo:hi].astype(np.float64).sum() - float(g[f"{tag}_{nm}_surfel_sum"])) < 1e-5 * float(g[f"{tag}_{nm}_surfel_abs"])
+            if intr:
+                ref = g[f"{tag}_{nm}_intr"]
+                assert np.abs(v[hi:] - ref).max() < 5e-5 * np.abs(ref).max(), (tag, nm)
+        assert np.all(np.abs(scal - g[f"{tag}_scalars"]) < 1e-5 * np.abs(g[f"{tag}_scalars"]))
+        res = ba.BundleAdjustment(None, intr, intr, False, True, True, 2, 2, use_pcg=True, pcg_max_inner_iterations=4, pcg_gauge_keyframe=1)
+        assert res.pcg_inner_iterations_total == 8
+        noise = max(max(S.pose_error(g[f"{tag}_ba_poses"][k], g[f"{tag}_ba_poses_rerun"][k])) for k in range(K))
+        pa = ba.GetKeyframeStates()[0]
+        for k in range(K):
+            dt, dr = S.pose_error(pa[k], g[f"{tag}_ba_poses"][k])
+            assert dt < 2e-5 + 3 * noise and dr < 2e-5 + 3 * noise, (tag, k, dt, dr, noise)
+        assert abs(res.pcg_last_r_norm - float(g[f"{tag}_ba_r_norm"])) < 5e-3 * float(g[f"{tag}_ba_r_norm"])
+        if intr:
+            d, c, a = ba._intrinsics()
+            assert np.abs(d - g["pcgi_ba_depth_K"]).max() < 2e-3 and np.abs(c - g["pcgi_ba_color_K"]).max() < 2e-3
+            assert abs(a - float(g["pcgi_ba_a"])) < 5e-4

@@ -54,8 +54,65 @@ def golden_for(name, use_depth=True, use_desc=True, tag=""):
     print("wrote", name, tag, "counts", out["pose_count"][:4], "ba_count", out["ba_count"])
 
 
+def distorted_scene(name="tiny"):
+    """Scene with a depth deformation in the raw depth, perturbed camera estimates and a non-zero deformation model."""
+    import dataclasses
+    sc = make_scene(dataclasses.replace(config_by_name(name), depth_a=0.03, cfactor=0.005))
+    sc.depth_K = (np.asarray(sc.depth_K, np.float32) * np.float32([1.003, 0.998, 1.002, 0.997])).astype(np.float32)
+    sc.color_K = (np.asarray(sc.color_K, np.float32) * np.float32([0.998, 1.002, 1.001, 0.999])).astype(np.float32)
+    a_init = 0.02
+    cf_init = (np.random.default_rng(5).standard_normal(sc.cfactor.shape) * 0.003).astype(np.float32)
+    return sc, a_init, cf_init
+
+
+def golden_intrinsics_pcg(name="tiny"):
+    """OptimizeIntrinsicsCUDA and the PCG solver's building blocks / short solves from the reference's kernels."""
+    sc, a_init, cf_init = distorted_scene(name)
+    K, n = sc.cfg.num_keyframes, sc.num_surfels
+    out = {"scene": name, "surfel_checksum": float(np.sum(sc.surfels[:3, :n].astype(np.float64)))}
+    ref = ref_cuda.RefDirectBA(sc)
+    ref.set_depth_params(a_init, cf_init)
+    for step in range(2):
+        ref.optimize_intrinsics(True, True)
+        d, c, a = ref.intrinsics()
+        out[f"intr{step}_depth_K"], out[f"intr{step}_color_K"], out[f"intr{step}_a"] = d, c, np.float32(a)
+        out[f"intr{step}_cfactor"] = ref.cfactor()
+    ref.close()
+    for intr in (False, True):
+        ref = ref_cuda.RefDirectBA(sc)
+        ref.set_depth_params(a_init, cf_init)
+        r, M, p, g, scal = ref.pcg_debug(optimize_depth_intrinsics=intr, optimize_color_intrinsics=intr, gauge_keyframe=1)
+        tag = "pcgi" if intr else "pcg"
+        lo, hi = 6 * (K - 1), 6 * (K - 1) + 3 * n
+        for nm, v in (("r", r), ("M", M), ("p", p), ("g", g)):
+            out[f"{tag}_{nm}_pose"] = v[:lo].copy()
+            out[f"{tag}_{nm}_surfel_sum"] = np.float64(v[lo:hi].astype(np.float64).sum())
+            out[f"{tag}_{nm}_surfel_abs"] = np.float64(np.abs(v[lo:hi].astype(np.float64)).sum())
+            if intr:
+                out[f"{tag}_{nm}_intr"] = v[hi:].copy()
+        out[f"{tag}_scalars"] = scal
+        res = ref.bundle_adjust_pcg(True, True, intr, intr, 2, 2, 4, 1)
+        out[f"{tag}_ba_poses"], out[f"{tag}_ba_r_norm"] = ref.poses(), np.float32(res.last_r_norm)
+        out[f"{tag}_ba_surfels"] = ref.surfels()[[0, 1, 2, 6, 7]].copy()
+        if intr:
+            d, c, a = ref.intrinsics()
+            out["pcgi_ba_depth_K"], out["pcgi_ba_color_K"], out["pcgi_ba_a"] = d, c, np.float32(a)
+        ref2 = ref_cuda.RefDirectBA(sc)
+        ref2.set_depth_params(a_init, cf_init)
+        ref2.bundle_adjust_pcg(True, True, intr, intr, 2, 2, 4, 1)
+        out[f"{tag}_ba_poses_rerun"] = ref2.poses()
+        ref.close(); ref2.close()
+    os.makedirs("gpurun_out/golden", exist_ok=True)
+    np.savez_compressed(f"gpurun_out/golden/{name}_intrinsics_pcg.npz", **out)
+    print("wrote", name, "intrinsics + pcg", out["intr1_depth_K"], out["pcg_scalars"], out["pcgi_scalars"])
+
+
 if __name__ == "__main__":
+    if "--extra-only" in sys.argv:
+        golden_intrinsics_pcg("tiny")
+        sys.exit(0)
     golden_for("cfg1")
     golden_for("tiny")
     golden_for("tiny", True, False, "_depth_only")
     golden_for("tiny", False, True, "_desc_only")
+    golden_intrinsics_pcg("tiny")
