@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbadba_b200.so")
+# BADBA_LIB: development override for A/B runs of kernel variants (tools/ab_bench.sh); the product is the in-tree library
+LIB_PATH = os.environ.get("BADBA_LIB") or os.path.join(HERE, "libbadba_b200.so")
 
 OK, ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED, ERR_NO_DEVICE = range(6)
 STATUS_NAMES = {0: "BBA_OK", 1: "BBA_ERR_INVALID_ARGUMENT", 2: "BBA_ERR_CUDA", 3: "BBA_ERR_STATE",
@@ -100,7 +101,9 @@ SYMBOLS = {
     "bba_pcg_debug": (C.c_int, [_P, C.POINTER(BAOptions), C.POINTER(C.c_uint32), _P, _P, _P, _P, _P, _P]),
     "bba_bundle_adjust": (C.c_int, [_P, C.POINTER(BAOptions), C.POINTER(BAResult), _P]),
     "bba_set_collective": (C.c_int, [_P, COLLECTIVE_FN, _P]),
-    "bba_shard_surfel_range": (None, [C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "bba_shard_surfel_owner": (C.c_int, [C.c_uint32, C.c_int]),
+    "bba_shard_surfel_local_index": (C.c_uint32, [C.c_uint32, C.c_int]),
+    "bba_shard_slice_length": (C.c_uint32, [C.c_uint32, C.c_int]),
     "bba_shard_keyframe_owner": (C.c_int, [C.c_int, C.c_int]),
     "bba_kernel_launch_count": (C.c_uint64, [_P]),
     "bba_update_keyframe_host": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),

@@ -215,6 +215,9 @@ struct bba_context {
 
   uint64_t launches = 0;
   int ba_iteration_count = 0;
+  // predicted cost of one pose step per keyframe (Gauss-Newton iterations x per-evaluation cost of the last step it took
+  // part in); 0 = unknown.  Identical on every rank; drives the keyframe -> rank assignment of the pose step.
+  std::vector<float> kf_cost;
 
   // profiling (bba_set_profiling)
   int profiling = 0;   // 0 off, 1 event timing, 2 event timing + byte-model counters in every iteration
@@ -318,6 +321,37 @@ bba_status CheckSurfels(bba_handle h) {
 // `init` poses.  On return (stream synchronised) h_pose_est / h_iterations / h_converged / h_first_stats hold the results.
 bba_status CheckCollective(bba_handle h);
 
+// Keyframe -> rank assignment of a pose step.  Without statistics: round-robin over the work list
+// (bba_shard_keyframe_owner).  With the statistics of the previous pose step (replicated, hence identical on all ranks):
+// longest-processing-time-first onto the least loaded rank, so that the ranks finish their Gauss-Newton loops together.
+void AssignKeyframes(bba_handle h, const std::vector<int>& ids, std::vector<int>* owner) {
+  const int world = h->cfg.world_size, n = static_cast<int>(ids.size());
+  double known_sum = 0;
+  int known = 0;
+  for (int kf : ids)
+    if (kf < static_cast<int>(h->kf_cost.size()) && h->kf_cost[kf] > 0) { known_sum += h->kf_cost[kf]; ++known; }
+  if (known == 0) {
+    for (int i = 0; i < n; ++i) (*owner)[i] = i % world;
+    return;
+  }
+  const double fallback = known_sum / known;
+  std::vector<std::pair<double, int>> order(n);
+  for (int i = 0; i < n; ++i) {
+    const int kf = ids[i];
+    const double c = (kf < static_cast<int>(h->kf_cost.size()) && h->kf_cost[kf] > 0) ? h->kf_cost[kf] : fallback;
+    order[i] = {-c, i};
+  }
+  std::sort(order.begin(), order.end());   // descending cost, ties by list position
+  std::vector<double> load(world, 0.0);
+  for (const auto& e : order) {
+    int best = 0;
+    for (int r = 1; r < world; ++r)
+      if (load[r] < load[best]) best = r;
+    (*owner)[e.second] = best;
+    load[best] -= e.first;
+  }
+}
+
 bba_status RunPoseStep(bba_handle h, const std::vector<int>& ids, const std::vector<Pose>& init, int max_iterations, cudaStream_t s) {
   const int K = static_cast<int>(h->keyframes.size());
   const int n = static_cast<int>(ids.size());
@@ -327,16 +361,18 @@ bba_status RunPoseStep(bba_handle h, const std::vector<int>& ids, const std::vec
     FillKfDevice(h->keyframes[k], h->keyframes[k].pose, h->h_kfs + k);
     PoseToArray(h->keyframes[k].pose, h->h_pose_est + 7 * k);
   }
-  // Multi-GPU: the work list is dealt round-robin to the ranks; every rank runs the Gauss-Newton loops of its own
+  // Multi-GPU: the work list is dealt to the ranks (AssignKeyframes); every rank runs the Gauss-Newton loops of its own
   // keyframes and the results are published with one sum all-reduce over disjoint slots (below).
   const int world = h->cfg.world_size, rank = h->cfg.rank;
   if (bba_status st = CheckCollective(h)) return st;
+  std::vector<int> owner(n, 0);
+  if (world > 1) AssignKeyframes(h, ids, &owner);
   std::vector<int> local;
   local.reserve(n);
   for (int i = 0; i < n; ++i) {
     FillKfDevice(h->keyframes[ids[i]], init[i], h->h_kfs + ids[i]);
     PoseToArray(init[i], h->h_pose_est + 7 * ids[i]);
-    if (world == 1 || i % world == rank) {
+    if (owner[i] == rank) {
       h->h_work[local.size()] = ids[i];
       local.push_back(ids[i]);
     }
@@ -436,6 +472,11 @@ bba_status RunPoseStep(bba_handle h, const std::vector<int>& ids, const std::vec
       for (int j = 0; j < 8; ++j) h->h_first_stats[8 * kf + j] = slot[9 + j];
     }
   }
+  // cost model for the next assignment: a culled pair costs ~6 % of a pair that projects into the image
+  if (h->kf_cost.size() < static_cast<size_t>(K)) h->kf_cost.resize(h->cfg.max_keyframes, 0.f);
+  for (int kf : ids)
+    h->kf_cost[kf] = static_cast<float>(std::max(1, h->h_iterations[kf]) *
+                                        (0.06 * h->surfels_size + h->h_first_stats[8 * kf + 5]));
   if (h->profiling && h->surfels_size > 0) {
     int real_iterations = 0;   // iterations that had a non-empty work list
     for (int kf : local) real_iterations = std::max(real_iterations, h->h_iterations[kf]);
@@ -456,14 +497,14 @@ bba_status RunPoseStep(bba_handle h, const std::vector<int>& ids, const std::vec
 }
 
 // ---- multi-GPU sharding (one process per GPU) --------------------------------------------------------------------
-void ShardSurfelRange(uint32_t n, int rank, int world, uint32_t* begin, uint32_t* end, uint32_t* shard_len) {
-  const uint32_t tiles = (n + 255u) / 256u;
-  const uint32_t tiles_per_rank = (tiles + world - 1) / world;
-  const uint32_t len = tiles_per_rank * 256u;
-  const uint64_t b = static_cast<uint64_t>(len) * rank, e = b + len;
-  *begin = static_cast<uint32_t>(std::min<uint64_t>(b, n));
-  *end = static_cast<uint32_t>(std::min<uint64_t>(e, n));
-  if (shard_len) *shard_len = len;
+// 256-surfel granules dealt round-robin (kernels.cuh SurfelShardToGlobal).  local_cap: size of this rank's local index space
+// (a multiple of 256; the last granule may reach past n); shard_len: the same for rank 0 = slice length of the exchange.
+void ShardSurfels(uint32_t n, int rank, int world, uint32_t* local_cap, uint32_t* shard_len) {
+  const uint32_t granules = (n + 255u) / 256u;
+  const uint32_t w = static_cast<uint32_t>(std::max(world, 1)), r = static_cast<uint32_t>(rank);
+  const uint32_t mine = granules > r ? (granules - r + w - 1) / w : 0;
+  if (local_cap) *local_cap = (world <= 1) ? n : mine * 256u;
+  if (shard_len) *shard_len = ((granules + w - 1) / w) * 256u;
 }
 
 bba_status CheckCollective(bba_handle h) {
@@ -476,20 +517,20 @@ bba_status CheckCollective(bba_handle h) {
 bba_status ExchangeGeometry(bba_handle h, cudaStream_t s) {
   if (h->cfg.world_size <= 1 || h->surfels_size == 0) return BBA_OK;
   const int world = h->cfg.world_size, rank = h->cfg.rank;
-  uint32_t begin, end, shard_len;
-  ShardSurfelRange(h->surfels_size, rank, world, &begin, &end, &shard_len);
+  uint32_t shard_len;
+  ShardSurfels(h->surfels_size, rank, world, nullptr, &shard_len);
   const size_t need = static_cast<size_t>(world) * bba::kShardRows * shard_len;
   if (need > h->exchange_floats) {
     cudaFree(h->d_exchange);
     h->d_exchange = nullptr;
-    uint32_t b2, e2, max_len;
-    ShardSurfelRange(std::max(h->cfg.max_surfel_count, h->surfels_size), 0, world, &b2, &e2, &max_len);
+    uint32_t max_len;
+    ShardSurfels(std::max(h->cfg.max_surfel_count, h->surfels_size), 0, world, nullptr, &max_len);
     h->exchange_floats = static_cast<size_t>(world) * bba::kShardRows * max_len;
     BBA_CUDA(h, cudaMalloc(&h->d_exchange, sizeof(float) * h->exchange_floats));
   }
   const uint32_t pitch = static_cast<uint32_t>(h->surfel_pitch_bytes / sizeof(float));
   const size_t slice_floats = static_cast<size_t>(bba::kShardRows) * shard_len;
-  bba::LaunchPackShard(h->surfels, pitch, h->active, begin, end, shard_len, h->d_exchange + slice_floats * rank, s);
+  bba::LaunchPackShard(h->surfels, pitch, h->active, h->surfels_size, rank, world, shard_len, h->d_exchange + slice_floats * rank, s);
   h->collective(h->collective_user, BBA_COLLECTIVE_ALLGATHER, h->d_exchange, slice_floats * sizeof(float), s);
   bba::LaunchUnpackShards(h->surfels, pitch, h->active, h->surfels_size, shard_len, world, rank, h->d_exchange, s);
   h->launches += 2;
@@ -519,8 +560,9 @@ bba_status BuildGeometryArgs(bba_handle h, bba::GeometryArgs* g, cudaStream_t s)
   g->pitch = static_cast<uint32_t>(h->surfel_pitch_bytes / sizeof(float));
   g->n = h->surfels_size;
   g->begin = 0;
-  g->end = h->surfels_size;
-  if (h->cfg.world_size > 1) ShardSurfelRange(h->surfels_size, h->cfg.rank, h->cfg.world_size, &g->begin, &g->end, nullptr);
+  g->shard_rank = static_cast<uint32_t>(h->cfg.rank);
+  g->shard_world = static_cast<uint32_t>(h->cfg.world_size);
+  ShardSurfels(h->surfels_size, h->cfg.rank, h->cfg.world_size, &g->end, nullptr);
   g->active = h->active;
   g->kfs = h->d_kfs;
   g->kf_list = h->d_geo_list;
@@ -566,9 +608,11 @@ bba_status OptimizeIntrinsics(bba_handle h, bool opt_depth, bool opt_color, cuda
   a.cam = MakeCamera(h);
   a.surfels = h->surfels;
   a.pitch = static_cast<uint32_t>(h->surfel_pitch_bytes / sizeof(float));
+  a.n = h->surfels_size;
   a.begin = 0;
-  a.end = h->surfels_size;
-  if (h->cfg.world_size > 1) ShardSurfelRange(h->surfels_size, h->cfg.rank, h->cfg.world_size, &a.begin, &a.end, nullptr);
+  a.shard_rank = static_cast<uint32_t>(h->cfg.rank);
+  a.shard_world = static_cast<uint32_t>(h->cfg.world_size);
+  ShardSurfels(h->surfels_size, h->cfg.rank, h->cfg.world_size, &a.end, nullptr);
   a.kfs = h->d_kfs;
   a.kf_list = h->d_all_list;
   a.kf_count = K;
@@ -1526,11 +1570,20 @@ bba_status bba_set_collective(bba_handle h, bba_collective_fn fn, void* user) {
   return BBA_OK;
 }
 
-void bba_shard_surfel_range(uint32_t surfels_size, int rank, int world_size, uint32_t* begin, uint32_t* end) {
-  uint32_t b = 0, e = surfels_size;
-  if (world_size > 1 && rank >= 0 && rank < world_size) ShardSurfelRange(surfels_size, rank, world_size, &b, &e, nullptr);
-  if (begin) *begin = b;
-  if (end) *end = e;
+int bba_shard_surfel_owner(uint32_t surfel_index, int world_size) {
+  return world_size > 1 ? static_cast<int>((surfel_index >> bba::kShardGranuleShift) % static_cast<uint32_t>(world_size)) : 0;
+}
+
+uint32_t bba_shard_surfel_local_index(uint32_t surfel_index, int world_size) {
+  if (world_size <= 1) return surfel_index;
+  const uint32_t g = surfel_index >> bba::kShardGranuleShift;
+  return ((g / static_cast<uint32_t>(world_size)) << bba::kShardGranuleShift) | (surfel_index & ((1u << bba::kShardGranuleShift) - 1u));
+}
+
+uint32_t bba_shard_slice_length(uint32_t surfels_size, int world_size) {
+  uint32_t len = 0;
+  ShardSurfels(surfels_size, 0, world_size, nullptr, &len);
+  return len;
 }
 
 int bba_shard_keyframe_owner(int list_index, int world_size) { return world_size > 1 ? list_index % world_size : 0; }

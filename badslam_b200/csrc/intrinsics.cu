@@ -88,8 +88,9 @@ __global__ void __launch_bounds__(kThreads) IntrinsicsAccumulateKernel(const __g
     for (int i = 0; i < 32; ++i) acc[i] = 0.f;
     float extra0 = 0.f, extra1 = 0.f;   // sums 32, 33
     for (uint32_t sub = 0; sub < kTile / 32; ++sub) {
-      const uint32_t i = a.begin + tile * kTile + sub * 32 + lane;
-      if (i >= a.end) continue;
+      const uint32_t li = a.begin + tile * kTile + sub * 32 + lane;
+      const uint32_t i = SurfelShardToGlobal(li, a.shard_rank, a.shard_world);
+      if (li >= a.end || i >= a.n) continue;
       const Vec3 gp = V3(a.surfels[kRowX * P + i], a.surfels[kRowY * P + i], a.surfels[kRowZ * P + i]);
       const Vec3 nrm = UnpackNormal(__float_as_uint(a.surfels[kRowNormal * P + i]));
       float radius_sq = 0.f, d1 = 0.f, d2 = 0.f;

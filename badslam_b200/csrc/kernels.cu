@@ -111,6 +111,9 @@ __device__ __forceinline__ float WarpTransposeReduce(float (&v)[32], int lane) {
   return v[0];
 }
 
+#ifndef BBA_POSE_MIN_CTAS
+#define BBA_POSE_MIN_CTAS 2   // resident CTAs per SM the register allocation is tuned for
+#endif
 constexpr int kPoseThreads = 256;
 constexpr int kPoseWarps = kPoseThreads / 32;
 constexpr int kPoseStagedRows = 7;   // x y z normal radius^2 d1 d2
@@ -124,7 +127,7 @@ constexpr int kPoseGroup = 8;        // keyframes per work item
 // STATS: also produce the residual costs and the stage counters of the byte model (the reference computes its
 // residual count / cost only in debug mode, kernel_opt_pose.cu:312-320,373-381).
 template <int TILE, bool STATS>
-__global__ void __launch_bounds__(kPoseThreads, 2) PoseAccumulateKernel(const __grid_constant__ PoseAccumulateArgs args) {
+__global__ void __launch_bounds__(kPoseThreads, BBA_POSE_MIN_CTAS) PoseAccumulateKernel(const __grid_constant__ PoseAccumulateArgs args) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stage_base = reinterpret_cast<float*>(smem_raw);   // [2][7][TILE]
   __shared__ __align__(8) uint64_t full_bar[2];
@@ -301,14 +304,14 @@ static void LaunchPoseAccumulateT(const PoseAccumulateArgs& args, int sm_count, 
     cudaFuncSetAttribute(PoseAccumulateKernel<TILE, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     configured = true;
   }
-  PoseAccumulateKernel<TILE, STATS><<<2 * sm_count, kPoseThreads, smem, stream>>>(args);   // persistent: 2 CTAs per SM
+  PoseAccumulateKernel<TILE, STATS><<<BBA_POSE_MIN_CTAS * sm_count, kPoseThreads, smem, stream>>>(args);   // persistent
 }
 
 template <bool STATS>
 static void LaunchPoseAccumulateS(const PoseAccumulateArgs& args, int sm_count, cudaStream_t stream) {
   // Tile size: as large as possible (one TMA transaction + one CTA barrier per item), but small enough that a
   // keyframe group still yields several items per resident CTA.
-  const uint64_t slots = static_cast<uint64_t>(2 * sm_count) * 4;
+  const uint64_t slots = static_cast<uint64_t>(BBA_POSE_MIN_CTAS * sm_count) * 4;
   if (args.n >= slots * 1024) LaunchPoseAccumulateT<1024, STATS>(args, sm_count, stream);
   else if (args.n >= slots * 512) LaunchPoseAccumulateT<512, STATS>(args, sm_count, stream);
   else LaunchPoseAccumulateT<256, STATS>(args, sm_count, stream);
@@ -380,8 +383,9 @@ __global__ void __launch_bounds__(kGeoThreads) ActivationNormalsKernel(const __g
     const bool first = group == 0, last = group + 1 == n_groups;
     const int j_begin = group * kGeoGroup, j_end = min(a.kf_count, static_cast<int>(group + 1) * kGeoGroup);
     for (uint32_t sub = 0; sub < tile_len / 32; ++sub) {
-      const uint32_t i = a.begin + (tile << a.tile_shift) + sub * 32 + lane;
-      if (i >= a.end) continue;
+      const uint32_t li = a.begin + (tile << a.tile_shift) + sub * 32 + lane;
+      const uint32_t i = SurfelShardToGlobal(li, a.shard_rank, a.shard_world);
+      if (li >= a.end || i >= a.n) continue;
       const uint8_t flags = a.active[i];
       if (!DETERMINE && !(flags & kSurfelActiveFlag)) continue;   // normals are updated for active surfels only
       bool act = !DETERMINE;
@@ -455,8 +459,9 @@ __global__ void __launch_bounds__(kGeoThreads) PositionDescriptorKernel(const __
     const bool first = group == 0, last = group + 1 == n_groups;
     const int j_begin = group * kGeoGroup, j_end = min(a.kf_count, static_cast<int>(group + 1) * kGeoGroup);
     for (uint32_t sub = 0; sub < tile_len / 32; ++sub) {
-      const uint32_t i = a.begin + (tile << a.tile_shift) + sub * 32 + lane;
-      if (i >= a.end || !(a.active[i] & kSurfelActiveFlag)) continue;
+      const uint32_t li = a.begin + (tile << a.tile_shift) + sub * 32 + lane;
+      const uint32_t i = SurfelShardToGlobal(li, a.shard_rank, a.shard_world);
+      if (li >= a.end || i >= a.n || !(a.active[i] & kSurfelActiveFlag)) continue;
       const Vec3 gp = V3(a.surfels[kRowX * P + i], a.surfels[kRowY * P + i], a.surfels[kRowZ * P + i]);
       const Vec3 nrm = UnpackNormal(__float_as_uint(a.surfels[kRowNormal * P + i]));
       float radius_sq = 0.f, d1 = 0.f, d2 = 0.f;
@@ -620,7 +625,7 @@ void LaunchActivationAndNormals(const GeometryArgs& a, int sm_count, bool determ
   if (a.end <= a.begin || (!determine_activation && !update_normals)) return;
   if (a.kf_count <= 0) {
     // no keyframe to look at: activation clears every flag, normals keep their value
-    if (determine_activation) cudaMemsetAsync(a.active + a.begin, 0, a.end - a.begin, stream);
+    if (determine_activation) cudaMemsetAsync(a.active, 0, a.n, stream);   // (every shard: the other ranks clear theirs as well)
     return;
   }
   if (determine_activation && update_normals) LaunchGeo(ActivationNormalsKernel<true, true>, a, sm_count, stream);
@@ -644,12 +649,12 @@ void LaunchPositionAndDescriptor(const GeometryArgs& a, int sm_count, cudaStream
 __constant__ int kShardRowIds[kShardRows - 1] = {kRowX, kRowY, kRowZ, kRowNormal, kRowD1, kRowD2};
 
 __global__ void __launch_bounds__(256) PackShardKernel(const float* __restrict__ surfels, uint32_t pitch,
-                                                       const uint8_t* __restrict__ active, uint32_t begin, uint32_t end,
+                                                       const uint8_t* __restrict__ active, uint32_t n, uint32_t rank, uint32_t world,
                                                        uint32_t shard_len, float* __restrict__ slice) {
-  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;   // local index
   if (c >= shard_len) return;
-  const uint32_t i = begin + c;
-  const bool in = i < end;
+  const uint32_t i = SurfelShardToGlobal(c, rank, world);
+  const bool in = i < n;
 #pragma unroll
   for (int r = 0; r < kShardRows - 1; ++r)
     slice[static_cast<size_t>(r) * shard_len + c] = in ? surfels[static_cast<size_t>(kShardRowIds[r]) * pitch + i] : 0.f;
@@ -657,12 +662,14 @@ __global__ void __launch_bounds__(256) PackShardKernel(const float* __restrict__
 }
 
 __global__ void __launch_bounds__(256) UnpackShardsKernel(float* __restrict__ surfels, uint32_t pitch, uint8_t* __restrict__ active,
-                                                          uint32_t n, uint32_t shard_len, int skip_rank,
+                                                          uint32_t n, uint32_t shard_len, uint32_t world, int skip_rank,
                                                           const float* __restrict__ buffer) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;   // global index
   if (i >= n) return;
-  const uint32_t rank = i / shard_len, c = i - rank * shard_len;
+  const uint32_t granule = i >> kShardGranuleShift;
+  const uint32_t rank = granule % world;
   if (static_cast<int>(rank) == skip_rank) return;
+  const uint32_t c = ((granule / world) << kShardGranuleShift) | (i & ((1u << kShardGranuleShift) - 1u));
   const float* slice = buffer + static_cast<size_t>(rank) * kShardRows * shard_len;
 #pragma unroll
   for (int r = 0; r < kShardRows - 1; ++r)
@@ -670,17 +677,16 @@ __global__ void __launch_bounds__(256) UnpackShardsKernel(float* __restrict__ su
   active[i] = static_cast<uint8_t>(slice[static_cast<size_t>(kShardRows - 1) * shard_len + c]);
 }
 
-void LaunchPackShard(const float* surfels, uint32_t pitch, const uint8_t* active, uint32_t begin, uint32_t end, uint32_t shard_len,
-                     float* slice, cudaStream_t stream) {
+void LaunchPackShard(const float* surfels, uint32_t pitch, const uint8_t* active, uint32_t n, uint32_t rank, uint32_t world,
+                     uint32_t shard_len, float* slice, cudaStream_t stream) {
   if (shard_len == 0) return;
-  PackShardKernel<<<(shard_len + 255) / 256, 256, 0, stream>>>(surfels, pitch, active, begin, end, shard_len, slice);
+  PackShardKernel<<<(shard_len + 255) / 256, 256, 0, stream>>>(surfels, pitch, active, n, rank, world, shard_len, slice);
 }
 
 void LaunchUnpackShards(float* surfels, uint32_t pitch, uint8_t* active, uint32_t n, uint32_t shard_len, int world, int skip_rank,
                         const float* buffer, cudaStream_t stream) {
-  (void)world;
   if (n == 0) return;
-  UnpackShardsKernel<<<(n + 255) / 256, 256, 0, stream>>>(surfels, pitch, active, n, shard_len, skip_rank, buffer);
+  UnpackShardsKernel<<<(n + 255) / 256, 256, 0, stream>>>(surfels, pitch, active, n, shard_len, static_cast<uint32_t>(world), skip_rank, buffer);
 }
 
 __global__ void PackPoseResultsKernel(const int* __restrict__ ids, int n, const float* __restrict__ pose_est,

@@ -58,7 +58,8 @@ struct GeometryArgs {
   float* surfels;
   uint32_t pitch;
   uint32_t n;
-  uint32_t begin, end;         // surfel range processed by this rank
+  uint32_t begin, end;         // range of this rank's LOCAL surfel indices (SurfelShardToGlobal maps them; 0 .. n on one GPU)
+  uint32_t shard_rank, shard_world;
   uint8_t* active;
   const KfDevice* kfs;
   const int* kf_list;          // non-inactive keyframes (ascending ids)
@@ -73,10 +74,17 @@ void LaunchActivationAndNormals(const GeometryArgs& args, int sm_count, bool det
 // Position (+ descriptor) accumulation and per-surfel solve (kernel_opt_geometry.cu:118-231,273-361 or :417-507).
 void LaunchPositionAndDescriptor(const GeometryArgs& args, int sm_count, cudaStream_t stream);
 
-// Multi-GPU exchange of a surfel shard: 7 rows (x y z normal d1 d2 active-as-float) x shard_len floats per rank.
+// Multi-GPU surfel sharding: 256-surfel granules are dealt round-robin to the ranks (granule g belongs to rank g % world), so
+// that every rank sees the same mix of well- and poorly-observed surfels (surfels are stored in creation order, and the
+// cost of a surfel is the number of keyframes that see it).  A rank addresses its surfels through a dense local index.
+constexpr uint32_t kShardGranuleShift = 8;
+__host__ __device__ inline uint32_t SurfelShardToGlobal(uint32_t local, uint32_t rank, uint32_t world) {
+  return world <= 1 ? local : ((((local >> kShardGranuleShift) * world + rank) << kShardGranuleShift) | (local & ((1u << kShardGranuleShift) - 1u)));
+}
+// Exchange of the shards: 7 rows (x y z normal d1 d2 active-as-float) x shard_len floats per rank, in local index order.
 constexpr int kShardRows = 7;
-void LaunchPackShard(const float* surfels, uint32_t pitch, const uint8_t* active, uint32_t begin, uint32_t end, uint32_t shard_len,
-                     float* slice, cudaStream_t stream);
+void LaunchPackShard(const float* surfels, uint32_t pitch, const uint8_t* active, uint32_t n, uint32_t rank, uint32_t world,
+                     uint32_t shard_len, float* slice, cudaStream_t stream);
 void LaunchUnpackShards(float* surfels, uint32_t pitch, uint8_t* active, uint32_t n, uint32_t shard_len, int world, int skip_rank,
                         const float* buffer, cudaStream_t stream);
 // Pose results of the locally owned keyframes -> [K][17] floats (zeros elsewhere) for the sum all-reduce.
@@ -90,7 +98,9 @@ struct IntrinsicsArgs {
   CameraParams cam;
   const float* surfels;
   uint32_t pitch;
-  uint32_t begin, end;         // surfel range processed by this rank
+  uint32_t n;
+  uint32_t begin, end;         // range of this rank's LOCAL surfel indices (SurfelShardToGlobal)
+  uint32_t shard_rank, shard_world;
   const KfDevice* kfs;
   const int* kf_list;          // every keyframe (ascending ids)
   int kf_count;

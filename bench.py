@@ -41,20 +41,50 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi sampled while the timed region runs (B200_PROFILING.md clocks line)."""
+    """SM clock + throttle reasons sampled WHILE the timed region runs (B200_PROFILING.md clocks line): NVML polled from a
+    thread every millisecond (a timed region can be a few tens of ms), nvidia-smi -lms as the fallback."""
+
+    _REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index=0):
         self.index = index
         self.proc = None
         self.lines = []
+        self.samples = []
+        self.mask = 0
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+
+    def _poll(self):
+        n, h = self._nvml, self._handle
+        while not self._stop.is_set():
+            try:
+                self.samples.append(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM))
+                self.mask |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            except Exception:
+                break
+            time.sleep(0.001)
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
+            return
+        except Exception:
+            self._nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}",
                  "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
+                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -65,6 +95,12 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self._nvml is not None:
+            self._stop.set()
+            self._thread.join(timeout=1.0)
+            reasons = sorted(name for bit, name in self._REASONS.items() if self.mask & bit)
+            return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": reasons, "samples": len(self.samples), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -83,7 +119,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def algorithmic_bytes(prof, kf_evals):

@@ -205,9 +205,17 @@ bba_status bba_bundle_adjust(bba_handle h, const bba_ba_options* options, bba_ba
  *    loops of its keyframes locally, and ONE all-reduce (sum of disjoint slots, K x 17 floats) publishes the poses.
  * Registers the exchange callback; required before any hot-path call when world_size > 1. */
 bba_status bba_set_collective(bba_handle h, bba_collective_fn fn, void* user);
-/* The partition itself, exposed so that hosts and tests can reason about it: surfel shard [begin, end) of `rank`
- * (256-aligned), and the owner rank of the i-th entry of a keyframe work list. */
-void bba_shard_surfel_range(uint32_t surfels_size, int rank, int world_size, uint32_t* begin, uint32_t* end);
+/* The partition itself, exposed so that hosts and tests can reason about it.
+ * Surfels: 256-surfel granules are dealt round-robin (granule g -> rank g % world_size), which gives every rank the same
+ * mix of well- and poorly-observed surfels; a rank addresses its surfels through a dense local index, and the exchange
+ * slices ([7][slice_length] floats per rank) are in local index order.
+ * Keyframes: the DEFAULT owner rank of the i-th entry of a keyframe work list is round-robin.  Once a pose step has run, the
+ * library balances the next one by the measured per-keyframe work (Gauss-Newton iterations x pairs projecting into the
+ * image, replicated on all ranks) with a longest-first greedy assignment; any disjoint assignment is valid because the
+ * results are published through disjoint slots of one sum all-reduce. */
+int      bba_shard_surfel_owner(uint32_t surfel_index, int world_size);
+uint32_t bba_shard_surfel_local_index(uint32_t surfel_index, int world_size);
+uint32_t bba_shard_slice_length(uint32_t surfels_size, int world_size);
 int  bba_shard_keyframe_owner(int list_index, int world_size);
 
 /* Re-uploads the images of an existing keyframe from host memory (same sizes as at creation) -- the per-step

@@ -12,27 +12,31 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 
-def shard(lib, n, rank, world):
-    b, e = C.c_uint32(), C.c_uint32()
-    lib.bba_shard_surfel_range(n, rank, world, C.byref(b), C.byref(e))
-    return b.value, e.value
+def owners(lib, n, world):
+    idx = np.arange(n, dtype=np.uint32)
+    own = np.array([lib.bba_shard_surfel_owner(int(i), world) for i in idx[::256]], np.int64).repeat(256)[:n]
+    return idx, own
 
 
 @pytest.mark.parametrize("n", [0, 1, 255, 256, 257, 1000, 200_000, 3_000_000])
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
-def test_surfel_shards_partition_the_range(n, world):
+def test_surfel_granules_partition_the_surfels(n, world):
+    """256-surfel granules dealt round-robin: every surfel has exactly one owner, the shards are balanced to one granule,
+    and (owner, local index) is a bijection into the exchange slices."""
     from badslam_b200 import _lib
     lib = _lib.load()
-    covered = 0
-    prev_end = 0
-    for r in range(world):
-        b, e = shard(lib, n, r, world)
-        assert b == prev_end or (b == n and e == n)       # contiguous, in rank order
-        assert b % 256 == 0 or b == n                      # tile aligned (the geometry kernels work on 256-surfel tiles)
-        assert e <= n
-        covered += e - b
-        prev_end = max(prev_end, e)
-    assert covered == n
+    idx, own = owners(lib, n, world)
+    assert np.array_equal(own, (idx >> 8) % world if world > 1 else np.zeros(n, np.int64))
+    counts = np.bincount(own, minlength=world) if n else np.zeros(world, np.int64)
+    assert counts.sum() == n and counts.max() - counts.min() <= 256
+    slice_len = lib.bba_shard_slice_length(n, world)
+    assert slice_len % 256 == 0 and slice_len * world >= n and (n == 0 or slice_len >= counts.max())
+    for i in (0, 1, 255, 256, 257, n // 2, n - 1):
+        if 0 <= i < n:
+            loc = lib.bba_shard_surfel_local_index(i, world)
+            assert loc < slice_len
+            g = i >> 8
+            assert loc == (((g // world) << 8) | (i & 255) if world > 1 else i)
 
 
 def test_keyframe_work_list_is_dealt_round_robin():
@@ -62,20 +66,22 @@ def _worker(rank, world, port, n, K, out_dir):
     rng = np.random.default_rng(0)                      # identical replicated state on every rank
     rows = rng.normal(size=(7, n)).astype(np.float32)
     new_rows = rng.normal(size=(7, n)).astype(np.float32)   # what a full (single-rank) geometry step would produce
-    b, e = shard(lib, n, rank, world)
+    idx, own = owners(lib, n, world)
+    loc = np.array([lib.bba_shard_surfel_local_index(int(i), world) for i in idx], np.int64)
+    mine = own == rank
     local = rows.copy()
-    local[:, b:e] = new_rows[:, b:e]                    # this rank only updates its shard
-    # exchange buffer: world slices of [7][shard_len] (kernels.cu PackShardKernel / UnpackShardsKernel)
-    shard_len = ((n + 255) // 256 + world - 1) // world * 256
+    local[:, mine] = new_rows[:, mine]                  # this rank only updates its shard
+    # exchange buffer: world slices of [7][shard_len] in local index order (kernels.cu PackShardKernel / UnpackShardsKernel)
+    shard_len = lib.bba_shard_slice_length(n, world)
     buf = torch.zeros(world * 7 * shard_len)
     sl = buf.view(world, 7, shard_len)
-    sl[rank, :, :e - b] = torch.from_numpy(local[:, b:e])
+    sl[rank][:, torch.from_numpy(loc[mine])] = torch.from_numpy(local[:, mine])
     dist.all_gather_into_tensor(buf, buf.view(world, -1)[rank].clone())
     merged = local.copy()
     for r in range(world):
-        rb, re = shard(lib, n, r, world)
         if r != rank:
-            merged[:, rb:re] = buf.view(world, 7, shard_len)[r, :, :re - rb].numpy()
+            theirs = own == r
+            merged[:, theirs] = buf.view(world, 7, shard_len)[r][:, torch.from_numpy(loc[theirs])].numpy()
     assert np.array_equal(merged, new_rows)             # every replica equals the single-rank result, bit for bit
 
     # pose slots: each keyframe of the work list is owned by exactly one rank; sum over disjoint slots == gather
