@@ -23,7 +23,9 @@ class Config(C.Structure):
                 ("raw_to_float_depth", C.c_float), ("baseline_fx", C.c_float),
                 ("sparse_surfel_cell_size", C.c_int), ("max_surfel_count", C.c_uint32), ("max_keyframes", C.c_int),
                 ("use_depth_residuals", C.c_int), ("use_descriptor_residuals", C.c_int),
-                ("device", C.c_int), ("rank", C.c_int), ("world_size", C.c_int)]
+                ("device", C.c_int), ("rank", C.c_int), ("world_size", C.c_int),
+                ("min_observation_count_while_bootstrapping_1", C.c_int), ("min_observation_count_while_bootstrapping_2", C.c_int),
+                ("min_observation_count", C.c_int), ("surfel_merge_dist_factor", C.c_float)]
 
 
 class BAOptions(C.Structure):
@@ -42,7 +44,8 @@ class BAResult(C.Structure):
                 ("ms_surfel_activation", C.c_float), ("ms_geometry_optimization", C.c_float),
                 ("ms_pose_optimization", C.c_float), ("ms_intrinsics_optimization", C.c_float),
                 ("kernel_launches", C.c_uint64),
-                ("pcg_inner_iterations_total", C.c_int), ("pcg_last_r_norm", C.c_float), ("ms_pcg", C.c_float)]
+                ("pcg_inner_iterations_total", C.c_int), ("pcg_last_r_norm", C.c_float), ("ms_pcg", C.c_float),
+                ("surfels_deleted", C.c_uint32), ("surfels_size", C.c_uint32)]
 
 
 class PoseCoeffs(C.Structure):
@@ -98,6 +101,10 @@ SYMBOLS = {
     "bba_update_surfel_activation": (C.c_int, [_P, _P]),
     "bba_optimize_geometry_iteration": (C.c_int, [_P, _P]),
     "bba_optimize_intrinsics": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "bba_perform_end_tasks": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), _P]),
+    "bba_surfels_size": (C.c_uint32, [_P]),
+    "bba_get_ba_iteration_counts": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "bba_set_ba_iteration_counts": (C.c_int, [_P, C.c_int, C.c_int]),
     "bba_pcg_debug": (C.c_int, [_P, C.POINTER(BAOptions), C.POINTER(C.c_uint32), _P, _P, _P, _P, _P, _P]),
     "bba_bundle_adjust": (C.c_int, [_P, C.POINTER(BAOptions), C.POINTER(BAResult), _P]),
     "bba_set_collective": (C.c_int, [_P, COLLECTIVE_FN, _P]),
@@ -127,7 +134,7 @@ def load():
         fn = getattr(lib, name)   # AttributeError if the symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.bba_abi_version() != 2:
+    if lib.bba_abi_version() != 3:
         raise ImportError("libbadba_b200.so ABI version mismatch")
     _lib = lib
     return lib

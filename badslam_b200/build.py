@@ -22,6 +22,7 @@ UNITS = [
     ("kernels.cu", ["-use_fast_math", "-Xptxas", "-v"]),
     ("intrinsics.cu", ["-use_fast_math", "-Xptxas", "-v"]),
     ("pcg.cu", ["-use_fast_math", "-Xptxas", "-v"]),
+    ("lifecycle.cu", ["-use_fast_math", "-Xptxas", "-v"]),
     ("pose_solve.cu", []),
     ("badba.cu", []),
 ]

@@ -206,6 +206,15 @@ struct bba_context {
   double* h_intr_sums = nullptr;      // pinned
   float* h_intr_x1 = nullptr;         // pinned, 8 floats
 
+  // end-of-BA surfel maintenance (PerformBASchemeEndTasks)
+  int last_ba_iteration_count = -1;          // direct_ba.cc:126
+  bba::KfRadius* d_kf_radius = nullptr;      // [max_keyframes], lazily allocated
+  bba::KfRadius* h_kf_radius = nullptr;      // pinned
+  unsigned int* d_deleted_count = nullptr;
+  unsigned int* h_deleted_count = nullptr;   // pinned
+  unsigned int* d_compact_sums = nullptr;
+  uint32_t compact_sums_capacity = 0;
+
   // PCG solver (lazily allocated): r, M, delta, g, p with pcg_capacity floats each
   float* d_pcg[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t pcg_capacity = 0;
@@ -675,6 +684,81 @@ bba_status OptimizeIntrinsics(bba_handle h, bool opt_depth, bool opt_color, cuda
   return BBA_OK;
 }
 
+// direct_ba.h:220-226
+int GetMinObservationCount(bba_handle h) {
+  const size_t K = h->keyframes.size();
+  return (K < 10) ? ((K < 5) ? h->cfg.min_observation_count_while_bootstrapping_1 : h->cfg.min_observation_count_while_bootstrapping_2)
+                  : h->cfg.min_observation_count;
+}
+
+// DirectBA::PerformBASchemeEndTasks (direct_ba.cc:566-653) without the final merge (do_surfel_updates is not supported yet):
+// DeleteSurfelsAndUpdateRadiiCUDA over every keyframe, then CompactSurfelsCUDA.  Replicated on every rank of a multi-GPU
+// job (once per BA call, deterministic, identical inputs -> identical surfel buffers without an exchange).
+bba_status PerformEndTasks(bba_handle h, cudaStream_t s, uint32_t* deleted_out) {
+  if (deleted_out) *deleted_out = 0;
+  const int K = static_cast<int>(h->keyframes.size());
+  const uint32_t N = h->surfels_size;
+  if (N == 0) return BBA_OK;   // kernel_delete_surfels.cc:52-54
+  if (!h->d_kf_radius) {
+    BBA_CUDA(h, cudaMalloc(&h->d_kf_radius, sizeof(bba::KfRadius) * h->cfg.max_keyframes));
+    BBA_CUDA(h, cudaMallocHost(&h->h_kf_radius, sizeof(bba::KfRadius) * h->cfg.max_keyframes));
+    BBA_CUDA(h, cudaMalloc(&h->d_deleted_count, sizeof(unsigned int)));
+    BBA_CUDA(h, cudaMallocHost(&h->h_deleted_count, sizeof(unsigned int)));
+  }
+  if (bba_status st = UploadKeyframes(h, s)) return st;   // (waits for the previous use of the staging buffers)
+  for (int k = 0; k < K; ++k) {
+    if (!h->keyframes[k].radius) return Fail(h, BBA_ERR_STATE, "end tasks need the keyframes' radius buffers");
+    h->h_kf_radius[k].ptr = h->keyframes[k].radius;
+    h->h_kf_radius[k].pitch = static_cast<uint32_t>(h->keyframes[k].radius_pitch);
+    h->h_kf_radius[k].pad = 0;
+  }
+  if (K) BBA_CUDA(h, cudaMemcpyAsync(h->d_kf_radius, h->h_kf_radius, sizeof(bba::KfRadius) * K, cudaMemcpyHostToDevice, s));
+  BBA_CUDA(h, cudaMemsetAsync(h->d_deleted_count, 0, sizeof(unsigned int), s));
+  if (!h->d_tile_epoch || h->tile_epoch_capacity < (N + 31u) / 32u) {
+    cudaFree(h->d_tile_epoch);
+    h->tile_epoch_capacity = std::max<uint32_t>((h->cfg.max_surfel_count + 31u) / 32u, (N + 31u) / 32u) + 1;
+    BBA_CUDA(h, cudaMalloc(&h->d_tile_epoch, sizeof(unsigned int) * h->tile_epoch_capacity));
+  }
+  bba::SurfelStatsArgs a;
+  a.cam = MakeCamera(h);
+  a.surfels = h->surfels;
+  a.pitch = static_cast<uint32_t>(h->surfel_pitch_bytes / sizeof(float));
+  a.n = N;
+  a.kfs = h->d_kfs;
+  a.radius = h->d_kf_radius;
+  a.kf_count = K;
+  a.min_observation_count = GetMinObservationCount(h);
+  a.queue = h->d_geo_queue;
+  a.tile_epoch = h->d_tile_epoch;
+  a.tile_shift = 8;
+  a.deleted_count = h->d_deleted_count;
+  if (K > 0) {
+    bba::LaunchObservationStats(a, h->sm_count, s);
+    ++h->launches;
+    BBA_CUDA(h, cudaGetLastError());
+  }
+  // (with no keyframe at all the reference still runs MarkDeletedSurfels on zero counts; not reachable through this API,
+  // a BA call without keyframes has nothing to optimise)
+  BBA_CUDA(h, cudaMemcpyAsync(h->h_deleted_count, h->d_deleted_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+  BBA_CUDA(h, cudaStreamSynchronize(s));   // kernel_delete_surfels.cc:93-96
+  h->staging_pending = false;
+  const uint32_t deleted = *h->h_deleted_count;
+  if (deleted_out) *deleted_out = deleted;
+  if (deleted > 0) {   // kernel_compact_surfels.cu:167-169
+    const uint32_t words = bba::CompactScratchWords(N);
+    if (words > h->compact_sums_capacity) {
+      cudaFree(h->d_compact_sums);
+      h->compact_sums_capacity = std::max(words, bba::CompactScratchWords(std::max(h->cfg.max_surfel_count, N)));
+      BBA_CUDA(h, cudaMalloc(&h->d_compact_sums, sizeof(unsigned int) * h->compact_sums_capacity));
+    }
+    bba::LaunchCompactSurfels(h->surfels, a.pitch, N, deleted, h->d_compact_sums, s);
+    h->launches += 4;
+    BBA_CUDA(h, cudaGetLastError());
+    h->surfels_size = N - deleted;
+  }
+  return BBA_OK;
+}
+
 // Unknown layout of the PCG solver (direct_ba_pcg.cc:273-309) + the vectors sized for it.
 struct PcgLayout {
   bool opt_poses, opt_geometry, opt_depth_intr, opt_color_intr, use_desc;
@@ -756,13 +840,19 @@ bba_status BundleAdjustPCG(bba_handle h, const bba_ba_options* o, bba_ba_result*
   if (bba_status st = MakePcgLayout(h, o, &L)) return st;
   const bool opt_depth_intr = L.opt_depth_intr, opt_color_intr = L.opt_color_intr, opt_poses = L.opt_poses, opt_geometry = L.opt_geometry;
   const bool use_desc = L.use_desc;
-  const uint32_t N = h->surfels_size;
   const uint32_t P = static_cast<uint32_t>(h->cf_w) * h->cf_h;
   const uint64_t launches_before = h->launches;
   const auto t_start = std::chrono::steady_clock::now();
+  if (!o->increase_ba_iteration_count && h->ba_iteration_count != h->last_ba_iteration_count) {   // :157-161
+    h->last_ba_iteration_count = h->ba_iteration_count;
+    uint32_t deleted = 0;
+    if (bba_status st = PerformEndTasks(h, s, &deleted)) return st;
+    res->surfels_deleted += deleted;
+  }
 
   for (int iteration = 0; iteration < o->max_iterations; ++iteration) {
     ++res->iterations_done;
+    const uint32_t N = h->surfels_size;
     if (N > 0) BBA_CUDA(h, cudaMemsetAsync(h->active, bba::kSurfelActiveFlag, N, s));   // :209-212
     if (bba_status st = UploadKeyframes(h, s)) return st;
     BBA_CUDA(h, cudaEventRecord(h->ev[0], s));
@@ -887,7 +977,13 @@ bba_status BundleAdjustPCG(bba_handle h, const bba_ba_options* o, bba_ba_result*
       if (el > o->time_limit_seconds) break;
     }
   }
-  if (o->increase_ba_iteration_count) ++h->ba_iteration_count;
+  if (o->increase_ba_iteration_count) {   // :771-776
+    uint32_t deleted = 0;
+    if (bba_status st = PerformEndTasks(h, s, &deleted)) return st;
+    res->surfels_deleted += deleted;
+    ++h->ba_iteration_count;
+  }
+  res->surfels_size = h->surfels_size;
   res->kernel_launches = h->launches - launches_before;
   return BBA_OK;
 }
@@ -1069,6 +1165,11 @@ void bba_destroy(bba_handle h) {
   cudaFree(h->d_all_list);
   cudaFreeHost(h->h_intr_sums);
   cudaFreeHost(h->h_intr_x1);
+  cudaFree(h->d_kf_radius);
+  cudaFreeHost(h->h_kf_radius);
+  cudaFree(h->d_deleted_count);
+  cudaFreeHost(h->h_deleted_count);
+  cudaFree(h->d_compact_sums);
   for (float* v : h->d_pcg) cudaFree(v);
   cudaFree(h->d_pcg_scalars);
   cudaFreeHost(h->h_pcg_scalars);
@@ -1415,6 +1516,13 @@ bba_status bba_bundle_adjust(bba_handle h, const bba_ba_options* o, bba_ba_resul
   const uint64_t launches_before = h->launches;
   const auto t_start = std::chrono::steady_clock::now();
 
+  if (!o->increase_ba_iteration_count && h->ba_iteration_count != h->last_ba_iteration_count) {   // :313-319
+    h->last_ba_iteration_count = h->ba_iteration_count;
+    uint32_t deleted = 0;
+    if (bba_status st = PerformEndTasks(h, s, &deleted)) return st;
+    res->surfels_deleted += deleted;
+  }
+
   const bool fixed_window = o->active_keyframe_window_start > 0 || o->active_keyframe_window_end > 0;   // :330-331
   const bool whole_window = !(o->active_keyframe_window_start != 0 || o->active_keyframe_window_end != K - 1);
 
@@ -1523,8 +1631,39 @@ bba_status bba_bundle_adjust(bba_handle h, const bba_ba_options* o, bba_ba_resul
     }
     DetermineCovisibleActiveKeyframes(h);   // :711-717
   }
-  if (o->increase_ba_iteration_count) ++h->ba_iteration_count;
+  if (o->increase_ba_iteration_count) {   // :725-735
+    uint32_t deleted = 0;
+    if (bba_status st = PerformEndTasks(h, s, &deleted)) return st;
+    res->surfels_deleted += deleted;
+    ++h->ba_iteration_count;
+  }
+  res->surfels_size = h->surfels_size;
   res->kernel_launches = h->launches - launches_before;
+  return BBA_OK;
+}
+
+bba_status bba_perform_end_tasks(bba_handle h, uint32_t* deleted, uint32_t* surfels_size, void* stream) {
+  if (!h) return BBA_ERR_INVALID_ARGUMENT;
+  if (bba_status st = CheckSurfels(h)) return st;
+  uint32_t d = 0;
+  if (bba_status st = PerformEndTasks(h, static_cast<cudaStream_t>(stream), &d)) return st;
+  if (deleted) *deleted = d;
+  if (surfels_size) *surfels_size = h->surfels_size;
+  return BBA_OK;
+}
+
+uint32_t bba_surfels_size(bba_handle h) { return h ? h->surfels_size : 0; }
+
+bba_status bba_get_ba_iteration_counts(bba_handle h, int* ba_iteration_count, int* last_ba_iteration_count) {
+  if (!h) return BBA_ERR_INVALID_ARGUMENT;
+  if (ba_iteration_count) *ba_iteration_count = h->ba_iteration_count;
+  if (last_ba_iteration_count) *last_ba_iteration_count = h->last_ba_iteration_count;
+  return BBA_OK;
+}
+bba_status bba_set_ba_iteration_counts(bba_handle h, int ba_iteration_count, int last_ba_iteration_count) {
+  if (!h) return BBA_ERR_INVALID_ARGUMENT;
+  h->ba_iteration_count = ba_iteration_count;
+  h->last_ba_iteration_count = last_ba_iteration_count;
   return BBA_OK;
 }
 

@@ -148,6 +148,31 @@ void LaunchPcgUpdateSurfels(float* surfels, uint32_t pitch, uint32_t n, bool use
                             cudaStream_t stream);
 void LaunchPcgUpdateCfactor(float* cfactor, uint32_t cells, const float* delta, cudaStream_t stream);
 
+// End-of-BA surfel maintenance (lifecycle.cu; PerformBASchemeEndTasks, direct_ba.cc:566-653).
+struct KfRadius {
+  const uint16_t* ptr;         // pitched u16 (IEEE half radius^2, keyframe.h radius_buffer)
+  uint32_t pitch;              // bytes
+  uint32_t pad;
+};
+struct SurfelStatsArgs {
+  CameraParams cam;
+  float* surfels;
+  uint32_t pitch;
+  uint32_t n;
+  const KfDevice* kfs;         // every keyframe, ids 0 .. kf_count-1
+  const KfRadius* radius;
+  int kf_count;
+  int min_observation_count;
+  unsigned int* queue;
+  unsigned int* tile_epoch;
+  int tile_shift;              // chosen by the launcher
+  unsigned int* deleted_count; // device scalar, += surfels deleted by this launch
+};
+void LaunchObservationStats(SurfelStatsArgs a, int sm_count, cudaStream_t stream);
+uint32_t CompactScratchWords(uint32_t n);   // size of block_sums for LaunchCompactSurfels
+// Moves surviving surfels from the tail into the free spots; afterwards the first n - free_count slots are the surfels.
+void LaunchCompactSurfels(float* surfels, uint32_t pitch, uint32_t n, uint32_t free_count, unsigned int* block_sums, cudaStream_t stream);
+
 // uchar4 (.w = luma) -> u8 plane.
 void LaunchExtractLuma(const uint8_t* rgba, size_t rgba_pitch, uint8_t* luma, size_t luma_pitch, int w, int h, cudaStream_t stream);
 

@@ -92,6 +92,8 @@ class BAResult:
     pcg_inner_iterations_total: int = 0
     pcg_last_r_norm: float = 0.0
     ms_pcg: float = 0.0
+    surfels_deleted: int = 0
+    surfels_size: int = 0
 
     @property
     def residual_count(self):
@@ -132,6 +134,9 @@ class DirectBA:
         cfg.use_descriptor_residuals = int(use_descriptor_residuals)
         cfg.device = self.device.index if self.device.index is not None else torch.cuda.current_device()
         cfg.rank, cfg.world_size = rank, world_size
+        (cfg.min_observation_count_while_bootstrapping_1, cfg.min_observation_count_while_bootstrapping_2,
+         cfg.min_observation_count) = self.min_observation_counts
+        cfg.surfel_merge_dist_factor = surfel_merge_dist_factor
         self._cfg = cfg
         self._h = C.c_void_p()
         st = self._lib.bba_create(C.byref(cfg), C.byref(self._h))
@@ -374,7 +379,27 @@ class DirectBA:
         return BAResult(r.iterations_done, bool(r.converged), r.depth_residual_count, r.descriptor_residual_count,
                         r.cost, r.pose_iterations_total, r.ms_surfel_activation, r.ms_geometry_optimization,
                         r.ms_pose_optimization, r.ms_intrinsics_optimization, r.kernel_launches,
-                        r.pcg_inner_iterations_total, r.pcg_last_r_norm, r.ms_pcg)
+                        r.pcg_inner_iterations_total, r.pcg_last_r_norm, r.ms_pcg, r.surfels_deleted, r.surfels_size)
+
+    def ba_iteration_count(self) -> int:
+        a, b = C.c_int(), C.c_int()
+        self._check(self._lib.bba_get_ba_iteration_counts(self._h, C.byref(a), C.byref(b)))
+        return a.value
+
+    def last_ba_iteration_count(self) -> int:
+        a, b = C.c_int(), C.c_int()
+        self._check(self._lib.bba_get_ba_iteration_counts(self._h, C.byref(a), C.byref(b)))
+        return b.value
+
+    def SetLastBAIterationCount(self, count: int):
+        """direct_ba.h:377."""
+        self._check(self._lib.bba_set_ba_iteration_counts(self._h, self.ba_iteration_count(), int(count)))
+
+    def PerformBASchemeEndTasks(self, stream=None):
+        """direct_ba.cc:566-653 (delete badly observed surfels, update radii, compact).  Returns (deleted, surfels_size)."""
+        d, n = C.c_uint32(), C.c_uint32()
+        self._check(self._lib.bba_perform_end_tasks(self._h, C.byref(d), C.byref(n), self._stream_ptr(stream)))
+        return d.value, n.value
 
     def PCGDebug(self, optimize_poses=True, optimize_geometry=True, optimize_depth_intrinsics=False,
                  optimize_color_intrinsics=False, gauge_keyframe=0, stream=None):

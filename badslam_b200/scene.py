@@ -540,3 +540,22 @@ def make_scene(cfg: SceneConfig, verbose: bool = False) -> Scene:
     surfels[:8, :n] = rows
     return Scene(cfg, depth_K, color_K, depth, normals, radius, color, poses_true, poses_init, mind, maxd,
                  surfels, n, cfactor_grid, 0.0, planes)
+
+
+def displace_surfels(scene, seed=3):
+    """A copy of `scene` with three groups of surfels displaced, to exercise the end-of-BA maintenance
+    (PerformBASchemeEndTasks): moved out of every view (unobserved), pulled towards keyframe 0's camera (in front of the
+    measured surface: free-space violations) and pushed away from it (behind the surface: occluded)."""
+    import copy
+    sc = copy.copy(scene)
+    sc.surfels = scene.surfels.copy()
+    n = sc.num_surfels
+    idx = np.random.default_rng(seed).permutation(n)
+    k1, k2 = max(n // 150, 8), max(n // 100, 12)
+    away, front, behind = idx[:k1], idx[k1:k1 + k2], idx[k1 + k2:k1 + 2 * k2]
+    sc.surfels[0:3, away] += np.float32(1000.0)
+    c0 = np.asarray(scene.poses_true[0][4:7], np.float32)
+    for sel, f in ((front, np.float32(0.7)), (behind, np.float32(1.3))):
+        p = sc.surfels[0:3, sel]
+        sc.surfels[0:3, sel] = c0[:, None] + f * (p - c0[:, None])
+    return sc, away, front, behind

@@ -175,6 +175,11 @@ def run_ours(args, scene, rank, world):
     backup = surf[:8].clone()
     poses0 = scene.poses_init.copy()
     act0 = np.zeros(K, np.int32)
+    # A step = ONE iteration of the alternation on the full configured workload.  The end-of-scheme surfel maintenance
+    # (PerformBASchemeEndTasks: delete / radius update / compaction) runs once per BundleAdjustment call, not per
+    # iteration, and would change the surfel set between steps: it is kept out of the steps (increase_ba_iteration_count =
+    # false with the counters in sync, direct_ba_alternating.cc:313-319) and is part of the full-BA number below.
+    ba.SetLastBAIterationCount(ba.ba_iteration_count())
 
     def step():
         surf[:8].copy_(backup, non_blocking=True)
@@ -293,6 +298,8 @@ def run_e2e(args, scene, dev, residuals):
     h2d = sum(t.numel() * t.element_size() for t in pinned[0]) + K * (96 + 28 + 4)
     d2h = K * (28 + 4 + 4 + 64)
 
+    ba.SetLastBAIterationCount(ba.ba_iteration_count())   # (see run_ours: no end-of-scheme maintenance inside a step)
+
     def step(i):
         k = i % slots
         d, n, r, c = pinned[k]
@@ -330,6 +337,7 @@ def run_e2e_multi(args, scene, dev, residuals, rank, world):
     backup = surf[:8].clone()
     poses0 = scene.poses_init.copy()
     act0 = np.zeros(K, np.int32)
+    ba.SetLastBAIterationCount(ba.ba_iteration_count())
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int16 if a.dtype == np.uint16 else a.dtype)).pin_memory()
     slots = min(K, 4)
     pinned = [(pin(scene.depth[k]), pin(scene.normals[k]), pin(scene.radius[k]), pin(scene.color[k])) for k in range(slots)]
@@ -377,11 +385,11 @@ def run_reference(args, scene):
     ref = ref_cuda.RefDirectBA(scene)
     ref.snapshot()
     # residual count from the reference's own debug counters (untimed)
-    r = ref.bundle_adjust(True, True, 1, 1, count_residuals=True)
+    r = ref.bundle_adjust(True, True, 1, 1, count_residuals=True, end_tasks=False)
     count_ref = int(r.n_count)
     for _ in range(max(args.warmup - 1, 0)):
         ref.restore()
-        ref.bundle_adjust(True, True, 1, 1, count_residuals=False)
+        ref.bundle_adjust(True, True, 1, 1, count_residuals=False, end_tasks=False)
     ref.sync()
     sampler = ClockSampler(0)
     sampler.start()
@@ -390,7 +398,7 @@ def run_reference(args, scene):
     stage = np.zeros(3)
     for _ in range(args.steps):
         ref.restore()
-        r = ref.bundle_adjust(True, True, 1, 1, count_residuals=False)
+        r = ref.bundle_adjust(True, True, 1, 1, count_residuals=False, end_tasks=False)
         stage += [r.ms_surfel_activation, r.ms_geometry_optimization, r.ms_pose_optimization]
     ref.sync()
     dt = (time.perf_counter() - t0) / args.steps
@@ -404,7 +412,7 @@ def run_reference(args, scene):
     if residuals is None:
         from badslam_b200.direct_ba import DirectBA
         ba = DirectBA.from_scene(scene)
-        rr = ba.BundleAdjustment(None, False, False, False, True, True, 1, 1)
+        rr = ba.BundleAdjustment(None, False, False, False, True, True, 1, 1, increase_ba_iteration_count=False)
         residuals = rr.depth_residual_count + rr.descriptor_residual_count
         ours_pairs = rr.depth_residual_count + rr.descriptor_residual_count // 2
         del ba

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BBA_ABI_VERSION 2
+#define BBA_ABI_VERSION 3
 
 typedef struct bba_context* bba_handle;
 
@@ -62,6 +62,11 @@ typedef struct {
   int use_descriptor_residuals;
   int device;                  /* CUDA device ordinal this handle lives on */
   int rank, world_size;        /* position in a one-process-per-GPU job (world_size 1 = single GPU) */
+  /* surfel maintenance (direct_ba.h:73-88; defaults of bad_slam_config.h:143-158 are 1, 2, 3 and 0.8) */
+  int min_observation_count_while_bootstrapping_1;   /* < 5 keyframes  */
+  int min_observation_count_while_bootstrapping_2;   /* < 10 keyframes */
+  int min_observation_count;
+  float surfel_merge_dist_factor;                    /* unused until do_surfel_updates is supported */
 } bba_config;
 
 /* Arguments of DirectBA::BundleAdjustment (direct_ba.h:143-162). */
@@ -106,6 +111,10 @@ typedef struct {
   int pcg_inner_iterations_total;
   float pcg_last_r_norm;
   float ms_pcg;
+  /* PerformBASchemeEndTasks (direct_ba.cc:566-653): surfels deleted by this call, surfels_size afterwards (the surviving
+   * surfels are compacted to the front of the caller's buffer) */
+  uint32_t surfels_deleted;
+  uint32_t surfels_size;
 } bba_ba_result;
 
 /* Counters of one pose pass (superset of kernel_opt_pose.cu's debug outputs; the n_* feed the
@@ -186,6 +195,19 @@ bba_status bba_estimate_frame_pose(bba_handle h, int keyframe_id, const float gl
 bba_status bba_update_surfel_activation(bba_handle h, void* stream);
 /* OptimizeGeometryIterationCUDA (kernels.h:234-244, kernel_opt_geometry.cc:80-201) */
 bba_status bba_optimize_geometry_iteration(bba_handle h, void* stream);
+/* DirectBA::PerformBASchemeEndTasks (direct_ba.cc:566-653): DeleteSurfelsAndUpdateRadiiCUDA over every keyframe (surfels
+ * with fewer than GetMinObservationCount() observations, or more free-space violations than observations, are deleted; the
+ * others get the smallest observed radius) + CompactSurfelsCUDA.  bba_bundle_adjust runs it like the reference does: at
+ * the end when increase_ba_iteration_count is set, else at the start of the first call after the counter changed.
+ * The keyframes' radius buffers must be valid.  *deleted / *surfels_size may be NULL. */
+bba_status bba_perform_end_tasks(bba_handle h, uint32_t* deleted, uint32_t* surfels_size, void* stream);
+/* surfels_size_ of the reference (the caller's buffer holds that many surfels at its front). */
+uint32_t bba_surfels_size(bba_handle h);
+/* ba_iteration_count_ / last_ba_iteration_count_ (direct_ba.h:373-377): the pair decides whether a call with
+ * increase_ba_iteration_count = 0 first runs the end tasks (direct_ba_alternating.cc:313-319). */
+bba_status bba_get_ba_iteration_counts(bba_handle h, int* ba_iteration_count, int* last_ba_iteration_count);
+bba_status bba_set_ba_iteration_counts(bba_handle h, int ba_iteration_count, int last_ba_iteration_count);
+
 /* Parity hook for the PCG solver's building blocks (kernel_pcg.cu:179-1037): runs the init pass (PCGInitCUDA for every
  * keyframe) -> out_r, out_M; PCGInit2 -> out_p; one PCGStep1 sweep -> out_g, out_scalars = {alpha_n, alpha_d}.
  * Host output buffers of *unknown_count floats; call with out_r = NULL to query the count.  o->pcg_gauge_keyframe >= 0. */

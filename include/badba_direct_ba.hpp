@@ -41,8 +41,8 @@ template <typename SE3f, typename PinholeCamera4f>
 class DirectBA {
  public:
   DirectBA(int max_surfel_count, float raw_to_float_depth, float baseline_fx, int sparse_surfel_cell_size,
-           float /*surfel_merge_dist_factor*/, int /*min_observation_count_while_bootstrapping_1*/,
-           int /*min_observation_count_while_bootstrapping_2*/, int /*min_observation_count*/,
+           float surfel_merge_dist_factor, int min_observation_count_while_bootstrapping_1,
+           int min_observation_count_while_bootstrapping_2, int min_observation_count,
            const PinholeCamera4f& color_camera_initial_estimate, const PinholeCamera4f& depth_camera_initial_estimate,
            int /*pyramid_level_for_color*/, bool use_depth_residuals, bool use_descriptor_residuals, int max_keyframes = 2500,
            int device = 0, int rank = 0, int world_size = 1) {
@@ -65,6 +65,10 @@ class DirectBA {
     c.device = device;
     c.rank = rank;
     c.world_size = world_size;
+    c.min_observation_count_while_bootstrapping_1 = min_observation_count_while_bootstrapping_1;
+    c.min_observation_count_while_bootstrapping_2 = min_observation_count_while_bootstrapping_2;
+    c.min_observation_count = min_observation_count;
+    c.surfel_merge_dist_factor = surfel_merge_dist_factor;
     Check(bba_create(&c, &h_), "bba_create");
   }
   ~DirectBA() { bba_destroy(h_); }
@@ -135,6 +139,7 @@ class DirectBA {
   void SetKeyframePose(int keyframe_id, const SE3f& global_T_frame) {
     Check(bba_set_keyframe_pose(h_, keyframe_id, global_T_frame.data()), "bba_set_keyframe_pose");
   }
+  uint32_t surfels_size() const { return bba_surfels_size(h_); }   // direct_ba.h:265
   void GetIntrinsics(float depth[4], float color[4], float* a) const { Check(bba_get_intrinsics(h_, depth, color, a), "bba_get_intrinsics"); }
   void SetPCGGaugeKeyframe(int keyframe_id) { pcg_gauge_keyframe_ = keyframe_id; }
   const bba_ba_result& last_result() const { return last_result_; }

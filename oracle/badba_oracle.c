@@ -1315,6 +1315,102 @@ uint32_t orc_pcg_debug(const orc_model* m, const orc_keyframes* kfs, const float
   return U;
 }
 
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * DirectBA::PerformBASchemeEndTasks (direct_ba.cc:566-653) without the final merge:
+ * DeleteSurfelsAndUpdateRadiiCUDA (kernel_delete_surfels.cc:40-98, .cu:42-164) + CompactSurfelsCUDA
+ * (kernel_compact_surfels.cu:159-279).  Returns the number of deleted surfels; *n becomes the new surfels_size.
+ * ------------------------------------------------------------------------------------------------------------------ */
+static inline float half_to_float(uint16_t h) {
+  uint32_t sign = (uint32_t)(h >> 15) << 31, exp = (h >> 10) & 31u, man = h & 1023u;
+  uint32_t bits;
+  if (exp == 0) {
+    if (man == 0) bits = sign;
+    else {   /* subnormal */
+      int e = -1;
+      do { ++e; man <<= 1; } while (!(man & 1024u));
+      bits = sign | (uint32_t)(127 - 15 - e) << 23 | (man & 1023u) << 13;
+    }
+  } else if (exp == 31) bits = sign | 0x7f800000u | man << 13;
+  else bits = sign | (exp + 112u) << 23 | man << 13;
+  return u2f(bits);
+}
+
+uint32_t orc_end_tasks(const orc_model* m, const orc_keyframes* kfs, float* surfels, int pitch, uint32_t* n_inout,
+                       int min_observation_count) {
+  const uint32_t n = *n_inout;
+  if (n == 0) return 0;
+  const int K = kfs->K;
+  const size_t P = (size_t)pitch;
+  const size_t npx = (size_t)m->depth_w * m->depth_h;
+  float* Ts = (float*)malloc(sizeof(float) * 12 * (size_t)(K > 0 ? K : 1));
+  kfview* vs = (kfview*)malloc(sizeof(kfview) * (size_t)(K > 0 ? K : 1));
+  for (int k = 0; k < K; ++k) { orc_frame_T_global(kfs->global_T_frame + 7 * k, Ts + 12 * k); make_view(m, kfs, k, vs + k); }
+  uint32_t deleted = 0;
+#pragma omp parallel for schedule(static) reduction(+ : deleted)
+  for (int64_t ii = 0; ii < (int64_t)n; ++ii) {
+    const size_t i = (size_t)ii;
+    float obs = 0, viol = 0, min_r2 = INFINITY;
+    const float x = surfels[ROW_X * P + i];
+    f3 gp = mk3(x, surfels[ROW_Y * P + i], surfels[ROW_Z * P + i]);
+    f3 nrm = unpack_normal(f2u(surfels[ROW_NORMAL * P + i]));
+    for (int k = 0; k < K; ++k) {   /* every keyframe (kernel_delete_surfels.cc:69-80) */
+      const kfview* v = vs + k;
+      const float* T = Ts + 12 * k;
+      /* SurfelProjectsToAssociatedPixel(..., SurfelProjectionResultXYFreeSpace*), surfel_projection_nvcc_only.cuh:482-511 */
+      f3 lp;
+      lp.z = T[8] * gp.x + T[9] * gp.y + T[10] * gp.z + T[11];
+      if (!(lp.z > 0.f)) continue;
+      lp.x = T[0] * gp.x + T[1] * gp.y + T[2] * gp.z + T[3];
+      lp.y = T[4] * gp.x + T[5] * gp.y + T[6] * gp.z + T[7];
+      float pxf = v->fx * (lp.x / lp.z) + v->cx, pyf = v->fy * (lp.y / lp.z) + v->cy;
+      if (!(pxf >= 0.f) || !(pyf >= 0.f) || !(pxf < 1e9f) || !(pyf < 1e9f)) continue;
+      int px = (int)pxf, py = (int)pyf;
+      if (px >= v->w || py >= v->h) continue;
+      uint16_t measured = v->depth[(size_t)py * v->w + px];
+      if (measured & K_INVALID_DEPTH_BIT) continue;
+      float d = raw_to_calibrated_depth(v->a, v->cfactor[(size_t)(py / v->cell) * v->cf_w + (px / v->cell)], v->raw_to_float, measured);
+      f3 ln = T_rot(T, nrm);
+      float nx = v->fx_inv * px + v->cx_inv, ny = v->fy_inv * py + v->cy_inv;
+      float thr = K_DEPTH_TUKEY * ((K_DEPTH_UNCERTAINTY_FACTOR * fabsf(ln.x * nx + ln.y * ny + ln.z) * (d * d)) / v->baseline_fx);
+      float diff = d - lp.z;
+      if (diff > thr) { viol += 1.f; continue; }
+      if (diff < -thr) continue;
+      float dist = sqrtf(dot3(lp, lp));
+      if ((1.0f / dist) * dot3(lp, ln) > 0) continue;
+      if (dot3(ln, u16_to_image_space_normal(v->normals[(size_t)py * v->w + px])) < K_COS_NORMAL_COMPAT) continue;
+      obs += 1.f;
+      min_r2 = fminf(min_r2, half_to_float(kfs->radius[npx * k + (size_t)py * v->w + px]));
+    }
+    surfels[(ROW_ACC0 + 0) * P + i] = obs; surfels[(ROW_ACC0 + 1) * P + i] = viol; surfels[(ROW_ACC0 + 2) * P + i] = min_r2;
+    if (obs < (float)min_observation_count || viol > obs) {   /* kernel_delete_surfels.cu:138-146 */
+      if (f2u(x) != 0x7fffffffu) { surfels[ROW_X * P + i] = u2f(0x7fffffffu); ++deleted; }
+    } else {
+      surfels[ROW_R2 * P + i] = min_r2;
+    }
+  }
+  free(Ts); free(vs);
+  if (deleted == 0) return 0;
+  /* compaction: the r-th valid surfel from the end moves into the r-th free spot from the front if that lies in front of it */
+  uint8_t* invalid = (uint8_t*)malloc(n);   /* validity BEFORE any move (the device kernel flags first, kernel_compact_surfels.cu:98-107) */
+  uint32_t free_count = 0;
+  for (uint32_t i = 0; i < n; ++i) { invalid[i] = f2u(surfels[ROW_X * P + i]) == 0x7fffffffu; free_count += invalid[i]; }
+  uint32_t* free_list = (uint32_t*)malloc(sizeof(uint32_t) * (free_count ? free_count : 1));
+  uint32_t nf = 0;
+  for (uint32_t i = 0; i < n; ++i) if (invalid[i]) free_list[nf++] = i;
+  uint32_t r = 0;
+  for (uint32_t i = n; i-- > 0 && r < free_count;) {
+    if (invalid[i]) continue;
+    if (free_list[r] < i)
+      for (int row = 0; row < ROW_ACC0; ++row) surfels[(size_t)row * P + free_list[r]] = surfels[(size_t)row * P + i];
+    ++r;
+  }
+  free(invalid);
+  free(free_list);
+  *n_inout = n - free_count;
+  return deleted;
+}
+
 void orc_se3_exp(const float a[6], float out[7]) { hm_se3_exp(a, out); }
 void orc_se3_log(const float T[7], float out[6]) { hm_se3_log(T, out); }
 void orc_se3_mul(const float A[7], const float B[7], float out[7]) { hm_se3_mul(A, B, out); }

@@ -146,6 +146,12 @@ typedef struct {
 void orc_bundle_adjust_pcg(orc_model* m, orc_keyframes* kfs, float* surfels, int pitch, uint32_t n, uint8_t* active,
                            const orc_pcg_options* opt, orc_pcg_result* res);
 
+/* DirectBA::PerformBASchemeEndTasks (direct_ba.cc:566-653) without the final merge: delete surfels with fewer than
+ * min_observation_count observations or more free-space violations than observations, give the others the smallest observed
+ * radius^2, compact.  Returns the number of deleted surfels; *n is updated to the new surfels_size. */
+uint32_t orc_end_tasks(const orc_model* m, const orc_keyframes* kfs, float* surfels, int pitch, uint32_t* n,
+                       int min_observation_count);
+
 /* Parity hook for the PCG building blocks: r, M after the init pass, p0, g after one J^T W J p sweep, {alpha_n, alpha_d}. */
 uint32_t orc_pcg_debug(const orc_model* m, const orc_keyframes* kfs, const float* surfels, int pitch, uint32_t n,
                        const orc_pcg_options* opt, float* out_r, float* out_M, float* out_p, float* out_g, double* out_scalars);

@@ -176,9 +176,23 @@ class Oracle:
         self.lib.orc_optimize_intrinsics(C.byref(self.model), C.byref(self.kfs), _p(self.surfels, C.c_float),
                                          C.c_int(self.pitch), C.c_uint32(self.n), C.c_int(depth), C.c_int(color))
 
+    min_observation_counts = (1, 2, 3)   # bad_slam_config.h:146,151,158
+
+    def end_tasks(self):
+        """PerformBASchemeEndTasks (direct_ba.cc:566-653): delete + radius update + compaction.  Returns the deleted count."""
+        K = self.K
+        b1, b2, mo = self.min_observation_counts
+        min_obs = (b1 if K < 5 else b2) if K < 10 else mo     # direct_ba.h:220-226
+        n = C.c_uint32(self.n)
+        self.lib.orc_end_tasks.restype = C.c_uint32
+        deleted = self.lib.orc_end_tasks(C.byref(self.model), C.byref(self.kfs), _p(self.surfels, C.c_float), C.c_int(self.pitch),
+                                         C.byref(n), C.c_int(min_obs))
+        self.n = int(n.value)
+        return int(deleted)
+
     def bundle_adjust(self, optimize_poses=True, optimize_geometry=True, min_iterations=1, max_iterations=10,
                       optimize_depth_intrinsics=False, optimize_color_intrinsics=False,
-                      window_start=0, window_end=None, max_pose_iterations=30):
+                      window_start=0, window_end=None, max_pose_iterations=30, end_tasks=True):
         o = BAOptions(int(optimize_depth_intrinsics), int(optimize_color_intrinsics), 0, int(optimize_poses),
                       int(optimize_geometry), min_iterations, max_iterations, window_start,
                       self.K - 1 if window_end is None else window_end, max_pose_iterations)
@@ -186,17 +200,21 @@ class Oracle:
         self.lib.orc_bundle_adjust(C.byref(self.model), C.byref(self.kfs), _p(self.surfels, C.c_float),
                                    C.c_int(self.pitch), C.c_uint32(self.n), _p(self.active, C.c_uint8),
                                    C.byref(o), C.byref(r))
+        if end_tasks:     # increase_ba_iteration_count = true (direct_ba_alternating.cc:725-735)
+            self.surfels_deleted = self.end_tasks()
         return r
 
     def bundle_adjust_pcg(self, optimize_poses=True, optimize_geometry=True, optimize_depth_intrinsics=False,
                           optimize_color_intrinsics=False, min_iterations=1, max_iterations=1, max_inner_iterations=30,
-                          gauge_keyframe=0):
+                          gauge_keyframe=0, end_tasks=True):
         o = PCGOptions(int(optimize_poses), int(optimize_geometry), int(optimize_depth_intrinsics),
                        int(optimize_color_intrinsics), min_iterations, max_iterations, max_inner_iterations, gauge_keyframe)
         r = PCGResult()
         self.lib.orc_bundle_adjust_pcg(C.byref(self.model), C.byref(self.kfs), _p(self.surfels, C.c_float),
                                        C.c_int(self.pitch), C.c_uint32(self.n), _p(self.active, C.c_uint8),
                                        C.byref(o), C.byref(r))
+        if end_tasks:
+            self.surfels_deleted = self.end_tasks()
         return r
 
     def pcg_debug(self, optimize_poses=True, optimize_geometry=True, optimize_depth_intrinsics=False,

@@ -25,25 +25,26 @@ class BAOptions(C.Structure):
     _fields_ = [("optimize_poses", C.c_int), ("optimize_geometry", C.c_int),
                 ("min_iterations", C.c_int), ("max_iterations", C.c_int),
                 ("active_keyframe_window_start", C.c_int), ("active_keyframe_window_end", C.c_int),
-                ("optimize_depth_intrinsics", C.c_int), ("optimize_color_intrinsics", C.c_int)]
+                ("optimize_depth_intrinsics", C.c_int), ("optimize_color_intrinsics", C.c_int), ("end_tasks", C.c_int)]
 
 
 class BAResult(C.Structure):
     _fields_ = [("iterations_done", C.c_int), ("converged", C.c_int), ("n_count", C.c_ulonglong), ("cost", C.c_double),
                 ("pose_iterations_total", C.c_int), ("ms_surfel_activation", C.c_float),
                 ("ms_geometry_optimization", C.c_float), ("ms_pose_optimization", C.c_float),
-                ("kernel_launches", C.c_ulonglong)]
+                ("kernel_launches", C.c_ulonglong), ("surfels_deleted", C.c_uint), ("surfels_size", C.c_uint)]
 
 
 class PCGOptions(C.Structure):
     _fields_ = [("optimize_poses", C.c_int), ("optimize_geometry", C.c_int), ("optimize_depth_intrinsics", C.c_int),
                 ("optimize_color_intrinsics", C.c_int), ("min_iterations", C.c_int), ("max_iterations", C.c_int),
-                ("max_inner_iterations", C.c_int), ("gauge_keyframe", C.c_int)]
+                ("max_inner_iterations", C.c_int), ("gauge_keyframe", C.c_int), ("end_tasks", C.c_int)]
 
 
 class PCGResult(C.Structure):
     _fields_ = [("iterations_done", C.c_int), ("converged", C.c_int), ("inner_iterations_total", C.c_int),
-                ("last_r_norm", C.c_float), ("ms_pcg", C.c_float), ("kernel_launches", C.c_ulonglong)]
+                ("last_r_norm", C.c_float), ("ms_pcg", C.c_float), ("kernel_launches", C.c_ulonglong),
+                ("surfels_deleted", C.c_uint), ("surfels_size", C.c_uint)]
 
 
 _lib = None
@@ -81,6 +82,11 @@ def lib():
         l.ref_bundle_adjust_pcg.argtypes = [C.c_void_p, C.POINTER(PCGOptions), C.POINTER(PCGResult)]
         l.ref_pcg_debug.restype = C.c_uint
         l.ref_pcg_debug.argtypes = [C.c_void_p, C.POINTER(PCGOptions), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.ref_end_tasks.restype = C.c_uint
+        l.ref_end_tasks.argtypes = [C.c_void_p]
+        l.ref_surfels_size.restype = C.c_uint
+        l.ref_surfels_size.argtypes = [C.c_void_p]
+        l.ref_set_min_observation_counts.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         l.ref_snapshot.argtypes = [C.c_void_p]
         l.ref_restore.argtypes = [C.c_void_p]
         l.ref_sync.argtypes = [C.c_void_p]
@@ -161,15 +167,23 @@ class RefDirectBA:
     def set_activation(self, k, a):
         self.l.ref_set_activation(self.h, k, int(a))
 
+    def surfels_size(self):
+        return int(self.l.ref_surfels_size(self.h))
+
+    def end_tasks(self):
+        """PerformBASchemeEndTasks (delete + radius update + compaction); returns the number of deleted surfels."""
+        return int(self.l.ref_end_tasks(self.h))
+
     def surfels(self, rows=8):
-        out = np.zeros((rows, max(self.n, 1)), np.float32)
+        n = self.surfels_size()
+        out = np.zeros((rows, max(n, 1)), np.float32)
         assert self.l.ref_get_surfels(self.h, out.ctypes.data, out.strides[0], rows) == 0
-        return out[:, :self.n]
+        return out[:, :n]
 
     def active(self):
         out = np.zeros(max(self.n, 1), np.uint8)
         assert self.l.ref_get_active(self.h, out.ctypes.data) == 0
-        return out[:self.n]
+        return out[:self.surfels_size()]
 
     def set_active(self, flags):
         f = np.ascontiguousarray(flags, np.uint8)
@@ -218,19 +232,20 @@ class RefDirectBA:
 
     def bundle_adjust(self, optimize_poses=True, optimize_geometry=True, min_iterations=1, max_iterations=10,
                       window_start=0, window_end=None, count_residuals=True, optimize_depth_intrinsics=False,
-                      optimize_color_intrinsics=False):
+                      optimize_color_intrinsics=False, end_tasks=True):
         o = BAOptions(int(optimize_poses), int(optimize_geometry), min_iterations, max_iterations, window_start,
                       self.K - 1 if window_end is None else window_end, int(optimize_depth_intrinsics),
-                      int(optimize_color_intrinsics))
+                      int(optimize_color_intrinsics), int(end_tasks))
         r = BAResult()
         self.l.ref_bundle_adjust(self.h, C.byref(o), C.byref(r), int(count_residuals))
         return r
 
     def bundle_adjust_pcg(self, optimize_poses=True, optimize_geometry=True, optimize_depth_intrinsics=False,
                           optimize_color_intrinsics=False, min_iterations=1, max_iterations=1, max_inner_iterations=30,
-                          gauge_keyframe=0):
+                          gauge_keyframe=0, end_tasks=True):
         o = PCGOptions(int(optimize_poses), int(optimize_geometry), int(optimize_depth_intrinsics),
-                       int(optimize_color_intrinsics), min_iterations, max_iterations, max_inner_iterations, gauge_keyframe)
+                       int(optimize_color_intrinsics), min_iterations, max_iterations, max_inner_iterations, gauge_keyframe,
+                       int(end_tasks))
         r = PCGResult()
         self.l.ref_bundle_adjust_pcg(self.h, C.byref(o), C.byref(r))
         return r
@@ -238,7 +253,7 @@ class RefDirectBA:
     def pcg_debug(self, optimize_poses=True, optimize_geometry=True, optimize_depth_intrinsics=False,
                   optimize_color_intrinsics=False, gauge_keyframe=0):
         o = PCGOptions(int(optimize_poses), int(optimize_geometry), int(optimize_depth_intrinsics),
-                       int(optimize_color_intrinsics), 1, 1, 30, gauge_keyframe)
+                       int(optimize_color_intrinsics), 1, 1, 30, gauge_keyframe, 0)
         n = self.l.ref_pcg_debug(self.h, C.byref(o), None, None, None, None, None)
         r, M, p, g = (np.zeros(n, np.float32) for _ in range(4))
         sc = np.zeros(2, np.float32)

@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 
+#include "badslam/kernel_delete_surfels.h"
 #include "badslam/kernel_opt_geometry.h"
 #include "badslam/kernel_opt_intrinsics.h"
 #include "badslam/kernel_opt_pose.h"
@@ -56,6 +57,8 @@ void UpdateSurfelsFromPCGDeltaCUDA(cudaStream_t stream, u32 surfels_size, CUDABu
                                    u32 surfel_unknown_start_index, const CUDABuffer_<PCGScalar>& pcg_delta);
 void UpdateCFactorsFromPCGDeltaCUDA(cudaStream_t stream, CUDABuffer_<float>* cfactor_buffer, u32 cfactor_unknown_start_index,
                                     const CUDABuffer_<PCGScalar>& pcg_delta);
+void CompactSurfelsCUDA(cudaStream_t stream, void** free_spots_temp_storage, usize* free_spots_temp_storage_bytes, u32 surfel_count,
+                        u32* surfels_size, CUDABuffer_<float>* surfels, CUDABuffer_<u8>* active_surfels);   // kernels.h:292-299
 }  // namespace vis
 
 namespace {
@@ -87,6 +90,7 @@ struct ref_ba_options {
   int min_iterations, max_iterations;
   int active_keyframe_window_start, active_keyframe_window_end;
   int optimize_depth_intrinsics, optimize_color_intrinsics;
+  int end_tasks;   // PerformBASchemeEndTasks at the end (increase_ba_iteration_count = true, direct_ba_alternating.cc:725-735)
 };
 
 struct ref_ba_result {
@@ -96,6 +100,7 @@ struct ref_ba_result {
   int pose_iterations_total;
   float ms_surfel_activation, ms_geometry_optimization, ms_pose_optimization;
   unsigned long long kernel_launches;
+  unsigned int surfels_deleted, surfels_size;
 };
 
 struct ref_context {
@@ -115,7 +120,12 @@ struct ref_context {
   float* intr_b1 = nullptr; float* intr_b2 = nullptr; float* intr_H = nullptr; float* intr_b = nullptr;
   // PCG vectors r, M, delta, g, p (direct_ba_pcg.cc:256-266) + the three scalars
   float* pcg[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; size_t pcg_capacity = 0; float* pcg_scalars = nullptr;
+  // PerformBASchemeEndTasks
+  u32* deleted_count = nullptr; void* free_spots_temp = nullptr; usize free_spots_temp_bytes = 0;
+  int min_observation_count[3] = {1, 2, 3};   // bad_slam_config.h:146,151,158
 };
+
+extern "C" unsigned int ref_end_tasks(ref_context* c);
 
 namespace {
 
@@ -621,17 +631,21 @@ void ref_bundle_adjust(ref_context* c, const ref_ba_options* o, ref_ba_result* r
     }
     DetermineCovisibleActive(c);
   }
+  if (o->end_tasks) res->surfels_deleted = ref_end_tasks(c);
+  res->surfels_size = c->surfels_size;
   res->kernel_launches = c->launches - launches_before;
 }
 
 struct ref_pcg_options {
   int optimize_poses, optimize_geometry, optimize_depth_intrinsics, optimize_color_intrinsics;
   int min_iterations, max_iterations, max_inner_iterations, gauge_keyframe;
+  int end_tasks;
 };
 struct ref_pcg_result {
   int iterations_done, converged, inner_iterations_total;
   float last_r_norm, ms_pcg;
   unsigned long long kernel_launches;
+  unsigned int surfels_deleted, surfels_size;
 };
 
 // DirectBA::BundleAdjustmentPCG (direct_ba_pcg.cc:43-819) without the surfel lifecycle branches; the gauge keyframe is an
@@ -776,6 +790,8 @@ void ref_bundle_adjust_pcg(ref_context* c, const ref_pcg_options* o, ref_pcg_res
   cudaStreamSynchronize(s);
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
+  if (o->end_tasks) res->surfels_deleted = ref_end_tasks(c);
+  res->surfels_size = c->surfels_size;
   res->kernel_launches = c->launches - launches_before;
 }
 
@@ -835,17 +851,53 @@ unsigned int ref_pcg_debug(ref_context* c, const ref_pcg_options* o, float* out_
   return U;
 }
 
+// DirectBA::PerformBASchemeEndTasks (direct_ba.cc:566-653) with do_surfel_updates = false: DeleteSurfelsAndUpdateRadiiCUDA
+// (kernel_delete_surfels.cc:40-98) + CompactSurfelsCUDA, driving the reference's own kernels.  Returns the deleted count.
+unsigned int ref_end_tasks(ref_context* c) {
+  if (c->surfels_size == 0) return 0;
+  cudaStream_t s = c->stream;
+  const size_t K = c->kfs.size();
+  const int min_obs = (K < 10) ? ((K < 5) ? c->min_observation_count[0] : c->min_observation_count[1]) : c->min_observation_count[2];
+  if (!c->deleted_count) cudaMalloc(&c->deleted_count, sizeof(u32));
+  CallResetSurfelAccumForSurfelDeletionAndRadiusUpdateCUDAKernel(s, c->surfels_size, SurfelBuf(c), true);
+  cudaMemsetAsync(c->deleted_count, 0, sizeof(u32), s);
+  c->launches += 1;
+  for (const RefKeyframe& kf : c->kfs) {
+    CallCountObservationsAndFreeSpaceViolationsCUDAKernel(s, MakeProjection(c, kf, MakeFrameTGlobal(kf.pose), c->surfels_size),
+                                                          CUDABuffer_<u16>(kf.radius, c->cfg.depth_h, c->cfg.depth_w, kf.radius_pitch), true);
+    ++c->launches;
+  }
+  CUDABuffer_<u32> deleted_buf(c->deleted_count, 1, 1, sizeof(u32));
+  CallMarkDeletedSurfelsCUDAKernel(s, min_obs, c->surfels_size, SurfelBuf(c), &deleted_buf, true);
+  ++c->launches;
+  u32 deleted = 0;
+  cudaMemcpyAsync(&deleted, c->deleted_count, sizeof(u32), cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+  u32 surfel_count = c->surfels_size - deleted;
+  CUDABuffer_<float> sb = SurfelBuf(c);
+  CompactSurfelsCUDA(s, &c->free_spots_temp, &c->free_spots_temp_bytes, surfel_count, &c->surfels_size, &sb, nullptr);
+  cudaStreamSynchronize(s);
+  return deleted;
+}
+unsigned int ref_surfels_size(ref_context* c) { return c->surfels_size; }
+void ref_set_min_observation_counts(ref_context* c, int b1, int b2, int m) {
+  c->min_observation_count[0] = b1; c->min_observation_count[1] = b2; c->min_observation_count[2] = m;
+}
+
 // Device-side snapshot / restore of the mutable state (surfel data rows, poses, activations) for benchmarking
 // repeated steps from the same starting point without host traffic.
 static float* g_snapshot = nullptr;
 static size_t g_snapshot_pitch = 0;
 static std::vector<RefKeyframe> g_snapshot_kfs;
+static unsigned int g_snapshot_size = 0;
 void ref_snapshot(ref_context* c) {
   if (!g_snapshot) cudaMallocPitch(reinterpret_cast<void**>(&g_snapshot), &g_snapshot_pitch, static_cast<size_t>(c->max_surfels) * 4, 8);
   cudaMemcpy2D(g_snapshot, g_snapshot_pitch, c->surfels, c->surfel_pitch, static_cast<size_t>(c->surfels_size) * 4, 8, cudaMemcpyDeviceToDevice);
   g_snapshot_kfs = c->kfs;
+  g_snapshot_size = c->surfels_size;
 }
 void ref_restore(ref_context* c) {
+  c->surfels_size = g_snapshot_size;
   cudaMemcpy2DAsync(c->surfels, c->surfel_pitch, g_snapshot, g_snapshot_pitch, static_cast<size_t>(c->surfels_size) * 4, 8,
                     cudaMemcpyDeviceToDevice, c->stream);
   for (size_t k = 0; k < c->kfs.size(); ++k) {

@@ -109,7 +109,7 @@ def test_bundle_adjustment_state_machine(tiny_scene):
         return c
 
     c0 = total_cost()
-    r = orc.bundle_adjust(True, True, 1, 30)
+    r = orc.bundle_adjust(True, True, 1, 30, end_tasks=False)   # (the end tasks shrink radii, which changes the descriptor samples)
     assert r.converged and 1 < r.iterations_done <= 30
     assert np.all(orc.activation == 2)      # all inactive
     assert total_cost() < 0.8 * c0          # joint optimisation of poses and geometry lowers the cost

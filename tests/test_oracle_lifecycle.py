@@ -1,0 +1,79 @@
+"""CPU-only: the oracle's PerformBASchemeEndTasks restatement (delete badly observed surfels, update radii, compact;
+direct_ba.cc:566-653, kernel_delete_surfels.cu:42-164, kernel_compact_surfels.cu:159-279) through its properties."""
+import numpy as np
+
+from badslam_b200 import scene as S
+from oracle import cpu_oracle as O
+
+DELETED = np.uint32(0x7fffffff)
+
+
+def perturbed_oracle():
+    """tiny scene with surfels moved out of view, in front of the surface and behind it (scene.displace_surfels)."""
+    sc, away, front, behind = S.displace_surfels(S.make_scene(S.config_by_name("tiny")))
+    return sc, O.Oracle(sc), away, front, behind
+
+
+def expected_compaction(rows, invalid):
+    """kernel_compact_surfels.cu:126-157: the r-th valid surfel counted from the END moves into the r-th free spot."""
+    n = len(invalid)
+    free = np.flatnonzero(invalid)
+    valid_desc = np.flatnonzero(~invalid)[::-1]
+    out = rows.copy()
+    for r, src in enumerate(valid_desc[:len(free)]):
+        if free[r] < src:
+            out[:, free[r]] = rows[:, src]
+    return out[:, :n - len(free)]
+
+
+def test_end_tasks_delete_update_radii_and_compact():
+    sc, orc, away, front, behind = perturbed_oracle()
+    n = sc.num_surfels
+    before = orc.surfels[:8, :n].copy()
+    deleted = orc.end_tasks()
+    assert orc.n == n - deleted and deleted >= len(away)
+    rows = orc.surfels[:8, :orc.n]
+    assert not np.any(rows[0].view(np.uint32) == DELETED)          # compacted: no hole left in [0, surfels_size)
+    # which surfels went: recompute the marks from the scratch rows the step leaves behind is not possible after the
+    # compaction, so re-run on a copy without compaction effects: a second call is idempotent
+    again = orc.end_tasks()
+    assert again == 0 and orc.n == n - deleted
+    assert np.array_equal(rows.view(np.uint32), orc.surfels[:8, :orc.n].view(np.uint32))
+    # the survivors are a subset of the original surfels (positions / normals / descriptors untouched), in the order the
+    # reference's compaction produces
+    key = lambda a: [tuple(c) for c in a[[0, 1, 2, 3, 6, 7]].view(np.uint32).T]
+    orig = {k: i for i, k in enumerate(key(before))}
+    src = np.array([orig[k] for k in key(rows)])
+    assert len(set(src)) == orc.n
+    gone = np.ones(n, bool)
+    gone[src] = False
+    assert gone[away].all()                                          # unobserved surfels are deleted
+    assert gone[front].mean() > 0.9                                  # more free-space violations than observations
+    exp = expected_compaction(before, gone)
+    assert np.array_equal(exp[[0, 1, 2, 3, 5, 6, 7]].view(np.uint32), rows[[0, 1, 2, 3, 5, 6, 7]].view(np.uint32))
+    # radii: the smallest radius^2 measured by an observing keyframe (IEEE half values)
+    r2 = rows[4]
+    assert np.all(np.isfinite(r2)) and np.all(r2 > 0)
+    assert np.array_equal(r2, r2.astype(np.float16).astype(np.float32))
+
+
+def test_min_observation_count_follows_the_bootstrapping_schedule():
+    """direct_ba.h:220-226: 1 below 5 keyframes, 2 below 10, 3 from 10 on."""
+    sc, orc, *_ = perturbed_oracle()
+    assert sc.cfg.num_keyframes < 5
+    n0 = orc.n
+    d1 = orc.end_tasks()
+    sc2, orc2, *_ = perturbed_oracle()
+    orc2.min_observation_counts = (3, 3, 3)
+    d3 = orc2.end_tasks()
+    assert d3 > d1 > 0 and orc2.n == n0 - d3
+
+
+def test_bundle_adjustment_runs_the_end_tasks_once_at_the_end():
+    sc, orc, *_ = perturbed_oracle()
+    n0 = orc.n
+    orc.bundle_adjust(True, True, 2, 2)
+    assert orc.n == n0 - orc.surfels_deleted and orc.surfels_deleted > 0
+    sc2, orc2, *_ = perturbed_oracle()
+    orc2.bundle_adjust(True, True, 2, 2, end_tasks=False)
+    assert orc2.n == n0

@@ -79,7 +79,7 @@ def test_pcg_short_solve_matches_reference_cuda_golden(setup, intr):
     """Two outer iterations x 4 inner PCG steps (few steps: the fp32 CG recurrences have not decorrelated yet)."""
     g, sc, a_init, cf_init = setup
     orc = make_oracle(sc, a_init, cf_init)
-    res = orc.bundle_adjust_pcg(True, True, intr, intr, 2, 2, 4, 1)
+    res = orc.bundle_adjust_pcg(True, True, intr, intr, 2, 2, 4, 1, end_tasks=False)
     tag = "pcgi" if intr else "pcg"
     assert res.iterations_done == 2 and res.inner_iterations_total == 8
     noise = max(max(S.pose_error(g[f"{tag}_ba_poses"][k], g[f"{tag}_ba_poses_rerun"][k])) for k in range(orc.K))
@@ -108,7 +108,7 @@ def test_pcg_converges_and_keeps_the_gauge_keyframe():
         return max(e)
 
     e0 = rel_err(orc.poses)
-    res = orc.bundle_adjust_pcg(min_iterations=5, max_iterations=5, gauge_keyframe=0)
+    res = orc.bundle_adjust_pcg(min_iterations=5, max_iterations=5, gauge_keyframe=0, end_tasks=False)
     assert res.iterations_done == 5 and 5 <= res.inner_iterations_total <= 150
     assert np.array_equal(orc.poses[0], sc.poses_init[0])
     assert rel_err(orc.poses) < 0.2 * e0

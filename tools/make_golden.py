@@ -41,12 +41,12 @@ def golden_for(name, use_depth=True, use_desc=True, tag=""):
     out["geometry_rows"] = ref.surfels()[[0, 1, 2, 3, 6, 7]].copy()
     ref.close()
     ref = ref_cuda.RefDirectBA(sc, use_depth, use_desc)
-    r = ref.bundle_adjust(True, True, 3, 3, count_residuals=True)
+    r = ref.bundle_adjust(True, True, 3, 3, count_residuals=True, end_tasks=False)
     out.update(ba_poses=ref.poses(), ba_activation=ref.activation(), ba_count=int(r.n_count), ba_cost=float(r.cost),
                ba_pose_iterations=int(r.pose_iterations_total), ba_surfels=ref.surfels()[[0, 1, 2, 6, 7]].copy())
     # run-to-run noise of the reference itself (float atomics): a second identical run
     ref2 = ref_cuda.RefDirectBA(sc, use_depth, use_desc)
-    ref2.bundle_adjust(True, True, 3, 3, count_residuals=True)
+    ref2.bundle_adjust(True, True, 3, 3, count_residuals=True, end_tasks=False)
     out["ba_poses_rerun"] = ref2.poses()
     ref.close(); ref2.close()
     os.makedirs("gpurun_out/golden", exist_ok=True)
@@ -91,7 +91,7 @@ def golden_intrinsics_pcg(name="tiny"):
             if intr:
                 out[f"{tag}_{nm}_intr"] = v[hi:].copy()
         out[f"{tag}_scalars"] = scal
-        res = ref.bundle_adjust_pcg(True, True, intr, intr, 2, 2, 4, 1)
+        res = ref.bundle_adjust_pcg(True, True, intr, intr, 2, 2, 4, 1, end_tasks=False)
         out[f"{tag}_ba_poses"], out[f"{tag}_ba_r_norm"] = ref.poses(), np.float32(res.last_r_norm)
         out[f"{tag}_ba_surfels"] = ref.surfels()[[0, 1, 2, 6, 7]].copy()
         if intr:
@@ -99,7 +99,7 @@ def golden_intrinsics_pcg(name="tiny"):
             out["pcgi_ba_depth_K"], out["pcgi_ba_color_K"], out["pcgi_ba_a"] = d, c, np.float32(a)
         ref2 = ref_cuda.RefDirectBA(sc)
         ref2.set_depth_params(a_init, cf_init)
-        ref2.bundle_adjust_pcg(True, True, intr, intr, 2, 2, 4, 1)
+        ref2.bundle_adjust_pcg(True, True, intr, intr, 2, 2, 4, 1, end_tasks=False)
         out[f"{tag}_ba_poses_rerun"] = ref2.poses()
         ref.close(); ref2.close()
     os.makedirs("gpurun_out/golden", exist_ok=True)
@@ -107,12 +107,33 @@ def golden_intrinsics_pcg(name="tiny"):
     print("wrote", name, "intrinsics + pcg", out["intr1_depth_K"], out["pcg_scalars"], out["pcgi_scalars"])
 
 
+def golden_end_tasks(name="tiny"):
+    """PerformBASchemeEndTasks (delete / radius update / compaction) from the reference's kernels on a scene with displaced
+    surfels (scene.displace_surfels)."""
+    from badslam_b200.scene import displace_surfels
+    sc = displace_surfels(make_scene(config_by_name(name)))[0]
+    ref = ref_cuda.RefDirectBA(sc)
+    deleted = ref.end_tasks()
+    rows = ref.surfels()
+    out = {"scene": name, "deleted": deleted, "surfels_size": ref.surfels_size(), "rows": rows.copy(),
+           "surfel_checksum": float(np.sum(sc.surfels[:3, :sc.num_surfels].astype(np.float64)))}
+    ref.close()
+    os.makedirs("gpurun_out/golden", exist_ok=True)
+    np.savez_compressed(f"gpurun_out/golden/{name}_end_tasks.npz", **out)
+    print("wrote", name, "end tasks: deleted", deleted, "of", sc.num_surfels)
+
+
 if __name__ == "__main__":
     if "--extra-only" in sys.argv:
         golden_intrinsics_pcg("tiny")
+        golden_end_tasks("tiny")
+        sys.exit(0)
+    if "--end-tasks-only" in sys.argv:
+        golden_end_tasks("tiny")
         sys.exit(0)
     golden_for("cfg1")
     golden_for("tiny")
     golden_for("tiny", True, False, "_depth_only")
     golden_for("tiny", False, True, "_desc_only")
     golden_intrinsics_pcg("tiny")
+    golden_end_tasks("tiny")
