@@ -48,6 +48,11 @@ class BAResult(C.Structure):
                 ("surfels_deleted", C.c_uint32), ("surfels_size", C.c_uint32)]
 
 
+class PeerHandle(C.Structure):
+    _fields_ = [("surfels_ipc", C.c_ubyte * 64), ("surfels_offset", C.c_uint64), ("active_ipc", C.c_ubyte * 64),
+                ("active_offset", C.c_uint64), ("pitch_bytes", C.c_uint64), ("surfels_size", C.c_uint32), ("rank", C.c_int32)]
+
+
 class PoseCoeffs(C.Structure):
     _fields_ = [("H", C.c_float * 21), ("b", C.c_float * 6),
                 ("n_pair", C.c_uint64), ("n_inimg", C.c_uint64), ("n_depthok", C.c_uint64),
@@ -107,6 +112,9 @@ SYMBOLS = {
     "bba_set_ba_iteration_counts": (C.c_int, [_P, C.c_int, C.c_int]),
     "bba_pcg_debug": (C.c_int, [_P, C.POINTER(BAOptions), C.POINTER(C.c_uint32), _P, _P, _P, _P, _P, _P]),
     "bba_bundle_adjust": (C.c_int, [_P, C.POINTER(BAOptions), C.POINTER(BAResult), _P]),
+    "bba_peer_export": (C.c_int, [_P, _P]),
+    "bba_peer_import": (C.c_int, [_P, _P, C.c_int]),
+    "bba_peer_count": (C.c_int, [_P]),
     "bba_set_collective": (C.c_int, [_P, COLLECTIVE_FN, _P]),
     "bba_shard_surfel_owner": (C.c_int, [C.c_uint32, C.c_int]),
     "bba_shard_surfel_local_index": (C.c_uint32, [C.c_uint32, C.c_int]),

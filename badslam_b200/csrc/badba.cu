@@ -206,6 +206,12 @@ struct bba_context {
   double* h_intr_sums = nullptr;      // pinned
   float* h_intr_x1 = nullptr;         // pinned, 8 floats
 
+  // NVLink peer replicas (bba_peer_import)
+  bba::PeerSet peers{};                       // count == 0: not mapped
+  void* peer_bases[2 * bba::kMaxPeers] = {};  // what cudaIpcOpenMemHandle returned (closed on unmap)
+  int peer_base_count = 0;
+  float* d_barrier = nullptr;
+
   // end-of-BA surfel maintenance (PerformBASchemeEndTasks)
   int last_ba_iteration_count = -1;          // direct_ba.cc:126
   bba::KfRadius* d_kf_radius = nullptr;      // [max_keyframes], lazily allocated
@@ -248,6 +254,12 @@ bba_status Fail(bba_handle h, bba_status s, const std::string& msg) {
     if (e__ != cudaSuccess)                                                                                 \
       return Fail(h, BBA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));                    \
   } while (0)
+
+void UnmapPeers(bba_handle h) {
+  for (int i = 0; i < h->peer_base_count; ++i) cudaIpcCloseMemHandle(h->peer_bases[i]);
+  h->peer_base_count = 0;
+  h->peers = bba::PeerSet{};
+}
 
 Pose PoseFromArray(const float p[7]) {
   Pose r;
@@ -526,6 +538,14 @@ bba_status CheckCollective(bba_handle h) {
 bba_status ExchangeGeometry(bba_handle h, cudaStream_t s) {
   if (h->cfg.world_size <= 1 || h->surfels_size == 0) return BBA_OK;
   const int world = h->cfg.world_size, rank = h->cfg.rank;
+  if (h->peers.count == world - 1) {
+    // the geometry kernels already stored the updated rows into every replica over NVLink: only a barrier is left (every
+    // rank's kernels have completed, in stream order, before its contribution to the all-reduce)
+    if (!h->d_barrier) BBA_CUDA(h, cudaMalloc(&h->d_barrier, sizeof(float)));
+    BBA_CUDA(h, cudaMemsetAsync(h->d_barrier, 0, sizeof(float), s));
+    h->collective(h->collective_user, BBA_COLLECTIVE_ALLREDUCE_SUM, h->d_barrier, 1, s);
+    return BBA_OK;
+  }
   uint32_t shard_len;
   ShardSurfels(h->surfels_size, rank, world, nullptr, &shard_len);
   const size_t need = static_cast<size_t>(world) * bba::kShardRows * shard_len;
@@ -578,6 +598,7 @@ bba_status BuildGeometryArgs(bba_handle h, bba::GeometryArgs* g, cudaStream_t s)
   g->kf_count = cnt;
   g->queue = h->d_geo_queue;
   g->tile_shift = 8;
+  g->peers = (h->cfg.world_size > 1 && h->peers.count == h->cfg.world_size - 1) ? h->peers : bba::PeerSet{};
   if (!h->d_tile_epoch || h->tile_epoch_capacity < (h->surfels_size + 31u) / 32u) {
     cudaFree(h->d_tile_epoch);
     h->tile_epoch_capacity = std::max<uint32_t>((h->cfg.max_surfel_count + 31u) / 32u, (h->surfels_size + 31u) / 32u) + 1;
@@ -1165,6 +1186,8 @@ void bba_destroy(bba_handle h) {
   cudaFree(h->d_all_list);
   cudaFreeHost(h->h_intr_sums);
   cudaFreeHost(h->h_intr_x1);
+  UnmapPeers(h);
+  cudaFree(h->d_barrier);
   cudaFree(h->d_kf_radius);
   cudaFreeHost(h->h_kf_radius);
   cudaFree(h->d_deleted_count);
@@ -1193,6 +1216,7 @@ void bba_destroy(bba_handle h) {
 }
 
 bba_status bba_set_surfels(bba_handle h, float* device_surfels, size_t pitch_bytes, uint32_t surfels_size) {
+  if (h && (device_surfels != h->surfels || pitch_bytes != h->surfel_pitch_bytes)) UnmapPeers(h);
   if (!h) return BBA_ERR_INVALID_ARGUMENT;
   if (!device_surfels || pitch_bytes % 16 != 0 || (reinterpret_cast<uintptr_t>(device_surfels) & 15) != 0 ||
       pitch_bytes < static_cast<size_t>((surfels_size + 3) / 4) * 16 || surfels_size > h->cfg.max_surfel_count)
@@ -1205,6 +1229,7 @@ bba_status bba_set_surfels(bba_handle h, float* device_surfels, size_t pitch_byt
 }
 
 bba_status bba_set_active_flags(bba_handle h, uint8_t* device_flags) {
+  if (h && device_flags != h->active) UnmapPeers(h);
   if (!h || !device_flags) return BBA_ERR_INVALID_ARGUMENT;
   h->active = device_flags;
   return BBA_OK;
@@ -1701,6 +1726,90 @@ bba_status bba_pcg_debug(bba_handle h, const bba_ba_options* o, uint32_t* unknow
   out_scalars[1] = h->h_pcg_scalars[1];
   return MarkStaging(h, s);
 }
+
+// ---- NVLink peer replicas ------------------------------------------------------------------------------------------------
+namespace {
+bba_status AllocationBase(bba_handle h, const void* ptr, void** base) {
+  typedef int (*GetRangeFn)(unsigned long long*, size_t*, unsigned long long);
+  static GetRangeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    BBA_CUDA(h, cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q));
+    if (!p) return Fail(h, BBA_ERR_CUDA, "cuMemGetAddressRange is not available");
+    fn = reinterpret_cast<GetRangeFn>(p);
+  }
+  unsigned long long b = 0;
+  size_t size = 0;
+  if (fn(&b, &size, reinterpret_cast<unsigned long long>(ptr)) != 0) return Fail(h, BBA_ERR_CUDA, "cuMemGetAddressRange failed");
+  *base = reinterpret_cast<void*>(b);
+  return BBA_OK;
+}
+}  // namespace
+
+bba_status bba_peer_export(bba_handle h, bba_peer_handle* out) {
+  if (!h || !out) return BBA_ERR_INVALID_ARGUMENT;
+  if (bba_status st = CheckSurfels(h)) return st;
+  std::memset(out, 0, sizeof(*out));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "bba_peer_handle layout");
+  void* base = nullptr;
+  cudaIpcMemHandle_t ipc;
+  if (bba_status st = AllocationBase(h, h->surfels, &base)) return st;
+  BBA_CUDA(h, cudaIpcGetMemHandle(&ipc, base));
+  std::memcpy(out->surfels_ipc, &ipc, 64);
+  out->surfels_offset = static_cast<uint64_t>(reinterpret_cast<const char*>(h->surfels) - static_cast<const char*>(base));
+  if (bba_status st = AllocationBase(h, h->active, &base)) return st;
+  BBA_CUDA(h, cudaIpcGetMemHandle(&ipc, base));
+  std::memcpy(out->active_ipc, &ipc, 64);
+  out->active_offset = static_cast<uint64_t>(reinterpret_cast<const char*>(h->active) - static_cast<const char*>(base));
+  out->pitch_bytes = h->surfel_pitch_bytes;
+  out->surfels_size = h->surfels_size;
+  out->rank = h->cfg.rank;
+  return BBA_OK;
+}
+
+bba_status bba_peer_import(bba_handle h, const bba_peer_handle* all, int count) {
+  if (!h || !all) return BBA_ERR_INVALID_ARGUMENT;
+  if (count != h->cfg.world_size) return Fail(h, BBA_ERR_INVALID_ARGUMENT, "bba_peer_import: need one handle per rank");
+  if (count - 1 > bba::kMaxPeers) return Fail(h, BBA_ERR_UNSUPPORTED, "bba_peer_import: more than 8 ranks");
+  if (bba_status st = CheckSurfels(h)) return st;
+  UnmapPeers(h);
+  bba::PeerSet ps{};
+  for (int r = 0; r < count; ++r) {
+    if (r == h->cfg.rank) continue;
+    const bba_peer_handle& ph = all[r];
+    if (ph.rank != r || ph.pitch_bytes != h->surfel_pitch_bytes || ph.surfels_size != h->surfels_size) {
+      UnmapPeers(h);
+      return Fail(h, BBA_ERR_INVALID_ARGUMENT, "bba_peer_import: replica layout differs between ranks");
+    }
+    cudaIpcMemHandle_t ipc;
+    void* base_s = nullptr;
+    std::memcpy(&ipc, ph.surfels_ipc, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(&base_s, ipc, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      UnmapPeers(h);
+      return Fail(h, BBA_ERR_CUDA, std::string("cudaIpcOpenMemHandle(surfels): ") + cudaGetErrorString(e));
+    }
+    h->peer_bases[h->peer_base_count++] = base_s;
+    void* base_a = base_s;
+    if (std::memcmp(ph.surfels_ipc, ph.active_ipc, 64) != 0) {
+      std::memcpy(&ipc, ph.active_ipc, 64);
+      e = cudaIpcOpenMemHandle(&base_a, ipc, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        UnmapPeers(h);
+        return Fail(h, BBA_ERR_CUDA, std::string("cudaIpcOpenMemHandle(active): ") + cudaGetErrorString(e));
+      }
+      h->peer_bases[h->peer_base_count++] = base_a;
+    }
+    ps.surfels[ps.count] = reinterpret_cast<float*>(static_cast<char*>(base_s) + ph.surfels_offset);
+    ps.active[ps.count] = reinterpret_cast<uint8_t*>(static_cast<char*>(base_a) + ph.active_offset);
+    ++ps.count;
+  }
+  h->peers = ps;
+  return BBA_OK;
+}
+
+int bba_peer_count(bba_handle h) { return h ? h->peers.count : 0; }
 
 bba_status bba_set_collective(bba_handle h, bba_collective_fn fn, void* user) {
   if (!h) return BBA_ERR_INVALID_ARGUMENT;

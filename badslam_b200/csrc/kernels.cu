@@ -111,10 +111,14 @@ __device__ __forceinline__ float WarpTransposeReduce(float (&v)[32], int lane) {
   return v[0];
 }
 
+#ifndef BBA_POSE_UNROLL
+#define BBA_POSE_UNROLL 1
+#endif
 #ifndef BBA_POSE_MIN_CTAS
 #define BBA_POSE_MIN_CTAS 2   // resident CTAs per SM the register allocation is tuned for
 #endif
 constexpr int kPoseThreads = 256;
+constexpr int kPoseUnroll = BBA_POSE_UNROLL;   // surfels of a chunk evaluated concurrently per lane
 constexpr int kPoseWarps = kPoseThreads / 32;
 constexpr int kPoseStagedRows = 7;   // x y z normal radius^2 d1 d2
 constexpr int kPoseGroup = 8;        // keyframes per work item
@@ -219,7 +223,7 @@ __global__ void __launch_bounds__(kPoseThreads, BBA_POSE_MIN_CTAS) PoseAccumulat
       unsigned touched = 0;
       unsigned n_inimg = 0, n_depthok = 0;
 
-#pragma unroll 1
+#pragma unroll kPoseUnroll
       for (uint32_t j = j0 + lane; j < j0 + (j1 - j0 + 31u) / 32u * 32u; j += 32) {
         int st = 0;
         Assoc r;
@@ -370,6 +374,21 @@ __device__ __forceinline__ void RetireGeoItem(const GeometryArgs& a, uint32_t gr
   }
 }
 
+// Final stores of the geometry step: the local replica and, when peers are mapped, every other rank's replica (NVLink).
+__device__ __forceinline__ void StoreSurfelRow(const GeometryArgs& a, int row, uint32_t i, float v) {
+  const size_t o = static_cast<size_t>(row) * a.pitch + i;
+  a.surfels[o] = v;
+#pragma unroll
+  for (int p = 0; p < kMaxPeers; ++p)
+    if (p < a.peers.count) a.peers.surfels[p][o] = v;
+}
+__device__ __forceinline__ void StoreActiveFlag(const GeometryArgs& a, uint32_t i, uint8_t v) {
+  a.active[i] = v;
+#pragma unroll
+  for (int p = 0; p < kMaxPeers; ++p)
+    if (p < a.peers.count) a.peers.active[p][i] = v;
+}
+
 template <bool DETERMINE, bool NORMALS>
 __global__ void __launch_bounds__(kGeoThreads) ActivationNormalsKernel(const __grid_constant__ GeometryArgs a) {
   const uint32_t tile_len = 1u << a.tile_shift;
@@ -434,11 +453,11 @@ __global__ void __launch_bounds__(kGeoThreads) ActivationNormalsKernel(const __g
         if (DETERMINE) __stcg(a.surfels + (kRowAccum0 + 4) * P + i, act ? 1.f : 0.f);
       } else {
         // SetSurfelInactive + DetermineActiveSurfels (kernel_surfel_activation.cu:38-79)
-        if (DETERMINE) a.active[i] = act ? kSurfelActiveFlag : static_cast<uint8_t>(flags & ~kSurfelActiveFlag);
+        if (DETERMINE) StoreActiveFlag(a, i, act ? kSurfelActiveFlag : static_cast<uint8_t>(flags & ~kSurfelActiveFlag));
         if (NORMALS && act && s3 >= 1.f) {
           // kernel_opt_geometry.cu:577-597: the mean is packed without re-normalisation
           const float inv = 1.f / s3;
-          a.surfels[kRowNormal * P + i] = __uint_as_float(PackNormal(V3(inv * s0, inv * s1, inv * s2)));
+          StoreSurfelRow(a, kRowNormal, i, __uint_as_float(PackNormal(V3(inv * s0, inv * s1, inv * s2))));
         }
       }
     }
@@ -556,9 +575,9 @@ __global__ void __launch_bounds__(kGeoThreads) PositionDescriptorKernel(const __
         // UpdateSurfelPositionCUDAKernel, kernel_opt_geometry.cu:487-507
         if (H00 > 1e-6f) {
           const float t = -1.f * b0 / H00;
-          a.surfels[kRowX * P + i] = gp.x + t * nrm.x;
-          a.surfels[kRowY * P + i] = gp.y + t * nrm.y;
-          a.surfels[kRowZ * P + i] = gp.z + t * nrm.z;
+          StoreSurfelRow(a, kRowX, i, gp.x + t * nrm.x);
+          StoreSurfelRow(a, kRowY, i, gp.y + t * nrm.y);
+          StoreSurfelRow(a, kRowZ, i, gp.z + t * nrm.z);
         }
       } else {
         // UpdateSurfelPositionAndDescriptorCUDAKernel, kernel_opt_geometry.cu:273-361 (in-place Cholesky)
@@ -576,12 +595,12 @@ __global__ void __launch_bounds__(kGeoThreads) PositionDescriptorKernel(const __
         const float x1 = (y1 - L12 * x2) / L11;
         const float x0 = (y0 - L02 * x2 - L01 * x1) / L00;
         if (x0 != 0) {
-          a.surfels[kRowX * P + i] = gp.x - x0 * nrm.x;
-          a.surfels[kRowY * P + i] = gp.y - x0 * nrm.y;
-          a.surfels[kRowZ * P + i] = gp.z - x0 * nrm.z;
+          StoreSurfelRow(a, kRowX, i, gp.x - x0 * nrm.x);
+          StoreSurfelRow(a, kRowY, i, gp.y - x0 * nrm.y);
+          StoreSurfelRow(a, kRowZ, i, gp.z - x0 * nrm.z);
         }
-        if (x1 != 0) a.surfels[kRowD1 * P + i] = fmaxf(-180.f, fminf(180.f, d1 - x1));
-        if (x2 != 0) a.surfels[kRowD2 * P + i] = fmaxf(-180.f, fminf(180.f, d2 - x2));
+        if (x1 != 0) StoreSurfelRow(a, kRowD1, i, fmaxf(-180.f, fminf(180.f, d1 - x1)));
+        if (x2 != 0) StoreSurfelRow(a, kRowD2, i, fmaxf(-180.f, fminf(180.f, d2 - x2)));
       }
     }
     RetireGeoItem(a, group, tile);
@@ -625,7 +644,7 @@ void LaunchActivationAndNormals(const GeometryArgs& a, int sm_count, bool determ
   if (a.end <= a.begin || (!determine_activation && !update_normals)) return;
   if (a.kf_count <= 0) {
     // no keyframe to look at: activation clears every flag, normals keep their value
-    if (determine_activation) cudaMemsetAsync(a.active, 0, a.n, stream);   // (every shard: the other ranks clear theirs as well)
+    if (determine_activation) cudaMemsetAsync(a.active, 0, a.n, stream);   // (every rank clears its whole replica)
     return;
   }
   if (determine_activation && update_normals) LaunchGeo(ActivationNormalsKernel<true, true>, a, sm_count, stream);

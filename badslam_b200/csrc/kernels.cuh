@@ -53,6 +53,16 @@ struct PoseSolveArgs {
 // Device-side Gauss-Newton step for every keyframe in the list (direct_ba_alternating.cc:173-233).
 void LaunchPoseSolve(const PoseSolveArgs& args, cudaStream_t stream);
 
+// Replicas of the surfel buffer / active flags on the OTHER ranks of a one-process-per-GPU job, mapped into this process
+// (CUDA IPC) and written directly over NVLink by the geometry kernels: the owner of a surfel stores its updated rows into
+// every replica, so the "all-gather" of the geometry step is fused into the kernels' own final stores.
+constexpr int kMaxPeers = 7;
+struct PeerSet {
+  int count;                   // 0: no peers mapped (single GPU, or the host-collective exchange is used)
+  float* surfels[kMaxPeers];   // same pitch / layout as the local buffer
+  uint8_t* active[kMaxPeers];
+};
+
 struct GeometryArgs {
   CameraParams cam;
   float* surfels;
@@ -67,6 +77,7 @@ struct GeometryArgs {
   unsigned int* queue;         // work-item counter (reset by the launcher)
   unsigned int* tile_epoch;    // [ceil(n / 32)] keyframe groups retired per tile (reset by the launcher)
   int tile_shift;              // log2(surfels per tile), 5..8; chosen by the launcher
+  PeerSet peers;
 };
 // SetSurfelInactive + DetermineActiveSurfels (kernel_surfel_activation.cu:38-79) fused with the normal
 // accumulation + update (kernel_opt_geometry.cu:527-597).

@@ -415,6 +415,22 @@ class DirectBA:
                                             g.ctypes.data, sc.ctypes.data, self._stream_ptr(stream)))
         return r, M, p, g, sc
 
+    def EnablePeerExchange(self, group=None) -> int:
+        """Maps the surfel replicas of the other ranks into this process (CUDA IPC over NVLink, bba_peer_export /
+        bba_peer_import): the geometry kernels then store updated surfels straight into every replica and the exchange
+        step is a barrier.  Collective call; returns the number of mapped peers."""
+        import torch.distributed as dist
+        ph = _lib.PeerHandle()
+        self._check(self._lib.bba_peer_export(self._h, C.byref(ph)))
+        world = dist.get_world_size(group)
+        blobs = [None] * world
+        dist.all_gather_object(blobs, bytes(ph), group=group)
+        arr = (_lib.PeerHandle * world)()
+        for r, b in enumerate(blobs):
+            C.memmove(C.byref(arr[r]), b, C.sizeof(_lib.PeerHandle))
+        self._check(self._lib.bba_peer_import(self._h, arr, world))
+        return int(self._lib.bba_peer_count(self._h))
+
     # -- multi-GPU (one process per GPU) ---------------------------------------------------------------
     def SetCollective(self, group=None):
         """Registers the exchange step (bba_set_collective) on top of torch.distributed (NCCL over NVLink): in-place

@@ -169,8 +169,16 @@ def run_ours(args, scene, rank, world):
             dist.barrier(device_ids=[dev.index])
 
     ba = DirectBA.from_scene(scene, device=dev, rank=rank, world_size=world)
+    exchange = "none"
     if world > 1:
         ba.SetCollective()
+        exchange = "nccl all-gather"
+        if not os.environ.get("BADBA_NO_PEER"):
+            try:   # geometry exchange fused into the kernels: stores into the peers' replicas over NVLink (CUDA IPC)
+                if ba.EnablePeerExchange() == world - 1:
+                    exchange = "nvlink peer stores from the geometry kernels + 1-element all-reduce barrier"
+            except Exception as e:   # noqa: BLE001  (IPC not permitted in this environment: keep the NCCL exchange)
+                exchange = f"nccl all-gather (peer mapping unavailable: {type(e).__name__})"
     surf = ba.surfels()
     backup = surf[:8].clone()
     poses0 = scene.poses_init.copy()
@@ -277,8 +285,9 @@ def run_ours(args, scene, rank, world):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_port_baseline(scene)
     if world > 1:
-        out["config"]["parallelism"] = (f"gpus={world}: keyframe images + surfels replicated; geometry step sharded by surfel range "
-                                        "(1 all-gather), pose step sharded by keyframe (1 all-reduce); NCCL over NVLink")
+        out["config"]["parallelism"] = (f"gpus={world}: keyframe images + surfels replicated; geometry step sharded by 256-surfel "
+                                        f"granules dealt round-robin (exchange: {exchange}), pose step sharded by keyframe, "
+                                        "balanced by measured work (1 all-reduce of K x 17 floats); NCCL over NVLink")
         dist.barrier(device_ids=[dev.index])
     return out
 

@@ -227,6 +227,24 @@ bba_status bba_bundle_adjust(bba_handle h, const bba_ba_options* options, bba_ba
  *    loops of its keyframes locally, and ONE all-reduce (sum of disjoint slots, K x 17 floats) publishes the poses.
  * Registers the exchange callback; required before any hot-path call when world_size > 1. */
 bba_status bba_set_collective(bba_handle h, bba_collective_fn fn, void* user);
+/* Fused geometry exchange over NVLink peer memory (optional, <= 8 ranks on one node): every rank exports CUDA IPC handles
+ * of its surfel buffer + active flags, the host passes the handles of ALL ranks (indexed by rank) to every rank, and from
+ * then on the geometry kernels store a surfel's updated rows straight into every replica; the all-gather of the exchange
+ * step degenerates to a 1-element all-reduce used as a barrier.  Without it the host-collective all-gather is used.
+ * The mapping is dropped by bba_set_surfels / bba_set_surfels_host / bba_set_active_flags. */
+typedef struct {
+  unsigned char surfels_ipc[64];   /* cudaIpcMemHandle_t of the allocation holding the surfel buffer */
+  uint64_t surfels_offset;         /* byte offset of the buffer inside that allocation */
+  unsigned char active_ipc[64];
+  uint64_t active_offset;
+  uint64_t pitch_bytes;
+  uint32_t surfels_size;
+  int32_t rank;
+} bba_peer_handle;
+bba_status bba_peer_export(bba_handle h, bba_peer_handle* out);
+bba_status bba_peer_import(bba_handle h, const bba_peer_handle* all_ranks, int count);
+int bba_peer_count(bba_handle h);
+
 /* The partition itself, exposed so that hosts and tests can reason about it.
  * Surfels: 256-surfel granules are dealt round-robin (granule g -> rank g % world_size), which gives every rank the same
  * mix of well- and poorly-observed surfels; a rank addresses its surfels through a dense local index, and the exchange

@@ -31,8 +31,14 @@ def _worker(rank, world, port, out_dir):
     ba.SetCollective()
     r = ba.BundleAdjustment(None, False, False, False, True, True, 3, 3)
     poses, act = ba.GetKeyframeStates()
+    # the same with the geometry exchange fused into the kernels (stores into the peers' replicas over NVLink)
+    bp = DirectBA.from_scene(sc, device=f"cuda:{rank}", rank=rank, world_size=world)
+    bp.SetCollective()
+    assert bp.EnablePeerExchange() == world - 1
+    bp.BundleAdjustment(None, False, False, False, True, True, 3, 3)
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), poses=poses, act=act, surfels=ba.GetSurfelsHost(), active=ba.GetActiveHost(),
-             counts=np.array([r.depth_residual_count, r.descriptor_residual_count, r.pose_iterations_total]))
+             counts=np.array([r.depth_residual_count, r.descriptor_residual_count, r.pose_iterations_total]),
+             peer_poses=bp.GetKeyframeStates()[0], peer_surfels=bp.GetSurfelsHost(), peer_active=bp.GetActiveHost())
     dist.barrier(device_ids=[rank])
     dist.destroy_process_group()
 
@@ -55,6 +61,10 @@ def test_two_rank_bundle_adjustment_matches_single_gpu(tmp_path):
     assert np.array_equal(r0["poses"], r1["poses"]) and np.array_equal(r0["act"], r1["act"])
     assert np.array_equal(r0["surfels"].view(np.uint32), r1["surfels"].view(np.uint32))
     assert np.array_equal(r0["active"], r1["active"])
+    # the NVLink peer-store exchange gives exactly the same replicas as the host-collective all-gather
+    for r_ in (r0, r1):
+        assert np.array_equal(r_["peer_surfels"].view(np.uint32), r0["surfels"].view(np.uint32))
+        assert np.array_equal(r_["peer_active"], r0["active"]) and np.array_equal(r_["peer_poses"], r0["poses"])
     # ... and with the single-GPU run up to the summation order of the pose normal equations
     assert tuple(r0["counts"]) == (r.depth_residual_count, r.descriptor_residual_count, r.pose_iterations_total)
     assert np.array_equal(r0["act"], act)
