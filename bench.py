@@ -421,6 +421,7 @@ def run_reference(args, scene):
     if residuals is None:
         from badslam_b200.direct_ba import DirectBA
         ba = DirectBA.from_scene(scene)
+        ba.SetLastBAIterationCount(ba.ba_iteration_count())   # (no end-of-scheme maintenance: same surfel set as the reference run)
         rr = ba.BundleAdjustment(None, False, False, False, True, True, 1, 1, increase_ba_iteration_count=False)
         residuals = rr.depth_residual_count + rr.descriptor_residual_count
         ours_pairs = rr.depth_residual_count + rr.descriptor_residual_count // 2
