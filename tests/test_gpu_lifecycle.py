@@ -69,3 +69,15 @@ def test_bundle_adjustment_end_task_schedule(mods):
     ba2 = DirectBA.from_scene(sc)      # a fresh handle (counters 0 != -1) runs the end tasks before its first iteration
     r3 = ba2.BundleAdjustment(None, False, False, False, True, True, 1, 1, increase_ba_iteration_count=False)
     assert r3.surfels_deleted > 0 and ba2.surfels_size() == n - r3.surfels_deleted and ba2.last_ba_iteration_count() == 0
+
+
+def test_end_tasks_against_golden_fixture(mods):
+    """The CUDA path against tests/golden/tiny_end_tasks.npz (outputs of the reference's kernels)."""
+    import os
+    S, DirectBA, O, R = mods
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiny_end_tasks.npz"))
+    sc = perturb(S.make_scene(S.config_by_name("tiny")))
+    ba = DirectBA.from_scene(sc)
+    deleted, size = ba.PerformBASchemeEndTasks()
+    assert deleted == int(g["deleted"]) and size == int(g["surfels_size"])
+    assert np.array_equal(ba.GetSurfelsHost().view(np.uint32), g["rows"].view(np.uint32))

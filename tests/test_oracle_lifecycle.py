@@ -77,3 +77,14 @@ def test_bundle_adjustment_runs_the_end_tasks_once_at_the_end():
     sc2, orc2, *_ = perturbed_oracle()
     orc2.bundle_adjust(True, True, 2, 2, end_tasks=False)
     assert orc2.n == n0
+
+
+def test_end_tasks_match_reference_cuda_golden():
+    """tests/golden/tiny_end_tasks.npz: outputs of the reference's own kernels (tools/make_golden.py::golden_end_tasks)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiny_end_tasks.npz"))
+    sc, orc, *_ = perturbed_oracle()
+    assert abs(float(np.sum(sc.surfels[:3, :sc.num_surfels].astype(np.float64))) - float(g["surfel_checksum"])) < 1e-6
+    deleted = orc.end_tasks()
+    assert deleted == int(g["deleted"]) and orc.n == int(g["surfels_size"])
+    assert np.array_equal(orc.surfels[:8, :orc.n].view(np.uint32), g["rows"].view(np.uint32))
