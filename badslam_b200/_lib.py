@@ -45,7 +45,8 @@ class BAResult(C.Structure):
                 ("ms_pose_optimization", C.c_float), ("ms_intrinsics_optimization", C.c_float),
                 ("kernel_launches", C.c_uint64),
                 ("pcg_inner_iterations_total", C.c_int), ("pcg_last_r_norm", C.c_float), ("ms_pcg", C.c_float),
-                ("surfels_deleted", C.c_uint32), ("surfels_size", C.c_uint32)]
+                ("surfels_deleted", C.c_uint32), ("surfels_size", C.c_uint32),
+                ("surfels_created", C.c_uint32), ("surfels_merged", C.c_uint32)]
 
 
 class PeerHandle(C.Structure):
@@ -110,6 +111,9 @@ SYMBOLS = {
     "bba_surfels_size": (C.c_uint32, [_P]),
     "bba_get_ba_iteration_counts": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "bba_set_ba_iteration_counts": (C.c_int, [_P, C.c_int, C.c_int]),
+    "bba_create_surfels_for_keyframe": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_uint32), _P]),
+    "bba_merge_surfels_for_keyframe": (C.c_int, [_P, C.c_int, C.POINTER(C.c_uint32), _P]),
+    "bba_compact_surfels": (C.c_int, [_P, C.c_uint32, C.c_int, C.POINTER(C.c_uint32), _P]),
     "bba_pcg_debug": (C.c_int, [_P, C.POINTER(BAOptions), C.POINTER(C.c_uint32), _P, _P, _P, _P, _P, _P]),
     "bba_bundle_adjust": (C.c_int, [_P, C.POINTER(BAOptions), C.POINTER(BAResult), _P]),
     "bba_peer_export": (C.c_int, [_P, _P]),
@@ -142,7 +146,7 @@ def load():
         fn = getattr(lib, name)   # AttributeError if the symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.bba_abi_version() != 3:
+    if lib.bba_abi_version() != 4:
         raise ImportError("libbadba_b200.so ABI version mismatch")
     _lib = lib
     return lib

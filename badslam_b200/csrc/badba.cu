@@ -13,6 +13,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -127,6 +128,11 @@ struct Keyframe {
   cudaArray_t luma = nullptr;   // library-owned u8 CUDA array (the .w channel of the caller's uchar4 colour buffer)
   cudaTextureObject_t tex = 0;
   void* owned[3] = {nullptr, nullptr, nullptr};   // depth / normals / radius copies made by bba_add_keyframe_host
+  const uint8_t* rgba = nullptr;   // uchar4 colour image (caller-owned, or owned_rgba): surfel colours at creation
+  size_t rgba_pitch = 0;
+  void* owned_rgba = nullptr;
+  int last_active_in_ba_iteration = -1;   // keyframe.cc:47-48
+  int last_covis_in_ba_iteration = -1;
   Pose pose;                 // global_T_frame
   int activation = BBA_KF_ACTIVE;
   float min_depth = 0.f, max_depth = 0.f;
@@ -212,6 +218,15 @@ struct bba_context {
   int peer_base_count = 0;
   float* d_barrier = nullptr;
 
+  // in-loop surfel lifecycle (creation / merge), lazily allocated
+  unsigned int* d_sup = nullptr;         // [3][cells]
+  unsigned int* d_cell_bits = nullptr;   // [cells]
+  unsigned int* d_flags = nullptr;       // [w * h]
+  unsigned int* d_scan_out = nullptr;    // [w * h]
+  unsigned int* d_scan_sums = nullptr;
+  bba::CovisEntry* d_covis = nullptr;    // [max_keyframes]
+  bba::CovisEntry* h_covis = nullptr;    // pinned
+
   // end-of-BA surfel maintenance (PerformBASchemeEndTasks)
   int last_ba_iteration_count = -1;          // direct_ba.cc:126
   bba::KfRadius* d_kf_radius = nullptr;      // [max_keyframes], lazily allocated
@@ -260,6 +275,13 @@ void UnmapPeers(bba_handle h) {
   h->peer_base_count = 0;
   h->peers = bba::PeerSet{};
 }
+
+// BADBA_TRACE=1: stage markers on stderr (debugging aid for host-side faults)
+#define BBA_TRACE(msg)                                                                   \
+  do {                                                                                   \
+    static const bool on__ = std::getenv("BADBA_TRACE") != nullptr;                      \
+    if (on__) { std::fprintf(stderr, "[badba] %s:%d %s\n", __func__, __LINE__, msg); std::fflush(stderr); } \
+  } while (0)
 
 Pose PoseFromArray(const float p[7]) {
   Pose r;
@@ -705,6 +727,145 @@ bba_status OptimizeIntrinsics(bba_handle h, bool opt_depth, bool opt_color, cuda
   return BBA_OK;
 }
 
+int GetMinObservationCount(bba_handle h);
+
+// ---- in-loop surfel lifecycle ---------------------------------------------------------------------------------------------
+uint32_t SurfelCapacity(bba_handle h) {
+  return std::min<uint32_t>(h->cfg.max_surfel_count, static_cast<uint32_t>(h->surfel_pitch_bytes / sizeof(float)));
+}
+
+bba_status MakeLifecycleArgs(bba_handle h, int k, bba::LifecycleArgs* a, cudaStream_t s) {
+  const uint32_t cells = static_cast<uint32_t>(h->cf_w) * h->cf_h;
+  const uint32_t pixels = static_cast<uint32_t>(h->cfg.depth_width) * h->cfg.depth_height;
+  if (!h->d_sup) {
+    BBA_CUDA(h, cudaMalloc(&h->d_sup, sizeof(unsigned int) * 3 * cells));
+    BBA_CUDA(h, cudaMalloc(&h->d_cell_bits, sizeof(unsigned int) * cells));
+    BBA_CUDA(h, cudaMalloc(&h->d_flags, sizeof(unsigned int) * pixels));
+    BBA_CUDA(h, cudaMalloc(&h->d_scan_out, sizeof(unsigned int) * pixels));
+    BBA_CUDA(h, cudaMalloc(&h->d_scan_sums, sizeof(unsigned int) * bba::ScanScratchWords(pixels)));
+    BBA_CUDA(h, cudaMalloc(&h->d_covis, sizeof(bba::CovisEntry) * h->cfg.max_keyframes));
+    BBA_CUDA(h, cudaMallocHost(&h->h_covis, sizeof(bba::CovisEntry) * h->cfg.max_keyframes));
+  }
+  if (!h->d_deleted_count) {
+    BBA_CUDA(h, cudaMalloc(&h->d_deleted_count, sizeof(unsigned int)));
+    BBA_CUDA(h, cudaMallocHost(&h->h_deleted_count, sizeof(unsigned int)));
+  }
+  const Keyframe& kf = h->keyframes[k];
+  a->cam = MakeCamera(h);
+  bba::ToMatrix3x4(bba::Inverse(kf.pose), a->T);
+  bba::ToMatrix3x4(kf.pose, a->G);
+  a->depth = kf.depth;
+  a->normals = kf.normals;
+  a->radius = kf.radius;
+  a->depth_pitch = static_cast<uint32_t>(kf.depth_pitch);
+  a->normals_pitch = static_cast<uint32_t>(kf.normals_pitch);
+  a->radius_pitch = static_cast<uint32_t>(kf.radius_pitch);
+  a->tex = kf.tex;
+  a->rgba = kf.rgba;
+  a->rgba_pitch = static_cast<uint32_t>(kf.rgba_pitch);
+  a->surfels = h->surfels;
+  a->pitch = static_cast<uint32_t>(h->surfel_pitch_bytes / sizeof(float));
+  a->n = h->surfels_size;
+  a->sup = h->d_sup;
+  a->cell_bits = h->d_cell_bits;
+  a->cells = cells;
+  a->flags = h->d_flags;
+  a->covis = h->d_covis;
+  a->covis_count = 0;
+  a->min_observation_count = GetMinObservationCount(h);
+  const float c = static_cast<float>(h->cfg.sparse_surfel_cell_size);
+  a->cell_merge_dist_squared = c * c * h->cfg.surfel_merge_dist_factor * h->cfg.surfel_merge_dist_factor;   // kernel_supporting_surfels.cc:76-78
+  a->counter = h->d_deleted_count;
+  (void)s;
+  return BBA_OK;
+}
+
+// DirectBA::CreateSurfelsForKeyframe (direct_ba.cc:340-405)
+bba_status CreateSurfelsForKeyframe(bba_handle h, int k, bool filter, cudaStream_t s, uint32_t* new_count) {
+  *new_count = 0;
+  const Keyframe& kf = h->keyframes[k];
+  if (!kf.radius || !kf.rgba) return Fail(h, BBA_ERR_STATE, "surfel creation needs the keyframe's radius and colour buffers");
+  BBA_TRACE("create: enter");
+  if (bba_status st = WaitStaging(h)) return st;
+  bba::LifecycleArgs a;
+  if (bba_status st = MakeLifecycleArgs(h, k, &a, s)) return st;
+  BBA_TRACE("create: args made");
+  if (filter) {   // covis_T_frame for every co-visible keyframe (direct_ba.cc:365-370)
+    int cnt = 0;
+    for (int c : kf.covis) {
+      const Keyframe& other = h->keyframes[c];
+      bba::CovisEntry& e = h->h_covis[cnt++];
+      bba::ToMatrix3x4(bba::Compose(bba::Inverse(other.pose), kf.pose), e.R);
+      e.depth = other.depth;
+      e.normals = other.normals;
+      e.depth_pitch = static_cast<uint32_t>(other.depth_pitch);
+      e.normals_pitch = static_cast<uint32_t>(other.normals_pitch);
+      e.pad[0] = e.pad[1] = 0;
+    }
+    a.covis_count = cnt;
+    if (cnt) BBA_CUDA(h, cudaMemcpyAsync(h->d_covis, h->h_covis, sizeof(bba::CovisEntry) * cnt, cudaMemcpyHostToDevice, s));
+  }
+  BBA_TRACE("create: covis uploaded");
+  const uint32_t pixels = static_cast<uint32_t>(h->cfg.depth_width) * h->cfg.depth_height;
+  bba::LaunchSupportSurfels(a, h->sm_count, s);     // DetermineSupportingSurfelsCUDA: is the cell supported at all
+  bba::LaunchSeedNewSurfels(a, filter, s);
+  bba::LaunchExclusiveScan(h->d_flags, pixels, h->d_scan_out, h->d_scan_sums, s);
+  h->launches += 6 + (filter ? 1 : 0);
+  BBA_CUDA(h, cudaGetLastError());
+  const uint32_t n_blocks = (pixels + 4095) / 4096;
+  BBA_CUDA(h, cudaMemcpyAsync(h->h_deleted_count, h->d_scan_sums + n_blocks, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+  BBA_CUDA(h, cudaStreamSynchronize(s));   // kernel_create_surfels.cu:466-474
+  h->staging_pending = false;
+  const uint32_t created = *h->h_deleted_count;
+  BBA_TRACE("create: counted");
+  if (created == 0) return BBA_OK;
+  if (h->surfels_size + static_cast<uint64_t>(created) > SurfelCapacity(h)) {
+    // the reference logs "Maximum surfel count exceeded" and creates nothing (kernel_create_surfels.cc:163-166)
+    h->error = "maximum surfel count exceeded: no surfels created for this keyframe";
+    return BBA_OK;
+  }
+  bba::LaunchCreateSurfels(a, h->d_scan_out, s);
+  ++h->launches;
+  BBA_CUDA(h, cudaGetLastError());
+  BBA_TRACE("create: appended");
+  h->surfels_size += created;
+  *new_count = created;
+  return MarkStaging(h, s);
+}
+
+// DetermineSupportingSurfelsAndMergeSurfelsCUDA (kernel_supporting_surfels.cc:40-118); deleted surfels are only marked
+bba_status MergeSurfelsForKeyframe(bba_handle h, int k, cudaStream_t s, uint32_t* deleted) {
+  *deleted = 0;
+  if (h->surfels_size == 0) return BBA_OK;
+  bba::LifecycleArgs a;
+  if (bba_status st = MakeLifecycleArgs(h, k, &a, s)) return st;
+  BBA_CUDA(h, cudaMemsetAsync(h->d_deleted_count, 0, sizeof(unsigned int), s));
+  bba::LaunchMergeSurfels(a, h->sm_count, s);
+  h->launches += 5;
+  BBA_CUDA(h, cudaGetLastError());
+  BBA_CUDA(h, cudaMemcpyAsync(h->h_deleted_count, h->d_deleted_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+  BBA_CUDA(h, cudaStreamSynchronize(s));   // kernel_supporting_surfels.cc:93-96
+  *deleted = *h->h_deleted_count;
+  return BBA_OK;
+}
+
+bba_status CompactSurfels(bba_handle h, uint32_t free_count, bool with_active, cudaStream_t s) {
+  const uint32_t N = h->surfels_size;
+  if (free_count == 0 || N == 0) return BBA_OK;
+  const uint32_t words = bba::CompactScratchWords(N);
+  if (words > h->compact_sums_capacity) {
+    cudaFree(h->d_compact_sums);
+    h->compact_sums_capacity = std::max(words, bba::CompactScratchWords(std::max(h->cfg.max_surfel_count, N)));
+    BBA_CUDA(h, cudaMalloc(&h->d_compact_sums, sizeof(unsigned int) * h->compact_sums_capacity));
+  }
+  bba::LaunchCompactSurfels(h->surfels, static_cast<uint32_t>(h->surfel_pitch_bytes / sizeof(float)), N, free_count, h->d_compact_sums,
+                            with_active ? h->active : nullptr, s);
+  h->launches += 4;
+  BBA_CUDA(h, cudaGetLastError());
+  h->surfels_size = N - free_count;
+  return BBA_OK;
+}
+
 // direct_ba.h:220-226
 int GetMinObservationCount(bba_handle h) {
   const size_t K = h->keyframes.size();
@@ -715,7 +876,7 @@ int GetMinObservationCount(bba_handle h) {
 // DirectBA::PerformBASchemeEndTasks (direct_ba.cc:566-653) without the final merge (do_surfel_updates is not supported yet):
 // DeleteSurfelsAndUpdateRadiiCUDA over every keyframe, then CompactSurfelsCUDA.  Replicated on every rank of a multi-GPU
 // job (once per BA call, deterministic, identical inputs -> identical surfel buffers without an exchange).
-bba_status PerformEndTasks(bba_handle h, cudaStream_t s, uint32_t* deleted_out) {
+bba_status PerformEndTasks(bba_handle h, cudaStream_t s, uint32_t* deleted_out, bool do_surfel_updates = false) {
   if (deleted_out) *deleted_out = 0;
   const int K = static_cast<int>(h->keyframes.size());
   const uint32_t N = h->surfels_size;
@@ -723,8 +884,21 @@ bba_status PerformEndTasks(bba_handle h, cudaStream_t s, uint32_t* deleted_out) 
   if (!h->d_kf_radius) {
     BBA_CUDA(h, cudaMalloc(&h->d_kf_radius, sizeof(bba::KfRadius) * h->cfg.max_keyframes));
     BBA_CUDA(h, cudaMallocHost(&h->h_kf_radius, sizeof(bba::KfRadius) * h->cfg.max_keyframes));
+  }
+  if (!h->d_deleted_count) {
     BBA_CUDA(h, cudaMalloc(&h->d_deleted_count, sizeof(unsigned int)));
     BBA_CUDA(h, cudaMallocHost(&h->h_deleted_count, sizeof(unsigned int)));
+  }
+  BBA_TRACE("end tasks");
+  // merge similar surfels using all keyframes which were active in this BA iteration block (direct_ba.cc:577-601)
+  uint32_t merged = 0;
+  if (do_surfel_updates) {
+    for (int k = 0; k < K; ++k) {
+      if (h->keyframes[k].last_active_in_ba_iteration != h->ba_iteration_count) continue;
+      uint32_t d = 0;
+      if (bba_status st = MergeSurfelsForKeyframe(h, k, s, &d)) return st;
+      merged += d;
+    }
   }
   if (bba_status st = UploadKeyframes(h, s)) return st;   // (waits for the previous use of the staging buffers)
   for (int k = 0; k < K; ++k) {
@@ -763,7 +937,8 @@ bba_status PerformEndTasks(bba_handle h, cudaStream_t s, uint32_t* deleted_out) 
   BBA_CUDA(h, cudaMemcpyAsync(h->h_deleted_count, h->d_deleted_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
   BBA_CUDA(h, cudaStreamSynchronize(s));   // kernel_delete_surfels.cc:93-96
   h->staging_pending = false;
-  const uint32_t deleted = *h->h_deleted_count;
+  BBA_TRACE("stats done");
+  const uint32_t deleted = *h->h_deleted_count + merged;
   if (deleted_out) *deleted_out = deleted;
   if (deleted > 0) {   // kernel_compact_surfels.cu:167-169
     const uint32_t words = bba::CompactScratchWords(N);
@@ -772,7 +947,7 @@ bba_status PerformEndTasks(bba_handle h, cudaStream_t s, uint32_t* deleted_out) 
       h->compact_sums_capacity = std::max(words, bba::CompactScratchWords(std::max(h->cfg.max_surfel_count, N)));
       BBA_CUDA(h, cudaMalloc(&h->d_compact_sums, sizeof(unsigned int) * h->compact_sums_capacity));
     }
-    bba::LaunchCompactSurfels(h->surfels, a.pitch, N, deleted, h->d_compact_sums, s);
+    bba::LaunchCompactSurfels(h->surfels, a.pitch, N, deleted, h->d_compact_sums, nullptr, s);   // direct_ba.cc:618: no active flags
     h->launches += 4;
     BBA_CUDA(h, cudaGetLastError());
     h->surfels_size = N - deleted;
@@ -867,12 +1042,29 @@ bba_status BundleAdjustPCG(bba_handle h, const bba_ba_options* o, bba_ba_result*
   if (!o->increase_ba_iteration_count && h->ba_iteration_count != h->last_ba_iteration_count) {   // :157-161
     h->last_ba_iteration_count = h->ba_iteration_count;
     uint32_t deleted = 0;
-    if (bba_status st = PerformEndTasks(h, s, &deleted)) return st;
+    if (bba_status st = PerformEndTasks(h, s, &deleted, o->do_surfel_updates != 0)) return st;
     res->surfels_deleted += deleted;
   }
+  std::vector<int> keyframes_with_new_surfels;
 
   for (int iteration = 0; iteration < o->max_iterations; ++iteration) {
     ++res->iterations_done;
+    // surfel creation (:183-206)
+    keyframes_with_new_surfels.clear();
+    if (opt_geometry && o->do_surfel_updates) {
+      for (int k = 0; k < K; ++k) {
+        Keyframe& kf = h->keyframes[k];
+        if (kf.activation == BBA_KF_ACTIVE && kf.last_active_in_ba_iteration != h->ba_iteration_count) {
+          kf.last_active_in_ba_iteration = h->ba_iteration_count;
+          uint32_t created = 0;
+          if (bba_status st = CreateSurfelsForKeyframe(h, k, /*filter_new_surfels=*/true, s, &created)) return st;
+          res->surfels_created += created;
+          keyframes_with_new_surfels.push_back(k);
+        } else if (kf.activation == BBA_KF_COVISIBLE_ACTIVE && kf.last_covis_in_ba_iteration != h->ba_iteration_count) {
+          kf.last_covis_in_ba_iteration = h->ba_iteration_count;
+        }
+      }
+    }
     const uint32_t N = h->surfels_size;
     if (N > 0) BBA_CUDA(h, cudaMemsetAsync(h->active, bba::kSurfelActiveFlag, N, s));   // :209-212
     if (bba_status st = UploadKeyframes(h, s)) return st;
@@ -981,6 +1173,17 @@ bba_status BundleAdjustPCG(bba_handle h, const bba_ba_options* o, bba_ba_result*
       }
       if (opt_color_intr)   // :623-638
         for (int c = 0; c < 4; ++c) h->color_K[c] = static_cast<float>(h->color_K[c] + h_ci[c]);
+      // surfel merge + compaction (:644-690) for the keyframes that received new surfels
+      if (o->do_surfel_updates && !keyframes_with_new_surfels.empty()) {
+        uint32_t merged = 0;
+        for (int k : keyframes_with_new_surfels) {
+          uint32_t d = 0;
+          if (bba_status st = MergeSurfelsForKeyframe(h, k, s, &d)) return st;
+          merged += d;
+        }
+        res->surfels_merged += merged;
+        if (bba_status st = CompactSurfels(h, merged, /*with_active=*/true, s)) return st;
+      }
     } else {
       BBA_CUDA(h, cudaEventRecord(h->ev[2], s));
       BBA_CUDA(h, cudaStreamSynchronize(s));
@@ -1000,7 +1203,7 @@ bba_status BundleAdjustPCG(bba_handle h, const bba_ba_options* o, bba_ba_result*
   }
   if (o->increase_ba_iteration_count) {   // :771-776
     uint32_t deleted = 0;
-    if (bba_status st = PerformEndTasks(h, s, &deleted)) return st;
+    if (bba_status st = PerformEndTasks(h, s, &deleted, o->do_surfel_updates != 0)) return st;
     res->surfels_deleted += deleted;
     ++h->ba_iteration_count;
   }
@@ -1156,6 +1359,7 @@ void bba_destroy(bba_handle h) {
     if (kf.tex) cudaDestroyTextureObject(kf.tex);
     if (kf.luma) cudaFreeArray(kf.luma);
     for (void* p : kf.owned) cudaFree(p);
+    cudaFree(kf.owned_rgba);
   }
   cudaFree(h->owned_surfels);
   cudaFree(h->owned_active);
@@ -1188,6 +1392,13 @@ void bba_destroy(bba_handle h) {
   cudaFreeHost(h->h_intr_x1);
   UnmapPeers(h);
   cudaFree(h->d_barrier);
+  cudaFree(h->d_sup);
+  cudaFree(h->d_cell_bits);
+  cudaFree(h->d_flags);
+  cudaFree(h->d_scan_out);
+  cudaFree(h->d_scan_sums);
+  cudaFree(h->d_covis);
+  cudaFreeHost(h->h_covis);
   cudaFree(h->d_kf_radius);
   cudaFreeHost(h->h_kf_radius);
   cudaFree(h->d_deleted_count);
@@ -1293,6 +1504,7 @@ bba_status bba_add_keyframe(bba_handle h, const uint16_t* device_depth, size_t d
   kf.depth = device_depth; kf.depth_pitch = depth_pitch;
   kf.normals = device_normals; kf.normals_pitch = normals_pitch;
   kf.radius = device_radius; kf.radius_pitch = radius_pitch;
+  kf.rgba = device_color_rgba; kf.rgba_pitch = color_pitch;
   return AddKeyframeCommon(h, std::move(kf), device_color_rgba, color_pitch, global_T_frame, min_depth, max_depth,
                            static_cast<cudaStream_t>(stream), out_keyframe_id);
 }
@@ -1315,16 +1527,16 @@ bba_status bba_add_keyframe_host(bba_handle h, const uint16_t* host_depth, const
   kf.depth = static_cast<const uint16_t*>(kf.owned[0]); kf.depth_pitch = pitch;
   kf.normals = static_cast<const uint16_t*>(kf.owned[1]); kf.normals_pitch = pitch;
   kf.radius = static_cast<const uint16_t*>(kf.owned[2]); kf.radius_pitch = pitch;
-  // the colour image is only needed to derive the luma plane: stage it in a temporary
+  // the colour image: the luma plane is derived from it; the copy is kept for the colours of surfels created later
   uint8_t* tmp = nullptr;
   size_t tmp_pitch = 0;
   BBA_CUDA(h, cudaMallocPitch(reinterpret_cast<void**>(&tmp), &tmp_pitch, static_cast<size_t>(cw) * 4, ch));
   BBA_CUDA(h, cudaMemcpy2DAsync(tmp, tmp_pitch, host_color_rgba, static_cast<size_t>(cw) * 4, static_cast<size_t>(cw) * 4, ch,
                                 cudaMemcpyHostToDevice, s));
-  bba_status st = AddKeyframeCommon(h, std::move(kf), tmp, tmp_pitch, global_T_frame, min_depth, max_depth, s, out_keyframe_id);
-  cudaStreamSynchronize(s);
-  cudaFree(tmp);
-  return st;
+  kf.owned_rgba = tmp;
+  kf.rgba = tmp;
+  kf.rgba_pitch = tmp_pitch;
+  return AddKeyframeCommon(h, std::move(kf), tmp, tmp_pitch, global_T_frame, min_depth, max_depth, s, out_keyframe_id);
 }
 
 int bba_keyframe_count(bba_handle h) { return h ? static_cast<int>(h->keyframes.size()) : 0; }
@@ -1530,7 +1742,8 @@ bba_status bba_bundle_adjust(bba_handle h, const bba_ba_options* o, bba_ba_resul
   if (!h || !o || !res) return BBA_ERR_INVALID_ARGUMENT;
   std::memset(res, 0, sizeof(*res));
   if (bba_status st = CheckSurfels(h)) return st;
-  if (o->do_surfel_updates) return Fail(h, BBA_ERR_UNSUPPORTED, "do_surfel_updates: surfel creation/merge/deletion is not implemented");
+  if (o->do_surfel_updates && h->cfg.world_size > 1)
+    return Fail(h, BBA_ERR_UNSUPPORTED, "do_surfel_updates is single-GPU only in this version");
   if (o->use_pcg) return BundleAdjustPCG(h, o, res, static_cast<cudaStream_t>(stream));   // direct_ba.cc:436-457
   // direct_ba.cc:427-434
   const bool opt_depth_intr = o->optimize_depth_intrinsics && h->cfg.use_depth_residuals;
@@ -1541,12 +1754,14 @@ bba_status bba_bundle_adjust(bba_handle h, const bba_ba_options* o, bba_ba_resul
   const uint64_t launches_before = h->launches;
   const auto t_start = std::chrono::steady_clock::now();
 
+  const int fixed_ba_iteration_count = h->ba_iteration_count;
   if (!o->increase_ba_iteration_count && h->ba_iteration_count != h->last_ba_iteration_count) {   // :313-319
     h->last_ba_iteration_count = h->ba_iteration_count;
     uint32_t deleted = 0;
-    if (bba_status st = PerformEndTasks(h, s, &deleted)) return st;
+    if (bba_status st = PerformEndTasks(h, s, &deleted, o->do_surfel_updates != 0)) return st;
     res->surfels_deleted += deleted;
   }
+  std::vector<int> keyframes_with_new_surfels;
 
   const bool fixed_window = o->active_keyframe_window_start > 0 || o->active_keyframe_window_end > 0;   // :330-331
   const bool whole_window = !(o->active_keyframe_window_start != 0 || o->active_keyframe_window_end != K - 1);
@@ -1562,15 +1777,49 @@ bba_status bba_bundle_adjust(bba_handle h, const bba_ba_options* o, bba_ba_resul
       DetermineCovisibleActiveKeyframes(h);
     }
 
+    BBA_TRACE("iteration start");
+    // --- surfel creation (:399-430): keyframes that became active for the first time within this BA iteration block
+    keyframes_with_new_surfels.clear();
+    const uint32_t old_surfels_size = h->surfels_size;
+    if (o->optimize_geometry && o->do_surfel_updates) {
+      for (int k = 0; k < K; ++k) {
+        Keyframe& kf = h->keyframes[k];
+        if (kf.activation == BBA_KF_ACTIVE && kf.last_active_in_ba_iteration != fixed_ba_iteration_count) {
+          kf.last_active_in_ba_iteration = fixed_ba_iteration_count;
+          keyframes_with_new_surfels.push_back(k);
+        } else if (kf.activation == BBA_KF_COVISIBLE_ACTIVE && kf.last_covis_in_ba_iteration != fixed_ba_iteration_count) {
+          kf.last_covis_in_ba_iteration = fixed_ba_iteration_count;
+        }
+      }
+      for (int k : keyframes_with_new_surfels) {
+        uint32_t created = 0;
+        if (bba_status st = CreateSurfelsForKeyframe(h, k, /*filter_new_surfels=*/true, s, &created)) return st;
+        res->surfels_created += created;
+      }
+    }
+
+    BBA_TRACE("creation done");
     if (bba_status st = UploadKeyframes(h, s)) return st;
+    BBA_TRACE("keyframes uploaded");
     bba::GeometryArgs g;
     if (bba_status st = BuildGeometryArgs(h, &g, s)) return st;
 
-    // --- surfel activation (:444-456) fused with the normal update of the geometry step (:466-485)
+    BBA_TRACE("after creation + upload");
+    // --- surfel activation (:432-456) fused with the normal update of the geometry step (:466-485)
     BBA_CUDA(h, cudaEventRecord(h->ev[0], s));
-    if (!whole_window) BBA_CUDA(h, cudaMemsetAsync(h->active, bba::kSurfelActiveFlag, h->surfels_size, s));
+    const bool has_new = o->optimize_geometry && h->surfels_size > old_surfels_size;
+    if (has_new)   // new surfels are active (:435-441); only the old ones are re-evaluated below
+      BBA_CUDA(h, cudaMemsetAsync(h->active + old_surfels_size, bba::kSurfelActiveFlag, h->surfels_size - old_surfels_size, s));
+    if (!whole_window) BBA_CUDA(h, cudaMemsetAsync(h->active, bba::kSurfelActiveFlag, old_surfels_size, s));
     if (h->surfels_size > 0) {
-      if (whole_window) {
+      if (whole_window && has_new) {
+        bba::GeometryArgs g_old = g, g_new = g;
+        g_old.end = old_surfels_size;
+        g_new.begin = old_surfels_size;
+        bba::LaunchActivationAndNormals(g_old, h->sm_count, true, true, s);
+        bba::LaunchActivationAndNormals(g_new, h->sm_count, false, true, s);
+        h->launches += 2;
+      } else if (whole_window) {
         bba::LaunchActivationAndNormals(g, h->sm_count, true, o->optimize_geometry != 0, s);
         ++h->launches;
       } else if (o->optimize_geometry) {
@@ -1588,6 +1837,20 @@ bba_status bba_bundle_adjust(bba_handle h, const bba_ba_options* o, bba_ba_resul
     BBA_CUDA(h, cudaEventRecord(h->ev[2], s));
     if (bba_status st = MarkStaging(h, s)) return st;
 
+    BBA_TRACE("after geometry");
+    // --- surfel merge + compaction (:489-541) for the keyframes that received new surfels
+    if (o->do_surfel_updates && !keyframes_with_new_surfels.empty()) {
+      uint32_t merged = 0;
+      for (int k : keyframes_with_new_surfels) {
+        uint32_t d = 0;
+        if (bba_status st = MergeSurfelsForKeyframe(h, k, s, &d)) return st;
+        merged += d;
+      }
+      res->surfels_merged += merged;
+      if (bba_status st = CompactSurfels(h, merged, /*with_active=*/true, s)) return st;
+    }
+
+    BBA_TRACE("before pose step");
     // --- pose optimisation (:543-577): all non-inactive keyframes at once
     int num_converged = 0;
     if (o->optimize_poses) {
@@ -1656,9 +1919,10 @@ bba_status bba_bundle_adjust(bba_handle h, const bba_ba_options* o, bba_ba_resul
     }
     DetermineCovisibleActiveKeyframes(h);   // :711-717
   }
+  BBA_TRACE("iterations done");
   if (o->increase_ba_iteration_count) {   // :725-735
     uint32_t deleted = 0;
-    if (bba_status st = PerformEndTasks(h, s, &deleted)) return st;
+    if (bba_status st = PerformEndTasks(h, s, &deleted, o->do_surfel_updates != 0)) return st;
     res->surfels_deleted += deleted;
     ++h->ba_iteration_count;
   }
@@ -1689,6 +1953,33 @@ bba_status bba_set_ba_iteration_counts(bba_handle h, int ba_iteration_count, int
   if (!h) return BBA_ERR_INVALID_ARGUMENT;
   h->ba_iteration_count = ba_iteration_count;
   h->last_ba_iteration_count = last_ba_iteration_count;
+  return BBA_OK;
+}
+
+bba_status bba_create_surfels_for_keyframe(bba_handle h, int id, int filter_new_surfels, uint32_t* created, void* stream) {
+  CHECK_KF(h, id);
+  if (bba_status st = CheckSurfels(h)) return st;
+  uint32_t c = 0;
+  if (bba_status st = CreateSurfelsForKeyframe(h, id, filter_new_surfels != 0, static_cast<cudaStream_t>(stream), &c)) return st;
+  if (created) *created = c;
+  return BBA_OK;
+}
+
+bba_status bba_merge_surfels_for_keyframe(bba_handle h, int id, uint32_t* deleted, void* stream) {
+  CHECK_KF(h, id);
+  if (bba_status st = CheckSurfels(h)) return st;
+  uint32_t d = 0;
+  if (bba_status st = MergeSurfelsForKeyframe(h, id, static_cast<cudaStream_t>(stream), &d)) return st;
+  if (deleted) *deleted = d;
+  return BBA_OK;
+}
+
+bba_status bba_compact_surfels(bba_handle h, uint32_t free_count, int with_active_flags, uint32_t* surfels_size, void* stream) {
+  if (!h) return BBA_ERR_INVALID_ARGUMENT;
+  if (bba_status st = CheckSurfels(h)) return st;
+  if (free_count > h->surfels_size) return Fail(h, BBA_ERR_INVALID_ARGUMENT, "free_count exceeds surfels_size");
+  if (bba_status st = CompactSurfels(h, free_count, with_active_flags != 0, static_cast<cudaStream_t>(stream))) return st;
+  if (surfels_size) *surfels_size = h->surfels_size;
   return BBA_OK;
 }
 
@@ -1868,12 +2159,18 @@ bba_status bba_update_keyframe_host(bba_handle h, int id, const uint16_t* host_d
                                   cudaMemcpyHostToDevice, s));
   }
   if (host_color_rgba) {
-    if (!h->color_staging) {
-      BBA_CUDA(h, cudaMallocPitch(reinterpret_cast<void**>(&h->color_staging), &h->color_staging_pitch, static_cast<size_t>(cw) * 4, ch));
+    uint8_t* dst = static_cast<uint8_t*>(kf.owned_rgba);
+    size_t dst_pitch = kf.rgba_pitch;
+    if (!dst) {   // caller-owned colour image: only the library's luma array is refreshed, through a staging image
+      if (!h->color_staging) {
+        BBA_CUDA(h, cudaMallocPitch(reinterpret_cast<void**>(&h->color_staging), &h->color_staging_pitch, static_cast<size_t>(cw) * 4, ch));
+      }
+      dst = h->color_staging;
+      dst_pitch = h->color_staging_pitch;
     }
-    BBA_CUDA(h, cudaMemcpy2DAsync(h->color_staging, h->color_staging_pitch, host_color_rgba, static_cast<size_t>(cw) * 4,
+    BBA_CUDA(h, cudaMemcpy2DAsync(dst, dst_pitch, host_color_rgba, static_cast<size_t>(cw) * 4,
                                   static_cast<size_t>(cw) * 4, ch, cudaMemcpyHostToDevice, s));
-    bba::LaunchExtractLuma(h->color_staging, h->color_staging_pitch, h->luma_staging, h->luma_staging_pitch, cw, ch, s);
+    bba::LaunchExtractLuma(dst, dst_pitch, h->luma_staging, h->luma_staging_pitch, cw, ch, s);
     ++h->launches;
     BBA_CUDA(h, cudaGetLastError());
     BBA_CUDA(h, cudaMemcpy2DToArrayAsync(kf.luma, 0, 0, h->luma_staging, h->luma_staging_pitch, cw, ch, cudaMemcpyDeviceToDevice, s));

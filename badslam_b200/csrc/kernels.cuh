@@ -182,7 +182,47 @@ struct SurfelStatsArgs {
 void LaunchObservationStats(SurfelStatsArgs a, int sm_count, cudaStream_t stream);
 uint32_t CompactScratchWords(uint32_t n);   // size of block_sums for LaunchCompactSurfels
 // Moves surviving surfels from the tail into the free spots; afterwards the first n - free_count slots are the surfels.
-void LaunchCompactSurfels(float* surfels, uint32_t pitch, uint32_t n, uint32_t free_count, unsigned int* block_sums, cudaStream_t stream);
+// active != nullptr: the active flags move with them (CompactSurfelsCUDA's adapt_active_surfels).
+void LaunchCompactSurfels(float* surfels, uint32_t pitch, uint32_t n, uint32_t free_count, unsigned int* block_sums, uint8_t* active,
+                          cudaStream_t stream);
+
+// In-loop surfel lifecycle for ONE keyframe (CreateSurfelsForKeyframe / DetermineSupportingSurfelsAndMergeSurfels).
+struct CovisEntry {              // one co-visible keyframe of the keyframe new surfels are created for
+  float R[12];                   // covis_T_frame = covis.frame_T_global * keyframe.global_T_frame (direct_ba.cc:365-370)
+  const uint16_t* depth;
+  const uint16_t* normals;
+  uint32_t depth_pitch, normals_pitch;
+  uint32_t pad[2];
+};
+struct LifecycleArgs {
+  CameraParams cam;
+  float T[12];                   // frame_T_global of the keyframe
+  float G[12];                   // global_T_frame
+  const uint16_t* depth;
+  const uint16_t* normals;
+  const uint16_t* radius;
+  uint32_t depth_pitch, normals_pitch, radius_pitch;
+  cudaTextureObject_t tex;       // luma
+  const uint8_t* rgba;           // the keyframe's uchar4 colour image (surfel colours)
+  uint32_t rgba_pitch;
+  float* surfels;
+  uint32_t pitch, n;
+  unsigned int* sup;             // [3][cells] supporting surfel indices
+  unsigned int* cell_bits;       // [cells]
+  uint32_t cells;
+  unsigned int* flags;           // [w * h] new-surfel flag per pixel
+  const CovisEntry* covis;
+  int covis_count;
+  int min_observation_count;
+  float cell_merge_dist_squared;
+  unsigned int* counter;         // device scalar (deleted surfels)
+};
+void LaunchSupportSurfels(const LifecycleArgs& a, int sm_count, cudaStream_t stream);   // sup[0] only (occupancy for the creation)
+void LaunchMergeSurfels(const LifecycleArgs& a, int sm_count, cudaStream_t stream);     // supports + merge, += *counter
+void LaunchSeedNewSurfels(const LifecycleArgs& a, bool filter, cudaStream_t stream);    // a.flags after LaunchSupportSurfels
+uint32_t ScanScratchWords(uint32_t n);
+void LaunchExclusiveScan(const unsigned int* in, uint32_t n, unsigned int* out, unsigned int* block_sums, cudaStream_t stream);
+void LaunchCreateSurfels(const LifecycleArgs& a, const unsigned int* index, cudaStream_t stream);
 
 // uchar4 (.w = luma) -> u8 plane.
 void LaunchExtractLuma(const uint8_t* rgba, size_t rgba_pitch, uint8_t* luma, size_t luma_pitch, int w, int h, cudaStream_t stream);

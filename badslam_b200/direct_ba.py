@@ -94,6 +94,8 @@ class BAResult:
     ms_pcg: float = 0.0
     surfels_deleted: int = 0
     surfels_size: int = 0
+    surfels_created: int = 0
+    surfels_merged: int = 0
 
     @property
     def residual_count(self):
@@ -379,7 +381,8 @@ class DirectBA:
         return BAResult(r.iterations_done, bool(r.converged), r.depth_residual_count, r.descriptor_residual_count,
                         r.cost, r.pose_iterations_total, r.ms_surfel_activation, r.ms_geometry_optimization,
                         r.ms_pose_optimization, r.ms_intrinsics_optimization, r.kernel_launches,
-                        r.pcg_inner_iterations_total, r.pcg_last_r_norm, r.ms_pcg, r.surfels_deleted, r.surfels_size)
+                        r.pcg_inner_iterations_total, r.pcg_last_r_norm, r.ms_pcg, r.surfels_deleted, r.surfels_size,
+                        r.surfels_created, r.surfels_merged)
 
     def ba_iteration_count(self) -> int:
         a, b = C.c_int(), C.c_int()
@@ -394,6 +397,24 @@ class DirectBA:
     def SetLastBAIterationCount(self, count: int):
         """direct_ba.h:377."""
         self._check(self._lib.bba_set_ba_iteration_counts(self._h, self.ba_iteration_count(), int(count)))
+
+    def CreateSurfelsForKeyframe(self, stream, filter_new_surfels: bool, keyframe_id: int) -> int:
+        """direct_ba.h:114-117; returns the number of surfels created."""
+        c = C.c_uint32()
+        self._check(self._lib.bba_create_surfels_for_keyframe(self._h, int(keyframe_id), int(filter_new_surfels), C.byref(c),
+                                                              self._stream_ptr(stream)))
+        return c.value
+
+    def MergeSurfelsForKeyframe(self, keyframe_id: int, stream=None) -> int:
+        """DetermineSupportingSurfelsAndMergeSurfelsCUDA for one keyframe; returns the number of surfels marked deleted."""
+        d = C.c_uint32()
+        self._check(self._lib.bba_merge_surfels_for_keyframe(self._h, int(keyframe_id), C.byref(d), self._stream_ptr(stream)))
+        return d.value
+
+    def CompactSurfels(self, free_count: int, with_active_flags: bool = True, stream=None) -> int:
+        n = C.c_uint32()
+        self._check(self._lib.bba_compact_surfels(self._h, int(free_count), int(with_active_flags), C.byref(n), self._stream_ptr(stream)))
+        return n.value
 
     def PerformBASchemeEndTasks(self, stream=None):
         """direct_ba.cc:566-653 (delete badly observed surfels, update radii, compact).  Returns (deleted, surfels_size)."""

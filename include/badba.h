@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BBA_ABI_VERSION 3
+#define BBA_ABI_VERSION 4
 
 typedef struct bba_context* bba_handle;
 
@@ -66,7 +66,7 @@ typedef struct {
   int min_observation_count_while_bootstrapping_1;   /* < 5 keyframes  */
   int min_observation_count_while_bootstrapping_2;   /* < 10 keyframes */
   int min_observation_count;
-  float surfel_merge_dist_factor;                    /* unused until do_surfel_updates is supported */
+  float surfel_merge_dist_factor;                    /* DetermineSupportingSurfelsAndMergeSurfelsCUDA */
 } bba_config;
 
 /* Arguments of DirectBA::BundleAdjustment (direct_ba.h:143-162). */
@@ -115,6 +115,9 @@ typedef struct {
    * surfels are compacted to the front of the caller's buffer) */
   uint32_t surfels_deleted;
   uint32_t surfels_size;
+  /* do_surfel_updates: surfels appended by CreateSurfelsForKeyframe / marked by the in-loop merges during this call */
+  uint32_t surfels_created;
+  uint32_t surfels_merged;
 } bba_ba_result;
 
 /* Counters of one pose pass (superset of kernel_opt_pose.cu's debug outputs; the n_* feed the
@@ -207,6 +210,21 @@ uint32_t bba_surfels_size(bba_handle h);
  * increase_ba_iteration_count = 0 first runs the end tasks (direct_ba_alternating.cc:313-319). */
 bba_status bba_get_ba_iteration_counts(bba_handle h, int* ba_iteration_count, int* last_ba_iteration_count);
 bba_status bba_set_ba_iteration_counts(bba_handle h, int ba_iteration_count, int last_ba_iteration_count);
+
+/* In-loop surfel lifecycle (do_surfel_updates = 1 runs these inside bba_bundle_adjust on the reference's schedule,
+ * direct_ba_alternating.cc:399-430,489-541, direct_ba.cc:577-601; single GPU in this version).
+ *  bba_create_surfels_for_keyframe: DirectBA::CreateSurfelsForKeyframe (direct_ba.h:114-117, direct_ba.cc:340-405): one new
+ *    surfel per sparse cell of the keyframe that no existing surfel is associated with, optionally filtered by the
+ *    observations / free-space violations in the co-visible keyframes, appended in raster order; surfels_size grows.
+ *  bba_merge_surfels_for_keyframe: DetermineSupportingSurfelsAndMergeSurfelsCUDA (kernels.h, kernel_supporting_surfels.cc:
+ *    40-118): surfels of a cell that are close to one of the cell's supporting surfels are marked deleted (x = NaN pattern).
+ *  bba_compact_surfels: CompactSurfelsCUDA (kernel_compact_surfels.cu:159-279) for `free_count` marked surfels.
+ * The reference resolves two races "first come" (which pixel of a cell seeds the new surfel, which surfels support a cell);
+ * this library uses the outcome of executing the reference's threads in index order (smallest raster index / three smallest
+ * surfel indices), which is reproducible and identical to the reference for sparse_surfel_cell_size = 1. */
+bba_status bba_create_surfels_for_keyframe(bba_handle h, int keyframe_id, int filter_new_surfels, uint32_t* created, void* stream);
+bba_status bba_merge_surfels_for_keyframe(bba_handle h, int keyframe_id, uint32_t* deleted, void* stream);
+bba_status bba_compact_surfels(bba_handle h, uint32_t free_count, int with_active_flags, uint32_t* surfels_size, void* stream);
 
 /* Parity hook for the PCG solver's building blocks (kernel_pcg.cu:179-1037): runs the init pass (PCGInitCUDA for every
  * keyframe) -> out_r, out_M; PCGInit2 -> out_p; one PCGStep1 sweep -> out_g, out_scalars = {alpha_n, alpha_d}.

@@ -892,6 +892,7 @@ void orc_bundle_adjust(orc_model* m, orc_keyframes* kfs, float* surfels, int pit
   const int fixed_window = opt->active_keyframe_window_start > 0 || opt->active_keyframe_window_end > 0;
   const int whole_window = !(opt->active_keyframe_window_start != 0 || opt->active_keyframe_window_end != K - 1);
   memset(active, 0, n);   /* :338 */
+  int* with_new = (int*)malloc(sizeof(int) * (size_t)(K > 0 ? K : 1));
   for (int iteration = 0; iteration < opt->max_iterations; ++iteration) {
     res->iterations_done++;
     if (fixed_window) {   /* :354-372 */
@@ -900,11 +901,36 @@ void orc_bundle_adjust(orc_model* m, orc_keyframes* kfs, float* surfels, int pit
                                  ? ORC_KF_ACTIVE : ORC_KF_INACTIVE;
       determine_covisible_active(kfs);
     }
-    /* :444-456 */
-    if (!whole_window) memset(active, K_SURFEL_ACTIVE_FLAG, n);
-    else orc_update_activation(m, kfs, surfels, pitch, n, active);
+    /* surfel creation, :399-430 */
+    int n_with_new = 0;
+    const uint32_t old_n = n;
+    if (opt->optimize_geometry && opt->do_surfel_updates) {
+      for (int k = 0; k < K; ++k) {
+        if (kfs->activation[k] == ORC_KF_ACTIVE && opt->last_active_in_ba_iteration[k] != opt->ba_iteration_count) {
+          opt->last_active_in_ba_iteration[k] = opt->ba_iteration_count;
+          with_new[n_with_new++] = k;
+        } else if (kfs->activation[k] == ORC_KF_COVIS_ACTIVE && opt->last_covis_in_ba_iteration[k] != opt->ba_iteration_count) {
+          opt->last_covis_in_ba_iteration[k] = opt->ba_iteration_count;
+        }
+      }
+      for (int q = 0; q < n_with_new; ++q)
+        res->surfels_created += orc_create_surfels_for_keyframe(m, kfs, with_new[q], 1, opt->min_observation_count, surfels, pitch, &n,
+                                                                opt->max_surfels);
+    }
+    /* :432-456: new surfels are active, the old ones are re-evaluated */
+    if (opt->optimize_geometry && n > old_n) memset(active + old_n, K_SURFEL_ACTIVE_FLAG, n - old_n);
+    if (!whole_window) memset(active, K_SURFEL_ACTIVE_FLAG, old_n);
+    else orc_update_activation(m, kfs, surfels, pitch, old_n, active);
     /* :466-485 */
     if (opt->optimize_geometry) orc_optimize_geometry_iteration(m, kfs, surfels, pitch, n, active);
+    /* surfel merge + compaction, :489-541 */
+    if (opt->do_surfel_updates && n_with_new > 0) {
+      uint32_t merged = 0;
+      for (int q = 0; q < n_with_new; ++q)
+        merged += orc_merge_surfels_for_keyframe(m, kfs, with_new[q], opt->surfel_merge_dist_factor, surfels, pitch, n);
+      res->surfels_merged += merged;
+      n = orc_compact_surfels(surfels, pitch, n, active);
+    }
     /* :543-577 */
     int num_converged = 0;
     if (opt->optimize_poses) {
@@ -947,6 +973,8 @@ void orc_bundle_adjust(orc_model* m, orc_keyframes* kfs, float* surfels, int pit
     }
     determine_covisible_active(kfs);   /* :711-717 */
   }
+  free(with_new);
+  res->surfels_size = n;
 }
 
 
@@ -1336,6 +1364,18 @@ static inline float half_to_float(uint16_t h) {
   return u2f(bits);
 }
 
+uint32_t orc_end_tasks_with_merge(const orc_model* m, const orc_keyframes* kfs, float* surfels, int pitch, uint32_t* n_inout,
+                                  int min_observation_count, const int32_t* last_active_in_ba_iteration, int ba_iteration_count,
+                                  float surfel_merge_dist_factor) {
+  /* direct_ba.cc:577-601: merge with every keyframe that was active in this BA iteration block, then the usual end tasks */
+  uint32_t merged = 0;
+  for (int k = 0; k < kfs->K; ++k)
+    if (last_active_in_ba_iteration[k] == ba_iteration_count)
+      merged += orc_merge_surfels_for_keyframe(m, kfs, k, surfel_merge_dist_factor, surfels, pitch, *n_inout);
+  /* orc_end_tasks compacts every marked surfel (its own deletions and the merged ones) */
+  return merged + orc_end_tasks(m, kfs, surfels, pitch, n_inout, min_observation_count);
+}
+
 uint32_t orc_end_tasks(const orc_model* m, const orc_keyframes* kfs, float* surfels, int pitch, uint32_t* n_inout,
                        int min_observation_count) {
   const uint32_t n = *n_inout;
@@ -1390,8 +1430,7 @@ uint32_t orc_end_tasks(const orc_model* m, const orc_keyframes* kfs, float* surf
     }
   }
   free(Ts); free(vs);
-  if (deleted == 0) return 0;
-  /* compaction: the r-th valid surfel from the end moves into the r-th free spot from the front if that lies in front of it */
+  /* compaction of every marked surfel (also those a preceding merge marked): the r-th valid surfel from the end moves into the r-th free spot from the front if that lies in front of it */
   uint8_t* invalid = (uint8_t*)malloc(n);   /* validity BEFORE any move (the device kernel flags first, kernel_compact_surfels.cu:98-107) */
   uint32_t free_count = 0;
   for (uint32_t i = 0; i < n; ++i) { invalid[i] = f2u(surfels[ROW_X * P + i]) == 0x7fffffffu; free_count += invalid[i]; }
@@ -1409,6 +1448,239 @@ uint32_t orc_end_tasks(const orc_model* m, const orc_keyframes* kfs, float* surf
   free(free_list);
   *n_inout = n - free_count;
   return deleted;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * In-loop surfel lifecycle: DirectBA::CreateSurfelsForKeyframe (direct_ba.cc:340-405, kernel_create_surfels.cc:40-183,
+ * kernel_create_surfels.cu:40-405) and DetermineSupportingSurfelsAndMergeSurfelsCUDA (kernel_supporting_surfels.cc:40-118,
+ * kernel_supporting_surfels.cu:44-101).
+ *
+ * The reference resolves two races with atomicCAS "first come": which pixel of an unoccupied sparse cell seeds the new
+ * surfel (kernel_create_surfels.cu:57-68) and which surfels become the supporting surfels of a cell
+ * (kernel_supporting_surfels.cu:60-62).  This restatement (and the CUDA path it checks) uses the outcome of executing the
+ * reference's threads in a FIXED order: the seed is the valid pixel with the smallest raster index of the cell; in the merge
+ * the surfels arrive in the order of a bijective hash of their index (a pseudo-random order like the hardware's; plain index
+ * order would always favour the oldest surfels).  With sparse_surfel_cell_size = 1 the creation is identical to the
+ * reference's; otherwise the two agree in distribution (same cells seeded, same number of new surfels; a similar number
+ * of merges between the same kind of neighbours).
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define K_MERGE_BUFFER_COUNT 3   /* kernels.cuh:51 */
+
+/* tex2D<float4>(color_texture, x, y) channel c with the measured B200 filter (see tex_w_hw) */
+static inline float tex_channel_hw(const kfview* v, float x, float y, int c) {
+  float xb = x - 0.5f, yb = y - 0.5f;
+  float fi = floorf(xb), fj = floorf(yb);
+  long i = (long)fi, j = (long)fj;
+  long a = (long)floorf((xb - fi) * 256.f + 0.5f), b = (long)floorf((yb - fj) * 256.f + 0.5f);
+  long w11 = (a * b + 128) >> 8, w10 = a - w11, w01 = b - w11, w00 = 256 - w11 - w10 - w01;
+  long t[4];
+  for (int q = 0; q < 4; ++q) {
+    long ii = i + (q & 1), jj = j + (q >> 1);
+    if (ii < 0) ii = 0;
+    if (jj < 0) jj = 0;
+    if (ii > v->cw - 1) ii = v->cw - 1;
+    if (jj > v->ch - 1) jj = v->ch - 1;
+    t[q] = v->color[((size_t)jj * v->cw + ii) * 4 + c] * 257L;
+  }
+  long sum = w00 * t[0] + w10 * t[1] + w01 * t[2] + w11 * t[3];
+  return (float)((sum + 128) >> 8) / 65535.f;
+}
+
+static void mat34_from_pose(const float pose[7], float M[12]) { hm_se3_matrix3x4(pose, M); }
+
+uint32_t orc_create_surfels_for_keyframe(const orc_model* m, const orc_keyframes* kfs, int k, int filter_new_surfels,
+                                         int min_observation_count, float* surfels, int pitch, uint32_t* n_inout,
+                                         uint32_t max_surfels) {
+  const uint32_t n = *n_inout;
+  const size_t P = (size_t)pitch;
+  const int w = m->depth_w, h = m->depth_h, cell = m->cell, cf_w = m->cf_w, cf_h = m->cf_h;
+  const size_t npx = (size_t)w * h;
+  kfview v;
+  make_view(m, kfs, k, &v);
+  float T[12], G[12];   /* frame_T_global, global_T_frame */
+  orc_frame_T_global(kfs->global_T_frame + 7 * k, T);
+  mat34_from_pose(kfs->global_T_frame + 7 * k, G);
+  /* DetermineSupportingSurfelsCUDA (merge_surfels = false): only "is the cell supported at all" is used (kernel_create_surfels.cc:68-80) */
+  uint8_t* occupied = (uint8_t*)calloc((size_t)cf_w * cf_h, 1);
+  for (uint32_t i = 0; i < n; ++i) {
+    assoc r;
+    f3 gp = mk3(surfels[ROW_X * P + i], surfels[ROW_Y * P + i], surfels[ROW_Z * P + i]);
+    if (project_associate(&v, T, gp, f2u(surfels[ROW_NORMAL * P + i]), &r) == 3) occupied[(size_t)(r.py / cell) * cf_w + r.px / cell] = 1;
+  }
+  /* seeds: CreateSurfelsForKeyframeCUDASerializingKernel (kernel_create_surfels.cu:40-73); of the valid pixels of the cell the
+   * one with the smallest hashed raster index (fixed pseudo-random choice in place of the reference's atomicCAS winner) */
+  uint8_t* flag = (uint8_t*)calloc(npx, 1);
+  for (int cy = 0; cy < cf_h; ++cy)
+    for (int cx = 0; cx < cf_w; ++cx) {
+      if (occupied[(size_t)cy * cf_w + cx]) continue;
+      uint32_t best_key = 0xffffffffu, best = 0xffffffffu;
+      for (int y = cy * cell; y < (cy + 1) * cell && y < h; ++y)
+        for (int x = cx * cell; x < (cx + 1) * cell && x < w; ++x) {
+          if (x < 1 || y < 1 || x >= w - 1 || y >= h - 1) continue;
+          if (v.depth[(size_t)y * w + x] & K_INVALID_DEPTH_BIT) continue;
+          const uint32_t seq = (uint32_t)y * (uint32_t)w + (uint32_t)x;
+          const uint32_t key = seq * 0x9E3779B1u;
+          if (best == 0xffffffffu || key < best_key) { best_key = key; best = seq; }
+        }
+      if (best != 0xffffffffu) flag[best] = 1;
+    }
+  free(occupied);
+  if (filter_new_surfels) {   /* kernel_create_surfels.cc:99-160 */
+    for (size_t s = 0; s < npx; ++s) {
+      if (!flag[s]) continue;
+      const int y = (int)(s / w), x = (int)(s - (size_t)y * w);
+      unsigned obs = 1, viol = 0;
+      float d = raw_to_calibrated_depth(v.a, v.cfactor[(size_t)(y / cell) * cf_w + x / cell], v.raw_to_float, v.depth[s]);
+      f3 p_in = mk3(d * (v.fx_inv * x + v.cx_inv), d * (v.fy_inv * y + v.cy_inv), d);
+      f3 n_in = u16_to_image_space_normal(v.normals[s]);
+      for (int c = 0; c < kfs->K; ++c) {   /* co_visibility_list (ascending ids, direct_ba.cc:231-249) */
+        if (c == k || !kfs->covis[(size_t)k * kfs->K + c]) continue;
+        kfview vc;
+        make_view(m, kfs, c, &vc);
+        /* covis_T_frame = covis.frame_T_global * keyframe.global_T_frame (direct_ba.cc:365-370) */
+        float inv_c[7], rel[7], R[12];
+        hm_se3_inverse(kfs->global_T_frame + 7 * c, inv_c);
+        hm_se3_mul(inv_c, kfs->global_T_frame + 7 * k, rel);
+        hm_se3_matrix3x4(rel, R);
+        f3 lp;
+        lp.z = R[8] * p_in.x + R[9] * p_in.y + R[10] * p_in.z + R[11];
+        if (!(lp.z > 0.f)) continue;
+        lp.x = R[0] * p_in.x + R[1] * p_in.y + R[2] * p_in.z + R[3];
+        lp.y = R[4] * p_in.x + R[5] * p_in.y + R[6] * p_in.z + R[7];
+        float pxf = vc.fx * (lp.x / lp.z) + vc.cx, pyf = vc.fy * (lp.y / lp.z) + vc.cy;
+        if (!(pxf >= 0.f) || !(pyf >= 0.f) || !(pxf < 1e9f) || !(pyf < 1e9f)) continue;
+        int px = (int)pxf, py = (int)pyf;
+        if (px >= w || py >= h) continue;
+        /* IsAssociatedWithPixel<true> for a pixel-defined surfel (surfel_projection_nvcc_only.cuh:130-236) */
+        uint16_t measured = vc.depth[(size_t)py * w + px];
+        if (measured & K_INVALID_DEPTH_BIT) continue;
+        float pd = raw_to_calibrated_depth(vc.a, vc.cfactor[(size_t)(py / cell) * cf_w + px / cell], vc.raw_to_float, measured);
+        f3 ln = T_rot(R, n_in);
+        float nx = vc.fx_inv * px + vc.cx_inv, ny = vc.fy_inv * py + vc.cy_inv;
+        float thr = K_DEPTH_TUKEY * ((K_DEPTH_UNCERTAINTY_FACTOR * fabsf(ln.x * nx + ln.y * ny + ln.z) * (pd * pd)) / vc.baseline_fx);
+        float diff = pd - lp.z;
+        if (diff > thr) { ++viol; continue; }
+        if (diff < -thr) continue;
+        float dist = sqrtf(dot3(lp, lp));
+        if ((1.0f / dist) * dot3(lp, ln) > 0) continue;
+        if (dot3(ln, u16_to_image_space_normal(vc.normals[(size_t)py * w + px])) < K_COS_NORMAL_COMPAT) continue;
+        ++obs;
+      }
+      if (obs < (unsigned)min_observation_count || viol > obs) flag[s] = 0;   /* kernel_create_surfels.cu:318-334 */
+    }
+  }
+  uint32_t new_count = 0;
+  for (size_t s = 0; s < npx; ++s) new_count += flag[s];
+  if (new_count == 0 || n + new_count > max_surfels) {   /* kernel_create_surfels.cc:163-166: error, nothing is created */
+    free(flag);
+    return 0;
+  }
+  uint32_t out = n;
+  for (size_t s = 0; s < npx; ++s) {   /* CreateNewSurfel, kernel_create_surfels.cu:97-165; appended in raster order */
+    if (!flag[s]) continue;
+    const int y = (int)(s / w), x = (int)(s - (size_t)y * w);
+    float d = raw_to_calibrated_depth(v.a, v.cfactor[(size_t)(y / cell) * cf_w + x / cell], v.raw_to_float, v.depth[s]);
+    f3 gp = T_mul(G, mk3(d * (v.fx_inv * x + v.cx_inv), d * (v.fy_inv * y + v.cy_inv), d));
+    f3 gn = T_rot(G, u16_to_image_space_normal(v.normals[s]));
+    float r2 = half_to_float(kfs->radius[npx * k + s]);
+    surfels[ROW_X * P + out] = gp.x; surfels[ROW_Y * P + out] = gp.y; surfels[ROW_Z * P + out] = gp.z;
+    uint32_t packed = pack_normal(gn);
+    surfels[ROW_NORMAL * P + out] = u2f(packed);
+    surfels[ROW_R2 * P + out] = r2;
+    float ccx = v.d2c_fx * (x + 0.5f) + v.d2c_cx, ccy = v.d2c_fy * (y + 0.5f) + v.d2c_cy;
+    uint32_t col = 0;
+    for (int c = 0; c < 3; ++c) col |= (uint32_t)(uint8_t)(255.f * tex_channel_hw(&v, ccx, ccy, c)) << (8 * c);
+    surfels[ROW_COLOR * P + out] = u2f(col);
+    /* the tangent projections use the UNPACKED float normal (kernel_create_surfels.cu:134-143) */
+    float t1x, t1y, t2x, t2y;
+    tangent_projections(&v, T, gp, gn, r2, &t1x, &t1y, &t2x, &t2y);
+    desc_eval e;
+    descriptor_eval(&v, ccx, ccy, t1x, t1y, t2x, t2y, 0.f, 0.f, &e);
+    surfels[ROW_D1 * P + out] = e.r1;
+    surfels[ROW_D2 * P + out] = e.r2;
+    ++out;
+  }
+  free(flag);
+  *n_inout = out;
+  return new_count;
+}
+
+static int cmp_u64(const void* a, const void* b) {
+  const uint64_t x = *(const uint64_t*)a, y = *(const uint64_t*)b;
+  return (x > y) - (x < y);
+}
+
+/* DetermineSupportingSurfelsAndMergeSurfelsCUDA for keyframe k; returns the number of surfels deleted (x = NaN pattern). */
+uint32_t orc_merge_surfels_for_keyframe(const orc_model* m, const orc_keyframes* kfs, int k, float merge_dist_factor,
+                                        float* surfels, int pitch, uint32_t n) {
+  const size_t P = (size_t)pitch;
+  const int cell = m->cell, cf_w = m->cf_w, cf_h = m->cf_h;
+  kfview v;
+  make_view(m, kfs, k, &v);
+  float T[12];
+  orc_frame_T_global(kfs->global_T_frame + 7 * k, T);
+  const float cell_merge_dist_squared = (float)cell * cell * merge_dist_factor * merge_dist_factor;   /* kernel_supporting_surfels.cc:76-78 */
+  const uint32_t kInvalid = 0xffffffffu;
+  uint32_t* sup = (uint32_t*)malloc(sizeof(uint32_t) * K_MERGE_BUFFER_COUNT * (size_t)cf_w * cf_h);
+  for (size_t c = 0; c < (size_t)K_MERGE_BUFFER_COUNT * cf_w * cf_h; ++c) sup[c] = kInvalid;
+  uint32_t deleted = 0;
+  /* arrival order: ascending key = index * 0x9E3779B1 mod 2^32 (a bijection) */
+  uint64_t* order = (uint64_t*)malloc(sizeof(uint64_t) * (n ? n : 1));
+  for (uint32_t i = 0; i < n; ++i) order[i] = ((uint64_t)(uint32_t)(i * 0x9E3779B1u) << 32) | i;
+  qsort(order, n, sizeof(uint64_t), cmp_u64);
+  for (uint32_t q = 0; q < n; ++q) {
+    const uint32_t i = (uint32_t)order[q];
+    assoc r;
+    f3 gp = mk3(surfels[ROW_X * P + i], surfels[ROW_Y * P + i], surfels[ROW_Z * P + i]);
+    if (project_associate(&v, T, gp, f2u(surfels[ROW_NORMAL * P + i]), &r) != 3) continue;
+    const size_t c = (size_t)(r.py / cell) * cf_w + r.px / cell;
+    int del = 0;
+    for (int b = 0; b < K_MERGE_BUFFER_COUNT; ++b) {   /* kernel_supporting_surfels.cu:59-87 (no break after a merge) */
+      uint32_t* slot = sup + (size_t)b * cf_w * cf_h + c;
+      if (*slot == kInvalid) { *slot = i; break; }
+      const uint32_t s = *slot;
+      f3 sn = unpack_normal(f2u(surfels[ROW_NORMAL * P + s])), tn = unpack_normal(f2u(surfels[ROW_NORMAL * P + i]));
+      if (dot3(sn, tn) > K_COS_NORMAL_COMPAT) {
+        f3 sp = mk3(surfels[ROW_X * P + s], surfels[ROW_Y * P + s], surfels[ROW_Z * P + s]);
+        f3 tp = mk3(surfels[ROW_X * P + i], surfels[ROW_Y * P + i], surfels[ROW_Z * P + i]);   /* (NaN once deleted) */
+        float min_r2 = fminf(surfels[ROW_R2 * P + s], surfels[ROW_R2 * P + i]);
+        f3 dd = sub3(sp, tp);
+        if (dot3(dd, dd) < min_r2 * cell_merge_dist_squared) {
+          surfels[ROW_X * P + i] = u2f(0x7fffffffu);
+          del = 1;
+        }
+      }
+    }
+    deleted += (uint32_t)del;
+  }
+  free(order);
+  free(sup);
+  return deleted;
+}
+
+/* CompactSurfelsCUDA (kernel_compact_surfels.cu:159-279); active may be NULL.  Returns the new surfels_size. */
+uint32_t orc_compact_surfels(float* surfels, int pitch, uint32_t n, uint8_t* active) {
+  const size_t P = (size_t)pitch;
+  uint8_t* invalid = (uint8_t*)malloc(n ? n : 1);
+  uint32_t free_count = 0;
+  for (uint32_t i = 0; i < n; ++i) { invalid[i] = f2u(surfels[ROW_X * P + i]) == 0x7fffffffu; free_count += invalid[i]; }
+  if (free_count) {
+    uint32_t* free_list = (uint32_t*)malloc(sizeof(uint32_t) * free_count);
+    uint32_t nf = 0;
+    for (uint32_t i = 0; i < n; ++i) if (invalid[i]) free_list[nf++] = i;
+    uint32_t r = 0;
+    for (uint32_t i = n; i-- > 0 && r < free_count;) {
+      if (invalid[i]) continue;
+      if (free_list[r] < i) {
+        for (int row = 0; row < ROW_ACC0; ++row) surfels[(size_t)row * P + free_list[r]] = surfels[(size_t)row * P + i];
+        if (active) active[free_list[r]] = active[i];
+      }
+      ++r;
+    }
+    free(free_list);
+  }
+  free(invalid);
+  return n - free_count;
 }
 
 void orc_se3_exp(const float a[6], float out[7]) { hm_se3_exp(a, out); }

@@ -111,11 +111,18 @@ void orc_optimize_intrinsics(orc_model* m, const orc_keyframes* kfs,
 
 typedef struct {
   int optimize_depth_intrinsics, optimize_color_intrinsics;
-  int do_surfel_updates;       /* must be 0 (lifecycle kernels are SURVEY 8f "next") */
+  int do_surfel_updates;
   int optimize_poses, optimize_geometry;
   int min_iterations, max_iterations;
   int active_keyframe_window_start, active_keyframe_window_end;
   int max_pose_iterations;     /* 30 (direct_ba_alternating.cc:130) */
+  /* do_surfel_updates: in-loop surfel creation / merge (direct_ba_alternating.cc:399-430,489-541) */
+  int ba_iteration_count;
+  int32_t* last_active_in_ba_iteration;   /* [K] keyframe.h:113-128, updated in place */
+  int32_t* last_covis_in_ba_iteration;    /* [K] */
+  float surfel_merge_dist_factor;
+  int min_observation_count;
+  uint32_t max_surfels;
 } orc_ba_options;
 
 typedef struct {
@@ -125,6 +132,7 @@ typedef struct {
   uint64_t n_assoc, n_photo;
   double cost;
   int pose_iterations_total;   /* sum over keyframes and outer iterations of GN iterations */
+  uint32_t surfels_size, surfels_created, surfels_merged;
 } orc_ba_result;
 
 /* DirectBA::BundleAdjustmentAlternating (direct_ba_alternating.cc:285-738), without
@@ -151,6 +159,20 @@ void orc_bundle_adjust_pcg(orc_model* m, orc_keyframes* kfs, float* surfels, int
  * radius^2, compact.  Returns the number of deleted surfels; *n is updated to the new surfels_size. */
 uint32_t orc_end_tasks(const orc_model* m, const orc_keyframes* kfs, float* surfels, int pitch, uint32_t* n,
                        int min_observation_count);
+/* ... with do_surfel_updates: first the merge over the keyframes that were active in this BA iteration block (direct_ba.cc:577-601) */
+uint32_t orc_end_tasks_with_merge(const orc_model* m, const orc_keyframes* kfs, float* surfels, int pitch, uint32_t* n,
+                                  int min_observation_count, const int32_t* last_active_in_ba_iteration, int ba_iteration_count,
+                                  float surfel_merge_dist_factor);
+
+/* In-loop surfel lifecycle with the deterministic resolution of the reference's atomicCAS races described in badba_oracle.c:
+ * DirectBA::CreateSurfelsForKeyframe (direct_ba.cc:340-405) -> returns the number of surfels appended (*n updated);
+ * DetermineSupportingSurfelsAndMergeSurfelsCUDA (kernel_supporting_surfels.cc:40-118) -> returns the number deleted;
+ * CompactSurfelsCUDA (kernel_compact_surfels.cu:159-279) -> returns the new surfels_size. */
+uint32_t orc_create_surfels_for_keyframe(const orc_model* m, const orc_keyframes* kfs, int k, int filter_new_surfels,
+                                         int min_observation_count, float* surfels, int pitch, uint32_t* n, uint32_t max_surfels);
+uint32_t orc_merge_surfels_for_keyframe(const orc_model* m, const orc_keyframes* kfs, int k, float merge_dist_factor,
+                                        float* surfels, int pitch, uint32_t n);
+uint32_t orc_compact_surfels(float* surfels, int pitch, uint32_t n, uint8_t* active);
 
 /* Parity hook for the PCG building blocks: r, M after the init pass, p0, g after one J^T W J p sweep, {alpha_n, alpha_d}. */
 uint32_t orc_pcg_debug(const orc_model* m, const orc_keyframes* kfs, const float* surfels, int pitch, uint32_t n,

@@ -53,13 +53,17 @@ class BAOptions(C.Structure):
                 ("do_surfel_updates", C.c_int), ("optimize_poses", C.c_int), ("optimize_geometry", C.c_int),
                 ("min_iterations", C.c_int), ("max_iterations", C.c_int),
                 ("active_keyframe_window_start", C.c_int), ("active_keyframe_window_end", C.c_int),
-                ("max_pose_iterations", C.c_int)]
+                ("max_pose_iterations", C.c_int),
+                ("ba_iteration_count", C.c_int), ("last_active_in_ba_iteration", C.POINTER(C.c_int32)),
+                ("last_covis_in_ba_iteration", C.POINTER(C.c_int32)), ("surfel_merge_dist_factor", C.c_float),
+                ("min_observation_count", C.c_int), ("max_surfels", C.c_uint32)]
 
 
 class BAResult(C.Structure):
     _fields_ = [("iterations_done", C.c_int), ("converged", C.c_int),
                 ("n_assoc", C.c_uint64), ("n_photo", C.c_uint64), ("cost", C.c_double),
-                ("pose_iterations_total", C.c_int)]
+                ("pose_iterations_total", C.c_int),
+                ("surfels_size", C.c_uint32), ("surfels_created", C.c_uint32), ("surfels_merged", C.c_uint32)]
 
 
 class PCGOptions(C.Structure):
@@ -113,7 +117,7 @@ class Oracle:
         self.max_depth = np.ascontiguousarray(scene.max_depth, np.float32)
         self.covis = np.zeros((self.K, self.K), np.uint8)
         self.surfels = np.ascontiguousarray(scene.surfels, np.float32).copy()
-        self.active = np.zeros(max(self.n, 1), np.uint8)
+        self.active = np.zeros(max(self.surfels.shape[1], 1), np.uint8)   # capacity (surfel creation grows n)
         m = Model()
         m.depth_w, m.depth_h, m.color_w, m.color_h = cfg.width, cfg.height, cfg.width, cfg.height
         m.depth_K[:] = [float(v) for v in scene.depth_K]
@@ -190,18 +194,64 @@ class Oracle:
         self.n = int(n.value)
         return int(deleted)
 
+    def min_observation_count(self):
+        K = self.K
+        b1, b2, mo = self.min_observation_counts
+        return (b1 if K < 5 else b2) if K < 10 else mo     # direct_ba.h:220-226
+
+    def create_surfels_for_keyframe(self, k, filter_new_surfels=True):
+        """DirectBA::CreateSurfelsForKeyframe (direct_ba.cc:340-405); returns the number of new surfels."""
+        n = C.c_uint32(self.n)
+        self.lib.orc_create_surfels_for_keyframe.restype = C.c_uint32
+        new = self.lib.orc_create_surfels_for_keyframe(C.byref(self.model), C.byref(self.kfs), C.c_int(k), C.c_int(filter_new_surfels),
+                                                       C.c_int(self.min_observation_count()), _p(self.surfels, C.c_float),
+                                                       C.c_int(self.pitch), C.byref(n), C.c_uint32(self.pitch))
+        self.n = int(n.value)
+        return int(new)
+
+    def merge_surfels_for_keyframe(self, k, merge_dist_factor=0.8):
+        """DetermineSupportingSurfelsAndMergeSurfelsCUDA (kernel_supporting_surfels.cc:40-118); returns the deleted count."""
+        self.lib.orc_merge_surfels_for_keyframe.restype = C.c_uint32
+        return int(self.lib.orc_merge_surfels_for_keyframe(C.byref(self.model), C.byref(self.kfs), C.c_int(k), C.c_float(merge_dist_factor),
+                                                           _p(self.surfels, C.c_float), C.c_int(self.pitch), C.c_uint32(self.n)))
+
+    def compact_surfels(self, with_active=True):
+        self.lib.orc_compact_surfels.restype = C.c_uint32
+        self.n = int(self.lib.orc_compact_surfels(_p(self.surfels, C.c_float), C.c_int(self.pitch), C.c_uint32(self.n),
+                                                  _p(self.active, C.c_uint8) if with_active else None))
+        return self.n
+
     def bundle_adjust(self, optimize_poses=True, optimize_geometry=True, min_iterations=1, max_iterations=10,
                       optimize_depth_intrinsics=False, optimize_color_intrinsics=False,
-                      window_start=0, window_end=None, max_pose_iterations=30, end_tasks=True):
-        o = BAOptions(int(optimize_depth_intrinsics), int(optimize_color_intrinsics), 0, int(optimize_poses),
+                      window_start=0, window_end=None, max_pose_iterations=30, end_tasks=True, do_surfel_updates=False,
+                      surfel_merge_dist_factor=0.8):
+        if not hasattr(self, "last_active_in_ba_iteration"):
+            self.last_active_in_ba_iteration = np.full(self.K, -1, np.int32)   # keyframe.cc:47-48
+            self.last_covis_in_ba_iteration = np.full(self.K, -1, np.int32)
+            self.ba_iteration_count = 0
+        o = BAOptions(int(optimize_depth_intrinsics), int(optimize_color_intrinsics), int(do_surfel_updates), int(optimize_poses),
                       int(optimize_geometry), min_iterations, max_iterations, window_start,
-                      self.K - 1 if window_end is None else window_end, max_pose_iterations)
+                      self.K - 1 if window_end is None else window_end, max_pose_iterations,
+                      self.ba_iteration_count, _p(self.last_active_in_ba_iteration, C.c_int32),
+                      _p(self.last_covis_in_ba_iteration, C.c_int32), float(surfel_merge_dist_factor),
+                      self.min_observation_count(), self.pitch)
         r = BAResult()
         self.lib.orc_bundle_adjust(C.byref(self.model), C.byref(self.kfs), _p(self.surfels, C.c_float),
                                    C.c_int(self.pitch), C.c_uint32(self.n), _p(self.active, C.c_uint8),
                                    C.byref(o), C.byref(r))
+        self.n = int(r.surfels_size)
         if end_tasks:     # increase_ba_iteration_count = true (direct_ba_alternating.cc:725-735)
-            self.surfels_deleted = self.end_tasks()
+            if do_surfel_updates:
+                n = C.c_uint32(self.n)
+                self.lib.orc_end_tasks_with_merge.restype = C.c_uint32
+                self.surfels_deleted = int(self.lib.orc_end_tasks_with_merge(
+                    C.byref(self.model), C.byref(self.kfs), _p(self.surfels, C.c_float), C.c_int(self.pitch), C.byref(n),
+                    C.c_int(self.min_observation_count()), _p(self.last_active_in_ba_iteration, C.c_int32),
+                    C.c_int(self.ba_iteration_count), C.c_float(surfel_merge_dist_factor)))
+                self.n = int(n.value)
+            else:
+                self.surfels_deleted = self.end_tasks()
+            self.ba_iteration_count += 1
         return r
 
     def bundle_adjust_pcg(self, optimize_poses=True, optimize_geometry=True, optimize_depth_intrinsics=False,

@@ -87,6 +87,13 @@ def lib():
         l.ref_surfels_size.restype = C.c_uint
         l.ref_surfels_size.argtypes = [C.c_void_p]
         l.ref_set_min_observation_counts.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        l.ref_create_surfels_for_keyframe.restype = C.c_uint
+        l.ref_create_surfels_for_keyframe.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        l.ref_merge_surfels_for_keyframe.restype = C.c_uint
+        l.ref_merge_surfels_for_keyframe.argtypes = [C.c_void_p, C.c_int]
+        l.ref_compact_surfels.restype = C.c_uint
+        l.ref_compact_surfels.argtypes = [C.c_void_p, C.c_uint, C.c_int]
+        l.ref_set_surfels_size.argtypes = [C.c_void_p, C.c_uint]
         l.ref_snapshot.argtypes = [C.c_void_p]
         l.ref_restore.argtypes = [C.c_void_p]
         l.ref_sync.argtypes = [C.c_void_p]
@@ -167,6 +174,18 @@ class RefDirectBA:
     def set_activation(self, k, a):
         self.l.ref_set_activation(self.h, k, int(a))
 
+    def create_surfels_for_keyframe(self, k, filter_new_surfels=True):
+        return int(self.l.ref_create_surfels_for_keyframe(self.h, int(k), int(filter_new_surfels)))
+
+    def merge_surfels_for_keyframe(self, k):
+        return int(self.l.ref_merge_surfels_for_keyframe(self.h, int(k)))
+
+    def compact_surfels(self, free_count, with_active=True):
+        return int(self.l.ref_compact_surfels(self.h, int(free_count), int(with_active)))
+
+    def set_surfels_size(self, n):
+        self.l.ref_set_surfels_size(self.h, int(n))
+
     def surfels_size(self):
         return int(self.l.ref_surfels_size(self.h))
 
@@ -181,7 +200,7 @@ class RefDirectBA:
         return out[:, :n]
 
     def active(self):
-        out = np.zeros(max(self.n, 1), np.uint8)
+        out = np.zeros(max(self.surfels_size(), self.n, 1), np.uint8)
         assert self.l.ref_get_active(self.h, out.ctypes.data) == 0
         return out[:self.surfels_size()]
 

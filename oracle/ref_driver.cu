@@ -17,7 +17,9 @@
 #include <string>
 #include <vector>
 
+#include "badslam/kernel_create_surfels.h"
 #include "badslam/kernel_delete_surfels.h"
+#include "badslam/kernel_supporting_surfels.h"
 #include "badslam/kernel_opt_geometry.h"
 #include "badslam/kernel_opt_intrinsics.h"
 #include "badslam/kernel_opt_pose.h"
@@ -123,6 +125,10 @@ struct ref_context {
   // PerformBASchemeEndTasks
   u32* deleted_count = nullptr; void* free_spots_temp = nullptr; usize free_spots_temp_bytes = 0;
   int min_observation_count[3] = {1, 2, 3};   // bad_slam_config.h:146,151,158
+  // surfel creation / merge (direct_ba.cc:131-145)
+  u32* sup[3] = {nullptr, nullptr, nullptr}; size_t sup_pitch = 0;
+  u8* new_flag = nullptr; u32* new_indices = nullptr; void* new_temp = nullptr; usize new_temp_bytes = 0;
+  float surfel_merge_dist_factor = 0.8f;      // bad_slam_config.h
 };
 
 extern "C" unsigned int ref_end_tasks(ref_context* c);
@@ -883,6 +889,121 @@ unsigned int ref_surfels_size(ref_context* c) { return c->surfels_size; }
 void ref_set_min_observation_counts(ref_context* c, int b1, int b2, int m) {
   c->min_observation_count[0] = b1; c->min_observation_count[1] = b2; c->min_observation_count[2] = m;
 }
+
+namespace {
+void EnsureLifecycleBuffers(ref_context* c) {
+  if (c->sup[0]) return;
+  for (int i = 0; i < 3; ++i) cudaMallocPitch(reinterpret_cast<void**>(&c->sup[i]), &c->sup_pitch, sizeof(u32) * c->cf_w, c->cf_h);
+  cudaMalloc(&c->new_flag, static_cast<size_t>(c->cfg.depth_w) * c->cfg.depth_h);
+  cudaMalloc(&c->new_indices, sizeof(u32) * static_cast<size_t>(c->cfg.depth_w) * c->cfg.depth_h);
+  if (!c->deleted_count) cudaMalloc(&c->deleted_count, sizeof(u32));
+}
+SupportingSurfelBuffers SupBuffers(ref_context* c) {
+  SupportingSurfelBuffers b;
+  for (int i = 0; i < 3; ++i) b.b[i] = CUDABuffer_<u32>(c->sup[i], c->cf_h, c->cf_w, c->sup_pitch);
+  return b;
+}
+int MinObservationCount(ref_context* c) {
+  const size_t K = c->kfs.size();
+  return (K < 10) ? ((K < 5) ? c->min_observation_count[0] : c->min_observation_count[1]) : c->min_observation_count[2];
+}
+// DetermineSupportingSurfelsCUDAImpl (kernel_supporting_surfels.cc:40-118)
+unsigned int DetermineSupportingSurfels(ref_context* c, const RefKeyframe& kf, bool merge) {
+  cudaStream_t s = c->stream;
+  for (int i = 0; i < 3; ++i) cudaMemset2DAsync(c->sup[i], c->sup_pitch, 0xff, sizeof(u32) * c->cf_w, c->cf_h, s);
+  if (c->surfels_size == 0) return 0;
+  CUDABuffer_<u32> deleted_buf(c->deleted_count, 1, 1, sizeof(u32));
+  float cmd2 = 0, cos_thr = 0;
+  if (merge) {
+    cudaMemsetAsync(c->deleted_count, 0, sizeof(u32), s);
+    cmd2 = static_cast<float>(c->cfg.cell) * c->cfg.cell * c->surfel_merge_dist_factor * c->surfel_merge_dist_factor;
+    cos_thr = cos_normal_compatibility_threshold;
+  }
+  CallDetermineSupportingSurfelsCUDAKernel(s, merge, cmd2, cos_thr, MakeProjection(c, kf, MakeFrameTGlobal(kf.pose), c->surfels_size),
+                                           SupBuffers(c), merge ? deleted_buf : CUDABuffer_<u32>());
+  ++c->launches;
+  if (!merge) return 0;
+  u32 deleted = 0;
+  cudaMemcpyAsync(&deleted, c->deleted_count, sizeof(u32), cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+  return deleted;
+}
+}  // namespace
+
+// DirectBA::CreateSurfelsForKeyframe (direct_ba.cc:340-405) + CreateSurfelsForKeyframeCUDA (kernel_create_surfels.cc:40-183),
+// driving the reference's own kernels.  Returns the number of surfels created.
+unsigned int ref_create_surfels_for_keyframe(ref_context* c, int k, int filter_new_surfels) {
+  EnsureLifecycleBuffers(c);
+  cudaStream_t s = c->stream;
+  const RefKeyframe& kf = c->kfs[k];
+  const int w = c->cfg.depth_w, h = c->cfg.depth_h;
+  DetermineSupportingSurfels(c, kf, false);
+  CUDABuffer_<u16> depth(kf.depth, h, w, kf.depth_pitch), normals(kf.normals, h, w, kf.normals_pitch), radius(kf.radius, h, w, kf.radius_pitch);
+  CUDABuffer_<uchar4> color(kf.color, c->cfg.color_h, c->cfg.color_w, kf.color_pitch);
+  CUDABuffer_<u8> flag(c->new_flag, 1, w * h, static_cast<size_t>(w) * h);
+  CUDABuffer_<u32> indices(c->new_indices, 1, w * h, sizeof(u32) * static_cast<size_t>(w) * h);
+  CallCreateSurfelsForKeyframeCUDASerializingKernel(s, c->cfg.cell, depth, color, CUDABuffer_<u32>(c->sup[0], c->cf_h, c->cf_w, c->sup_pitch), flag);
+  u32 new_count = CreateSurfelsForKeyframeCUDA_CountNewSurfels(s, w * h, &c->new_temp, &c->new_temp_bytes, &flag, &indices);
+  c->launches += 2;
+  if (new_count == 0) return 0;
+  const PixelCenterUnprojector unproj = CenterUnprojector(c->cfg.depth_K);
+  if (filter_new_surfels) {
+    u16* obs = reinterpret_cast<u16*>(reinterpret_cast<u8*>(c->surfels) + kSurfelAccum0 * c->surfel_pitch);
+    u16* viol = reinterpret_cast<u16*>(reinterpret_cast<u8*>(c->surfels) + kSurfelAccum1 * c->surfel_pitch);
+    u32* list = reinterpret_cast<u32*>(reinterpret_cast<u8*>(c->surfels) + kSurfelAccum2 * c->surfel_pitch);
+    CallWriteNewSurfelIndexAndInitializeObservationsCUDAKernel(s, w * h, flag, indices, obs, viol, list);
+    for (int o : kf.covis) {
+      const RefKeyframe& other = c->kfs[o];
+      float inv[7], rel[7], M[12];
+      hm_se3_inverse(other.pose, inv);
+      hm_se3_mul(inv, kf.pose, rel);
+      hm_se3_matrix3x4(rel, M);
+      CUDAMatrix3x4 covis_T_frame;
+      covis_T_frame.row0 = make_float4(M[0], M[1], M[2], M[3]);
+      covis_T_frame.row1 = make_float4(M[4], M[5], M[6], M[7]);
+      covis_T_frame.row2 = make_float4(M[8], M[9], M[10], M[11]);
+      CallCountObservationsForNewSurfelsCUDAKernel(s, new_count, list, obs, viol, MakeDepthParams(c), unproj, depth, normals, covis_T_frame,
+                                                   CornerProjector(c->cfg.depth_K), CUDABuffer_<u16>(other.depth, h, w, other.depth_pitch),
+                                                   CUDABuffer_<u16>(other.normals, h, w, other.normals_pitch));
+      ++c->launches;
+    }
+    CallFilterNewSurfelsCUDAKernel(s, static_cast<u16>(MinObservationCount(c)), new_count, list, obs, viol, flag);
+    new_count = CreateSurfelsForKeyframeCUDA_CountNewSurfels(s, w * h, &c->new_temp, &c->new_temp_bytes, &flag, &indices);
+    c->launches += 3;
+    if (new_count == 0) return 0;
+  }
+  if (c->surfels_size + new_count > c->max_surfels) return 0;   // kernel_create_surfels.cc:163-166
+  float gm[12];
+  hm_se3_matrix3x4(kf.pose, gm);
+  CUDAMatrix3x4 global_T_frame;
+  global_T_frame.row0 = make_float4(gm[0], gm[1], gm[2], gm[3]);
+  global_T_frame.row1 = make_float4(gm[4], gm[5], gm[6], gm[7]);
+  global_T_frame.row2 = make_float4(gm[8], gm[9], gm[10], gm[11]);
+  CallCreateSurfelsForKeyframeCUDACreationAppendKernel(s, unproj, DepthToColor(c->cfg), CornerProjector(c->cfg.color_K), global_T_frame,
+                                                       MakeFrameTGlobal(kf.pose), MakeDepthParams(c), depth, normals, radius, kf.tex, flag, indices,
+                                                       c->surfels_size, SurfelBuf(c));
+  ++c->launches;
+  cudaStreamSynchronize(s);
+  c->surfels_size += new_count;
+  return new_count;
+}
+
+// DetermineSupportingSurfelsAndMergeSurfelsCUDA for keyframe k; returns the number of merged (deleted) surfels
+unsigned int ref_merge_surfels_for_keyframe(ref_context* c, int k) {
+  EnsureLifecycleBuffers(c);
+  return DetermineSupportingSurfels(c, c->kfs[k], true);
+}
+
+// CompactSurfelsCUDA with the active flags (direct_ba_alternating.cc:530)
+unsigned int ref_compact_surfels(ref_context* c, unsigned int free_count, int with_active) {
+  CUDABuffer_<float> sb = SurfelBuf(c);
+  CUDABuffer_<u8> ab = ActiveBuf(c);
+  CompactSurfelsCUDA(c->stream, &c->free_spots_temp, &c->free_spots_temp_bytes, c->surfels_size - free_count, &c->surfels_size, &sb,
+                     with_active ? &ab : nullptr);
+  cudaStreamSynchronize(c->stream);
+  return c->surfels_size;
+}
+void ref_set_surfels_size(ref_context* c, unsigned int n) { c->surfels_size = n; }
 
 // Device-side snapshot / restore of the mutable state (surfel data rows, poses, activations) for benchmarking
 // repeated steps from the same starting point without host traffic.

@@ -88,3 +88,68 @@ def test_end_tasks_match_reference_cuda_golden():
     deleted = orc.end_tasks()
     assert deleted == int(g["deleted"]) and orc.n == int(g["surfels_size"])
     assert np.array_equal(orc.surfels[:8, :orc.n].view(np.uint32), g["rows"].view(np.uint32))
+
+
+def _empty_map_oracle(name="tiny"):
+    sc = S.make_scene(S.config_by_name(name))
+    orc = O.Oracle(sc)
+    orc.poses[:] = sc.poses_true
+    orc.n = 0
+    return sc, orc
+
+
+def test_create_surfels_fills_unsupported_cells_once():
+    """DirectBA::CreateSurfelsForKeyframe (direct_ba.cc:340-405): one surfel per unsupported sparse cell with a valid pixel; a second
+    call finds (almost) every cell supported; the new surfels are associated with their keyframe and carry its measurements."""
+    sc, orc = _empty_map_oracle()
+    cells = orc.model.cf_w * orc.model.cf_h
+    new = orc.create_surfels_for_keyframe(0, filter_new_surfels=False)
+    assert 0.8 * cells < new <= cells and orc.n == new
+    st = orc.pose_coeffs(0)
+    assert st.n_assoc >= 0.98 * new and st.cost_depth < 1e-2 * st.n_assoc      # they lie on the measured depth
+    assert orc.create_surfels_for_keyframe(0, filter_new_surfels=False) <= 0.02 * new
+    rows = orc.surfels[:8, :orc.n]
+    assert np.all(np.isfinite(rows[[0, 1, 2, 4, 6, 7]])) and np.all(rows[4] > 0)
+    assert np.array_equal(rows[4], rows[4].astype(np.float16).astype(np.float32))             # radius^2 from the half buffer
+    assert np.all(rows[5].view(np.uint32) >> 24 == 0)                                          # uchar4 colour, w = 0
+    # the filter (observations in the co-visible keyframes) only removes candidates
+    sc2, orc2 = _empty_map_oracle()
+    assert 0 < orc2.create_surfels_for_keyframe(0, filter_new_surfels=True) <= new
+    # capacity: nothing is created when the buffer would overflow (kernel_create_surfels.cc:163-166)
+    sc3, orc3 = _empty_map_oracle()
+    orc3.n = orc3.pitch - 10
+    assert orc3.create_surfels_for_keyframe(0, filter_new_surfels=False) == 0 and orc3.n == orc3.pitch - 10
+
+
+def test_merge_removes_duplicates_created_by_other_keyframes():
+    sc, orc = _empty_map_oracle("tiny")
+    # a buffer with room for two keyframes' worth of surfels
+    orc.surfels = np.pad(orc.surfels, ((0, 0), (0, 4096)))
+    orc.active = np.zeros(orc.surfels.shape[1], np.uint8)
+    orc.pitch = orc.surfels.shape[1]
+    n0 = orc.create_surfels_for_keyframe(0, False)
+    # the same surface seen again by a keyframe at the same pose yields nothing new; merging keyframe 0 against its own
+    # surfels deletes nothing either (one surfel per cell)
+    assert orc.merge_surfels_for_keyframe(0) == 0
+    # duplicate every surfel with a tiny offset: all the copies that land in a cell with their original are merged
+    orc.surfels[:8, n0:2 * n0] = orc.surfels[:8, :n0]
+    orc.surfels[0, n0:2 * n0] += 1e-4
+    orc.n = 2 * n0
+    deleted = orc.merge_surfels_for_keyframe(0)
+    assert 0.9 * n0 <= deleted <= n0
+    assert orc.compact_surfels() == 2 * n0 - deleted
+    assert not np.any(orc.surfels[0, :orc.n].view(np.uint32) == DELETED)
+
+
+def test_bundle_adjustment_with_surfel_updates_runs_the_lifecycle():
+    sc = S.make_scene(S.config_by_name("tiny"))
+    orc = O.Oracle(sc)
+    orc.surfels = np.pad(orc.surfels, ((0, 0), (0, 8192)))
+    orc.active = np.zeros(orc.surfels.shape[1], np.uint8)
+    orc.pitch = orc.surfels.shape[1]
+    orc.n = sc.num_surfels // 2
+    r = orc.bundle_adjust(True, True, 2, 2, do_surfel_updates=True)
+    assert r.surfels_created > 0 and r.surfels_merged >= 0
+    assert orc.n == r.surfels_size - orc.surfels_deleted and orc.ba_iteration_count == 1
+    assert np.all(orc.last_active_in_ba_iteration == 0)
+    assert not np.any(orc.surfels[0, :orc.n].view(np.uint32) == DELETED)
