@@ -189,7 +189,7 @@ def test_bundle_adjustment_with_surfel_updates(mods):
         dt, dr = S.pose_error(pa[k], orc.poses[k])
         assert dt < 1e-4 and dr < 1e-4, (k, dt, dr)
     assert not np.any(ba.GetSurfelsHost()[0].view(np.uint32) == 0x7fffffff)
-    # a second call: the keyframes are no longer "newly active" within a new BA iteration block? they are (counter increased):
-    # creation runs again but finds (almost) every cell supported
+    # a second BA iteration block (the counter increased): the keyframes that are still active create surfels again, but only
+    # where the end tasks deleted badly observed ones
     r2 = ba.BundleAdjustment(None, False, False, True, True, True, 1, 1)
-    assert r2.surfels_created <= 0.05 * ro.surfels_created + 5
+    assert r2.surfels_created < ro.surfels_created and ba.ba_iteration_count() == 2

@@ -196,10 +196,8 @@ def test_edge_cases(mods, tiny_scene):
     before = ba.GetSurfelsHost()
     ba.OptimizeGeometryIteration()
     assert np.array_equal(before.view(np.uint32), ba.GetSurfelsHost().view(np.uint32))
-    # unsupported options fail loudly instead of silently doing something else
+    # invalid options fail loudly instead of silently doing something else
     from badslam_b200._lib import BadBAError
-    with pytest.raises(BadBAError):
-        ba.BundleAdjustment(None, False, False, True, True, True, 1, 1)      # do_surfel_updates
     with pytest.raises(BadBAError):   # gauge keyframe out of range / more keyframes than pcg_max_keyframes (direct_ba_pcg.cc:232)
         ba.BundleAdjustment(None, False, False, False, True, True, 1, 1, use_pcg=True, pcg_gauge_keyframe=sc.cfg.num_keyframes)
     with pytest.raises(BadBAError):
