@@ -131,6 +131,18 @@ class DirectBA {
     last_result_ = r;
   }
 
+  // direct_ba.h:114-117 (frame = an already added keyframe); returns the number of surfels created
+  uint32_t CreateSurfelsForKeyframe(cudaStream_t stream, bool filter_new_surfels, int keyframe_id) {
+    uint32_t created = 0;
+    Check(bba_create_surfels_for_keyframe(h_, keyframe_id, filter_new_surfels, &created, stream), "bba_create_surfels_for_keyframe");
+    return created;
+  }
+
+  // direct_ba.cc:566-653 (runs inside BundleAdjustment on the reference's schedule; exposed like the reference does)
+  void PerformBASchemeEndTasks(cudaStream_t stream) {
+    Check(bba_perform_end_tasks(h_, nullptr, nullptr, stream), "bba_perform_end_tasks");
+  }
+
   void GetKeyframePose(int keyframe_id, SE3f* global_T_frame) const {
     float p[7];
     Check(bba_get_keyframe_pose(h_, keyframe_id, p), "bba_get_keyframe_pose");
