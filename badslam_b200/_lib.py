@@ -124,6 +124,7 @@ SYMBOLS = {
     "bba_shard_surfel_local_index": (C.c_uint32, [C.c_uint32, C.c_int]),
     "bba_shard_slice_length": (C.c_uint32, [C.c_uint32, C.c_int]),
     "bba_shard_keyframe_owner": (C.c_int, [C.c_int, C.c_int]),
+    "bba_balance_keyframes": (None, [_P, C.c_int, C.c_int, _P]),
     "bba_kernel_launch_count": (C.c_uint64, [_P]),
     "bba_update_keyframe_host": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
     "bba_set_profiling": (C.c_int, [_P, C.c_int]),

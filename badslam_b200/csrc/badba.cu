@@ -367,32 +367,34 @@ bba_status CheckCollective(bba_handle h);
 // Keyframe -> rank assignment of a pose step.  Without statistics: round-robin over the work list
 // (bba_shard_keyframe_owner).  With the statistics of the previous pose step (replicated, hence identical on all ranks):
 // longest-processing-time-first onto the least loaded rank, so that the ranks finish their Gauss-Newton loops together.
-void AssignKeyframes(bba_handle h, const std::vector<int>& ids, std::vector<int>* owner) {
-  const int world = h->cfg.world_size, n = static_cast<int>(ids.size());
+void BalanceWork(const float* cost, int n, int world, int* owner) {
   double known_sum = 0;
   int known = 0;
-  for (int kf : ids)
-    if (kf < static_cast<int>(h->kf_cost.size()) && h->kf_cost[kf] > 0) { known_sum += h->kf_cost[kf]; ++known; }
-  if (known == 0) {
-    for (int i = 0; i < n; ++i) (*owner)[i] = i % world;
+  for (int i = 0; i < n; ++i)
+    if (cost && cost[i] > 0) { known_sum += cost[i]; ++known; }
+  if (known == 0 || world <= 1) {
+    for (int i = 0; i < n; ++i) owner[i] = world > 1 ? i % world : 0;
     return;
   }
   const double fallback = known_sum / known;
   std::vector<std::pair<double, int>> order(n);
-  for (int i = 0; i < n; ++i) {
-    const int kf = ids[i];
-    const double c = (kf < static_cast<int>(h->kf_cost.size()) && h->kf_cost[kf] > 0) ? h->kf_cost[kf] : fallback;
-    order[i] = {-c, i};
-  }
+  for (int i = 0; i < n; ++i) order[i] = {-(cost[i] > 0 ? static_cast<double>(cost[i]) : fallback), i};
   std::sort(order.begin(), order.end());   // descending cost, ties by list position
   std::vector<double> load(world, 0.0);
   for (const auto& e : order) {
     int best = 0;
     for (int r = 1; r < world; ++r)
       if (load[r] < load[best]) best = r;
-    (*owner)[e.second] = best;
+    owner[e.second] = best;
     load[best] -= e.first;
   }
+}
+
+void AssignKeyframes(bba_handle h, const std::vector<int>& ids, std::vector<int>* owner) {
+  std::vector<float> cost(ids.size(), 0.f);
+  for (size_t i = 0; i < ids.size(); ++i)
+    if (ids[i] < static_cast<int>(h->kf_cost.size())) cost[i] = h->kf_cost[ids[i]];
+  BalanceWork(cost.data(), static_cast<int>(ids.size()), h->cfg.world_size, owner->data());
 }
 
 bba_status RunPoseStep(bba_handle h, const std::vector<int>& ids, const std::vector<Pose>& init, int max_iterations, cudaStream_t s) {
@@ -2126,6 +2128,10 @@ uint32_t bba_shard_slice_length(uint32_t surfels_size, int world_size) {
 }
 
 int bba_shard_keyframe_owner(int list_index, int world_size) { return world_size > 1 ? list_index % world_size : 0; }
+
+void bba_balance_keyframes(const float* cost, int count, int world_size, int* owner) {
+  if (count > 0 && owner) BalanceWork(cost, count, world_size, owner);
+}
 
 uint64_t bba_kernel_launch_count(bba_handle h) { return h ? h->launches : 0; }
 

@@ -275,6 +275,9 @@ int      bba_shard_surfel_owner(uint32_t surfel_index, int world_size);
 uint32_t bba_shard_surfel_local_index(uint32_t surfel_index, int world_size);
 uint32_t bba_shard_slice_length(uint32_t surfels_size, int world_size);
 int  bba_shard_keyframe_owner(int list_index, int world_size);
+/* The assignment rule itself (host-only, no device needed): cost[i] > 0 = measured work of work-list entry i, 0 = unknown
+ * (mean of the known ones); all unknown or world_size 1 -> round-robin. */
+void bba_balance_keyframes(const float* cost, int count, int world_size, int* owner);
 
 /* Re-uploads the images of an existing keyframe from host memory (same sizes as at creation) -- the per-step
  * host->device input path of a live system, where a keyframe's RGB-D data arrives from the sensor thread

@@ -105,3 +105,33 @@ def test_exchange_patterns_world_size_2_gloo(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(world, port, 1000, 9, str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def test_keyframe_balancing_rule():
+    """bba_balance_keyframes: longest-first onto the least loaded rank; deterministic; round-robin without statistics."""
+    from badslam_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(1)
+    for world in (2, 3, 8):
+        n = 200
+        cost = (rng.random(n) ** 3 * 100 + 1).astype(np.float32)      # skewed work, like Gauss-Newton iterations x visible pairs
+        owner = np.full(n, -1, np.int32)
+        lib.bba_balance_keyframes(cost.ctypes.data, n, world, owner.ctypes.data)
+        assert owner.min() >= 0 and owner.max() < world
+        load = np.bincount(owner, weights=cost, minlength=world)
+        assert load.max() - load.min() <= cost.max()                     # LPT bound: within one item of each other
+        rr = np.bincount(np.arange(n) % world, weights=cost, minlength=world)
+        assert load.max() <= rr.max() + 1e-3                             # never worse than round-robin here
+        again = np.full(n, -1, np.int32)
+        lib.bba_balance_keyframes(cost.ctypes.data, n, world, again.ctypes.data)
+        assert np.array_equal(owner, again)                              # every rank computes the same assignment
+        # unknown entries take the mean of the known ones; no statistics at all -> round-robin
+        partial = cost.copy()
+        partial[::3] = 0
+        lib.bba_balance_keyframes(partial.ctypes.data, n, world, owner.ctypes.data)
+        assert np.bincount(owner, minlength=world).min() > 0
+        zeros = np.zeros(n, np.float32)
+        lib.bba_balance_keyframes(zeros.ctypes.data, n, world, owner.ctypes.data)
+        assert np.array_equal(owner, np.arange(n) % world)
+    lib.bba_balance_keyframes(cost.ctypes.data, n, 1, owner.ctypes.data)
+    assert not owner.any()
