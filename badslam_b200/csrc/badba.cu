@@ -2104,6 +2104,12 @@ bba_status bba_peer_import(bba_handle h, const bba_peer_handle* all, int count) 
 
 int bba_peer_count(bba_handle h) { return h ? h->peers.count : 0; }
 
+bba_status bba_peer_unmap(bba_handle h) {
+  if (!h) return BBA_ERR_INVALID_ARGUMENT;
+  UnmapPeers(h);
+  return BBA_OK;
+}
+
 bba_status bba_set_collective(bba_handle h, bba_collective_fn fn, void* user) {
   if (!h) return BBA_ERR_INVALID_ARGUMENT;
   h->collective = fn;

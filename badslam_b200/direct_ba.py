@@ -439,17 +439,30 @@ class DirectBA:
     def EnablePeerExchange(self, group=None) -> int:
         """Maps the surfel replicas of the other ranks into this process (CUDA IPC over NVLink, bba_peer_export /
         bba_peer_import): the geometry kernels then store updated surfels straight into every replica and the exchange
-        step is a barrier.  Collective call; returns the number of mapped peers."""
+        step is a barrier.  Collective call.  All ranks end up in the same mode: if the mapping fails anywhere (IPC not
+        permitted, ...) every rank unmaps and 0 is returned, otherwise the number of mapped peers."""
+        import torch
         import torch.distributed as dist
-        ph = _lib.PeerHandle()
-        self._check(self._lib.bba_peer_export(self._h, C.byref(ph)))
         world = dist.get_world_size(group)
+        ok = 1
+        ph = _lib.PeerHandle()
+        if self._lib.bba_peer_export(self._h, C.byref(ph)) != 0:
+            ok = 0
         blobs = [None] * world
-        dist.all_gather_object(blobs, bytes(ph), group=group)
-        arr = (_lib.PeerHandle * world)()
-        for r, b in enumerate(blobs):
-            C.memmove(C.byref(arr[r]), b, C.sizeof(_lib.PeerHandle))
-        self._check(self._lib.bba_peer_import(self._h, arr, world))
+        dist.all_gather_object(blobs, bytes(ph) if ok else None, group=group)
+        if ok and all(b is not None for b in blobs):
+            arr = (_lib.PeerHandle * world)()
+            for r, b in enumerate(blobs):
+                C.memmove(C.byref(arr[r]), b, C.sizeof(_lib.PeerHandle))
+            if self._lib.bba_peer_import(self._h, arr, world) != 0:
+                ok = 0
+        else:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self._surfels.device if self._surfels is not None else "cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            self._lib.bba_peer_unmap(self._h)
+            return 0
         return int(self._lib.bba_peer_count(self._h))
 
     # -- multi-GPU (one process per GPU) ---------------------------------------------------------------

@@ -262,6 +262,8 @@ typedef struct {
 bba_status bba_peer_export(bba_handle h, bba_peer_handle* out);
 bba_status bba_peer_import(bba_handle h, const bba_peer_handle* all_ranks, int count);
 int bba_peer_count(bba_handle h);
+/* Back to the host-collective exchange (all ranks must agree on the mode: a rank whose import failed makes everyone unmap). */
+bba_status bba_peer_unmap(bba_handle h);
 
 /* The partition itself, exposed so that hosts and tests can reason about it.
  * Surfels: 256-surfel granules are dealt round-robin (granule g -> rank g % world_size), which gives every rank the same
