@@ -49,6 +49,11 @@ class BAResult(C.Structure):
                 ("surfels_created", C.c_uint32), ("surfels_merged", C.c_uint32)]
 
 
+class PreprocessOptions(C.Structure):
+    _fields_ = [("bilateral_filter_sigma_xy", C.c_float), ("bilateral_filter_sigma_inv_depth", C.c_float),
+                ("bilateral_filter_radius_factor", C.c_float), ("max_depth", C.c_float)]
+
+
 class PeerHandle(C.Structure):
     _fields_ = [("surfels_ipc", C.c_ubyte * 64), ("surfels_offset", C.c_uint64), ("active_ipc", C.c_ubyte * 64),
                 ("active_offset", C.c_uint64), ("pitch_bytes", C.c_uint64), ("surfels_size", C.c_uint32), ("rank", C.c_int32)]
@@ -114,6 +119,8 @@ SYMBOLS = {
     "bba_create_surfels_for_keyframe": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_uint32), _P]),
     "bba_merge_surfels_for_keyframe": (C.c_int, [_P, C.c_int, C.POINTER(C.c_uint32), _P]),
     "bba_compact_surfels": (C.c_int, [_P, C.c_uint32, C.c_int, C.POINTER(C.c_uint32), _P]),
+    "bba_preprocess_frame": (C.c_int, [_P, C.POINTER(PreprocessOptions), _P, C.c_size_t, _P, C.c_size_t, _P, C.c_size_t,
+                                       _P, C.c_size_t, _P, C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_float), C.POINTER(C.c_float), _P]),
     "bba_pcg_debug": (C.c_int, [_P, C.POINTER(BAOptions), C.POINTER(C.c_uint32), _P, _P, _P, _P, _P, _P]),
     "bba_bundle_adjust": (C.c_int, [_P, C.POINTER(BAOptions), C.POINTER(BAResult), _P]),
     "bba_peer_export": (C.c_int, [_P, _P]),
@@ -148,7 +155,7 @@ def load():
         fn = getattr(lib, name)   # AttributeError if the symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.bba_abi_version() != 4:
+    if lib.bba_abi_version() != 5:
         raise ImportError("libbadba_b200.so ABI version mismatch")
     _lib = lib
     return lib

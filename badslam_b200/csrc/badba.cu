@@ -22,6 +22,7 @@
 #include "../../include/badba.h"
 #include "host_math.hpp"
 #include "kernels.cuh"
+#include "preprocess_tile.cuh"
 
 namespace {
 
@@ -235,6 +236,10 @@ struct bba_context {
   unsigned int* h_deleted_count = nullptr;   // pinned
   unsigned int* d_compact_sums = nullptr;
   uint32_t compact_sums_capacity = 0;
+
+  // keyframe preprocessing (bba_preprocess_frame), lazily allocated
+  float* d_min_max = nullptr;
+  float* h_min_max = nullptr;                // pinned
 
   // PCG solver (lazily allocated): r, M, delta, g, p with pcg_capacity floats each
   float* d_pcg[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -1406,6 +1411,8 @@ void bba_destroy(bba_handle h) {
   cudaFree(h->d_deleted_count);
   cudaFreeHost(h->h_deleted_count);
   cudaFree(h->d_compact_sums);
+  cudaFree(h->d_min_max);
+  cudaFreeHost(h->h_min_max);
   for (float* v : h->d_pcg) cudaFree(v);
   cudaFree(h->d_pcg_scalars);
   cudaFreeHost(h->h_pcg_scalars);
@@ -1696,6 +1703,67 @@ bba_status bba_estimate_frame_pose(bba_handle h, int id, const float init[7], fl
   std::memcpy(out, h->h_pose_est + 7 * id, sizeof(float) * 7);
   if (iterations) *iterations = h->h_iterations[id];
   if (converged) *converged = h->h_converged[id];
+  return BBA_OK;
+}
+
+bba_status bba_preprocess_frame(bba_handle h, const bba_preprocess_options* o,
+                                const uint16_t* device_raw_depth, size_t raw_depth_pitch,
+                                const uint8_t* device_rgb, size_t rgb_pitch,
+                                uint16_t* device_depth, size_t depth_pitch,
+                                uint16_t* device_normals, size_t normals_pitch,
+                                uint16_t* device_radius, size_t radius_pitch,
+                                uint8_t* device_color_rgba, size_t color_pitch,
+                                float* min_depth, float* max_depth, void* stream) {
+  if (!h || !o || !device_raw_depth || !device_depth || !device_normals || !device_radius) return h ? Fail(h, BBA_ERR_INVALID_ARGUMENT, "bba_preprocess_frame: null argument") : BBA_ERR_INVALID_ARGUMENT;
+  if ((device_rgb == nullptr) != (device_color_rgba == nullptr))
+    return Fail(h, BBA_ERR_INVALID_ARGUMENT, "bba_preprocess_frame: rgb input and rgba output go together");
+  if ((raw_depth_pitch | depth_pitch | normals_pitch | radius_pitch) & 1u)
+    return Fail(h, BBA_ERR_INVALID_ARGUMENT, "bba_preprocess_frame: u16 image pitches must be even");
+  if (device_color_rgba && ((color_pitch & 3u) || (reinterpret_cast<uintptr_t>(device_color_rgba) & 3u)))
+    return Fail(h, BBA_ERR_INVALID_ARGUMENT, "bba_preprocess_frame: the rgba image must be 4-byte aligned");
+  if (device_depth == device_raw_depth)
+    return Fail(h, BBA_ERR_INVALID_ARGUMENT, "bba_preprocess_frame: in-place filtering is not possible (tiles read their neighbours' raw depth)");
+  // BilateralFilteringAndDepthCutoffCUDA (cuda_depth_processing.cu:100-128)
+  const int radius = static_cast<int>(o->bilateral_filter_radius_factor * o->bilateral_filter_sigma_xy + 0.5f);
+  if (radius < 0 || radius > bba::pre::kMaxFilterRadius)
+    return Fail(h, BBA_ERR_INVALID_ARGUMENT, "bba_preprocess_frame: bilateral filter radius outside [0, 16]");
+  if (!(o->bilateral_filter_sigma_xy > 0.f) || !(o->bilateral_filter_sigma_inv_depth > 0.f) || !(o->max_depth > 0.f))
+    return Fail(h, BBA_ERR_INVALID_ARGUMENT, "bba_preprocess_frame: sigma_xy, sigma_inv_depth and max_depth must be positive");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!h->d_min_max) {
+    BBA_CUDA(h, cudaMalloc(&h->d_min_max, 2 * sizeof(float)));
+    BBA_CUDA(h, cudaMallocHost(&h->h_min_max, 2 * sizeof(float)));
+  }
+  const bba::CameraParams cam = MakeCamera(h);
+  bba::pre::FrameArgs f{};
+  f.w = cam.w; f.h = cam.h;
+  f.fx_inv = cam.fx_inv; f.fy_inv = cam.fy_inv; f.cx_inv = cam.cx_inv; f.cy_inv = cam.cy_inv;
+  f.raw_to_float = cam.raw_to_float; f.a = cam.a;
+  f.cell = cam.cell; f.cf_w = cam.cf_w; f.cfactor = cam.cfactor;
+  f.denom_xy = 2.0f * o->bilateral_filter_sigma_xy * o->bilateral_filter_sigma_xy;
+  f.denom_value = 2.0f * o->bilateral_filter_sigma_inv_depth * o->bilateral_filter_sigma_inv_depth;
+  f.radius = radius;
+  f.radius_squared = radius * radius;
+  const float max_raw = o->max_depth / cam.raw_to_float;   // bad_slam.cc:703 (float -> u16 at the call)
+  f.max_depth = max_raw >= 65535.f ? static_cast<uint16_t>(65535) : static_cast<uint16_t>(max_raw);
+  f.raw_depth = device_raw_depth; f.raw_pitch = static_cast<uint32_t>(raw_depth_pitch);
+  f.out_depth = device_depth; f.out_depth_pitch = static_cast<uint32_t>(depth_pitch);
+  f.out_normals = device_normals; f.out_normals_pitch = static_cast<uint32_t>(normals_pitch);
+  f.out_radius = device_radius; f.out_radius_pitch = static_cast<uint32_t>(radius_pitch);
+  f.min_max = h->d_min_max;
+  f.cw = cam.cw; f.ch = cam.ch;
+  f.rgb = device_rgb; f.rgb_pitch = static_cast<uint32_t>(rgb_pitch);
+  f.rgba = device_color_rgba; f.rgba_pitch = static_cast<uint32_t>(color_pitch);
+  f.tiles_x = (f.w + bba::pre::kTile - 1) / bba::pre::kTile;
+  f.tiles_y = (f.h + bba::pre::kTile - 1) / bba::pre::kTile;
+  h->launches += bba::LaunchPreprocessFrame(f, s);
+  BBA_CUDA(h, cudaGetLastError());
+  if (min_depth || max_depth) {   // ComputeMinMaxDepthCUDA returns host values and synchronises (cuda_depth_processing.cu:452-463)
+    BBA_CUDA(h, cudaMemcpyAsync(h->h_min_max, h->d_min_max, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    BBA_CUDA(h, cudaStreamSynchronize(s));
+    if (min_depth) *min_depth = h->h_min_max[0];
+    if (max_depth) *max_depth = h->h_min_max[1];
+  }
   return BBA_OK;
 }
 

@@ -210,6 +210,49 @@ class DirectBA:
         self._keyframes.append(kf)
         return kf.id
 
+    # -- keyframe preprocessing ------------------------------------------------------
+    def PreprocessFrame(self, raw_depth: torch.Tensor, rgb: Optional[torch.Tensor] = None, *,
+                        bilateral_filter_sigma_xy: float = 1.5, bilateral_filter_sigma_inv_depth: float = 0.005,
+                        bilateral_filter_radius_factor: float = 2.0, max_depth: float = 3.0,
+                        want_min_max: bool = True, stream=None):
+        """BadSlam::PreprocessFrame (bad_slam.cc:692-765) + ComputeMinMaxDepthCUDA (bad_slam.cc:978) in one kernel launch:
+        raw u16 depth [h, w] (0 = no measurement) and uchar3 colour [ch, cw, 3] on the device -> (depth, normals, radius, rgba,
+        min_depth, max_depth), the buffers Keyframe() / AddKeyframe take.  Defaults: bad_slam_config.h:96-122."""
+        assert raw_depth.is_cuda and raw_depth.dim() == 2 and raw_depth.element_size() == 2 and raw_depth.stride(1) == 1
+        dev = raw_depth.device
+        h, w = raw_depth.shape
+        depth = torch.empty((h, w), dtype=torch.int16, device=dev)
+        normals = torch.empty((h, w), dtype=torch.int16, device=dev)
+        radius = torch.empty((h, w), dtype=torch.int16, device=dev)
+        rgba = None
+        rgb_ptr, rgb_pitch, rgba_ptr, rgba_pitch = None, 0, None, 0
+        if rgb is not None:
+            assert rgb.is_cuda and rgb.dtype == torch.uint8 and rgb.dim() == 3 and rgb.shape[2] == 3 and rgb.stride(2) == 1 \
+                and rgb.stride(1) == 3
+            rgba = torch.empty((rgb.shape[0], rgb.shape[1], 4), dtype=torch.uint8, device=dev)
+            rgb_ptr, rgb_pitch, rgba_ptr, rgba_pitch = rgb.data_ptr(), rgb.stride(0), rgba.data_ptr(), rgba.stride(0)
+        opt = _lib.PreprocessOptions(bilateral_filter_sigma_xy, bilateral_filter_sigma_inv_depth,
+                                     bilateral_filter_radius_factor, max_depth)
+        mn, mx = C.c_float(float("inf")), C.c_float(0.0)
+        self._check(self._lib.bba_preprocess_frame(
+            self._h, C.byref(opt), raw_depth.data_ptr(), raw_depth.stride(0) * 2, rgb_ptr, rgb_pitch,
+            depth.data_ptr(), depth.stride(0) * 2, normals.data_ptr(), normals.stride(0) * 2,
+            radius.data_ptr(), radius.stride(0) * 2, rgba_ptr, rgba_pitch,
+            C.byref(mn) if want_min_max else None, C.byref(mx) if want_min_max else None, self._stream_ptr(stream)))
+        u16 = lambda a: a.view(torch.uint16)
+        return u16(depth), u16(normals), u16(radius), rgba, mn.value, mx.value
+
+    def CreateKeyframeFromFrame(self, frame_index: int, raw_depth: torch.Tensor, rgb: torch.Tensor, global_T_frame,
+                                stream=None, **preprocess_options) -> "Keyframe":
+        """Preprocesses a raw frame and adds it as a keyframe (BadSlam::CreateKeyframe, bad_slam.cc:957-1010: min / max depth,
+        Keyframe(), DirectBA::AddKeyframe)."""
+        depth, normals, radius, rgba, mn, mx = self.PreprocessFrame(raw_depth, rgb, stream=stream, **preprocess_options)
+        if not (mn > 0.0 and mx >= mn):
+            raise BadBAError(_lib.ERR_STATE, "CreateKeyframeFromFrame: the frame has no valid depth (keyframe.cc:57-59 requires min_depth > 0)")
+        kf = Keyframe(frame_index, mn, mx, depth, normals, radius, rgba, global_T_frame)
+        self.AddKeyframe(kf, stream=stream)
+        return kf
+
     def keyframes(self) -> List[Keyframe]:
         return self._keyframes
 

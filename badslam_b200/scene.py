@@ -559,3 +559,47 @@ def displace_surfels(scene, seed=3):
         p = sc.surfels[0:3, sel]
         sc.surfels[0:3, sel] = c0[:, None] + f * (p - c0[:, None])
     return sc, away, front, behind
+
+
+def raw_frame(scene, k, noise_raw=3.0, hole_fraction=0.01, far_fraction=0.01, seed=11):
+    """The sensor's view of keyframe k before preprocessing: raw u16 depth (0 = no measurement; Gaussian noise of `noise_raw`
+    raw units, a fraction of pixels dropped, a fraction pushed beyond any sensible max_depth) and the uchar3 colour image --
+    the inputs of BadSlam::PreprocessFrame (bad_slam.cc:640-765)."""
+    cfg = scene.cfg
+    raw, rgb = _render_keyframe(cfg, scene.depth_K, np.asarray(scene.poses_true[k]), scene.planes)
+    rng = np.random.default_rng(seed + 1000 * k)
+    valid = raw != UNKNOWN_DEPTH
+    out = raw.astype(np.float64)
+    out += rng.normal(0.0, noise_raw, raw.shape)
+    out = np.clip(np.rint(out), 1, 32000).astype(np.uint16)
+    out[~valid] = 0
+    out[rng.random(raw.shape) < hole_fraction] = 0
+    far = (rng.random(raw.shape) < far_fraction) & valid
+    out[far] = np.uint16(30000)
+    return out, rgb
+
+
+def blank_scene(width, height, cell=4, seed=9, depth_a=0.02, cfactor_scale=1e-3):
+    """A camera model without content (one empty keyframe, no surfels, a random depth-deformation grid): what the
+    preprocessing tests need to build a DirectBA / oracle / reference context for an arbitrary image size."""
+    cfg = SceneConfig(width, height, 1, 0, cell=cell, seed=seed, name=f"blank{width}x{height}")
+    rng = np.random.default_rng(seed)
+    depth_K = np.array([0.5 * height + 7, 0.5 * height + 7, 0.5 * width - 0.5, 0.5 * height - 0.5], np.float32)
+    z16 = np.full((1, height, width), UNKNOWN_DEPTH, np.uint16)
+    cf = (cfactor_scale * rng.random(((height - 1) // cell + 1, (width - 1) // cell + 1))).astype(np.float32)
+    ident = np.array([[0, 0, 0, 1, 0, 0, 0]], np.float32)
+    return Scene(cfg, depth_K, depth_K.copy(), z16, np.zeros_like(z16), np.zeros_like(z16),
+                 np.zeros((1, height, width, 4), np.uint8), ident, ident.copy(), np.ones(1, np.float32), np.ones(1, np.float32),
+                 np.zeros((17, 128), np.float32), 0, cf, depth_a, None)
+
+
+def random_raw_frame(width, height, seed=0, hole_fraction=0.05):
+    """Raw depth of a slanted surface around 1.5 - 2 m with 2 raw units of noise and holes, and random colours.  (White-noise
+    depth would make the bilateral filter return its centre sample, rcp(rcp(c)) truncated: c or c - 1 depending on the last
+    bit of the arithmetic -- a coin flip no two implementations share.)"""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:height, 0:width]
+    raw = (1500.3 + 0.83 * xx + 0.47 * yy + rng.normal(0, 2.0, (height, width))).astype(np.uint16)
+    raw[rng.random((height, width)) < hole_fraction] = 0
+    rgb = rng.integers(0, 256, (height, width, 3), dtype=np.uint8)
+    return raw, rgb

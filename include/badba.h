@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BBA_ABI_VERSION 4
+#define BBA_ABI_VERSION 5
 
 typedef struct bba_context* bba_handle;
 
@@ -287,6 +287,32 @@ void bba_balance_keyframes(const float* cost, int count, int world_size, int* ow
 bba_status bba_update_keyframe_host(bba_handle h, int keyframe_id,
                                     const uint16_t* host_depth, const uint16_t* host_normals,
                                     const uint16_t* host_radius, const uint8_t* host_color_rgba, void* stream);
+
+/* ---- keyframe preprocessing: raw RGB-D frame -> the keyframe buffers bba_add_keyframe takes ----
+ * BadSlam::PreprocessFrame (bad_slam.cc:692-765): ComputeBrightnessCUDA (cuda_image_processing.cu:165-193),
+ * BilateralFilteringAndDepthCutoffCUDA (cuda_depth_processing.cu:42-128), ComputeNormalsCUDA (:134-276),
+ * ComputePointRadiiAndRemoveIsolatedPixelsCUDA (:295-383), and the ComputeMinMaxDepthCUDA (:390-465) of keyframe creation
+ * (bad_slam.cc:978), fused into one kernel launch.  Uses the handle's depth camera, depth deformation (a, cfactor) and
+ * raw_to_float_depth.  All images are device memory with byte pitches; raw depth: 0 = no measurement; rgb: uchar3.  The output
+ * depth must not alias the raw depth.  device_rgb / device_color_rgba may both be NULL (depth only).  Pixels dropped by a stage
+ * get depth 65535, normal 0 and radius 0 (the reference leaves their radius untouched).  min_depth / max_depth (metres, over
+ * the valid output pixels; +inf / 0 when there is none) may be NULL; when given the call synchronises the stream like
+ * ComputeMinMaxDepthCUDA does.  The reference's optional CPU median filter (preprocessing.cc:37-85, off by default) and the
+ * depth / colour pyramids are not part of this call. */
+typedef struct {
+  float bilateral_filter_sigma_xy;         /* BadSlamConfig::bilateral_filter_sigma_xy          default 1.5   (bad_slam_config.h:113) */
+  float bilateral_filter_sigma_inv_depth;  /* BadSlamConfig::bilateral_filter_sigma_inv_depth   default 0.005 (:122) */
+  float bilateral_filter_radius_factor;    /* BadSlamConfig::bilateral_filter_radius_factor     default 2.0   (:118); radius <= 16 px */
+  float max_depth;                         /* BadSlamConfig::max_depth, metres                  default 3.0   (:96) */
+} bba_preprocess_options;
+bba_status bba_preprocess_frame(bba_handle h, const bba_preprocess_options* options,
+                                const uint16_t* device_raw_depth, size_t raw_depth_pitch,
+                                const uint8_t* device_rgb, size_t rgb_pitch,
+                                uint16_t* device_depth, size_t depth_pitch,
+                                uint16_t* device_normals, size_t normals_pitch,
+                                uint16_t* device_radius, size_t radius_pitch,
+                                uint8_t* device_color_rgba, size_t color_pitch,
+                                float* min_depth, float* max_depth, void* stream);
 
 /* ---- instrumentation ---- */
 uint64_t   bba_kernel_launch_count(bba_handle h);   /* kernels launched through this handle so far */

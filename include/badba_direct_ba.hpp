@@ -37,6 +37,12 @@ struct DeviceImage {
   size_t pitch_bytes;
 };
 
+template <typename T>
+struct MutableDeviceImage {
+  T* address;
+  size_t pitch_bytes;
+};
+
 template <typename SE3f, typename PinholeCamera4f>
 class DirectBA {
  public:
@@ -136,6 +142,22 @@ class DirectBA {
     uint32_t created = 0;
     Check(bba_create_surfels_for_keyframe(h_, keyframe_id, filter_new_surfels, &created, stream), "bba_create_surfels_for_keyframe");
     return created;
+  }
+
+  // BadSlam::PreprocessFrame (bad_slam.cc:692-765: ComputeBrightnessCUDA, BilateralFilteringAndDepthCutoffCUDA,
+  // ComputeNormalsCUDA, ComputePointRadiiAndRemoveIsolatedPixelsCUDA) + ComputeMinMaxDepthCUDA (bad_slam.cc:978) in one
+  // launch.  depth_cutoff = BadSlamConfig::max_depth (metres); rgb: uchar3; the outputs are the buffers AddKeyframe takes.  min_depth / max_depth may be nullptr (no sync).
+  void PreprocessFrame(cudaStream_t stream, float bilateral_filter_sigma_xy, float bilateral_filter_sigma_inv_depth,
+                       float bilateral_filter_radius_factor, float depth_cutoff,
+                       DeviceImage<uint16_t> raw_depth, DeviceImage<uint8_t> rgb,
+                       MutableDeviceImage<uint16_t> depth, MutableDeviceImage<uint16_t> normals,
+                       MutableDeviceImage<uint16_t> radius, MutableDeviceImage<uint8_t> color_rgba,
+                       float* min_depth, float* max_depth) {
+    const bba_preprocess_options o{bilateral_filter_sigma_xy, bilateral_filter_sigma_inv_depth, bilateral_filter_radius_factor, depth_cutoff};
+    Check(bba_preprocess_frame(h_, &o, raw_depth.address, raw_depth.pitch_bytes, rgb.address, rgb.pitch_bytes, depth.address,
+                               depth.pitch_bytes, normals.address, normals.pitch_bytes, radius.address, radius.pitch_bytes,
+                               color_rgba.address, color_rgba.pitch_bytes, min_depth, max_depth, stream),
+          "bba_preprocess_frame");
   }
 
   // direct_ba.cc:566-653 (runs inside BundleAdjustment on the reference's schedule; exposed like the reference does)

@@ -195,6 +195,18 @@ int orc_pair_residuals_debug(const orc_model* m, const orc_keyframes* kfs, int k
 /* Sampling helper exposed for the generator / hardware validation. */
 float orc_tex_luma(const orc_model* m, const orc_keyframes* kfs, int k, float x, float y);
 
+/* ---- keyframe preprocessing (preprocess_oracle.c) ---- dense row-major images */
+uint16_t orc_float_to_half(float f);   /* __float2half_rn as bits */
+void orc_bilateral_filter_and_depth_cutoff(int w, int h, float sigma_xy, float sigma_value, float radius_factor,
+                                           uint16_t max_depth, float raw_to_float, const uint16_t* in, uint16_t* out);
+void orc_compute_normals(const orc_model* m, const uint16_t* in_depth, uint16_t* out_depth, uint16_t* out_normals);
+void orc_compute_point_radii_and_remove_isolated_pixels(const orc_model* m, const uint16_t* depth, uint16_t* radius, uint16_t* out_depth);
+void orc_compute_min_max_depth(int w, int h, float raw_to_float, const uint16_t* depth, float* min_depth, float* max_depth);
+void orc_compute_brightness(int w, int h, const uint8_t* rgb, uint8_t* rgba);
+void orc_preprocess_frame(const orc_model* m, float sigma_xy, float sigma_inv_depth, float radius_factor, float max_depth_m,
+                          const uint16_t* raw_depth, const uint8_t* rgb, uint16_t* out_depth, uint16_t* out_normals,
+                          uint16_t* out_radius, uint8_t* out_rgba, float* min_depth, float* max_depth);
+
 /* Small pose utilities for the python harness. */
 void orc_se3_exp(const float a[6], float out[7]);
 void orc_se3_log(const float T[7], float out[6]);

@@ -18,7 +18,7 @@ _LIB_PATH = os.path.join(_HERE, "_build", "libbadba_oracle.so")
 def build(force: bool = False) -> str:
     if force or not os.path.exists(_LIB_PATH) or any(
             os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB_PATH)
-            for f in ("badba_oracle.c", "badba_oracle.h", "host_math.h")):
+            for f in ("badba_oracle.c", "preprocess_oracle.c", "badba_oracle.h", "host_math.h")):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _LIB_PATH
 
@@ -220,6 +220,47 @@ class Oracle:
         self.n = int(self.lib.orc_compact_surfels(_p(self.surfels, C.c_float), C.c_int(self.pitch), C.c_uint32(self.n),
                                                   _p(self.active, C.c_uint8) if with_active else None))
         return self.n
+
+    # -- keyframe preprocessing (preprocess_oracle.c) --------------------------------------------------------------------
+    def preprocess_frame(self, raw_depth, rgb, sigma_xy=1.5, sigma_inv_depth=0.005, radius_factor=2.0, max_depth=3.0):
+        """BadSlam::PreprocessFrame + min / max depth: (depth, normals, radius, rgba, min_depth, max_depth)."""
+        m = self.model
+        raw = np.ascontiguousarray(raw_depth, np.uint16)
+        assert raw.shape == (m.depth_h, m.depth_w)
+        depth, normals, radius = (np.zeros_like(raw) for _ in range(3))
+        rgba = None
+        if rgb is not None:
+            rgb = np.ascontiguousarray(rgb, np.uint8)
+            assert rgb.shape == (m.color_h, m.color_w, 3)
+            rgba = np.zeros((m.color_h, m.color_w, 4), np.uint8)
+        mn, mx = C.c_float(), C.c_float()
+        self.lib.orc_preprocess_frame(C.byref(m), C.c_float(sigma_xy), C.c_float(sigma_inv_depth), C.c_float(radius_factor),
+                                      C.c_float(max_depth), _p(raw, C.c_uint16), None if rgb is None else _p(rgb, C.c_uint8),
+                                      _p(depth, C.c_uint16), _p(normals, C.c_uint16), _p(radius, C.c_uint16),
+                                      None if rgba is None else _p(rgba, C.c_uint8), C.byref(mn), C.byref(mx))
+        return depth, normals, radius, rgba, mn.value, mx.value
+
+    def bilateral_filter(self, raw_depth, sigma_xy=1.5, sigma_inv_depth=0.005, radius_factor=2.0, max_depth_raw=15000):
+        raw = np.ascontiguousarray(raw_depth, np.uint16)
+        out = np.zeros_like(raw)
+        self.lib.orc_bilateral_filter_and_depth_cutoff(C.c_int(raw.shape[1]), C.c_int(raw.shape[0]), C.c_float(sigma_xy),
+                                                       C.c_float(sigma_inv_depth), C.c_float(radius_factor),
+                                                       C.c_uint16(max_depth_raw), C.c_float(self.model.raw_to_float_depth),
+                                                       _p(raw, C.c_uint16), _p(out, C.c_uint16))
+        return out
+
+    def compute_normals(self, depth):
+        d = np.ascontiguousarray(depth, np.uint16)
+        out_d, out_n = np.zeros_like(d), np.zeros_like(d)
+        self.lib.orc_compute_normals(C.byref(self.model), _p(d, C.c_uint16), _p(out_d, C.c_uint16), _p(out_n, C.c_uint16))
+        return out_d, out_n
+
+    def compute_radii(self, depth):
+        d = np.ascontiguousarray(depth, np.uint16)
+        rad, out_d = np.zeros_like(d), np.zeros_like(d)
+        self.lib.orc_compute_point_radii_and_remove_isolated_pixels(C.byref(self.model), _p(d, C.c_uint16), _p(rad, C.c_uint16),
+                                                                    _p(out_d, C.c_uint16))
+        return rad, out_d
 
     def bundle_adjust(self, optimize_poses=True, optimize_geometry=True, min_iterations=1, max_iterations=10,
                       optimize_depth_intrinsics=False, optimize_color_intrinsics=False,

@@ -1,0 +1,237 @@
+/* oracle/preprocess_oracle.c -- TEST INFRASTRUCTURE ONLY (see badba_oracle.h).
+ *
+ * CPU restatement of the reference's keyframe preprocessing: the five whole-image passes
+ * BadSlam::PreprocessFrame runs on every frame (bad_slam.cc:692-765) plus the min / max depth of keyframe creation
+ * (bad_slam.cc:978).  Dense row-major images, one function per reference kernel, IEEE arithmetic.
+ *
+ * PARITY STATUS: the reference has no golden vectors for these kernels.  They are pinned on the GPU box against the
+ * reference's own kernels compiled into oracle/_ref (ref_driver.cu: ref_preprocess_frame; tests/test_gpu_preprocess.py).  The
+ * reference is compiled with -use_fast_math: its divisions are MUFU.RCP products and exp is MUFU.EX2 (see the SASS of
+ * cuda_depth_processing.cu), so the filtered depth (a TRUNCATED float) differs from IEEE arithmetic by one raw unit on a small
+ * fraction of the pixels -- the tests bound that fraction instead of demanding bit equality.  The luma is exact: it follows
+ * the compiled contraction fma(b, 0.114, fma(r, 0.299, 0.587 * g)) + 0.5 (SASS of ComputeBrightnessKernel).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "badba_oracle.h"
+
+#define ORC_UNKNOWN_DEPTH 65535u   /* kernels.cuh:41 */
+#define ORC_INVALID_BIT 0x8000u    /* kernels.cuh:38 */
+
+static uint16_t trunc_u16(float f) {   /* cvt.rzi.u16.f32: saturating, NaN -> 0 */
+  if (!(f > 0.f)) return 0;
+  if (f >= 65535.f) return 65535;
+  return (uint16_t)f;
+}
+
+/* __float2half_rn (cuda_depth_processing.cu:355) through exact arithmetic on the value. */
+static uint16_t float_to_half_rn(float f) {
+  if (isnan(f)) return 0x7e00;
+  uint16_t sign = signbit(f) ? 0x8000 : 0;
+  double a = fabs((double)f);
+  if (a >= 65520.0) return (uint16_t)(sign | 0x7c00);   /* 65520 is the midpoint between 65504 and 2^16: ties away to inf */
+  if (a < ldexp(1.0, -14)) {                             /* subnormal half: multiples of 2^-24 */
+    double q = nearbyint(ldexp(a, 24));                  /* default rounding mode: to nearest even */
+    return (uint16_t)(sign | (uint16_t)q);               /* q == 1024 lands on the smallest normal, as it should */
+  }
+  int e;
+  double m = frexp(a, &e);                               /* a = m 2^e, m in [0.5, 1) */
+  double q = nearbyint(ldexp(m, 11));                    /* 11 significant bits: 1024 .. 2048 */
+  if (q == 2048.0) { q = 1024.0; ++e; }
+  return (uint16_t)(sign | (uint16_t)(((e - 1 + 15) << 10) + ((int)q - 1024)));
+}
+
+uint16_t orc_float_to_half(float f) { return float_to_half_rn(f); }
+
+/* BilateralFilteringAndDepthCutoffCUDAKernel (cuda_depth_processing.cu:42-98), host wrapper :100-128. */
+void orc_bilateral_filter_and_depth_cutoff(int w, int h, float sigma_xy, float sigma_value, float radius_factor,
+                                           uint16_t max_depth, float raw_to_float, const uint16_t* in, uint16_t* out) {
+  const int radius = (int)(radius_factor * sigma_xy + 0.5f);
+  const int radius_squared = radius * radius;
+  const float denom_xy = 2.0f * sigma_xy * sigma_xy;
+  const float denom_value = 2.0f * sigma_value * sigma_value;
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < h; ++y) {
+    for (int x = 0; x < w; ++x) {
+      const uint16_t center_value = in[(size_t)y * w + x];
+      if (center_value == 0 || center_value > max_depth) {
+        out[(size_t)y * w + x] = ORC_UNKNOWN_DEPTH;
+        continue;
+      }
+      const float inv_center_value = 1.0f / (raw_to_float * center_value);
+      float sum = 0, weight = 0;
+      const int min_y = y - radius > 0 ? y - radius : 0, max_y = y + radius < h - 1 ? y + radius : h - 1;
+      const int min_x = x - radius > 0 ? x - radius : 0, max_x = x + radius < w - 1 ? x + radius : w - 1;
+      for (int sy = min_y; sy <= max_y; ++sy) {
+        const int dy = sy - y;
+        for (int sx = min_x; sx <= max_x; ++sx) {
+          const int dx = sx - x;
+          const int grid_distance_squared = dx * dx + dy * dy;
+          if (grid_distance_squared > radius_squared) continue;
+          const uint16_t sample = in[(size_t)sy * w + sx];
+          if (sample == 0) continue;
+          const float inv_sample = 1.0f / (raw_to_float * sample);
+          float value_distance_squared = inv_center_value - inv_sample;
+          value_distance_squared *= value_distance_squared;
+          const float wgt = expf(-grid_distance_squared / denom_xy + -value_distance_squared / denom_value);
+          sum += wgt * inv_sample;
+          weight += wgt;
+        }
+      }
+      out[(size_t)y * w + x] = (weight == 0) ? ORC_UNKNOWN_DEPTH : trunc_u16(1.0f / (raw_to_float * sum / weight));
+    }
+  }
+}
+
+static float pre_calibrated_depth(const orc_model* m, int x, int y, uint16_t raw) {   /* util.cuh:62-69 */
+  const float cfactor = m->cfactor[(size_t)(y / m->cell) * m->cf_w + (x / m->cell)];
+  const float inv_depth = 1.0f / (m->raw_to_float_depth * raw);
+  return 1.f / (inv_depth + cfactor * expf(-m->a * inv_depth));
+}
+
+typedef struct { float x, y, z; } pre_v3;
+static pre_v3 pre_sub(pre_v3 a, pre_v3 b) { pre_v3 r = {a.x - b.x, a.y - b.y, a.z - b.z}; return r; }
+static float pre_sq(pre_v3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+
+static uint16_t image_space_normal_to_u16(float x, float y) {   /* util.cuh:121-136 */
+  const int8_t qx = (int8_t)(x * 127 + ((x > 0) ? 0.5f : -0.5f));
+  const int8_t qy = (int8_t)(y * 127 + ((y > 0) ? 0.5f : -0.5f));
+  return (uint16_t)((uint8_t)qx | ((uint16_t)(uint8_t)qy << 8));
+}
+
+/* ComputeNormalsCUDAKernel (cuda_depth_processing.cu:134-255). */
+void orc_compute_normals(const orc_model* m, const uint16_t* in_depth, uint16_t* out_depth, uint16_t* out_normals) {
+  const int w = m->depth_w, h = m->depth_h;
+  /* PixelCenterUnprojector (surfel_projection.cuh:92-99, built by surfel_projection.h:58-67) */
+  const float fx_inv = 1.0f / m->depth_K[0], fy_inv = 1.0f / m->depth_K[1];
+  const float cx_inv = -(m->depth_K[2] - 0.5f) * fx_inv, cy_inv = -(m->depth_K[3] - 0.5f) * fy_inv;
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < h; ++y) {
+    for (int x = 0; x < w; ++x) {
+      const size_t i = (size_t)y * w + x;
+      out_depth[i] = ORC_UNKNOWN_DEPTH;
+      out_normals[i] = 0;   /* ImageSpaceNormalToU16(0, 0) */
+      if (x < 1 || y < 1 || x >= w - 1 || y >= h - 1) continue;
+      const uint16_t c = in_depth[i], r = in_depth[i + 1], l = in_depth[i - 1], b = in_depth[i + w], t = in_depth[i - w];
+      if ((c | r | l | b | t) & ORC_INVALID_BIT) continue;
+      const float cd = pre_calibrated_depth(m, x, y, c), ld = pre_calibrated_depth(m, x - 1, y, l);
+      const float td = pre_calibrated_depth(m, x, y - 1, t), rd = pre_calibrated_depth(m, x + 1, y, r);
+      const float bd = pre_calibrated_depth(m, x, y + 1, b);
+      const pre_v3 lp = {ld * (fx_inv * (x - 1) + cx_inv), ld * (fy_inv * y + cy_inv), ld};
+      const pre_v3 tp = {td * (fx_inv * x + cx_inv), td * (fy_inv * (y - 1) + cy_inv), td};
+      const pre_v3 rp = {rd * (fx_inv * (x + 1) + cx_inv), rd * (fy_inv * y + cy_inv), rd};
+      const pre_v3 bp = {bd * (fx_inv * x + cx_inv), bd * (fy_inv * (y + 1) + cy_inv), bd};
+      const pre_v3 cp = {cd * (fx_inv * x + cx_inv), cd * (fy_inv * y + cy_inv), cd};
+      const float thr = 4.f;   /* kRatioThreshold^2 */
+      const float ldist = pre_sq(pre_sub(lp, cp)), rdist = pre_sq(pre_sub(rp, cp));
+      const float lr = ldist / rdist;
+      pre_v3 l2r;
+      if (lr < thr && lr > 1.f / thr) l2r = pre_sub(rp, lp);
+      else if (ldist < rdist) l2r = pre_sub(cp, lp);
+      else l2r = pre_sub(rp, cp);
+      const float bdist = pre_sq(pre_sub(bp, cp)), tdist = pre_sq(pre_sub(tp, cp));
+      const float bt = bdist / tdist;
+      pre_v3 b2t;
+      if (bt < thr && bt > 1.f / thr) b2t = pre_sub(tp, bp);
+      else if (bdist < tdist) b2t = pre_sub(cp, bp);
+      else b2t = pre_sub(tp, cp);
+      /* CrossProduct(left_to_right, bottom_to_top) (cuda_util.cuh:75-79) */
+      float nx = l2r.y * b2t.z - b2t.y * l2r.z;
+      float ny = b2t.x * l2r.z - l2r.x * b2t.z;
+      const float nz = l2r.x * b2t.y - b2t.x * l2r.y;
+      const float length = sqrtf(nx * nx + ny * ny + nz * nz);
+      if (!(length > 1e-6f)) {
+        nx = 0; ny = 0;
+      } else {
+        const float inv_length = ((fy_inv < 0) ? -1.0f : 1.0f) / length;
+        nx *= inv_length; ny *= inv_length;
+      }
+      out_normals[i] = image_space_normal_to_u16(nx, ny);
+      out_depth[i] = c;
+    }
+  }
+}
+
+/* ComputePointRadiiAndRemoveIsolatedPixelsCUDAKernel<4> (cuda_depth_processing.cu:295-358).  The reference leaves the radius of
+ * an invalid pixel untouched; 0 is written here (and by the CUDA path) so that the output is a function of the input. */
+void orc_compute_point_radii_and_remove_isolated_pixels(const orc_model* m, const uint16_t* depth, uint16_t* radius, uint16_t* out_depth) {
+  const int w = m->depth_w, h = m->depth_h;
+  const float fx_inv = 1.0f / m->depth_K[0], fy_inv = 1.0f / m->depth_K[1];
+  const float cx_inv = -(m->depth_K[2] - 0.5f) * fx_inv, cy_inv = -(m->depth_K[3] - 0.5f) * fy_inv;
+  const float rtf = m->raw_to_float_depth;
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < h; ++y) {
+    for (int x = 0; x < w; ++x) {
+      const size_t i = (size_t)y * w + x;
+      const uint16_t d16 = depth[i];
+      out_depth[i] = ORC_UNKNOWN_DEPTH;
+      radius[i] = 0;
+      if (d16 & ORC_INVALID_BIT) continue;
+      const float d = rtf * d16;
+      const pre_v3 local = {d * (fx_inv * x + cx_inv), d * (fy_inv * y + cy_inv), d};
+      int count = 0;
+      float min_sq = INFINITY;
+      for (int ny = y - 1; ny <= y + 1; ++ny) {
+        for (int nx = x - 1; nx <= x + 1; ++nx) {
+          if ((nx != x && ny != y) || (nx == x && ny == y)) continue;
+          if (nx < 0 || ny < 0 || nx >= w || ny >= h) continue;   /* cannot happen for valid pixels (1-pixel border is invalid) */
+          const uint16_t n16 = depth[(size_t)ny * w + nx];
+          if (n16 & ORC_INVALID_BIT) continue;
+          ++count;
+          const float nd = rtf * n16;
+          const pre_v3 other = {nd * (fx_inv * nx + cx_inv), nd * (fy_inv * ny + cy_inv), nd};
+          const float dist = pre_sq(pre_sub(other, local));
+          if (dist < min_sq) min_sq = dist;
+        }
+      }
+      if (count >= 4) {
+        radius[i] = float_to_half_rn(min_sq);
+        out_depth[i] = d16;
+      }
+    }
+  }
+}
+
+/* ComputeMinMaxDepthCUDAKernel + host part (cuda_depth_processing.cu:390-465); init values cuda_depth_processing.cc:41. */
+void orc_compute_min_max_depth(int w, int h, float raw_to_float, const uint16_t* depth, float* min_depth, float* max_depth) {
+  float mn = INFINITY, mx = 0;
+  for (size_t i = 0; i < (size_t)w * h; ++i) {
+    if (depth[i] & ORC_INVALID_BIT) continue;
+    const float d = raw_to_float * depth[i];
+    if (d < mn) mn = d;
+    if (d > mx) mx = d;
+  }
+  *min_depth = mn;
+  *max_depth = mx;
+}
+
+/* ComputeBrightnessKernel (cuda_image_processing.cu:165-176): rgb uchar3 -> uchar4 with .w = luma. */
+void orc_compute_brightness(int w, int h, const uint8_t* rgb, uint8_t* rgba) {
+  for (size_t i = 0; i < (size_t)w * h; ++i) {
+    const uint8_t r = rgb[3 * i], g = rgb[3 * i + 1], b = rgb[3 * i + 2];
+    const float luma = fmaf((float)b, 0.114f, fmaf((float)r, 0.299f, 0.587f * (float)g)) + 0.5f;
+    rgba[4 * i] = r; rgba[4 * i + 1] = g; rgba[4 * i + 2] = b;
+    rgba[4 * i + 3] = (uint8_t)luma;
+  }
+}
+
+/* BadSlam::PreprocessFrame (bad_slam.cc:692-765) + ComputeMinMaxDepthCUDA on its result (bad_slam.cc:978). */
+void orc_preprocess_frame(const orc_model* m, float sigma_xy, float sigma_inv_depth, float radius_factor, float max_depth_m,
+                          const uint16_t* raw_depth, const uint8_t* rgb, uint16_t* out_depth, uint16_t* out_normals,
+                          uint16_t* out_radius, uint8_t* out_rgba, float* min_depth, float* max_depth) {
+  const int w = m->depth_w, h = m->depth_h;
+  uint16_t* a = (uint16_t*)malloc(sizeof(uint16_t) * (size_t)w * h);
+  uint16_t* b = (uint16_t*)malloc(sizeof(uint16_t) * (size_t)w * h);
+  if (rgb && out_rgba) orc_compute_brightness(m->color_w, m->color_h, rgb, out_rgba);
+  const float max_raw = max_depth_m / m->raw_to_float_depth;   /* bad_slam.cc:703, float -> u16 at the call */
+  orc_bilateral_filter_and_depth_cutoff(w, h, sigma_xy, sigma_inv_depth, radius_factor, trunc_u16(max_raw), m->raw_to_float_depth, raw_depth, a);
+  orc_compute_normals(m, a, b, out_normals);
+  orc_compute_point_radii_and_remove_isolated_pixels(m, b, out_radius, out_depth);
+  /* pixels removed by the last stage keep the normal the reference computed for them; the CUDA path does the same */
+  orc_compute_min_max_depth(w, h, m->raw_to_float_depth, out_depth, min_depth, max_depth);
+  free(a);
+  free(b);
+}

@@ -94,6 +94,9 @@ def lib():
         l.ref_compact_surfels.restype = C.c_uint
         l.ref_compact_surfels.argtypes = [C.c_void_p, C.c_uint, C.c_int]
         l.ref_set_surfels_size.argtypes = [C.c_void_p, C.c_uint]
+        l.ref_preprocess_frame.restype = C.c_int
+        l.ref_preprocess_frame.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         l.ref_snapshot.argtypes = [C.c_void_p]
         l.ref_restore.argtypes = [C.c_void_p]
         l.ref_sync.argtypes = [C.c_void_p]
@@ -182,6 +185,23 @@ class RefDirectBA:
 
     def compact_surfels(self, free_count, with_active=True):
         return int(self.l.ref_compact_surfels(self.h, int(free_count), int(with_active)))
+
+    def preprocess_frame(self, raw_depth, rgb, sigma_xy=1.5, sigma_inv_depth=0.005, radius_factor=2.0, max_depth=3.0):
+        """BadSlam::PreprocessFrame + ComputeMinMaxDepthCUDA with the reference's kernels:
+        (depth, normals, radius, rgba, min_depth, max_depth)."""
+        raw = np.ascontiguousarray(raw_depth, np.uint16)
+        depth, normals, radius = (np.zeros_like(raw) for _ in range(3))
+        rgba = None
+        if rgb is not None:
+            rgb = np.ascontiguousarray(rgb, np.uint8)
+            rgba = np.zeros(rgb.shape[:2] + (4,), np.uint8)
+        mn, mx = C.c_float(), C.c_float()
+        rc = self.l.ref_preprocess_frame(self.h, sigma_xy, sigma_inv_depth, radius_factor, max_depth, raw.ctypes.data,
+                                         None if rgb is None else rgb.ctypes.data, depth.ctypes.data, normals.ctypes.data,
+                                         radius.ctypes.data, None if rgba is None else rgba.ctypes.data,
+                                         C.addressof(mn), C.addressof(mx))
+        assert rc > 0, self.l.ref_last_cuda_error()
+        return depth, normals, radius, rgba, mn.value, mx.value
 
     def set_surfels_size(self, n):
         self.l.ref_set_surfels_size(self.h, int(n))

@@ -14,9 +14,12 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
+#include "badslam/cuda_depth_processing.cuh"
+#include "badslam/cuda_image_processing.cuh"
 #include "badslam/kernel_create_surfels.h"
 #include "badslam/kernel_delete_surfels.h"
 #include "badslam/kernel_supporting_surfels.h"
@@ -1003,6 +1006,70 @@ unsigned int ref_compact_surfels(ref_context* c, unsigned int free_count, int wi
   cudaStreamSynchronize(c->stream);
   return c->surfels_size;
 }
+// BadSlam::PreprocessFrame (bad_slam.cc:692-765) followed by the ComputeMinMaxDepthCUDA of keyframe creation (bad_slam.cc:978),
+// with the reference's own kernels and host launchers (cuda_depth_processing.cu, cuda_image_processing.cu).  Dense host images
+// in and out; the radius buffer starts zeroed (the reference does not write the radius of pixels it drops).  Returns the
+// number of kernel launches (5), or -1 on a CUDA error.
+int ref_preprocess_frame(ref_context* c, float sigma_xy, float sigma_inv_depth, float radius_factor, float max_depth_m,
+                         const unsigned short* raw_depth, const unsigned char* rgb, unsigned short* out_depth,
+                         unsigned short* out_normals, unsigned short* out_radius, unsigned char* out_rgba, float* min_depth,
+                         float* max_depth) {
+  cudaStream_t s = c->stream;
+  const int w = c->cfg.depth_w, h = c->cfg.depth_h, cw = c->cfg.color_w, ch = c->cfg.color_h;
+  u16 *d_raw = nullptr, *d_a = nullptr, *d_b = nullptr, *d_normals = nullptr, *d_radius = nullptr;
+  size_t p_raw = 0, p_a = 0, p_b = 0, p_normals = 0, p_radius = 0, p_rgb = 0, p_rgba = 0;
+  uchar3* d_rgb = nullptr;
+  uchar4* d_rgba = nullptr;
+  float *d_init = nullptr, *d_result = nullptr;
+  bool ok = true;
+  auto alloc2d = [&](void** ptr, size_t* pitch, size_t row_bytes, int rows) { ok = ok && cudaMallocPitch(ptr, pitch, row_bytes, rows) == cudaSuccess; };
+  alloc2d(reinterpret_cast<void**>(&d_raw), &p_raw, sizeof(u16) * w, h);
+  alloc2d(reinterpret_cast<void**>(&d_a), &p_a, sizeof(u16) * w, h);
+  alloc2d(reinterpret_cast<void**>(&d_b), &p_b, sizeof(u16) * w, h);
+  alloc2d(reinterpret_cast<void**>(&d_normals), &p_normals, sizeof(u16) * w, h);
+  alloc2d(reinterpret_cast<void**>(&d_radius), &p_radius, sizeof(u16) * w, h);
+  if (rgb) {
+    alloc2d(reinterpret_cast<void**>(&d_rgb), &p_rgb, sizeof(uchar3) * cw, ch);
+    alloc2d(reinterpret_cast<void**>(&d_rgba), &p_rgba, sizeof(uchar4) * cw, ch);
+  }
+  ok = ok && cudaMalloc(&d_init, 2 * sizeof(float)) == cudaSuccess && cudaMalloc(&d_result, 2 * sizeof(float)) == cudaSuccess;
+  int launches = -1;
+  if (ok) {
+    const float init[2] = {std::numeric_limits<float>::infinity(), 0.f};   // cuda_depth_processing.cc:41
+    cudaMemcpyAsync(d_init, init, sizeof(init), cudaMemcpyHostToDevice, s);
+    cudaMemcpy2DAsync(d_raw, p_raw, raw_depth, sizeof(u16) * w, sizeof(u16) * w, h, cudaMemcpyHostToDevice, s);
+    cudaMemset2DAsync(d_radius, p_radius, 0, sizeof(u16) * w, h, s);
+    CUDABuffer_<u16> raw_buf(d_raw, h, w, p_raw), a_buf(d_a, h, w, p_a), b_buf(d_b, h, w, p_b);
+    CUDABuffer_<u16> normals_buf(d_normals, h, w, p_normals), radius_buf(d_radius, h, w, p_radius);
+    launches = 0;
+    if (rgb) {
+      cudaMemcpy2DAsync(d_rgb, p_rgb, rgb, sizeof(uchar3) * cw, sizeof(uchar3) * cw, ch, cudaMemcpyHostToDevice, s);
+      CUDABuffer_<uchar3> rgb_buf(d_rgb, ch, cw, p_rgb);
+      CUDABuffer_<uchar4> rgba_buf(d_rgba, ch, cw, p_rgba);
+      ComputeBrightnessCUDA(s, rgb_buf, &rgba_buf);                                                       // bad_slam.cc:692
+      ++launches;
+    }
+    BilateralFilteringAndDepthCutoffCUDA(s, sigma_xy, sigma_inv_depth, radius_factor,
+                                         max_depth_m / c->cfg.raw_to_float_depth,                         // float -> u16 (bad_slam.cc:703)
+                                         c->cfg.raw_to_float_depth, raw_buf, &a_buf);                     // bad_slam.cc:698
+    const PixelCenterUnprojector unproj = CenterUnprojector(c->cfg.depth_K);
+    ComputeNormalsCUDA(s, unproj, MakeDepthParams(c), a_buf, &b_buf, &normals_buf);                       // bad_slam.cc:716
+    ComputePointRadiiAndRemoveIsolatedPixelsCUDA(s, unproj, c->cfg.raw_to_float_depth, b_buf, &radius_buf, &a_buf);   // bad_slam.cc:754
+    CUDABuffer_<float> init_buf(d_init, 1, 2, 2 * sizeof(float)), result_buf(d_result, 1, 2, 2 * sizeof(float));
+    ComputeMinMaxDepthCUDA(s, a_buf, c->cfg.raw_to_float_depth, init_buf, &result_buf, min_depth, max_depth);        // bad_slam.cc:978
+    launches += 4;
+    c->launches += launches;
+    cudaMemcpy2DAsync(out_depth, sizeof(u16) * w, d_a, p_a, sizeof(u16) * w, h, cudaMemcpyDeviceToHost, s);
+    cudaMemcpy2DAsync(out_normals, sizeof(u16) * w, d_normals, p_normals, sizeof(u16) * w, h, cudaMemcpyDeviceToHost, s);
+    cudaMemcpy2DAsync(out_radius, sizeof(u16) * w, d_radius, p_radius, sizeof(u16) * w, h, cudaMemcpyDeviceToHost, s);
+    if (rgb) cudaMemcpy2DAsync(out_rgba, sizeof(uchar4) * cw, d_rgba, p_rgba, sizeof(uchar4) * cw, ch, cudaMemcpyDeviceToHost, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) launches = -1;
+  }
+  cudaFree(d_raw); cudaFree(d_a); cudaFree(d_b); cudaFree(d_normals); cudaFree(d_radius); cudaFree(d_rgb); cudaFree(d_rgba);
+  cudaFree(d_init); cudaFree(d_result);
+  return launches;
+}
+
 void ref_set_surfels_size(ref_context* c, unsigned int n) { c->surfels_size = n; }
 
 // Device-side snapshot / restore of the mutable state (surfel data rows, poses, activations) for benchmarking

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/badba.h but not exported"
     # and the python binding types every one of them
     assert set(declared_symbols()) == set(_lib.SYMBOLS.keys())
-    assert _lib.load().bba_abi_version() == 4
+    assert _lib.load().bba_abi_version() == 5
 
 
 def test_no_cpu_fallback_without_a_device():
@@ -83,9 +83,16 @@ def test_cpp_adaptor_header_compiles_and_fails_loudly_without_device(tmp_path):
 #include "badba_direct_ba.hpp"
 struct SE3 { float d[7]; float* data() { return d; } const float* data() const { return d; } };
 struct Cam { int w, h; float p[4]; int width() const { return w; } int height() const { return h; } const float* parameters() const { return p; } };
-int main() {
+int main(int argc, char**) {
   Cam c{64, 48, {30, 30, 32, 24}};
-  try { badba::DirectBA<SE3, Cam> ba(1000, 1e-3f, 40.f, 4, 0.8f, 1, 2, 3, c, c, 0, true, true); }
+  try {
+    badba::DirectBA<SE3, Cam> ba(1000, 1e-3f, 40.f, 4, 0.8f, 1, 2, 3, c, c, 0, true, true);
+    if (argc > 100) {   // never taken: instantiates member templates that need real buffers to run
+      float mn, mx;
+      ba.PreprocessFrame(nullptr, 1.5f, 0.005f, 2.f, 3.f, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, &mn, &mx);
+      ba.CreateSurfelsForKeyframe(nullptr, true, 0);
+    }
+  }
   catch (const badba::Error& e) { return e.status == BBA_ERR_NO_DEVICE ? 42 : 1; }
   return 0;
 }''')
