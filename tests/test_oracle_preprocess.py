@@ -215,3 +215,17 @@ def test_tile_program_on_ragged_and_tiny_images(harness):
         assert got[4] == want[4] and got[5] == want[5], (w, h)
         if min(w, h) < 5:
             assert not valid.any()      # nothing survives a 2-pixel frame
+
+
+def test_tile_program_is_clean_under_address_sanitizer(tmp_path):
+    """Every global / shared-memory index of the tile program, on ragged sizes and filter radii 0 / 3 / 16, with exactly sized
+    buffers under ASan + UBSan."""
+    exe = str(tmp_path / "asan_test")
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-x", "c++",
+           os.path.join(HERE, "harness", "preprocess_host.cpp"), os.path.join(HERE, "harness", "preprocess_asan_main.cpp"), "-o", exe]
+    built = subprocess.run(cmd, capture_output=True, text=True)
+    if built.returncode != 0:
+        pytest.skip("no sanitizer runtime for this g++: " + built.stderr[-200:])
+    run = subprocess.run([exe], capture_output=True, text=True, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
+    assert run.returncode == 0 and "runtime error" not in run.stderr and "AddressSanitizer" not in run.stderr, run.stderr[-2000:]
+    assert "320x240 sigma 8.0: 80 tiles" in run.stdout
