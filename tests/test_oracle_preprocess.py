@@ -229,3 +229,30 @@ def test_tile_program_is_clean_under_address_sanitizer(tmp_path):
     run = subprocess.run([exe], capture_output=True, text=True, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
     assert run.returncode == 0 and "runtime error" not in run.stderr and "AddressSanitizer" not in run.stderr, run.stderr[-2000:]
     assert "320x240 sigma 8.0: 80 tiles" in run.stdout
+
+
+def test_preprocessed_raw_frames_feed_surfel_creation_and_bundle_adjustment(small):
+    """The chain BadSlam::ProcessFrame -> CreateKeyframe -> RunBundleAdjustment takes (bad_slam.cc:640-1010), in the oracle: noisy raw
+    frames -> preprocessing -> keyframes -> CreateSurfelsForKeyframe -> 3 BA iterations improve the relative poses."""
+    import copy
+    sc, orc0 = small
+    K = sc.cfg.num_keyframes
+    outs = [orc0.preprocess_frame(*S.raw_frame(sc, k, noise_raw=1.0), max_depth=6.0) for k in range(K)]
+    sc2 = copy.copy(sc)
+    sc2.depth, sc2.normals, sc2.radius, sc2.color = (np.stack([o[i] for o in outs]) for i in range(4))
+    sc2.min_depth = np.array([o[4] for o in outs], np.float32)
+    sc2.max_depth = np.array([o[5] for o in outs], np.float32)
+    assert np.all(sc2.min_depth > 0) and np.all(sc2.max_depth <= 6.0)
+    sc2.surfels = np.zeros((17, 1 << 17), np.float32)
+    sc2.num_surfels = 0
+    orc = O.Oracle(sc2)
+    created = sum(orc.create_surfels_for_keyframe(k, True) for k in range(K))
+    assert created > 20000 and orc.n == created
+    r = orc.bundle_adjust(True, True, 3, 3)
+    assert r.iterations_done == 3 and r.n_assoc > created
+
+    def rel(P, k):
+        return S.se3_mul(S.se3_inverse(P[0]), P[k])
+    e_init = max(S.pose_error(rel(sc.poses_init, k), rel(sc.poses_true, k))[0] for k in range(1, K))
+    e_ba = max(S.pose_error(rel(orc.poses, k), rel(sc.poses_true, k))[0] for k in range(1, K))
+    assert e_ba < 0.8 * e_init
