@@ -1,0 +1,13 @@
+# First GPU call of the next round: validates what was written after round 1's GPU budget was spent (the fused preprocessing
+# kernel), times it, captures it with ncu, and refreshes the headline numbers.
+#   gpurun --timeout 1500 -- 'bash tools/round2_first_gpu.sh'
+set -x
+mkdir -p gpurun_out
+python -m pytest tests/test_gpu_preprocess.py -m gpu -q --tb=short -s 2>&1 | grep -v "^E   *+" | cut -c1-400 | tail -60 > gpurun_out/gpu_preprocess_tests.log
+python -m pytest tests -m gpu -q --tb=short 2>&1 | grep -v "^E   *+" | cut -c1-300 | tail -15 > gpurun_out/gpu_tests.log
+python tools/preprocess_time.py --size 640x480 > gpurun_out/preprocess_time.log 2>&1
+python tools/preprocess_time.py --size 640x480 --flush >> gpurun_out/preprocess_time.log 2>&1
+python tools/preprocess_time.py --size 1280x720 >> gpurun_out/preprocess_time.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'PreprocessFrameKernel' -c 2 -o gpurun_out/r2_preprocess -f python tools/preprocess_time.py --iters 3 > gpurun_out/ncu_preprocess.log 2>&1
+python bench.py --steps 5 --warmup 3 > gpurun_out/bench_r2_first.json 2> gpurun_out/bench_r2_first.err
+tail -25 gpurun_out/gpu_preprocess_tests.log; tail -3 gpurun_out/gpu_tests.log; cat gpurun_out/preprocess_time.log; tail -c 300 gpurun_out/bench_r2_first.json
