@@ -28,13 +28,17 @@ class Config(C.Structure):
                 ("min_observation_count", C.c_int), ("surfel_merge_dist_factor", C.c_float)]
 
 
+PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int)   # bba_ba_options::progress_function
+
+
 class BAOptions(C.Structure):
     _fields_ = [("optimize_depth_intrinsics", C.c_int), ("optimize_color_intrinsics", C.c_int),
                 ("do_surfel_updates", C.c_int), ("optimize_poses", C.c_int), ("optimize_geometry", C.c_int),
                 ("min_iterations", C.c_int), ("max_iterations", C.c_int), ("use_pcg", C.c_int),
                 ("active_keyframe_window_start", C.c_int), ("active_keyframe_window_end", C.c_int),
                 ("increase_ba_iteration_count", C.c_int), ("time_limit_seconds", C.c_double),
-                ("pcg_max_inner_iterations", C.c_int), ("pcg_max_keyframes", C.c_int), ("pcg_gauge_keyframe", C.c_int)]
+                ("pcg_max_inner_iterations", C.c_int), ("pcg_max_keyframes", C.c_int), ("pcg_gauge_keyframe", C.c_int),
+                ("progress_function", PROGRESS_FN), ("progress_user", C.c_void_p)]
 
 
 class BAResult(C.Structure):

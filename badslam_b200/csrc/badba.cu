@@ -1055,6 +1055,7 @@ bba_status BundleAdjustPCG(bba_handle h, const bba_ba_options* o, bba_ba_result*
   std::vector<int> keyframes_with_new_surfels;
 
   for (int iteration = 0; iteration < o->max_iterations; ++iteration) {
+    if (o->progress_function && !o->progress_function(o->progress_user, iteration)) break;
     ++res->iterations_done;
     // surfel creation (:183-206)
     keyframes_with_new_surfels.clear();
@@ -1839,6 +1840,7 @@ bba_status bba_bundle_adjust(bba_handle h, const bba_ba_options* o, bba_ba_resul
   BBA_CUDA(h, cudaMemsetAsync(h->active, 0, h->surfels_size, s));   // :338
 
   for (int iteration = 0; iteration < o->max_iterations; ++iteration) {
+    if (o->progress_function && !o->progress_function(o->progress_user, iteration)) break;
     ++res->iterations_done;
     if (fixed_window) {   // :354-372
       for (int k = 0; k < K; ++k)

@@ -409,9 +409,10 @@ class DirectBA:
                          active_keyframe_window_start: int = 0, active_keyframe_window_end: int = -1,
                          increase_ba_iteration_count: bool = True, time_limit: float = 0.0,
                          pcg_max_inner_iterations: int = 30, pcg_max_keyframes: int = 2500,
-                         pcg_gauge_keyframe: int = -1) -> BAResult:
+                         pcg_gauge_keyframe: int = -1, progress_function=None) -> BAResult:
         """direct_ba.h:143-162.  pcg_gauge_keyframe >= 0 pins the keyframe the PCG solver holds fixed (the reference draws
-        rand() % K in every iteration, direct_ba_pcg.cc:324)."""
+        rand() % K in every iteration, direct_ba_pcg.cc:324).  progress_function(iteration) -> bool is called at the top of
+        every iteration; False stops the optimisation (direct_ba_alternating.cc:346-348)."""
         if active_keyframe_window_end < 0:
             active_keyframe_window_end = len(self._keyframes) - 1
         o = _lib.BAOptions(int(optimize_depth_intrinsics), int(optimize_color_intrinsics), int(do_surfel_updates),
@@ -419,6 +420,9 @@ class DirectBA:
                            int(use_pcg), int(active_keyframe_window_start), int(active_keyframe_window_end),
                            int(increase_ba_iteration_count), float(time_limit), int(pcg_max_inner_iterations),
                            int(pcg_max_keyframes), int(pcg_gauge_keyframe))
+        if progress_function is not None:
+            cb = _lib.PROGRESS_FN(lambda _user, iteration: 1 if progress_function(int(iteration)) else 0)
+            o.progress_function = cb   # `cb` stays referenced until the call returns
         r = _lib.BAResult()
         self._check(self._lib.bba_bundle_adjust(self._h, C.byref(o), C.byref(r), self._stream_ptr(stream)))
         return BAResult(r.iterations_done, bool(r.converged), r.depth_residual_count, r.descriptor_residual_count,

@@ -88,6 +88,11 @@ typedef struct {
   int pcg_max_keyframes;          /* <= 0: 2500; keyframe_count must not exceed it */
   int pcg_gauge_keyframe;         /* keyframe whose pose is held fixed in every iteration; < 0: rand() % keyframe_count per
                                      iteration as the reference does (direct_ba_pcg.cc:324) */
+  /* progress_function of direct_ba.h:160-162: called at the top of every iteration with the iteration index; returning 0
+   * stops the optimisation before that iteration runs (direct_ba_alternating.cc:346-348, direct_ba_pcg.cc:174-176).
+   * NULL = none.  With world_size > 1 it must return the same value on every rank. */
+  int (*progress_function)(void* user, int iteration);
+  void* progress_user;
 } bba_ba_options;
 
 typedef struct {

@@ -113,7 +113,7 @@ class DirectBA {
                         int active_keyframe_window_start, int active_keyframe_window_end, bool increase_ba_iteration_count,
                         int* iterations_done = nullptr, bool* converged = nullptr, double time_limit = 0, void* /*timer*/ = nullptr,
                         int pcg_max_inner_iterations = 30, int pcg_max_keyframes = 2500,
-                        std::function<bool(int)> /*progress_function*/ = nullptr) {
+                        std::function<bool(int)> progress_function = nullptr) {
     bba_ba_options o{};
     o.optimize_depth_intrinsics = optimize_depth_intrinsics;
     o.optimize_color_intrinsics = optimize_color_intrinsics;
@@ -130,6 +130,10 @@ class DirectBA {
     o.pcg_max_inner_iterations = pcg_max_inner_iterations;
     o.pcg_max_keyframes = pcg_max_keyframes;
     o.pcg_gauge_keyframe = pcg_gauge_keyframe_;   // -1: rand() % K per iteration like direct_ba_pcg.cc:324
+    if (progress_function) {
+      o.progress_function = [](void* user, int iteration) -> int { return (*static_cast<std::function<bool(int)>*>(user))(iteration) ? 1 : 0; };
+      o.progress_user = &progress_function;
+    }
     bba_ba_result r{};
     Check(bba_bundle_adjust(h_, &o, &r, stream), "bba_bundle_adjust");
     if (iterations_done) *iterations_done = r.iterations_done;

@@ -469,3 +469,17 @@ def test_intrinsics_and_pcg_against_golden_fixture(mods):
             d, c, a = ba._intrinsics()
             assert np.abs(d - g["pcgi_ba_depth_K"]).max() < 2e-3 and np.abs(c - g["pcgi_ba_color_K"]).max() < 2e-3
             assert abs(a - float(g["pcgi_ba_a"])) < 5e-4
+
+
+def test_progress_function_stops_the_iterations(mods, tiny_scene):
+    """direct_ba_alternating.cc:346-348 / direct_ba_pcg.cc:174-176: progress_function(iteration) is asked before every iteration;
+    false ends the optimisation there."""
+    S, DirectBA, O, R = mods
+    for use_pcg in (False, True):
+        ba = DirectBA.from_scene(tiny_scene)
+        seen = []
+        r = ba.BundleAdjustment(None, False, False, False, True, True, 5, 5, use_pcg=use_pcg, pcg_gauge_keyframe=0,
+                                progress_function=lambda it: (seen.append(it), it < 2)[1])
+        assert seen == [0, 1, 2] and r.iterations_done == 2
+        r = ba.BundleAdjustment(None, False, False, False, True, True, 2, 2, use_pcg=use_pcg, pcg_gauge_keyframe=0)
+        assert r.iterations_done == 2
