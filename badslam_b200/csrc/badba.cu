@@ -1609,6 +1609,20 @@ bba_status bba_set_intrinsics(bba_handle h, const float d[4], const float c[4], 
   h->depth_a = a;
   return BBA_OK;
 }
+bba_status bba_set_residual_types(bba_handle h, int use_depth_residuals, int use_descriptor_residuals) {
+  if (!h) return BBA_ERR_INVALID_ARGUMENT;
+  if (!use_depth_residuals && !use_descriptor_residuals)
+    return Fail(h, BBA_ERR_INVALID_ARGUMENT, "bba_set_residual_types: at least one residual type must stay enabled");
+  h->cfg.use_depth_residuals = use_depth_residuals != 0;
+  h->cfg.use_descriptor_residuals = use_descriptor_residuals != 0;
+  return BBA_OK;
+}
+bba_status bba_get_residual_types(bba_handle h, int* use_depth_residuals, int* use_descriptor_residuals) {
+  if (!h) return BBA_ERR_INVALID_ARGUMENT;
+  if (use_depth_residuals) *use_depth_residuals = h->cfg.use_depth_residuals;
+  if (use_descriptor_residuals) *use_descriptor_residuals = h->cfg.use_descriptor_residuals;
+  return BBA_OK;
+}
 bba_status bba_get_intrinsics(bba_handle h, float d[4], float c[4], float* a) {
   if (!h) return BBA_ERR_INVALID_ARGUMENT;
   if (d) std::memcpy(d, h->depth_K, sizeof(h->depth_K));

@@ -317,6 +317,23 @@ class DirectBA:
         _, c, a = self._intrinsics()
         self._set_intrinsics(camera.parameters, c, a)
 
+    # direct_ba.h:317-328
+    def use_depth_residuals(self) -> bool:
+        d, c = C.c_int(), C.c_int()
+        self._check(self._lib.bba_get_residual_types(self._h, C.byref(d), C.byref(c)))
+        return bool(d.value)
+
+    def use_descriptor_residuals(self) -> bool:
+        d, c = C.c_int(), C.c_int()
+        self._check(self._lib.bba_get_residual_types(self._h, C.byref(d), C.byref(c)))
+        return bool(c.value)
+
+    def SetUseDepthResiduals(self, use_depth_residuals: bool):
+        self._check(self._lib.bba_set_residual_types(self._h, int(use_depth_residuals), int(self.use_descriptor_residuals())))
+
+    def SetUseDescriptorResiduals(self, use_descriptor_residuals: bool):
+        self._check(self._lib.bba_set_residual_types(self._h, int(self.use_depth_residuals()), int(use_descriptor_residuals)))
+
     def SetA(self, a: float):
         d, c, _ = self._intrinsics()
         self._set_intrinsics(d, c, a)

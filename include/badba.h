@@ -186,6 +186,10 @@ bba_status bba_get_covisibility(bba_handle h, int keyframe_id, uint8_t* out_row 
 /* depth_params_ / cameras (direct_ba.h:243-297; SetColorCamera etc.) */
 bba_status bba_set_intrinsics(bba_handle h, const float depth_intrinsics[4], const float color_intrinsics[4], float depth_a);
 bba_status bba_get_intrinsics(bba_handle h, float depth_intrinsics[4], float color_intrinsics[4], float* depth_a);
+/* DirectBA::SetUseDepthResiduals / SetUseDescriptorResiduals (direct_ba.h:317-328; main.cc:853 switches the descriptor
+ * residuals off for the final BA): takes effect from the next call.  At least one type must stay enabled. */
+bba_status bba_set_residual_types(bba_handle h, int use_depth_residuals, int use_descriptor_residuals);
+bba_status bba_get_residual_types(bba_handle h, int* use_depth_residuals, int* use_descriptor_residuals);
 bba_status bba_set_cfactor_host(bba_handle h, const float* host_cfactor /* dense [cf_h][cf_w] */, void* stream);
 bba_status bba_get_cfactor_host(bba_handle h, float* host_cfactor, void* stream);
 bba_status bba_cfactor_size(bba_handle h, int* cf_width, int* cf_height);

@@ -180,6 +180,12 @@ class DirectBA {
   uint32_t surfels_size() const { return bba_surfels_size(h_); }   // direct_ba.h:265
   void GetIntrinsics(float depth[4], float color[4], float* a) const { Check(bba_get_intrinsics(h_, depth, color, a), "bba_get_intrinsics"); }
   void SetPCGGaugeKeyframe(int keyframe_id) { pcg_gauge_keyframe_ = keyframe_id; }
+
+  // direct_ba.h:317-328
+  bool use_depth_residuals() const { int d = 0, c = 0; bba_get_residual_types(h_, &d, &c); return d != 0; }
+  bool use_descriptor_residuals() const { int d = 0, c = 0; bba_get_residual_types(h_, &d, &c); return c != 0; }
+  void SetUseDepthResiduals(bool v) { Check(bba_set_residual_types(h_, v, use_descriptor_residuals()), "bba_set_residual_types"); }
+  void SetUseDescriptorResiduals(bool v) { Check(bba_set_residual_types(h_, use_depth_residuals(), v), "bba_set_residual_types"); }
   const bba_ba_result& last_result() const { return last_result_; }
   bba_handle handle() const { return h_; }
 

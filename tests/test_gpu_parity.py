@@ -483,3 +483,26 @@ def test_progress_function_stops_the_iterations(mods, tiny_scene):
         assert seen == [0, 1, 2] and r.iterations_done == 2
         r = ba.BundleAdjustment(None, False, False, False, True, True, 2, 2, use_pcg=use_pcg, pcg_gauge_keyframe=0)
         assert r.iterations_done == 2
+
+
+def test_residual_types_can_be_switched_at_runtime(mods, tiny_scene):
+    """DirectBA::SetUseDepthResiduals / SetUseDescriptorResiduals (direct_ba.h:317-328; main.cc:853 turns the descriptor residuals
+    off for the final BA): the same numbers as a backend created with those flags."""
+    S, DirectBA, O, R = mods
+    sc = tiny_scene
+    ba = DirectBA.from_scene(sc)
+    assert ba.use_depth_residuals() and ba.use_descriptor_residuals()
+    for use_depth, use_desc in ((True, False), (False, True), (True, True)):
+        ba.SetUseDepthResiduals(True)          # keep one type enabled while switching the other
+        ba.SetUseDescriptorResiduals(use_desc)
+        ba.SetUseDepthResiduals(use_depth)
+        assert (ba.use_depth_residuals(), ba.use_descriptor_residuals()) == (use_depth, use_desc)
+        fixed = DirectBA.from_scene(sc, use_depth_residuals=use_depth, use_descriptor_residuals=use_desc)
+        for k in range(sc.cfg.num_keyframes):
+            p, q = ba.AccumulatePoseEstimationCoeffs(k, sc.poses_init[k]), fixed.AccumulatePoseEstimationCoeffs(k, sc.poses_init[k])
+            assert (p.n_assoc, p.n_photo) == (q.n_assoc, q.n_photo)
+            assert rel(p.H[:], q.H[:]) < 1e-6 and rel(p.b[:], q.b[:]) < 1e-6
+    from badslam_b200._lib import BadBAError
+    ba.SetUseDescriptorResiduals(False)
+    with pytest.raises(BadBAError):
+        ba.SetUseDepthResiduals(False)
