@@ -98,7 +98,9 @@ BBA_PRE_HD uint16_t FloatToHalfBits(float f) {
 #endif
 }
 
-BBA_PRE_HD uint16_t TruncToU16(float f) {   // static_cast<u16>(float) on the device: cvt.rzi.u16.f32 (saturating, NaN -> 0)
+// static_cast<u16>(float) as nvcc compiles it (F2I.U32.TRUNC, low 16 bits stored).  The filtered depth is a weighted mean of
+// u16 samples, so it never reaches 65536; the host build only has to agree below that.
+BBA_PRE_HD uint16_t TruncToU16(float f) {
 #if defined(__CUDA_ARCH__)
   return static_cast<uint16_t>(f);
 #else

@@ -21,7 +21,7 @@
 #define ORC_UNKNOWN_DEPTH 65535u   /* kernels.cuh:41 */
 #define ORC_INVALID_BIT 0x8000u    /* kernels.cuh:38 */
 
-static uint16_t trunc_u16(float f) {   /* cvt.rzi.u16.f32: saturating, NaN -> 0 */
+static uint16_t trunc_u16(float f) {   /* float -> u16 of the reference's build: truncation (the values here stay below 65536) */
   if (!(f > 0.f)) return 0;
   if (f >= 65535.f) return 65535;
   return (uint16_t)f;
