@@ -1,0 +1,96 @@
+"""Runs one BASELINE.json configuration at FULL size on the GPU(s) and checks size-independent properties.
+
+    python tools/run_config.py --workload cfg4            # 500 keyframes / 4 M surfels, intrinsics + depth deformation on
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \
+        tools/run_config.py --workload cfg5               # 1280x720, 400 keyframes / 8 M surfels on 8 GPUs
+
+bench.py times cfg3 (the configuration the metric is quoted on); cfg4 and cfg5 are parity-test cases, too large for the oracle or
+the reference arm to finish in test time, so this script checks what does not depend on size: identical association counts when
+a pass is repeated, a symmetric positive semi-definite H, unit quaternions, a robust cost that decreases over the iterations,
+pose errors below the start, the depth-deformation parameter `a` moving towards the value the scene was rendered with (cfg4),
+and -- with more than one rank -- poses / surfels identical on every rank.  Prints one JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from badslam_b200 import scene as S
+    from badslam_b200.direct_ba import DirectBA
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="cfg4")
+    ap.add_argument("--iterations", type=int, default=5)
+    a = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=dev)
+    t0 = time.time()
+    sc = S.make_scene(S.config_by_name(a.workload))
+    t_scene = time.time() - t0
+    K = sc.cfg.num_keyframes
+    intr = a.workload == "cfg4"
+    ba = DirectBA.from_scene(sc, device=dev, rank=rank, world_size=world)
+    if world > 1:
+        ba.SetCollective()
+        ba.EnablePeerExchange()
+    out = {"workload": a.workload, "n_gpus": world, "keyframes": K, "surfels": sc.num_surfels,
+           "image": [sc.cfg.width, sc.cfg.height], "scene_seconds": round(t_scene, 1), "checks": {}}
+    chk = out["checks"]
+    if world == 1:
+        for k in (0, K // 2, K - 1):
+            p = ba.AccumulatePoseEstimationCoeffs(k, sc.poses_init[k])
+            q = ba.AccumulatePoseEstimationCoeffs(k, sc.poses_init[k])
+            chk[f"counts_repeat_kf{k}"] = (p.n_inimg, p.n_depthok, p.n_assoc, p.n_photo) == (q.n_inimg, q.n_depthok, q.n_assoc, q.n_photo)
+            H = np.zeros((6, 6))
+            H[np.triu_indices(6)] = p.H[:]
+            H = H + H.T - np.diag(H.diagonal())
+            chk[f"H_psd_kf{k}"] = bool(np.linalg.eigvalsh(H).min() > -1e-3 * np.abs(H).max())
+    costs, ms = [], []
+    for it in range(a.iterations):
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        r = ba.BundleAdjustment(None, intr, intr, False, True, True, 1, 1, increase_ba_iteration_count=False)
+        torch.cuda.synchronize()
+        ms.append(1e3 * (time.perf_counter() - t))
+        costs.append(r.cost)
+    poses, _ = ba.GetKeyframeStates()
+    chk["unit_quaternions"] = bool(np.allclose(np.linalg.norm(poses[:, :4], axis=1), 1.0, atol=1e-5))
+    chk["cost_decreases"] = bool(costs[-1] < costs[0])
+    e0 = np.mean([S.pose_error(sc.poses_init[k], sc.poses_true[k])[0] for k in range(K)])
+    e1 = np.mean([S.pose_error(poses[k], sc.poses_true[k])[0] for k in range(K)])
+    chk["pose_error_decreases"] = bool(e1 < e0)
+    out.update(cost=costs, ms_per_iteration=[round(v, 2) for v in ms], mean_pose_error_m=[float(e0), float(e1)],
+               residuals_last=int(r.depth_residual_count + r.descriptor_residual_count))
+    if intr:
+        out["depth_a"] = [0.0, float(ba.a()), float(sc.cfg.depth_a)]      # start, now, value the scene was rendered with
+        chk["a_moves_towards_truth"] = bool(abs(ba.a() - sc.cfg.depth_a) < abs(0.0 - sc.cfg.depth_a))
+    surf = ba.surfels()[:8, :ba.surfels_size()]
+    chk["surfels_finite"] = bool(torch.isfinite(surf[[0, 1, 2, 4, 6, 7]]).all().item())
+    if world > 1:
+        mine = torch.cat([torch.from_numpy(poses).to(dev).flatten().double(), surf[:3].double().sum(dim=1)])
+        lo, hi = mine.clone(), mine.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        chk["replicas_identical"] = bool(torch.equal(lo, hi))
+    out["ok"] = all(chk.values())
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier(device_ids=[dev.index])
+        dist.destroy_process_group()
+    return 0 if out["ok"] else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
