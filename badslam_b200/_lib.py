@@ -115,6 +115,8 @@ SYMBOLS = {
     "bba_cfactor_size": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "bba_accumulate_pose_coeffs": (C.c_int, [_P, C.c_int, _F7, C.POINTER(PoseCoeffs), _P]),
     "bba_estimate_frame_pose": (C.c_int, [_P, C.c_int, _F7, _F7, C.POINTER(C.c_int), C.POINTER(C.c_int), _P]),
+    "bba_estimate_frame_pose_for_frame": (C.c_int, [_P, _P, C.c_size_t, _P, C.c_size_t, _P, C.c_size_t, _F7, _F7,
+                                                    C.POINTER(C.c_int), C.POINTER(C.c_int), _P]),
     "bba_update_surfel_activation": (C.c_int, [_P, _P]),
     "bba_optimize_geometry_iteration": (C.c_int, [_P, _P]),
     "bba_optimize_intrinsics": (C.c_int, [_P, C.c_int, C.c_int, _P]),

@@ -237,6 +237,10 @@ struct bba_context {
   unsigned int* d_compact_sums = nullptr;
   uint32_t compact_sums_capacity = 0;
 
+  // frame-to-model tracking of a frame that is not a keyframe (bba_estimate_frame_pose_for_frame): luma array + texture
+  cudaArray_t scratch_luma = nullptr;
+  cudaTextureObject_t scratch_tex = 0;
+
   // keyframe preprocessing (bba_preprocess_frame), lazily allocated
   float* d_min_max = nullptr;
   float* h_min_max = nullptr;                // pinned
@@ -1220,32 +1224,43 @@ bba_status BundleAdjustPCG(bba_handle h, const bba_ba_options* o, bba_ba_result*
   return BBA_OK;
 }
 
-bba_status AddKeyframeCommon(bba_handle h, Keyframe&& kf, const uint8_t* device_rgba, size_t color_pitch, const float pose[7],
-                             float min_depth, float max_depth, cudaStream_t s, int* out_id) {
-  if (static_cast<int>(h->keyframes.size()) >= h->cfg.max_keyframes) return Fail(h, BBA_ERR_STATE, "max_keyframes exceeded");
+// The luma plane (the .w channel of a uchar4 image) as a gather-enabled CUDA array (block-linear: 2-D locality for the sample
+// footprints) + a texture with the reference's sampling state (keyframe.cc:67-73).  *array / *tex are created when null and
+// refilled otherwise.
+bba_status MakeLumaTexture(bba_handle h, const uint8_t* device_rgba, size_t color_pitch, cudaArray_t* array, cudaTextureObject_t* tex_out,
+                           cudaStream_t s) {
   const int cw = h->cfg.color_width, ch = h->cfg.color_height;
   if (!h->luma_staging)
     BBA_CUDA(h, cudaMallocPitch(reinterpret_cast<void**>(&h->luma_staging), &h->luma_staging_pitch, cw, ch));
-  // luma plane (the .w channel) -> gather-enabled CUDA array (block-linear: 2-D locality for the sample footprints)
-  const cudaChannelFormatDesc desc = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
-  BBA_CUDA(h, cudaMallocArray(&kf.luma, &desc, cw, ch, cudaArrayTextureGather));
+  if (!*array) {
+    const cudaChannelFormatDesc desc = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
+    BBA_CUDA(h, cudaMallocArray(array, &desc, cw, ch, cudaArrayTextureGather));
+  }
   bba::LaunchExtractLuma(device_rgba, color_pitch, h->luma_staging, h->luma_staging_pitch, cw, ch, s);
   ++h->launches;
   BBA_CUDA(h, cudaGetLastError());
-  BBA_CUDA(h, cudaMemcpy2DToArrayAsync(kf.luma, 0, 0, h->luma_staging, h->luma_staging_pitch, cw, ch, cudaMemcpyDeviceToDevice, s));
-  // Texture with the reference's sampling state (keyframe.cc:67-73) over the single luma channel.
-  cudaResourceDesc res;
-  std::memset(&res, 0, sizeof(res));
-  res.resType = cudaResourceTypeArray;
-  res.res.array.array = kf.luma;
-  cudaTextureDesc tex;
-  std::memset(&tex, 0, sizeof(tex));
-  tex.addressMode[0] = cudaAddressModeClamp;
-  tex.addressMode[1] = cudaAddressModeClamp;
-  tex.filterMode = cudaFilterModeLinear;
-  tex.readMode = cudaReadModeNormalizedFloat;
-  tex.normalizedCoords = 0;
-  BBA_CUDA(h, cudaCreateTextureObject(&kf.tex, &res, &tex, nullptr));
+  BBA_CUDA(h, cudaMemcpy2DToArrayAsync(*array, 0, 0, h->luma_staging, h->luma_staging_pitch, cw, ch, cudaMemcpyDeviceToDevice, s));
+  if (!*tex_out) {
+    cudaResourceDesc res;
+    std::memset(&res, 0, sizeof(res));
+    res.resType = cudaResourceTypeArray;
+    res.res.array.array = *array;
+    cudaTextureDesc tex;
+    std::memset(&tex, 0, sizeof(tex));
+    tex.addressMode[0] = cudaAddressModeClamp;
+    tex.addressMode[1] = cudaAddressModeClamp;
+    tex.filterMode = cudaFilterModeLinear;
+    tex.readMode = cudaReadModeNormalizedFloat;
+    tex.normalizedCoords = 0;
+    BBA_CUDA(h, cudaCreateTextureObject(tex_out, &res, &tex, nullptr));
+  }
+  return BBA_OK;
+}
+
+bba_status AddKeyframeCommon(bba_handle h, Keyframe&& kf, const uint8_t* device_rgba, size_t color_pitch, const float pose[7],
+                             float min_depth, float max_depth, cudaStream_t s, int* out_id) {
+  if (static_cast<int>(h->keyframes.size()) >= h->cfg.max_keyframes) return Fail(h, BBA_ERR_STATE, "max_keyframes exceeded");
+  if (bba_status st = MakeLumaTexture(h, device_rgba, color_pitch, &kf.luma, &kf.tex, s)) return st;
   kf.pose = PoseFromArray(pose);
   kf.activation = BBA_KF_ACTIVE;   // keyframe.cc:75
   kf.min_depth = min_depth;
@@ -1414,6 +1429,8 @@ void bba_destroy(bba_handle h) {
   cudaFree(h->d_compact_sums);
   cudaFree(h->d_min_max);
   cudaFreeHost(h->h_min_max);
+  if (h->scratch_tex) cudaDestroyTextureObject(h->scratch_tex);
+  if (h->scratch_luma) cudaFreeArray(h->scratch_luma);
   for (float* v : h->d_pcg) cudaFree(v);
   cudaFree(h->d_pcg_scalars);
   cudaFreeHost(h->h_pcg_scalars);
@@ -1715,6 +1732,41 @@ bba_status bba_estimate_frame_pose(bba_handle h, int id, const float init[7], fl
   std::vector<int> ids(1, id);
   std::vector<Pose> poses(1, PoseFromArray(init));
   if (bba_status st = RunPoseStep(h, ids, poses, 30, static_cast<cudaStream_t>(stream))) return st;
+  std::memcpy(out, h->h_pose_est + 7 * id, sizeof(float) * 7);
+  if (iterations) *iterations = h->h_iterations[id];
+  if (converged) *converged = h->h_converged[id];
+  return BBA_OK;
+}
+
+bba_status bba_estimate_frame_pose_for_frame(bba_handle h, const uint16_t* device_depth, size_t depth_pitch,
+                                             const uint16_t* device_normals, size_t normals_pitch,
+                                             const uint8_t* device_color_rgba, size_t color_pitch, const float init[7], float out[7],
+                                             int* iterations, int* converged, void* stream) {
+  if (!h || !device_depth || !device_normals || !device_color_rgba || !init || !out) return BBA_ERR_INVALID_ARGUMENT;
+  if (depth_pitch < static_cast<size_t>(h->cfg.depth_width) * 2 || normals_pitch < static_cast<size_t>(h->cfg.depth_width) * 2 ||
+      color_pitch < static_cast<size_t>(h->cfg.color_width) * 4 || depth_pitch > 0xffffffffull || normals_pitch > 0xffffffffull)
+    return Fail(h, BBA_ERR_INVALID_ARGUMENT, "frame buffer pitch too small");
+  if (bba_status st = CheckSurfels(h)) return st;
+  const int id = static_cast<int>(h->keyframes.size());
+  if (id >= h->cfg.max_keyframes)
+    return Fail(h, BBA_ERR_STATE, "bba_estimate_frame_pose_for_frame needs one free keyframe slot (max_keyframes reached)");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (bba_status st = MakeLumaTexture(h, device_color_rgba, color_pitch, &h->scratch_luma, &h->scratch_tex, s)) return st;
+  // The frame rides through the pose step as a temporary entry behind the keyframes: it takes part in nothing else
+  // (no co-visibility, no activation state) and is removed again before the call returns.
+  Keyframe frame{};
+  frame.depth = device_depth; frame.depth_pitch = depth_pitch;
+  frame.normals = device_normals; frame.normals_pitch = normals_pitch;
+  frame.tex = h->scratch_tex;
+  frame.pose = PoseFromArray(init);
+  frame.activation = BBA_KF_ACTIVE;
+  h->keyframes.push_back(frame);
+  std::vector<int> ids(1, id);
+  std::vector<Pose> poses(1, PoseFromArray(init));
+  const bba_status st = RunPoseStep(h, ids, poses, 30, s);
+  h->keyframes.pop_back();
+  if (id < static_cast<int>(h->kf_cost.size())) h->kf_cost[id] = 0.f;   // the slot's cost statistics belong to a future keyframe
+  if (st) return st;
   std::memcpy(out, h->h_pose_est + 7 * id, sizeof(float) * 7);
   if (iterations) *iterations = h->h_iterations[id];
   if (converged) *converged = h->h_converged[id];

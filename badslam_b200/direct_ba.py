@@ -410,6 +410,20 @@ class DirectBA:
                                                       self._stream_ptr(stream)))
         return out, it.value, bool(conv.value)
 
+    def EstimateFramePoseFromBuffers(self, stream, global_T_frame_initial_estimate, depth_buffer: torch.Tensor,
+                                     normals_buffer: torch.Tensor, color_buffer: torch.Tensor):
+        """The buffer-taking form of DirectBA::EstimateFramePose (direct_ba.h:122-129) for a frame that is not a keyframe:
+        depth / normals [h, w] u16 and colour [ch, cw, 4] u8 (.w = luma) device tensors.  Returns
+        (global_T_frame_estimate, iterations, converged)."""
+        p = np.ascontiguousarray(global_T_frame_initial_estimate, np.float32)
+        out = np.zeros(7, np.float32)
+        it, conv = C.c_int(), C.c_int()
+        self._check(self._lib.bba_estimate_frame_pose_for_frame(
+            self._h, depth_buffer.data_ptr(), depth_buffer.stride(0) * 2, normals_buffer.data_ptr(), normals_buffer.stride(0) * 2,
+            color_buffer.data_ptr(), color_buffer.stride(0), p.ctypes.data_as(C.POINTER(C.c_float)),
+            out.ctypes.data_as(C.POINTER(C.c_float)), C.byref(it), C.byref(conv), self._stream_ptr(stream)))
+        return out, it.value, bool(conv.value)
+
     def UpdateSurfelActivation(self, stream=None):
         self._check(self._lib.bba_update_surfel_activation(self._h, self._stream_ptr(stream)))
 

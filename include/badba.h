@@ -203,6 +203,15 @@ bba_status bba_accumulate_pose_coeffs(bba_handle h, int keyframe_id, const float
  * images.  iterations/converged may be NULL. */
 bba_status bba_estimate_frame_pose(bba_handle h, int keyframe_id, const float global_T_frame_initial[7],
                                    float global_T_frame_out[7], int* iterations, int* converged, void* stream);
+/* The same for a frame that is NOT a keyframe -- the buffer-taking signature of DirectBA::EstimateFramePose
+ * (direct_ba.h:122-129: depth_buffer, normals_buffer, color_texture): frame-to-model tracking against the current surfels.
+ * The colour image is the uchar4 buffer (.w = luma) the reference builds its texture from.  Needs one free keyframe slot
+ * (keyframe_count < max_keyframes); nothing about the frame is kept after the call. */
+bba_status bba_estimate_frame_pose_for_frame(bba_handle h, const uint16_t* device_depth, size_t depth_pitch,
+                                             const uint16_t* device_normals, size_t normals_pitch,
+                                             const uint8_t* device_color_rgba, size_t color_pitch,
+                                             const float global_T_frame_initial[7], float global_T_frame_estimate[7],
+                                             int* iterations, int* converged, void* stream);
 /* UpdateSurfelActivationCUDA (kernels.h:262-269, kernel_surfel_activation.cc:39-67) */
 bba_status bba_update_surfel_activation(bba_handle h, void* stream);
 /* OptimizeGeometryIterationCUDA (kernels.h:234-244, kernel_opt_geometry.cc:80-201) */

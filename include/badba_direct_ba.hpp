@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstring>
 #include <functional>
 #include <stdexcept>
 #include <string>
@@ -105,6 +106,19 @@ class DirectBA {
     Check(bba_estimate_frame_pose(h_, keyframe_id, global_T_frame_initial_estimate.data(), out, nullptr, nullptr, stream),
           "bba_estimate_frame_pose");
     for (int i = 0; i < 7; ++i) out_global_T_frame_estimate->data()[i] = out[i];
+  }
+
+  // direct_ba.h:122-129 for a frame that is not a keyframe (depth_buffer, normals_buffer, colour image in place of the
+  // texture): frame-to-model tracking against the current surfels.
+  void EstimateFramePose(cudaStream_t stream, const SE3f& global_T_frame_initial_estimate, DeviceImage<uint16_t> depth_buffer,
+                         DeviceImage<uint16_t> normals_buffer, DeviceImage<uint8_t> color_buffer_rgba,
+                         SE3f* out_global_T_frame_estimate, bool /*called_within_ba*/ = false) {
+    float out[7];
+    Check(bba_estimate_frame_pose_for_frame(h_, depth_buffer.address, depth_buffer.pitch_bytes, normals_buffer.address,
+                                            normals_buffer.pitch_bytes, color_buffer_rgba.address, color_buffer_rgba.pitch_bytes,
+                                            global_T_frame_initial_estimate.data(), out, nullptr, nullptr, stream),
+          "bba_estimate_frame_pose_for_frame");
+    std::memcpy(out_global_T_frame_estimate->data(), out, sizeof(out));
   }
 
   // direct_ba.h:143-162, same argument order and defaults.

@@ -91,6 +91,8 @@ int main(int argc, char**) {
       float mn, mx;
       ba.PreprocessFrame(nullptr, 1.5f, 0.005f, 2.f, 3.f, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, &mn, &mx);
       ba.CreateSurfelsForKeyframe(nullptr, true, 0);
+      SE3 pose{};
+      ba.EstimateFramePose(nullptr, pose, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, &pose);
       int done; bool conv;
       ba.BundleAdjustment(nullptr, false, false, true, true, true, 1, 10, false, 0, 0, true, &done, &conv, 0, nullptr, 30, 2500,
                           [](int it) { return it < 3; });

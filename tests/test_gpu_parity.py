@@ -506,3 +506,31 @@ def test_residual_types_can_be_switched_at_runtime(mods, tiny_scene):
     ba.SetUseDescriptorResiduals(False)
     with pytest.raises(BadBAError):
         ba.SetUseDepthResiduals(False)
+
+
+def test_estimate_frame_pose_from_buffers_equals_the_keyframe_form(mods, small_scene):
+    """DirectBA::EstimateFramePose takes a frame's buffers (direct_ba.h:122-129); a frame that is not a keyframe must be
+    tracked exactly like the same images stored as a keyframe, and must leave no trace in the backend."""
+    import torch
+    S, DirectBA, O, R = mods
+    sc = small_scene
+    K = sc.cfg.num_keyframes
+    ba = DirectBA.from_scene(sc, max_keyframes=K + 1)
+    k = 2
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int16)).cuda()
+    depth, normals = up(sc.depth[k]), up(sc.normals[k])
+    color = torch.from_numpy(np.ascontiguousarray(sc.color[k])).cuda()
+    want, it_w, conv_w = ba.EstimateFramePose(None, sc.poses_init[k], k)
+    got, it_g, conv_g = ba.EstimateFramePoseFromBuffers(None, sc.poses_init[k], depth, normals, color)
+    assert (it_g, conv_g) == (it_w, conv_w)
+    assert np.max(np.abs(got - want)) < 1e-6
+    assert ba._lib.bba_keyframe_count(ba._h) == K
+    # the backend is unchanged: the keyframe form gives the same answer again, BA still runs
+    again, _, _ = ba.EstimateFramePose(None, sc.poses_init[k], k)
+    assert np.max(np.abs(again - want)) < 1e-6
+    assert ba.BundleAdjustment(None, False, False, False, True, True, 1, 1).iterations_done == 1
+    # no free keyframe slot: a loud error, not a silent reallocation
+    full = DirectBA.from_scene(sc, max_keyframes=K)
+    from badslam_b200._lib import BadBAError
+    with pytest.raises(BadBAError):
+        full.EstimateFramePoseFromBuffers(None, sc.poses_init[k], depth, normals, color)
