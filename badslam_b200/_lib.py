@@ -108,6 +108,13 @@ SYMBOLS = {
     "bba_get_covisibility": (C.c_int, [_P, C.c_int, _P]),
     "bba_set_intrinsics": (C.c_int, [_P, _F7, _F7, C.c_float]),
     "bba_get_intrinsics": (C.c_int, [_P, _F7, _F7, C.POINTER(C.c_float)]),
+    "bba_host_se3_exp": (None, [_P, _P]),
+    "bba_host_se3_log": (None, [_P, _P]),
+    "bba_host_se3_compose": (None, [_P, _P, _P]),
+    "bba_host_se3_inverse": (None, [_P, _P]),
+    "bba_host_pose_update_converged": (C.c_int, [_P]),
+    "bba_host_solve_ldlt": (C.c_int, [C.c_int, _P, _P, _P]),
+    "bba_host_frusta_intersect": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_float, C.c_float, _P, C.c_float, C.c_float]),
     "bba_set_residual_types": (C.c_int, [_P, C.c_int, C.c_int]),
     "bba_get_residual_types": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "bba_set_cfactor_host": (C.c_int, [_P, _P, _P]),

@@ -1566,6 +1566,28 @@ bba_status bba_add_keyframe_host(bba_handle h, const uint16_t* host_depth, const
   return AddKeyframeCommon(h, std::move(kf), tmp, tmp_pitch, global_T_frame, min_depth, max_depth, s, out_keyframe_id);
 }
 
+// ---- host-side building blocks, callable without a device (the CPU test-suite checks them against the oracle) ----
+void bba_host_se3_exp(const float a[6], float out[7]) { PoseToArray(bba::Exp(a), out); }
+void bba_host_se3_log(const float T[7], float out[6]) { bba::Log(PoseFromArray(T), out); }
+void bba_host_se3_compose(const float A[7], const float B[7], float out[7]) { PoseToArray(bba::Compose(PoseFromArray(A), PoseFromArray(B)), out); }
+void bba_host_se3_inverse(const float A[7], float out[7]) { PoseToArray(bba::Inverse(PoseFromArray(A)), out); }
+int bba_host_pose_update_converged(const float x[6]) { return bba::IsScale1PoseEstimationConverged(x) ? 1 : 0; }
+int bba_host_solve_ldlt(int n, const double* upper, const double* b, double* x) {
+  if (!upper || !b || !x) return 0;
+  if (n == 4) bba::SolveLDLT<4>(upper, b, x);
+  else if (n == 5) bba::SolveLDLT<5>(upper, b, x);
+  else if (n == 6) bba::SolveLDLT<6>(upper, b, x);
+  else return 0;
+  return 1;
+}
+int bba_host_frusta_intersect(const float depth_intrinsics[4], int width, int height, const float global_T_frame_a[7], float min_depth_a,
+                              float max_depth_a, const float global_T_frame_b[7], float min_depth_b, float max_depth_b) {
+  Frustum a, b;
+  MakeFrustum(&a, depth_intrinsics, width, height, min_depth_a, max_depth_a, PoseFromArray(global_T_frame_a));
+  MakeFrustum(&b, depth_intrinsics, width, height, min_depth_b, max_depth_b, PoseFromArray(global_T_frame_b));
+  return FrustaIntersect(a, b) ? 1 : 0;
+}
+
 int bba_keyframe_count(bba_handle h) { return h ? static_cast<int>(h->keyframes.size()) : 0; }
 
 #define CHECK_KF(h, id)                                                                   \

@@ -332,6 +332,22 @@ bba_status bba_preprocess_frame(bba_handle h, const bba_preprocess_options* opti
                                 uint8_t* device_color_rgba, size_t color_pitch,
                                 float* min_depth, float* max_depth, void* stream);
 
+/* ---- host-side building blocks (no handle, no device) ----
+ * The host arithmetic the backend runs between kernels, exported so that it can be checked without a GPU: Sophus'
+ * SE3 exp / log / product / inverse on {qx,qy,qz,qw,tx,ty,tz} (se3.hpp:127-130,203-207,293-313,435-468), the convergence test of
+ * convergence_analysis.h:45-52, the fp64 pivoted LDLT solve standing in for Eigen's (direct_ba_alternating.cc:206,
+ * kernel_opt_intrinsics.cc:171,272; n = 4, 5 or 6, upper triangle packed row-major; returns 0 for another n), and the frustum
+ * intersection behind the co-visibility lists (camera_frustum.h:73-143, direct_ba.cc:231-249). */
+void bba_host_se3_exp(const float tangent[6], float out_pose[7]);
+void bba_host_se3_log(const float pose[7], float out_tangent[6]);
+void bba_host_se3_compose(const float a[7], const float b[7], float out_pose[7]);
+void bba_host_se3_inverse(const float a[7], float out_pose[7]);
+int  bba_host_pose_update_converged(const float x[6]);
+int  bba_host_solve_ldlt(int n, const double* upper, const double* b, double* x);
+int  bba_host_frusta_intersect(const float depth_intrinsics[4], int width, int height,
+                               const float global_T_frame_a[7], float min_depth_a, float max_depth_a,
+                               const float global_T_frame_b[7], float min_depth_b, float max_depth_b);
+
 /* ---- instrumentation ---- */
 uint64_t   bba_kernel_launch_count(bba_handle h);   /* kernels launched through this handle so far */
 
