@@ -123,13 +123,35 @@ def golden_end_tasks(name="tiny"):
     print("wrote", name, "end tasks: deleted", deleted, "of", sc.num_surfels)
 
 
+def golden_preprocess(name="tiny", kf=1):
+    """BadSlam::PreprocessFrame + min / max depth from the reference's kernels (cuda_depth_processing.cu,
+    cuda_image_processing.cu) on one noisy raw frame of the scene, with a non-trivial depth deformation."""
+    from badslam_b200.scene import raw_frame
+    sc = make_scene(config_by_name(name))
+    sc.depth_a = 0.02
+    sc.cfactor = (2e-3 * np.random.default_rng(5).random(sc.cfactor.shape)).astype(np.float32)
+    raw, rgb = raw_frame(sc, kf)
+    ref = ref_cuda.RefDirectBA(sc)
+    depth, normals, radius, rgba, mn, mx = ref.preprocess_frame(raw, rgb)
+    ref.close()
+    os.makedirs("gpurun_out/golden", exist_ok=True)
+    np.savez_compressed(f"gpurun_out/golden/{name}_preprocess.npz", scene=name, kf=kf, raw_checksum=int(raw.astype(np.uint64).sum()),
+                        depth=depth, normals=normals, radius=radius, luma=rgba[..., 3].copy(), min_depth=mn, max_depth=mx)
+    print("wrote", name, "preprocess: valid", float(((depth & 0x8000) == 0).mean()), mn, mx)
+
+
 if __name__ == "__main__":
+    if "--preprocess-only" in sys.argv:
+        golden_preprocess("tiny")
+        sys.exit(0)
     if "--extra-only" in sys.argv:
         golden_intrinsics_pcg("tiny")
         golden_end_tasks("tiny")
+    golden_preprocess("tiny")
         sys.exit(0)
     if "--end-tasks-only" in sys.argv:
         golden_end_tasks("tiny")
+    golden_preprocess("tiny")
         sys.exit(0)
     golden_for("cfg1")
     golden_for("tiny")
@@ -137,3 +159,4 @@ if __name__ == "__main__":
     golden_for("tiny", False, True, "_desc_only")
     golden_intrinsics_pcg("tiny")
     golden_end_tasks("tiny")
+    golden_preprocess("tiny")

@@ -5,6 +5,7 @@ set -x
 mkdir -p gpurun_out
 python -m pytest tests/test_gpu_preprocess.py -m gpu -q --tb=short -s 2>&1 | grep -v "^E   *+" | cut -c1-400 | tail -60 > gpurun_out/gpu_preprocess_tests.log
 python -m pytest tests -m gpu -q --tb=short 2>&1 | grep -v "^E   *+" | cut -c1-300 | tail -15 > gpurun_out/gpu_tests.log
+python tools/make_golden.py --preprocess-only > gpurun_out/golden_preprocess.log 2>&1   # -> gpurun_out/golden/tiny_preprocess.npz, copy to tests/golden/
 python tools/preprocess_time.py --size 640x480 > gpurun_out/preprocess_time.log 2>&1
 python tools/preprocess_time.py --size 640x480 --flush >> gpurun_out/preprocess_time.log 2>&1
 python tools/preprocess_time.py --size 1280x720 >> gpurun_out/preprocess_time.log 2>&1
