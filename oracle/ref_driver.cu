@@ -474,6 +474,7 @@ void ref_destroy(ref_context* c) {
 int ref_set_surfels(ref_context* c, const float* host, size_t host_pitch_bytes, unsigned int n) {
   if (n > c->max_surfels) return 1;
   c->surfels_size = n;
+  if (n == 0) return 0;
   cudaMemcpy2D(c->surfels, c->surfel_pitch, host, host_pitch_bytes, static_cast<size_t>(n) * 4, 8, cudaMemcpyHostToDevice);
   return cudaGetLastError() != cudaSuccess;
 }
