@@ -147,11 +147,9 @@ if __name__ == "__main__":
     if "--extra-only" in sys.argv:
         golden_intrinsics_pcg("tiny")
         golden_end_tasks("tiny")
-    golden_preprocess("tiny")
         sys.exit(0)
     if "--end-tasks-only" in sys.argv:
         golden_end_tasks("tiny")
-    golden_preprocess("tiny")
         sys.exit(0)
     golden_for("cfg1")
     golden_for("tiny")
