@@ -136,3 +136,76 @@ def test_empty_and_degenerate_inputs(tiny_scene):
     assert orc2.pose_coeffs(0).n_inimg == 0
     orc2.update_activation()
     assert not orc2.active.any()
+
+
+# ---- the intrinsics / depth-deformation tests (test_intrinsics_optimization_*.cc), at a quarter of the reference's image size.
+# reference_test_scene / empty_map_oracle are shared with tests/test_gpu_reference_tests.py, which runs the same three tests on
+# the CUDA path and compares it with the oracle's result.
+
+def reference_test_scene(seed, **kw):
+    """12 keyframes looking at 20 random planes from poses spread like the reference tests' (scene.py follows
+    test_intrinsics_optimization_photometric_residual.cc:182-211), exact poses, an empty surfel map with room to grow."""
+    import dataclasses
+    cfg = dataclasses.replace(S.SceneConfig(160, 120, 12, 2000, cell=2, seed=seed, name=f"reftest{seed}"),
+                              pose_noise_t=0.0, pose_noise_r=0.0, **kw)
+    sc = S.make_scene(cfg)
+    sc.surfels = np.zeros((17, 1 << 17), np.float32)
+    sc.num_surfels = 0
+    return sc
+
+
+def empty_map_oracle(sc, **kw):
+    orc = O.Oracle(sc, poses=sc.poses_true, **kw)
+    orc.n = 0
+    return orc
+
+
+DEPTH_CAMERA_PERTURBATION = 0.25 * np.array([0.5, -0.6, 1.23, -2.17])   # the reference's offsets (:150, :430) at quarter resolution
+
+
+def test_depth_deformation_optimization_with_geometric_residual():
+    """AlternatingDepthDeformationOptimizationWithGeometricResidual (test_intrinsics_optimization_geometric_residual.cc:178-366):
+    raw depth distorted with a = 0.03, cfactor = 0.005; 400 x BundleAdjustment(max 10 iterations, surfel updates on, poses fixed,
+    depth intrinsics on from the second call) starting from an EMPTY map -- the whole loop: creation, merging, deletion,
+    compaction, geometry, intrinsics + deformation Schur step.  Same assertions as the reference (:347-349)."""
+    sc = reference_test_scene(21, depth_a=0.03, cfactor=0.005)
+    orc = empty_map_oracle(sc, use_descriptor=False)
+    for i in range(400):
+        orc.bundle_adjust(False, True, 1, 10, optimize_depth_intrinsics=(i != 0), do_surfel_updates=True, end_tasks=(i != 0))
+    assert orc.n > 10000
+    assert abs(orc.model.a - 0.03) < 1e-2
+    assert abs(orc.cfactor[25, 25] - 0.005) < 1e-3
+    seen = orc.cfactor != 0
+    assert seen.mean() > 0.9 and abs(np.median(orc.cfactor[seen]) - 0.005) < 1e-3
+
+
+def test_intrinsics_optimization_with_geometric_residual():
+    """AlternatingIntrinsicsOptimizationWithGeometricResidual (:371-559): surfels created with the true camera, then the depth
+    camera estimate is perturbed; 100 x BundleAdjustment(depth intrinsics only) recover it to 1e-3 px (:539-542)."""
+    sc = reference_test_scene(22)
+    orc = empty_map_oracle(sc, use_descriptor=False)
+    for k in range(sc.cfg.num_keyframes):
+        orc.create_surfels_for_keyframe(k, True)
+    true_K = np.array(orc.model.depth_K[:], np.float64)
+    for i in range(4):
+        orc.model.depth_K[i] = float(true_K[i] + DEPTH_CAMERA_PERTURBATION[i])
+    for i in range(100):
+        orc.bundle_adjust(False, False, 1, 10, optimize_depth_intrinsics=True, end_tasks=(i != 0))
+    assert np.all(np.abs(np.array(orc.model.depth_K[:]) - true_K) < 1e-3)
+
+
+def test_intrinsics_optimization_with_photometric_residual():
+    """AlternatingIntrinsicsOptimizationWithPhotometricResidual (test_intrinsics_optimization_photometric_residual.cc:105-282):
+    descriptor residuals only, colour camera perturbed, 10 x BundleAdjustment(colour intrinsics only, surfel updates on);
+    thresholds 0.03 / 0.03 / 0.15 / 0.15 px (:262-265)."""
+    sc = reference_test_scene(23)
+    orc = empty_map_oracle(sc, use_depth=False)
+    for k in range(sc.cfg.num_keyframes):
+        orc.create_surfels_for_keyframe(k, True)
+    true_K = np.array(orc.model.color_K[:], np.float64)
+    for i in range(4):
+        orc.model.color_K[i] = float(true_K[i] + DEPTH_CAMERA_PERTURBATION[i])
+    for i in range(10):
+        orc.bundle_adjust(False, False, 1, 10, optimize_color_intrinsics=True, do_surfel_updates=True, end_tasks=(i != 0))
+    err = np.abs(np.array(orc.model.color_K[:]) - true_K)
+    assert np.all(err < [0.03, 0.03, 0.15, 0.15])
