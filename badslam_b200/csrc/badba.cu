@@ -1218,6 +1218,16 @@ bba_status BundleAdjustPCG(bba_handle h, const bba_ba_options* o, bba_ba_result*
     if (bba_status st = PerformEndTasks(h, s, &deleted, o->do_surfel_updates != 0)) return st;
     res->surfels_deleted += deleted;
     ++h->ba_iteration_count;
+  } else if (o->do_surfel_updates && !keyframes_with_new_surfels.empty()) {
+    // :775-815: without the end tasks, the keyframes of the last iteration's creation step are merged (and the map compacted) once more
+    uint32_t merged = 0;
+    for (int k : keyframes_with_new_surfels) {
+      uint32_t d = 0;
+      if (bba_status st = MergeSurfelsForKeyframe(h, k, s, &d)) return st;
+      merged += d;
+    }
+    res->surfels_merged += merged;
+    if (bba_status st = CompactSurfels(h, merged, /*with_active=*/true, s)) return st;
   }
   res->surfels_size = h->surfels_size;
   res->kernel_launches = h->launches - launches_before;

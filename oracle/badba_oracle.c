@@ -884,7 +884,7 @@ static void determine_covisible_active(orc_keyframes* kfs) {
   }
 }
 
-/* direct_ba_alternating.cc:285-738 (lifecycle branches omitted: do_surfel_updates must be 0). */
+/* direct_ba_alternating.cc:285-738, including the do_surfel_updates branches (creation :399-430, merge + compaction :489-541). */
 void orc_bundle_adjust(orc_model* m, orc_keyframes* kfs, float* surfels, int pitch, uint32_t n, uint8_t* active,
                        const orc_ba_options* opt, orc_ba_result* res) {
   memset(res, 0, sizeof(*res));
@@ -1178,8 +1178,24 @@ void orc_bundle_adjust_pcg(orc_model* m, orc_keyframes* kfs, float* surfels, int
   const uint32_t Pn = (uint32_t)(m->cf_w * m->cf_h);
   const uint32_t kInvalid = 0xffffffffu;
   const int max_inner = opt->max_inner_iterations > 0 ? opt->max_inner_iterations : 30;
+  int* with_new = (int*)malloc(sizeof(int) * (size_t)(K > 0 ? K : 1));
+  int n_with_new = 0;
   for (int iteration = 0; iteration < opt->max_iterations; ++iteration) {
     ++res->iterations_done;
+    /* surfel creation, direct_ba_pcg.cc:180-206 */
+    n_with_new = 0;
+    if (opt->optimize_geometry && opt->do_surfel_updates) {
+      for (int k = 0; k < K; ++k) {
+        if (kfs->activation[k] == ORC_KF_ACTIVE && opt->last_active_in_ba_iteration[k] != opt->ba_iteration_count) {
+          opt->last_active_in_ba_iteration[k] = opt->ba_iteration_count;
+          res->surfels_created += orc_create_surfels_for_keyframe(m, kfs, k, 1, opt->min_observation_count, surfels, pitch, &n,
+                                                                  opt->max_surfels);
+          with_new[n_with_new++] = k;
+        } else if (kfs->activation[k] == ORC_KF_COVIS_ACTIVE && opt->last_covis_in_ba_iteration[k] != opt->ba_iteration_count) {
+          opt->last_covis_in_ba_iteration[k] = opt->ba_iteration_count;
+        }
+      }
+    }
     memset(active, K_SURFEL_ACTIVE_FLAG, n);   /* direct_ba_pcg.cc:209-212 */
     if (opt->optimize_geometry && n > 0) {     /* :215-227 */
       float* Ts = (float*)malloc(sizeof(float) * 12 * (size_t)K);
@@ -1294,11 +1310,25 @@ void orc_bundle_adjust_pcg(orc_model* m, orc_keyframes* kfs, float* surfels, int
       if (L.opt_ci) for (int c = 0; c < 4; ++c) m->color_K[c] = (float)(m->color_K[c] + delta[L.color_start + c]);
       free(acc0); free(acc1); free(r); free(M); free(delta); free(g); free(p);
     }
+    /* surfel merge + compaction for the keyframes that received new surfels, direct_ba_pcg.cc:644-690 */
+    if (opt->do_surfel_updates && n_with_new > 0) {
+      for (int q = 0; q < n_with_new; ++q)
+        res->surfels_merged += orc_merge_surfels_for_keyframe(m, kfs, with_new[q], opt->surfel_merge_dist_factor, surfels, pitch, n);
+      n = orc_compact_surfels(surfels, pitch, n, active);
+    }
     if (iteration >= opt->min_iterations - 1 && (num_converged == K || !L.opt_poses)) {
       res->converged = 1;
       break;
     }
   }
+  /* direct_ba_pcg.cc:775-815: without the end tasks, the keyframes of the LAST iteration's creation step are merged once more */
+  if (!opt->increase_ba_iteration_count && opt->do_surfel_updates && n_with_new > 0) {
+    for (int q = 0; q < n_with_new; ++q)
+      res->surfels_merged += orc_merge_surfels_for_keyframe(m, kfs, with_new[q], opt->surfel_merge_dist_factor, surfels, pitch, n);
+    n = orc_compact_surfels(surfels, pitch, n, active);
+  }
+  free(with_new);
+  res->surfels_size = n;
 }
 
 /* Parity hook: r, M after the init pass; p = M^-1 r (with the prior on a); g after one J^T W J p sweep;

@@ -146,10 +146,20 @@ void orc_bundle_adjust(orc_model* m, orc_keyframes* kfs,
 typedef struct {
   int optimize_poses, optimize_geometry, optimize_depth_intrinsics, optimize_color_intrinsics;
   int min_iterations, max_iterations, max_inner_iterations, gauge_keyframe;
+  /* do_surfel_updates (direct_ba_pcg.cc:180-206,644-690,775-815); same meaning as in orc_ba_options */
+  int do_surfel_updates;
+  int increase_ba_iteration_count;        /* 0: the loop is followed by one more merge + compaction (:775-815) */
+  int ba_iteration_count;
+  int32_t* last_active_in_ba_iteration;   /* [K], updated */
+  int32_t* last_covis_in_ba_iteration;    /* [K], updated */
+  float surfel_merge_dist_factor;
+  int min_observation_count;
+  uint32_t max_surfels;
 } orc_pcg_options;
 typedef struct {
   int iterations_done, converged, inner_iterations_total;
   float last_r_norm;
+  uint32_t surfels_size, surfels_created, surfels_merged;
 } orc_pcg_result;
 void orc_bundle_adjust_pcg(orc_model* m, orc_keyframes* kfs, float* surfels, int pitch, uint32_t n, uint8_t* active,
                            const orc_pcg_options* opt, orc_pcg_result* res);

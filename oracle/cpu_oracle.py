@@ -69,12 +69,16 @@ class BAResult(C.Structure):
 class PCGOptions(C.Structure):
     _fields_ = [("optimize_poses", C.c_int), ("optimize_geometry", C.c_int), ("optimize_depth_intrinsics", C.c_int),
                 ("optimize_color_intrinsics", C.c_int), ("min_iterations", C.c_int), ("max_iterations", C.c_int),
-                ("max_inner_iterations", C.c_int), ("gauge_keyframe", C.c_int)]
+                ("max_inner_iterations", C.c_int), ("gauge_keyframe", C.c_int),
+                ("do_surfel_updates", C.c_int), ("increase_ba_iteration_count", C.c_int), ("ba_iteration_count", C.c_int),
+                ("last_active_in_ba_iteration", C.POINTER(C.c_int32)), ("last_covis_in_ba_iteration", C.POINTER(C.c_int32)),
+                ("surfel_merge_dist_factor", C.c_float), ("min_observation_count", C.c_int), ("max_surfels", C.c_uint32)]
 
 
 class PCGResult(C.Structure):
     _fields_ = [("iterations_done", C.c_int), ("converged", C.c_int), ("inner_iterations_total", C.c_int),
-                ("last_r_norm", C.c_float)]
+                ("last_r_norm", C.c_float),
+                ("surfels_size", C.c_uint32), ("surfels_created", C.c_uint32), ("surfels_merged", C.c_uint32)]
 
 
 _lib = None
@@ -295,23 +299,52 @@ class Oracle:
             self.ba_iteration_count += 1
         return r
 
+    def _lifecycle_state(self):
+        if not hasattr(self, "last_active_in_ba_iteration"):
+            self.last_active_in_ba_iteration = np.full(self.K, -1, np.int32)   # keyframe.cc:47-48
+            self.last_covis_in_ba_iteration = np.full(self.K, -1, np.int32)
+            self.ba_iteration_count = 0
+
+    def _pcg_options(self, optimize_poses, optimize_geometry, optimize_depth_intrinsics, optimize_color_intrinsics, min_iterations,
+                     max_iterations, max_inner_iterations, gauge_keyframe, do_surfel_updates=False, increase=True,
+                     surfel_merge_dist_factor=0.8):
+        self._lifecycle_state()
+        return PCGOptions(int(optimize_poses), int(optimize_geometry), int(optimize_depth_intrinsics),
+                          int(optimize_color_intrinsics), min_iterations, max_iterations, max_inner_iterations, gauge_keyframe,
+                          int(do_surfel_updates), int(increase), self.ba_iteration_count,
+                          _p(self.last_active_in_ba_iteration, C.c_int32), _p(self.last_covis_in_ba_iteration, C.c_int32),
+                          float(surfel_merge_dist_factor), self.min_observation_count(), self.pitch)
+
     def bundle_adjust_pcg(self, optimize_poses=True, optimize_geometry=True, optimize_depth_intrinsics=False,
                           optimize_color_intrinsics=False, min_iterations=1, max_iterations=1, max_inner_iterations=30,
-                          gauge_keyframe=0, end_tasks=True):
-        o = PCGOptions(int(optimize_poses), int(optimize_geometry), int(optimize_depth_intrinsics),
-                       int(optimize_color_intrinsics), min_iterations, max_iterations, max_inner_iterations, gauge_keyframe)
+                          gauge_keyframe=0, end_tasks=True, do_surfel_updates=False, surfel_merge_dist_factor=0.8):
+        """DirectBA::BundleAdjustmentPCG; end_tasks = increase_ba_iteration_count (direct_ba_pcg.cc:763-776)."""
+        o = self._pcg_options(optimize_poses, optimize_geometry, optimize_depth_intrinsics, optimize_color_intrinsics,
+                              min_iterations, max_iterations, max_inner_iterations, gauge_keyframe, do_surfel_updates, end_tasks,
+                              surfel_merge_dist_factor)
         r = PCGResult()
         self.lib.orc_bundle_adjust_pcg(C.byref(self.model), C.byref(self.kfs), _p(self.surfels, C.c_float),
                                        C.c_int(self.pitch), C.c_uint32(self.n), _p(self.active, C.c_uint8),
                                        C.byref(o), C.byref(r))
+        self.n = int(r.surfels_size)
         if end_tasks:
-            self.surfels_deleted = self.end_tasks()
+            if do_surfel_updates:
+                n = C.c_uint32(self.n)
+                self.lib.orc_end_tasks_with_merge.restype = C.c_uint32
+                self.surfels_deleted = int(self.lib.orc_end_tasks_with_merge(
+                    C.byref(self.model), C.byref(self.kfs), _p(self.surfels, C.c_float), C.c_int(self.pitch), C.byref(n),
+                    C.c_int(self.min_observation_count()), _p(self.last_active_in_ba_iteration, C.c_int32),
+                    C.c_int(self.ba_iteration_count), C.c_float(surfel_merge_dist_factor)))
+                self.n = int(n.value)
+            else:
+                self.surfels_deleted = self.end_tasks()
+            self.ba_iteration_count += 1
         return r
 
     def pcg_debug(self, optimize_poses=True, optimize_geometry=True, optimize_depth_intrinsics=False,
                   optimize_color_intrinsics=False, gauge_keyframe=0):
-        o = PCGOptions(int(optimize_poses), int(optimize_geometry), int(optimize_depth_intrinsics),
-                       int(optimize_color_intrinsics), 1, 1, 30, gauge_keyframe)
+        o = self._pcg_options(optimize_poses, optimize_geometry, optimize_depth_intrinsics, optimize_color_intrinsics, 1, 1, 30,
+                              gauge_keyframe)
         self.lib.orc_pcg_debug.restype = C.c_uint32
         args = (C.byref(self.model), C.byref(self.kfs), _p(self.surfels, C.c_float), C.c_int(self.pitch), C.c_uint32(self.n),
                 C.byref(o))

@@ -67,3 +67,20 @@ def test_intrinsics_optimization_with_photometric_residual(mods):
     err = np.abs(np.asarray(ba.color_camera().parameters, np.float64) - true_K)
     print("colour camera error (px):", err)
     assert np.all(err < [0.03, 0.03, 0.15, 0.15])
+
+
+def test_pcg_depth_deformation_optimization_with_geometric_residual(mods):
+    """PCGDepthDeformationOptimizationWithGeometricResidual (:364-366): 20 x BundleAdjustment(use_pcg) with surfel updates
+    (direct_ba_pcg.cc:180-206,644-690,775-815)."""
+    S, DirectBA, Cam, T = mods
+    sc = T.reference_test_scene(21, depth_a=0.03, cfactor=0.005)
+    ba = DirectBA.from_scene(sc, poses=sc.poses_true, use_descriptor_residuals=False)
+    for i in range(20):
+        r = ba.BundleAdjustment(None, i != 0, False, True, False, True, 1, 10, use_pcg=True, increase_ba_iteration_count=(i != 0),
+                                pcg_gauge_keyframe=0)
+        assert r.surfels_size == ba.surfels_size()
+    cf = ba.cfactor_buffer()
+    print(f"PCG: a = {ba.a():.4f} (true 0.03), cfactor[25, 25] = {cf[25, 25]:.5f} (true 0.005), surfels {ba.surfels_size()}")
+    assert ba.surfels_size() > 10000
+    assert abs(ba.a() - 0.03) < 1e-2
+    assert abs(cf[25, 25] - 0.005) < 1e-3

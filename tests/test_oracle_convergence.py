@@ -209,3 +209,17 @@ def test_intrinsics_optimization_with_photometric_residual():
         orc.bundle_adjust(False, False, 1, 10, optimize_color_intrinsics=True, do_surfel_updates=True, end_tasks=(i != 0))
     err = np.abs(np.array(orc.model.color_K[:]) - true_K)
     assert np.all(err < [0.03, 0.03, 0.15, 0.15])
+
+
+def test_pcg_depth_deformation_optimization_with_geometric_residual():
+    """PCGDepthDeformationOptimizationWithGeometricResidual (test_intrinsics_optimization_geometric_residual.cc:364-366): the same
+    test through BundleAdjustmentPCG with its surfel-update branches (direct_ba_pcg.cc:180-206,644-690,775-815); the joint
+    solve needs 20 calls instead of 400."""
+    sc = reference_test_scene(21, depth_a=0.03, cfactor=0.005)
+    orc = empty_map_oracle(sc, use_descriptor=False)
+    for i in range(20):
+        r = orc.bundle_adjust_pcg(False, True, i != 0, False, 1, 10, 30, 0, end_tasks=(i != 0), do_surfel_updates=True)
+        assert r.surfels_size == orc.n or i != 0          # with the end tasks the map shrinks once more after the call
+    assert orc.n > 10000
+    assert abs(orc.model.a - 0.03) < 1e-2
+    assert abs(orc.cfactor[25, 25] - 0.005) < 1e-3
