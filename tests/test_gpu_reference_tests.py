@@ -25,8 +25,13 @@ def test_depth_deformation_optimization_with_geometric_residual(mods):
     sc = T.reference_test_scene(21, depth_a=0.03, cfactor=0.005)
     ba = DirectBA.from_scene(sc, poses=sc.poses_true, use_descriptor_residuals=False)
     assert ba.surfels_size() == 0
+    orc = T.empty_map_oracle(sc, use_descriptor=False)
     for i in range(400):
         ba.BundleAdjustment(None, i != 0, False, True, False, True, 1, 10, increase_ba_iteration_count=(i != 0))
+        if i < 3:      # side by side with the oracle while rounding differences have had no time to grow
+            orc.bundle_adjust(False, True, 1, 10, optimize_depth_intrinsics=(i != 0), do_surfel_updates=True, end_tasks=(i != 0))
+            assert abs(ba.surfels_size() - orc.n) <= 0.01 * orc.n, (i, ba.surfels_size(), orc.n)
+            assert abs(ba.a() - orc.model.a) <= 1e-3 + 0.05 * abs(orc.model.a), (i, ba.a(), orc.model.a)
     cf = ba.cfactor_buffer()
     print(f"a = {ba.a():.4f} (true 0.03), cfactor[25, 25] = {cf[25, 25]:.5f} (true 0.005), surfels {ba.surfels_size()}")
     assert ba.surfels_size() > 10000
