@@ -89,3 +89,33 @@ def test_pcg_depth_deformation_optimization_with_geometric_residual(mods):
     assert ba.surfels_size() > 10000
     assert abs(ba.a() - 0.03) < 1e-2
     assert abs(cf[25, 25] - 0.005) < 1e-3
+
+
+def test_pcg_intrinsics_optimization_with_geometric_and_photometric_residuals(mods):
+    """The PCG variants of the two camera tests (…geometric_residual.cc:565-567, …photometric_residual.cc:288-290)."""
+    S, DirectBA, Cam, T = mods
+    sc = T.reference_test_scene(22)
+    ba = DirectBA.from_scene(sc, poses=sc.poses_true, use_descriptor_residuals=False)
+    for k in range(sc.cfg.num_keyframes):
+        ba.CreateSurfelsForKeyframe(None, True, k)
+    true_K = np.asarray(sc.depth_K, np.float64)
+    ba.SetDepthCamera(Cam(sc.cfg.width, sc.cfg.height, (true_K + T.DEPTH_CAMERA_PERTURBATION).astype(np.float32)))
+    for i in range(100):
+        ba.BundleAdjustment(None, True, False, False, False, False, 1, 10, use_pcg=True, increase_ba_iteration_count=(i != 0),
+                            pcg_gauge_keyframe=0)
+    err = np.abs(np.asarray(ba.depth_camera().parameters, np.float64) - true_K)
+    print("PCG depth camera error (px):", err)
+    assert np.all(err < 2e-3)      # the oracle reaches 5e-4 on this quarter-resolution scene
+
+    sc = T.reference_test_scene(23)
+    ba = DirectBA.from_scene(sc, poses=sc.poses_true, use_depth_residuals=False)
+    for k in range(sc.cfg.num_keyframes):
+        ba.CreateSurfelsForKeyframe(None, True, k)
+    true_K = np.asarray(sc.color_K, np.float64)
+    ba.SetColorCamera(Cam(sc.cfg.width, sc.cfg.height, (true_K + T.DEPTH_CAMERA_PERTURBATION).astype(np.float32)))
+    for i in range(10):
+        ba.BundleAdjustment(None, False, True, True, False, False, 1, 10, use_pcg=True, increase_ba_iteration_count=(i != 0),
+                            pcg_gauge_keyframe=0)
+    err = np.abs(np.asarray(ba.color_camera().parameters, np.float64) - true_K)
+    print("PCG colour camera error (px):", err)
+    assert np.all(err < [0.03, 0.03, 0.15, 0.15])

@@ -223,3 +223,29 @@ def test_pcg_depth_deformation_optimization_with_geometric_residual():
     assert orc.n > 10000
     assert abs(orc.model.a - 0.03) < 1e-2
     assert abs(orc.cfactor[25, 25] - 0.005) < 1e-3
+
+
+def test_pcg_intrinsics_optimization_with_geometric_and_photometric_residuals():
+    """PCGIntrinsicsOptimizationWithGeometricResidual (test_intrinsics_optimization_geometric_residual.cc:565-567, 100 calls, 1e-3 px)
+    and PCGIntrinsicsOptimizationWithPhotometricResidual (test_intrinsics_optimization_photometric_residual.cc:288-290)."""
+    sc = reference_test_scene(22)
+    orc = empty_map_oracle(sc, use_descriptor=False)
+    for k in range(sc.cfg.num_keyframes):
+        orc.create_surfels_for_keyframe(k, True)
+    true_K = np.array(orc.model.depth_K[:], np.float64)
+    for i in range(4):
+        orc.model.depth_K[i] = float(true_K[i] + DEPTH_CAMERA_PERTURBATION[i])
+    for i in range(100):
+        orc.bundle_adjust_pcg(False, False, True, False, 1, 10, 30, 0, end_tasks=(i != 0))
+    assert np.all(np.abs(np.array(orc.model.depth_K[:]) - true_K) < 1e-3)
+
+    sc = reference_test_scene(23)
+    orc = empty_map_oracle(sc, use_depth=False)
+    for k in range(sc.cfg.num_keyframes):
+        orc.create_surfels_for_keyframe(k, True)
+    true_K = np.array(orc.model.color_K[:], np.float64)
+    for i in range(4):
+        orc.model.color_K[i] = float(true_K[i] + DEPTH_CAMERA_PERTURBATION[i])
+    for i in range(10):
+        orc.bundle_adjust_pcg(False, False, False, True, 1, 10, 30, 0, end_tasks=(i != 0), do_surfel_updates=True)
+    assert np.all(np.abs(np.array(orc.model.color_K[:]) - true_K) < [0.03, 0.03, 0.15, 0.15])
