@@ -83,6 +83,22 @@ def test_geometry_optimization_with_geometric_residual():
     assert np.percentile(after[act], 90) < 1.5e-3
 
 
+def test_pcg_geometry_optimization_with_geometric_residual():
+    """PCGGeometryOptimizationWithGeometricResidual (test_geometry_optimization_geometric_residual.cc:220-222): the same scene
+    through BundleAdjustmentPCG (one unknown per surfel, the offset along its normal)."""
+    sc = _scene(surfel_depth_noise=0.002)
+    orc = O.Oracle(sc, use_depth=True, use_descriptor=False, poses=sc.poses_true)
+    n = sc.num_surfels
+    pl = sc.planes.astype(np.float64)
+    surface_distance = lambda xyz: np.min(np.abs(pl[:, :3] @ xyz.astype(np.float64) + pl[:, 3:4]), axis=0)
+    before = surface_distance(sc.surfels[:3, :n])
+    for _ in range(3):
+        r = orc.bundle_adjust_pcg(False, True, False, False, 10, 10, 30, 0, end_tasks=False)
+        assert r.iterations_done == 10 and r.converged
+    after = surface_distance(orc.surfels[:3, :n])
+    assert np.median(after) < 0.35 * np.median(before) and np.percentile(after, 90) < 1.5e-3
+
+
 def test_geometry_optimization_with_photometric_residual():
     """test_geometry_optimization_photometric_residual.cc:120-285: descriptors are re-estimated jointly with the
     position; after a few iterations the descriptor cost must have dropped."""
