@@ -189,10 +189,18 @@ def run_ours(args, scene, rank, world):
     # false with the counters in sync, direct_ba_alternating.cc:313-319) and is part of the full-BA number below.
     ba.SetLastBAIterationCount(ba.ba_iteration_count())
 
+    # --intrinsics (cfg4): the depth-intrinsics / depth-deformation and colour-intrinsics steps are part of the iteration; the
+    # camera model is restored before every step like the surfels and poses are.
+    intr = bool(getattr(args, "intrinsics", False))
+    if intr:
+        cam0 = (ba.depth_camera(), ba.color_camera(), ba.a(), ba.cfactor_buffer().copy())
+
     def step():
         surf[:8].copy_(backup, non_blocking=True)
         ba.SetKeyframeStates(poses0, act0)
-        return ba.BundleAdjustment(None, False, False, False, True, True, 1, 1, increase_ba_iteration_count=False)
+        if intr:
+            ba.SetDepthCamera(cam0[0]); ba.SetColorCamera(cam0[1]); ba.SetA(cam0[2]); ba.SetCFactorBuffer(cam0[3])
+        return ba.BundleAdjustment(None, intr, intr, False, True, True, 1, 1, increase_ba_iteration_count=False)
 
     for _ in range(args.warmup):
         res = step()
@@ -282,6 +290,9 @@ def run_ours(args, scene, rank, world):
         "pose_iterations_per_step": res.pose_iterations_total,
         "ms_full_ba_10_iterations": ms_full, "full_ba_iterations": full.iterations_done,
     }
+    if intr:
+        out["config"]["intrinsics"] = "depth intrinsics + depth deformation + colour intrinsics optimised in every step (--intrinsics)"
+        out["stage_ms"]["BA_intrinsics_optimization"] = res.ms_intrinsics_optimization
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_port_baseline(scene)
     if world > 1:
@@ -470,6 +481,8 @@ def _main(saved_stdout):
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("BADBA_WORKLOAD", "cfg3"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--intrinsics", action="store_true",
+                    help="optimise depth intrinsics + depth deformation and colour intrinsics inside the step (the cfg4 configuration)")
     ap.add_argument("--residuals-override", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
