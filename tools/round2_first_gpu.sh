@@ -5,10 +5,11 @@ set -x
 mkdir -p gpurun_out
 python -m pytest tests/test_gpu_preprocess.py -m gpu -q --tb=short -s 2>&1 | grep -v "^E   *+" | cut -c1-400 | tail -60 > gpurun_out/gpu_preprocess_tests.log
 python -m pytest tests -m gpu -q --tb=short 2>&1 | grep -v "^E   *+" | cut -c1-300 | tail -15 > gpurun_out/gpu_tests.log
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_preprocess.py -m gpu -q -x -k 'ragged or edge' > gpurun_out/sanitizer_preprocess.log 2>&1; echo "sanitizer exit $?" >> gpurun_out/sanitizer_preprocess.log
 python tools/make_golden.py --preprocess-only > gpurun_out/golden_preprocess.log 2>&1   # -> gpurun_out/golden/tiny_preprocess.npz, copy to tests/golden/
 python tools/preprocess_time.py --size 640x480 > gpurun_out/preprocess_time.log 2>&1
 python tools/preprocess_time.py --size 640x480 --flush >> gpurun_out/preprocess_time.log 2>&1
 python tools/preprocess_time.py --size 1280x720 >> gpurun_out/preprocess_time.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'PreprocessFrameKernel' -c 2 -o gpurun_out/r2_preprocess -f python tools/preprocess_time.py --iters 3 > gpurun_out/ncu_preprocess.log 2>&1
 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_r2_first.json 2> gpurun_out/bench_r2_first.err
-tail -25 gpurun_out/gpu_preprocess_tests.log; tail -3 gpurun_out/gpu_tests.log; cat gpurun_out/preprocess_time.log; tail -c 300 gpurun_out/bench_r2_first.json
+tail -25 gpurun_out/gpu_preprocess_tests.log; tail -4 gpurun_out/sanitizer_preprocess.log; tail -3 gpurun_out/gpu_tests.log; cat gpurun_out/preprocess_time.log; tail -c 300 gpurun_out/bench_r2_first.json
