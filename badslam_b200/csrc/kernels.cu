@@ -119,7 +119,6 @@ __device__ __forceinline__ float WarpTransposeReduce(float (&v)[32], int lane) {
 #endif
 constexpr int kPoseThreads = 256;
 constexpr int kPoseUnroll = BBA_POSE_UNROLL;   // surfels of a chunk evaluated concurrently per lane
-constexpr int kPoseWarps = kPoseThreads / 32;
 constexpr int kPoseStagedRows = 7;   // x y z normal radius^2 d1 d2
 constexpr int kPoseGroup = 8;        // keyframes per work item
 
