@@ -107,3 +107,32 @@ int main(int argc, char**) {
                            "-L", libdir, "-lbadba_b200", f"-Wl,-rpath,{libdir}"])
     rc = subprocess.call([str(exe)])
     assert rc == (0 if torch.cuda.is_available() else 42)
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/badba.h is the FFI boundary: it must compile as C99 (cgo / JNI / ctypes-style bindings parse it as C) and a C
+    program must link against the library and call a device-free entry point."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "binding.c"
+    src.write_text(r'''
+#include "badba.h"
+#include <math.h>
+int main(void) {
+  bba_ba_options o;
+  float tangent[6] = {0.1f, -0.2f, 0.3f, 0.0f, 0.0f, 0.0f}, pose[7], back[6];
+  (void)o;
+  if (bba_abi_version() != BBA_ABI_VERSION) return 1;
+  bba_host_se3_exp(tangent, pose);            /* pure translation: q = (0, 0, 0, 1), t = tangent[0..2] */
+  bba_host_se3_log(pose, back);
+  if (fabsf(pose[3] - 1.0f) > 1e-6f || fabsf(pose[4] - 0.1f) > 1e-6f || fabsf(back[2] - 0.3f) > 1e-6f) return 2;
+  return bba_create(0, 0) == BBA_ERR_INVALID_ARGUMENT ? 0 : 3;
+}''')
+    exe = tmp_path / "binding"
+    libdir = os.path.join(ROOT, "badslam_b200")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                           "-o", str(exe), "-L", libdir, "-lbadba_b200", "-lm", f"-Wl,-rpath,{libdir}"])
+    assert subprocess.call([str(exe)]) == 0
