@@ -100,10 +100,12 @@ def _worker(rank, world, port, n, K, out_dir):
     dist.destroy_process_group()
 
 
-def test_exchange_patterns_world_size_2_gloo(tmp_path):
-    world = 2
+@pytest.mark.parametrize("world,n", [(2, 1000), (4, 5000)])
+def test_exchange_patterns_gloo(tmp_path, world, n):
+    """One process per rank over gloo: the surfel-granule all-gather and the keyframe-slot all-reduce reassemble the same state on
+    every rank (world 2, and world 4 with surfel counts that leave ranks with uneven granule counts)."""
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, 1000, 9, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, n, 9, str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
 
 
