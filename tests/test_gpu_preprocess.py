@@ -10,7 +10,8 @@ agrees, normals and radii must agree as well."""
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+UNVALIDATED = ("written after the round-1 GPU budget was spent: first hardware run pending (XPASS = validated; remove this mark once it has passed on a B200)")
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason=UNVALIDATED)]
 
 
 @pytest.fixture(scope="module")
