@@ -17,7 +17,9 @@
 
 #include <cstdint>
 #include <cstring>
+#include <fstream>
 #include <functional>
+#include <vector>
 #include <stdexcept>
 #include <string>
 
@@ -211,5 +213,47 @@ class DirectBA {
   bba_ba_result last_result_{};
   int pcg_gauge_keyframe_ = -1;
 };
+
+// SaveCalibration / LoadCalibration (io.h:60-72, io.cc:570-700), same three text files: <base>.depth_intrinsics.txt and
+// <base>.color_intrinsics.txt ("fx fy cx-0.5 cy-0.5") and <base>.deformation.txt ("w h", a, then the cfactor grid row by row).
+inline bool SaveCalibration(cudaStream_t stream, bba_handle h, const std::string& export_base_path) {
+  float d[4], c[4], a;
+  int w = 0, hh = 0;
+  if (bba_get_intrinsics(h, d, c, &a) != BBA_OK || bba_cfactor_size(h, &w, &hh) != BBA_OK) return false;
+  std::vector<float> cf(static_cast<size_t>(w) * hh);
+  if (bba_get_cfactor_host(h, cf.data(), stream) != BBA_OK) return false;   // synchronises the stream
+  const float* cams[2] = {d, c};
+  const char* names[2] = {".depth_intrinsics.txt", ".color_intrinsics.txt"};
+  for (int i = 0; i < 2; ++i) {
+    std::ofstream f(export_base_path + names[i], std::ios::out);
+    if (!f) return false;
+    f << cams[i][0] << " " << cams[i][1] << " " << (cams[i][2] - 0.5) << " " << (cams[i][3] - 0.5);
+  }
+  std::ofstream f(export_base_path + ".deformation.txt", std::ios::out);
+  if (!f) return false;
+  f.precision(8);
+  f << w << " " << hh << std::endl << a << std::endl;
+  for (float v : cf) f << v << std::endl;
+  return true;
+}
+
+inline bool LoadCalibration(cudaStream_t stream, bba_handle h, const std::string& import_base_path) {
+  float cams[2][4], a = 0.f;
+  const char* names[2] = {".depth_intrinsics.txt", ".color_intrinsics.txt"};
+  for (int i = 0; i < 2; ++i) {
+    std::ifstream f(import_base_path + names[i], std::ios::in);
+    if (!f || !(f >> cams[i][0] >> cams[i][1] >> cams[i][2] >> cams[i][3])) return false;
+    cams[i][2] += 0.5f;
+    cams[i][3] += 0.5f;
+  }
+  std::ifstream f(import_base_path + ".deformation.txt", std::ios::in);
+  int w = 0, hh = 0, fw = 0, fh = 0;
+  if (!f || !(f >> fw >> fh) || bba_cfactor_size(h, &w, &hh) != BBA_OK || fw != w || fh != hh) return false;   // io.cc:676-680
+  if (!(f >> a)) return false;
+  std::vector<float> cf(static_cast<size_t>(w) * hh);
+  for (float& v : cf)
+    if (!(f >> v)) return false;
+  return bba_set_intrinsics(h, cams[0], cams[1], a) == BBA_OK && bba_set_cfactor_host(h, cf.data(), stream) == BBA_OK;   // synchronises
+}
 
 }  // namespace badba

@@ -93,6 +93,8 @@ int main(int argc, char**) {
       ba.CreateSurfelsForKeyframe(nullptr, true, 0);
       SE3 pose{};
       ba.EstimateFramePose(nullptr, pose, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, &pose);
+      badba::SaveCalibration(nullptr, ba.handle(), "/tmp/calib");
+      badba::LoadCalibration(nullptr, ba.handle(), "/tmp/calib");
       int done; bool conv;
       ba.BundleAdjustment(nullptr, false, false, true, true, true, 1, 10, false, 0, 0, true, &done, &conv, 0, nullptr, 30, 2500,
                           [](int it) { return it < 3; });

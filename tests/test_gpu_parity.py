@@ -540,3 +540,22 @@ def test_estimate_frame_pose_from_buffers_equals_the_keyframe_form(mods, small_s
     from badslam_b200._lib import BadBAError
     with pytest.raises(BadBAError):
         full.EstimateFramePoseFromBuffers(None, sc.poses_init[k], depth, normals, color)
+
+
+@UNVALIDATED
+def test_calibration_files_round_trip_through_the_backend(mods, tiny_scene, tmp_path):
+    """SaveCalibration / LoadCalibration (io.cc:570-700) on the real backend state."""
+    S, DirectBA, O, R = mods
+    from badslam_b200 import calibration_io as IO
+    from badslam_b200.direct_ba import PinholeCamera4f
+    sc = tiny_scene
+    src, dst = DirectBA.from_scene(sc), DirectBA.from_scene(sc)
+    src.SetDepthCamera(PinholeCamera4f(sc.cfg.width, sc.cfg.height, np.asarray(sc.depth_K) * np.float32(1.01)))
+    src.SetA(0.0275)
+    cf = (1e-3 * np.random.default_rng(1).random(src.cfactor_buffer().shape)).astype(np.float32)
+    src.SetCFactorBuffer(cf)
+    base = str(tmp_path / "calib")
+    assert IO.SaveCalibration(src, base) and IO.LoadCalibration(dst, base)
+    assert np.allclose(dst.depth_camera().parameters, src.depth_camera().parameters, rtol=1e-5)
+    assert np.allclose(dst.color_camera().parameters, src.color_camera().parameters, rtol=1e-5)
+    assert abs(dst.a() - 0.0275) < 1e-7 and np.allclose(dst.cfactor_buffer(), cf, rtol=1e-7)
