@@ -11,5 +11,6 @@ python tools/preprocess_time.py --size 640x480 > gpurun_out/preprocess_time.log 
 python tools/preprocess_time.py --size 640x480 --flush >> gpurun_out/preprocess_time.log 2>&1
 python tools/preprocess_time.py --size 1280x720 >> gpurun_out/preprocess_time.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'PreprocessFrameKernel' -c 2 -o gpurun_out/r2_preprocess -f python tools/preprocess_time.py --iters 3 > gpurun_out/ncu_preprocess.log 2>&1
+python tools/run_dataset.py --make-synthetic /tmp/synth_ds > gpurun_out/run_dataset.log 2>&1 && python tools/run_dataset.py /tmp/synth_ds --keyframe-interval 1 --raw-to-float-depth 0.001 --cell-size 2 --max-depth 6 --max-surfels 1000000 >> gpurun_out/run_dataset.log 2>&1
 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_r2_first.json 2> gpurun_out/bench_r2_first.err
-tail -25 gpurun_out/gpu_preprocess_tests.log; tail -4 gpurun_out/sanitizer_preprocess.log; tail -3 gpurun_out/gpu_tests.log; cat gpurun_out/preprocess_time.log; tail -c 300 gpurun_out/bench_r2_first.json
+tail -25 gpurun_out/gpu_preprocess_tests.log; tail -4 gpurun_out/sanitizer_preprocess.log; tail -3 gpurun_out/gpu_tests.log; cat gpurun_out/preprocess_time.log; tail -2 gpurun_out/run_dataset.log; tail -c 300 gpurun_out/bench_r2_first.json
