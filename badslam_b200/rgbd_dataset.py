@@ -166,3 +166,23 @@ def write_tum_dataset(folder: str, camera_parameters, colors, depths, timestamps
             for t, p in zip(timestamps, poses):
                 p = np.asarray(p, np.float64)
                 f.write(f"{t:.6f} {p[4]:.9g} {p[5]:.9g} {p[6]:.9g} {p[0]:.9g} {p[1]:.9g} {p[2]:.9g} {p[3]:.9g}\n")
+
+
+def save_poses(export_poses_path: str, time_strings, poses_global_T_frame, start_frame: int = 0) -> bool:
+    """SavePoses (io.cc:537-568): the trajectory in TUM format, "time tx ty tz qx qy qz qw" with 16 significant digits, every
+    pose pre-multiplied by frame_T_global of `start_frame` so that that frame sits at the identity; time stamps are written as
+    the strings they were read with."""
+    from . import scene as S
+    P = np.asarray(poses_global_T_frame, np.float64)
+    start_frame_T_global = S.se3_inverse(P[start_frame])
+    try:
+        f = open(export_poses_path, "w")
+    except OSError:
+        return False
+    with f:
+        f.write("# Format: Each line gives one global_T_frame pose with values: tx ty tz qx qy qz qw\n")
+        for ts, p in zip(time_strings, P):
+            g = np.asarray(S.se3_mul(start_frame_T_global, p), np.float32)   # SE3f arithmetic, then printed through double
+            vals = [g[4], g[5], g[6], g[0], g[1], g[2], g[3]]
+            f.write(str(ts) + " " + " ".join("%.16g" % float(v) for v in vals) + "\n")
+    return True

@@ -68,3 +68,21 @@ def test_malformed_inputs_raise(tmp_path):
     (tmp_path / "associated.txt").write_text("1.0 rgb/1.png 1.0 depth/1.png\n")
     with pytest.raises(OSError):
         D.TUMRGBDDataset(str(tmp_path))                       # the image files are missing
+
+
+def test_saved_poses_read_back_relative_to_the_start_frame(tmp_path, tiny_scene):
+    """SavePoses (io.cc:537-568) writes what ReadTUMRGBDTrajectory reads; the start frame ends up at the identity."""
+    sc = tiny_scene
+    K = sc.cfg.num_keyframes
+    names = [f"{100.0 + k:.6f}" for k in range(K)]
+    path = str(tmp_path / "poses.txt")
+    assert D.save_poses(path, names, sc.poses_true, start_frame=1)
+    ts, poses = D.read_tum_trajectory(path)
+    assert list(ts) == [100.0 + k for k in range(K)]
+    assert S.pose_error(poses[1], [0, 0, 0, 1, 0, 0, 0]) < (1e-6, 1e-6)
+    for k in range(K):
+        want = S.se3_mul(S.se3_inverse(sc.poses_true[1]), sc.poses_true[k])
+        e = S.pose_error(poses[k], want)
+        assert e[0] < 1e-5 and e[1] < 1e-5
+    assert open(path).readline().startswith("# Format: Each line gives one global_T_frame pose")
+    assert not D.save_poses(str(tmp_path / "no_such_dir" / "poses.txt"), names, sc.poses_true)
