@@ -19,6 +19,7 @@
 #include <cstring>
 #include <fstream>
 #include <functional>
+#include <mutex>
 #include <vector>
 #include <stdexcept>
 #include <string>
@@ -78,6 +79,9 @@ class DirectBA {
     c.min_observation_count_while_bootstrapping_2 = min_observation_count_while_bootstrapping_2;
     c.min_observation_count = min_observation_count;
     c.surfel_merge_dist_factor = surfel_merge_dist_factor;
+    min_observation_counts_[0] = min_observation_count_while_bootstrapping_1;
+    min_observation_counts_[1] = min_observation_count_while_bootstrapping_2;
+    min_observation_counts_[2] = min_observation_count;
     Check(bba_create(&c, &h_), "bba_create");
   }
   ~DirectBA() { bba_destroy(h_); }
@@ -197,6 +201,25 @@ class DirectBA {
   void GetIntrinsics(float depth[4], float color[4], float* a) const { Check(bba_get_intrinsics(h_, depth, color, a), "bba_get_intrinsics"); }
   void SetPCGGaugeKeyframe(int keyframe_id) { pcg_gauge_keyframe_ = keyframe_id; }
 
+  // direct_ba.h:195-211: the mutex callers on other threads take around reads of poses / intrinsics / surfel counts while a
+  // BundleAdjustment call is running (the backend itself is one-call-at-a-time per handle)
+  void Lock() const { mutex_.lock(); }
+  void Unlock() const { mutex_.unlock(); }
+  std::mutex& Mutex() const { return mutex_; }
+
+  // direct_ba.h:220-226, 290-300, 311
+  int GetMinObservationCount() const {
+    const int K = bba_keyframe_count(h_);
+    return (K < 10) ? ((K < 5) ? min_observation_counts_[0] : min_observation_counts_[1]) : min_observation_counts_[2];
+  }
+  float a() const { float d[4], c[4], a = 0.f; bba_get_intrinsics(h_, d, c, &a); return a; }
+  void SetA(float a) { float d[4], c[4], old = 0.f; GetIntrinsics(d, c, &old); Check(bba_set_intrinsics(h_, d, c, a), "bba_set_intrinsics"); }
+  void IncreaseBAIterationCount() {
+    int count = 0, last = 0;
+    Check(bba_get_ba_iteration_counts(h_, &count, &last), "bba_get_ba_iteration_counts");
+    Check(bba_set_ba_iteration_counts(h_, count + 1, last), "bba_set_ba_iteration_counts");
+  }
+
   // direct_ba.h:317-328
   bool use_depth_residuals() const { int d = 0, c = 0; bba_get_residual_types(h_, &d, &c); return d != 0; }
   bool use_descriptor_residuals() const { int d = 0, c = 0; bba_get_residual_types(h_, &d, &c); return c != 0; }
@@ -212,6 +235,8 @@ class DirectBA {
   bba_handle h_ = nullptr;
   bba_ba_result last_result_{};
   int pcg_gauge_keyframe_ = -1;
+  int min_observation_counts_[3] = {1, 2, 3};
+  mutable std::mutex mutex_;
 };
 
 // SaveCalibration / LoadCalibration (io.h:60-72, io.cc:570-700), same three text files: <base>.depth_intrinsics.txt and

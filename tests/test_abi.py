@@ -95,6 +95,8 @@ int main(int argc, char**) {
       ba.EstimateFramePose(nullptr, pose, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}, &pose);
       badba::SaveCalibration(nullptr, ba.handle(), "/tmp/calib");
       badba::LoadCalibration(nullptr, ba.handle(), "/tmp/calib");
+      { std::lock_guard<std::mutex> lock(ba.Mutex()); ba.SetA(ba.a() + ba.GetMinObservationCount()); }
+      ba.Lock(); ba.IncreaseBAIterationCount(); ba.Unlock();
       int done; bool conv;
       ba.BundleAdjustment(nullptr, false, false, true, true, true, 1, 10, false, 0, 0, true, &done, &conv, 0, nullptr, 30, 2500,
                           [](int it) { return it < 3; });
