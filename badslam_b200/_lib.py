@@ -127,7 +127,7 @@ SYMBOLS = {
     "bba_update_surfel_activation": (C.c_int, [_P, _P]),
     "bba_optimize_geometry_iteration": (C.c_int, [_P, _P]),
     "bba_optimize_intrinsics": (C.c_int, [_P, C.c_int, C.c_int, _P]),
-    "bba_perform_end_tasks": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), _P]),
+    "bba_perform_end_tasks": (C.c_int, [_P, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), _P]),
     "bba_surfels_size": (C.c_uint32, [_P]),
     "bba_get_ba_iteration_counts": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "bba_set_ba_iteration_counts": (C.c_int, [_P, C.c_int, C.c_int]),
@@ -170,7 +170,7 @@ def load():
         fn = getattr(lib, name)   # AttributeError if the symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.bba_abi_version() != 5:
+    if lib.bba_abi_version() != 6:
         raise ImportError("libbadba_b200.so ABI version mismatch")
     _lib = lib
     return lib

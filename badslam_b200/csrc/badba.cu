@@ -162,6 +162,7 @@ struct bba_context {
   float* d_cfactor = nullptr;
   uint8_t* luma_staging = nullptr;    // u8 plane staging for the luma arrays
   size_t luma_staging_pitch = 0;
+  cudaEvent_t luma_staging_free = nullptr;   // recorded after the staging plane was consumed; the next user (any stream) waits on it
   uint8_t* color_staging = nullptr;   // uchar4 staging image for bba_update_keyframe_host
   size_t color_staging_pitch = 0;
   std::vector<Keyframe> keyframes;
@@ -493,7 +494,9 @@ bba_status RunPoseStep(bba_handle h, const std::vector<int>& ids, const std::vec
     // never blocked) until iteration it-1 has finished, and stop as soon as it left no unconverged keyframe.
     if (it >= 1) {
       while (h->h_flag[0] < it) {
-        if (cudaStreamQuery(s) == cudaSuccess) break;   // everything drained (or an error surfaced below)
+        // cudaSuccess: everything drained; any other result than "not ready" is a (sticky) device fault that would
+        // otherwise leave this loop spinning for ever -- the BBA_CUDA check below reports it
+        if (cudaStreamQuery(s) != cudaErrorNotReady) break;
       }
       if (h->h_flag[0] >= it && h->h_flag[1] == 0) break;
     }
@@ -1234,6 +1237,15 @@ bba_status BundleAdjustPCG(bba_handle h, const bba_ba_options* o, bba_ba_result*
   return BBA_OK;
 }
 
+// The u8 staging plane is shared by every keyframe / frame upload of the handle.  Calls may arrive on different streams (the
+// reference's tracking thread and BA thread use their own, bad_slam.cc:73-78,1197-1200): the next user waits until the previous
+// copy-to-array has consumed the plane.
+bba_status AcquireLumaStaging(bba_handle h, cudaStream_t s) {
+  if (!h->luma_staging_free) BBA_CUDA(h, cudaEventCreateWithFlags(&h->luma_staging_free, cudaEventDisableTiming));
+  else BBA_CUDA(h, cudaStreamWaitEvent(s, h->luma_staging_free, 0));
+  return BBA_OK;
+}
+
 // The luma plane (the .w channel of a uchar4 image) as a gather-enabled CUDA array (block-linear: 2-D locality for the sample
 // footprints) + a texture with the reference's sampling state (keyframe.cc:67-73).  *array / *tex are created when null and
 // refilled otherwise.
@@ -1242,6 +1254,7 @@ bba_status MakeLumaTexture(bba_handle h, const uint8_t* device_rgba, size_t colo
   const int cw = h->cfg.color_width, ch = h->cfg.color_height;
   if (!h->luma_staging)
     BBA_CUDA(h, cudaMallocPitch(reinterpret_cast<void**>(&h->luma_staging), &h->luma_staging_pitch, cw, ch));
+  if (bba_status st = AcquireLumaStaging(h, s)) return st;
   if (!*array) {
     const cudaChannelFormatDesc desc = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
     BBA_CUDA(h, cudaMallocArray(array, &desc, cw, ch, cudaArrayTextureGather));
@@ -1250,6 +1263,7 @@ bba_status MakeLumaTexture(bba_handle h, const uint8_t* device_rgba, size_t colo
   ++h->launches;
   BBA_CUDA(h, cudaGetLastError());
   BBA_CUDA(h, cudaMemcpy2DToArrayAsync(*array, 0, 0, h->luma_staging, h->luma_staging_pitch, cw, ch, cudaMemcpyDeviceToDevice, s));
+  BBA_CUDA(h, cudaEventRecord(h->luma_staging_free, s));
   if (!*tex_out) {
     cudaResourceDesc res;
     std::memset(&res, 0, sizeof(res));
@@ -1399,6 +1413,7 @@ void bba_destroy(bba_handle h) {
   cudaFree(h->d_cfactor);
   cudaFree(h->color_staging);
   cudaFree(h->luma_staging);
+  if (h->luma_staging_free) cudaEventDestroy(h->luma_staging_free);
   cudaFree(h->d_kfs);
   cudaFree(h->d_pose_est);
   cudaFree(h->d_acc);
@@ -2101,11 +2116,11 @@ bba_status bba_bundle_adjust(bba_handle h, const bba_ba_options* o, bba_ba_resul
   return BBA_OK;
 }
 
-bba_status bba_perform_end_tasks(bba_handle h, uint32_t* deleted, uint32_t* surfels_size, void* stream) {
+bba_status bba_perform_end_tasks(bba_handle h, int do_surfel_updates, uint32_t* deleted, uint32_t* surfels_size, void* stream) {
   if (!h) return BBA_ERR_INVALID_ARGUMENT;
   if (bba_status st = CheckSurfels(h)) return st;
   uint32_t d = 0;
-  if (bba_status st = PerformEndTasks(h, static_cast<cudaStream_t>(stream), &d)) return st;
+  if (bba_status st = PerformEndTasks(h, static_cast<cudaStream_t>(stream), &d, do_surfel_updates != 0)) return st;
   if (deleted) *deleted = d;
   if (surfels_size) *surfels_size = h->surfels_size;
   return BBA_OK;
@@ -2350,10 +2365,12 @@ bba_status bba_update_keyframe_host(bba_handle h, int id, const uint16_t* host_d
     }
     BBA_CUDA(h, cudaMemcpy2DAsync(dst, dst_pitch, host_color_rgba, static_cast<size_t>(cw) * 4,
                                   static_cast<size_t>(cw) * 4, ch, cudaMemcpyHostToDevice, s));
+    if (bba_status st = AcquireLumaStaging(h, s)) return st;
     bba::LaunchExtractLuma(dst, dst_pitch, h->luma_staging, h->luma_staging_pitch, cw, ch, s);
     ++h->launches;
     BBA_CUDA(h, cudaGetLastError());
     BBA_CUDA(h, cudaMemcpy2DToArrayAsync(kf.luma, 0, 0, h->luma_staging, h->luma_staging_pitch, cw, ch, cudaMemcpyDeviceToDevice, s));
+    BBA_CUDA(h, cudaEventRecord(h->luma_staging_free, s));
   }
   return BBA_OK;
 }

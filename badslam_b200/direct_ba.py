@@ -494,10 +494,12 @@ class DirectBA:
         self._check(self._lib.bba_compact_surfels(self._h, int(free_count), int(with_active_flags), C.byref(n), self._stream_ptr(stream)))
         return n.value
 
-    def PerformBASchemeEndTasks(self, stream=None):
-        """direct_ba.cc:566-653 (delete badly observed surfels, update radii, compact).  Returns (deleted, surfels_size)."""
+    def PerformBASchemeEndTasks(self, stream=None, do_surfel_updates: bool = False):
+        """direct_ba.cc:566-653 (with do_surfel_updates: merge similar surfels of the keyframes active in this BA block; then
+        delete badly observed surfels, update radii, compact).  Returns (deleted, surfels_size)."""
         d, n = C.c_uint32(), C.c_uint32()
-        self._check(self._lib.bba_perform_end_tasks(self._h, C.byref(d), C.byref(n), self._stream_ptr(stream)))
+        self._check(self._lib.bba_perform_end_tasks(self._h, int(bool(do_surfel_updates)), C.byref(d), C.byref(n),
+                                                    self._stream_ptr(stream)))
         return d.value, n.value
 
     def PCGDebug(self, optimize_poses=True, optimize_geometry=True, optimize_depth_intrinsics=False,

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BBA_ABI_VERSION 5
+#define BBA_ABI_VERSION 6
 
 typedef struct bba_context* bba_handle;
 
@@ -220,8 +220,10 @@ bba_status bba_optimize_geometry_iteration(bba_handle h, void* stream);
  * with fewer than GetMinObservationCount() observations, or more free-space violations than observations, are deleted; the
  * others get the smallest observed radius) + CompactSurfelsCUDA.  bba_bundle_adjust runs it like the reference does: at
  * the end when increase_ba_iteration_count is set, else at the start of the first call after the counter changed.
+ * do_surfel_updates (the reference's second argument, direct_ba.h:435-437): first merge similar surfels using every keyframe
+ * that was active in this BA iteration block (direct_ba.cc:577-601).
  * The keyframes' radius buffers must be valid.  *deleted / *surfels_size may be NULL. */
-bba_status bba_perform_end_tasks(bba_handle h, uint32_t* deleted, uint32_t* surfels_size, void* stream);
+bba_status bba_perform_end_tasks(bba_handle h, int do_surfel_updates, uint32_t* deleted, uint32_t* surfels_size, void* stream);
 /* surfels_size_ of the reference (the caller's buffer holds that many surfels at its front). */
 uint32_t bba_surfels_size(bba_handle h);
 /* ba_iteration_count_ / last_ba_iteration_count_ (direct_ba.h:373-377): the pair decides whether a call with

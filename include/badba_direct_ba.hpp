@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstddef>
 #include <cstring>
 #include <fstream>
 #include <functional>
@@ -23,6 +24,7 @@
 #include <vector>
 #include <stdexcept>
 #include <string>
+#include <utility>
 
 #include "badba.h"
 
@@ -45,6 +47,12 @@ template <typename T>
 struct MutableDeviceImage {
   T* address;
   size_t pitch_bytes;
+};
+
+// Stand-in for libvis' Timer (timing.h:114) when the caller passes none: BundleAdjustment is templated on the timer type and
+// only needs GetTimeSinceStart() (direct_ba_alternating.cc:703-709).
+struct NoTimer {
+  double GetTimeSinceStart() const { return 0; }
 };
 
 template <typename SE3f, typename PinholeCamera4f>
@@ -127,11 +135,12 @@ class DirectBA {
     std::memcpy(out_global_T_frame_estimate->data(), out, sizeof(out));
   }
 
-  // direct_ba.h:143-162, same argument order and defaults.
+  // direct_ba.h:143-162, same argument order and defaults (Timer* is any type with GetTimeSinceStart()).
+  template <typename TimerT = NoTimer>
   void BundleAdjustment(cudaStream_t stream, bool optimize_depth_intrinsics, bool optimize_color_intrinsics, bool do_surfel_updates,
                         bool optimize_poses, bool optimize_geometry, int min_iterations, int max_iterations, bool use_pcg,
                         int active_keyframe_window_start, int active_keyframe_window_end, bool increase_ba_iteration_count,
-                        int* iterations_done = nullptr, bool* converged = nullptr, double time_limit = 0, void* /*timer*/ = nullptr,
+                        int* iterations_done = nullptr, bool* converged = nullptr, double time_limit = 0, TimerT* timer = nullptr,
                         int pcg_max_inner_iterations = 30, int pcg_max_keyframes = 2500,
                         std::function<bool(int)> progress_function = nullptr) {
     bba_ba_options o{};
@@ -146,7 +155,14 @@ class DirectBA {
     o.active_keyframe_window_start = active_keyframe_window_start;
     o.active_keyframe_window_end = active_keyframe_window_end;
     o.increase_ba_iteration_count = increase_ba_iteration_count;
-    o.time_limit_seconds = time_limit;
+    // direct_ba_alternating.cc:703-709: the limit is tested only when a timer is given, against timer->GetTimeSinceStart(),
+    // i.e. counted from the timer's own start: hand the backend what is left of the budget at the time of the call
+    // (0 = no limit; an already exhausted budget still runs one iteration, like the reference's test at the loop's end).
+    o.time_limit_seconds = 0;
+    if (timer != nullptr) {
+      const double left = time_limit - timer->GetTimeSinceStart();
+      o.time_limit_seconds = left > 1e-9 ? left : 1e-9;
+    }
     o.pcg_max_inner_iterations = pcg_max_inner_iterations;
     o.pcg_max_keyframes = pcg_max_keyframes;
     o.pcg_gauge_keyframe = pcg_gauge_keyframe_;   // -1: rand() % K per iteration like direct_ba_pcg.cc:324
@@ -159,6 +175,19 @@ class DirectBA {
     if (iterations_done) *iterations_done = r.iterations_done;
     if (converged) *converged = r.converged != 0;
     last_result_ = r;
+  }
+
+  // ... and with a literal nullptr in the timer position (no type to deduce): no time limit, like the reference without a timer
+  void BundleAdjustment(cudaStream_t stream, bool optimize_depth_intrinsics, bool optimize_color_intrinsics, bool do_surfel_updates,
+                        bool optimize_poses, bool optimize_geometry, int min_iterations, int max_iterations, bool use_pcg,
+                        int active_keyframe_window_start, int active_keyframe_window_end, bool increase_ba_iteration_count,
+                        int* iterations_done, bool* converged, double time_limit, std::nullptr_t,
+                        int pcg_max_inner_iterations = 30, int pcg_max_keyframes = 2500,
+                        std::function<bool(int)> progress_function = nullptr) {
+    BundleAdjustment<NoTimer>(stream, optimize_depth_intrinsics, optimize_color_intrinsics, do_surfel_updates, optimize_poses,
+                              optimize_geometry, min_iterations, max_iterations, use_pcg, active_keyframe_window_start,
+                              active_keyframe_window_end, increase_ba_iteration_count, iterations_done, converged, time_limit,
+                              static_cast<NoTimer*>(nullptr), pcg_max_inner_iterations, pcg_max_keyframes, std::move(progress_function));
   }
 
   // direct_ba.h:114-117 (frame = an already added keyframe); returns the number of surfels created
@@ -185,8 +214,8 @@ class DirectBA {
   }
 
   // direct_ba.cc:566-653 (runs inside BundleAdjustment on the reference's schedule; exposed like the reference does)
-  void PerformBASchemeEndTasks(cudaStream_t stream) {
-    Check(bba_perform_end_tasks(h_, nullptr, nullptr, stream), "bba_perform_end_tasks");
+  void PerformBASchemeEndTasks(cudaStream_t stream, bool do_surfel_updates) {   // direct_ba.h:435-437
+    Check(bba_perform_end_tasks(h_, do_surfel_updates ? 1 : 0, nullptr, nullptr, stream), "bba_perform_end_tasks");
   }
 
   void GetKeyframePose(int keyframe_id, SE3f* global_T_frame) const {

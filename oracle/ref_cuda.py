@@ -32,7 +32,8 @@ class BAResult(C.Structure):
     _fields_ = [("iterations_done", C.c_int), ("converged", C.c_int), ("n_count", C.c_ulonglong), ("cost", C.c_double),
                 ("pose_iterations_total", C.c_int), ("ms_surfel_activation", C.c_float),
                 ("ms_geometry_optimization", C.c_float), ("ms_pose_optimization", C.c_float),
-                ("kernel_launches", C.c_ulonglong), ("surfels_deleted", C.c_uint), ("surfels_size", C.c_uint)]
+                ("kernel_launches", C.c_ulonglong), ("surfels_deleted", C.c_uint), ("surfels_size", C.c_uint),
+                ("n_depth_count", C.c_ulonglong)]
 
 
 class PCGOptions(C.Structure):

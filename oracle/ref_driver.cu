@@ -106,6 +106,8 @@ struct ref_ba_result {
   float ms_surfel_activation, ms_geometry_optimization, ms_pose_optimization;
   unsigned long long kernel_launches;
   unsigned int surfels_deleted, surfels_size;
+  unsigned long long n_depth_count;   // count_residuals == 2: the debug count of the same launches with the descriptor residuals
+                                      // off, i.e. the number of associated pairs (depth residuals) alone
 };
 
 struct ref_context {
@@ -232,7 +234,7 @@ void AccumulatePoseEstimationCoeffs(ref_context* c, int k, const float global_T_
 
 // direct_ba_alternating.cc:42-283
 int EstimateFramePose(ref_context* c, int k, const float init[7], float out[7], int* converged_out, bool debug_first,
-                      u32* first_count, float* first_sum) {
+                      u32* first_count, float* first_sum, u32* first_depth_count = nullptr) {
   float est[7];
   std::memcpy(est, init, sizeof(est));
   int converged = 0, iteration;
@@ -248,6 +250,15 @@ int EstimateFramePose(ref_context* c, int k, const float init[7], float out[7], 
       const bool dbg = debug_first && iteration == 0;
       AccumulatePoseEstimationCoeffs(c, k, est, dbg, &cnt, &sum, H, b);
       if (dbg) { *first_count = cnt; *first_sum = sum; }
+      if (dbg && first_depth_count && c->cfg.use_depth_residuals) {
+        // the same launch with the descriptor residuals switched off: its debug counter is the number of depth residuals
+        // (kernel_opt_pose.cu:312-320), which separates n_assoc from the n_assoc + n_photo the combined counter reports
+        float H2[21], b2[6], sum2 = 0;
+        const int desc = c->cfg.use_descriptor_residuals;
+        c->cfg.use_descriptor_residuals = 0;
+        AccumulatePoseEstimationCoeffs(c, k, est, true, first_depth_count, &sum2, H2, b2);
+        c->cfg.use_descriptor_residuals = desc;
+      }
       int idx = 0;
       for (int r = 0; r < 6; ++r)
         for (int cc = r; cc < 6; ++cc) Hd[r * 6 + cc] = H[idx++];
@@ -605,16 +616,19 @@ void ref_bundle_adjust(ref_context* c, const ref_ba_options* o, ref_ba_result* r
     int num_converged = 0;
     if (o->optimize_poses) {
       res->n_count = 0;
+      res->n_depth_count = 0;
       res->cost = 0;
       for (int k = 0; k < K; ++k) {
         RefKeyframe& kf = c->kfs[k];
         if (kf.activation == 2) { ++num_converged; continue; }
         float est[7], ftg[7], diff[7], lg[6];
         int conv;
-        u32 cnt = 0;
+        u32 cnt = 0, dcnt = 0;
         float sum = 0;
-        res->pose_iterations_total += EstimateFramePose(c, k, kf.pose, est, &conv, count_residuals != 0, &cnt, &sum);
+        res->pose_iterations_total +=
+            EstimateFramePose(c, k, kf.pose, est, &conv, count_residuals != 0, &cnt, &sum, count_residuals == 2 ? &dcnt : nullptr);
         res->n_count += cnt;
+        res->n_depth_count += dcnt;
         res->cost += sum;
         hm_se3_inverse(kf.pose, ftg);
         hm_se3_mul(ftg, est, diff);

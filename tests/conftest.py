@@ -12,6 +12,19 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`gpu`-marked tests are skipped (not errors) on a box without a CUDA device."""
+    if not any("gpu" in it.keywords for it in items):
+        return
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def tiny_scene():
     from badslam_b200.scene import config_by_name, make_scene

@@ -10,8 +10,7 @@ agrees, normals and radii must agree as well."""
 import numpy as np
 import pytest
 
-UNVALIDATED = ("written after the round-1 GPU budget was spent: first hardware run pending (XPASS = validated; remove this mark once it has passed on a B200)")
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason=UNVALIDATED)]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.fixture(scope="module")
@@ -59,7 +58,10 @@ def compare(got, want, rtf, depth_fraction, other_fraction, what, min_agree=0.5)
         assert max(np.abs(ax - bx).max(), np.abs(ay - by).max()) <= 1, what
         assert np.mean((ax != bx) | (ay != by)) <= other_fraction, (what, np.mean((ax != bx) | (ay != by)))
         ra, rb = gr[nb].view(np.float16).astype(np.float64), wr[nb].view(np.float16).astype(np.float64)
-        assert np.all(np.abs(ra - rb) <= 2.0 ** -9 * rb) and np.mean(ra != rb) <= other_fraction, what
+        # radius^2 is stored as an IEEE half: close surfaces give SUBNORMAL halves (pixel spacing 1.7 mm at 0.2 m: r^2 = 3e-6 =
+        # 50 units of 2^-24), where one rounding step is 2 % of the value -- the tolerance is two half ulps, normal or subnormal
+        assert np.all(np.abs(ra - rb) <= np.maximum(2.0 ** -9 * rb, 2.0 ** -23)), (what, np.abs(ra - rb).max())
+        assert np.mean(ra != rb) <= other_fraction, (what, np.mean(ra != rb))
     assert np.all(gn[0] == 0) and np.all(gn[:, 0] == 0)
     if wc is not None:
         assert np.array_equal(gc, wc), f"{what}: rgba / luma"
@@ -128,6 +130,26 @@ def test_ragged_and_tiny_images(mods, size):
     got = run_cuda(ba, raw, rgb)
     compare(got, ref.preprocess_frame(raw, rgb), sc.cfg.raw_to_float_depth, 2e-3, 2e-2, f"cuda vs reference kernels {size}")
     compare(got, O.Oracle(sc).preprocess_frame(raw, rgb), sc.cfg.raw_to_float_depth, 5e-2, 3e-2, f"cuda vs oracle {size}")
+
+
+def test_product_reproduces_the_reference_golden_fixture_bit_for_bit(mods):
+    """tests/golden/tiny_preprocess.npz holds the reference kernels' outputs (tools/make_golden.py --preprocess-only).  On the B200
+    the product agreed with the reference's -use_fast_math kernels bit for bit on every case measured (same SASS arithmetic),
+    so the fixture is demanded exactly: depth, normals, radii, luma, min / max depth."""
+    import os
+    S, DirectBA, O, R = mods
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiny_preprocess.npz"))
+    sc = S.make_scene(S.config_by_name("tiny"))
+    sc.depth_a = 0.02
+    sc.cfactor = (2e-3 * np.random.default_rng(5).random(sc.cfactor.shape)).astype(np.float32)
+    raw, rgb = S.raw_frame(sc, int(g["kf"]))
+    assert int(raw.astype(np.uint64).sum()) == int(g["raw_checksum"])
+    d, n, r, c, mn, mx = run_cuda(DirectBA.from_scene(sc), raw, rgb)
+    valid = (g["depth"] & 0x8000) == 0
+    assert np.array_equal(d, g["depth"])
+    assert np.array_equal(n[valid], g["normals"][valid]) and np.array_equal(r[valid], g["radius"][valid])
+    assert np.array_equal(c[..., 3], g["luma"])
+    assert mn == float(g["min_depth"]) and mx == float(g["max_depth"])
 
 
 def test_edge_cases_and_errors(mods):

@@ -5,8 +5,7 @@ BundleAdjustment calls on a growing map, the assertions are the reference's conv
 import numpy as np
 import pytest
 
-UNVALIDATED = ("written after the round-1 GPU budget was spent: first hardware run pending (XPASS = validated; remove this mark once it has passed on a B200)")
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason=UNVALIDATED)]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.fixture(scope="module")
