@@ -24,6 +24,10 @@
 #include "kernels.cuh"
 #include "preprocess_tile.cuh"
 
+#ifndef BBA_POSE_PRECOMPUTE
+#define BBA_POSE_PRECOMPUTE 1   // per-surfel frames (normal, tangent points) computed once per pose step (kernels.cuh LaunchSurfelFrames)
+#endif
+
 namespace {
 
 using bba::KfDevice;
@@ -169,6 +173,9 @@ struct bba_context {
 
   // device state sized for cfg.max_keyframes
   KfDevice* d_kfs = nullptr;
+  KfDevice* d_work_records = nullptr;   // [max_kf] the pose kernel's work list as contiguous records
+  float* d_frames = nullptr;            // [9][frames_pitch] per-surfel normal + tangent points, rebuilt at the start of a pose step
+  uint32_t frames_pitch = 0;
   float* d_pose_est = nullptr;
   double* d_acc = nullptr;
   unsigned long long* d_stage_counts = nullptr;
@@ -197,6 +204,10 @@ struct bba_context {
   double* h_acc = nullptr;        // one record (32) + 2 stage counts, for bba_accumulate_pose_coeffs
   cudaEvent_t staging_event = nullptr;
   bool staging_pending = false;
+  // Multi-GPU with mapped peers: set by every REPLICATED whole-buffer pass (surfel creation / merge / compaction / end tasks),
+  // cleared by the next collective.  The geometry kernels store into the other ranks' replicas; a rank must not start them
+  // while a slower rank is still reading or rewriting its whole replica in such a pass (PeerFence).
+  bool replicated_pass_pending = false;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
   bba_collective_fn collective = nullptr;
@@ -453,9 +464,29 @@ bba_status RunPoseStep(bba_handle h, const std::vector<int>& ids, const std::vec
   acc.pitch = static_cast<uint32_t>(h->surfel_pitch_bytes / sizeof(float));
   acc.n = h->surfels_size;
   acc.kfs = h->d_kfs;
+  acc.work_records = h->d_work_records;
   acc.acc = h->d_acc;
   acc.stage_counts = h->d_stage_counts;
   acc.queue = h->d_queue;
+  acc.frames = nullptr;
+  acc.frames_pitch = 0;
+  // The surfels do not move during a pose step: what the descriptor residual needs of a surfel alone (unpacked normal, the two
+  // tangent points) is computed once here instead of once per (surfel, keyframe, Gauss-Newton iteration) pair.  Not worth a
+  // launch + 9 rows of traffic for a handful of keyframes (frame tracking): the kernel then derives them per pair.
+  static const bool precompute = BBA_POSE_PRECOMPUTE && !std::getenv("BADBA_POSE_NO_PRECOMPUTE");   // (development switch for A/B runs)
+  if (precompute && h->cfg.use_descriptor_residuals && n_local >= 4 && h->surfels_size > 0) {
+    const uint32_t pitch = static_cast<uint32_t>(h->surfel_pitch_bytes / sizeof(float));
+    if (!h->d_frames || h->frames_pitch < pitch) {
+      cudaFree(h->d_frames);
+      h->d_frames = nullptr;
+      h->frames_pitch = pitch;
+      BBA_CUDA(h, cudaMalloc(&h->d_frames, sizeof(float) * 9 * static_cast<size_t>(pitch)));
+    }
+    bba::LaunchSurfelFrames(h->surfels, pitch, h->surfels_size, h->d_frames, h->frames_pitch, s);
+    ++h->launches;
+    acc.frames = h->d_frames;
+    acc.frames_pitch = h->frames_pitch;
+  }
   bba::PoseSolveArgs sol;
   sol.kfs = h->d_kfs;
   sol.pose_est = h->d_pose_est;
@@ -478,9 +509,9 @@ bba_status RunPoseStep(bba_handle h, const std::vector<int>& ids, const std::vec
     acc.work_count = h->d_count + cur;
     if (h->surfels_size > 0) {
       if (h->profiling && it < 32) BBA_CUDA(h, cudaEventRecord(h->prof_ev[2 * it], s));
-      bba::LaunchPoseAccumulate(acc, h->sm_count, /*with_stats=*/it == 0 || h->profiling >= 2, s);
+      bba::LaunchPoseAccumulate(acc, h->sm_count, /*with_stats=*/it == 0 || h->profiling >= 2, n_local, s);
       if (h->profiling && it < 32) BBA_CUDA(h, cudaEventRecord(h->prof_ev[2 * it + 1], s));
-      ++h->launches;
+      h->launches += 2;   // record packing + the kernel
     }
     sol.work_in = h->d_work[cur];
     sol.count_in = h->d_count + cur;
@@ -509,6 +540,7 @@ bba_status RunPoseStep(bba_handle h, const std::vector<int>& ids, const std::vec
                                h->d_pose_pack, s);
     ++h->launches;
     h->collective(h->collective_user, BBA_COLLECTIVE_ALLREDUCE_SUM, h->d_pose_pack, static_cast<size_t>(bba::kPoseSlot) * K, s);
+    h->replicated_pass_pending = false;   // (every rank's earlier work on this stream precedes its contribution)
     BBA_CUDA(h, cudaMemcpyAsync(h->h_pose_pack, h->d_pose_pack, sizeof(float) * bba::kPoseSlot * K, cudaMemcpyDeviceToHost, s));
   } else {
     BBA_CUDA(h, cudaMemcpyAsync(h->h_pose_est, h->d_pose_est, sizeof(float) * 7 * K, cudaMemcpyDeviceToHost, s));
@@ -614,7 +646,32 @@ void DetermineCovisibleActiveKeyframes(bba_handle h) {
   }
 }
 
+// A barrier across the ranks (1-element all-reduce) in front of kernels that write into the peers' replicas, needed only when a
+// replicated pass ran since the last collective.
+bba_status PeerFence(bba_handle h, cudaStream_t s) {
+  if (h->cfg.world_size <= 1 || !h->replicated_pass_pending) return BBA_OK;
+  h->replicated_pass_pending = false;
+  if (h->peers.count != h->cfg.world_size - 1) return BBA_OK;   // exchange through the host's collective: no remote stores
+  if (bba_status st = CheckCollective(h)) return st;
+  if (!h->d_barrier) BBA_CUDA(h, cudaMalloc(&h->d_barrier, sizeof(float)));
+  BBA_CUDA(h, cudaMemsetAsync(h->d_barrier, 0, sizeof(float), s));
+  h->collective(h->collective_user, BBA_COLLECTIVE_ALLREDUCE_SUM, h->d_barrier, 1, s);
+  return BBA_OK;
+}
+
+// Number of this rank's LOCAL surfel indices whose global index is below `global_end` (local -> global is monotonic).
+uint32_t LocalCountBelow(uint32_t global_end, int rank, int world) {
+  if (world <= 1) return global_end;
+  const uint32_t full = global_end >> 8, rest = global_end & 255u;   // granules completely below, surfels of the next one
+  const uint32_t w = static_cast<uint32_t>(world), r = static_cast<uint32_t>(rank);
+  uint32_t mine = full > r ? (full - r + w - 1) / w : 0;
+  uint32_t n = mine * 256u;
+  if (full % w == r) n += rest;
+  return n;
+}
+
 bba_status BuildGeometryArgs(bba_handle h, bba::GeometryArgs* g, cudaStream_t s) {
+  if (bba_status st = PeerFence(h, s)) return st;
   const int K = static_cast<int>(h->keyframes.size());
   int cnt = 0;
   for (int k = 0; k < K; ++k)
@@ -800,6 +857,7 @@ bba_status CreateSurfelsForKeyframe(bba_handle h, int k, bool filter, cudaStream
   const Keyframe& kf = h->keyframes[k];
   if (!kf.radius || !kf.rgba) return Fail(h, BBA_ERR_STATE, "surfel creation needs the keyframe's radius and colour buffers");
   BBA_TRACE("create: enter");
+  h->replicated_pass_pending = true;
   if (bba_status st = WaitStaging(h)) return st;
   bba::LifecycleArgs a;
   if (bba_status st = MakeLifecycleArgs(h, k, &a, s)) return st;
@@ -851,6 +909,7 @@ bba_status CreateSurfelsForKeyframe(bba_handle h, int k, bool filter, cudaStream
 bba_status MergeSurfelsForKeyframe(bba_handle h, int k, cudaStream_t s, uint32_t* deleted) {
   *deleted = 0;
   if (h->surfels_size == 0) return BBA_OK;
+  h->replicated_pass_pending = true;
   bba::LifecycleArgs a;
   if (bba_status st = MakeLifecycleArgs(h, k, &a, s)) return st;
   BBA_CUDA(h, cudaMemsetAsync(h->d_deleted_count, 0, sizeof(unsigned int), s));
@@ -866,6 +925,7 @@ bba_status MergeSurfelsForKeyframe(bba_handle h, int k, cudaStream_t s, uint32_t
 bba_status CompactSurfels(bba_handle h, uint32_t free_count, bool with_active, cudaStream_t s) {
   const uint32_t N = h->surfels_size;
   if (free_count == 0 || N == 0) return BBA_OK;
+  h->replicated_pass_pending = true;
   const uint32_t words = bba::CompactScratchWords(N);
   if (words > h->compact_sums_capacity) {
     cudaFree(h->d_compact_sums);
@@ -895,6 +955,7 @@ bba_status PerformEndTasks(bba_handle h, cudaStream_t s, uint32_t* deleted_out, 
   const int K = static_cast<int>(h->keyframes.size());
   const uint32_t N = h->surfels_size;
   if (N == 0) return BBA_OK;   // kernel_delete_surfels.cc:52-54
+  h->replicated_pass_pending = true;
   if (!h->d_kf_radius) {
     BBA_CUDA(h, cudaMalloc(&h->d_kf_radius, sizeof(bba::KfRadius) * h->cfg.max_keyframes));
     BBA_CUDA(h, cudaMallocHost(&h->h_kf_radius, sizeof(bba::KfRadius) * h->cfg.max_keyframes));
@@ -1351,6 +1412,7 @@ bba_status bba_create(const bba_config* cfg, bba_handle* out) {
   CREATE_TRY(cudaMalloc(&h->d_cfactor, sizeof(float) * h->cf_w * h->cf_h));
   CREATE_TRY(cudaMemset(h->d_cfactor, 0, sizeof(float) * h->cf_w * h->cf_h));
   CREATE_TRY(cudaMalloc(&h->d_kfs, sizeof(KfDevice) * K));
+  CREATE_TRY(cudaMalloc(&h->d_work_records, sizeof(KfDevice) * K));
   CREATE_TRY(cudaMalloc(&h->d_pose_est, sizeof(float) * 7 * K));
   CREATE_TRY(cudaMalloc(&h->d_acc, sizeof(double) * bba::kPoseAccSize * K));
   CREATE_TRY(cudaMemset(h->d_acc, 0, sizeof(double) * bba::kPoseAccSize * K));
@@ -1415,6 +1477,8 @@ void bba_destroy(bba_handle h) {
   cudaFree(h->luma_staging);
   if (h->luma_staging_free) cudaEventDestroy(h->luma_staging_free);
   cudaFree(h->d_kfs);
+  cudaFree(h->d_work_records);
+  cudaFree(h->d_frames);
   cudaFree(h->d_pose_est);
   cudaFree(h->d_acc);
   cudaFree(h->d_stage_counts);
@@ -1737,6 +1801,9 @@ bba_status bba_accumulate_pose_coeffs(bba_handle h, int id, const float pose[7],
   acc.pitch = static_cast<uint32_t>(h->surfel_pitch_bytes / sizeof(float));
   acc.n = h->surfels_size;
   acc.kfs = h->d_kfs;
+  acc.work_records = h->d_work_records;
+  acc.frames = nullptr;
+  acc.frames_pitch = 0;
   acc.acc = h->d_acc;
   acc.stage_counts = h->d_stage_counts;
   acc.queue = h->d_queue;
@@ -1744,8 +1811,8 @@ bba_status bba_accumulate_pose_coeffs(bba_handle h, int id, const float pose[7],
   acc.work_list = h->d_work[0];
   acc.work_count = h->d_count;
   if (h->surfels_size > 0) {
-    bba::LaunchPoseAccumulate(acc, h->sm_count, /*with_stats=*/true, s);
-    ++h->launches;
+    bba::LaunchPoseAccumulate(acc, h->sm_count, /*with_stats=*/true, 1, s);
+    h->launches += 2;   // record packing + the kernel
   }
   BBA_CUDA(h, cudaGetLastError());
   BBA_CUDA(h, cudaMemcpyAsync(h->h_acc, h->d_acc + static_cast<size_t>(id) * bba::kPoseAccSize, sizeof(double) * bba::kPoseAccSize,
@@ -1926,8 +1993,8 @@ bba_status bba_bundle_adjust(bba_handle h, const bba_ba_options* o, bba_ba_resul
   if (!h || !o || !res) return BBA_ERR_INVALID_ARGUMENT;
   std::memset(res, 0, sizeof(*res));
   if (bba_status st = CheckSurfels(h)) return st;
-  if (o->do_surfel_updates && h->cfg.world_size > 1)
-    return Fail(h, BBA_ERR_UNSUPPORTED, "do_surfel_updates is single-GPU only in this version");
+  // (do_surfel_updates with more than one rank: creation / merging / compaction run REPLICATED -- they are deterministic and
+  // every rank holds the whole surfel buffer -- while the geometry and pose steps stay sharded; see PeerFence)
   if (o->use_pcg) return BundleAdjustPCG(h, o, res, static_cast<cudaStream_t>(stream));   // direct_ba.cc:436-457
   // direct_ba.cc:427-434
   const bool opt_depth_intr = o->optimize_depth_intrinsics && h->cfg.use_depth_residuals;
@@ -1998,9 +2065,9 @@ bba_status bba_bundle_adjust(bba_handle h, const bba_ba_options* o, bba_ba_resul
     if (!whole_window) BBA_CUDA(h, cudaMemsetAsync(h->active, bba::kSurfelActiveFlag, old_surfels_size, s));
     if (h->surfels_size > 0) {
       if (whole_window && has_new) {
-        bba::GeometryArgs g_old = g, g_new = g;
-        g_old.end = old_surfels_size;
-        g_new.begin = old_surfels_size;
+        bba::GeometryArgs g_old = g, g_new = g;   // (begin / end are LOCAL indices of this rank's shard)
+        g_old.end = LocalCountBelow(old_surfels_size, h->cfg.rank, h->cfg.world_size);
+        g_new.begin = g_old.end;
         bba::LaunchActivationAndNormals(g_old, h->sm_count, true, true, s);
         bba::LaunchActivationAndNormals(g_new, h->sm_count, false, true, s);
         h->launches += 2;

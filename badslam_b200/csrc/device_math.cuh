@@ -74,6 +74,43 @@ __device__ __forceinline__ Vec3 Transform(const float* __restrict__ T, const Vec
             T[8] * p.x + T[9] * p.y + T[10] * p.z + T[11]);
 }
 
+// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2) -----------------------------------------------------------------
+// A pair of floats in an aligned 64-bit register.  Every operation rounds each half exactly like the scalar instruction
+// (IEEE rn, flush-to-zero like the -use_fast_math scalar code); one issue slot does the work of two.  Splat() operands become
+// the instructions' scalar-broadcast form (Ra.F32), so a scalar x pair product costs no extra move.
+struct F2 {
+  unsigned long long v;
+};
+__device__ __forceinline__ F2 Pack(float lo, float hi) {
+  F2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ F2 Splat(float s) { return Pack(s, s); }
+__device__ __forceinline__ void Unpack(F2 a, float* lo, float* hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(*lo), "=f"(*hi) : "l"(a.v)); }
+__device__ __forceinline__ float Lo(F2 a) { float lo, hi; Unpack(a, &lo, &hi); return lo; }
+__device__ __forceinline__ float Hi(F2 a) { float lo, hi; Unpack(a, &lo, &hi); return hi; }
+__device__ __forceinline__ F2 operator+(F2 a, F2 b) {
+  F2 r;
+  asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ F2 operator-(F2 a, F2 b) {
+  F2 r;
+  asm("sub.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ F2 operator*(F2 a, F2 b) {
+  F2 r;
+  asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ F2 Fma(F2 a, F2 b, F2 c) {   // a * b + c, fused
+  F2 r;
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
+
 // robust_weighting.cuh:39-86
 __device__ __forceinline__ float TukeyResidual(float r, float p) {
   if (fabsf(r) < p) {
@@ -138,6 +175,20 @@ __device__ __forceinline__ float RawToCalibratedDepth(float a, float cfactor, fl
 __device__ __forceinline__ uint16_t LoadPixelU16(const uint16_t* base, uint32_t pitch, int px, int py) {
   return __ldg(reinterpret_cast<const uint16_t*>(reinterpret_cast<const char*>(base) + static_cast<size_t>(py) * pitch) + px);
 }
+// The same read-only loads as `asm volatile`: the compiler must issue them where they are written.  Plain __ldg()s of the
+// pixel's depth / normal / cfactor get SUNK below the association's early-outs (seen in the SASS of the geometry kernels: depth,
+// then -- after the valid-depth branch -- cfactor, then -- after the depth tests -- the normal: three serial L2 round trips per
+// pair instead of one).
+__device__ __forceinline__ uint16_t LoadU16Now(const uint16_t* p) {
+  uint16_t v;
+  asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float LoadF32Now(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
 
 // Result of projecting one surfel into one keyframe.
 struct Assoc {
@@ -180,12 +231,12 @@ struct PixelLoads {
 __device__ __forceinline__ PixelLoads LoadPixel(const CameraParams& cam, const uint16_t* __restrict__ depth, uint32_t depth_pitch,
                                                 const uint16_t* __restrict__ normals, uint32_t normals_pitch, const Assoc& r) {
   PixelLoads l;
-  l.measured = LoadPixelU16(depth, depth_pitch, r.px, r.py);
-  l.kf_normal = LoadPixelU16(normals, normals_pitch, r.px, r.py);
+  l.measured = LoadU16Now(reinterpret_cast<const uint16_t*>(reinterpret_cast<const char*>(depth) + static_cast<size_t>(r.py) * depth_pitch) + r.px);
+  l.kf_normal = LoadU16Now(reinterpret_cast<const uint16_t*>(reinterpret_cast<const char*>(normals) + static_cast<size_t>(r.py) * normals_pitch) + r.px);
   // sparse cell of the pixel: exact integer division by multiplication with a precomputed reciprocal
   const unsigned int cell_x = (cam.cell == 1) ? static_cast<unsigned int>(r.px) : __umulhi(static_cast<unsigned int>(r.px), cam.cell_magic);
   const unsigned int cell_y = (cam.cell == 1) ? static_cast<unsigned int>(r.py) : __umulhi(static_cast<unsigned int>(r.py), cam.cell_magic);
-  l.cf = __ldg(cam.cfactor + cell_y * cam.cf_w + cell_x);
+  l.cf = LoadF32Now(cam.cfactor + cell_y * cam.cf_w + cell_x);
   return l;
 }
 
@@ -193,20 +244,24 @@ __device__ __forceinline__ PixelLoads LoadPixel(const CameraParams& cam, const u
 // facing tests, 3 associated.
 __device__ __forceinline__ int Associate(const CameraParams& cam, const float* __restrict__ T, const Vec3& n, const PixelLoads& l,
                                          Assoc* r) {
-  if (l.measured & kInvalidDepthBit) return 1;
+  // Written without early returns: every test is evaluated and the stage selected at the end, so that all three loaded values
+  // are consumed unconditionally.  With the reference's chain of early-outs the compiler sinks each load below the previous
+  // test (three serial L2 round trips per pair); ~99 % of the in-image pairs pass every test anyway.  The predicates are the
+  // reference's, including how they treat NaN (a comparison with NaN is false = "test passed", as in its `if (...) return`).
+  const bool invalid = (l.measured & kInvalidDepthBit) != 0;
   r->d = RawToCalibratedDepth(cam.a, l.cf, cam.raw_to_float, l.measured);
   r->ln = Rotate(T, n);
   r->nx = cam.fx_inv * r->px + cam.cx_inv;
   r->ny = cam.fy_inv * r->py + cam.cy_inv;
   const float stddev =
       (kDepthUncertaintyFactor * fabsf(r->ln.x * r->nx + r->ln.y * r->ny + r->ln.z) * (r->d * r->d)) / cam.baseline_fx;
-  if (fabsf(r->lp.z - r->d) > kDepthTukey * stddev) return 1;
+  const bool too_far = fabsf(r->lp.z - r->d) > kDepthTukey * stddev;
   // The reference tests (1 / |lp|) * dot(lp, ln) > 0 (surfel_projection_nvcc_only.cuh:104-108); for the finite,
   // positive |lp| of a point in front of the camera that is the sign of the dot product alone.
-  if (Dot(r->lp, r->ln) > 0) return 1;
+  const bool back_facing = Dot(r->lp, r->ln) > 0;
   r->kf_normal = l.kf_normal;
-  if (Dot(r->ln, U16ToImageSpaceNormal(l.kf_normal)) < kCosNormalCompat) return 2;
-  return 3;
+  const bool incompatible = Dot(r->ln, U16ToImageSpaceNormal(l.kf_normal)) < kCosNormalCompat;
+  return (invalid | too_far | back_facing) ? 1 : (incompatible ? 2 : 3);
 }
 
 // All three steps.  Returns 0 culled / outside, else the stage of Associate().
@@ -245,6 +300,28 @@ __device__ __forceinline__ void TangentProjections(const CameraParams& cam, cons
   Vec3 t2 = Cross(n, t1);
   t2 = (kTangentScaling * sqrtf(radius_sq / fmaxf(1e-12f, Dot(t2, t2)))) * t2;
   const Vec3 p2 = Transform(T, gp + t2);
+  *t2x = cam.cfx * (p2.x / p2.z) + cam.ccx;
+  *t2y = cam.cfy * (p2.y / p2.z) + cam.ccy;
+}
+
+
+// The pose-independent half of ComputeTangentProjections (cost_function.cuh:115-133): the two tangent points gp + t1, gp + t2 of
+// a surfel.  Same expressions as TangentProjections above (the pose kernel reads them precomputed per surfel, see
+// SurfelFramesKernel; only Transform + projection depend on the keyframe).
+__device__ __forceinline__ void TangentPoints(const Vec3& gp, const Vec3& n, float radius_sq, Vec3* q1, Vec3* q2) {
+  Vec3 t1 = Cross(n, (fabsf(n.x) > 0.9f) ? V3(0, 1, 0) : V3(1, 0, 0));
+  t1 = (kTangentScaling * sqrtf(radius_sq / fmaxf(1e-12f, Dot(t1, t1)))) * t1;
+  *q1 = gp + t1;
+  Vec3 t2 = Cross(n, t1);
+  t2 = (kTangentScaling * sqrtf(radius_sq / fmaxf(1e-12f, Dot(t2, t2)))) * t2;
+  *q2 = gp + t2;
+}
+__device__ __forceinline__ void ProjectTangentPoints(const CameraParams& cam, const float* __restrict__ T, const Vec3& q1, const Vec3& q2,
+                                                     float* t1x, float* t1y, float* t2x, float* t2y) {
+  const Vec3 p1 = Transform(T, q1);
+  *t1x = cam.cfx * (p1.x / p1.z) + cam.ccx;
+  *t1y = cam.cfy * (p1.y / p1.z) + cam.ccy;
+  const Vec3 p2 = Transform(T, q2);
   *t2x = cam.cfx * (p2.x / p2.z) + cam.ccx;
   *t2y = cam.cfy * (p2.y / p2.z) + cam.ccy;
 }
@@ -297,6 +374,105 @@ __device__ __forceinline__ void DescPoseJacobian(const CameraParams& cam, const 
   J[3] = ((ls.y * ls.y + z_sq) * gy + xy * gx) * inv_z_sq;
   J[4] = -((ls.x * ls.x + z_sq) * gx + xy * gy) * inv_z_sq;
   J[5] = -(ls.x * gy - ls.y * gx) * inv_z;
+}
+
+// ---- packed (fp32x2) forms of the post-association maths -------------------------------------------------------------------
+// The association itself (ProjectIntoImage / Associate above) stays scalar and textually identical to the reference, so that
+// which pairs associate does not depend on how the compiler pairs instructions.  Everything after it -- tangent-point
+// projection, sample coordinates, residuals, Jacobians, the rank-1 updates -- is 2-wide: the (x, y) components of an image
+// point, columns (c, c+1) of a Jacobian row, or the two descriptor residuals of a pair.
+
+// frame_T_global with the first two rows interleaved: c_k = (T[k], T[4 + k]), so that (x, y) of Transform(T, q) is three FFMA2.
+struct KfPairs {
+  F2 c0, c1, c2, c3;
+};
+__device__ __forceinline__ KfPairs MakeKfPairs(const float* __restrict__ T) {
+  KfPairs P;
+  P.c0 = Pack(T[0], T[4]);
+  P.c1 = Pack(T[1], T[5]);
+  P.c2 = Pack(T[2], T[6]);
+  P.c3 = Pack(T[3], T[7]);
+  return P;
+}
+__device__ __forceinline__ F2 TransformXY(const KfPairs& P, const Vec3& q) {   // cuda_matrix.cuh:104-112, rows 0 and 1
+  return Fma(P.c0, Splat(q.x), Fma(P.c1, Splat(q.y), Fma(P.c2, Splat(q.z), P.c3)));
+}
+
+// cost_function.cuh:115-136 -> the two tangent points' pixel positions (x, y) in the colour image
+__device__ __forceinline__ void TangentProjections2(const CameraParams& cam, const KfPairs& P, const float* __restrict__ T,
+                                                    const Vec3& gp, const Vec3& n, float radius_sq, F2* t1_pxy, F2* t2_pxy) {
+  Vec3 t1 = Cross(n, (fabsf(n.x) > 0.9f) ? V3(0, 1, 0) : V3(1, 0, 0));
+  t1 = (kTangentScaling * sqrtf(radius_sq / fmaxf(1e-12f, Dot(t1, t1)))) * t1;
+  Vec3 t2 = Cross(n, t1);
+  t2 = (kTangentScaling * sqrtf(radius_sq / fmaxf(1e-12f, Dot(t2, t2)))) * t2;
+  const Vec3 q1 = gp + t1, q2 = gp + t2;
+  const float z1 = T[8] * q1.x + T[9] * q1.y + T[10] * q1.z + T[11];
+  const float z2 = T[8] * q2.x + T[9] * q2.y + T[10] * q2.z + T[11];
+  const F2 cf = Pack(cam.cfx, cam.cfy), cc = Pack(cam.ccx, cam.ccy);
+  *t1_pxy = Fma(cf, TransformXY(P, q1) * Splat(1.0f / z1), cc);
+  *t2_pxy = Fma(cf, TransformXY(P, q2) * Splat(1.0f / z2), cc);
+}
+
+// SamplePoint for an (x, y) pair: the coordinate arithmetic is packed, the gradient uses the gather's (x, y, z, w) quad as is.
+__device__ __forceinline__ void SamplePoint2(cudaTextureObject_t tex, F2 xy, float* intensity, float* dx, float* dy) {
+  float mx, my;
+  Unpack(xy - Splat(0.5f), &mx, &my);
+  mx = fmaxf(0.f, mx);
+  my = fmaxf(0.f, my);
+  const float fx = floorf(mx), fy = floorf(my);
+  const F2 f = Pack(fx, fy);
+  float tx, ty, gx, gy, x, y;
+  Unpack(Pack(mx, my) - f, &tx, &ty);
+  Unpack(f + Splat(1.0f), &gx, &gy);
+  Unpack(xy, &x, &y);
+  const float4 g = tex2Dgather<float4>(tex, gx, gy, 0);
+  *intensity = tex2D<float>(tex, x, y);
+  *dx = (g.y - g.x) * ty + (g.z - g.w) * (1 - ty);
+  *dy = (g.y - g.z) * tx + (g.x - g.w) * (1 - tx);
+}
+
+struct DescEval2 {
+  F2 r;        // (r1, r2) raw residuals (cost_function.cuh:140-156)
+  F2 g1, g2;   // (d r_i / d px, d r_i / d py) (cost_function.cuh:250-253)
+};
+__device__ __forceinline__ void EvalDescriptor2(cudaTextureObject_t tex, F2 c_pxy, F2 t1_pxy, F2 t2_pxy, float d1, float d2, DescEval2* e) {
+  float intensity, t1i, t2i, cdx, cdy, t1dx, t1dy, t2dx, t2dy;
+  SamplePoint2(tex, c_pxy, &intensity, &cdx, &cdy);
+  SamplePoint2(tex, t1_pxy, &t1i, &t1dx, &t1dy);
+  SamplePoint2(tex, t2_pxy, &t2i, &t2dx, &t2dy);
+  const F2 k = Splat(180.f);
+  e->r = k * (Pack(t1i, t2i) - Splat(intensity)) - Pack(d1, d2);
+  const F2 cd = Pack(cdx, cdy);
+  e->g1 = k * (Pack(t1dx, t1dy) - cd);
+  e->g2 = k * (Pack(t2dx, t2dy) - cd);
+}
+
+// kernel_opt_pose.cu:96-142 for both descriptor residuals of a pair: everything that depends on the surfel position only is
+// built once; each residual's six Jacobian entries then cost 1 + 3 + 3 packed instructions.
+struct DescJacShared {
+  F2 x_xy, y_a, nb_y, nxy_nx, iz2_iz;
+  float neg_iz, iz2;
+};
+__device__ __forceinline__ DescJacShared MakeDescJacShared(const Vec3& ls) {
+  DescJacShared s;
+  const float iz = 1.f / ls.z, z_sq = ls.z * ls.z, xy = ls.x * ls.y;
+  s.iz2 = iz * iz;
+  s.neg_iz = -iz;
+  s.x_xy = Pack(ls.x, xy);
+  s.y_a = Pack(ls.y, ls.y * ls.y + z_sq);
+  s.nb_y = Pack(-(ls.x * ls.x + z_sq), ls.y);
+  s.nxy_nx = Pack(-xy, -ls.x);
+  s.iz2_iz = Pack(s.iz2, iz);
+  return s;
+}
+// g = (gx, gy) of one residual -> (J0, J1), (J2, J3), (J4, J5)
+__device__ __forceinline__ void DescPoseJacobian2(const CameraParams& cam, const DescJacShared& s, F2 g, F2* J01, F2* J23, F2* J45) {
+  g = g * Pack(cam.cfx, cam.cfy);
+  float gx, gy;
+  Unpack(g, &gx, &gy);
+  *J01 = g * Splat(s.neg_iz);
+  *J23 = Fma(Splat(gx), s.x_xy, Splat(gy) * s.y_a) * Splat(s.iz2);
+  *J45 = Fma(Splat(gy), s.nxy_nx, Splat(gx) * s.nb_y) * s.iz2_iz;
 }
 
 }  // namespace bba

@@ -33,6 +33,9 @@ __device__ __forceinline__ void FenceBarrierInit() { asm volatile("fence.mbarrie
 __device__ __forceinline__ void MbarArriveExpectTx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(SmemAddr(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void MbarArrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(SmemAddr(bar)) : "memory");
+}
 __device__ __forceinline__ void MbarWait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -64,6 +67,35 @@ struct KfRegs {
   int activation;
 };
 
+// The same record from shared memory (staged by the TMA engine together with the surfel tile).  Returns the keyframe id (pad).
+__device__ __forceinline__ int LoadKfShared(const KfDevice* rec, KfRegs* r) {
+  const float4* p = reinterpret_cast<const float4*>(rec);
+  const float4 a = p[0], b = p[1], c = p[2];
+  r->T[0] = a.x; r->T[1] = a.y; r->T[2] = a.z; r->T[3] = a.w;
+  r->T[4] = b.x; r->T[5] = b.y; r->T[6] = b.z; r->T[7] = b.w;
+  r->T[8] = c.x; r->T[9] = c.y; r->T[10] = c.z; r->T[11] = c.w;
+  const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(p + 3);
+  r->depth = reinterpret_cast<const uint16_t*>(q.x);
+  r->normals = reinterpret_cast<const uint16_t*>(q.y);
+  const ulonglong2 q2 = *reinterpret_cast<const ulonglong2*>(p + 4);
+  r->tex = static_cast<cudaTextureObject_t>(q2.x);
+  r->depth_pitch = static_cast<uint32_t>(q2.y & 0xffffffffu);
+  r->normals_pitch = static_cast<uint32_t>(q2.y >> 32);
+  const int2 tail = *reinterpret_cast<const int2*>(p + 5);
+  r->activation = tail.x;
+  return tail.y;
+}
+
+// A texture handle that is the same in every lane, said in a way ptxas can see (a shuffle from lane 0): without it every
+// TEX / TLD4 is wrapped in a per-lane "waterfall" loop (R2UR + predicated fetch + BRA.U.ANY, ~8 extra instructions per fetch).
+// Must be called by all 32 lanes.
+__device__ __forceinline__ cudaTextureObject_t UniformTexture(cudaTextureObject_t tex) {
+  const unsigned long long t = tex;
+  const unsigned lo = __shfl_sync(0xffffffffu, static_cast<unsigned>(t), 0);
+  const unsigned hi = __shfl_sync(0xffffffffu, static_cast<unsigned>(t >> 32), 0);
+  return (static_cast<unsigned long long>(hi) << 32) | lo;
+}
+
 __device__ __forceinline__ void LoadKf(const KfDevice* __restrict__ kfs, int kf, KfRegs* r) {
   const float4* p = reinterpret_cast<const float4*>(kfs + kf);
   const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
@@ -80,6 +112,11 @@ __device__ __forceinline__ void LoadKf(const KfDevice* __restrict__ kfs, int kf,
   r->activation = __ldg(reinterpret_cast<const int*>(p + 5));
 }
 
+#ifndef BBA_POSE_FFMA2
+#define BBA_POSE_FFMA2 1   // packed fp32x2 arithmetic (sm_100 FFMA2 / FMUL2) for the rank-1 updates of H and b
+#endif
+
+#if !BBA_POSE_FFMA2
 // H += w J^T J (upper triangle, row-major), b += w r J   (gauss_newton.cuh:59-92, per thread)
 __device__ __forceinline__ void AccumulateHb(float (&acc)[kPoseAccSize], const float (&J)[6], float raw, float w) {
   int idx = 0;
@@ -93,6 +130,81 @@ __device__ __forceinline__ void AccumulateHb(float (&acc)[kPoseAccSize], const f
 #pragma unroll
   for (int i = 0; i < 6; ++i) acc[21 + i] += wr * J[i];
 }
+__device__ __forceinline__ int AccSlot(int lane) { return lane; }
+#else
+// The same update with packed fp32x2 instructions (fma.rn.f32x2 / mul.rn.f32x2 -> SASS FFMA2 / FMUL2): each instruction
+// updates two adjacent coefficients.  The per-lane accumulators are kept in a PAIR-ALIGNED order --
+//   0..5  H00 H01 H02 H03 H04 H05 | 6..9 H12 H13 H14 H15 | 10..13 H22 H23 H24 H25 | 14,15 H34 H35 | 16,17 H44 H45 |
+//   18..23 b0..b5 | 24 H11  25 H33  26 H55 | 27..31 statistics
+// -- so that every row of the upper triangle is a run of (even, odd) column pairs of J plus at most one leading diagonal
+// element; AccSlot() maps the order back to the row-major upper triangle + b the solver reads (gauss_newton.cuh:59-92).
+// 12 FFMA2 + 3 FMUL2 + 3 FFMA + 1 FMUL per residual instead of 27 FFMA + 7 FMUL; each product / sum is rounded exactly as in the
+// scalar form.
+typedef unsigned long long F32x2;
+__device__ __forceinline__ F32x2 Pack2(float lo, float hi) {
+  F32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void Unpack2(F32x2 v, float* lo, float* hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(*lo), "=f"(*hi) : "l"(v)); }
+__device__ __forceinline__ F32x2 Mul2(F32x2 a, F32x2 b) {
+  F32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ void Fma2(float* lo, float* hi, F32x2 a, F32x2 b) {   // (*lo, *hi) += a * b
+  F32x2 c = Pack2(*lo, *hi);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+  Unpack2(c, lo, hi);
+}
+__device__ __forceinline__ void AccumulateHbPacked(float (&acc)[kPoseAccSize], F32x2 J01, F32x2 J23, F32x2 J45, float raw, float w);
+__device__ __forceinline__ void AccumulateHb(float (&acc)[kPoseAccSize], const float (&J)[6], float raw, float w) {
+  AccumulateHbPacked(acc, Pack2(J[0], J[1]), Pack2(J[2], J[3]), Pack2(J[4], J[5]), raw, w);
+}
+__device__ __forceinline__ void AccumulateHbPacked(float (&acc)[kPoseAccSize], F32x2 J01, F32x2 J23, F32x2 J45, float raw, float w) {
+  float J[6];
+  Unpack2(J01, &J[0], &J[1]);
+  Unpack2(J23, &J[2], &J[3]);
+  Unpack2(J45, &J[4], &J[5]);
+  const F32x2 ww = Pack2(w, w);
+  float wj[6];
+  Unpack2(Mul2(ww, J01), &wj[0], &wj[1]);
+  Unpack2(Mul2(ww, J23), &wj[2], &wj[3]);
+  Unpack2(Mul2(ww, J45), &wj[4], &wj[5]);
+  const F32x2 d0 = Pack2(wj[0], wj[0]), d1 = Pack2(wj[1], wj[1]), d2 = Pack2(wj[2], wj[2]), d3 = Pack2(wj[3], wj[3]),
+              d4 = Pack2(wj[4], wj[4]);
+  Fma2(&acc[0], &acc[1], d0, J01);
+  Fma2(&acc[2], &acc[3], d0, J23);
+  Fma2(&acc[4], &acc[5], d0, J45);
+  acc[24] += wj[1] * J[1];
+  Fma2(&acc[6], &acc[7], d1, J23);
+  Fma2(&acc[8], &acc[9], d1, J45);
+  Fma2(&acc[10], &acc[11], d2, J23);
+  Fma2(&acc[12], &acc[13], d2, J45);
+  acc[25] += wj[3] * J[3];
+  Fma2(&acc[14], &acc[15], d3, J45);
+  Fma2(&acc[16], &acc[17], d4, J45);
+  acc[26] += wj[5] * J[5];
+  const float wr = w * raw;
+  const F32x2 dr = Pack2(wr, wr);
+  Fma2(&acc[18], &acc[19], dr, J01);
+  Fma2(&acc[20], &acc[21], dr, J23);
+  Fma2(&acc[22], &acc[23], dr, J45);
+}
+// accumulator index in the pair-aligned order -> index in the solver's order (21 upper-triangle coefficients row-major, 6 b, 5 stats)
+__device__ __forceinline__ int AccSlot(int lane) {
+  //            H00 H01 H02 H03 H04 H05 H12 H13 H14 H15 H22 H23 H24 H25 H34 H35 H44 H45 b0  b1  b2  b3  b4  b5 H11 H33 H55
+  constexpr unsigned long long lo = 0x0ull | (1ull << 5) | (2ull << 10) | (3ull << 15) | (4ull << 20) | (5ull << 25) | (7ull << 30) |
+                                    (8ull << 35) | (9ull << 40) | (10ull << 45) | (11ull << 50) | (12ull << 55);   // slots 0..11
+  constexpr unsigned long long mid = 13ull | (14ull << 5) | (16ull << 10) | (17ull << 15) | (18ull << 20) | (19ull << 25) | (21ull << 30) |
+                                     (22ull << 35) | (23ull << 40) | (24ull << 45) | (25ull << 50) | (26ull << 55);   // slots 12..23
+  constexpr unsigned long long hi = 6ull | (15ull << 5) | (20ull << 10);                                               // slots 24..26
+  if (lane < 12) return static_cast<int>((lo >> (5 * lane)) & 31u);
+  if (lane < 24) return static_cast<int>((mid >> (5 * (lane - 12))) & 31u);
+  if (lane < 27) return static_cast<int>((hi >> (5 * (lane - 24))) & 31u);
+  return lane;
+}
+#endif
 
 // Sums acc[i] over the 32 lanes of the warp for all 32 i at once: after the call lane L holds the total of
 // acc[L].  16+8+4+2+1 = 31 shuffles instead of 32 x 5.
@@ -117,9 +229,32 @@ __device__ __forceinline__ float WarpTransposeReduce(float (&v)[32], int lane) {
 #ifndef BBA_POSE_MIN_CTAS
 #define BBA_POSE_MIN_CTAS 2   // resident CTAs per SM the register allocation is tuned for
 #endif
-constexpr int kPoseThreads = 256;
+// 2-wide (fp32x2) post-association maths (device_math.cuh: tangent points, sample coordinates, Jacobians).  OFF: measured on
+// B200 it does not shorten the kernel (3.7145 vs 3.7148 ms per launch: the kernel is bound by dependent-issue latency at 4 warps
+// per scheduler, not by the instruction count), and it rounds the texture sample coordinates differently from the reference's
+// compiled expressions -- the texture unit quantises the filter fraction to 1/256 pixel, so a last-bit change of a coordinate
+// flips the filter weights of ~1 % of the samples (residual changes of up to ~0.5 of +-180).  In the geometry kernel that cost
+// the bit-exact agreement of the surfel positions with the reference (errors up to 9e-5 m on 0.07 % of the surfels).
+#ifndef BBA_POSE_PACKED
+#define BBA_POSE_PACKED 0
+#endif
+#ifndef BBA_GEO_PACKED
+#define BBA_GEO_PACKED 0
+#endif
+#ifndef BBA_POSE_CHUNK_SHIFT
+#define BBA_POSE_CHUNK_SHIFT 8
+#endif
+constexpr int kPoseChunkShift = BBA_POSE_CHUNK_SHIFT;   // log2 of the surfels one warp evaluates per (keyframe) sub-item
+#ifndef BBA_POSE_NOBARRIER
+#define BBA_POSE_NOBARRIER 1   // item loop without a CTA-wide barrier (the last warp out of a stage re-arms it)
+#endif
+#ifndef BBA_POSE_THREADS
+#define BBA_POSE_THREADS 256
+#endif
+constexpr int kPoseThreads = BBA_POSE_THREADS;
 constexpr int kPoseUnroll = BBA_POSE_UNROLL;   // surfels of a chunk evaluated concurrently per lane
 constexpr int kPoseStagedRows = 7;   // x y z normal radius^2 d1 d2
+constexpr int kPoseStagedRowsPre = 14;   // x y z d1 d2 + the 9 frame rows (normal, tangent point 1, tangent point 2)
 constexpr int kPoseGroup = 8;        // keyframes per work item
 
 // Work decomposition.  A work ITEM is (group of <= 8 keyframes from the work list) x (tile of TILE surfels); items are
@@ -129,10 +264,13 @@ constexpr int kPoseGroup = 8;        // keyframes per work item
 // evens out the very different cost of culled vs. associated chunks.
 // STATS: also produce the residual costs and the stage counters of the byte model (the reference computes its
 // residual count / cost only in debug mode, kernel_opt_pose.cu:312-320,373-381).
-template <int TILE, bool STATS>
+// PRE: the per-surfel frames (unpacked normal, tangent points) are staged instead of the packed normal and the radius.
+template <int TILE, bool STATS, bool PRE>
 __global__ void __launch_bounds__(kPoseThreads, BBA_POSE_MIN_CTAS) PoseAccumulateKernel(const __grid_constant__ PoseAccumulateArgs args) {
+  constexpr int kRows = PRE ? kPoseStagedRowsPre : kPoseStagedRows;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* stage_base = reinterpret_cast<float*>(smem_raw);   // [2][7][TILE]
+  float* stage_base = reinterpret_cast<float*>(smem_raw);   // [2][kRows][TILE]
+  __shared__ __align__(16) KfDevice s_kf[2][kPoseGroup];   // the work group's keyframe records, staged with the tile
   __shared__ __align__(8) uint64_t full_bar[2];
   __shared__ unsigned int s_item[2];
   __shared__ int s_sub[2];
@@ -146,25 +284,71 @@ __global__ void __launch_bounds__(kPoseThreads, BBA_POSE_MIN_CTAS) PoseAccumulat
   const uint32_t n_groups = (n_work + kPoseGroup - 1) / kPoseGroup;
   const uint32_t n_items = n_groups * n_tiles;
   // 256-surfel chunks (one warp-level reduction per 8 steps); 128 when there are few keyframes so that all warps get work
-  const int chunk_shift = (n_work >= 4) ? 8 : 7;
+  constexpr int kTileShift = (TILE == 1024) ? 10 : (TILE == 512) ? 9 : 8;
+  const int chunk_shift = (n_work >= 4) ? (kPoseChunkShift < kTileShift ? kPoseChunkShift : kTileShift) : 7;
   const uint32_t chunk_len = 1u << chunk_shift;
   const int chunks_per_tile = TILE >> chunk_shift;
 
   const CameraParams& cam = args.cam;
   constexpr int kRowIds[kPoseStagedRows] = {kRowX, kRowY, kRowZ, kRowNormal, kRowRadiusSq, kRowD1, kRowD2};
 
-  auto issue_tile = [&](uint32_t tile, int s) {
+  auto issue_tile = [&](uint32_t item, int s) {
+    const uint32_t group = item / n_tiles, tile = item - group * n_tiles;
     const uint32_t base = tile * TILE;
     const uint32_t cnt = min(static_cast<uint32_t>(TILE), args.n - base);
     const uint32_t bytes = ((cnt * 4u + 15u) / 16u) * 16u;
-    MbarArriveExpectTx(&full_bar[s], bytes * kPoseStagedRows);
+    const uint32_t kf_bytes = static_cast<uint32_t>(sizeof(KfDevice)) * min(kPoseGroup, n_work - static_cast<int>(group) * kPoseGroup);
+    MbarArriveExpectTx(&full_bar[s], bytes * kRows + kf_bytes);
+    BulkCopyG2S(&s_kf[s][0], args.work_records + static_cast<size_t>(group) * kPoseGroup, kf_bytes, &full_bar[s]);
+    if (PRE) {
+      constexpr int kPreRowIds[5] = {kRowX, kRowY, kRowZ, kRowD1, kRowD2};
 #pragma unroll
-    for (int r = 0; r < kPoseStagedRows; ++r) {
-      BulkCopyG2S(stage_base + (s * kPoseStagedRows + r) * TILE,
-                  args.surfels + static_cast<size_t>(kRowIds[r]) * args.pitch + base, bytes, &full_bar[s]);
+      for (int r = 0; r < 5; ++r)
+        BulkCopyG2S(stage_base + (s * kRows + r) * TILE, args.surfels + static_cast<size_t>(kPreRowIds[r]) * args.pitch + base, bytes,
+                    &full_bar[s]);
+#pragma unroll
+      for (int r = 0; r < 9; ++r)
+        BulkCopyG2S(stage_base + (s * kRows + 5 + r) * TILE, args.frames + static_cast<size_t>(r) * args.frames_pitch + base, bytes,
+                    &full_bar[s]);
+    } else {
+#pragma unroll
+      for (int r = 0; r < kPoseStagedRows; ++r) {
+        BulkCopyG2S(stage_base + (s * kRows + r) * TILE,
+                    args.surfels + static_cast<size_t>(kRowIds[r]) * args.pitch + base, bytes, &full_bar[s]);
+      }
     }
   };
 
+#if BBA_POSE_NOBARRIER
+  // No CTA-wide barrier in the item loop: a warp that has run out of sub-items of stage s moves on to stage s ^ 1 at once.
+  // The LAST warp to leave a stage (shared-memory counter) re-arms it: claims the next item, resets the sub-item counter and
+  // starts the TMA copies; everybody else finds the stage ready through its mbarrier phase.  When the queue is exhausted the
+  // stage gets a sentinel item and a plain arrive, so that the waiting warps wake up and leave.
+  __shared__ int s_done[2];
+  constexpr int kWarps = kPoseThreads / 32;
+  auto arm_stage = [&](int s) {   // one thread
+    s_sub[s] = 0;
+    s_done[s] = 0;
+    const unsigned int item = atomicAdd(args.queue, 1u);
+    s_item[s] = item;
+    if (item < n_items) issue_tile(item, s);
+    else MbarArrive(&full_bar[s]);
+  };
+  if (tid == 0) {
+    MbarInit(&full_bar[0], 1);
+    MbarInit(&full_bar[1], 1);
+    FenceBarrierInit();
+    arm_stage(0);
+    arm_stage(1);
+  }
+  __syncthreads();
+
+  for (uint32_t it = 0;; ++it) {
+    const int s = it & 1;
+    MbarWait(&full_bar[s], (it >> 1) & 1);
+    const unsigned int item = *reinterpret_cast<volatile unsigned int*>(&s_item[s]);
+    if (item >= n_items) break;
+#else
   if (tid == 0) {
     MbarInit(&full_bar[0], 1);
     MbarInit(&full_bar[1], 1);
@@ -173,7 +357,7 @@ __global__ void __launch_bounds__(kPoseThreads, BBA_POSE_MIN_CTAS) PoseAccumulat
     s_sub[1] = 0;
     const unsigned int first = atomicAdd(args.queue, 1u);
     s_item[0] = first;
-    if (first < n_items) issue_tile(first % n_tiles, 0);
+    if (first < n_items) issue_tile(first, 0);
   }
   __syncthreads();
 
@@ -185,17 +369,20 @@ __global__ void __launch_bounds__(kPoseThreads, BBA_POSE_MIN_CTAS) PoseAccumulat
       // stage s^1 was released by the __syncthreads that ended the previous iteration
       const unsigned int next = atomicAdd(args.queue, 1u);
       s_item[s ^ 1] = next;
-      if (next < n_items) issue_tile(next % n_tiles, s ^ 1);
+      if (next < n_items) issue_tile(next, s ^ 1);
     }
     MbarWait(&full_bar[s], (it >> 1) & 1);
+#endif
 
-    const float* sx = stage_base + (s * kPoseStagedRows + 0) * TILE;
+    // staged rows: x y z normal radius^2 d1 d2, or (PRE) x y z d1 d2 + 9 frame rows
+    const float* sx = stage_base + (s * kRows + 0) * TILE;
     const float* sy = sx + TILE;
     const float* sz = sy + TILE;
-    const float* sn = sz + TILE;
-    const float* sr = sn + TILE;
-    const float* sd1 = sr + TILE;
+    const float* sn = sz + TILE;                 // !PRE: packed normal
+    const float* sr = sn + TILE;                 // !PRE: radius^2
+    const float* sd1 = PRE ? sz + TILE : sr + TILE;
     const float* sd2 = sd1 + TILE;
+    const float* sf = sd2 + TILE;                // PRE: nx ny nz q1x q1y q1z q2x q2y q2z
     const uint32_t group = item / n_tiles;
     const uint32_t tile = item - group * n_tiles;
     const uint32_t base = tile * TILE;
@@ -212,10 +399,13 @@ __global__ void __launch_bounds__(kPoseThreads, BBA_POSE_MIN_CTAS) PoseAccumulat
       const uint32_t j0 = static_cast<uint32_t>(sub - kf_local * chunks_per_tile) << chunk_shift;
       if (j0 >= cnt) continue;
       const uint32_t j1 = min(cnt, j0 + chunk_len);
-      const int kf = __ldg(args.work_list + group * kPoseGroup + kf_local);
       KfRegs K;
-      LoadKf(args.kfs, kf, &K);
+      const int kf = LoadKfShared(&s_kf[s][kf_local], &K);
+      K.tex = UniformTexture(K.tex);
 
+#if BBA_POSE_PACKED
+      const KfPairs KP = MakeKfPairs(K.T);
+#endif
       float acc[kPoseAccSize];
 #pragma unroll
       for (int i = 0; i < kPoseAccSize; ++i) acc[i] = 0.f;
@@ -227,7 +417,11 @@ __global__ void __launch_bounds__(kPoseThreads, BBA_POSE_MIN_CTAS) PoseAccumulat
         int st = 0;
         Assoc r;
         Vec3 gp, nrm;
+#if BBA_POSE_PACKED
+        DescEval2 e2;
+#else
         DescEval e;
+#endif
         bool photo = false;
         if (j < j1) {
           gp = V3(sx[j], sy[j], sz[j]);
@@ -236,13 +430,28 @@ __global__ void __launch_bounds__(kPoseThreads, BBA_POSE_MIN_CTAS) PoseAccumulat
             // cfactor, and -- speculatively, ~99 % of in-image pairs end up associated -- the six texture fetches of
             // the descriptor residual.  The association tests below then wait for the slowest load once.
             const PixelLoads l = LoadPixel(cam, K.depth, K.depth_pitch, K.normals, K.normals_pitch, r);
-            nrm = UnpackNormal(__float_as_uint(sn[j]));
+            nrm = PRE ? V3(sf[j], sf[TILE + j], sf[2 * TILE + j]) : UnpackNormal(__float_as_uint(sn[j]));
             if (cam.use_desc) {
+#if BBA_POSE_PACKED
+              const F2 c_pxy = Fma(Pack(cam.d2c_fx, cam.d2c_fy), Pack(r.pxf, r.pyf), Pack(cam.d2c_cx, cam.d2c_cy));   // DepthToColor
+              float ccx, ccy;
+              Unpack(c_pxy, &ccx, &ccy);
+              photo = ccx >= 0 && ccy >= 0 && static_cast<int>(ccx) < cam.cw && static_cast<int>(ccy) < cam.ch;
+              F2 t1, t2;
+              TangentProjections2(cam, KP, K.T, gp, nrm, sr[j], &t1, &t2);
+              EvalDescriptor2(K.tex, c_pxy, t1, t2, sd1[j], sd2[j], &e2);
+#else
               float ccx, ccy;
               photo = DepthToColor(cam, r.pxf, r.pyf, &ccx, &ccy);
               float t1x, t1y, t2x, t2y;
-              TangentProjections(cam, K.T, gp, nrm, sr[j], &t1x, &t1y, &t2x, &t2y);
+              if (PRE) {
+                ProjectTangentPoints(cam, K.T, V3(sf[3 * TILE + j], sf[4 * TILE + j], sf[5 * TILE + j]),
+                                     V3(sf[6 * TILE + j], sf[7 * TILE + j], sf[8 * TILE + j]), &t1x, &t1y, &t2x, &t2y);
+              } else {
+                TangentProjections(cam, K.T, gp, nrm, sr[j], &t1x, &t1y, &t2x, &t2y);
+              }
               EvalDescriptor(K.tex, ccx, ccy, t1x, t1y, t2x, t2y, sd1[j], sd2[j], &e);
+#endif
             }
             st = Associate(cam, K.T, nrm, l, &r);
           }
@@ -256,12 +465,19 @@ __global__ void __launch_bounds__(kPoseThreads, BBA_POSE_MIN_CTAS) PoseAccumulat
         touched |= assoc_mask;
         if (st == 3) {
           acc[27] += 1.f;
-          float J[6];
           if (cam.use_depth) {
             float inv_stddev;
             Vec3 up;
             const float raw = DepthResidual(cam, r, &inv_stddev, &up);
             // kernel_opt_pose.cu:88-93
+#if BBA_POSE_PACKED
+            const F2 inv2 = Splat(inv_stddev);
+            const F2 J01 = inv2 * Pack(r.ln.x, r.ln.y);
+            const F2 J23 = inv2 * Pack(r.ln.z, -r.ln.y * up.z + r.ln.z * up.y);
+            const F2 J45 = inv2 * Pack(r.ln.x * up.z - r.ln.z * up.x, -r.ln.x * up.y + r.ln.y * up.x);
+            AccumulateHbPacked(acc, J01.v, J23.v, J45.v, raw, DepthWeight(raw));
+#else
+            float J[6];
             J[0] = inv_stddev * r.ln.x;
             J[1] = inv_stddev * r.ln.y;
             J[2] = inv_stddev * r.ln.z;
@@ -269,10 +485,26 @@ __global__ void __launch_bounds__(kPoseThreads, BBA_POSE_MIN_CTAS) PoseAccumulat
             J[4] = inv_stddev * (r.ln.x * up.z - r.ln.z * up.x);
             J[5] = inv_stddev * (-r.ln.x * up.y + r.ln.y * up.x);
             AccumulateHb(acc, J, raw, DepthWeight(raw));
+#endif
             if (STATS) acc[29] += DepthCost(raw);
           }
           if (cam.use_desc && photo) {
             acc[28] += 1.f;
+#if BBA_POSE_PACKED
+            const DescJacShared js = MakeDescJacShared(r.lp);
+            float r1, r2;
+            Unpack(e2.r, &r1, &r2);
+            F2 J01, J23, J45;
+            DescPoseJacobian2(cam, js, e2.g1, &J01, &J23, &J45);
+            AccumulateHbPacked(acc, J01.v, J23.v, J45.v, r1, DescWeight(r1));
+            DescPoseJacobian2(cam, js, e2.g2, &J01, &J23, &J45);
+            AccumulateHbPacked(acc, J01.v, J23.v, J45.v, r2, DescWeight(r2));
+            if (STATS) {
+              acc[30] += DescCost(r1);
+              acc[31] += DescCost(r2);
+            }
+#else
+            float J[6];
             DescPoseJacobian(cam, r.lp, e.gx1, e.gy1, J);
             AccumulateHb(acc, J, e.r1, DescWeight(e.r1));
             DescPoseJacobian(cam, r.lp, e.gx2, e.gy2, J);
@@ -281,49 +513,102 @@ __global__ void __launch_bounds__(kPoseThreads, BBA_POSE_MIN_CTAS) PoseAccumulat
               acc[30] += DescCost(e.r1);
               acc[31] += DescCost(e.r2);
             }
+#endif
           }
         }
       }
 
       if (touched) {
         const float total = WarpTransposeReduce(acc, lane);
-        atomicAdd(args.acc + static_cast<size_t>(kf) * kPoseAccSize + lane, static_cast<double>(total));
+        atomicAdd(args.acc + static_cast<size_t>(kf) * kPoseAccSize + AccSlot(lane), static_cast<double>(total));
       }
       if (STATS && lane == 0 && n_inimg) {
         atomicAdd(args.stage_counts + 2 * kf, static_cast<unsigned long long>(n_inimg));
         if (n_depthok) atomicAdd(args.stage_counts + 2 * kf + 1, static_cast<unsigned long long>(n_depthok));
       }
     }
+#if BBA_POSE_NOBARRIER
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();   // this warp's reads of stage s are complete before the stage can be handed back
+      if (atomicAdd(&s_done[s], 1) == kWarps - 1) {
+        __threadfence_block();
+        arm_stage(s);
+      }
+    }
+#else
     __syncthreads();   // every warp is done with stage s (and with s_item[s]) before either is refilled
     if (tid == 0) s_sub[s] = 0;
+#endif
   }
 }
 
-template <int TILE, bool STATS>
+// work_records[i] = kfs[work_list[i]] with pad = the keyframe id: makes the records of a work group contiguous.
+__global__ void __launch_bounds__(128) PackWorkRecordsKernel(const KfDevice* __restrict__ kfs, const int* __restrict__ work_list,
+                                                             const int* __restrict__ work_count, KfDevice* __restrict__ records) {
+  const int n = __ldg(work_count);
+  constexpr int kWords = sizeof(KfDevice) / 16;   // 6 x 16 bytes per record
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * kWords; i += gridDim.x * blockDim.x) {
+    const int rec = i / kWords, w = i - rec * kWords;
+    const int kf = __ldg(work_list + rec);
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(kfs + kf) + w);
+    if (w == kWords - 1) v.y = static_cast<unsigned int>(kf);   // KfDevice::pad
+    reinterpret_cast<uint4*>(records + rec)[w] = v;
+  }
+}
+
+template <int TILE, bool STATS, bool PRE>
 static void LaunchPoseAccumulateT(const PoseAccumulateArgs& args, int sm_count, cudaStream_t stream) {
-  const size_t smem = static_cast<size_t>(2) * kPoseStagedRows * TILE * sizeof(float);
+  const size_t smem = static_cast<size_t>(2) * (PRE ? kPoseStagedRowsPre : kPoseStagedRows) * TILE * sizeof(float);
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(PoseAccumulateKernel<TILE, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaFuncSetAttribute(PoseAccumulateKernel<TILE, STATS, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     configured = true;
   }
-  PoseAccumulateKernel<TILE, STATS><<<BBA_POSE_MIN_CTAS * sm_count, kPoseThreads, smem, stream>>>(args);   // persistent
+  PoseAccumulateKernel<TILE, STATS, PRE><<<BBA_POSE_MIN_CTAS * sm_count, kPoseThreads, smem, stream>>>(args);   // persistent
 }
 
 template <bool STATS>
 static void LaunchPoseAccumulateS(const PoseAccumulateArgs& args, int sm_count, cudaStream_t stream) {
-  // Tile size: as large as possible (one TMA transaction + one CTA barrier per item), but small enough that a
-  // keyframe group still yields several items per resident CTA.
+  // Tile size: as large as possible (one group of TMA transactions per item), but small enough that a keyframe group still
+  // yields several items per resident CTA.  With the precomputed frames 14 rows are staged: 512 surfels x 2 stages = 56 KB per
+  // CTA (two CTAs per SM), the same footprint as 1024 surfels of the 7-row variant.
   const uint64_t slots = static_cast<uint64_t>(BBA_POSE_MIN_CTAS * sm_count) * 4;
-  if (args.n >= slots * 1024) LaunchPoseAccumulateT<1024, STATS>(args, sm_count, stream);
-  else if (args.n >= slots * 512) LaunchPoseAccumulateT<512, STATS>(args, sm_count, stream);
-  else LaunchPoseAccumulateT<256, STATS>(args, sm_count, stream);
+  if (args.frames != nullptr) {
+    if (args.n >= slots * 512) LaunchPoseAccumulateT<512, STATS, true>(args, sm_count, stream);
+    else LaunchPoseAccumulateT<256, STATS, true>(args, sm_count, stream);
+    return;
+  }
+  if (args.n >= slots * 1024) LaunchPoseAccumulateT<1024, STATS, false>(args, sm_count, stream);
+  else if (args.n >= slots * 512) LaunchPoseAccumulateT<512, STATS, false>(args, sm_count, stream);
+  else LaunchPoseAccumulateT<256, STATS, false>(args, sm_count, stream);
 }
 
-void LaunchPoseAccumulate(const PoseAccumulateArgs& args, int sm_count, bool with_stats, cudaStream_t stream) {
+void LaunchPoseAccumulate(const PoseAccumulateArgs& args, int sm_count, bool with_stats, int max_work, cudaStream_t stream) {
   if (args.n == 0) return;
+  PackWorkRecordsKernel<<<(max_work * 6 + 127) / 128, 128, 0, stream>>>(args.kfs, args.work_list, args.work_count, args.work_records);
   if (with_stats) LaunchPoseAccumulateS<true>(args, sm_count, stream);
   else LaunchPoseAccumulateS<false>(args, sm_count, stream);
+}
+
+__global__ void __launch_bounds__(256) SurfelFramesKernel(const float* __restrict__ surfels, uint32_t pitch, uint32_t n,
+                                                          float* __restrict__ frames, uint32_t fp) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t P = pitch;
+  const Vec3 gp = V3(surfels[kRowX * P + i], surfels[kRowY * P + i], surfels[kRowZ * P + i]);
+  const Vec3 nrm = UnpackNormal(__float_as_uint(surfels[kRowNormal * P + i]));
+  Vec3 q1, q2;
+  TangentPoints(gp, nrm, surfels[kRowRadiusSq * P + i], &q1, &q2);
+  const size_t F = fp;
+  frames[0 * F + i] = nrm.x; frames[1 * F + i] = nrm.y; frames[2 * F + i] = nrm.z;
+  frames[3 * F + i] = q1.x;  frames[4 * F + i] = q1.y;  frames[5 * F + i] = q1.z;
+  frames[6 * F + i] = q2.x;  frames[7 * F + i] = q2.y;  frames[8 * F + i] = q2.z;
+}
+
+void LaunchSurfelFrames(const float* surfels, uint32_t pitch, uint32_t n, float* frames, uint32_t frames_pitch, cudaStream_t stream) {
+  if (n == 0) return;
+  SurfelFramesKernel<<<(n + 255) / 256, 256, 0, stream>>>(surfels, pitch, n, frames, frames_pitch);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -335,8 +620,16 @@ void LaunchPoseAccumulate(const PoseAccumulateArgs& args, int sm_count, bool wit
 // reference uses for exactly this purpose, kernels.cuh:78-86); a per-tile epoch word orders (group g, tile t) after
 // (group g-1, tile t).  With K <= 16 there is a single group and no scratch traffic at all.
 
+#ifndef BBA_GEO_GROUP
+#define BBA_GEO_GROUP 16
+#endif
+// (surfel, keyframe) pairs a thread of the activation / normals kernel keeps in flight.  Measured at cfg3: 1 -> 2.26 ms (64
+// registers, 32 warps / SM), 2 -> 2.54 ms (78 registers, 24 warps / SM); before the gathers were un-sunk and the records staged: 2.97 ms.
+#ifndef BBA_GEO_INTERLEAVE
+#define BBA_GEO_INTERLEAVE 1
+#endif
 constexpr int kGeoThreads = 256;
-constexpr int kGeoGroup = 16;   // keyframes per work item
+constexpr int kGeoGroup = BBA_GEO_GROUP;   // keyframes per work item
 
 __device__ __forceinline__ unsigned int LoadAcquire(const unsigned int* p) {
   unsigned int v;
@@ -388,18 +681,49 @@ __device__ __forceinline__ void StoreActiveFlag(const GeometryArgs& a, uint32_t 
     if (p < a.peers.count) a.peers.active[p][i] = v;
 }
 
+// The <= kGeoGroup keyframe records of a work item, copied once per item into the warp's own shared-memory slice (coalesced
+// 16-byte loads; the per-keyframe reads in the pair loop are then conflict-free broadcasts with a fixed ~25-cycle latency
+// instead of a chain of dependent L1 accesses: keyframe id -> record row 2 -> rows 0, 1 -> image pointers).
+__device__ __forceinline__ void StageGroupRecords(const KfDevice* __restrict__ kfs, const int* __restrict__ kf_list, int count,
+                                                  KfDevice* dst, int lane) {
+  constexpr int kWords = sizeof(KfDevice) / 16;
+  __syncwarp();   // the previous item's readers are done
+  const int my_kf = lane < count ? __ldg(kf_list + lane) : 0;
+#pragma unroll
+  for (int w = 0; w < (kGeoGroup * kWords + 31) / 32; ++w) {
+    const int idx = w * 32 + lane, rec = idx / kWords, part = idx - rec * kWords;
+    const int kf = __shfl_sync(0xffffffffu, my_kf, rec & 31);
+    if (rec < count) {
+      uint4 v = __ldg(reinterpret_cast<const uint4*>(kfs + kf) + part);
+      reinterpret_cast<uint4*>(dst + rec)[part] = v;
+    }
+  }
+  __syncwarp();
+}
+
+// One (surfel, keyframe) pair between "gathers issued" and "gathers consumed": two of them are kept in flight per thread.
+struct PendingPair {
+  bool in_image;
+  Assoc r;
+  PixelLoads l;
+};
+
 template <bool DETERMINE, bool NORMALS>
 __global__ void __launch_bounds__(kGeoThreads) ActivationNormalsKernel(const __grid_constant__ GeometryArgs a) {
+  __shared__ __align__(16) KfDevice s_kfs[kGeoThreads / 32][kGeoGroup];
   const uint32_t tile_len = 1u << a.tile_shift;
   const uint32_t n_tiles = (a.end - a.begin + tile_len - 1) >> a.tile_shift;
   const uint32_t n_groups = (a.kf_count + kGeoGroup - 1) / kGeoGroup;
   const uint32_t n_items = n_groups * n_tiles;
   const size_t P = a.pitch;
   const int lane = threadIdx.x & 31;
+  KfDevice* recs = s_kfs[threadIdx.x >> 5];
   uint32_t group, tile;
   while (NextGeoItem(a, n_tiles, n_items, &group, &tile)) {
     const bool first = group == 0, last = group + 1 == n_groups;
     const int j_begin = group * kGeoGroup, j_end = min(a.kf_count, static_cast<int>(group + 1) * kGeoGroup);
+    const int n_kf = j_end - j_begin;
+    StageGroupRecords(a.kfs, a.kf_list + j_begin, n_kf, recs, lane);
     for (uint32_t sub = 0; sub < tile_len / 32; ++sub) {
       const uint32_t li = a.begin + (tile << a.tile_shift) + sub * 32 + lane;
       const uint32_t i = SurfelShardToGlobal(li, a.shard_rank, a.shard_world);
@@ -420,27 +744,50 @@ __global__ void __launch_bounds__(kGeoThreads) ActivationNormalsKernel(const __g
       if (NORMALS || !act) {   // activation alone stops at the first association with an active keyframe
         const Vec3 gp = V3(a.surfels[kRowX * P + i], a.surfels[kRowY * P + i], a.surfels[kRowZ * P + i]);
         const Vec3 nrm = UnpackNormal(__float_as_uint(a.surfels[kRowNormal * P + i]));
-        for (int j = j_begin; j < j_end; ++j) {
-          const int kf = __ldg(a.kf_list + j);
-          KfRegs K;
-          LoadKf(a.kfs, kf, &K);
-          if (!NORMALS && K.activation != 0) continue;   // activation only looks at kActive keyframes
-          Assoc r;
-          const int st = ProjectAssociate(a.cam, K.T, K.depth, K.depth_pitch, K.normals, K.normals_pitch, gp, nrm, &r);
-          if (st == 3) {
-            if (K.activation == 0) act = true;
-            if (NORMALS) {
-              // kernel_opt_geometry.cu:545-553: global_R_frame * local normal, global_R_frame = R(frame_T_global)^T
-              const Vec3 ln = U16ToImageSpaceNormal(r.kf_normal);
-              s0 += K.T[0] * ln.x + K.T[4] * ln.y + K.T[8] * ln.z;
-              s1 += K.T[1] * ln.x + K.T[5] * ln.y + K.T[9] * ln.z;
-              s2 += K.T[2] * ln.x + K.T[6] * ln.y + K.T[10] * ln.z;
-              s3 += 1.f;
-            } else if (act) {
-              break;
-            }
+        // Two keyframes per step: both projections, then both pixels' gathers, then the association tests and the sums in
+        // keyframe order (the summation order -- and with it the result -- is the reference's: one thread, ascending keyframes).
+        auto issue = [&](const KfRegs& K, PendingPair* p) {
+          p->in_image = (NORMALS || K.activation == 0) && ProjectIntoImage(a.cam, K.T, gp, &p->r);   // activation only looks at kActive keyframes
+          if (p->in_image) p->l = LoadPixel(a.cam, K.depth, K.depth_pitch, K.normals, K.normals_pitch, p->r);
+        };
+        auto consume = [&](const KfRegs& K, PendingPair* p) {
+          if (!p->in_image || Associate(a.cam, K.T, nrm, p->l, &p->r) != 3) return;
+          if (K.activation == 0) act = true;
+          if (NORMALS) {
+            // kernel_opt_geometry.cu:545-553: global_R_frame * local normal, global_R_frame = R(frame_T_global)^T
+            const Vec3 ln = U16ToImageSpaceNormal(p->r.kf_normal);
+            s0 += K.T[0] * ln.x + K.T[4] * ln.y + K.T[8] * ln.z;
+            s1 += K.T[1] * ln.x + K.T[5] * ln.y + K.T[9] * ln.z;
+            s2 += K.T[2] * ln.x + K.T[6] * ln.y + K.T[10] * ln.z;
+            s3 += 1.f;
           }
+        };
+#if BBA_GEO_INTERLEAVE == 2
+        for (int j = 0; j < n_kf; j += 2) {
+          KfRegs K0, K1;
+          PendingPair p0, p1;
+          LoadKfShared(recs + j, &K0);
+          issue(K0, &p0);
+          p1.in_image = false;
+          if (j + 1 < n_kf) {
+            LoadKfShared(recs + j + 1, &K1);
+            issue(K1, &p1);
+          }
+          consume(K0, &p0);
+          if (!NORMALS && act) break;
+          consume(K1, &p1);
+          if (!NORMALS && act) break;
         }
+#else
+        for (int j = 0; j < n_kf; ++j) {
+          KfRegs K0;
+          PendingPair p0;
+          LoadKfShared(recs + j, &K0);
+          issue(K0, &p0);
+          consume(K0, &p0);
+          if (!NORMALS && act) break;
+        }
+#endif
       }
       if (!last) {
         if (NORMALS) {
@@ -465,7 +812,9 @@ __global__ void __launch_bounds__(kGeoThreads) ActivationNormalsKernel(const __g
 }
 
 template <bool USE_DEPTH, bool USE_DESC>
-__global__ void __launch_bounds__(kGeoThreads) PositionDescriptorKernel(const __grid_constant__ GeometryArgs a) {
+__global__ void __launch_bounds__(kGeoThreads, 3) PositionDescriptorKernel(const __grid_constant__ GeometryArgs a) {
+  __shared__ __align__(16) KfDevice s_kfs[kGeoThreads / 32][kGeoGroup];
+  KfDevice* recs = s_kfs[threadIdx.x >> 5];
   const uint32_t tile_len = 1u << a.tile_shift;
   const uint32_t n_tiles = (a.end - a.begin + tile_len - 1) >> a.tile_shift;
   const uint32_t n_groups = (a.kf_count + kGeoGroup - 1) / kGeoGroup;
@@ -476,22 +825,29 @@ __global__ void __launch_bounds__(kGeoThreads) PositionDescriptorKernel(const __
   while (NextGeoItem(a, n_tiles, n_items, &group, &tile)) {
     const bool first = group == 0, last = group + 1 == n_groups;
     const int j_begin = group * kGeoGroup, j_end = min(a.kf_count, static_cast<int>(group + 1) * kGeoGroup);
+    StageGroupRecords(a.kfs, a.kf_list + j_begin, j_end - j_begin, recs, lane);
     for (uint32_t sub = 0; sub < tile_len / 32; ++sub) {
       const uint32_t li = a.begin + (tile << a.tile_shift) + sub * 32 + lane;
       const uint32_t i = SurfelShardToGlobal(li, a.shard_rank, a.shard_world);
-      if (li >= a.end || i >= a.n || !(a.active[i] & kSurfelActiveFlag)) continue;
-      const Vec3 gp = V3(a.surfels[kRowX * P + i], a.surfels[kRowY * P + i], a.surfels[kRowZ * P + i]);
-      const Vec3 nrm = UnpackNormal(__float_as_uint(a.surfels[kRowNormal * P + i]));
+      // The keyframe loop below is executed by the whole warp (a lane without a live surfel just skips every pair): the
+      // per-keyframe record -- in particular the texture handle -- is then provably warp-uniform, see UniformTexture().
+      const bool live = li < a.end && i < a.n && (a.active[i] & kSurfelActiveFlag);
+      if (__ballot_sync(0xffffffffu, live) == 0) continue;
+      Vec3 gp = V3(0.f, 0.f, 0.f), nrm = V3(0.f, 0.f, 1.f);
       float radius_sq = 0.f, d1 = 0.f, d2 = 0.f;
-      if (USE_DESC) {
-        radius_sq = a.surfels[kRowRadiusSq * P + i];
-        d1 = a.surfels[kRowD1 * P + i];
-        d2 = a.surfels[kRowD2 * P + i];
+      if (live) {
+        gp = V3(a.surfels[kRowX * P + i], a.surfels[kRowY * P + i], a.surfels[kRowZ * P + i]);
+        nrm = UnpackNormal(__float_as_uint(a.surfels[kRowNormal * P + i]));
+        if (USE_DESC) {
+          radius_sq = a.surfels[kRowRadiusSq * P + i];
+          d1 = a.surfels[kRowD1 * P + i];
+          d2 = a.surfels[kRowD2 * P + i];
+        }
       }
       // 3x3 normal equations over (t along normal, d1, d2): H00 H01 H02 H11 H12 H22 | b0 b1 b2
       float H00 = 0.f, H01 = 0.f, H02 = 0.f, H11 = 0.f, H22 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
       const float H12 = 0.f;   // never accumulated by the reference either (kernel_opt_geometry.cu:216-227)
-      if (!first) {
+      if (!first && live) {
         // same row assignment as the reference's accumulators (kernel_opt_geometry.cu:216-227)
         H00 = __ldcg(a.surfels + (kRowAccum0 + 0) * P + i);
         b0 = __ldcg(a.surfels + (kRowAccum0 + 6) * P + i);
@@ -504,22 +860,36 @@ __global__ void __launch_bounds__(kGeoThreads) PositionDescriptorKernel(const __
           b2 = __ldcg(a.surfels + (kRowAccum0 + 8) * P + i);
         }
       }
-      for (int j = j_begin; j < j_end; ++j) {
-        const int kf = __ldg(a.kf_list + j);
+      for (int j = 0; j < j_end - j_begin; ++j) {
         KfRegs K;
-        LoadKf(a.kfs, kf, &K);
+        LoadKfShared(recs + j, &K);
+        K.tex = UniformTexture(K.tex);
         Assoc r;
-        if (!ProjectIntoImage(a.cam, K.T, gp, &r)) continue;
+        if (!live || !ProjectIntoImage(a.cam, K.T, gp, &r)) continue;
         // all gathers of the pair in flight before the first dependent use (see PoseAccumulateKernel)
         const PixelLoads l = LoadPixel(a.cam, K.depth, K.depth_pitch, K.normals, K.normals_pitch, r);
         DescEval e;
         bool photo = false;
         if (USE_DESC) {
+#if BBA_GEO_PACKED
+          const F2 c_pxy = Fma(Pack(a.cam.d2c_fx, a.cam.d2c_fy), Pack(r.pxf, r.pyf), Pack(a.cam.d2c_cx, a.cam.d2c_cy));   // DepthToColor
+          float ccx, ccy;
+          Unpack(c_pxy, &ccx, &ccy);
+          photo = ccx >= 0 && ccy >= 0 && static_cast<int>(ccx) < a.cam.cw && static_cast<int>(ccy) < a.cam.ch;
+          F2 t1, t2;
+          TangentProjections2(a.cam, MakeKfPairs(K.T), K.T, gp, nrm, radius_sq, &t1, &t2);
+          DescEval2 e2;
+          EvalDescriptor2(K.tex, c_pxy, t1, t2, d1, d2, &e2);
+          Unpack(e2.r, &e.r1, &e.r2);
+          Unpack(e2.g1, &e.gx1, &e.gy1);
+          Unpack(e2.g2, &e.gx2, &e.gy2);
+#else
           float ccx, ccy;
           photo = DepthToColor(a.cam, r.pxf, r.pyf, &ccx, &ccy);
           float t1x, t1y, t2x, t2y;
           TangentProjections(a.cam, K.T, gp, nrm, radius_sq, &t1x, &t1y, &t2x, &t2y);
           EvalDescriptor(K.tex, ccx, ccy, t1x, t1y, t2x, t2y, d1, d2, &e);
+#endif
         }
         if (Associate(a.cam, K.T, nrm, l, &r) != 3) continue;
         if (USE_DEPTH) {
@@ -559,6 +929,7 @@ __global__ void __launch_bounds__(kGeoThreads) PositionDescriptorKernel(const __
         }
       }
 
+      if (!live) continue;
       if (!last) {
         __stcg(a.surfels + (kRowAccum0 + 0) * P + i, H00);
         __stcg(a.surfels + (kRowAccum0 + 6) * P + i, b0);

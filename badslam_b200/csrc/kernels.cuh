@@ -22,6 +22,10 @@ struct PoseAccumulateArgs {
   const KfDevice* kfs;
   const int* work_list;      // keyframe ids to evaluate
   const int* work_count;     // device scalar
+  const float* frames;       // 9 rows x frames_pitch: per-surfel unpacked normal, gp + t1, gp + t2 (SurfelFramesKernel); may be null
+  uint32_t frames_pitch;     // floats per row
+  KfDevice* work_records;    // [max_kf] scratch: the work list's KfDevice records in list order (pad = keyframe id), filled by
+                             // LaunchPoseAccumulate so that a work group's <= 8 records are ONE contiguous bulk copy
   double* acc;               // [max_kf][32]
   unsigned long long* stage_counts;  // [max_kf][2]
   unsigned int* queue;       // global work-item counter, must be 0 at launch
@@ -30,7 +34,13 @@ struct PoseAccumulateArgs {
 // Persistent, TMA-staged pose residual/Jacobian/Hessian kernel (AccumulatePoseEstimationCoeffsCUDAKernel,
 // kernel_opt_pose.cu:251-383, for a whole list of keyframes in one launch).
 // with_stats: also accumulate residual costs + the stage counters (iteration 0 of a pose step, profiling, debug API).
-void LaunchPoseAccumulate(const PoseAccumulateArgs& args, int sm_count, bool with_stats, cudaStream_t stream);
+// Per-surfel, pose-independent inputs of the descriptor residual, computed once per pose step (the surfels do not move while the
+// keyframe poses are optimised): rows 0-2 unpacked + re-normalised normal (util_nvcc_only.cuh:83-95), rows 3-5 / 6-8 the tangent
+// points gp + t1 / gp + t2 (cost_function.cuh:115-133).  frames: [9][frames_pitch] floats.
+void LaunchSurfelFrames(const float* surfels, uint32_t pitch, uint32_t n, float* frames, uint32_t frames_pitch, cudaStream_t stream);
+// max_work: upper bound of *work_count known to the host (sizes the record-packing launch that precedes the kernel).
+// args.frames != null selects the variant that stages the precomputed frames instead of the packed normal / radius rows.
+void LaunchPoseAccumulate(const PoseAccumulateArgs& args, int sm_count, bool with_stats, int max_work, cudaStream_t stream);
 
 struct PoseSolveArgs {
   KfDevice* kfs;

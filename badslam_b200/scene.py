@@ -367,8 +367,8 @@ def preprocess_depth(cfg, K4, raw_in, cfactor_grid, depth_a):
     left, right = pts[1:-1, :-2], pts[1:-1, 2:]
     top, bottom = pts[:-2, 1:-1], pts[2:, 1:-1]
 
-    def sq(a):
-        return (a * a).sum(-1)
+    def sq(a):   # (a * a).sum(-1) over the 3 components, in the same order, without the generic reduction machinery
+        return a[..., 0] * a[..., 0] + a[..., 1] * a[..., 1] + a[..., 2] * a[..., 2]
 
     with np.errstate(divide="ignore", invalid="ignore"):
         ld, rd = sq(left - c), sq(right - c)

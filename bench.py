@@ -271,6 +271,10 @@ def run_ours(args, scene, rank, world):
                 "kernel_share_of_step": prof["pose_ms"] / ms_total,
                 "pairs_per_s": prof["n_pair"] / pose_s if pose_s > 0 else 0.0}
 
+    multi_gpu_check = None
+    if world > 1:
+        multi_gpu_check = check_replicas(scene, ba, step, dev, rank, world)
+
     # full BA (10 continuing iterations) for the second headline number
     surf[:8].copy_(backup)
     ba.SetKeyframeStates(poses0, act0)
@@ -306,6 +310,8 @@ def run_ours(args, scene, rank, world):
     }
     if e2e_all is not None:
         out["e2e_all_keyframes"] = e2e_all
+    if multi_gpu_check is not None:
+        out["multi_gpu_check"] = multi_gpu_check
     if intr:
         out["config"]["intrinsics"] = "depth intrinsics + depth deformation + colour intrinsics optimised in every step (--intrinsics)"
         out["stage_ms"]["BA_intrinsics_optimization"] = res.ms_intrinsics_optimization
@@ -316,6 +322,45 @@ def run_ours(args, scene, rank, world):
                                         f"granules dealt round-robin (exchange: {exchange}), pose step sharded by keyframe, "
                                         "balanced by measured work (1 all-reduce of K x 17 floats); NCCL over NVLink")
         dist.barrier(device_ids=[dev.index])
+    return out
+
+
+def check_replicas(scene, ba, step, dev, rank, world):
+    """Correctness of the N-rank step, carried by the bench line: (1) after one more (untimed) step every rank's replica --
+    surfel rows, active flags, keyframe poses and activations -- must be bit-identical (hashes all-gathered); (2) rank 0 runs
+    the same step on ONE GPU (a world-size-1 backend on its device) and reports the difference of the N-rank result to it."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    from badslam_b200.direct_ba import DirectBA
+    from badslam_b200.scene import pose_error
+    step()
+    torch.cuda.synchronize()
+    rows, flags = ba.GetSurfelsHost(), ba.GetActiveHost()
+    poses, act = ba.GetKeyframeStates()
+    digest = hashlib.sha256(rows.tobytes() + flags.tobytes() + np.ascontiguousarray(poses).tobytes() + np.ascontiguousarray(act).tobytes()).digest()
+    mine = torch.tensor(list(digest), dtype=torch.uint8, device=dev)
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    identical = all(bool(torch.equal(g, gathered[0])) for g in gathered)
+    out = {"replicas_bit_identical": identical, "ranks": world}
+    if rank == 0:
+        single = DirectBA.from_scene(scene, device=dev)
+        single.SetLastBAIterationCount(single.ba_iteration_count())
+        single.BundleAdjustment(None, False, False, False, True, True, 1, 1, increase_ba_iteration_count=False)
+        torch.cuda.synchronize()
+        rows1, flags1 = single.GetSurfelsHost(), single.GetActiveHost()
+        poses1, act1 = single.GetKeyframeStates()
+        errs = [pose_error(poses[k], poses1[k]) for k in range(scene.cfg.num_keyframes)]
+        out.update({"vs_1gpu_pose_max_m": float(max(e[0] for e in errs)), "vs_1gpu_pose_max_rad": float(max(e[1] for e in errs)),
+                    "vs_1gpu_surfel_rows_max_abs": float(np.max(np.abs(rows[:8].astype(np.float64) - rows1[:8].astype(np.float64))[[0, 1, 2, 6, 7]])),
+                    "vs_1gpu_packed_normals_differ": int((rows[3].view(np.uint32) != rows1[3].view(np.uint32)).sum()),
+                    "vs_1gpu_active_flags_equal": bool(np.array_equal(flags, flags1)),
+                    "vs_1gpu_keyframe_activations_equal": bool(np.array_equal(act, act1)),
+                    "tolerance": "north_star: 1e-5 m / 1e-5 rad on poses"})
+        del single
+        torch.cuda.empty_cache()
+    dist.barrier(device_ids=[dev.index])
     return out
 
 

@@ -122,3 +122,76 @@ def test_two_rank_intrinsics_step_matches_single_gpu(tmp_path):
     # the all-reduce sums fp32 partials: agreement with the single-GPU fp64 accumulation at the fp32 level
     assert np.abs(r0["d"] - d).max() < 2e-3 and np.abs(r0["c"] - c).max() < 2e-3 and abs(float(r0["a"]) - a) < 1e-5
     assert np.abs(r0["cf"] - cf).max() < 1e-4
+
+
+def _half_small():
+    """tests/test_gpu_lifecycle.py::_half_map("small") with the perturbed poses: half of the surfels, room for new ones."""
+    import copy
+    from badslam_b200.scene import config_by_name, make_scene
+    full = make_scene(config_by_name("small"))
+    sc = copy.copy(full)
+    sc.num_surfels = full.num_surfels // 2
+    cells = sc.cfactor.size * sc.cfg.num_keyframes
+    sc.surfels = np.pad(full.surfels, ((0, 0), (0, (cells + 127) // 128 * 128)))
+    return sc
+
+
+def _lifecycle_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from badslam_b200.direct_ba import DirectBA
+    out = {}
+    for tag, peers in (("gather", False), ("peer", True)):
+        ba = DirectBA.from_scene(_half_small(), device=f"cuda:{rank}", rank=rank, world_size=world)
+        ba.SetCollective()
+        if peers:
+            assert ba.EnablePeerExchange() == world - 1
+        r = ba.BundleAdjustment(None, False, False, True, True, True, 2, 2)     # do_surfel_updates = true
+        r2 = ba.BundleAdjustment(None, False, False, True, True, True, 1, 1)
+        out[f"{tag}_counts"] = np.array([r.surfels_created, r.surfels_merged, r.surfels_deleted, r.surfels_size,
+                                         r2.surfels_created, r2.surfels_size, r.pose_iterations_total], np.int64)
+        out[f"{tag}_poses"] = ba.GetKeyframeStates()[0]
+        out[f"{tag}_surfels"] = ba.GetSurfelsHost()
+        out[f"{tag}_active"] = ba.GetActiveHost()
+    np.savez(os.path.join(out_dir, f"life{rank}.npz"), **out)
+    dist.barrier(device_ids=[rank])
+    dist.destroy_process_group()
+
+
+def test_two_rank_surfel_updates_match_single_gpu(tmp_path):
+    """do_surfel_updates with 2 ranks (direct_ba_alternating.cc:399-430,489-541): creation / merging / compaction / end tasks run
+    replicated and deterministically on every rank, the geometry and pose steps sharded; replicas bit-identical, same surfel
+    counts as one GPU, poses equal up to the summation order of the pose normal equations."""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from badslam_b200.direct_ba import DirectBA
+    from badslam_b200.scene import pose_error
+    mp.spawn(_lifecycle_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    sc = _half_small()
+    ba = DirectBA.from_scene(sc, device="cuda:0")
+    r = ba.BundleAdjustment(None, False, False, True, True, True, 2, 2)
+    r2 = ba.BundleAdjustment(None, False, False, True, True, True, 1, 1)
+    want = np.array([r.surfels_created, r.surfels_merged, r.surfels_deleted, r.surfels_size, r2.surfels_created, r2.surfels_size,
+                     r.pose_iterations_total], np.int64)
+    assert r.surfels_created > 0 and r.surfels_merged > 0
+    poses, surf = ba.GetKeyframeStates()[0], ba.GetSurfelsHost()
+    r0, r1 = np.load(tmp_path / "life0.npz"), np.load(tmp_path / "life1.npz")
+    for tag in ("gather", "peer"):
+        for key in ("counts", "poses", "surfels", "active"):
+            a, b = r0[f"{tag}_{key}"], r1[f"{tag}_{key}"]
+            assert a.shape == b.shape and np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a,
+                                                         b.view(np.uint32) if b.dtype == np.float32 else b), (tag, key)
+        # the surfel sets are the same size as on one GPU (tiny pose differences may flip a handful of merges / deletions)
+        c = r0[f"{tag}_counts"]
+        assert c[0] == want[0], (tag, c, want)
+        assert np.all(np.abs(c[1:6] - want[1:6]) <= np.maximum(3, 0.002 * want[1:6])), (tag, c, want)
+        for k in range(sc.cfg.num_keyframes):
+            dt, dr = pose_error(r0[f"{tag}_poses"][k], poses[k])
+            assert dt < 2e-5 and dr < 2e-5, (tag, k, dt, dr)
+    assert np.array_equal(r0["peer_surfels"].view(np.uint32), r0["gather_surfels"].view(np.uint32))
