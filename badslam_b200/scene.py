@@ -498,6 +498,29 @@ def _create_surfels_for_keyframe(cfg, depth_K, color_K, pose, depth, normals, ra
 
 
 def make_scene(cfg: SceneConfig, verbose: bool = False) -> Scene:
+    """The seeded scene of a configuration.  BADBA_SCENE_CACHE=<dir> keeps a pickle per configuration there, so that several
+    processes of one GPU session (tests, tools, both bench arms) generate a large scene once (cfg5: minutes of host time)."""
+    import os
+    cache = os.environ.get("BADBA_SCENE_CACHE")
+    if not cache:
+        return _make_scene(cfg, verbose)
+    import hashlib
+    import pickle
+    os.makedirs(cache, exist_ok=True)
+    key = hashlib.sha1(repr(cfg).encode()).hexdigest()[:12]
+    path = os.path.join(cache, f"{cfg.name}_{key}.pkl")
+    if os.path.exists(path):
+        with open(path, "rb") as f:
+            return pickle.load(f)
+    sc = _make_scene(cfg, verbose)
+    tmp = f"{path}.{os.getpid()}.tmp"
+    with open(tmp, "wb") as f:
+        pickle.dump(sc, f, protocol=4)
+    os.replace(tmp, path)
+    return sc
+
+
+def _make_scene(cfg: SceneConfig, verbose: bool = False) -> Scene:
     rng = np.random.Generator(np.random.PCG64(cfg.seed))
     w, h, K = cfg.width, cfg.height, cfg.num_keyframes
     depth_K = np.array([0.5 * h, 0.5 * h, 0.5 * w - 0.5, 0.5 * h - 0.5], np.float32)

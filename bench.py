@@ -472,6 +472,21 @@ def run_reference(args, scene):
                 "config": {"workload": scene.cfg.name}}
     ref = ref_cuda.RefDirectBA(scene)
     ref.snapshot()
+    # --intrinsics (cfg4): OptimizeIntrinsicsCUDA for the depth camera + depth deformation and the colour camera inside the
+    # iteration (direct_ba_alternating.cc:599-655), camera model restored before every step like on our arm
+    intr = bool(getattr(args, "intrinsics", False))
+    kw = dict(optimize_depth_intrinsics=intr, optimize_color_intrinsics=intr)
+    if intr:
+        d0, c0, a0 = ref.intrinsics()
+        cf0 = ref.cfactor()
+    _restore = ref.restore
+
+    def restore():
+        _restore()
+        if intr:
+            ref.set_intrinsics(d0, c0)
+            ref.set_depth_params(a0, cf0)
+    ref.restore = restore
     # residual count from the reference's own debug counters (untimed): n_count = n_assoc + n_photo with both residual types,
     # n_depth_count = n_assoc from the same launches with the descriptor residuals off.  Our metric counts both descriptor
     # residuals of a pair: n_assoc + 2 n_photo = 2 n_count - n_depth_count.  (This arm loads nothing of the product.)
@@ -480,7 +495,7 @@ def run_reference(args, scene):
     residuals = args.residuals_override or (2 * count_ref - count_depth)
     for _ in range(max(args.warmup - 1, 0)):
         ref.restore()
-        ref.bundle_adjust(True, True, 1, 1, count_residuals=False, end_tasks=False)
+        ref.bundle_adjust(True, True, 1, 1, count_residuals=False, end_tasks=False, **kw)
     ref.sync()
     sampler = ClockSampler(0)
     sampler.start()
@@ -489,7 +504,7 @@ def run_reference(args, scene):
     stage = np.zeros(3)
     for _ in range(args.steps):
         ref.restore()
-        r = ref.bundle_adjust(True, True, 1, 1, count_residuals=False, end_tasks=False)
+        r = ref.bundle_adjust(True, True, 1, 1, count_residuals=False, end_tasks=False, **kw)
         stage += [r.ms_surfel_activation, r.ms_geometry_optimization, r.ms_pose_optimization]
     ref.sync()
     dt = (time.perf_counter() - t0) / args.steps
@@ -499,16 +514,17 @@ def run_reference(args, scene):
     ref.restore()
     ref.sync()
     t0 = time.perf_counter()
-    full = ref.bundle_adjust(True, True, 10, 10, count_residuals=False, end_tasks=True)
+    full = ref.bundle_adjust(True, True, 10, 10, count_residuals=False, end_tasks=True, **kw)
     ref.sync()
     ms_full = (time.perf_counter() - t0) * 1e3
     value = residuals / dt
+    extra_cfg = {"intrinsics": "depth intrinsics + depth deformation + colour intrinsics optimised in every step (--intrinsics)"} if intr else {}
     return {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(scene), "keyframes": K, "surfels": scene.num_surfels,
                        "residuals_per_step": int(residuals),
-                       "l2": "inputs larger than L2 (keyframe images + surfels)", "parallelism": "gpus=1"},
+                       "l2": "inputs larger than L2 (keyframe images + surfels)", "parallelism": "gpus=1", **extra_cfg},
             "residual_count_source": "the reference's own debug counters (kernel_opt_pose.cu:312-320,373-381): one untimed iteration "
                                      "with both residual types (n_assoc + n_photo) and the same launches with the descriptor "
                                      "residuals off (n_assoc); residuals = n_assoc + 2 n_photo",

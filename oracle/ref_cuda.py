@@ -266,6 +266,11 @@ class RefDirectBA:
         self.l.ref_get_cfactor(self.h, out.ctypes.data)
         return out
 
+    def set_intrinsics(self, depth_K, color_K):
+        d = np.ascontiguousarray(depth_K, np.float32)
+        c = np.ascontiguousarray(color_K, np.float32)
+        self.l.ref_set_intrinsics(self.h, d.ctypes.data, c.ctypes.data)
+
     def set_depth_params(self, a, cfactor):
         cf = np.ascontiguousarray(cfactor, np.float32)
         self.l.ref_set_depth_params(self.h, float(a), cf.ctypes.data)

@@ -89,3 +89,35 @@ def test_cfg3_spread_keyframes_and_one_ba_iteration(mods):
     check_pose_coefficients(S, ba, ref, sc, (0, 7, 8, 63, 100, 129, 150, 191, 192, 199))
     ref2 = R.RefDirectBA(sc)
     check_one_ba_iteration(S, ba, ref, ref2, sc)
+
+
+# BASELINE.json configs 4 and 5 (500 keyframes / 4 M surfels with intrinsics + depth deformation; 1280x720, 400 keyframes /
+# 8 M surfels).  Scene generation alone takes minutes, so these two only run when BADBA_BIG_CONFIGS=1 (tools/r2_big_configs.sh;
+# the logs of the hardware runs are under profiles/bench/).  The spot check is the one of the benchmarked configuration:
+# association counts, H, b and cost of four keyframes from different work groups against the reference's own kernels.
+import os
+
+big = pytest.mark.skipif(not os.environ.get("BADBA_BIG_CONFIGS"), reason="set BADBA_BIG_CONFIGS=1 (minutes of scene generation)")
+
+
+@big
+@pytest.mark.parametrize("name", ["cfg4", "cfg5"])
+def test_big_config_spot_check(mods, name):
+    import torch
+    S, DirectBA, O, R = mods
+    sc = S.make_scene(S.config_by_name(name))
+    K = sc.cfg.num_keyframes
+    ba, ref = DirectBA.from_scene(sc), R.RefDirectBA(sc)
+    check_pose_coefficients(S, ba, ref, sc, (0, K // 3 + 1, 2 * K // 3 + 2, K - 1))
+    if name == "cfg4":
+        # one intrinsics + depth-deformation step (the cfg4 flags) on both sides from the same state
+        ba.OptimizeIntrinsics(True, True)
+        ref.optimize_intrinsics(True, True)
+        di, ci, a = ba._intrinsics()
+        rdi, rci, ra = ref.intrinsics()
+        # tolerances of tests/test_gpu_parity.py::test_intrinsics_step_three_way
+        assert np.all(np.abs(di - rdi) < REL * np.abs(rdi) + 1e-3) and np.all(np.abs(ci - rci) < REL * np.abs(rci) + 1e-3), (di, rdi, ci, rci)
+        assert abs(a - ra) < 1e-5, (a, ra)
+        assert np.abs(ba.cfactor_buffer() - ref.cfactor()).max() < 1e-4
+    free, total = torch.cuda.mem_get_info()
+    print(f"{name}: device memory in use with product + reference resident {(total - free) / 2**30:.2f} GiB")

@@ -75,6 +75,8 @@ def main():
     if intr:
         out["depth_a"] = [0.0, float(ba.a()), float(sc.cfg.depth_a)]      # start, now, value the scene was rendered with
         chk["a_moves_towards_truth"] = bool(abs(ba.a() - sc.cfg.depth_a) < abs(0.0 - sc.cfg.depth_a))
+    free_b, total_b = torch.cuda.mem_get_info()
+    out["device_memory_in_use_gib"] = round((total_b - free_b) / 2**30, 2)     # this rank: keyframe images + surfels + work buffers
     surf = ba.surfels()[:8, :ba.surfels_size()]
     chk["surfels_finite"] = bool(torch.isfinite(surf[[0, 1, 2, 4, 6, 7]]).all().item())
     if world > 1:
