@@ -58,6 +58,16 @@ class PreprocessOptions(C.Structure):
                 ("bilateral_filter_radius_factor", C.c_float), ("max_depth", C.c_float)]
 
 
+class OdometryOptions(C.Structure):
+    _fields_ = [("num_scales", C.c_int), ("use_pyramid_level_0", C.c_int), ("use_gradmag", C.c_int),
+                ("test_different_initial_estimates", C.c_int), ("max_iterations_per_scale", C.c_int)]
+
+
+class OdometryResult(C.Structure):
+    _fields_ = [("iterations", C.c_int * 8), ("chose_initial", C.c_int * 8), ("residual_count", C.c_uint32),
+                ("residual_sum", C.c_float), ("passes", C.c_uint32), ("kernel_launches", C.c_uint32)]
+
+
 class PeerHandle(C.Structure):
     _fields_ = [("surfels_ipc", C.c_ubyte * 64), ("surfels_offset", C.c_uint64), ("active_ipc", C.c_ubyte * 64),
                 ("active_offset", C.c_uint64), ("pitch_bytes", C.c_uint64), ("surfels_size", C.c_uint32), ("rank", C.c_int32)]
@@ -124,6 +134,11 @@ SYMBOLS = {
     "bba_estimate_frame_pose": (C.c_int, [_P, C.c_int, _F7, _F7, C.POINTER(C.c_int), C.POINTER(C.c_int), _P]),
     "bba_estimate_frame_pose_for_frame": (C.c_int, [_P, _P, C.c_size_t, _P, C.c_size_t, _P, C.c_size_t, _F7, _F7,
                                                     C.POINTER(C.c_int), C.POINTER(C.c_int), _P]),
+    "bba_track_frame_pairwise": (C.c_int, [_P, C.POINTER(OdometryOptions), C.c_int, _P, C.c_size_t, _P, C.c_size_t, _P, C.c_size_t,
+                                           _F7, _F7, _F7, C.POINTER(OdometryResult), _P]),
+    "bba_odometry_get_level": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, C.POINTER(C.c_int), C.POINTER(C.c_int), _P]),
+    "bba_odometry_debug_coeffs": (C.c_int, [_P, C.c_int, C.c_int, _F7, _F7, _P, _P, C.POINTER(C.c_uint32), C.POINTER(C.c_float),
+                                            _P, _P, _P]),
     "bba_update_surfel_activation": (C.c_int, [_P, _P]),
     "bba_optimize_geometry_iteration": (C.c_int, [_P, _P]),
     "bba_optimize_intrinsics": (C.c_int, [_P, C.c_int, C.c_int, _P]),
@@ -170,7 +185,7 @@ def load():
         fn = getattr(lib, name)   # AttributeError if the symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.bba_abi_version() != 6:
+    if lib.bba_abi_version() != 7:
         raise ImportError("libbadba_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -24,10 +24,11 @@ UNITS = [
     ("pcg.cu", ["-use_fast_math", "-Xptxas", "-v"]),
     ("lifecycle.cu", ["-use_fast_math", "-Xptxas", "-v"]),
     ("preprocess.cu", ["-use_fast_math", "-Xptxas", "-v"]),
+    ("odometry.cu", ["-use_fast_math", "-Xptxas", "-v"]),
     ("pose_solve.cu", []),
     ("badba.cu", []),
 ]
-HEADERS = ["device_math.cuh", "kernels.cuh", "preprocess_tile.cuh", "host_math.hpp", os.path.join("..", "..", "include", "badba.h")]
+HEADERS = ["device_math.cuh", "kernels.cuh", "odometry.cuh", "preprocess_tile.cuh", "host_math.hpp", os.path.join("..", "..", "include", "badba.h")]
 
 
 def _newer(src, dst):

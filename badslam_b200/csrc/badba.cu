@@ -22,6 +22,7 @@
 #include "../../include/badba.h"
 #include "host_math.hpp"
 #include "kernels.cuh"
+#include "odometry.cuh"
 #include "preprocess_tile.cuh"
 
 #ifndef BBA_POSE_PRECOMPUTE
@@ -252,6 +253,25 @@ struct bba_context {
   // frame-to-model tracking of a frame that is not a keyframe (bba_estimate_frame_pose_for_frame): luma array + texture
   cudaArray_t scratch_luma = nullptr;
   cudaTextureObject_t scratch_tex = 0;
+
+  // image-pair odometry (bba_track_frame_pairwise), lazily allocated: intensity / gradient-magnitude images of both frames
+  // (colour-sized), the depth / normal / colour pyramids of both frames, accumulators + barrier + result of the persistent kernel
+  struct Odometry {
+    int num_scales = 0;          // levels allocated
+    int last_num_scales = 0;     // levels filled by the last call (parity hooks)
+    int last_first_scale = 0;
+    uint8_t* gradmag[2] = {nullptr, nullptr};
+    size_t gradmag_pitch[2] = {0, 0};
+    cudaTextureObject_t gradmag_tex[2] = {0, 0};
+    bba::odom::Image image[2][bba::odom::kMaxScales] = {};   // [0 base | 1 tracked][scale]; owned planes only (level-0 normals are the caller's)
+    bool owns_normals[2][bba::odom::kMaxScales] = {};
+    int w[bba::odom::kMaxScales] = {}, h[bba::odom::kMaxScales] = {};
+    bba::odom::Level level[bba::odom::kMaxScales] = {};      // as passed to the last launch
+    double* d_acc = nullptr;             // [3][32]
+    unsigned int* d_barrier = nullptr;   // [2]
+    bba::odom::TrackResult* d_result = nullptr;
+    bba::odom::TrackResult* h_result = nullptr;   // pinned
+  } odo;
 
   // keyframe preprocessing (bba_preprocess_frame), lazily allocated
   float* d_min_max = nullptr;
@@ -1342,6 +1362,118 @@ bba_status MakeLumaTexture(bba_handle h, const uint8_t* device_rgba, size_t colo
   return BBA_OK;
 }
 
+// ---- image-pair odometry (bba_track_frame_pairwise) --------------------------------------------------------------------
+void FreeOdometry(bba_handle h) {
+  auto& o = h->odo;
+  for (int f = 0; f < 2; ++f) {
+    if (o.gradmag_tex[f]) cudaDestroyTextureObject(o.gradmag_tex[f]);
+    cudaFree(o.gradmag[f]);
+    o.gradmag_tex[f] = 0;
+    o.gradmag[f] = nullptr;
+    for (int s = 0; s < bba::odom::kMaxScales; ++s) {
+      bba::odom::Image& im = o.image[f][s];
+      if (im.color_tex) cudaDestroyTextureObject(im.color_tex);
+      cudaFree(im.depth);
+      if (o.owns_normals[f][s]) cudaFree(im.normals);
+      cudaFree(im.color);
+      im = bba::odom::Image{};
+      o.owns_normals[f][s] = false;
+    }
+  }
+  cudaFree(o.d_acc);
+  cudaFree(o.d_barrier);
+  cudaFree(o.d_result);
+  if (o.h_result) cudaFreeHost(o.h_result);
+  o.d_acc = nullptr; o.d_barrier = nullptr; o.d_result = nullptr; o.h_result = nullptr;
+  o.num_scales = 0;
+  o.last_num_scales = 0;
+}
+
+// A u8 plane in pitched device memory as a texture with the sampler state of CUDABuffer::CreateTextureObject as the reference
+// calls it for the pyramid colour planes (pairwise_frame_tracking.cc:57-79): clamp, linear, normalised float, unnormalised coordinates.
+bba_status MakePitchedU8Texture(bba_handle h, uint8_t* data, size_t pitch, int w, int ht, cudaTextureObject_t* out) {
+  cudaResourceDesc res;
+  std::memset(&res, 0, sizeof(res));
+  res.resType = cudaResourceTypePitch2D;
+  res.res.pitch2D.devPtr = data;
+  res.res.pitch2D.desc = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
+  res.res.pitch2D.width = w;
+  res.res.pitch2D.height = ht;
+  res.res.pitch2D.pitchInBytes = pitch;
+  cudaTextureDesc tex;
+  std::memset(&tex, 0, sizeof(tex));
+  tex.addressMode[0] = cudaAddressModeClamp;
+  tex.addressMode[1] = cudaAddressModeClamp;
+  tex.filterMode = cudaFilterModeLinear;
+  tex.readMode = cudaReadModeNormalizedFloat;
+  tex.normalizedCoords = 0;
+  BBA_CUDA(h, cudaCreateTextureObject(out, &res, &tex, nullptr));
+  return BBA_OK;
+}
+
+// PairwiseFrameTrackingBuffers + CreatePairwiseTrackingInputBuffersAndTextures (pairwise_frame_tracking.cc:39-151)
+bba_status EnsureOdometry(bba_handle h, int num_scales) {
+  auto& o = h->odo;
+  if (o.num_scales >= num_scales) return BBA_OK;
+  FreeOdometry(h);
+  const int cw = h->cfg.color_width, ch = h->cfg.color_height;
+  for (int f = 0; f < 2; ++f) {
+    BBA_CUDA(h, cudaMallocPitch(reinterpret_cast<void**>(&o.gradmag[f]), &o.gradmag_pitch[f], cw, ch));
+    if (bba_status st = MakePitchedU8Texture(h, o.gradmag[f], o.gradmag_pitch[f], cw, ch, &o.gradmag_tex[f])) return st;
+  }
+  for (int s = 0; s < num_scales; ++s) {
+    // pairwise_frame_tracking.cc:51-53: int scale_width = depth_width / pow(2, scale)
+    o.w[s] = static_cast<int>(h->cfg.depth_width / std::pow(2, s));
+    o.h[s] = static_cast<int>(h->cfg.depth_height / std::pow(2, s));
+    if (o.w[s] < 1 || o.h[s] < 1) return Fail(h, BBA_ERR_INVALID_ARGUMENT, "bba_track_frame_pairwise: too many pyramid levels for this image size");
+    for (int f = 0; f < 2; ++f) {
+      bba::odom::Image& im = o.image[f][s];
+      size_t pitch = 0;
+      BBA_CUDA(h, cudaMallocPitch(reinterpret_cast<void**>(&im.depth), &pitch, sizeof(float) * o.w[s], o.h[s]));
+      im.depth_pitch = static_cast<uint32_t>(pitch / sizeof(float));
+      if (s >= 1) {   // level 0 uses the caller's normal images
+        BBA_CUDA(h, cudaMallocPitch(reinterpret_cast<void**>(&im.normals), &pitch, sizeof(uint16_t) * o.w[s], o.h[s]));
+        im.normals_pitch = static_cast<uint32_t>(pitch);
+        o.owns_normals[f][s] = true;
+      }
+      BBA_CUDA(h, cudaMallocPitch(reinterpret_cast<void**>(&im.color), &pitch, o.w[s], o.h[s]));
+      im.color_pitch = static_cast<uint32_t>(pitch);
+      if (bba_status st = MakePitchedU8Texture(h, im.color, pitch, o.w[s], o.h[s], &im.color_tex)) return st;
+    }
+  }
+  BBA_CUDA(h, cudaMalloc(&o.d_acc, sizeof(double) * 96));
+  BBA_CUDA(h, cudaMalloc(&o.d_barrier, sizeof(unsigned int) * 2));
+  BBA_CUDA(h, cudaMalloc(&o.d_result, sizeof(bba::odom::TrackResult)));
+  BBA_CUDA(h, cudaMallocHost(&o.h_result, sizeof(bba::odom::TrackResult)));
+  o.num_scales = num_scales;
+  return BBA_OK;
+}
+
+// The camera model of one pyramid level: PinholeCamera4f::Scaled (libvis camera.h:1696-1705, 1086-1097: all four parameters
+// times the factor, width = factor * width + 0.5) through the builders of surfel_projection.h:42-124.
+bba::odom::LevelCamera MakeLevelCamera(bba_handle h, int scale, int level_w, int level_h) {
+  bba::odom::LevelCamera c;
+  const float scaling_factor = static_cast<float>(std::pow(2, scale));
+  const float df = static_cast<float>(1.f / scaling_factor);   // depth_camera.Scaled(1.f / scaling_factor)
+  const float cf = static_cast<float>((h->cfg.depth_width == h->cfg.color_width) ? (1.f / scaling_factor) : (2.f / scaling_factor));
+  const float dK[4] = {h->depth_K[0] * df, h->depth_K[1] * df, h->depth_K[2] * df, h->depth_K[3] * df};
+  const float cK[4] = {h->color_K[0] * cf, h->color_K[1] * cf, h->color_K[2] * cf, h->color_K[3] * cf};
+  c.w = level_w; c.h = level_h;
+  c.fx = dK[0]; c.fy = dK[1]; c.cx = dK[2]; c.cy = dK[3];
+  c.fx_inv = 1.0f / dK[0];
+  c.fy_inv = 1.0f / dK[1];
+  c.cx_inv = -(dK[2] - 0.5f) * c.fx_inv;
+  c.cy_inv = -(dK[3] - 0.5f) * c.fy_inv;
+  c.d2c_fx = cK[0] / dK[0];
+  c.d2c_cx = -1 * cK[0] * dK[2] / dK[0] + cK[2];
+  c.d2c_fy = cK[1] / dK[1];
+  c.d2c_cy = -1 * cK[1] * dK[3] / dK[1] + cK[3];
+  c.cw = static_cast<int>(static_cast<double>(cf) * h->cfg.color_width + 0.5f);
+  c.ch = static_cast<int>(static_cast<double>(cf) * h->cfg.color_height + 0.5f);
+  c.cfx = cK[0]; c.cfy = cK[1];
+  return c;
+}
+
 bba_status AddKeyframeCommon(bba_handle h, Keyframe&& kf, const uint8_t* device_rgba, size_t color_pitch, const float pose[7],
                              float min_depth, float max_depth, cudaStream_t s, int* out_id) {
   if (static_cast<int>(h->keyframes.size()) >= h->cfg.max_keyframes) return Fail(h, BBA_ERR_STATE, "max_keyframes exceeded");
@@ -1518,6 +1650,7 @@ void bba_destroy(bba_handle h) {
   cudaFree(h->d_compact_sums);
   cudaFree(h->d_min_max);
   cudaFreeHost(h->h_min_max);
+  FreeOdometry(h);
   if (h->scratch_tex) cudaDestroyTextureObject(h->scratch_tex);
   if (h->scratch_luma) cudaFreeArray(h->scratch_luma);
   for (float* v : h->d_pcg) cudaFree(v);
@@ -1884,6 +2017,185 @@ bba_status bba_estimate_frame_pose_for_frame(bba_handle h, const uint16_t* devic
   std::memcpy(out, h->h_pose_est + 7 * id, sizeof(float) * 7);
   if (iterations) *iterations = h->h_iterations[id];
   if (converged) *converged = h->h_converged[id];
+  return BBA_OK;
+}
+
+namespace {
+
+// Fills the pyramids of both frames for the given options (stages 1-3 of odometry.cuh) and the level descriptors in h->odo.level.
+bba_status BuildOdometryPyramids(bba_handle h, const bba_odometry_options& o, const Keyframe& base, const uint16_t* trk_depth, size_t trk_depth_pitch,
+                                 const uint16_t* trk_normals, size_t trk_normals_pitch, cudaStream_t s) {
+  namespace od = bba::odom;
+  auto& st = h->odo;
+  const int S = o.num_scales;
+  od::BrightnessArgs br{};
+  br.luma_tex[0] = base.tex; br.luma_tex[1] = h->scratch_tex;
+  for (int f = 0; f < 2; ++f) { br.out[f] = st.gradmag[f]; br.out_pitch[f] = static_cast<uint32_t>(st.gradmag_pitch[f]); }
+  br.w = h->cfg.color_width; br.h = h->cfg.color_height;
+  br.use_gradmag = o.use_gradmag;
+  od::LaunchBrightness(br, s);
+  ++h->launches;
+
+  // level images as seen by the kernels: level 0 normals are the keyframe's / the frame's own buffers
+  od::Image img[2][od::kMaxScales];
+  for (int f = 0; f < 2; ++f)
+    for (int l = 0; l < S; ++l) img[f][l] = st.image[f][l];
+  img[0][0].normals = const_cast<uint16_t*>(base.normals); img[0][0].normals_pitch = static_cast<uint32_t>(base.normals_pitch);
+  img[1][0].normals = const_cast<uint16_t*>(trk_normals);  img[1][0].normals_pitch = static_cast<uint32_t>(trk_normals_pitch);
+
+  const bba::CameraParams cam = MakeCamera(h);
+  od::Level0Args l0{};
+  l0.raw_depth[0] = base.depth; l0.raw_depth_pitch[0] = static_cast<uint32_t>(base.depth_pitch);
+  l0.raw_depth[1] = trk_depth;  l0.raw_depth_pitch[1] = static_cast<uint32_t>(trk_depth_pitch);
+  l0.raw_normals = trk_normals; l0.raw_normals_pitch = static_cast<uint32_t>(trk_normals_pitch);
+  l0.gradmag_tex[0] = st.gradmag_tex[0]; l0.gradmag_tex[1] = st.gradmag_tex[1];
+  l0.out[0] = img[0][0];
+  l0.skip_level0 = o.use_pyramid_level_0 ? 0 : 1;
+  l0.out[1] = l0.skip_level0 ? img[1][1] : img[1][0];
+  l0.w = st.w[0]; l0.h = st.h[0];
+  l0.out_w = l0.skip_level0 ? st.w[1] : st.w[0];
+  l0.out_h = l0.skip_level0 ? st.h[1] : st.h[0];
+  l0.d2c_fx = cam.d2c_fx; l0.d2c_fy = cam.d2c_fy; l0.d2c_cx = cam.d2c_cx; l0.d2c_cy = cam.d2c_cy;
+  l0.cw = cam.cw; l0.ch = cam.ch;
+  l0.a = cam.a; l0.raw_to_float = cam.raw_to_float; l0.cfactor = cam.cfactor; l0.cf_w = cam.cf_w; l0.cell = cam.cell;
+  l0.downsample_color = h->cfg.depth_width == h->cfg.color_width;
+  od::LaunchLevel0(l0, s);
+  ++h->launches;
+
+  for (int l = 1; l < S; ++l) {
+    // pairwise_frame_tracking.cc:325-347: the tracked image from level 2 on (level 1 too when level 0 is in use), the base always
+    od::DownsampleArgs d{};
+    d.in[0] = img[0][l - 1]; d.out[0] = img[0][l];
+    d.count = 1;
+    if (l >= 2 || o.use_pyramid_level_0) {
+      d.in[1] = img[1][l - 1]; d.out[1] = img[1][l];
+      d.count = 2;
+    }
+    d.w = st.w[l]; d.h = st.h[l];
+    od::LaunchDownsample(d, s);
+    ++h->launches;
+  }
+  for (int l = 0; l < S; ++l) {
+    st.level[l].cam = MakeLevelCamera(h, l, st.w[l], st.h[l]);
+    st.level[l].base = img[0][l];
+    st.level[l].tracked = img[1][l];
+  }
+  st.last_num_scales = S;
+  st.last_first_scale = o.use_pyramid_level_0 ? 0 : 1;
+  BBA_CUDA(h, cudaGetLastError());
+  return BBA_OK;
+}
+
+bba_status LaunchOdometryKernel(bba_handle h, int num_scales, int first_scale, int max_iterations, int use_gradmag, int test_different,
+                                int debug_scale, const float init1[7], const float init2[7], cudaStream_t s) {
+  namespace od = bba::odom;
+  auto& st = h->odo;
+  od::TrackArgs a{};
+  for (int l = 0; l < num_scales; ++l) a.level[l] = st.level[l];
+  a.num_scales = num_scales;
+  a.first_scale = first_scale;
+  a.max_iterations = max_iterations;
+  a.use_depth = h->cfg.use_depth_residuals;
+  a.use_desc = h->cfg.use_descriptor_residuals;
+  a.use_gradmag = use_gradmag;
+  a.test_different_initial_estimates = test_different;
+  a.debug_scale = debug_scale;
+  a.baseline_fx = h->cfg.baseline_fx;
+  std::memcpy(a.init1, init1, sizeof(float) * 7);
+  std::memcpy(a.init2, init2, sizeof(float) * 7);
+  a.acc = st.d_acc;
+  a.barrier = st.d_barrier;
+  a.result = st.d_result;
+  BBA_CUDA(h, cudaMemsetAsync(st.d_acc, 0, sizeof(double) * 96, s));
+  BBA_CUDA(h, cudaMemsetAsync(st.d_barrier, 0, sizeof(unsigned int) * 2, s));
+  BBA_CUDA(h, cudaMemsetAsync(st.d_result, 0, sizeof(od::TrackResult), s));
+  od::LaunchTrack(a, h->sm_count, s);
+  ++h->launches;
+  BBA_CUDA(h, cudaGetLastError());
+  BBA_CUDA(h, cudaMemcpyAsync(st.h_result, st.d_result, sizeof(od::TrackResult), cudaMemcpyDeviceToHost, s));
+  BBA_CUDA(h, cudaStreamSynchronize(s));
+  return BBA_OK;
+}
+
+}  // namespace
+
+bba_status bba_track_frame_pairwise(bba_handle h, const bba_odometry_options* o, int base_keyframe_id,
+                                    const uint16_t* device_depth, size_t depth_pitch, const uint16_t* device_normals, size_t normals_pitch,
+                                    const uint8_t* device_color_rgba, size_t color_pitch, const float init1[7], const float init2[7],
+                                    float out[7], bba_odometry_result* result, void* stream) {
+  if (!h || !o || !device_depth || !device_normals || !device_color_rgba || !init1 || !out) return h ? Fail(h, BBA_ERR_INVALID_ARGUMENT, "bba_track_frame_pairwise: null argument") : BBA_ERR_INVALID_ARGUMENT;
+  if (base_keyframe_id < 0 || base_keyframe_id >= static_cast<int>(h->keyframes.size()))
+    return Fail(h, BBA_ERR_INVALID_ARGUMENT, "bba_track_frame_pairwise: no such keyframe");
+  if (o->num_scales < 1 || o->num_scales > bba::odom::kMaxScales || (!o->use_pyramid_level_0 && o->num_scales < 2))
+    return Fail(h, BBA_ERR_INVALID_ARGUMENT, "bba_track_frame_pairwise: num_scales must be 1..8 (>= 2 without pyramid level 0)");
+  if (depth_pitch < static_cast<size_t>(h->cfg.depth_width) * 2 || normals_pitch < static_cast<size_t>(h->cfg.depth_width) * 2 ||
+      color_pitch < static_cast<size_t>(h->cfg.color_width) * 4 || depth_pitch > 0xffffffffull || normals_pitch > 0xffffffffull ||
+      ((depth_pitch | normals_pitch) & 1u))
+    return Fail(h, BBA_ERR_INVALID_ARGUMENT, "bba_track_frame_pairwise: bad frame buffer pitch");
+  // pairwise_frame_tracking.cc:300-306 (LOG(FATAL) in the reference)
+  if (!o->use_pyramid_level_0 && h->cfg.depth_width != h->cfg.color_width && h->cfg.depth_width != 2 * h->cfg.color_width)
+    return Fail(h, BBA_ERR_UNSUPPORTED, "The chosen depth / color pyramid level combination is not supported here.");
+  if (o->test_different_initial_estimates && !init2)
+    return Fail(h, BBA_ERR_INVALID_ARGUMENT, "bba_track_frame_pairwise: test_different_initial_estimates needs the second estimate");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const uint64_t launches_before = h->launches;
+  if (bba_status st = EnsureOdometry(h, o->num_scales)) return st;
+  if (bba_status st = MakeLumaTexture(h, device_color_rgba, color_pitch, &h->scratch_luma, &h->scratch_tex, s)) return st;
+  const Keyframe& base = h->keyframes[base_keyframe_id];
+  if (bba_status st = BuildOdometryPyramids(h, *o, base, device_depth, depth_pitch, device_normals, normals_pitch, s)) return st;
+  const int max_it = o->max_iterations_per_scale > 0 ? o->max_iterations_per_scale : 30;
+  if (bba_status st = LaunchOdometryKernel(h, o->num_scales, o->use_pyramid_level_0 ? 0 : 1, max_it, o->use_gradmag ? 1 : 0,
+                                           o->test_different_initial_estimates ? 1 : 0, -1, init1, init2 ? init2 : init1, s))
+    return st;
+  const bba::odom::TrackResult& r = *h->odo.h_result;
+  std::memcpy(out, r.base_T_frame, sizeof(float) * 7);
+  if (result) {
+    for (int i = 0; i < 8; ++i) {
+      result->iterations[i] = r.iterations[i];
+      result->chose_initial[i] = i < o->num_scales ? r.chose_initial[i] : -1;
+    }
+    result->residual_count = r.residual_count;
+    result->residual_sum = r.residual_sum;
+    result->passes = r.passes;
+    result->kernel_launches = static_cast<uint32_t>(h->launches - launches_before);
+  }
+  return BBA_OK;
+}
+
+bba_status bba_odometry_get_level(bba_handle h, int which, int scale, float* host_depth, uint16_t* host_normals, uint8_t* host_color,
+                                  int* width, int* height, void* stream) {
+  if (!h) return BBA_ERR_INVALID_ARGUMENT;
+  auto& st = h->odo;
+  if (which < 0 || which > 1 || scale < 0 || scale >= st.last_num_scales || (which == 1 && scale < st.last_first_scale))
+    return Fail(h, BBA_ERR_STATE, "bba_odometry_get_level: this level was not built by the last bba_track_frame_pairwise call");
+  const bba::odom::Image& im = which ? st.level[scale].tracked : st.level[scale].base;
+  const int w = st.w[scale], ht = st.h[scale];
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (host_depth) BBA_CUDA(h, cudaMemcpy2DAsync(host_depth, sizeof(float) * w, im.depth, sizeof(float) * im.depth_pitch, sizeof(float) * w, ht, cudaMemcpyDeviceToHost, s));
+  if (host_normals) BBA_CUDA(h, cudaMemcpy2DAsync(host_normals, sizeof(uint16_t) * w, im.normals, im.normals_pitch, sizeof(uint16_t) * w, ht, cudaMemcpyDeviceToHost, s));
+  if (host_color) BBA_CUDA(h, cudaMemcpy2DAsync(host_color, w, im.color, im.color_pitch, w, ht, cudaMemcpyDeviceToHost, s));
+  BBA_CUDA(h, cudaStreamSynchronize(s));
+  if (width) *width = w;
+  if (height) *height = ht;
+  return BBA_OK;
+}
+
+bba_status bba_odometry_debug_coeffs(bba_handle h, int scale, int use_gradmag, const float pose_a[7], const float pose_b[7], float H[21],
+                                     float b[6], uint32_t* residual_count, float* residual_sum, uint32_t counts[2], float costs[2], void* stream) {
+  if (!h || !pose_a) return BBA_ERR_INVALID_ARGUMENT;
+  auto& st = h->odo;
+  if (scale < st.last_first_scale || scale >= st.last_num_scales)
+    return Fail(h, BBA_ERR_STATE, "bba_odometry_debug_coeffs: this level was not built by the last bba_track_frame_pairwise call");
+  if (bba_status s2 = LaunchOdometryKernel(h, st.last_num_scales, st.last_first_scale, 1, use_gradmag ? 1 : 0, 0, scale, pose_a,
+                                           pose_b ? pose_b : pose_a, static_cast<cudaStream_t>(stream)))
+    return s2;
+  const double* d = st.h_result->debug;
+  if (H) for (int i = 0; i < 21; ++i) H[i] = static_cast<float>(d[i]);
+  if (b) for (int i = 0; i < 6; ++i) b[i] = static_cast<float>(d[21 + i]);
+  if (residual_count) *residual_count = static_cast<uint32_t>(d[27] + 0.5);
+  if (residual_sum) *residual_sum = static_cast<float>(d[28]);
+  if (counts) { counts[0] = static_cast<uint32_t>(d[32] + 0.5); counts[1] = static_cast<uint32_t>(d[34] + 0.5); }
+  if (costs) { costs[0] = static_cast<float>(d[33]); costs[1] = static_cast<float>(d[35]); }
   return BBA_OK;
 }
 

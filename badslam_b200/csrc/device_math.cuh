@@ -111,6 +111,23 @@ __device__ __forceinline__ F2 Fma(F2 a, F2 b, F2 c) {   // a * b + c, fused
   return r;
 }
 
+// Sums acc[i] over the 32 lanes of the warp for all 32 i at once: after the call lane L holds the total of
+// acc[L].  16+8+4+2+1 = 31 shuffles instead of 32 x 5.
+__device__ __forceinline__ float WarpTransposeReduce(float (&v)[32], int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float lo = v[i], hi = v[i + half];
+      const float send = upper ? lo : hi;
+      const float keep = upper ? hi : lo;
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return v[0];
+}
+
 // robust_weighting.cuh:39-86
 __device__ __forceinline__ float TukeyResidual(float r, float p) {
   if (fabsf(r) < p) {

@@ -424,6 +424,52 @@ class DirectBA:
             out.ctypes.data_as(C.POINTER(C.c_float)), C.byref(it), C.byref(conv), self._stream_ptr(stream)))
         return out, it.value, bool(conv.value)
 
+    def TrackFramePairwise(self, stream, base_keyframe_id: int, depth_buffer: torch.Tensor, normals_buffer: torch.Tensor,
+                           color_buffer: torch.Tensor, base_T_frame_initial_estimate_1, base_T_frame_initial_estimate_2=None,
+                           num_scales: int = 5, use_pyramid_level_0: bool = True, use_gradmag: bool = False,
+                           test_different_initial_estimates: bool = True, max_iterations_per_scale: int = 30):
+        """BadSlam::RunOdometry -> TrackFramePairwise (bad_slam.cc:829-950, pairwise_frame_tracking.cc:153-678): the frame given by
+        depth / normals [h, w] u16 and colour [ch, cw, 4] u8 (.w = luma) device tensors is tracked against keyframe
+        `base_keyframe_id`.  Defaults = what RunOdometry passes.  Returns (base_T_frame_estimate, OdometryResult)."""
+        p1 = np.ascontiguousarray(base_T_frame_initial_estimate_1, np.float32)
+        p2 = p1 if base_T_frame_initial_estimate_2 is None else np.ascontiguousarray(base_T_frame_initial_estimate_2, np.float32)
+        out = np.zeros(7, np.float32)
+        o = _lib.OdometryOptions(int(num_scales), int(use_pyramid_level_0), int(use_gradmag), int(test_different_initial_estimates),
+                                 int(max_iterations_per_scale))
+        res = _lib.OdometryResult()
+        F = C.POINTER(C.c_float)
+        self._check(self._lib.bba_track_frame_pairwise(
+            self._h, C.byref(o), int(base_keyframe_id), depth_buffer.data_ptr(), depth_buffer.stride(0) * 2, normals_buffer.data_ptr(),
+            normals_buffer.stride(0) * 2, color_buffer.data_ptr(), color_buffer.stride(0), p1.ctypes.data_as(F), p2.ctypes.data_as(F),
+            out.ctypes.data_as(F), C.byref(res), self._stream_ptr(stream)))
+        return out, res
+
+    def OdometryLevel(self, which: int, scale: int, stream=None):
+        """Parity hook: (depth f32, normals u16, colour u8) of one pyramid level of the last TrackFramePairwise call
+        (which: 0 = base keyframe, 1 = tracked frame)."""
+        w, h = C.c_int(), C.c_int()
+        self._check(self._lib.bba_odometry_get_level(self._h, which, scale, None, None, None, C.byref(w), C.byref(h), self._stream_ptr(stream)))
+        d = np.zeros((h.value, w.value), np.float32)
+        n = np.zeros((h.value, w.value), np.uint16)
+        c = np.zeros((h.value, w.value), np.uint8)
+        self._check(self._lib.bba_odometry_get_level(self._h, which, scale, d.ctypes.data, n.ctypes.data, c.ctypes.data, C.byref(w),
+                                                     C.byref(h), self._stream_ptr(stream)))
+        return d, n, c
+
+    def OdometryCoeffs(self, scale: int, base_T_frame_a, base_T_frame_b=None, use_gradmag: bool = False, stream=None):
+        """Parity hook on the pyramids of the last TrackFramePairwise call: AccumulatePoseEstimationCoeffsFromImagesCUDA at pose a
+        -> (H[21], b[6], residual_count, residual_sum) and ComputeCostAndResidualCountFromImagesCUDA at a and b -> (counts[2], costs[2])."""
+        pa = np.ascontiguousarray(base_T_frame_a, np.float32)
+        pb = pa if base_T_frame_b is None else np.ascontiguousarray(base_T_frame_b, np.float32)
+        H, b = np.zeros(21, np.float32), np.zeros(6, np.float32)
+        cnt, rs = C.c_uint32(), C.c_float()
+        counts, costs = np.zeros(2, np.uint32), np.zeros(2, np.float32)
+        F = C.POINTER(C.c_float)
+        self._check(self._lib.bba_odometry_debug_coeffs(self._h, scale, int(use_gradmag), pa.ctypes.data_as(F), pb.ctypes.data_as(F),
+                                                        H.ctypes.data, b.ctypes.data, C.byref(cnt), C.byref(rs), counts.ctypes.data,
+                                                        costs.ctypes.data, self._stream_ptr(stream)))
+        return H, b, cnt.value, rs.value, counts, costs
+
     def UpdateSurfelActivation(self, stream=None):
         self._check(self._lib.bba_update_surfel_activation(self._h, self._stream_ptr(stream)))
 

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BBA_ABI_VERSION 6
+#define BBA_ABI_VERSION 7
 
 typedef struct bba_context* bba_handle;
 
@@ -333,6 +333,50 @@ bba_status bba_preprocess_frame(bba_handle h, const bba_preprocess_options* opti
                                 uint16_t* device_radius, size_t radius_pitch,
                                 uint8_t* device_color_rgba, size_t color_pitch,
                                 float* min_depth, float* max_depth, void* stream);
+
+/* ---- image-pair odometry: a new frame tracked against a stored keyframe ----
+ * BadSlam::RunOdometry (bad_slam.cc:829-950) -> TrackFramePairwise (pairwise_frame_tracking.cc:153-678): intensity (or Sobel
+ * gradient magnitude) images of both frames (cuda_image_processing.cu:103-206), calibrated float depth of both, the base
+ * keyframe's colour transformed to the depth intrinsics (kernel_downsample.cu:345-372), the depth / normal / colour pyramids
+ * (kernel_downsample.cu:40-156), and on every level from coarse to fine: the cost comparison between the previous result and
+ * the initial estimate (kernel_opt_pose.cu:939-1296, pairwise_frame_tracking.cc:427-508) and up to 30 damped Gauss-Newton
+ * iterations on depth + descriptor (or gradient-magnitude) residuals of every base pixel projected into the tracked frame
+ * (kernel_opt_pose.cu:422-885; fp64 LDLT + SE3 update pairwise_frame_tracking.cc:553-593; convergence_analysis.h:56-63).
+ * The pyramids are one launch per level for both images; the whole coarse-to-fine optimisation is ONE persistent kernel
+ * launch with no host round trip (the reference synchronises the stream once per iteration).
+ * The tracked frame is given like in bba_estimate_frame_pose_for_frame (preprocessed depth, normals, uchar4 colour with
+ * .w = luma); poses are base_T_frame as {qx,qy,qz,qw,tx,ty,tz}.  Uses the handle's cameras, depth deformation and residual types. */
+typedef struct {
+  int num_scales;                        /* BadSlamConfig::num_scales, default 5 (bad_slam_config.h:167); 1..8 */
+  int use_pyramid_level_0;               /* RunOdometry passes true (bad_slam.cc:923) */
+  int use_gradmag;                       /* RunOdometry passes false: separate x/y gradient components (bad_slam.cc:833) */
+  int test_different_initial_estimates;  /* RunOdometry passes true: the two motion-model predictions are compared on the coarsest level */
+  int max_iterations_per_scale;          /* kMaxIterationsPerScale = 30 (pairwise_frame_tracking.cc:247); <= 0 selects it */
+} bba_odometry_options;
+typedef struct {
+  int iterations[8];        /* Gauss-Newton iterations per pyramid level (index = scale) */
+  int chose_initial[8];     /* 1: the initial-estimate arm won the cost comparison on this level, 0: the other arm, -1: no comparison */
+  uint32_t residual_count;  /* the reference's debug counters at the last accumulation (kernel_opt_pose.cu:619-657) */
+  float residual_sum;
+  uint32_t passes;          /* image passes (grid-wide barriers) of the persistent kernel */
+  uint32_t kernel_launches; /* launches of the whole call */
+} bba_odometry_result;
+bba_status bba_track_frame_pairwise(bba_handle h, const bba_odometry_options* options, int base_keyframe_id,
+                                    const uint16_t* device_depth, size_t depth_pitch,
+                                    const uint16_t* device_normals, size_t normals_pitch,
+                                    const uint8_t* device_color_rgba, size_t color_pitch,
+                                    const float base_T_frame_initial_1[7], const float base_T_frame_initial_2[7],
+                                    float base_T_frame_estimate[7], bba_odometry_result* result, void* stream);
+/* Parity hooks (the pyramids and normal equations of the LAST bba_track_frame_pairwise call of this handle, device-resident):
+ *  bba_odometry_get_level: one pyramid level of the base (which = 0) or tracked (1) image into dense host arrays
+ *    [height][width] (any may be NULL); *width / *height return the level's size.
+ *  bba_odometry_debug_coeffs: AccumulatePoseEstimationCoeffsFromImagesCUDA (kernels.h:181-203) at base_T_frame_a -> H[21], b[6],
+ *    residual count / sum, and ComputeCostAndResidualCountFromImagesCUDA (kernels.h:205-223) at both poses -> counts[2], costs[2]. */
+bba_status bba_odometry_get_level(bba_handle h, int which, int scale, float* host_depth, uint16_t* host_normals, uint8_t* host_color,
+                                  int* width, int* height, void* stream);
+bba_status bba_odometry_debug_coeffs(bba_handle h, int scale, int use_gradmag, const float base_T_frame_a[7], const float base_T_frame_b[7],
+                                     float H[21], float b[6], uint32_t* residual_count, float* residual_sum,
+                                     uint32_t counts[2], float costs[2], void* stream);
 
 /* ---- host-side building blocks (no handle, no device) ----
  * The host arithmetic the backend runs between kernels, exported so that it can be checked without a GPU: Sophus'

@@ -26,7 +26,7 @@ SRCS=("$B/kernel_opt_pose.cu" "$B/kernel_opt_geometry.cu" "$B/kernel_surfel_acti
       "$B/kernel_opt_intrinsics.cu" "$B/kernel_pcg.cu"
       "$B/kernel_delete_surfels.cu" "$B/kernel_supporting_surfels.cu"
       "$B/kernel_compact_surfels.cu" "$B/kernel_create_surfels.cu"
-      "$B/cuda_depth_processing.cu" "$B/cuda_image_processing.cu"
+      "$B/cuda_depth_processing.cu" "$B/cuda_image_processing.cu" "$B/kernel_downsample.cu"
       "$REF/libvis/src/libvis/cuda/cuda_buffer.cu")
 pids=()
 for s in "${SRCS[@]}"; do

@@ -62,6 +62,19 @@ void UpdateSurfelsFromPCGDeltaCUDA(cudaStream_t stream, u32 surfels_size, CUDABu
                                    u32 surfel_unknown_start_index, const CUDABuffer_<PCGScalar>& pcg_delta);
 void UpdateCFactorsFromPCGDeltaCUDA(cudaStream_t stream, CUDABuffer_<float>* cfactor_buffer, u32 cfactor_unknown_start_index,
                                     const CUDABuffer_<PCGScalar>& pcg_delta);
+// kernel_downsample.cu (kernels.h:338-378)
+void CalibrateDepthAndTransformColorToDepthCUDA(cudaStream_t stream, const DepthToColorPixelCorner& depth_to_color,
+                                                const DepthParameters& depth_params, const CUDABuffer_<u16>& depth_buffer,
+                                                cudaTextureObject_t color_texture, CUDABuffer_<float>* out_depth, CUDABuffer_<u8>* out_color);
+void CalibrateDepthCUDA(cudaStream_t stream, const DepthParameters& depth_params, const CUDABuffer_<u16>& depth_buffer,
+                        CUDABuffer_<float>* out_depth);
+void CalibrateAndDownsampleImagesCUDA(cudaStream_t stream, bool downsample_color, const DepthParameters& depth_params,
+                                      const CUDABuffer_<u16>& depth_buffer, const CUDABuffer_<u16>& normals_buffer,
+                                      cudaTextureObject_t color_texture, CUDABuffer_<float>* downsampled_depth,
+                                      CUDABuffer_<u16>* downsampled_normals, CUDABuffer_<u8>* downsampled_color, bool debug);
+void DownsampleImagesCUDA(cudaStream_t stream, const CUDABuffer_<float>& depth_buffer, const CUDABuffer_<u16>& normals_buffer,
+                          cudaTextureObject_t color_texture, CUDABuffer_<float>* downsampled_depth,
+                          CUDABuffer_<u16>* downsampled_normals, CUDABuffer_<u8>* downsampled_color, bool debug);
 void CompactSurfelsCUDA(cudaStream_t stream, void** free_spots_temp_storage, usize* free_spots_temp_storage_bytes, u32 surfel_count,
                         u32* surfels_size, CUDABuffer_<float>* surfels, CUDABuffer_<u8>* active_surfels);   // kernels.h:292-299
 }  // namespace vis
@@ -134,6 +147,13 @@ struct ref_context {
   u32* sup[3] = {nullptr, nullptr, nullptr}; size_t sup_pitch = 0;
   u8* new_flag = nullptr; u32* new_indices = nullptr; void* new_temp = nullptr; usize new_temp_bytes = 0;
   float surfel_merge_dist_factor = 0.8f;      // bad_slam_config.h
+  // image-pair odometry (PairwiseFrameTrackingBuffers + the RunOdometry inputs), lazily allocated by ref_track_frame_pairwise
+  struct OdoImage { float* depth = nullptr; size_t depth_pitch = 0; u16* normals = nullptr; size_t normals_pitch = 0;
+                    u8* color = nullptr; size_t color_pitch = 0; cudaTextureObject_t tex = 0; int w = 0, h = 0; bool owns_normals = false; };
+  OdoImage odo[2][8];            // [0 base | 1 tracked][scale]
+  u8* odo_gradmag[2] = {nullptr, nullptr}; size_t odo_gradmag_pitch[2] = {0, 0}; cudaTextureObject_t odo_gradmag_tex[2] = {0, 0};
+  RefKeyframe odo_frame;         // the tracked frame's device images
+  int odo_scales = 0;
 };
 
 extern "C" unsigned int ref_end_tasks(ref_context* c);
@@ -1111,5 +1131,343 @@ void ref_restore(ref_context* c) {
 void ref_sync(ref_context* c) { cudaStreamSynchronize(c->stream); }
 
 const char* ref_last_cuda_error(void) { return cudaGetErrorString(cudaGetLastError()); }
+
+}  // extern "C"
+
+// ---- image-pair odometry: BadSlam::RunOdometry (bad_slam.cc:829-950) + TrackFramePairwise (pairwise_frame_tracking.cc:153-678)
+// restated on the reference's own kernels (kernel_downsample.cu, cuda_image_processing.cu, kernel_opt_pose.cu:422-1340).
+namespace {
+
+cudaTextureObject_t MakeU8Texture(u8* data, size_t pitch, int w, int h) {   // CUDABuffer::CreateTextureObject as called in pairwise_frame_tracking.cc:57-79
+  cudaResourceDesc res;
+  std::memset(&res, 0, sizeof(res));
+  res.resType = cudaResourceTypePitch2D;
+  res.res.pitch2D.devPtr = data;
+  res.res.pitch2D.desc = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
+  res.res.pitch2D.width = w;
+  res.res.pitch2D.height = h;
+  res.res.pitch2D.pitchInBytes = pitch;
+  cudaTextureDesc td;
+  std::memset(&td, 0, sizeof(td));
+  td.addressMode[0] = cudaAddressModeClamp;
+  td.addressMode[1] = cudaAddressModeClamp;
+  td.filterMode = cudaFilterModeLinear;
+  td.readMode = cudaReadModeNormalizedFloat;
+  td.normalizedCoords = 0;
+  cudaTextureObject_t t = 0;
+  cudaCreateTextureObject(&t, &res, &td, nullptr);
+  return t;
+}
+
+void EnsureOdoBuffers(ref_context* c, int num_scales) {
+  if (c->odo_scales >= num_scales) return;
+  for (int f = 0; f < 2; ++f) {
+    if (!c->odo_gradmag[f]) {
+      cudaMallocPitch(reinterpret_cast<void**>(&c->odo_gradmag[f]), &c->odo_gradmag_pitch[f], c->cfg.color_w, c->cfg.color_h);
+      c->odo_gradmag_tex[f] = MakeU8Texture(c->odo_gradmag[f], c->odo_gradmag_pitch[f], c->cfg.color_w, c->cfg.color_h);
+    }
+    for (int sc = c->odo_scales; sc < num_scales; ++sc) {
+      ref_context::OdoImage& im = c->odo[f][sc];
+      im.w = static_cast<int>(c->cfg.depth_w / pow(2, sc));
+      im.h = static_cast<int>(c->cfg.depth_h / pow(2, sc));
+      cudaMallocPitch(reinterpret_cast<void**>(&im.depth), &im.depth_pitch, sizeof(float) * im.w, im.h);
+      if (sc >= 1) {
+        cudaMallocPitch(reinterpret_cast<void**>(&im.normals), &im.normals_pitch, sizeof(u16) * im.w, im.h);
+        im.owns_normals = true;
+      }
+      cudaMallocPitch(reinterpret_cast<void**>(&im.color), &im.color_pitch, im.w, im.h);
+      im.tex = MakeU8Texture(im.color, im.color_pitch, im.w, im.h);
+    }
+  }
+  c->odo_scales = num_scales;
+}
+
+CUDABuffer_<float> DepthBuf(const ref_context::OdoImage& im) { return CUDABuffer_<float>(im.depth, im.h, im.w, im.depth_pitch); }
+CUDABuffer_<u16> NormalsBuf(const ref_context::OdoImage& im) { return CUDABuffer_<u16>(im.normals, im.h, im.w, im.normals_pitch); }
+CUDABuffer_<u8> ColorBuf(const ref_context::OdoImage& im) { return CUDABuffer_<u8>(im.color, im.h, im.w, im.color_pitch); }
+
+// PinholeCamera4f::Scaled (libvis camera.h:1086-1097,1696-1705): parameters * factor, width = factor * width + 0.5
+void ScaledCamera(const float K[4], int w, int h, double factor, float out_K[4], int* out_w, int* out_h) {
+  const float f = static_cast<float>(factor);
+  for (int i = 0; i < 4; ++i) out_K[i] = K[i] * f;
+  *out_w = static_cast<int>(factor * w + 0.5f);
+  *out_h = static_cast<int>(factor * h + 0.5f);
+}
+
+struct OdoCameras {
+  float dK[4], cK[4];
+  int cw, ch;
+};
+OdoCameras ScaleCameras(ref_context* c, int scale) {   // pairwise_frame_tracking.cc:409-417
+  OdoCameras r;
+  const float scaling_factor = pow(2, scale);
+  int dw, dh;
+  ScaledCamera(c->cfg.color_K, c->cfg.color_w, c->cfg.color_h, (c->cfg.depth_w == c->cfg.color_w) ? (1.f / scaling_factor) : (2.f / scaling_factor),
+               r.cK, &r.cw, &r.ch);
+  ScaledCamera(c->cfg.depth_K, c->cfg.depth_w, c->cfg.depth_h, 1.f / scaling_factor, r.dK, &dw, &dh);
+  return r;
+}
+DepthToColorPixelCorner DepthToColorScaled(const OdoCameras& k) {   // surfel_projection.h:105-124
+  DepthToColorPixelCorner r;
+  r.width = k.cw;
+  r.height = k.ch;
+  r.fx = k.cK[0] / k.dK[0];
+  r.cx = -1 * k.cK[0] * k.dK[2] / k.dK[0] + k.cK[2];
+  r.fy = k.cK[1] / k.dK[1];
+  r.cy = -1 * k.cK[1] * k.dK[3] / k.dK[1] + k.cK[3];
+  return r;
+}
+
+CUDAMatrix3x4 FrameTBase(const float base_T_frame[7]) { return MakeFrameTGlobal(base_T_frame); }   // CUDAMatrix3x4(base_T_frame.inverse().matrix3x4())
+
+// AccumulatePoseEstimationCoeffsFromImagesCUDA, kernel_opt_pose.cc:99-191
+void OdoAccumulate(ref_context* c, int scale, const float base_T_frame[7], bool use_gradmag, bool debug, u32* count, float* sum, float H[21], float b[6]) {
+  cudaStream_t s = c->stream;
+  const OdoCameras k = ScaleCameras(c, scale);
+  const float threshold_factor = pow(2, scale);
+  if (debug) {
+    cudaMemsetAsync(c->residual_count, 0, sizeof(u32), s);
+    cudaMemsetAsync(c->residual_sum, 0, sizeof(float), s);
+    c->launches += 2;
+  }
+  cudaMemsetAsync(c->H, 0, sizeof(float) * 21, s);
+  cudaMemsetAsync(c->b, 0, sizeof(float) * 6, s);
+  c->launches += 2;
+  const ref_context::OdoImage& base = c->odo[0][scale];
+  const ref_context::OdoImage& trk = c->odo[1][scale];
+  CUDABuffer_<u32> cnt_buf(c->residual_count, 1, 1, sizeof(u32));
+  CUDABuffer_<float> sum_buf(c->residual_sum, 1, 1, sizeof(float)), H_buf(c->H, 1, 21, sizeof(float) * 21), b_buf(c->b, 1, 6, sizeof(float) * 6);
+  if (use_gradmag)
+    CallAccumulatePoseEstimationCoeffsFromImagesCUDAKernel_GradMag(
+        s, debug, c->cfg.use_depth_residuals != 0, c->cfg.use_descriptor_residuals != 0, CornerProjector(k.dK), CenterProjector(k.cK),
+        CenterUnprojector(k.dK), c->cfg.baseline_fx, DepthToColorScaled(k), threshold_factor, FrameTBase(base_T_frame), DepthBuf(base),
+        NormalsBuf(base), ColorBuf(base), DepthBuf(trk), NormalsBuf(trk), trk.tex, cnt_buf, sum_buf, H_buf, b_buf, nullptr);
+  else
+    CallAccumulatePoseEstimationCoeffsFromImagesCUDAKernel_GradientXY(
+        s, debug, c->cfg.use_depth_residuals != 0, c->cfg.use_descriptor_residuals != 0, CornerProjector(k.dK), CenterProjector(k.cK),
+        CenterUnprojector(k.dK), c->cfg.baseline_fx, DepthToColorScaled(k), threshold_factor, FrameTBase(base_T_frame), DepthBuf(base),
+        NormalsBuf(base), ColorBuf(base), DepthBuf(trk), NormalsBuf(trk), trk.tex, cnt_buf, sum_buf, H_buf, b_buf, nullptr);
+  ++c->launches;
+  if (debug) {
+    cudaMemcpyAsync(count, c->residual_count, sizeof(u32), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(sum, c->residual_sum, sizeof(float), cudaMemcpyDeviceToHost, s);
+  }
+  cudaMemcpyAsync(H, c->H, sizeof(float) * 21, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(b, c->b, sizeof(float) * 6, cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+}
+
+// ComputeCostAndResidualCountFromImagesCUDA, kernel_opt_pose.cc:194-260
+void OdoCost(ref_context* c, int scale, const float base_T_frame[7], bool use_gradmag, u32* count, float* cost) {
+  cudaStream_t s = c->stream;
+  const OdoCameras k = ScaleCameras(c, scale);
+  const float threshold_factor = pow(2, scale);
+  cudaMemsetAsync(c->residual_count, 0, sizeof(u32), s);
+  cudaMemsetAsync(c->residual_sum, 0, sizeof(float), s);
+  c->launches += 2;
+  const ref_context::OdoImage& base = c->odo[0][scale];
+  const ref_context::OdoImage& trk = c->odo[1][scale];
+  CUDABuffer_<u32> cnt_buf(c->residual_count, 1, 1, sizeof(u32));
+  CUDABuffer_<float> sum_buf(c->residual_sum, 1, 1, sizeof(float));
+  if (use_gradmag)
+    CallComputeCostAndResidualCountFromImagesCUDAKernel_GradMag(
+        s, c->cfg.use_depth_residuals != 0, c->cfg.use_descriptor_residuals != 0, CornerProjector(k.dK), CenterUnprojector(k.dK),
+        c->cfg.baseline_fx, DepthToColorScaled(k), threshold_factor, FrameTBase(base_T_frame), DepthBuf(base), NormalsBuf(base), ColorBuf(base),
+        DepthBuf(trk), NormalsBuf(trk), trk.tex, cnt_buf, sum_buf);
+  else
+    ComputeCostAndResidualCountFromImagesCUDAKernel_GradientXY(
+        s, c->cfg.use_depth_residuals != 0, c->cfg.use_descriptor_residuals != 0, CornerProjector(k.dK), CenterUnprojector(k.dK),
+        c->cfg.baseline_fx, DepthToColorScaled(k), threshold_factor, FrameTBase(base_T_frame), DepthBuf(base), NormalsBuf(base), ColorBuf(base),
+        DepthBuf(trk), NormalsBuf(trk), trk.tex, cnt_buf, sum_buf);
+  ++c->launches;
+  cudaMemcpyAsync(count, c->residual_count, sizeof(u32), cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(cost, c->residual_sum, sizeof(float), cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+}
+
+}  // namespace
+
+extern "C" {
+
+struct ref_odometry_result {
+  int iterations[8];
+  int chose_initial[8];
+  unsigned int residual_count;
+  float residual_sum;
+  unsigned long long kernel_launches;
+  float ms;   // wall time of the call after the uploads (pyramids + optimisation), stream-synchronised like the reference
+};
+
+// The tracked frame comes as dense host images (depth / normals u16 [h][w], colour uchar4 [ch][cw]); base = a stored keyframe.
+int ref_track_frame_pairwise(ref_context* c, int base_kf, const unsigned short* depth, const unsigned short* normals, const unsigned char* color_rgba,
+                             int num_scales, int use_pyramid_level_0, int use_gradmag, int test_different_initial_estimates,
+                             const float init1[7], const float init2[7], float out[7], ref_odometry_result* res) {
+  const ref_config& cfg = c->cfg;
+  cudaStream_t s = c->stream;
+  std::memset(res, 0, sizeof(*res));
+  EnsureOdoBuffers(c, num_scales);
+  RefKeyframe& fr = c->odo_frame;
+  if (!fr.depth) {
+    cudaMallocPitch(reinterpret_cast<void**>(&fr.depth), &fr.depth_pitch, cfg.depth_w * sizeof(u16), cfg.depth_h);
+    cudaMallocPitch(reinterpret_cast<void**>(&fr.normals), &fr.normals_pitch, cfg.depth_w * sizeof(u16), cfg.depth_h);
+    cudaMallocPitch(reinterpret_cast<void**>(&fr.color), &fr.color_pitch, cfg.color_w * sizeof(uchar4), cfg.color_h);
+    // Keyframe / frame colour texture (keyframe.cc:67-73, bad_slam.cc color_texture_): uchar4, normalised float, linear, clamp
+    cudaResourceDesc rd;
+    std::memset(&rd, 0, sizeof(rd));
+    rd.resType = cudaResourceTypePitch2D;
+    rd.res.pitch2D.devPtr = fr.color;
+    rd.res.pitch2D.desc = cudaCreateChannelDesc<uchar4>();
+    rd.res.pitch2D.width = cfg.color_w;
+    rd.res.pitch2D.height = cfg.color_h;
+    rd.res.pitch2D.pitchInBytes = fr.color_pitch;
+    cudaTextureDesc td;
+    std::memset(&td, 0, sizeof(td));
+    td.addressMode[0] = cudaAddressModeClamp;
+    td.addressMode[1] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeNormalizedFloat;
+    td.normalizedCoords = 0;
+    cudaCreateTextureObject(&fr.tex, &rd, &td, nullptr);
+  }
+  cudaMemcpy2D(fr.depth, fr.depth_pitch, depth, cfg.depth_w * sizeof(u16), cfg.depth_w * sizeof(u16), cfg.depth_h, cudaMemcpyHostToDevice);
+  cudaMemcpy2D(fr.normals, fr.normals_pitch, normals, cfg.depth_w * sizeof(u16), cfg.depth_w * sizeof(u16), cfg.depth_h, cudaMemcpyHostToDevice);
+  cudaMemcpy2D(fr.color, fr.color_pitch, color_rgba, cfg.color_w * 4, cfg.color_w * 4, cfg.color_h, cudaMemcpyHostToDevice);
+  cudaStreamSynchronize(s);
+  const unsigned long long launches_before = c->launches;
+  cudaEventRecord(c->ev[0], s);
+
+  const RefKeyframe& base = c->kfs[base_kf];
+  CUDABuffer_<u8> base_kf_gradmag(c->odo_gradmag[0], cfg.color_h, cfg.color_w, c->odo_gradmag_pitch[0]);
+  CUDABuffer_<u8> tracked_gradmag(c->odo_gradmag[1], cfg.color_h, cfg.color_w, c->odo_gradmag_pitch[1]);
+  // ---- BadSlam::RunOdometry, bad_slam.cc:863-902
+  if (use_gradmag) ComputeSobelGradientMagnitudeCUDA(s, base.tex, &base_kf_gradmag);
+  else ComputeBrightnessCUDA(s, base.tex, &base_kf_gradmag);
+  ++c->launches;
+  {
+    CUDABuffer_<float> d0 = DepthBuf(c->odo[0][0]);
+    CUDABuffer_<u8> c0 = ColorBuf(c->odo[0][0]);
+    CalibrateDepthAndTransformColorToDepthCUDA(s, DepthToColor(cfg), MakeDepthParams(c), CUDABuffer_<u16>(base.depth, cfg.depth_h, cfg.depth_w, base.depth_pitch),
+                                               c->odo_gradmag_tex[0], &d0, &c0);
+    ++c->launches;
+  }
+  if (use_gradmag) ComputeSobelGradientMagnitudeCUDA(s, fr.tex, &tracked_gradmag);
+  else ComputeBrightnessCUDA(s, fr.tex, &tracked_gradmag);
+  ++c->launches;
+
+  // ---- TrackFramePairwise, pairwise_frame_tracking.cc:153-678 (kDebug = false, no convergence-sample file)
+  // per-level image views: level 0 of the base uses the keyframe's normals, level 0 of the tracked frame the frame's
+  ref_context::OdoImage img[2][8];
+  for (int f = 0; f < 2; ++f)
+    for (int l = 0; l < num_scales; ++l) img[f][l] = c->odo[f][l];
+  img[0][0].normals = base.normals; img[0][0].normals_pitch = base.normals_pitch;
+  img[1][0].normals = fr.normals;   img[1][0].normals_pitch = fr.normals_pitch;
+  const CUDABuffer_<u16> tracked_depth_buffer(fr.depth, cfg.depth_h, cfg.depth_w, fr.depth_pitch);
+  const CUDABuffer_<u16> tracked_normals_buffer(fr.normals, cfg.depth_h, cfg.depth_w, fr.normals_pitch);
+  if (use_pyramid_level_0) {
+    CUDABuffer_<float> d = DepthBuf(img[1][0]);
+    CalibrateDepthCUDA(s, MakeDepthParams(c), tracked_depth_buffer, &d);
+    ++c->launches;
+    ColorBuf(img[1][0]).SetToReadModeNormalized(c->odo_gradmag_tex[1], s);
+    ++c->launches;
+  } else {
+    if (cfg.depth_w != cfg.color_w && cfg.depth_w != 2 * cfg.color_w) return 1;   // LOG(FATAL) in the reference
+    CUDABuffer_<float> d = DepthBuf(img[1][1]);
+    CUDABuffer_<u16> n = NormalsBuf(img[1][1]);
+    CUDABuffer_<u8> col = ColorBuf(img[1][1]);
+    CalibrateAndDownsampleImagesCUDA(s, cfg.depth_w == cfg.color_w, MakeDepthParams(c), tracked_depth_buffer, tracked_normals_buffer,
+                                     c->odo_gradmag_tex[1], &d, &n, &col, false);
+    ++c->launches;
+  }
+  for (int scale = 1; scale < num_scales; ++scale) {
+    if (scale >= 2 || use_pyramid_level_0) {
+      CUDABuffer_<float> d = DepthBuf(img[1][scale]);
+      CUDABuffer_<u16> n = NormalsBuf(img[1][scale]);
+      CUDABuffer_<u8> col = ColorBuf(img[1][scale]);
+      DownsampleImagesCUDA(s, DepthBuf(img[1][scale - 1]), NormalsBuf(img[1][scale - 1]), img[1][scale - 1].tex, &d, &n, &col, false);
+      ++c->launches;
+    }
+    CUDABuffer_<float> d = DepthBuf(img[0][scale]);
+    CUDABuffer_<u16> n = NormalsBuf(img[0][scale]);
+    CUDABuffer_<u8> col = ColorBuf(img[0][scale]);
+    DownsampleImagesCUDA(s, DepthBuf(img[0][scale - 1]), NormalsBuf(img[0][scale - 1]), img[0][scale - 1].tex, &d, &n, &col, false);
+    ++c->launches;
+  }
+  // the views (with the level-0 normals of this call) are what the kernels and the parity hooks see
+  for (int f = 0; f < 2; ++f)
+    for (int l = 0; l < num_scales; ++l) { c->odo[f][l].normals = img[f][l].normals; c->odo[f][l].normals_pitch = img[f][l].normals_pitch; }
+
+  float est[7], chosen_initial[7];
+  std::memcpy(est, init1, sizeof(est));
+  std::memcpy(chosen_initial, init1, sizeof(est));
+  const int kMaxIterationsPerScale = 30;
+  for (int scale = num_scales - 1; scale >= (use_pyramid_level_0 ? 0 : 1); --scale) {
+    const float scaling_factor = pow(2, scale);
+    res->chose_initial[scale] = -1;
+    if (scale != num_scales - 1 || test_different_initial_estimates) {
+      float last_scale[7], initial[7];
+      std::memcpy(last_scale, (scale != num_scales - 1) ? est : init1, sizeof(est));
+      std::memcpy(initial, (scale != num_scales - 1) ? chosen_initial : init2, sizeof(est));
+      u32 count_last = 0, count_init = 0;
+      float cost_last = 0, cost_init = 0;
+      OdoCost(c, scale, last_scale, use_gradmag != 0, &count_last, &cost_last);
+      OdoCost(c, scale, initial, use_gradmag != 0, &count_init, &cost_init);
+      bool take_last;
+      if (count_last > 2 * count_init) take_last = true;
+      else if (count_init > 2 * count_last) take_last = false;
+      else take_last = cost_last < cost_init;
+      std::memcpy(est, take_last ? last_scale : initial, sizeof(est));
+      res->chose_initial[scale] = take_last ? 0 : 1;
+      if (scale == num_scales - 1) std::memcpy(chosen_initial, est, sizeof(est));
+    }
+    int iteration;
+    for (iteration = 0; iteration < kMaxIterationsPerScale; ++iteration) {
+      float H[21], b[6];
+      double Hd[36], bd[6], xd[6];
+      std::memset(Hd, 0, sizeof(Hd));
+      OdoAccumulate(c, scale, est, use_gradmag != 0, false, nullptr, nullptr, H, b);
+      int idx = 0;
+      for (int r = 0; r < 6; ++r)
+        for (int cc = r; cc < 6; ++cc) Hd[r * 6 + cc] = H[idx++];
+      for (int i = 0; i < 6; ++i) bd[i] = b[i];
+      hm_ldlt_solve(6, Hd, bd, xd);
+      float damping = 1.f;
+      if (scale == num_scales - 2) damping = 0.5f;
+      else if (scale == num_scales - 1) damping = 0.25f;
+      float x[6], step[6], e[7], next[7];
+      for (int i = 0; i < 6; ++i) { x[i] = static_cast<float>(xd[i]); step[i] = -damping * x[i]; }
+      hm_se3_exp(step, e);
+      hm_se3_mul(est, e, next);
+      std::memcpy(est, next, sizeof(est));
+      // IsScaleNPoseEstimationConverged, convergence_analysis.h:56-63
+      const float sq = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3] + x[4] * x[4] + x[5] * x[5];
+      if (sq < scaling_factor * scaling_factor * 1e-08f) { ++iteration; break; }
+    }
+    res->iterations[scale] = iteration;
+  }
+  cudaEventRecord(c->ev[1], s);
+  cudaEventSynchronize(c->ev[1]);
+  cudaEventElapsedTime(&res->ms, c->ev[0], c->ev[1]);
+  std::memcpy(out, est, sizeof(est));
+  res->kernel_launches = c->launches - launches_before;
+  return 0;
+}
+
+// Parity hooks on the pyramids of the last ref_track_frame_pairwise call.
+int ref_odometry_get_level(ref_context* c, int which, int scale, float* depth, unsigned short* normals, unsigned char* color, int* w, int* h) {
+  if (which < 0 || which > 1 || scale < 0 || scale >= c->odo_scales) return 1;
+  const ref_context::OdoImage& im = c->odo[which][scale];
+  if (depth) cudaMemcpy2D(depth, sizeof(float) * im.w, im.depth, im.depth_pitch, sizeof(float) * im.w, im.h, cudaMemcpyDeviceToHost);
+  if (normals) cudaMemcpy2D(normals, sizeof(u16) * im.w, im.normals, im.normals_pitch, sizeof(u16) * im.w, im.h, cudaMemcpyDeviceToHost);
+  if (color) cudaMemcpy2D(color, im.w, im.color, im.color_pitch, im.w, im.h, cudaMemcpyDeviceToHost);
+  if (w) *w = im.w;
+  if (h) *h = im.h;
+  return 0;
+}
+void ref_odometry_coeffs(ref_context* c, int scale, int use_gradmag, const float pose_a[7], const float pose_b[7], float H[21], float b[6],
+                         unsigned int* count, float* sum, unsigned int counts[2], float costs[2]) {
+  OdoAccumulate(c, scale, pose_a, use_gradmag != 0, true, count, sum, H, b);
+  OdoCost(c, scale, pose_a, use_gradmag != 0, &counts[0], &costs[0]);
+  OdoCost(c, scale, pose_b, use_gradmag != 0, &counts[1], &costs[1]);
+}
 
 }  // extern "C"
