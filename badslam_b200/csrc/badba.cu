@@ -133,6 +133,7 @@ struct Keyframe {
   size_t depth_pitch = 0, normals_pitch = 0, radius_pitch = 0;
   cudaArray_t luma = nullptr;   // library-owned u8 CUDA array (the .w channel of the caller's uchar4 colour buffer)
   cudaTextureObject_t tex = 0;
+  bool tex_alias = false;       // development switch BADBA_ALIAS_LUMA (tools/ab_locality.py): tex belongs to keyframe 0
   void* owned[3] = {nullptr, nullptr, nullptr};   // depth / normals / radius copies made by bba_add_keyframe_host
   const uint8_t* rgba = nullptr;   // uchar4 colour image (caller-owned, or owned_rgba): surfel colours at creation
   size_t rgba_pitch = 0;
@@ -247,6 +248,8 @@ struct bba_context {
   bba::KfRadius* h_kf_radius = nullptr;      // pinned
   unsigned int* d_deleted_count = nullptr;
   unsigned int* h_deleted_count = nullptr;   // pinned
+  float* d_count_xchg = nullptr;             // [2] deleted count of this rank's shard for the sum all-reduce (multi-GPU)
+  float* h_count_xchg = nullptr;             // pinned
   unsigned int* d_compact_sums = nullptr;
   uint32_t compact_sums_capacity = 0;
 
@@ -1022,6 +1025,19 @@ bba_status PerformEndTasks(bba_handle h, cudaStream_t s, uint32_t* deleted_out, 
   a.tile_epoch = h->d_tile_epoch;
   a.tile_shift = 8;
   a.deleted_count = h->d_deleted_count;
+  // Multi-GPU: every rank evaluates the surfels of its granule shard (the launch is as expensive as a geometry pass over every
+  // keyframe); the two result rows reach the other replicas through peer stores or one all-gather, the deleted counts through a
+  // sum all-reduce (which is also the barrier behind the peer stores).  The compaction then runs replicated on identical replicas.
+  const int world = h->cfg.world_size, rank = h->cfg.rank;
+  const bool peers_mapped = world > 1 && h->peers.count == world - 1;
+  a.shard_rank = static_cast<uint32_t>(rank);
+  a.shard_world = static_cast<uint32_t>(world);
+  ShardSurfels(N, rank, world, &a.local_count, nullptr);
+  a.peers = peers_mapped ? h->peers : bba::PeerSet{};
+  if (world > 1) {
+    if (bba_status st = CheckCollective(h)) return st;
+    if (bba_status st = PeerFence(h, s)) return st;   // (e.g. the merges above rewrote whole replicas)
+  }
   if (K > 0) {
     bba::LaunchObservationStats(a, h->sm_count, s);
     ++h->launches;
@@ -1029,11 +1045,49 @@ bba_status PerformEndTasks(bba_handle h, cudaStream_t s, uint32_t* deleted_out, 
   }
   // (with no keyframe at all the reference still runs MarkDeletedSurfels on zero counts; not reachable through this API,
   // a BA call without keyframes has nothing to optimise)
-  BBA_CUDA(h, cudaMemcpyAsync(h->h_deleted_count, h->d_deleted_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
-  BBA_CUDA(h, cudaStreamSynchronize(s));   // kernel_delete_surfels.cc:93-96
+  uint32_t deleted_total = 0;
+  if (world > 1) {
+    if (!peers_mapped && K > 0) {
+      uint32_t shard_len;
+      ShardSurfels(N, rank, world, nullptr, &shard_len);
+      const size_t need = static_cast<size_t>(world) * 2 * shard_len;
+      if (need > h->exchange_floats) {
+        cudaFree(h->d_exchange);
+        h->d_exchange = nullptr;
+        uint32_t max_len;
+        ShardSurfels(std::max(h->cfg.max_surfel_count, N), 0, world, nullptr, &max_len);
+        h->exchange_floats = static_cast<size_t>(world) * bba::kShardRows * max_len;
+        BBA_CUDA(h, cudaMalloc(&h->d_exchange, sizeof(float) * h->exchange_floats));
+      }
+      const size_t slice_floats = static_cast<size_t>(2) * shard_len;
+      bba::LaunchPackStatsShard(h->surfels, a.pitch, N, rank, world, shard_len, h->d_exchange + slice_floats * rank, s);
+      h->collective(h->collective_user, BBA_COLLECTIVE_ALLGATHER, h->d_exchange, slice_floats * sizeof(float), s);
+      bba::LaunchUnpackStatsShards(h->surfels, a.pitch, N, shard_len, world, rank, h->d_exchange, s);
+      h->launches += 2;
+    }
+    // deleted count of this shard as two exactly representable floats (low 12 bits, the rest), summed over the ranks
+    if (!h->d_count_xchg) {
+      BBA_CUDA(h, cudaMalloc(&h->d_count_xchg, sizeof(float) * 2));
+      BBA_CUDA(h, cudaMallocHost(&h->h_count_xchg, sizeof(float) * 2));
+    }
+    BBA_CUDA(h, cudaMemcpyAsync(h->h_deleted_count, h->d_deleted_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+    BBA_CUDA(h, cudaStreamSynchronize(s));
+    h->h_count_xchg[0] = static_cast<float>(*h->h_deleted_count & 0xfffu);
+    h->h_count_xchg[1] = static_cast<float>(*h->h_deleted_count >> 12);
+    BBA_CUDA(h, cudaMemcpyAsync(h->d_count_xchg, h->h_count_xchg, sizeof(float) * 2, cudaMemcpyHostToDevice, s));
+    h->collective(h->collective_user, BBA_COLLECTIVE_ALLREDUCE_SUM, h->d_count_xchg, 2, s);
+    BBA_CUDA(h, cudaMemcpyAsync(h->h_count_xchg, h->d_count_xchg, sizeof(float) * 2, cudaMemcpyDeviceToHost, s));
+    BBA_CUDA(h, cudaStreamSynchronize(s));
+    deleted_total = static_cast<uint32_t>(h->h_count_xchg[0] + 0.5f) + (static_cast<uint32_t>(h->h_count_xchg[1] + 0.5f) << 12);
+    h->replicated_pass_pending = true;   // the compaction below rewrites every replica as a whole
+  } else {
+    BBA_CUDA(h, cudaMemcpyAsync(h->h_deleted_count, h->d_deleted_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+    BBA_CUDA(h, cudaStreamSynchronize(s));   // kernel_delete_surfels.cc:93-96
+    deleted_total = *h->h_deleted_count;
+  }
   h->staging_pending = false;
   BBA_TRACE("stats done");
-  const uint32_t deleted = *h->h_deleted_count + merged;
+  const uint32_t deleted = deleted_total + merged;
   if (deleted_out) *deleted_out = deleted;
   if (deleted > 0) {   // kernel_compact_surfels.cu:167-169
     const uint32_t words = bba::CompactScratchWords(N);
@@ -1074,7 +1128,8 @@ bba_status MakePcgLayout(bba_handle h, const bba_ba_options* o, PcgLayout* L) {
   if (L->opt_color_intr) { L->color_start = cur; cur += 4u; }
   L->unknown_count = cur;
   if (!h->d_pcg_scalars) {
-    BBA_CUDA(h, cudaMalloc(&h->d_pcg_scalars, sizeof(double) * 4));
+    BBA_CUDA(h, cudaMalloc(&h->d_pcg_scalars, sizeof(double) * bba::kPcgScalarDoubles));   // scalars + the ordered-sum workspace
+    BBA_CUDA(h, cudaMemset(h->d_pcg_scalars, 0, sizeof(double) * bba::kPcgScalarDoubles));
     BBA_CUDA(h, cudaMallocHost(&h->h_pcg_scalars, sizeof(double) * 4));
     BBA_CUDA(h, cudaMallocHost(&h->h_pcg_delta, sizeof(float) * (6 * static_cast<size_t>(h->cfg.max_keyframes) + 16)));
   }
@@ -1084,7 +1139,7 @@ bba_status MakePcgLayout(bba_handle h, const bba_ba_options* o, PcgLayout* L) {
     for (float*& v : h->d_pcg) {
       cudaFree(v);
       v = nullptr;
-      BBA_CUDA(h, cudaMalloc(&v, sizeof(float) * cap));
+      BBA_CUDA(h, cudaMalloc(&v, sizeof(float) * (cap + 8)));   // (+ the alpha_d pair that travels with g, multi-GPU)
     }
     h->pcg_capacity = cap;
   }
@@ -1097,7 +1152,11 @@ bba::PcgArgs MakePcgArgs(bba_handle h, const PcgLayout& L, int gauge) {
   a.surfels = h->surfels;
   a.pitch = static_cast<uint32_t>(h->surfel_pitch_bytes / sizeof(float));
   a.begin = 0;
-  a.end = h->surfels_size;
+  a.n = h->surfels_size;
+  a.shard_rank = static_cast<uint32_t>(h->cfg.rank);
+  a.shard_world = static_cast<uint32_t>(h->cfg.world_size);
+  ShardSurfels(h->surfels_size, h->cfg.rank, h->cfg.world_size, &a.end, nullptr);   // this rank's surfels (all of them on one GPU)
+  a.alpha_d_slot = h->cfg.world_size > 1 ? 3 : 1;
   a.kfs = h->d_kfs;
   a.kf_count = static_cast<int>(h->keyframes.size());
   a.gauge_kf = gauge;
@@ -1121,7 +1180,14 @@ bba::PcgArgs MakePcgArgs(bba_handle h, const PcgLayout& L, int gauge) {
 // DirectBA::BundleAdjustmentPCG (direct_ba_pcg.cc:43-819) without the surfel lifecycle branches.
 bba_status BundleAdjustPCG(bba_handle h, const bba_ba_options* o, bba_ba_result* res, cudaStream_t s) {
   const int K = static_cast<int>(h->keyframes.size());
-  if (h->cfg.world_size > 1) return Fail(h, BBA_ERR_UNSUPPORTED, "use_pcg is single-GPU only");
+  // Multi-GPU: the matrix-free products J^T W F / diag(J^T W J) / J^T W J p are summed over THIS rank's surfels (granule
+  // sharding of the geometry step); one sum all-reduce of the vector per product makes every rank hold the full result (a
+  // surfel's entries are non-zero on its owner only, pose / intrinsics entries are true sums), and the vector kernels, the
+  // scalars and the updates then run replicated and bit-identically on every rank (fixed-order sums, pcg.cu GridOrderedAdd).
+  const int world = h->cfg.world_size;
+  if (bba_status st = CheckCollective(h)) return st;
+  if (world > 1 && o->pcg_gauge_keyframe < 0)
+    return Fail(h, BBA_ERR_INVALID_ARGUMENT, "use_pcg with more than one rank needs pcg_gauge_keyframe >= 0 (the reference draws rand() % K)");
   if (K == 0) return Fail(h, BBA_ERR_STATE, "use_pcg: no keyframes");
   const int max_inner = o->pcg_max_inner_iterations > 0 ? o->pcg_max_inner_iterations : 30;
   const int max_keyframes = o->pcg_max_keyframes > 0 ? o->pcg_max_keyframes : 2500;
@@ -1170,6 +1236,7 @@ bba_status BundleAdjustPCG(bba_handle h, const bba_ba_options* o, bba_ba_result*
       if (bba_status st = BuildGeometryArgs(h, &g, s)) return st;
       bba::LaunchActivationAndNormals(g, h->sm_count, false, true, s);
       ++h->launches;
+      if (bba_status st = ExchangeGeometry(h, s)) return st;   // multi-GPU: every replica gets the other shards' normals
     }
     BBA_CUDA(h, cudaEventRecord(h->ev[1], s));
 
@@ -1186,6 +1253,11 @@ bba_status BundleAdjustPCG(bba_handle h, const bba_ba_options* o, bba_ba_result*
       BBA_CUDA(h, cudaMemsetAsync(h->d_pcg_scalars, 0, sizeof(double) * 4, s));
       const bba::PcgArgs a = MakePcgArgs(h, L, gauge);
       bba::LaunchPcgAccumulate(a, h->sm_count, true, s);   // PCGInitCUDA for every keyframe, :336-361
+      if (world > 1) {
+        h->collective(h->collective_user, BBA_COLLECTIVE_ALLREDUCE_SUM, pcg_r, unknown_count, s);
+        h->collective(h->collective_user, BBA_COLLECTIVE_ALLREDUCE_SUM, pcg_M, unknown_count, s);
+        h->replicated_pass_pending = false;
+      }
       int an = 0, bn = 2;
       bba::LaunchPcgInit2(unknown_count, a_index, h->depth_a, K, pcg_r, pcg_M, pcg_delta, pcg_g, pcg_p, h->d_pcg_scalars, an,
                           h->sm_count, s);   // :363-373
@@ -1195,6 +1267,12 @@ bba_status BundleAdjustPCG(bba_handle h, const bba_ba_options* o, bba_ba_result*
       for (int step = 0; step < max_inner; ++step) {
         if (step > 0) std::swap(an, bn);   // alpha_n <- beta_n (:386); g was cleared and alpha_d re-armed by PcgStep3Kernel
         bba::LaunchPcgAccumulate(a, h->sm_count, false, s);   // PCGStep1CUDA for every keyframe, :392-419
+        if (world > 1) {   // g and this rank's part of alpha_d: one all-reduce
+          bba::LaunchPcgPackAlphaD(h->d_pcg_scalars, pcg_g + unknown_count, s);
+          h->collective(h->collective_user, BBA_COLLECTIVE_ALLREDUCE_SUM, pcg_g, static_cast<size_t>(unknown_count) + 2, s);
+          bba::LaunchPcgUnpackAlphaD(h->d_pcg_scalars, pcg_g + unknown_count, s);
+          h->launches += 2;
+        }
         BBA_CUDA(h, cudaMemsetAsync(h->d_pcg_scalars + bn, 0, sizeof(double), s));
         bba::LaunchPcgStep2(unknown_count, a_index, pcg_r, pcg_M, pcg_delta, pcg_g, pcg_p, h->d_pcg_scalars, an, bn, h->sm_count, s);
         h->launches += 2;
@@ -1233,6 +1311,7 @@ bba_status BundleAdjustPCG(bba_handle h, const bba_ba_options* o, bba_ba_result*
       if (opt_geometry && N > 0) {
         bba::LaunchPcgUpdateSurfels(h->surfels, a.pitch, N, use_desc, surfel_start, pcg_delta, s);
         ++h->launches;
+        h->replicated_pass_pending = true;   // every rank rewrites its whole replica (PeerFence)
       }
       if (opt_depth_intr) {
         bba::LaunchPcgUpdateCfactor(h->d_cfactor, P, pcg_delta + depth_start + 5, s);
@@ -1477,7 +1556,14 @@ bba::odom::LevelCamera MakeLevelCamera(bba_handle h, int scale, int level_w, int
 bba_status AddKeyframeCommon(bba_handle h, Keyframe&& kf, const uint8_t* device_rgba, size_t color_pitch, const float pose[7],
                              float min_depth, float max_depth, cudaStream_t s, int* out_id) {
   if (static_cast<int>(h->keyframes.size()) >= h->cfg.max_keyframes) return Fail(h, BBA_ERR_STATE, "max_keyframes exceeded");
-  if (bba_status st = MakeLumaTexture(h, device_rgba, color_pitch, &kf.luma, &kf.tex, s)) return st;
+  // (development switch for the locality A/B of tools/ab_locality.py: every keyframe samples keyframe 0's luma array)
+  static const bool alias_luma = std::getenv("BADBA_ALIAS_LUMA") != nullptr;
+  if (alias_luma && !h->keyframes.empty()) {
+    kf.tex = h->keyframes[0].tex;
+    kf.tex_alias = true;
+  } else if (bba_status st = MakeLumaTexture(h, device_rgba, color_pitch, &kf.luma, &kf.tex, s)) {
+    return st;
+  }
   kf.pose = PoseFromArray(pose);
   kf.activation = BBA_KF_ACTIVE;   // keyframe.cc:75
   kf.min_depth = min_depth;
@@ -1597,7 +1683,7 @@ void bba_destroy(bba_handle h) {
   if (!h) return;
   cudaDeviceSynchronize();
   for (Keyframe& kf : h->keyframes) {
-    if (kf.tex) cudaDestroyTextureObject(kf.tex);
+    if (kf.tex && !kf.tex_alias) cudaDestroyTextureObject(kf.tex);
     if (kf.luma) cudaFreeArray(kf.luma);
     for (void* p : kf.owned) cudaFree(p);
     cudaFree(kf.owned_rgba);
@@ -1646,6 +1732,8 @@ void bba_destroy(bba_handle h) {
   cudaFree(h->d_kf_radius);
   cudaFreeHost(h->h_kf_radius);
   cudaFree(h->d_deleted_count);
+  cudaFree(h->d_count_xchg);
+  if (h->h_count_xchg) cudaFreeHost(h->h_count_xchg);
   cudaFreeHost(h->h_deleted_count);
   cudaFree(h->d_compact_sums);
   cudaFree(h->d_min_max);
@@ -2114,6 +2202,7 @@ bba_status LaunchOdometryKernel(bba_handle h, int num_scales, int first_scale, i
   BBA_CUDA(h, cudaGetLastError());
   BBA_CUDA(h, cudaMemcpyAsync(st.h_result, st.d_result, sizeof(od::TrackResult), cudaMemcpyDeviceToHost, s));
   BBA_CUDA(h, cudaStreamSynchronize(s));
+  if (st.h_result->barrier_timeout) return Fail(h, BBA_ERR_CUDA, "odometry kernel: grid barrier timed out");
   return BBA_OK;
 }
 

@@ -144,7 +144,10 @@ struct PcgArgs {
   CameraParams cam;
   const float* surfels;
   uint32_t pitch;
-  uint32_t begin, end;         // surfel range processed by this rank
+  uint32_t begin, end;         // range of this rank's LOCAL surfel indices (SurfelShardToGlobal maps them; 0 .. n on one GPU)
+  uint32_t n;                  // surfels_size
+  uint32_t shard_rank, shard_world;
+  int alpha_d_slot;            // scalars slot that receives this launch's p^T J^T W J p: 1 on one GPU, 3 (exchanged, then added to 1) otherwise
   const KfDevice* kfs;         // every keyframe, ids 0 .. kf_count-1
   int kf_count;
   int gauge_kf;                // keyframe whose pose is fixed (no unknowns), direct_ba_pcg.cc:315-333
@@ -158,7 +161,12 @@ struct PcgArgs {
   double* scalars;             // [0] / [2] alpha_n, beta_n (swapping roles), [1] alpha_d
   unsigned int* queue;         // work-item counter (reset by the launcher)
 };
+// Layout of the fp64 scalar block: [0] / [2] alpha_n, beta_n (swapping roles), [1] alpha_d, [3] this rank's part of alpha_d
+// (multi-GPU), then the workspace of the fixed-order grid sums of the vector kernels.
+constexpr int kPcgPartialsA = 8, kPcgPartialsB = 8 + 2048, kPcgCounters = 8 + 4096, kPcgScalarDoubles = 8 + 4096 + 2;
 void LaunchPcgAccumulate(const PcgArgs& a, int sm_count, bool init, cudaStream_t stream);
+void LaunchPcgPackAlphaD(const double* scalars, float* tail, cudaStream_t stream);
+void LaunchPcgUnpackAlphaD(double* scalars, const float* tail, cudaStream_t stream);
 void LaunchPcgInit2(uint32_t n, uint32_t a_index, float a, int kf_count, const float* r, const float* M, float* delta, float* g, float* p,
                     double* scalars, int slot_alpha_n, int sm_count, cudaStream_t stream);
 void LaunchPcgStep2(uint32_t n, uint32_t a_index, float* r, const float* M, float* delta, float* g, const float* p, double* scalars,
@@ -188,8 +196,17 @@ struct SurfelStatsArgs {
   unsigned int* tile_epoch;
   int tile_shift;              // chosen by the launcher
   unsigned int* deleted_count; // device scalar, += surfels deleted by this launch
+  // multi-GPU: this rank handles the surfels of its granule shard (local indices [0, local_count)); with mapped peers the two
+  // result rows (x = deletion marker, radius^2) are stored into every replica, like the geometry step's results
+  uint32_t local_count, shard_rank, shard_world;
+  PeerSet peers;
 };
 void LaunchObservationStats(SurfelStatsArgs a, int sm_count, cudaStream_t stream);
+// Exchange of the end tasks' two result rows through the host collective (no mapped peers): slice = [2][shard_len] floats.
+void LaunchPackStatsShard(const float* surfels, uint32_t pitch, uint32_t n, uint32_t rank, uint32_t world, uint32_t shard_len, float* slice,
+                          cudaStream_t stream);
+void LaunchUnpackStatsShards(float* surfels, uint32_t pitch, uint32_t n, uint32_t shard_len, int world, int skip_rank, const float* buffer,
+                             cudaStream_t stream);
 uint32_t CompactScratchWords(uint32_t n);   // size of block_sums for LaunchCompactSurfels
 // Moves surviving surfels from the tail into the free spots; afterwards the first n - free_count slots are the surfels.
 // active != nullptr: the active flags move with them (CompactSurfelsCUDA's adapt_active_surfels).

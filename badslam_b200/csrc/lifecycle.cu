@@ -36,12 +36,20 @@ __device__ __forceinline__ void StoreRelease(unsigned int* p, unsigned int v) {
 
 __global__ void __launch_bounds__(kThreads) ObservationStatsKernel(const __grid_constant__ SurfelStatsArgs a) {
   const uint32_t tile_len = 1u << a.tile_shift;
-  const uint32_t n_tiles = (a.n + tile_len - 1) >> a.tile_shift;
+  const uint32_t n_tiles = (a.local_count + tile_len - 1) >> a.tile_shift;
   const uint32_t n_groups = (a.kf_count + kGroup - 1) / kGroup;
   const uint32_t n_items = n_groups * n_tiles;
   const size_t P = a.pitch;
   const int lane = threadIdx.x & 31;
   const CameraParams& cam = a.cam;
+  // result rows of this rank's surfels go to the local replica and -- with mapped peers -- to every other rank's (NVLink)
+  auto store_row = [&](int row, uint32_t i, float v) {
+    const size_t o = static_cast<size_t>(row) * P + i;
+    a.surfels[o] = v;
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; ++p)
+      if (p < a.peers.count) a.peers.surfels[p][o] = v;
+  };
   for (;;) {
     // warp-owned item (group, tile); (g, t) runs after (g - 1, t) has been retired
     unsigned int item = 0;
@@ -59,9 +67,10 @@ __global__ void __launch_bounds__(kThreads) ObservationStatsKernel(const __grid_
     const int j_begin = group * kGroup, j_end = min(a.kf_count, static_cast<int>(group + 1) * kGroup);
     unsigned int deleted_here = 0;
     for (uint32_t sub = 0; sub < tile_len / 32; ++sub) {
-      const uint32_t i = (tile << a.tile_shift) + sub * 32 + lane;
+      const uint32_t li = (tile << a.tile_shift) + sub * 32 + lane;   // local index of the granule sharding (identity on one GPU)
+      const uint32_t i = SurfelShardToGlobal(li, a.shard_rank, a.shard_world);
       bool deleted = false;
-      if (i < a.n) {
+      if (li < a.local_count && i < a.n) {
         float obs = 0.f, viol = 0.f, min_r2 = __int_as_float(0x7f800000);   // +inf (kernel_delete_surfels.cu:50)
         if (!first) {
           obs = __ldcg(a.surfels + (kRowAccum0 + 0) * P + i);
@@ -106,11 +115,11 @@ __global__ void __launch_bounds__(kThreads) ObservationStatsKernel(const __grid_
           // MarkDeletedSurfelsCUDAKernel (kernel_delete_surfels.cu:129-164)
           if (obs < static_cast<float>(a.min_observation_count) || viol > obs) {
             if (__float_as_uint(x) != kDeletedPattern) {
-              a.surfels[kRowX * P + i] = __uint_as_float(kDeletedPattern);
+              store_row(kRowX, i, __uint_as_float(kDeletedPattern));
               deleted = true;
             }
           } else {
-            a.surfels[kRowRadiusSq * P + i] = min_r2;
+            store_row(kRowRadiusSq, i, min_r2);
           }
         }
       }
@@ -604,16 +613,49 @@ void LaunchCreateSurfels(const LifecycleArgs& a, const unsigned int* index, cuda
   CreateSurfelsKernel<<<(pixels + 255) / 256, 256, 0, stream>>>(a, index);
 }
 
+// rows x (deletion marker) and radius^2 of this rank's shard, in local index order
+__global__ void __launch_bounds__(256) PackStatsShardKernel(const float* __restrict__ surfels, uint32_t pitch, uint32_t n, uint32_t rank,
+                                                            uint32_t world, uint32_t shard_len, float* __restrict__ slice) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= shard_len) return;
+  const uint32_t i = SurfelShardToGlobal(c, rank, world);
+  const bool in = i < n;
+  slice[c] = in ? surfels[static_cast<size_t>(kRowX) * pitch + i] : 0.f;
+  slice[static_cast<size_t>(shard_len) + c] = in ? surfels[static_cast<size_t>(kRowRadiusSq) * pitch + i] : 0.f;
+}
+__global__ void __launch_bounds__(256) UnpackStatsShardsKernel(float* __restrict__ surfels, uint32_t pitch, uint32_t n, uint32_t shard_len,
+                                                               uint32_t world, int skip_rank, const float* __restrict__ buffer) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t granule = i >> kShardGranuleShift;
+  const uint32_t rank = granule % world;
+  if (static_cast<int>(rank) == skip_rank) return;
+  const uint32_t c = ((granule / world) << kShardGranuleShift) | (i & ((1u << kShardGranuleShift) - 1u));
+  const float* slice = buffer + static_cast<size_t>(rank) * 2 * shard_len;
+  surfels[static_cast<size_t>(kRowX) * pitch + i] = slice[c];
+  surfels[static_cast<size_t>(kRowRadiusSq) * pitch + i] = slice[static_cast<size_t>(shard_len) + c];
+}
+void LaunchPackStatsShard(const float* surfels, uint32_t pitch, uint32_t n, uint32_t rank, uint32_t world, uint32_t shard_len, float* slice,
+                          cudaStream_t stream) {
+  if (shard_len == 0) return;
+  PackStatsShardKernel<<<(shard_len + 255) / 256, 256, 0, stream>>>(surfels, pitch, n, rank, world, shard_len, slice);
+}
+void LaunchUnpackStatsShards(float* surfels, uint32_t pitch, uint32_t n, uint32_t shard_len, int world, int skip_rank, const float* buffer,
+                             cudaStream_t stream) {
+  if (n == 0) return;
+  UnpackStatsShardsKernel<<<(n + 255) / 256, 256, 0, stream>>>(surfels, pitch, n, shard_len, static_cast<uint32_t>(world), skip_rank, buffer);
+}
+
 void LaunchObservationStats(SurfelStatsArgs a, int sm_count, cudaStream_t stream) {
-  if (a.n == 0 || a.kf_count <= 0) return;
+  if (a.local_count == 0 || a.kf_count <= 0) return;
   int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ObservationStatsKernel, kThreads, 0);
   if (per_sm < 1) per_sm = 1;
   const uint64_t resident_warps = static_cast<uint64_t>(per_sm) * sm_count * (kThreads / 32);
   int shift = 8;
-  while (shift > 5 && 2 * static_cast<uint64_t>((a.n + (1u << shift) - 1) >> shift) < 3 * resident_warps) --shift;
+  while (shift > 5 && 2 * static_cast<uint64_t>((a.local_count + (1u << shift) - 1) >> shift) < 3 * resident_warps) --shift;
   a.tile_shift = shift;
-  const uint32_t n_tiles = (a.n + (1u << shift) - 1) >> shift;
+  const uint32_t n_tiles = (a.local_count + (1u << shift) - 1) >> shift;
   const uint64_t n_items = static_cast<uint64_t>(n_tiles) * ((a.kf_count + kGroup - 1) / kGroup);
   cudaMemsetAsync(a.queue, 0, sizeof(unsigned int), stream);
   cudaMemsetAsync(a.tile_epoch, 0, sizeof(unsigned int) * n_tiles, stream);

@@ -372,7 +372,9 @@ __device__ __forceinline__ unsigned int LoadAcquireU32(const unsigned int* p) {
 }
 
 // Grid-wide barrier of a persistent kernel whose CTAs are all resident (one per SM).  bar[0] = arrival count, bar[1] = generation.
-__device__ __forceinline__ void GridBarrier(unsigned int* bar) {
+// A CTA that waits longer than ~2^22 polls (seconds; a pass takes microseconds) gives up and raises *timeout: the launch is
+// cooperative, so this can only happen after a device fault elsewhere -- the kernel must still terminate.
+__device__ __forceinline__ void GridBarrier(unsigned int* bar, unsigned int* timeout) {
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned int gen = LoadAcquireU32(bar + 1);
@@ -382,7 +384,14 @@ __device__ __forceinline__ void GridBarrier(unsigned int* bar) {
       __threadfence();
       atomicAdd(bar + 1, 1u);
     } else {
-      while (LoadAcquireU32(bar + 1) == gen) __nanosleep(32);
+      unsigned int polls = 0;
+      while (LoadAcquireU32(bar + 1) == gen) {
+        __nanosleep(64);
+        if (++polls > (1u << 22)) {
+          *timeout = 1u;
+          break;
+        }
+      }
     }
     __threadfence();
   }
@@ -487,7 +496,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) OdomTrackKernel(const __grid
     __syncthreads();
     LevelPass<GRADMAG, 0>(a, L, s_T[0], s_T[0], threshold_factor, s_acc, a.acc);
     LevelPass<GRADMAG, 1>(a, L, s_T[0], s_T[1], threshold_factor, s_acc, a.acc + 32);
-    GridBarrier(a.barrier);
+    GridBarrier(a.barrier, &a.result->barrier_timeout);
     if (blockIdx.x == 0 && threadIdx.x < 36) a.result->debug[threadIdx.x] = __ldcg(a.acc + threadIdx.x);
     return;
   }
@@ -511,7 +520,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) OdomTrackKernel(const __grid
       double* g = a.acc + (pass % 3) * 32;
       LevelPass<GRADMAG, 1>(a, L, s_T[0], s_T[1], threshold_factor, s_acc, g);
       next_buffer_clear();
-      GridBarrier(a.barrier);
+      GridBarrier(a.barrier, &a.result->barrier_timeout);
       if (threadIdx.x == 0) {
         const unsigned int count_a = static_cast<unsigned int>(__ldcg(g + 0) + 0.5), count_b = static_cast<unsigned int>(__ldcg(g + 2) + 0.5);
         const float cost_a = static_cast<float>(__ldcg(g + 1)), cost_b = static_cast<float>(__ldcg(g + 3));
@@ -535,7 +544,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) OdomTrackKernel(const __grid
       double* g = a.acc + (pass % 3) * 32;
       LevelPass<GRADMAG, 0>(a, L, s_T[0], s_T[0], threshold_factor, s_acc, g);
       next_buffer_clear();
-      GridBarrier(a.barrier);
+      GridBarrier(a.barrier, &a.result->barrier_timeout);
       if (threadIdx.x == 0) {
         // the reference's buffers are fp32 and are cast to double for the solve (pairwise_frame_tracking.cc:557-566)
         double H[21], b[6], xd[6];
@@ -580,8 +589,10 @@ void LaunchTrack(const TrackArgs& a, int sm_count, cudaStream_t stream) {
   const Level& L0 = a.level[a.first_scale];
   const int tiles = ((L0.cam.w + 31) / 32) * ((L0.cam.h + 7) / 8);
   const int grid = tiles < sm_count ? (tiles > 0 ? tiles : 1) : sm_count;
-  if (a.use_gradmag) OdomTrackKernel<true><<<grid, kTrackThreads, 0, stream>>>(a);
-  else OdomTrackKernel<false><<<grid, kTrackThreads, 0, stream>>>(a);
+  // cooperative launch: the runtime guarantees that all CTAs are resident at the same time (or refuses the launch)
+  void* params[] = {const_cast<TrackArgs*>(&a)};
+  if (a.use_gradmag) cudaLaunchCooperativeKernel(reinterpret_cast<void*>(OdomTrackKernel<true>), dim3(grid), dim3(kTrackThreads), params, 0, stream);
+  else cudaLaunchCooperativeKernel(reinterpret_cast<void*>(OdomTrackKernel<false>), dim3(grid), dim3(kTrackThreads), params, 0, stream);
 }
 
 }  // namespace odom

@@ -91,6 +91,7 @@ struct TrackResult {           // written by the kernel (device memory, copied b
   unsigned int residual_count;     // last accumulation pass (debug counters of kernel_opt_pose.cu:619-657)
   float residual_sum;
   unsigned int passes;
+  unsigned int barrier_timeout;    // a CTA gave up waiting at a grid barrier (device fault): the result is invalid
   double debug[36];                // debug_scale >= 0: [0..20] H, [21..26] b, [27] count, [28] cost at init1; [32..35] count / cost at init1, init2
 };
 struct TrackArgs {

@@ -62,8 +62,12 @@ __device__ __forceinline__ void LoadKfLite(const KfDevice* __restrict__ kfs, int
   r->normals_pitch = k.normals_pitch;
 }
 
-// Block-wide fp64 sum -> one atomic (for the vector kernels).
-__device__ __forceinline__ void BlockAtomicAdd(double* dst, double v) {
+// Grid-wide fp64 sum in a FIXED order (for the vector kernels): every block parks its partial sum, the last block to arrive adds
+// them up in block order and folds the total into *dst.  The result depends on the inputs only -- not on the order in which
+// atomics land -- so the replicas of a multi-GPU job, which run these kernels on identical vectors, compute bit-identical
+// alpha / beta (and with them identical step lengths and identical inner-loop decisions), and single-GPU runs are reproducible.
+// partials: >= gridDim.x doubles; counter: zero before the launch, zero again after it.
+__device__ __forceinline__ void GridOrderedAdd(double* dst, double v, double* partials, unsigned int* counter) {
   __shared__ double partial[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -74,7 +78,17 @@ __device__ __forceinline__ void BlockAtomicAdd(double* dst, double v) {
     double s = (lane < static_cast<int>(blockDim.x >> 5)) ? partial[lane] : 0.0;
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0 && s != 0.0) atomicAdd(dst, s);
+    if (lane == 0) {
+      partials[blockIdx.x] = s;
+      __threadfence();
+      if (atomicAdd(counter, 1u) == gridDim.x - 1) {
+        __threadfence();
+        double total = 0.0;
+        for (unsigned int b = 0; b < gridDim.x; ++b) total += __ldcg(partials + b);
+        *dst += total;
+        *counter = 0u;
+      }
+    }
   }
   __syncthreads();
 }
@@ -104,8 +118,10 @@ __global__ void __launch_bounds__(kThreads) PcgAccumulateKernel(const __grid_con
     if (item >= n_items) break;
     const uint32_t group = item / n_tiles, tile = item - group * n_tiles;
     const int j_begin = group * kGroup, j_end = min(a.kf_count, static_cast<int>(group + 1) * kGroup);
-    const uint32_t i = a.begin + tile * 32u + lane;
-    const bool valid = i < a.end;
+    // this rank's surfels through the dense local index of the 256-surfel granule sharding (kernels.cuh; identity on one GPU)
+    const uint32_t li = a.begin + tile * 32u + lane;
+    const uint32_t i = SurfelShardToGlobal(li, a.shard_rank, a.shard_world);
+    const bool valid = li < a.end && i < a.n;
 
     Vec3 gp = V3(0, 0, 0), nrm = V3(0, 0, 1);
     float radius_sq = 0.f, d1 = 0.f, d2 = 0.f;
@@ -391,7 +407,7 @@ __global__ void __launch_bounds__(kThreads) PcgAccumulateKernel(const __grid_con
       if (total != 0.f) {
         if (lane < 5) { if (a.opt_depth_intr) atomicAdd(a.g + a.depth_intr_start + lane, total); }
         else if (lane < 9) { if (a.opt_color_intr) atomicAdd(a.g + a.color_intr_start + (lane - 5), total); }
-        else if (lane == 9) atomicAdd(a.scalars + 1, static_cast<double>(total));
+        else if (lane == 9) atomicAdd(a.scalars + a.alpha_d_slot, static_cast<double>(total));
       }
     }
   }
@@ -413,8 +429,8 @@ __global__ void __launch_bounds__(256) PcgInit2Kernel(uint32_t n, uint32_t a_ind
     alpha += static_cast<double>(r_value * p_value);
     eps += static_cast<double>(DiagExtra(i, a_index) * p_value * p_value);
   }
-  BlockAtomicAdd(scalars + slot_alpha_n, alpha);
-  BlockAtomicAdd(scalars + 1, eps * kf_count);
+  GridOrderedAdd(scalars + slot_alpha_n, alpha, scalars + kPcgPartialsA, reinterpret_cast<unsigned int*>(scalars + kPcgCounters));
+  GridOrderedAdd(scalars + 1, eps * kf_count, scalars + kPcgPartialsB, reinterpret_cast<unsigned int*>(scalars + kPcgCounters) + 1);
 }
 
 // PCGStep2CUDAKernel (kernel_pcg.cu:1115-1166)
@@ -434,7 +450,7 @@ __global__ void __launch_bounds__(256) PcgStep2Kernel(uint32_t n, uint32_t a_ind
     g[i] = z_value;
     beta += static_cast<double>(z_value * r_value);
   }
-  BlockAtomicAdd(scalars + slot_beta_n, beta);
+  GridOrderedAdd(scalars + slot_beta_n, beta, scalars + kPcgPartialsA, reinterpret_cast<unsigned int*>(scalars + kPcgCounters));
 }
 
 // PCGStep3CUDAKernel (kernel_pcg.cu:1206-1224) + the g = 0 of the next step (direct_ba_pcg.cc:379) + the next alpha_d's
@@ -450,7 +466,7 @@ __global__ void __launch_bounds__(256) PcgStep3Kernel(uint32_t n, uint32_t a_ind
     g[i] = 0.f;
     eps += static_cast<double>(DiagExtra(i, a_index) * p_value * p_value);
   }
-  BlockAtomicAdd(scalars + 1, eps * kf_count);
+  GridOrderedAdd(scalars + 1, eps * kf_count, scalars + kPcgPartialsB, reinterpret_cast<unsigned int*>(scalars + kPcgCounters) + 1);
 }
 
 // UpdateSurfelsFromPCGDeltaCUDAKernel (kernel_pcg.cu:1278-1308)
@@ -479,6 +495,21 @@ __global__ void __launch_bounds__(256) PcgUpdateCfactorKernel(float* __restrict_
   if (i < cells) cfactor[i] += delta[i];
 }
 
+// Multi-GPU: this rank's part of p^T J^T W J p (fp64, scalars[3]) travels with g through the fp32 sum all-reduce as a
+// (high, low) float pair appended to the vector; afterwards the total joins the lambda / prior term already waiting in scalars[1].
+__global__ void PcgPackAlphaDKernel(const double* __restrict__ scalars, float* __restrict__ tail) {
+  const double v = scalars[3];
+  const float hi = static_cast<float>(v);
+  tail[0] = hi;
+  tail[1] = static_cast<float>(v - static_cast<double>(hi));
+}
+__global__ void PcgUnpackAlphaDKernel(double* __restrict__ scalars, const float* __restrict__ tail) {
+  scalars[1] += static_cast<double>(tail[0]) + static_cast<double>(tail[1]);
+  scalars[3] = 0.0;
+}
+void LaunchPcgPackAlphaD(const double* scalars, float* tail, cudaStream_t stream) { PcgPackAlphaDKernel<<<1, 1, 0, stream>>>(scalars, tail); }
+void LaunchPcgUnpackAlphaD(double* scalars, const float* tail, cudaStream_t stream) { PcgUnpackAlphaDKernel<<<1, 1, 0, stream>>>(scalars, tail); }
+
 void LaunchPcgAccumulate(const PcgArgs& a, int sm_count, bool init, cudaStream_t stream) {
   if (a.end <= a.begin || a.kf_count <= 0) return;
   cudaMemsetAsync(a.queue, 0, sizeof(unsigned int), stream);
@@ -496,7 +527,8 @@ void LaunchPcgAccumulate(const PcgArgs& a, int sm_count, bool init, cudaStream_t
 }
 
 static uint32_t VectorGrid(uint32_t n, int sm_count) {
-  return static_cast<uint32_t>(std::min<uint64_t>((static_cast<uint64_t>(n) + 255) / 256, static_cast<uint64_t>(sm_count) * 8));
+  // (<= 2048 blocks: the workspace of the ordered grid sums, kPcgPartialsA / B)
+  return static_cast<uint32_t>(std::min<uint64_t>(std::min<uint64_t>((static_cast<uint64_t>(n) + 255) / 256, static_cast<uint64_t>(sm_count) * 8), 2048));
 }
 
 void LaunchPcgInit2(uint32_t n, uint32_t a_index, float a, int kf_count, const float* r, const float* M, float* delta, float* g, float* p,

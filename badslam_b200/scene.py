@@ -565,6 +565,17 @@ def _make_scene(cfg: SceneConfig, verbose: bool = False) -> Scene:
                  surfels, n, cfactor_grid, 0.0, planes)
 
 
+def render_frame(scene, global_T_frame):
+    """A preprocessed RGB-D frame of the scene's planes seen from an arbitrary pose, in the keyframe format
+    (depth, normals, radius u16 [h, w]; colour uchar4 [h, w, 4] with .w = luma): the input of frame tracking / odometry."""
+    cfg = scene.cfg
+    pose = np.asarray(global_T_frame, np.float32)
+    raw, rgb = _render_keyframe(cfg, scene.depth_K, pose, scene.planes)
+    color = compute_brightness(rgb)
+    depth, normals, radius, _, _ = preprocess_depth(cfg, scene.depth_K, raw, scene.cfactor, scene.depth_a)
+    return depth, normals, radius, color
+
+
 def displace_surfels(scene, seed=3):
     """A copy of `scene` with three groups of surfels displaced, to exercise the end-of-BA maintenance
     (PerformBASchemeEndTasks): moved out of every view (unobserved), pulled towards keyframe 0's camera (in front of the

@@ -48,6 +48,11 @@ class PCGResult(C.Structure):
                 ("surfels_deleted", C.c_uint), ("surfels_size", C.c_uint)]
 
 
+class OdometryResult(C.Structure):
+    _fields_ = [("iterations", C.c_int * 8), ("chose_initial", C.c_int * 8), ("residual_count", C.c_uint),
+                ("residual_sum", C.c_float), ("kernel_launches", C.c_ulonglong), ("ms", C.c_float)]
+
+
 _lib = None
 
 
@@ -98,6 +103,14 @@ def lib():
         l.ref_preprocess_frame.restype = C.c_int
         l.ref_preprocess_frame.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.ref_track_frame_pairwise.restype = C.c_int
+        l.ref_track_frame_pairwise.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                               C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(OdometryResult)]
+        l.ref_odometry_get_level.restype = C.c_int
+        l.ref_odometry_get_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int),
+                                             C.POINTER(C.c_int)]
+        l.ref_odometry_coeffs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.POINTER(C.c_uint), C.POINTER(C.c_float), C.c_void_p, C.c_void_p]
         l.ref_snapshot.argtypes = [C.c_void_p]
         l.ref_restore.argtypes = [C.c_void_p]
         l.ref_sync.argtypes = [C.c_void_p]
@@ -203,6 +216,42 @@ class RefDirectBA:
                                          C.addressof(mn), C.addressof(mx))
         assert rc > 0, self.l.ref_last_cuda_error()
         return depth, normals, radius, rgba, mn.value, mx.value
+
+    def track_frame_pairwise(self, base_kf, depth, normals, color_rgba, init1, init2=None, num_scales=5, use_pyramid_level_0=True,
+                             use_gradmag=False, test_different_initial_estimates=True):
+        """BadSlam::RunOdometry + TrackFramePairwise on the reference's own kernels (restated host loop, ref_driver.cu):
+        (base_T_frame_estimate, OdometryResult)."""
+        d = np.ascontiguousarray(depth, np.uint16)
+        n = np.ascontiguousarray(normals, np.uint16)
+        c = np.ascontiguousarray(color_rgba, np.uint8)
+        p1 = np.ascontiguousarray(init1, np.float32)
+        p2 = p1 if init2 is None else np.ascontiguousarray(init2, np.float32)
+        out = np.zeros(7, np.float32)
+        res = OdometryResult()
+        rc = self.l.ref_track_frame_pairwise(self.h, int(base_kf), d.ctypes.data, n.ctypes.data, c.ctypes.data, int(num_scales),
+                                             int(use_pyramid_level_0), int(use_gradmag), int(test_different_initial_estimates),
+                                             p1.ctypes.data, p2.ctypes.data, out.ctypes.data, C.byref(res))
+        assert rc == 0, self.l.ref_last_cuda_error()
+        return out, res
+
+    def odometry_level(self, which, scale):
+        w, h = C.c_int(), C.c_int()
+        assert self.l.ref_odometry_get_level(self.h, which, scale, None, None, None, C.byref(w), C.byref(h)) == 0
+        d = np.zeros((h.value, w.value), np.float32)
+        n = np.zeros((h.value, w.value), np.uint16)
+        c = np.zeros((h.value, w.value), np.uint8)
+        assert self.l.ref_odometry_get_level(self.h, which, scale, d.ctypes.data, n.ctypes.data, c.ctypes.data, C.byref(w), C.byref(h)) == 0
+        return d, n, c
+
+    def odometry_coeffs(self, scale, pose_a, pose_b=None, use_gradmag=False):
+        pa = np.ascontiguousarray(pose_a, np.float32)
+        pb = pa if pose_b is None else np.ascontiguousarray(pose_b, np.float32)
+        H, b = np.zeros(21, np.float32), np.zeros(6, np.float32)
+        cnt, sm = C.c_uint(), C.c_float()
+        counts, costs = np.zeros(2, np.uint32), np.zeros(2, np.float32)
+        self.l.ref_odometry_coeffs(self.h, int(scale), int(use_gradmag), pa.ctypes.data, pb.ctypes.data, H.ctypes.data, b.ctypes.data,
+                                   C.byref(cnt), C.byref(sm), counts.ctypes.data, costs.ctypes.data)
+        return H, b, cnt.value, sm.value, counts, costs
 
     def set_surfels_size(self, n):
         self.l.ref_set_surfels_size(self.h, int(n))

@@ -153,6 +153,7 @@ struct ref_context {
   OdoImage odo[2][8];            // [0 base | 1 tracked][scale]
   u8* odo_gradmag[2] = {nullptr, nullptr}; size_t odo_gradmag_pitch[2] = {0, 0}; cudaTextureObject_t odo_gradmag_tex[2] = {0, 0};
   RefKeyframe odo_frame;         // the tracked frame's device images
+  float* odo_debug = nullptr; size_t odo_debug_pitch = 0;   // debug_residual_image of the accumulate kernels (written when debug = true)
   int odo_scales = 0;
 };
 
@@ -497,6 +498,21 @@ void ref_destroy(ref_context* c) {
   }
   cudaFree(c->cfactor); cudaFree(c->surfels); cudaFree(c->active);
   cudaFree(c->residual_count); cudaFree(c->residual_sum); cudaFree(c->H); cudaFree(c->b);
+  // image-pair odometry buffers
+  for (int f = 0; f < 2; ++f) {
+    if (c->odo_gradmag_tex[f]) cudaDestroyTextureObject(c->odo_gradmag_tex[f]);
+    cudaFree(c->odo_gradmag[f]);
+    for (int sc = 0; sc < c->odo_scales; ++sc) {
+      ref_context::OdoImage& im = c->odo[f][sc];
+      if (im.tex) cudaDestroyTextureObject(im.tex);
+      cudaFree(im.depth);
+      if (im.owns_normals && sc >= 1) cudaFree(im.normals);
+      cudaFree(im.color);
+    }
+  }
+  if (c->odo_frame.tex) cudaDestroyTextureObject(c->odo_frame.tex);
+  cudaFree(c->odo_frame.depth); cudaFree(c->odo_frame.normals); cudaFree(c->odo_frame.color);
+  cudaFree(c->odo_debug);
   for (auto& e : c->ev) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -1237,16 +1253,20 @@ void OdoAccumulate(ref_context* c, int scale, const float base_T_frame[7], bool 
   const ref_context::OdoImage& trk = c->odo[1][scale];
   CUDABuffer_<u32> cnt_buf(c->residual_count, 1, 1, sizeof(u32));
   CUDABuffer_<float> sum_buf(c->residual_sum, 1, 1, sizeof(float)), H_buf(c->H, 1, 21, sizeof(float) * 21), b_buf(c->b, 1, 6, sizeof(float) * 6);
+  // with debug = true the kernels also write a residual image (kernel_opt_pose.cu:578-585): it must exist
+  if (debug && !c->odo_debug) cudaMallocPitch(reinterpret_cast<void**>(&c->odo_debug), &c->odo_debug_pitch, sizeof(float) * c->cfg.depth_w, c->cfg.depth_h);
+  CUDABuffer_<float> debug_image(c->odo_debug, base.h, base.w, c->odo_debug_pitch);
+  CUDABuffer_<float>* debug_ptr = debug ? &debug_image : nullptr;
   if (use_gradmag)
     CallAccumulatePoseEstimationCoeffsFromImagesCUDAKernel_GradMag(
         s, debug, c->cfg.use_depth_residuals != 0, c->cfg.use_descriptor_residuals != 0, CornerProjector(k.dK), CenterProjector(k.cK),
         CenterUnprojector(k.dK), c->cfg.baseline_fx, DepthToColorScaled(k), threshold_factor, FrameTBase(base_T_frame), DepthBuf(base),
-        NormalsBuf(base), ColorBuf(base), DepthBuf(trk), NormalsBuf(trk), trk.tex, cnt_buf, sum_buf, H_buf, b_buf, nullptr);
+        NormalsBuf(base), ColorBuf(base), DepthBuf(trk), NormalsBuf(trk), trk.tex, cnt_buf, sum_buf, H_buf, b_buf, debug_ptr);
   else
     CallAccumulatePoseEstimationCoeffsFromImagesCUDAKernel_GradientXY(
         s, debug, c->cfg.use_depth_residuals != 0, c->cfg.use_descriptor_residuals != 0, CornerProjector(k.dK), CenterProjector(k.cK),
         CenterUnprojector(k.dK), c->cfg.baseline_fx, DepthToColorScaled(k), threshold_factor, FrameTBase(base_T_frame), DepthBuf(base),
-        NormalsBuf(base), ColorBuf(base), DepthBuf(trk), NormalsBuf(trk), trk.tex, cnt_buf, sum_buf, H_buf, b_buf, nullptr);
+        NormalsBuf(base), ColorBuf(base), DepthBuf(trk), NormalsBuf(trk), trk.tex, cnt_buf, sum_buf, H_buf, b_buf, debug_ptr);
   ++c->launches;
   if (debug) {
     cudaMemcpyAsync(count, c->residual_count, sizeof(u32), cudaMemcpyDeviceToHost, s);

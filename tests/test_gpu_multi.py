@@ -195,3 +195,83 @@ def test_two_rank_surfel_updates_match_single_gpu(tmp_path):
             dt, dr = pose_error(r0[f"{tag}_poses"][k], poses[k])
             assert dt < 2e-5 and dr < 2e-5, (tag, k, dt, dr)
     assert np.array_equal(r0["peer_surfels"].view(np.uint32), r0["gather_surfels"].view(np.uint32))
+
+
+def _pcg_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from badslam_b200.direct_ba import DirectBA
+    from badslam_b200._lib import BadBAError
+    out = {}
+    for tag, peers, intr in (("gather", False, False), ("peer", True, False), ("intr", True, True)):
+        sc = _distorted_small() if intr else _small()
+        ba = DirectBA.from_scene(sc, device=f"cuda:{rank}", rank=rank, world_size=world)
+        ba.SetCollective()
+        if peers:
+            assert ba.EnablePeerExchange() == world - 1
+        r = ba.BundleAdjustment(None, intr, intr, False, True, True, 2, 2, use_pcg=True, pcg_max_inner_iterations=6, pcg_gauge_keyframe=1)
+        d, c, a = ba._intrinsics()
+        out[f"{tag}_poses"] = ba.GetKeyframeStates()[0]
+        out[f"{tag}_surfels"] = ba.GetSurfelsHost()
+        out[f"{tag}_intr"] = np.concatenate([d, c, [np.float32(a)]]).astype(np.float32)
+        out[f"{tag}_cf"] = ba.cfactor_buffer()
+        out[f"{tag}_stats"] = np.array([r.pcg_inner_iterations_total, r.iterations_done], np.int64)
+        out[f"{tag}_rnorm"] = np.float32(r.pcg_last_r_norm)
+    # the reference's random gauge keyframe cannot be drawn consistently on several ranks: it has to be pinned
+    ba = DirectBA.from_scene(_small(), device=f"cuda:{rank}", rank=rank, world_size=world)
+    ba.SetCollective()
+    try:
+        ba.BundleAdjustment(None, False, False, False, True, True, 1, 1, use_pcg=True)
+        out["unpinned_gauge_rejected"] = np.array(0)
+    except BadBAError:
+        out["unpinned_gauge_rejected"] = np.array(1)
+    np.savez(os.path.join(out_dir, f"pcg{rank}.npz"), **out)
+    dist.barrier(device_ids=[rank])
+    dist.destroy_process_group()
+
+
+def _small():
+    from badslam_b200.scene import config_by_name, make_scene
+    return make_scene(config_by_name("small"))
+
+
+def test_two_rank_pcg_matches_single_gpu(tmp_path):
+    """BundleAdjustmentPCG (direct_ba_pcg.cc:43-819) with 2 ranks: the matrix-free products are summed over each rank's surfel
+    shard and completed by one sum all-reduce of the vector (+ the alpha_d pair) per product; everything else runs replicated with
+    fixed-order sums.  Replicas bit-identical (poses, surfels, intrinsics, depth deformation, inner iteration counts); equal to
+    the single-GPU solve up to what fp32 conjugate gradients allow (tests/test_gpu_parity.py: the reference differs from itself
+    by 1e-5 m after 30 steps)."""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from badslam_b200.direct_ba import DirectBA
+    from badslam_b200.scene import pose_error
+    mp.spawn(_pcg_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "pcg0.npz"), np.load(tmp_path / "pcg1.npz")
+    assert int(r0["unpinned_gauge_rejected"]) == 1 and int(r1["unpinned_gauge_rejected"]) == 1
+    for tag in ("gather", "peer", "intr"):
+        for key in ("poses", "surfels", "intr", "cf", "stats", "rnorm"):
+            a, b = r0[f"{tag}_{key}"], r1[f"{tag}_{key}"]
+            assert np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a, b.view(np.uint32) if b.dtype == np.float32 else b), (tag, key)
+    assert np.array_equal(r0["peer_surfels"].view(np.uint32), r0["gather_surfels"].view(np.uint32))
+    for tag, intr in (("gather", False), ("intr", True)):
+        sc = _distorted_small() if intr else _small()
+        ba = DirectBA.from_scene(sc, device="cuda:0")
+        r = ba.BundleAdjustment(None, intr, intr, False, True, True, 2, 2, use_pcg=True, pcg_max_inner_iterations=6, pcg_gauge_keyframe=1)
+        poses, surf = ba.GetKeyframeStates()[0], ba.GetSurfelsHost()
+        assert tuple(r0[f"{tag}_stats"]) == (r.pcg_inner_iterations_total, r.iterations_done), (tag, r0[f"{tag}_stats"], r.pcg_inner_iterations_total)
+        assert abs(float(r0[f"{tag}_rnorm"]) - r.pcg_last_r_norm) < 1e-3 * max(1.0, r.pcg_last_r_norm)
+        for k in range(sc.cfg.num_keyframes):
+            dt, dr = pose_error(r0[f"{tag}_poses"][k], poses[k])
+            assert dt < 5e-5 and dr < 5e-5, (tag, k, dt, dr)
+        assert np.mean(np.abs(r0[f"{tag}_surfels"][:3] - surf[:3])) < 2e-6
+        if intr:
+            d, c, a = ba._intrinsics()
+            want = np.concatenate([d, c, [np.float32(a)]])
+            assert np.abs(r0["intr_intr"][:8] - want[:8]).max() < 5e-3 and abs(r0["intr_intr"][8] - want[8]) < 1e-3
+            assert np.abs(r0["intr_cf"] - ba.cfactor_buffer()).max() < 1e-4

@@ -140,7 +140,50 @@ def golden_preprocess(name="tiny", kf=1):
     print("wrote", name, "preprocess: valid", float(((depth & 0x8000) == 0).mean()), mn, mx)
 
 
+ODOMETRY_MOTION = [0.02, -0.01, 0.015, 0.01, -0.008, 0.012]   # base_T_frame of the tracked frame (tests/test_oracle_odometry.py)
+
+
+def golden_odometry(name="tiny", num_scales=3):
+    """Image-pair odometry (BadSlam::RunOdometry + TrackFramePairwise) on the reference's own kernels: the pyramids of keyframe 0
+    and of a frame rendered 2 cm / 1 degree away from it, the normal equations / costs at two poses on every level, and the
+    result of the whole coarse-to-fine optimisation (twice: the reference's own run-to-run difference)."""
+    from badslam_b200 import scene as S
+    sc = make_scene(config_by_name(name))
+    true_rel = S.se3_exp(ODOMETRY_MOTION)
+    depth, normals, _, color = S.render_frame(sc, S.se3_mul(sc.poses_true[0], true_rel))
+    ident = np.array([0, 0, 0, 1, 0, 0, 0], np.float32)
+    init2 = S.se3_exp([0.01, 0.0, 0.0, 0.0, 0.0, 0.0])
+    out = {"scene": name, "num_scales": num_scales, "true_rel": true_rel, "init2": init2,
+           "frame_checksum": int(depth.astype(np.uint64).sum()) + int(color.astype(np.uint64).sum())}
+    for tag, gm in (("", False), ("_gradmag", True)):
+        ref = ref_cuda.RefDirectBA(sc)
+        est, res = ref.track_frame_pairwise(0, depth, normals, color, ident, init2, num_scales=num_scales, use_gradmag=gm)
+        est2, _ = ref.track_frame_pairwise(0, depth, normals, color, ident, init2, num_scales=num_scales, use_gradmag=gm)
+        out[f"est{tag}"], out[f"est_rerun{tag}"] = est, est2
+        out[f"iterations{tag}"] = np.array(list(res.iterations)[:num_scales])
+        out[f"chose_initial{tag}"] = np.array(list(res.chose_initial)[:num_scales])
+        off = S.se3_mul(true_rel, S.se3_exp([0.004, -0.003, 0.002, 0.002, 0.001, -0.002]))
+        out["off"] = off
+        for scale in range(num_scales):
+            for which, wn in ((0, "base"), (1, "tracked")):
+                d, n, c = ref.odometry_level(which, scale)
+                out[f"{wn}{scale}_depth{tag}"], out[f"{wn}{scale}_color{tag}"] = d, c
+                out[f"{wn}{scale}_normals{tag}"] = np.where(d > 0, n, 0).astype(np.uint16)
+            H, b, cnt, sm, counts, costs = ref.odometry_coeffs(scale, true_rel, off, use_gradmag=gm)
+            out[f"H{scale}{tag}"], out[f"b{scale}{tag}"] = H, b
+            out[f"count{scale}{tag}"], out[f"sum{scale}{tag}"] = cnt, sm
+            out[f"cost_counts{scale}{tag}"], out[f"cost_costs{scale}{tag}"] = counts, costs
+        ref.close()
+    os.makedirs("gpurun_out/golden", exist_ok=True)
+    np.savez_compressed(f"gpurun_out/golden/{name}_odometry.npz", **out)
+    print("wrote", name, "odometry: iterations", out["iterations"], "counts", [int(out[f"count{s}"]) for s in range(num_scales)],
+          "error to the rendered motion", S.pose_error(out["est"], true_rel))
+
+
 if __name__ == "__main__":
+    if "--odometry-only" in sys.argv:
+        golden_odometry("tiny")
+        sys.exit(0)
     if "--preprocess-only" in sys.argv:
         golden_preprocess("tiny")
         sys.exit(0)
@@ -158,3 +201,4 @@ if __name__ == "__main__":
     golden_intrinsics_pcg("tiny")
     golden_end_tasks("tiny")
     golden_preprocess("tiny")
+    golden_odometry("tiny")
