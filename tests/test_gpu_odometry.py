@@ -9,7 +9,7 @@ What is demanded:
   * the whole coarse-to-fine optimisation: the Gauss-Newton iterations of this path do not settle to a fixed point on every
     level (associations flip between iterations; the reference caps them at 30 per level), so two runs that differ in the last
     bit drift apart like the reference drifts from itself (unordered float atomics): the poses must agree to 1e-5 m / rad plus
-    three times the reference's own run-to-run difference, and reach an equally low cost.
+    ten times the reference's own run-to-run spread (three extra runs), with identical iteration counts and an equally low cost.
 """
 import numpy as np
 import pytest
