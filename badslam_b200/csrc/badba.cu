@@ -2160,6 +2160,7 @@ bba_status BuildOdometryPyramids(bba_handle h, const bba_odometry_options& o, co
       d.count = 2;
     }
     d.w = st.w[l]; d.h = st.h[l];
+    d.in_w = st.w[l - 1]; d.in_h = st.h[l - 1];
     od::LaunchDownsample(d, s);
     ++h->launches;
   }

@@ -154,14 +154,18 @@ __global__ void __launch_bounds__(256) DownsampleKernel(const __grid_constant__ 
   if (x >= a.w || y >= a.h) return;
   const Image& in = a.in[blockIdx.z];
   const Image& o = a.out[blockIdx.z];
-  // DownsampleImagesCUDAKernel, kernel_downsample.cu:107-156
-  constexpr int kOffsets[4][2] = {{0, 0}, {0, 1}, {1, 0}, {1, 1}};
+  // DownsampleImagesCUDAKernel, kernel_downsample.cu:107-156 (block order {0,0}, {0,1}, {1,0}, {1,1} as (row, column) offsets)
   float depths[4];
   float depth_sum = 0;
   int depth_count = 0;
+  // (With image sizes that are not multiples of 2^levels a coarse level can be one pixel wider than half the finer one rounded
+  //  down allows -- 37 -> 18 needs column 37 -- and the reference then reads the row padding.  Clamped here: defined, and
+  //  identical to the reference whenever the reference's result is defined.)
+  const int x1 = min(2 * x + 1, a.in_w - 1), y1 = min(2 * y + 1, a.in_h - 1);
+  const int xs[4] = {2 * x, x1, 2 * x, x1}, ys[4] = {2 * y, 2 * y, y1, y1};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    depths[i] = in.depth[static_cast<size_t>(2 * y + kOffsets[i][0]) * in.depth_pitch + 2 * x + kOffsets[i][1]];
+    depths[i] = in.depth[static_cast<size_t>(ys[i]) * in.depth_pitch + xs[i]];
     if (depths[i] > 0) {
       depth_sum += depths[i];
       depth_count += 1;
@@ -174,7 +178,7 @@ __global__ void __launch_bounds__(256) DownsampleKernel(const __grid_constant__ 
     o.depth[static_cast<size_t>(y) * o.depth_pitch + x] = 0;
   } else {
     o.depth[static_cast<size_t>(y) * o.depth_pitch + x] = depths[c];
-    StoreU16(o.normals, o.normals_pitch, x, y, LoadU16(in.normals, in.normals_pitch, 2 * x + kOffsets[c][1], 2 * y + kOffsets[c][0]));
+    StoreU16(o.normals, o.normals_pitch, x, y, LoadU16(in.normals, in.normals_pitch, xs[c], ys[c]));
   }
   const float color = tex2D<float>(in.color_tex, 2 * x + 1.0f, 2 * y + 1.0f);
   o.color[static_cast<size_t>(y) * o.color_pitch + x] = static_cast<uint8_t>(255.f * color + 0.5f);

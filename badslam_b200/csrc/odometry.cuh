@@ -79,6 +79,7 @@ struct DownsampleArgs {
   Image in[2], out[2];
   int count;      // images to process (2 = base + tracked, 1 = base only)
   int w, h;       // output size
+  int in_w, in_h; // input size (>= 2 w, 2 h; one more when the finer level is odd-sized)
 };
 void LaunchDownsample(const DownsampleArgs& a, cudaStream_t stream);
 
