@@ -157,6 +157,7 @@ SYMBOLS = {
     "bba_peer_import": (C.c_int, [_P, _P, C.c_int]),
     "bba_peer_count": (C.c_int, [_P]),
     "bba_peer_unmap": (C.c_int, [_P]),
+    "bba_mark_replica_rewritten": (C.c_int, [_P]),
     "bba_set_collective": (C.c_int, [_P, COLLECTIVE_FN, _P]),
     "bba_shard_surfel_owner": (C.c_int, [C.c_uint32, C.c_int]),
     "bba_shard_surfel_local_index": (C.c_uint32, [C.c_uint32, C.c_int]),

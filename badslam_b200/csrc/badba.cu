@@ -17,6 +17,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/badba.h"
@@ -544,16 +545,20 @@ bba_status RunPoseStep(bba_handle h, const std::vector<int>& ids, const std::vec
     bba::LaunchPoseSolve(sol, s);
     ++h->launches;
     ++enqueued;
-    // Keep exactly one iteration queued ahead of the one executing: wait (host spin on zero-copy memory, the stream is
-    // never blocked) until iteration it-1 has finished, and stop as soon as it left no unconverged keyframe.
-    if (it >= 1) {
-      while (h->h_flag[0] < it) {
+    // Keep two iterations queued ahead of the one executing: wait (host poll on zero-copy memory, the stream is never
+    // blocked) until iteration it-2 has finished, and stop as soon as an iteration left no unconverged keyframe.  (An iteration
+    // whose list turned out empty costs three immediately-returning launches; a depth of two rides out a host thread that is
+    // descheduled for a moment -- on a box whose cores are oversubscribed a depth of one left the GPU idle between iterations.)
+    if (it >= 2) {
+      unsigned int polls = 0;
+      while (h->h_flag[0] < it - 1) {
         // cudaSuccess: everything drained; any other result than "not ready" is a (sticky) device fault that would
         // otherwise leave this loop spinning for ever -- the BBA_CUDA check below reports it
         if (cudaStreamQuery(s) != cudaErrorNotReady) break;
+        if (++polls > 256 && (polls & 15) == 0) std::this_thread::yield();   // let the other ranks' host threads run
       }
-      if (h->h_flag[0] >= it && h->h_flag[1] == 0) break;
     }
+    if (it >= 1 && h->h_flag[0] >= 1 && h->h_flag[1] == 0) break;   // (h_flag[1] belongs to the last finished iteration)
   }
   BBA_CUDA(h, cudaGetLastError());
   if (world > 1) {
@@ -714,6 +719,11 @@ bba_status BuildGeometryArgs(bba_handle h, bba::GeometryArgs* g, cudaStream_t s)
   g->kf_count = cnt;
   g->queue = h->d_geo_queue;
   g->tile_shift = 8;
+  // Keyframes per work item.  A group's images (1.5 MB per keyframe at 640x480) are what all resident warps gather from at one
+  // time; between groups a surfel's partial sums are parked in the scratch rows.  16 keeps a group's images in a fifth of the L2
+  // when millions of surfels stream past them; (development switch BADBA_GEO_GROUP for A/B runs)
+  static const int group_override = std::getenv("BADBA_GEO_GROUP") ? std::atoi(std::getenv("BADBA_GEO_GROUP")) : 0;
+  g->group = group_override;
   g->peers = (h->cfg.world_size > 1 && h->peers.count == h->cfg.world_size - 1) ? h->peers : bba::PeerSet{};
   if (!h->d_tile_epoch || h->tile_epoch_capacity < (h->surfels_size + 31u) / 32u) {
     cudaFree(h->d_tile_epoch);
@@ -2755,6 +2765,12 @@ bba_status bba_peer_import(bba_handle h, const bba_peer_handle* all, int count) 
 }
 
 int bba_peer_count(bba_handle h) { return h ? h->peers.count : 0; }
+
+bba_status bba_mark_replica_rewritten(bba_handle h) {
+  if (!h) return BBA_ERR_INVALID_ARGUMENT;
+  h->replicated_pass_pending = true;   // -> PeerFence in front of the next kernel with peer stores
+  return BBA_OK;
+}
 
 bba_status bba_peer_unmap(bba_handle h) {
   if (!h) return BBA_ERR_INVALID_ARGUMENT;

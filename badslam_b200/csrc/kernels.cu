@@ -228,6 +228,9 @@ __device__ __forceinline__ int AccSlot(int lane) {
 #define BBA_POSE_CHUNK_SHIFT 8
 #endif
 constexpr int kPoseChunkShift = BBA_POSE_CHUNK_SHIFT;   // log2 of the surfels one warp evaluates per (keyframe) sub-item
+#ifndef BBA_POSE_ITEM_CHUNKS
+#define BBA_POSE_ITEM_CHUNKS 1   // sub-item size chosen per item from the number of keyframes in its group
+#endif
 #ifndef BBA_POSE_NOBARRIER
 #define BBA_POSE_NOBARRIER 1   // item loop without a CTA-wide barrier (the last warp out of a stage re-arms it)
 #endif
@@ -266,11 +269,9 @@ __global__ void __launch_bounds__(kPoseThreads, BBA_POSE_MIN_CTAS) PoseAccumulat
   const uint32_t n_tiles = (args.n + TILE - 1) / TILE;
   const uint32_t n_groups = (n_work + kPoseGroup - 1) / kPoseGroup;
   const uint32_t n_items = n_groups * n_tiles;
-  // 256-surfel chunks (one warp-level reduction per 8 steps); 128 when there are few keyframes so that all warps get work
+  // 256-surfel chunks (one warp-level reduction per 8 steps); smaller ones when the item's group holds few keyframes, so that
+  // every warp of the CTA still finds a sub-item (the tail of a Gauss-Newton loop, the last group of a short work list)
   constexpr int kTileShift = (TILE == 1024) ? 10 : (TILE == 512) ? 9 : 8;
-  const int chunk_shift = (n_work >= 4) ? (kPoseChunkShift < kTileShift ? kPoseChunkShift : kTileShift) : 7;
-  const uint32_t chunk_len = 1u << chunk_shift;
-  const int chunks_per_tile = TILE >> chunk_shift;
 
   const CameraParams& cam = args.cam;
   constexpr int kRowIds[kPoseStagedRows] = {kRowX, kRowY, kRowZ, kRowNormal, kRowRadiusSq, kRowD1, kRowD2};
@@ -371,6 +372,14 @@ __global__ void __launch_bounds__(kPoseThreads, BBA_POSE_MIN_CTAS) PoseAccumulat
     const uint32_t base = tile * TILE;
     const uint32_t cnt = min(static_cast<uint32_t>(TILE), args.n - base);
     const int kfs_in_group = min(kPoseGroup, n_work - static_cast<int>(group) * kPoseGroup);
+#if BBA_POSE_ITEM_CHUNKS
+    const int wanted_shift = kfs_in_group >= 4 ? kPoseChunkShift : (kfs_in_group >= 2 ? 7 : 6);
+#else
+    const int wanted_shift = n_work >= 4 ? kPoseChunkShift : 7;   // (round-1 rule: one size per launch; kept for A/B builds)
+#endif
+    const int chunk_shift = wanted_shift < kTileShift ? wanted_shift : kTileShift;
+    const uint32_t chunk_len = 1u << chunk_shift;
+    const int chunks_per_tile = TILE >> chunk_shift;
     const int n_sub = kfs_in_group * chunks_per_tile;
 
     for (;;) {
@@ -684,6 +693,27 @@ __device__ __forceinline__ void StageGroupRecords(const KfDevice* __restrict__ k
   __syncwarp();
 }
 
+// The records of ALL keyframes of the launch, copied once per CTA (persistent grid) when they fit the shared-memory budget:
+// the per-item staging above costs a coalesced copy + an L2 round trip per (group, tile) item, which is noise next to a 256-surfel
+// tile but a fifth of the work of the 32-surfel tiles a rank of an 8-GPU job ends up with.
+#ifndef BBA_GEO_STAGE_ALL
+#define BBA_GEO_STAGE_ALL 1
+#endif
+constexpr int kGeoStageAllMax = 48 * 1024 / static_cast<int>(sizeof(KfDevice));   // 512 keyframes
+__device__ __forceinline__ void StageAllRecords(const KfDevice* __restrict__ kfs, const int* __restrict__ kf_list, int count, KfDevice* dst) {
+  constexpr int kWords = sizeof(KfDevice) / 16;
+  for (int idx = threadIdx.x; idx < count * kWords; idx += blockDim.x) {
+    const int rec = idx / kWords, part = idx - rec * kWords;
+    const int kf = __ldg(kf_list + rec);
+    reinterpret_cast<uint4*>(dst + rec)[part] = __ldg(reinterpret_cast<const uint4*>(kfs + kf) + part);
+  }
+  __syncthreads();
+}
+__host__ __device__ inline bool GeoStageAll(int kf_count) { return BBA_GEO_STAGE_ALL && kf_count <= kGeoStageAllMax; }
+// Keyframes per work item: the launcher's choice (GeometryArgs::group) when all records sit in shared memory, else the size of the
+// per-warp record slices.
+__host__ __device__ inline int GeoGroupSize(const GeometryArgs& a) { return (GeoStageAll(a.kf_count) && a.group > 0) ? a.group : kGeoGroup; }
+
 // One (surfel, keyframe) pair between "gathers issued" and "gathers consumed": two of them are kept in flight per thread.
 struct PendingPair {
   bool in_image;
@@ -693,20 +723,24 @@ struct PendingPair {
 
 template <bool DETERMINE, bool NORMALS>
 __global__ void __launch_bounds__(kGeoThreads) ActivationNormalsKernel(const __grid_constant__ GeometryArgs a) {
-  __shared__ __align__(16) KfDevice s_kfs[kGeoThreads / 32][kGeoGroup];
+  extern __shared__ __align__(16) unsigned char geo_smem[];   // all records, or one kGeoGroup-record slice per warp
+  KfDevice* s_kfs = reinterpret_cast<KfDevice*>(geo_smem);
   const uint32_t tile_len = 1u << a.tile_shift;
   const uint32_t n_tiles = (a.end - a.begin + tile_len - 1) >> a.tile_shift;
-  const uint32_t n_groups = (a.kf_count + kGeoGroup - 1) / kGeoGroup;
+  const bool stage_all = GeoStageAll(a.kf_count);
+  const int G = GeoGroupSize(a);   // keyframes per work item
+  const uint32_t n_groups = (a.kf_count + G - 1) / G;
   const uint32_t n_items = n_groups * n_tiles;
   const size_t P = a.pitch;
   const int lane = threadIdx.x & 31;
-  KfDevice* recs = s_kfs[threadIdx.x >> 5];
+  if (stage_all) StageAllRecords(a.kfs, a.kf_list, a.kf_count, s_kfs);
   uint32_t group, tile;
   while (NextGeoItem(a, n_tiles, n_items, &group, &tile)) {
     const bool first = group == 0, last = group + 1 == n_groups;
-    const int j_begin = group * kGeoGroup, j_end = min(a.kf_count, static_cast<int>(group + 1) * kGeoGroup);
+    const int j_begin = group * G, j_end = min(a.kf_count, static_cast<int>(group + 1) * G);
     const int n_kf = j_end - j_begin;
-    StageGroupRecords(a.kfs, a.kf_list + j_begin, n_kf, recs, lane);
+    KfDevice* recs = stage_all ? s_kfs + j_begin : s_kfs + (threadIdx.x >> 5) * kGeoGroup;
+    if (!stage_all) StageGroupRecords(a.kfs, a.kf_list + j_begin, n_kf, recs, lane);
     for (uint32_t sub = 0; sub < tile_len / 32; ++sub) {
       const uint32_t li = a.begin + (tile << a.tile_shift) + sub * 32 + lane;
       const uint32_t i = SurfelShardToGlobal(li, a.shard_rank, a.shard_world);
@@ -796,19 +830,23 @@ __global__ void __launch_bounds__(kGeoThreads) ActivationNormalsKernel(const __g
 
 template <bool USE_DEPTH, bool USE_DESC>
 __global__ void __launch_bounds__(kGeoThreads, 3) PositionDescriptorKernel(const __grid_constant__ GeometryArgs a) {
-  __shared__ __align__(16) KfDevice s_kfs[kGeoThreads / 32][kGeoGroup];
-  KfDevice* recs = s_kfs[threadIdx.x >> 5];
+  extern __shared__ __align__(16) unsigned char geo_smem[];
+  KfDevice* s_kfs = reinterpret_cast<KfDevice*>(geo_smem);
+  const bool stage_all = GeoStageAll(a.kf_count);
+  if (stage_all) StageAllRecords(a.kfs, a.kf_list, a.kf_count, s_kfs);
   const uint32_t tile_len = 1u << a.tile_shift;
   const uint32_t n_tiles = (a.end - a.begin + tile_len - 1) >> a.tile_shift;
-  const uint32_t n_groups = (a.kf_count + kGeoGroup - 1) / kGeoGroup;
+  const int G = GeoGroupSize(a);
+  const uint32_t n_groups = (a.kf_count + G - 1) / G;
   const uint32_t n_items = n_groups * n_tiles;
   const size_t P = a.pitch;
   const int lane = threadIdx.x & 31;
   uint32_t group, tile;
   while (NextGeoItem(a, n_tiles, n_items, &group, &tile)) {
     const bool first = group == 0, last = group + 1 == n_groups;
-    const int j_begin = group * kGeoGroup, j_end = min(a.kf_count, static_cast<int>(group + 1) * kGeoGroup);
-    StageGroupRecords(a.kfs, a.kf_list + j_begin, j_end - j_begin, recs, lane);
+    const int j_begin = group * G, j_end = min(a.kf_count, static_cast<int>(group + 1) * G);
+    KfDevice* recs = stage_all ? s_kfs + j_begin : s_kfs + (threadIdx.x >> 5) * kGeoGroup;
+    if (!stage_all) StageGroupRecords(a.kfs, a.kf_list + j_begin, j_end - j_begin, recs, lane);
     for (uint32_t sub = 0; sub < tile_len / 32; ++sub) {
       const uint32_t li = a.begin + (tile << a.tile_shift) + sub * 32 + lane;
       const uint32_t i = SurfelShardToGlobal(li, a.shard_rank, a.shard_world);
@@ -963,10 +1001,14 @@ __global__ void __launch_bounds__(kGeoThreads, 3) PositionDescriptorKernel(const
 // Persistent grid: as many CTAs as can be co-resident (the epoch wait relies on every launched CTA being scheduled).
 // The tile (the unit one warp walks through, 32..256 surfels) is chosen so that every keyframe group offers several
 // items per resident warp: with too few tiles the per-tile epoch chain serialises the groups (seen at 2+ ranks).
+static size_t GeoSmemBytes(int kf_count) {
+  return sizeof(KfDevice) * (GeoStageAll(kf_count) ? static_cast<size_t>(kf_count) : static_cast<size_t>(kGeoThreads / 32) * kGeoGroup);
+}
+
 template <typename Kernel>
 static uint32_t GeoGrid(Kernel kernel, GeometryArgs* a, int sm_count) {
   int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kGeoThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kGeoThreads, GeoSmemBytes(a->kf_count));
   if (per_sm < 1) per_sm = 1;
   const uint64_t resident_warps = static_cast<uint64_t>(per_sm) * sm_count * (kGeoThreads / 32);
   const uint32_t n = a->end - a->begin;
@@ -974,7 +1016,8 @@ static uint32_t GeoGrid(Kernel kernel, GeometryArgs* a, int sm_count) {
   while (shift > 5 && 2 * static_cast<uint64_t>((n + (1u << shift) - 1) >> shift) < 3 * resident_warps) --shift;
   a->tile_shift = shift;
   const uint32_t n_tiles = (n + (1u << shift) - 1) >> shift;
-  const uint32_t n_groups = (a->kf_count + kGeoGroup - 1) / kGeoGroup;
+  const int G = GeoGroupSize(*a);
+  const uint32_t n_groups = (a->kf_count + G - 1) / G;
   const uint64_t n_items = static_cast<uint64_t>(n_tiles) * (n_groups ? n_groups : 1);
   const uint64_t ctas_needed = (n_items + kGeoThreads / 32 - 1) / (kGeoThreads / 32);   // one item per warp
   return static_cast<uint32_t>(std::min<uint64_t>(ctas_needed, static_cast<uint64_t>(per_sm) * sm_count));
@@ -990,7 +1033,7 @@ template <typename Kernel>
 static void LaunchGeo(Kernel kernel, GeometryArgs a, int sm_count, cudaStream_t stream) {
   const uint32_t grid = GeoGrid(kernel, &a, sm_count);
   PrepareGeo(a, stream);
-  kernel<<<grid, kGeoThreads, 0, stream>>>(a);
+  kernel<<<grid, kGeoThreads, GeoSmemBytes(a.kf_count), stream>>>(a);
 }
 
 void LaunchActivationAndNormals(const GeometryArgs& a, int sm_count, bool determine_activation, bool update_normals, cudaStream_t stream) {

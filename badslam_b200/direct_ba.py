@@ -592,6 +592,11 @@ class DirectBA:
         return int(self._lib.bba_peer_count(self._h))
 
     # -- multi-GPU (one process per GPU) ---------------------------------------------------------------
+    def MarkReplicaRewritten(self):
+        """bba_mark_replica_rewritten: call on every rank after rewriting the surfel replica outside the library (e.g. restoring a
+        snapshot) while peers are mapped."""
+        self._check(self._lib.bba_mark_replica_rewritten(self._h))
+
     def SetCollective(self, group=None):
         """Registers the exchange step (bba_set_collective) on top of torch.distributed (NCCL over NVLink): in-place
         all-gather of the updated surfel shards, sum all-reduce of the pose slots."""

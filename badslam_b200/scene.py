@@ -64,6 +64,10 @@ def config_by_name(name: str) -> SceneConfig:
                            pose_spread_t=1.5, name="cfg4")
     if name == "cfg5":
         return SceneConfig(1280, 720, 400, 8_000_000, cell=4, seed=5, name="cfg5")
+    if name == "cfg3_rank8":
+        # what ONE rank of an 8-GPU cfg3 job sees in the geometry step: every keyframe, an eighth of the surfels (development
+        # workload for tuning the geometry kernels at small shards on a single GPU, tools/ab_fast.py --workload cfg3_rank8)
+        return SceneConfig(640, 480, 200, 375_000, cell=4, seed=3, name="cfg3_rank8")
     if name == "tiny":
         return SceneConfig(160, 120, 4, 6000, cell=2, seed=7, name="tiny")
     if name == "small":
@@ -504,11 +508,9 @@ def make_scene(cfg: SceneConfig, verbose: bool = False) -> Scene:
     cache = os.environ.get("BADBA_SCENE_CACHE")
     if not cache:
         return _make_scene(cfg, verbose)
-    import hashlib
     import pickle
     os.makedirs(cache, exist_ok=True)
-    key = hashlib.sha1(repr(cfg).encode()).hexdigest()[:12]
-    path = os.path.join(cache, f"{cfg.name}_{key}.pkl")
+    path = scene_cache_path(cfg, cache)
     if os.path.exists(path):
         with open(path, "rb") as f:
             return pickle.load(f)
@@ -518,6 +520,12 @@ def make_scene(cfg: SceneConfig, verbose: bool = False) -> Scene:
         pickle.dump(sc, f, protocol=4)
     os.replace(tmp, path)
     return sc
+
+
+def scene_cache_path(cfg: SceneConfig, cache_dir: str) -> str:
+    import hashlib
+    import os
+    return os.path.join(cache_dir, f"{cfg.name}_{hashlib.sha1(repr(cfg).encode()).hexdigest()[:12]}.pkl")
 
 
 def _make_scene(cfg: SceneConfig, verbose: bool = False) -> Scene:

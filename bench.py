@@ -210,6 +210,8 @@ def run_ours(args, scene, rank, world):
 
     def step():
         surf[:8].copy_(backup, non_blocking=True)
+        if world > 1:
+            ba.MarkReplicaRewritten()   # (the other ranks' geometry kernels store into this replica: fence them behind the restore)
         ba.SetKeyframeStates(poses0, act0)
         if intr:
             ba.SetDepthCamera(cam0[0]); ba.SetColorCamera(cam0[1]); ba.SetA(cam0[2]); ba.SetCFactorBuffer(cam0[3])
@@ -277,8 +279,11 @@ def run_ours(args, scene, rank, world):
 
     # full BA (10 continuing iterations) for the second headline number
     surf[:8].copy_(backup)
+    if world > 1:
+        ba.MarkReplicaRewritten()
     ba.SetKeyframeStates(poses0, act0)
     torch.cuda.synchronize()
+    barrier()
     t0 = time.perf_counter()
     full = ba.BundleAdjustment(None, False, False, False, True, True, 10, 10)
     torch.cuda.synchronize()
@@ -312,6 +317,9 @@ def run_ours(args, scene, rank, world):
         out["e2e_all_keyframes"] = e2e_all
     if multi_gpu_check is not None:
         out["multi_gpu_check"] = multi_gpu_check
+    # host side of the box (the Gauss-Newton loop of the pose step polls from a host thread per rank: a box whose cores are
+    # oversubscribed by other tenants shows up here)
+    out["host"] = {"cpus_available": len(os.sched_getaffinity(0)), "loadavg_1min": round(os.getloadavg()[0], 1)}
     if intr:
         out["config"]["intrinsics"] = "depth intrinsics + depth deformation + colour intrinsics optimised in every step (--intrinsics)"
         out["stage_ms"]["BA_intrinsics_optimization"] = res.ms_intrinsics_optimization
@@ -576,6 +584,17 @@ def _main(saved_stdout):
     from badslam_b200.scene import config_by_name, make_scene
     if args.impl == "reference" and rank != 0:
         return 0
+    if world > 1:
+        # one process per GPU: rank 0 generates the (seeded, identical) scene once and the other ranks load its pickle, instead of
+        # every rank spending a host-core-minute on the same numpy work
+        from badslam_b200.scene import scene_cache_path
+        cache = os.environ.setdefault("BADBA_SCENE_CACHE", os.path.join(
+            "/tmp", f"badba_scenes_{os.environ.get('MASTER_PORT', '0')}_{os.environ.get('TORCHELASTIC_RUN_ID', 'run')}"))
+        path = scene_cache_path(config_by_name(args.workload), cache)
+        if rank != 0:
+            t_wait = time.time()
+            while not os.path.exists(path) and time.time() - t_wait < 1800:
+                time.sleep(0.2)
     scene = make_scene(config_by_name(args.workload))
     if args.impl == "reference":
         out = run_reference(args, scene)

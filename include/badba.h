@@ -284,6 +284,12 @@ bba_status bba_peer_import(bba_handle h, const bba_peer_handle* all_ranks, int c
 int bba_peer_count(bba_handle h);
 /* Back to the host-collective exchange (all ranks must agree on the mode: a rank whose import failed makes everyone unmap). */
 bba_status bba_peer_unmap(bba_handle h);
+/* With mapped peers the geometry kernels of the OTHER ranks store into this rank's replica.  A caller that rewrites its replica
+ * outside the library (restores a snapshot of the surfel rows, uploads new surfels in place, ...) must say so on every rank, in
+ * the same place: the next kernel that stores into peer replicas is then preceded by a barrier across the ranks, so that no
+ * rank's stores can land in a replica before its owner's rewrite has happened (and be overwritten by it).  No-op on one GPU
+ * or with the host-collective exchange. */
+bba_status bba_mark_replica_rewritten(bba_handle h);
 
 /* The partition itself, exposed so that hosts and tests can reason about it.
  * Surfels: 256-surfel granules are dealt round-robin (granule g -> rank g % world_size), which gives every rank the same
