@@ -228,8 +228,12 @@ __device__ __forceinline__ int AccSlot(int lane) {
 #define BBA_POSE_CHUNK_SHIFT 8
 #endif
 constexpr int kPoseChunkShift = BBA_POSE_CHUNK_SHIFT;   // log2 of the surfels one warp evaluates per (keyframe) sub-item
+// Sub-item size chosen per ITEM from the number of keyframes in its group (so that the last, short group of a work list and the
+// tail of a Gauss-Newton loop still offer every warp a sub-item) instead of per launch.  OFF: measured on B200 at cfg3 it is
+// 0.5 % slower (pose stage 20.26 vs 20.15 ms; the extra warp reductions of the smaller chunks cost more than the idle warps of
+// the few short groups), tools/r2_gpu14.sh.
 #ifndef BBA_POSE_ITEM_CHUNKS
-#define BBA_POSE_ITEM_CHUNKS 1   // sub-item size chosen per item from the number of keyframes in its group
+#define BBA_POSE_ITEM_CHUNKS 0
 #endif
 #ifndef BBA_POSE_NOBARRIER
 #define BBA_POSE_NOBARRIER 1   // item loop without a CTA-wide barrier (the last warp out of a stage re-arms it)
@@ -693,11 +697,14 @@ __device__ __forceinline__ void StageGroupRecords(const KfDevice* __restrict__ k
   __syncwarp();
 }
 
-// The records of ALL keyframes of the launch, copied once per CTA (persistent grid) when they fit the shared-memory budget:
-// the per-item staging above costs a coalesced copy + an L2 round trip per (group, tile) item, which is noise next to a 256-surfel
-// tile but a fifth of the work of the 32-surfel tiles a rank of an 8-GPU job ends up with.
+// The records of ALL keyframes of the launch, copied once per CTA (persistent grid) when they fit the shared-memory budget,
+// instead of a coalesced copy + an L2 round trip per (group, tile) item.  OFF: measured on B200 (tools/r2_gpu14.sh) it does not
+// pay -- position + descriptor 4.76 vs 4.58 ms at cfg3 and 0.81 vs 0.77 ms on one rank's share of an 8-GPU job (cfg3_rank8),
+// activation + normals unchanged: the per-warp slices keep the records a warp reads next to each other, the 19 KB block does not.
+// With it on, GeometryArgs::group (keyframes per work item, BADBA_GEO_GROUP) becomes a runtime choice: 32 / 64 / 200 instead of
+// 16 moved the two kernels by -10 % / +2 % ... +0 % / +38 % at cfg3_rank8, i.e. no setting beats 16 for both.
 #ifndef BBA_GEO_STAGE_ALL
-#define BBA_GEO_STAGE_ALL 1
+#define BBA_GEO_STAGE_ALL 0
 #endif
 constexpr int kGeoStageAllMax = 48 * 1024 / static_cast<int>(sizeof(KfDevice));   // 512 keyframes
 __device__ __forceinline__ void StageAllRecords(const KfDevice* __restrict__ kfs, const int* __restrict__ kf_list, int count, KfDevice* dst) {

@@ -290,25 +290,30 @@ def test_intrinsics_step_three_way(mods, opt_depth, opt_color):
     """OptimizeIntrinsicsCUDA (kernel_opt_intrinsics.cc:39-281): one step, ours vs the reference kernels vs the oracle."""
     S, DirectBA, O, R = mods
     sc = _distorted_scene(S, "small")
-    ba, ref, orc = DirectBA.from_scene(sc), R.RefDirectBA(sc), O.Oracle(sc)
+    ba, ref, ref2, orc = DirectBA.from_scene(sc), R.RefDirectBA(sc), R.RefDirectBA(sc), O.Oracle(sc)
     # a non-zero deformation model, so that the d/da and d/dcfactor terms (kernel_opt_intrinsics.cu:97-113) are exercised
     a_init = 0.02
     cf_init = (np.random.default_rng(5).standard_normal(sc.cfactor.shape) * 0.003).astype(np.float32)
     ba.SetA(a_init); ba.SetCFactorBuffer(cf_init)
     ref.set_depth_params(a_init, cf_init)
+    ref2.set_depth_params(a_init, cf_init)
     orc.model.a = a_init; orc.cfactor[:] = cf_init
     for _ in range(2):
         ba.OptimizeIntrinsics(opt_depth, opt_color)
         ref.optimize_intrinsics(opt_depth, opt_color)
+        ref2.optimize_intrinsics(opt_depth, opt_color)
         orc.optimize_intrinsics(opt_depth, opt_color)
     d0, c0, a0 = ba._intrinsics()
     d1, c1, a1 = ref.intrinsics()
+    # `a` is the weakly constrained unknown of this step (hence the reference's prior, kernel_opt_intrinsics.cc:146-155): the
+    # reference's own run-to-run difference (unordered fp32 atomics on the per-cell terms) sets the scale of what can be asked
+    a_noise = abs(a1 - ref2.intrinsics()[2])
     d2, c2, a2 = np.array(orc.model.depth_K[:], np.float32), np.array(orc.model.color_K[:], np.float32), orc.model.a
     # the UPDATE (new - old, up to ~0.5 px here) must agree to 1e-4 relative of the parameter scale + fp32 atomics noise
     tol_d = REL * np.abs(d1) + 1e-3
     assert np.all(np.abs(d0 - d1) < tol_d), (d0, d1)
     assert np.all(np.abs(c0 - c1) < REL * np.abs(c1) + 1e-3), (c0, c1)
-    assert abs(a0 - a1) < 1e-5
+    assert abs(a0 - a1) < 1e-5 + 5 * a_noise, (a0, a1, a_noise)
     assert np.all(np.abs(d0 - d2) < tol_d) and np.all(np.abs(c0 - c2) < REL * np.abs(c2) + 1e-3) and abs(a0 - a2) < 1e-4
     cf0, cf1 = ba.cfactor_buffer(), ref.cfactor()
     if opt_depth:
