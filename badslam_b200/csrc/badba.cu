@@ -545,13 +545,15 @@ bba_status RunPoseStep(bba_handle h, const std::vector<int>& ids, const std::vec
     bba::LaunchPoseSolve(sol, s);
     ++h->launches;
     ++enqueued;
-    // Keep two iterations queued ahead of the one executing: wait (host poll on zero-copy memory, the stream is never
-    // blocked) until iteration it-2 has finished, and stop as soon as an iteration left no unconverged keyframe.  (An iteration
-    // whose list turned out empty costs three immediately-returning launches; a depth of two rides out a host thread that is
-    // descheduled for a moment -- on a box whose cores are oversubscribed a depth of one left the GPU idle between iterations.)
-    if (it >= 2) {
+    // Keep kDepth iterations queued ahead of the one executing: wait (host poll on zero-copy memory, the stream is never
+    // blocked) until iteration it-kDepth has finished, and stop as soon as an iteration left no unconverged keyframe.  (An
+    // iteration whose list turned out empty costs three immediately-returning launches, ~10 us; the depth rides out a host
+    // thread that is descheduled for a moment -- on a box whose cores were oversubscribed, 2 CPUs for 4 ranks, a depth of one
+    // left the GPU idle between iterations.)
+    constexpr int kDepth = 3;
+    if (it >= kDepth) {
       unsigned int polls = 0;
-      while (h->h_flag[0] < it - 1) {
+      while (h->h_flag[0] < it - kDepth + 1) {
         // cudaSuccess: everything drained; any other result than "not ready" is a (sticky) device fault that would
         // otherwise leave this loop spinning for ever -- the BBA_CUDA check below reports it
         if (cudaStreamQuery(s) != cudaErrorNotReady) break;
