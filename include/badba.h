@@ -232,7 +232,7 @@ bba_status bba_get_ba_iteration_counts(bba_handle h, int* ba_iteration_count, in
 bba_status bba_set_ba_iteration_counts(bba_handle h, int ba_iteration_count, int last_ba_iteration_count);
 
 /* In-loop surfel lifecycle (do_surfel_updates = 1 runs these inside bba_bundle_adjust on the reference's schedule,
- * direct_ba_alternating.cc:399-430,489-541, direct_ba.cc:577-601; single GPU in this version).
+ * direct_ba_alternating.cc:399-430,489-541, direct_ba.cc:577-601; with several ranks they run replicated -- they are deterministic).
  *  bba_create_surfels_for_keyframe: DirectBA::CreateSurfelsForKeyframe (direct_ba.h:114-117, direct_ba.cc:340-405): one new
  *    surfel per sparse cell of the keyframe that no existing surfel is associated with, optionally filtered by the
  *    observations / free-space violations in the co-visible keyframes, appended in raster order; surfels_size grows.
@@ -259,10 +259,13 @@ bba_status bba_bundle_adjust(bba_handle h, const bba_ba_options* options, bba_ba
 
 /* ---- multi-GPU (one process per GPU; not present in the reference) ---- */
 /* Sharding (DESIGN.md "Multi-GPU"): keyframe images and the surfel buffer are replicated on every rank.
- *  - geometry step: rank r updates the surfels of its contiguous shard; ONE all-gather of the updated rows
- *    (x, y, z, normal, descriptor 1/2, active flag) per outer iteration makes every replica identical again;
- *  - pose step: the non-inactive keyframes are dealt round-robin to the ranks, each rank runs the Gauss-Newton
- *    loops of its keyframes locally, and ONE all-reduce (sum of disjoint slots, K x 17 floats) publishes the poses.
+ *  - geometry step: rank r updates the surfels of its shard (256-surfel granules dealt round-robin, see bba_shard_*); ONE
+ *    all-gather of the updated rows (x, y, z, normal, descriptor 1/2, active flag) per outer iteration -- or direct stores into
+ *    the peers' replicas, bba_peer_import -- makes every replica identical again;
+ *  - pose step: the non-inactive keyframes are dealt to the ranks (balanced by measured work), each rank runs the Gauss-Newton
+ *    loops of its keyframes locally, and ONE all-reduce (sum of disjoint slots, K x 17 floats) publishes the poses;
+ *  - intrinsics step and PCG products: summed over each rank's surfel shard, completed by one sum all-reduce;
+ *  - surfel creation / merging / compaction: replicated (deterministic); end tasks: statistics sharded, compaction replicated.
  * Registers the exchange callback; required before any hot-path call when world_size > 1. */
 bba_status bba_set_collective(bba_handle h, bba_collective_fn fn, void* user);
 /* Fused geometry exchange over NVLink peer memory (optional, <= 8 ranks on one node): every rank exports CUDA IPC handles
