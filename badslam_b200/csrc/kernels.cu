@@ -453,8 +453,9 @@ __global__ void __launch_bounds__(kPoseThreads, BBA_POSE_MIN_CTAS) PoseAccumulat
           }
         }
         if (STATS) {
-          n_inimg += __popc(__ballot_sync(0xffffffffu, st >= 1));
-          n_depthok += __popc(__ballot_sync(0xffffffffu, st >= 2));
+          // per-lane counts (one predicated add each), summed over the warp once per chunk below
+          n_inimg += st >= 1;
+          n_depthok += st >= 2;
         }
         const unsigned assoc_mask = __ballot_sync(0xffffffffu, st == 3);
         if (assoc_mask == 0) continue;
@@ -517,6 +518,10 @@ __global__ void __launch_bounds__(kPoseThreads, BBA_POSE_MIN_CTAS) PoseAccumulat
       if (touched) {
         const float total = WarpTransposeReduce(acc, lane);
         atomicAdd(args.acc + static_cast<size_t>(kf) * kPoseAccSize + AccSlot(lane), static_cast<double>(total));
+      }
+      if (STATS) {
+        n_inimg = __reduce_add_sync(0xffffffffu, n_inimg);
+        n_depthok = __reduce_add_sync(0xffffffffu, n_depthok);
       }
       if (STATS && lane == 0 && n_inimg) {
         atomicAdd(args.stage_counts + 2 * kf, static_cast<unsigned long long>(n_inimg));
