@@ -105,6 +105,13 @@ def test_create_surfels_for_keyframe_three_way(mods, name, filt):
     sc = _half_map(S, name)
     n0 = sc.num_surfels
     ba, ref, orc = DirectBA.from_scene(sc), R.RefDirectBA(sc), O.Oracle(sc)
+    # The reference's outcome for cell size > 1 depends on an atomicCAS race (kernel_create_surfels.cu:68): two more independent
+    # runs give its own spread.  Measured on B200 with five runs (profiles/r2/lifecycle_spread.log): the reference scatters by
+    # 0.1 - 1 % per keyframe, while a fixed tie-break rule is a DIFFERENT sample of the race, systematically: this backend's hashed
+    # order creates +0.1 ... +3.5 % (13 % for the last keyframe of the smallest scene) more surfels than the reference's mean --
+    # 4 to 13 of the reference's standard deviations.  So the reference's spread cannot be the bound; the bound is the measured
+    # offset with a margin, and the spread is printed next to it.
+    more = [R.RefDirectBA(sc) for _ in range(2)] if sc.cfg.cell > 1 else []
     K = sc.cfg.num_keyframes
     for k in range(K):
         c0 = ba.CreateSurfelsForKeyframe(None, filt, k)
@@ -114,8 +121,11 @@ def test_create_surfels_for_keyframe_three_way(mods, name, filt):
         if sc.cfg.cell == 1:
             assert c0 == c1, (k, c0, c1)
         else:
-            print(name, filt, "keyframe", k, "created (ours, reference):", c0, c1)
-            assert abs(c0 - c1) <= max(60, 0.25 * max(c0, c1)), (k, c0, c1)   # (different seed pixels: different coverage / filter outcome)
+            runs = [c1] + [r.create_surfels_for_keyframe(k, filt) for r in more]
+            mean = float(np.mean(runs))
+            print(name, filt, "keyframe", k, "created: ours", c0, "| reference runs", runs, f"relative offset {(c0 - mean) / mean:+.3f}")
+            assert max(runs) - min(runs) <= max(10, 0.03 * mean), (k, runs)          # the reference's own scatter
+            assert abs(c0 - mean) <= max(40, 0.16 * mean), (k, c0, runs)            # (different seed pixels: different coverage / filter outcome)
         assert ba.surfels_size() == orc.n
     n1 = ba.surfels_size()
     assert n1 > n0
@@ -155,14 +165,19 @@ def test_merge_surfels_three_way(mods, name):
     sc2.surfels = sc.surfels.copy()
     sc2.num_surfels = rows.shape[1]
     sc2.surfels[:8, :sc2.num_surfels] = rows
-    ba, ref, orc = DirectBA.from_scene(sc2), R.RefDirectBA(sc2), O.Oracle(sc2)
+    ba, ref, ref2, orc = DirectBA.from_scene(sc2), R.RefDirectBA(sc2), R.RefDirectBA(sc2), O.Oracle(sc2)
     total = [0, 0, 0]
+    total_ref2 = 0
     for k in range(K):
         d0, d1, d2 = ba.MergeSurfelsForKeyframe(k), ref.merge_surfels_for_keyframe(k), orc.merge_surfels_for_keyframe(k)
+        total_ref2 += ref2.merge_surfels_for_keyframe(k)
         assert d0 == d2, (k, d0, d2)
         total = [total[0] + d0, total[1] + d1, total[2] + d2]
-    print("merged (ours, reference, oracle):", total, "of", sc2.num_surfels)
-    assert total[0] > 0 and abs(total[0] - total[1]) <= max(5, 0.3 * total[1]), total
+    print("merged (ours, reference, second reference run, oracle):", total[0], total[1], total_ref2, total[2], "of", sc2.num_surfels)
+    # measured with five reference runs (profiles/r2/lifecycle_spread.log): the reference scatters by 0.3 - 0.7 %, this backend's
+    # fixed order merges 0.9 % / 4.3 % fewer surfels than its mean (tiny / small)
+    assert abs(total[1] - total_ref2) <= max(5, 0.03 * total[1]), (total[1], total_ref2)
+    assert total[0] > 0 and abs(total[0] - total[1]) <= max(5, 0.08 * total[1]), total
     a, c = ba.GetSurfelsHost(), orc.surfels[:8, :orc.n]
     assert np.array_equal(a[0].view(np.uint32) == 0x7fffffff, c[0].view(np.uint32) == 0x7fffffff)   # the same surfels are marked
     n_a = ba.CompactSurfels(total[0], True)
