@@ -124,7 +124,7 @@ def test_create_surfels_for_keyframe_three_way(mods, name, filt):
             runs = [c1] + [r.create_surfels_for_keyframe(k, filt) for r in more]
             mean = float(np.mean(runs))
             print(name, filt, "keyframe", k, "created: ours", c0, "| reference runs", runs, f"relative offset {(c0 - mean) / mean:+.3f}")
-            assert max(runs) - min(runs) <= max(10, 0.03 * mean), (k, runs)          # the reference's own scatter
+            assert max(runs) - min(runs) <= max(20, 0.06 * mean), (k, runs)          # the reference's own scatter (measured: <= 3 % range over five runs)
             assert abs(c0 - mean) <= max(40, 0.16 * mean), (k, c0, runs)            # (different seed pixels: different coverage / filter outcome)
         assert ba.surfels_size() == orc.n
     n1 = ba.surfels_size()
@@ -176,7 +176,7 @@ def test_merge_surfels_three_way(mods, name):
     print("merged (ours, reference, second reference run, oracle):", total[0], total[1], total_ref2, total[2], "of", sc2.num_surfels)
     # measured with five reference runs (profiles/r2/lifecycle_spread.log): the reference scatters by 0.3 - 0.7 %, this backend's
     # fixed order merges 0.9 % / 4.3 % fewer surfels than its mean (tiny / small)
-    assert abs(total[1] - total_ref2) <= max(5, 0.03 * total[1]), (total[1], total_ref2)
+    assert abs(total[1] - total_ref2) <= max(10, 0.05 * total[1]), (total[1], total_ref2)
     assert total[0] > 0 and abs(total[0] - total[1]) <= max(5, 0.08 * total[1]), total
     a, c = ba.GetSurfelsHost(), orc.surfels[:8, :orc.n]
     assert np.array_equal(a[0].view(np.uint32) == 0x7fffffff, c[0].view(np.uint32) == 0x7fffffff)   # the same surfels are marked
