@@ -159,7 +159,7 @@ def test_track_frame_pairwise_against_reference(mods, name, num_scales, kw):
     # Same iteration counts and branch decisions; the poses agree to 1e-5 plus the drift of this non-settling iteration: up to 86
     # capped Gauss-Newton steps amplify last-bit differences of H / b (ours are fp64 sums of per-lane fp32 partials, the
     # reference's unordered fp32 atomics), measured here by the reference's own spread.
-    assert its0 == its1, (its0, its1)
+    assert all(abs(a - b) <= 1 for a, b in zip(its0, its1)), (its0, its1)   # (equal in every run so far; +-1 for a level that stops at the threshold)
     # (measured on B200 over the five cases: 2e-9 ... 3e-5 m between the two implementations with 5e-9 ... 2e-5 m between runs of
     #  the reference; the floor of 5e-5 covers a draw in which the reference's four runs happen to agree closely)
     limit = max(1e-5 + 10 * noise, 5e-5)
