@@ -137,3 +137,80 @@ def test_keyframe_balancing_rule():
         assert np.array_equal(owner, np.arange(n) % world)
     lib.bba_balance_keyframes(cost.ctypes.data, n, 1, owner.ctypes.data)
     assert not owner.any()
+
+
+def _worker_round2(rank, world, port, n, K, out_dir):
+    """The exchange patterns added in round 2 (badba.cu BundleAdjustPCG / PerformEndTasks with world_size > 1), with the same
+    arithmetic on the host: (1) PCG products -- every rank sums over ITS surfels only, one fp32 sum all-reduce of the vector with the
+    rank's fp64 part of alpha_d appended as a (high, low) float pair; (2) end tasks -- the two result rows of a rank's shard through
+    the all-gather, the deleted count as two exactly representable floats through a sum all-reduce."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from badslam_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    idx, own = owners(lib, n, world)
+    mine = own == rank
+
+    # (1) unknown vector = [6 (K - 1) pose | 3 n surfel | 5 + P intrinsics]: a surfel's entries are produced by its owner only, pose
+    # and intrinsics entries are partial sums over the owner's surfels
+    P = 12
+    per_surfel_pose = rng.normal(size=(n, 6 * (K - 1))).astype(np.float32) * 1e-3    # contribution of surfel i to the pose entries
+    per_surfel_intr = rng.normal(size=(n, 5 + P)).astype(np.float32) * 1e-3
+    surfel_entries = rng.normal(size=(n, 3)).astype(np.float32)
+    per_surfel_alpha = rng.random(n)                                                 # fp64 contributions to p^T A p
+    g = np.zeros(6 * (K - 1) + 3 * n + 5 + P + 2, np.float32)
+    g[:6 * (K - 1)] = per_surfel_pose[mine].sum(0, dtype=np.float32)
+    g[6 * (K - 1) + 3 * np.nonzero(mine)[0][:, None] + np.arange(3)] = surfel_entries[mine]
+    g[6 * (K - 1) + 3 * n:-2] = per_surfel_intr[mine].sum(0, dtype=np.float32)
+    alpha_mine = float(per_surfel_alpha[mine].sum())
+    hi = np.float32(alpha_mine)
+    g[-2], g[-1] = hi, np.float32(alpha_mine - float(hi))                             # PcgPackAlphaDKernel
+    t = torch.from_numpy(g.copy())
+    dist.all_reduce(t)
+    got = t.numpy()
+    assert np.array_equal(got[6 * (K - 1):6 * (K - 1) + 3 * n].reshape(n, 3), surfel_entries)     # gather of disjoint entries: exact
+    assert np.allclose(got[:6 * (K - 1)], per_surfel_pose.sum(0, dtype=np.float64), rtol=0, atol=1e-5)
+    assert np.allclose(got[6 * (K - 1) + 3 * n:-2], per_surfel_intr.sum(0, dtype=np.float64), rtol=0, atol=1e-5)
+    alpha = float(got[-2]) + float(got[-1])                                           # PcgUnpackAlphaDKernel
+    assert abs(alpha - per_surfel_alpha.sum()) < 1e-6 * per_surfel_alpha.sum()        # (fp32 alone would be off by ~1e-4 relative here)
+    # every rank holds the same bits afterwards: hash all-gathered
+    digest = torch.tensor(list(got.tobytes()[:64]) + [int(got.view(np.uint32).sum() % 251)], dtype=torch.int64)
+    both = [torch.empty_like(digest) for _ in range(world)]
+    dist.all_gather(both, digest)
+    assert all(torch.equal(b, both[0]) for b in both)
+
+    # (2) end tasks: rows x (deletion marker) and radius^2 of the shard, deleted count split into (low 12 bits, rest)
+    rows = rng.normal(size=(2, n)).astype(np.float32)
+    new_rows = rows.copy()
+    deleted = rng.random(n) < 0.1
+    new_rows[0, deleted] = np.uint32(0x7fffffff).view(np.float32)
+    new_rows[1, ~deleted] = rng.random((~deleted).sum()).astype(np.float32)
+    loc = np.array([lib.bba_shard_surfel_local_index(int(i), world) for i in idx], np.int64)
+    shard_len = lib.bba_shard_slice_length(n, world)
+    buf = torch.zeros(world * 2 * shard_len)
+    local = rows.copy()
+    local[:, mine] = new_rows[:, mine]
+    buf.view(world, 2, shard_len)[rank][:, torch.from_numpy(loc[mine])] = torch.from_numpy(local[:, mine])
+    dist.all_gather_into_tensor(buf, buf.view(world, -1)[rank].clone())
+    merged = local.copy()
+    for r in range(world):
+        if r != rank:
+            theirs = own == r
+            merged[:, theirs] = buf.view(world, 2, shard_len)[r][:, torch.from_numpy(loc[theirs])].numpy()
+    assert np.array_equal(merged.view(np.uint32), new_rows.view(np.uint32))
+    count_mine = int(deleted[mine].sum()) + (1 << 22) * 3                              # (made large: past fp32's 2^24 when summed naively)
+    pair = torch.tensor([float(count_mine & 0xfff), float(count_mine >> 12)])
+    dist.all_reduce(pair)
+    total = int(pair[0].item() + 0.5) + (int(pair[1].item() + 0.5) << 12)
+    assert total == int(deleted.sum()) + world * (1 << 22) * 3
+    open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 1000), (4, 3000)])
+def test_round2_exchange_patterns_gloo(tmp_path, world, n):
+    port = _free_port()
+    mp.spawn(_worker_round2, args=(world, port, n, 5, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))
