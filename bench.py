@@ -548,6 +548,23 @@ def run_reference(args, scene):
                          "BA_pose_optimization": stage[2] / args.steps}}
 
 
+def load_scene(workload, rank, world, wait_seconds=1800):
+    """The seeded scene of `workload`.  With one process per GPU, rank 0 generates it once and the other ranks load its pickle
+    (BADBA_SCENE_CACHE, a per-job directory under /tmp unless set) instead of every rank spending a host-core-minute on the same
+    numpy work; a rank that waited in vain generates the scene itself (it is deterministic)."""
+    from badslam_b200.scene import config_by_name, make_scene, scene_cache_path
+    cfg = config_by_name(workload)
+    if world > 1:
+        cache = os.environ.setdefault("BADBA_SCENE_CACHE", os.path.join(
+            "/tmp", f"badba_scenes_{os.environ.get('MASTER_PORT', '0')}_{os.environ.get('TORCHELASTIC_RUN_ID', 'run')}"))
+        path = scene_cache_path(cfg, cache)
+        if rank != 0:
+            t_wait = time.time()
+            while not os.path.exists(path) and time.time() - t_wait < wait_seconds:
+                time.sleep(0.2)
+    return make_scene(cfg)
+
+
 def main():
     # Exactly one JSON line may reach stdout: route everything libraries print there (e.g. NCCL's version banner)
     # to stderr while the benchmark runs.
@@ -584,18 +601,7 @@ def _main(saved_stdout):
     from badslam_b200.scene import config_by_name, make_scene
     if args.impl == "reference" and rank != 0:
         return 0
-    if world > 1:
-        # one process per GPU: rank 0 generates the (seeded, identical) scene once and the other ranks load its pickle, instead of
-        # every rank spending a host-core-minute on the same numpy work
-        from badslam_b200.scene import scene_cache_path
-        cache = os.environ.setdefault("BADBA_SCENE_CACHE", os.path.join(
-            "/tmp", f"badba_scenes_{os.environ.get('MASTER_PORT', '0')}_{os.environ.get('TORCHELASTIC_RUN_ID', 'run')}"))
-        path = scene_cache_path(config_by_name(args.workload), cache)
-        if rank != 0:
-            t_wait = time.time()
-            while not os.path.exists(path) and time.time() - t_wait < 1800:
-                time.sleep(0.2)
-    scene = make_scene(config_by_name(args.workload))
+    scene = load_scene(args.workload, rank, world)
     if args.impl == "reference":
         out = run_reference(args, scene)
     else:
