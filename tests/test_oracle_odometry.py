@@ -181,3 +181,28 @@ def test_oracle_matches_reference_golden(pair, tag, gm):
         noise = max(S.pose_error(g["est"], g["est_rerun"]))
         dt, dr = S.pose_error(est, g["est"])
         assert dt < 1e-3 + 3 * noise and dr < 1e-3 + 3 * noise, (dt, dr, noise)
+
+
+def test_edge_cases_empty_and_identical_frames(pair):
+    """No usable pixel at all -> no residuals, zero normal equations, the estimate stays where it was (the reference's LDLT of a
+    zero matrix yields a zero update, which counts as converged: one iteration per level).  Tracking a keyframe against ITSELF
+    starts and stays at the identity."""
+    sc, true_rel, frame = pair
+    depth, normals, color = frame
+    empty = (np.full_like(depth, 65535), np.zeros_like(normals), color)
+    od = make(sc, empty)
+    for s in range(od.num_scales):
+        H, b, cnt, total = od.coeffs(s, IDENT)
+        assert cnt == 0 and total == 0.0 and not np.any(H) and not np.any(b)
+        assert od.cost(s, IDENT) == (0, 0.0)
+    start = S.se3_exp([0.01, 0.0, -0.01, 0.0, 0.002, 0.0])
+    est, iterations, chose = od.track(start, start)
+    assert np.allclose(est, start, atol=1e-7) and iterations == [1, 1, 1]
+    same = make(sc, (sc.depth[0], sc.normals[0], sc.color[0]))
+    est, iterations, _ = same.track(IDENT, IDENT)
+    dt, dr = S.pose_error(est, IDENT)
+    assert dt < 2e-4 and dr < 2e-4, (dt, dr)
+    # at the identity every valid interior pixel of the keyframe is associated with itself
+    H, b, cnt, total = same.coeffs(0, IDENT)
+    d0 = same.levels[0]["base"][0]
+    assert cnt >= 2 * 0.9 * (d0[:-1, :-1] > 0).sum()
