@@ -151,7 +151,11 @@ def cpu_port_baseline(scene, max_kf=20, max_surfels=200_000, repeats=3):
     sub.poses_init, sub.poses_true = scene.poses_init[:K], scene.poses_true[:K]
     sub.min_depth, sub.max_depth = scene.min_depth[:K], scene.max_depth[:K]
     sub.num_surfels = n
-    cores = cpu_oracle.lib().orc_get_max_threads()
+    # threads = what the OpenMP runtime would use, but never more than the CPUs this process may run on (a shared box hands a job
+    # a couple of cores while OMP_NUM_THREADS / the core count say 64: the baseline would then time 64 threads taking turns)
+    lib_ = cpu_oracle.lib()
+    cores = max(1, min(int(lib_.orc_get_max_threads()), len(os.sched_getaffinity(0))))
+    lib_.orc_set_num_threads(cores)
     times = []
     for _ in range(repeats):   # best of `repeats` (a shared host: single runs varied 3x in round 1); threads pinned via OMP_PROC_BIND
         orc = cpu_oracle.Oracle(sub)
