@@ -100,7 +100,7 @@ def _worker(rank, world, port, n, K, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n", [(2, 1000), (4, 5000)])
+@pytest.mark.parametrize("world,n", [(2, 1000), (4, 5000), (8, 9001)])
 def test_exchange_patterns_gloo(tmp_path, world, n):
     """One process per rank over gloo: the surfel-granule all-gather and the keyframe-slot all-reduce reassemble the same state on
     every rank (world 2, and world 4 with surfel counts that leave ranks with uneven granule counts)."""
@@ -209,7 +209,7 @@ def _worker_round2(rank, world, port, n, K, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n", [(2, 1000), (4, 3000)])
+@pytest.mark.parametrize("world,n", [(2, 1000), (4, 3000), (8, 7001)])
 def test_round2_exchange_patterns_gloo(tmp_path, world, n):
     port = _free_port()
     mp.spawn(_worker_round2, args=(world, port, n, 5, str(tmp_path)), nprocs=world, join=True)
