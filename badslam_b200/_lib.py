@@ -68,6 +68,10 @@ class OdometryResult(C.Structure):
                 ("residual_sum", C.c_float), ("passes", C.c_uint32), ("kernel_launches", C.c_uint32)]
 
 
+class MotionModelRecord(C.Structure):
+    _fields_ = [("count", C.c_int), ("base_kf_tr_frame", (C.c_float * 7) * 3), ("frame_tr_base_kf", (C.c_float * 7) * 3)]
+
+
 class PeerHandle(C.Structure):
     _fields_ = [("surfels_ipc", C.c_ubyte * 64), ("surfels_offset", C.c_uint64), ("active_ipc", C.c_ubyte * 64),
                 ("active_offset", C.c_uint64), ("pitch_bytes", C.c_uint64), ("surfels_size", C.c_uint32), ("rank", C.c_int32)]
@@ -125,6 +129,10 @@ SYMBOLS = {
     "bba_host_pose_update_converged": (C.c_int, [_P]),
     "bba_host_solve_ldlt": (C.c_int, [C.c_int, _P, _P, _P]),
     "bba_host_frusta_intersect": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_float, C.c_float, _P, C.c_float, C.c_float]),
+    "bba_host_motion_model_clear": (None, [C.POINTER(MotionModelRecord), _P, _P]),
+    "bba_host_motion_model_predict": (C.c_int, [C.POINTER(MotionModelRecord), C.c_int, _P, _P]),
+    "bba_host_motion_model_push": (None, [C.POINTER(MotionModelRecord), _P]),
+    "bba_host_motion_model_rebase": (None, [C.POINTER(MotionModelRecord)]),
     "bba_set_residual_types": (C.c_int, [_P, C.c_int, C.c_int]),
     "bba_get_residual_types": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "bba_set_cfactor_host": (C.c_int, [_P, _P, _P]),
@@ -186,7 +194,7 @@ def load():
         fn = getattr(lib, name)   # AttributeError if the symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.bba_abi_version() != 7:
+    if lib.bba_abi_version() != 8:
         raise ImportError("libbadba_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -1910,6 +1910,83 @@ int bba_host_frusta_intersect(const float depth_intrinsics[4], int width, int he
   return FrustaIntersect(a, b) ? 1 : 0;
 }
 
+// Constant-motion model of the odometry front end.  The stored transforms and their inverses are two lists that are updated side
+// by side (never re-derived from each other), like base_kf_tr_frame_ / frame_tr_base_kf_ of the reference; products associate
+// left to right like its `a * b * c`.
+namespace {
+const float kIdentityPose[7] = {0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f};
+void CopyPose(const float* src, float* dst) { for (int i = 0; i < 7; ++i) dst[i] = src[i]; }
+}  // namespace
+
+void bba_host_motion_model_clear(bba_motion_model* m, const float last_kf_frame_T_global[7], const float global_T_frame[7]) {   // bad_slam.cc:542-565
+  if (!m) return;
+  m->count = 1;
+  if (!last_kf_frame_T_global || !global_T_frame) {
+    CopyPose(kIdentityPose, m->base_kf_tr_frame[0]);
+    CopyPose(kIdentityPose, m->frame_tr_base_kf[0]);
+    return;
+  }
+  const Pose rel = bba::Compose(PoseFromArray(last_kf_frame_T_global), PoseFromArray(global_T_frame));
+  PoseToArray(rel, m->base_kf_tr_frame[0]);
+  PoseToArray(bba::Inverse(rel), m->frame_tr_base_kf[0]);
+}
+
+int bba_host_motion_model_predict(const bba_motion_model* m, int use_motion_model, float e1[7], float e2[7]) {   // bad_slam.cc:767-827
+  if (!m || !e1 || !e2 || m->count < 1 || m->count > 3) return 0;
+  const int n = m->count;
+  const Pose last = PoseFromArray(m->base_kf_tr_frame[n - 1]);
+  if (!use_motion_model) {
+    PoseToArray(last, e1);
+    PoseToArray(last, e2);
+    return 1;
+  }
+  // the motion of the last step applied once more
+  Pose first = last;
+  if (n >= 2) first = bba::Compose(bba::Compose(last, PoseFromArray(m->frame_tr_base_kf[n - 2])), last);
+  PoseToArray(first, e1);
+  // the motion of the step before, applied twice to the frame before the last: an outlier in the last frame does not enter
+  if (n >= 3) {
+    const Pose step = bba::Compose(PoseFromArray(m->frame_tr_base_kf[n - 3]), PoseFromArray(m->base_kf_tr_frame[n - 2]));
+    PoseToArray(bba::Compose(bba::Compose(PoseFromArray(m->base_kf_tr_frame[n - 2]), step), step), e2);
+  } else {
+    PoseToArray(first, e2);
+  }
+  return 1;
+}
+
+void bba_host_motion_model_push(bba_motion_model* m, const float estimate[7]) {   // bad_slam.cc:949-954
+  if (!m || !estimate) return;
+  if (m->count < 0 || m->count > 3) m->count = 0;
+  if (m->count == 3) {
+    for (int i = 0; i < 2; ++i) {
+      CopyPose(m->base_kf_tr_frame[i + 1], m->base_kf_tr_frame[i]);
+      CopyPose(m->frame_tr_base_kf[i + 1], m->frame_tr_base_kf[i]);
+    }
+    m->count = 2;
+  }
+  CopyPose(estimate, m->base_kf_tr_frame[m->count]);
+  PoseToArray(bba::Inverse(PoseFromArray(estimate)), m->frame_tr_base_kf[m->count]);
+  ++m->count;
+}
+
+void bba_host_motion_model_rebase(bba_motion_model* m) {   // bad_slam.cc:1057-1068
+  if (!m) return;
+  if (m->count < 0 || m->count > 3) m->count = 0;
+  const int n = m->count;
+  if (n == 0) {
+    m->count = 1;
+  } else {
+    const Pose last = PoseFromArray(m->base_kf_tr_frame[n - 1]);
+    const Pose last_inv = PoseFromArray(m->frame_tr_base_kf[n - 1]);
+    for (int i = 0; i + 1 < n; ++i) {
+      PoseToArray(bba::Compose(PoseFromArray(m->frame_tr_base_kf[i]), last), m->frame_tr_base_kf[i]);
+      PoseToArray(bba::Compose(last_inv, PoseFromArray(m->base_kf_tr_frame[i])), m->base_kf_tr_frame[i]);
+    }
+  }
+  CopyPose(kIdentityPose, m->base_kf_tr_frame[m->count - 1]);
+  CopyPose(kIdentityPose, m->frame_tr_base_kf[m->count - 1]);
+}
+
 int bba_keyframe_count(bba_handle h) { return h ? static_cast<int>(h->keyframes.size()) : 0; }
 
 #define CHECK_KF(h, id)                                                                   \

@@ -102,6 +102,51 @@ class BAResult:
         return self.depth_residual_count + self.descriptor_residual_count
 
 
+class MotionModel:
+    """The constant-motion model BadSlam keeps in front of TrackFramePairwise (base_kf_tr_frame_ / frame_tr_base_kf_,
+    bad_slam.cc:542-565, 767-827, 949-954, 1057-1068), on the library's host functions.  One tracked frame of RunOdometry:
+
+        e1, e2 = mm.PredictFramePose()
+        estimate, _ = ba.TrackFramePairwise(stream, base_kf_id, depth, normals, color, e1, e2)
+        mm.Push(estimate)
+
+    and mm.Rebase() after a keyframe was created from the frame tracked last."""
+
+    def __init__(self, use_motion_model: bool = True):
+        self._lib = _lib.load()
+        self._m = _lib.MotionModelRecord()
+        self.use_motion_model = bool(use_motion_model)
+        self.Clear()
+
+    def Clear(self, last_kf_frame_T_global=None, global_T_frame=None):
+        """BadSlam::ClearMotionModel: restart from the frame's pose relative to the last keyframe (identity without arguments)."""
+        a = None if last_kf_frame_T_global is None else np.ascontiguousarray(last_kf_frame_T_global, np.float32)
+        b = None if global_T_frame is None else np.ascontiguousarray(global_T_frame, np.float32)
+        self._lib.bba_host_motion_model_clear(C.byref(self._m), None if a is None else a.ctypes.data, None if b is None else b.ctypes.data)
+
+    def PredictFramePose(self):
+        """BadSlam::PredictFramePose -> (base_kf_tr_frame_initial_estimate, base_kf_tr_frame_initial_estimate_2)."""
+        e1, e2 = np.zeros(7, np.float32), np.zeros(7, np.float32)
+        if not self._lib.bba_host_motion_model_predict(C.byref(self._m), int(self.use_motion_model), e1.ctypes.data, e2.ctypes.data):
+            raise BadBAError(1, "motion model holds no estimate")
+        return e1, e2
+
+    def Push(self, base_T_frame_estimate):
+        e = np.ascontiguousarray(base_T_frame_estimate, np.float32)
+        self._lib.bba_host_motion_model_push(C.byref(self._m), e.ctypes.data)
+
+    def Rebase(self):
+        self._lib.bba_host_motion_model_rebase(C.byref(self._m))
+
+    @property
+    def base_kf_tr_frame(self):
+        return np.array([list(self._m.base_kf_tr_frame[i]) for i in range(self._m.count)], np.float32).reshape(-1, 7)
+
+    @property
+    def frame_tr_base_kf(self):
+        return np.array([list(self._m.frame_tr_base_kf[i]) for i in range(self._m.count)], np.float32).reshape(-1, 7)
+
+
 class DirectBA:
     """Drop-in for vis::DirectBA (direct_ba.h:65-550) backed by the sm_100a library."""
 

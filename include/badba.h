@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BBA_ABI_VERSION 7
+#define BBA_ABI_VERSION 8
 
 typedef struct bba_context* bba_handle;
 
@@ -402,6 +402,29 @@ int  bba_host_solve_ldlt(int n, const double* upper, const double* b, double* x)
 int  bba_host_frusta_intersect(const float depth_intrinsics[4], int width, int height,
                                const float global_T_frame_a[7], float min_depth_a, float max_depth_a,
                                const float global_T_frame_b[7], float min_depth_b, float max_depth_b);
+
+/* The constant-motion model in front of the image-pair odometry (BadSlam::PredictFramePose / RunOdometry / ClearMotionModel /
+ * the rebase in BadSlam::ProcessFrame when a keyframe is created: bad_slam.cc:542-565, 767-827, 949-954, 1057-1068).  Host
+ * arithmetic on at most three stored estimates of base_kf_tr_frame and, kept separately as in the reference, their inverses;
+ * the caller owns the record.  One tracked frame of BadSlam::RunOdometry is
+ *     bba_host_motion_model_predict(&m, use_motion_model, e1, e2);
+ *     bba_track_frame_pairwise(..., e1, e2, estimate, ...);
+ *     bba_host_motion_model_push(&m, estimate);
+ * and bba_host_motion_model_rebase(&m) follows the creation of a keyframe from the frame tracked last. */
+typedef struct {
+  int   count;                       /* stored estimates, 0..3 (oldest first) */
+  float base_kf_tr_frame[3][7];
+  float frame_tr_base_kf[3][7];
+} bba_motion_model;
+/* ClearMotionModel: one stored estimate = last_kf_frame_T_global * global_T_frame, or identity if there is no keyframe yet
+ * (last_kf_frame_T_global == NULL). */
+void bba_host_motion_model_clear(bba_motion_model* m, const float last_kf_frame_T_global[7], const float global_T_frame[7]);
+/* PredictFramePose: the two initial estimates TrackFramePairwise tries.  Returns 0 (and writes nothing) if m holds no estimate. */
+int  bba_host_motion_model_predict(const bba_motion_model* m, int use_motion_model, float out_estimate_1[7], float out_estimate_2[7]);
+/* The tail of RunOdometry: drop the oldest of three, append the new estimate and its inverse. */
+void bba_host_motion_model_push(bba_motion_model* m, const float base_T_frame_estimate[7]);
+/* A keyframe was created from the frame tracked last: re-express the older estimates relative to it; the last becomes identity. */
+void bba_host_motion_model_rebase(bba_motion_model* m);
 
 /* ---- instrumentation ---- */
 uint64_t   bba_kernel_launch_count(bba_handle h);   /* kernels launched through this handle so far */

@@ -333,4 +333,35 @@ inline bool LoadCalibration(cudaStream_t stream, bba_handle h, const std::string
   return bba_set_intrinsics(h, cams[0], cams[1], a) == BBA_OK && bba_set_cfactor_host(h, cf.data(), stream) == BBA_OK;   // synchronises
 }
 
+// The motion model BadSlam keeps in front of TrackFramePairwise (members base_kf_tr_frame_ / frame_tr_base_kf_, bad_slam.h:346-347),
+// with the reference's method names.  RunOdometry (bad_slam.cc:829-955) becomes
+//   motion_model.PredictFramePose(&e1, &e2);  direct_ba.TrackFramePairwise(..., e1, e2, &estimate);  motion_model.Push(estimate);
+// and ProcessFrame calls motion_model.Rebase() where it re-expresses the lists after creating a keyframe (bad_slam.cc:1057-1068).
+template <typename SE3f>
+class MotionModel {
+ public:
+  explicit MotionModel(bool use_motion_model = true) : use_motion_model_(use_motion_model) { bba_host_motion_model_clear(&m_, nullptr, nullptr); }
+
+  // BadSlam::ClearMotionModel (bad_slam.cc:542-565); last_kf_frame_T_global == nullptr: no keyframe yet
+  void ClearMotionModel(const SE3f* last_kf_frame_T_global, const SE3f* global_T_frame) {
+    bba_host_motion_model_clear(&m_, last_kf_frame_T_global ? last_kf_frame_T_global->data() : nullptr,
+                                global_T_frame ? global_T_frame->data() : nullptr);
+  }
+  // BadSlam::PredictFramePose (bad_slam.cc:767-827)
+  void PredictFramePose(SE3f* base_kf_tr_frame_initial_estimate, SE3f* base_kf_tr_frame_initial_estimate_2) const {
+    float e1[7], e2[7];
+    if (!bba_host_motion_model_predict(&m_, use_motion_model_, e1, e2)) throw Error(BBA_ERR_INVALID_ARGUMENT, "motion model holds no estimate");
+    std::memcpy(base_kf_tr_frame_initial_estimate->data(), e1, sizeof(e1));
+    std::memcpy(base_kf_tr_frame_initial_estimate_2->data(), e2, sizeof(e2));
+  }
+  void Push(const SE3f& base_T_frame_estimate) { bba_host_motion_model_push(&m_, base_T_frame_estimate.data()); }
+  void Rebase() { bba_host_motion_model_rebase(&m_); }
+  int stored_frames() const { return m_.count; }
+  const bba_motion_model& record() const { return m_; }
+
+ private:
+  bba_motion_model m_{};
+  bool use_motion_model_;
+};
+
 }  // namespace badba

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/badba.h but not exported"
     # and the python binding types every one of them
     assert set(declared_symbols()) == set(_lib.SYMBOLS.keys())
-    assert _lib.load().bba_abi_version() == 7
+    assert _lib.load().bba_abi_version() == 8
 
 
 def test_no_cpu_fallback_without_a_device():
